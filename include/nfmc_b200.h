@@ -1,0 +1,157 @@
+/*
+ * nfmc_b200.h -- C ABI of libnfmc_b200.so: the B200 (sm_100a) implementation of nfmc's batched
+ * per-iteration hot path (jump_mala / jump_hmc / neutra_hmc / imh + RealNVP).
+ *
+ * The reference (davidnabergoj/nfmc) is pure Python and has no FFI; the seams this library sits behind are
+ * the duck-typed operator contracts listed next to each entry point (paths under /root/reference/nfmc/).
+ * A maintainer binds these with ctypes; nfmc_b200/_native.py is that binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; tensors are fp32, row-major
+ *     [n, d] with d = prod(event_shape); no ownership is transferred; nothing is allocated by the library
+ *     except inside the *_host entry points.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); work is enqueued, never
+ *     synchronised, except in *_host entry points which synchronise before returning.
+ *   - return value: 0 on success, nonzero on error; nfmc_last_error() gives the message (thread-local).
+ *   - chains are keyed by GLOBAL index `chain0 + row`, so a chain's random stream does not depend on how
+ *     the batch is sharded over GPUs.
+ */
+#ifndef NFMC_B200_H
+#define NFMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NFMC_ABI_VERSION 1
+#if defined(__GNUC__)
+#define NFMC_API __attribute__((visibility("default")))
+#else
+#define NFMC_API
+#endif
+#define NFMC_MAX_DIM 1024
+
+/* ---- analytic target potentials (negative log densities) -------------------------------------------- */
+enum nfmc_potential_kind {
+  NFMC_POT_ISO_GAUSSIAN = 0, /* U = 1/2 w sum x_i^2;  scalar[0] = w  (w = 2: README.md:45-46 `sum(x**2)`)  */
+  NFMC_POT_DIAG_GAUSSIAN = 1,/* U = 1/2 sum w_i (x_i - mu_i)^2;  params = float2[d] {w_i, mu_i}            */
+  NFMC_POT_FUNNEL = 2,       /* U = x0^2/(2 s^2) + (d-1)/2 x0 + 1/2 exp(-x0) sum_{i>=1} x_i^2; scalar[0]=s (3) */
+  NFMC_POT_ROSENBROCK = 3,   /* U = sum_{k<d/2} (x_k - 1)^2 + c (x_{k+d/2} - x_k^2)^2;  scalar[0] = c (10)  */
+  NFMC_POT_MIXTURE4 = 4      /* U = -logsumexp_k(-1/2 |x - mu_k|^2), mu_k = (+-a, +-a, 0, ...); scalar[0]=a */
+};
+
+typedef struct nfmc_potential {
+  int32_t kind;        /* nfmc_potential_kind */
+  int32_t d;
+  const float* params; /* device, per-dimension parameters or NULL */
+  float scalar[4];
+} nfmc_potential;
+
+/* ---- packed RealNVP (replaces torchflows.RealNVP; call sites sampling/base.py:26, util.py:280-281) ---- */
+/* blob layout: see DESIGN.md "flow blob"; produced by nfmc_b200.flow.pack_realnvp() or nfmc_realnvp_blob_floats */
+typedef struct nfmc_realnvp {
+  int32_t d;          /* event size */
+  int32_t n_coupling; /* Lc */
+  int32_t n_linear;   /* M: linear layers per conditioner (>= 1) */
+  int32_t hidden;     /* H */
+  const float* blob;  /* device */
+  int64_t blob_floats;
+} nfmc_realnvp;
+
+/* ---- random numbers: counter-based Philox4x32-10, or injected tensors ----------------------------------- */
+typedef struct nfmc_rng {
+  uint64_t seed;
+  uint64_t step0;        /* global index of the first step of this launch (advance by the steps taken) */
+  const float* normals;  /* optional injected N(0,1): [steps, n, d]  (NULL -> Philox) */
+  const float* uniforms; /* optional injected U[0,1): [steps, n]     (NULL -> Philox) */
+} nfmc_rng;
+
+/* ---- statistics accumulated on the device (replaces MCMCExpectation.update, sampling/base.py:75-95, and
+ *      MCMCStatistics.update_counters, sampling/base.py:139-149) ------------------------------------------ */
+typedef struct nfmc_stats {
+  double* sum_x;              /* [d]  += sum over (step, chain) of x after the accept          (or NULL) */
+  double* sum_x2;             /* [d]  += sum of x^2                                              (or NULL) */
+  unsigned long long* counts; /* [4]: [0] += accepted, [1] += attempted, [2] += non-finite log-ratios, [3] spare */
+} nfmc_stats;
+
+/* optional sample sink (MCMCSamples.add, sampling/base.py:234-263): rows written for steps whose global
+ * index (seen0 + k) is divisible by `thinning`; row r of the launch goes to samples[r, :, :] */
+typedef struct nfmc_sink {
+  float* samples;   /* [rows, n, d] or NULL */
+  int64_t seen0;
+  int32_t thinning; /* >= 1 */
+} nfmc_sink;
+
+NFMC_API const char* nfmc_last_error(void);
+NFMC_API int nfmc_abi_version(void);
+
+/* lanes-per-chain / slots-per-lane layout chosen for event size d (defines the Philox noise layout) */
+NFMC_API int nfmc_layout_for_dim(int32_t d, int32_t* lanes_per_chain, int32_t* slots_per_half);
+/* number of floats of the packed blob for (d, Lc, M, H) */
+NFMC_API int64_t nfmc_realnvp_blob_floats(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden);
+
+/* U(x) [n] and optionally grad U(x) [n,d]  -- replaces `target(x)` + autograd (langevin.py:66-68, hmc.py:40-48) */
+NFMC_API int nfmc_potential_eval(const nfmc_potential* pot, const float* x, float* u, float* grad, int64_t n, void* stream);
+
+/* RealNVP bijection.forward / bijection.inverse (neutra.py:60,122): y [n,d], log_det [n] */
+NFMC_API int nfmc_realnvp_forward(const nfmc_realnvp* flow, const float* x, float* z, float* log_det, int64_t n, void* stream);
+NFMC_API int nfmc_realnvp_inverse(const nfmc_realnvp* flow, const float* z, float* x, float* log_det, int64_t n, void* stream);
+/* Flow.log_prob (jump.py:218, imh.py:133-134,214) */
+NFMC_API int nfmc_flow_log_prob(const nfmc_realnvp* flow, const float* x, float* log_q, int64_t n, void* stream);
+/* Flow.sample(n, return_log_prob=True) (jump.py:205, imh.py:221): base draw from rng (stream id 1) */
+NFMC_API int nfmc_flow_sample(const nfmc_realnvp* flow, const nfmc_rng* rng, int64_t chain0, float* x, float* log_q,
+                     int64_t n, void* stream);
+
+/* K Langevin steps for all chains -- Langevin.propose (mcmc/langevin.py:61-122) inside the local loop
+ * MCMCSampler.sample (mcmc/base.py:69-99).  inv_mass_diag may be NULL (= ones).  adjusted=0 -> ULA. */
+NFMC_API int nfmc_mala_steps(const nfmc_potential* pot, float* x, int64_t n, int32_t n_steps, float step_size,
+                    const float* inv_mass_diag, int32_t adjusted, const nfmc_rng* rng, int64_t chain0,
+                    const nfmc_stats* stats, const nfmc_sink* sink, void* stream);
+
+/* K HMC steps -- HMC.propose (mcmc/hmc.py:96-126; trajectory :61-77) inside the same local loop */
+NFMC_API int nfmc_hmc_steps(const nfmc_potential* pot, float* x, int64_t n, int32_t n_steps, float step_size,
+                   int32_t n_leapfrog, const float* inv_mass_diag, int32_t adjusted, const nfmc_rng* rng,
+                   int64_t chain0, const nfmc_stats* stats, const nfmc_sink* sink, void* stream);
+
+/* one NF jump for all chains -- JumpNFMC.sample jump block (nfmc/jump.py:203-243); counts[0]/[1] receive
+ * accepted / attempted JUMPS */
+NFMC_API int nfmc_jump_step(const nfmc_potential* pot, const nfmc_realnvp* flow, float* x, int64_t n, int32_t adjusted,
+                   const nfmc_rng* rng, int64_t chain0, const nfmc_stats* stats, const nfmc_sink* sink, void* stream);
+
+/* T independence-MH iterations -- FixedIMH.sample (nfmc/imh.py:214-249).  log_q_x [n] is the cached
+ * flow.log_prob(x) (imh.py:214), updated in place; pass recompute_logq=1 for AdaptiveIMH (imh.py:133-134) */
+NFMC_API int nfmc_imh_steps(const nfmc_potential* pot, const nfmc_realnvp* flow, float* x, float* log_q_x, int64_t n,
+                   int32_t n_steps, int32_t recompute_logq, const nfmc_rng* rng, int64_t chain0,
+                   const nfmc_stats* stats, const nfmc_sink* sink, void* stream);
+
+/* T NeuTra-HMC iterations in latent space -- NeuTra.adjusted_target (nfmc/neutra.py:58-68) under HMC.propose */
+NFMC_API int nfmc_neutra_hmc_steps(const nfmc_potential* pot, const nfmc_realnvp* flow, float* z, int64_t n, int32_t n_steps,
+                          float step_size, int32_t n_leapfrog, const float* inv_mass_diag, const nfmc_rng* rng,
+                          int64_t chain0, const nfmc_stats* stats, const nfmc_sink* sink, void* stream);
+/* latent potential and its gradient (for tests): u [n], grad [n,d] (grad may be NULL) */
+NFMC_API int nfmc_neutra_potential(const nfmc_potential* pot, const nfmc_realnvp* flow, const float* z, float* u, float* grad,
+                          int64_t n, void* stream);
+
+/* the numbers the Philox path would draw (for parity tests): normals [steps, n, d], uniforms [steps, n];
+ * stream_id 0 = local kernels, 1 = flow base draw */
+NFMC_API int nfmc_rng_fill(const nfmc_rng* rng, int32_t stream_id, int64_t chain0, int32_t d, int64_t n, int32_t n_steps,
+                  float* normals, float* uniforms, void* stream);
+
+/* ---- host-buffer entry point (end-to-end measurement; the call a reference-side plugin would make) ------
+ * Runs `n_outer` iterations of [n_inner local steps (kind 0 = MALA, 1 = HMC) + one NF jump] on host data:
+ * copies x_host [n,d] to the device, runs, copies the final state back into x_host, and returns the pooled
+ * moments (sum_x_host/sum_x2_host [d], doubles) and counters (counts_host[4] local, counts_host[4..8) jump).
+ * Device buffers are taken from `workspace` (>= nfmc_jump_workspace_bytes bytes of device memory). */
+NFMC_API int64_t nfmc_jump_workspace_bytes(int32_t d, int64_t n, int64_t blob_floats);
+NFMC_API int nfmc_jump_sample_host(const nfmc_potential* pot_host_desc, const float* pot_params_host, int64_t pot_params_floats,
+                          const nfmc_realnvp* flow_host_desc, const float* blob_host, float* x_host, int64_t n,
+                          int32_t inner_kind, int32_t n_outer, int32_t n_inner, float step_size, int32_t n_leapfrog,
+                          uint64_t seed, int64_t chain0, double* sum_x_host, double* sum_x2_host,
+                          unsigned long long* counts_host, void* workspace, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFMC_B200_H */

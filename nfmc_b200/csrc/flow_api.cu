@@ -1,0 +1,135 @@
+// flow_api.cu -- C-ABI entry points of the flow / jump / IMH / NeuTra kernels (dispatch over E).
+#include "launchers.cuh"
+
+using namespace nfmc;
+
+
+static int flow_pass(const nfmc_realnvp* flow, int mode, const float* in, float* out, float* aux, int64_t n, void* stream) {
+  if (int e = validate_flow(flow)) return e;
+  if (!in || n < 1) return set_error("flow pass: bad arguments");
+  Layout L;
+  if (!layout_for_dim(flow->d, L)) return set_error("flow pass: unsupported event size");
+  FlowArgs A;
+  const size_t smem = plan_flow_smem(A, flow, L, false);
+  const int grid = grid_for(n, L.gs, 4);
+  cudaStream_t s = (cudaStream_t)stream;
+  NFMC_DISPATCH_E(L.E, { return launch_flow_pass<E>(A, mode, in, out, aux, n, grid, smem, s); });
+  return 0;
+}
+
+extern "C" int nfmc_realnvp_forward(const nfmc_realnvp* flow, const float* x, float* z, float* log_det, int64_t n, void* stream) {
+  return flow_pass(flow, PASS_FORWARD, x, z, log_det, n, stream);
+}
+extern "C" int nfmc_realnvp_inverse(const nfmc_realnvp* flow, const float* z, float* x, float* log_det, int64_t n, void* stream) {
+  return flow_pass(flow, PASS_INVERSE, z, x, log_det, n, stream);
+}
+extern "C" int nfmc_flow_log_prob(const nfmc_realnvp* flow, const float* x, float* log_q, int64_t n, void* stream) {
+  if (!log_q) return set_error("flow_log_prob: log_q is NULL");
+  return flow_pass(flow, PASS_LOGPROB, x, nullptr, log_q, n, stream);
+}
+
+extern "C" int nfmc_flow_sample(const nfmc_realnvp* flow, const nfmc_rng* rng, int64_t chain0, float* x, float* log_q,
+                                int64_t n, void* stream) {
+  if (int e = validate_flow(flow)) return e;
+  if (!x || !rng || n < 1) return set_error("flow_sample: bad arguments");
+  Layout L;
+  if (!layout_for_dim(flow->d, L)) return set_error("flow_sample: unsupported event size");
+  FlowArgs A;
+  const size_t smem = plan_flow_smem(A, flow, L, false);
+  RngArgs R{rng->seed, rng->step0, rng->normals, rng->uniforms};
+  const int grid = grid_for(n, L.gs, 4);
+  cudaStream_t s = (cudaStream_t)stream;
+  NFMC_DISPATCH_E(L.E, { return launch_flow_sample<E>(A, R, chain0, x, log_q, n, grid, smem, s); });
+  return 0;
+}
+
+static int launch_jump(const nfmc_potential* pot, const nfmc_realnvp* flow, float* x, float* logq_x, int64_t n,
+                       int32_t n_steps, int32_t recompute_logq, int32_t adjusted, const nfmc_rng* rng, int64_t chain0,
+                       const nfmc_stats* stats, const nfmc_sink* sink, void* stream) {
+  if (int e = validate_pot(pot)) return e;
+  if (int e = validate_flow(flow)) return e;
+  if (pot->d != flow->d) return set_error("jump: potential and flow event sizes differ");
+  if (!x || n < 1 || n_steps < 0) return set_error("jump: bad x/n/n_steps");
+  if (n_steps == 0) return 0;
+  Layout L;
+  if (!layout_for_dim(pot->d, L)) return set_error("jump: unsupported event size");
+  JumpArgs A;
+  A.c.pot = pot_params(pot);
+  A.c.x = x; A.c.n = n; A.c.chain0 = chain0; A.c.d = pot->d; A.c.gs = L.gs; A.c.n_steps = n_steps;
+  A.c.rng = RngArgs{rng ? rng->seed : 0, rng ? rng->step0 : 0, rng ? rng->normals : nullptr, rng ? rng->uniforms : nullptr};
+  A.c.stats = StatsArgs{stats ? stats->sum_x : nullptr, stats ? stats->sum_x2 : nullptr, stats ? stats->counts : nullptr};
+  A.c.sink = SinkArgs{sink ? sink->samples : nullptr, sink ? sink->seen0 : 0, (sink && sink->thinning > 0) ? sink->thinning : 1};
+  A.logq_x = logq_x; A.recompute_logq = recompute_logq; A.adjusted = adjusted;
+  const size_t smem = plan_flow_smem(A.f, flow, L, true);
+  const int grid = grid_for(n, L.gs, 4);
+  cudaStream_t s = (cudaStream_t)stream;
+  A.pot_kind = pot->kind;
+  NFMC_DISPATCH_E(L.E, { return launch_jump<E>(A, grid, smem, s); });
+  return 0;
+}
+
+extern "C" int nfmc_jump_step(const nfmc_potential* pot, const nfmc_realnvp* flow, float* x, int64_t n, int32_t adjusted,
+                              const nfmc_rng* rng, int64_t chain0, const nfmc_stats* stats, const nfmc_sink* sink, void* stream) {
+  return launch_jump(pot, flow, x, nullptr, n, 1, 1, adjusted, rng, chain0, stats, sink, stream);
+}
+
+extern "C" int nfmc_imh_steps(const nfmc_potential* pot, const nfmc_realnvp* flow, float* x, float* log_q_x, int64_t n,
+                              int32_t n_steps, int32_t recompute_logq, const nfmc_rng* rng, int64_t chain0,
+                              const nfmc_stats* stats, const nfmc_sink* sink, void* stream) {
+  if (!recompute_logq && !log_q_x) return set_error("imh_steps: log_q_x is required unless recompute_logq");
+  return launch_jump(pot, flow, x, log_q_x, n, n_steps, recompute_logq, 1, rng, chain0, stats, sink, stream);
+}
+
+extern "C" int64_t nfmc_realnvp_blob_floats(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden) {
+  return flow_blob_floats(d, n_coupling, n_linear, hidden);
+}
+extern "C" int nfmc_layout_for_dim(int32_t d, int32_t* lanes_per_chain, int32_t* slots_per_half) {
+  Layout L;
+  if (!layout_for_dim(d, L)) return set_error("layout_for_dim: d out of range [1, 1024]");
+  if (lanes_per_chain) *lanes_per_chain = L.gs;
+  if (slots_per_half) *slots_per_half = L.E;
+  return 0;
+}
+
+
+extern "C" int nfmc_neutra_hmc_steps(const nfmc_potential* pot, const nfmc_realnvp* flow, float* z, int64_t n, int32_t n_steps,
+                                     float step_size, int32_t n_leapfrog, const float* inv_mass_diag, const nfmc_rng* rng,
+                                     int64_t chain0, const nfmc_stats* stats, const nfmc_sink* sink, void* stream) {
+  if (int e = validate_pot(pot)) return e;
+  if (int e = validate_flow(flow)) return e;
+  if (pot->d != flow->d) return set_error("neutra_hmc: potential and flow event sizes differ");
+  if (!z || n < 1 || n_steps < 0 || n_leapfrog < 0) return set_error("neutra_hmc: bad arguments");
+  if (n_steps == 0) return 0;
+  Layout L;
+  if (!layout_for_dim(pot->d, L)) return set_error("neutra_hmc: unsupported event size");
+  NeutraArgs A;
+  A.c.pot = pot_params(pot);
+  A.c.x = z; A.c.n = n; A.c.chain0 = chain0; A.c.d = pot->d; A.c.gs = L.gs; A.c.n_steps = n_steps;
+  A.c.rng = RngArgs{rng ? rng->seed : 0, rng ? rng->step0 : 0, rng ? rng->normals : nullptr, rng ? rng->uniforms : nullptr};
+  A.c.stats = StatsArgs{stats ? stats->sum_x : nullptr, stats ? stats->sum_x2 : nullptr, stats ? stats->counts : nullptr};
+  A.c.sink = SinkArgs{sink ? sink->samples : nullptr, sink ? sink->seen0 : 0, (sink && sink->thinning > 0) ? sink->thinning : 1};
+  A.tau = step_size; A.imd = inv_mass_diag; A.n_leapfrog = n_leapfrog;
+  const size_t smem = plan_flow_smem(A.f, flow, L, true);
+  const int grid = grid_for(n, L.gs, 2);
+  cudaStream_t s = (cudaStream_t)stream;
+  A.pot_kind = pot->kind;
+  NFMC_DISPATCH_E(L.E, { return launch_neutra_hmc<E>(A, grid, smem, s); });
+  return 0;
+}
+
+extern "C" int nfmc_neutra_potential(const nfmc_potential* pot, const nfmc_realnvp* flow, const float* z, float* u, float* grad,
+                                     int64_t n, void* stream) {
+  if (int e = validate_pot(pot)) return e;
+  if (int e = validate_flow(flow)) return e;
+  if (pot->d != flow->d) return set_error("neutra_potential: potential and flow event sizes differ");
+  if (!z || !u || n < 1) return set_error("neutra_potential: bad arguments");
+  Layout L;
+  if (!layout_for_dim(pot->d, L)) return set_error("neutra_potential: unsupported event size");
+  FlowArgs FA;
+  const size_t smem = plan_flow_smem(FA, flow, L, false);
+  const PotParams P = pot_params(pot);
+  const int grid = grid_for(n, L.gs, 2);
+  cudaStream_t s = (cudaStream_t)stream;
+  NFMC_DISPATCH_E(L.E, { return launch_neutra_potential<E>(FA, pot->kind, P, z, u, grad, n, grid, smem, s); });
+  return 0;
+}

@@ -1,0 +1,194 @@
+// flow_kernels.cu -- RealNVP passes, flow sampling, the NF jump and independence-MH, one chain per lane group
+// (one translation unit per E).
+//
+// Replaces (reference paths under /root/reference/nfmc/algorithms/sampling/):
+//   flow.bijection.forward / inverse          nfmc/neutra.py:60,122
+//   flow.log_prob                             nfmc/jump.py:218, nfmc/imh.py:133-134,214
+//   flow.sample(n, return_log_prob=True)      nfmc/jump.py:205, nfmc/imh.py:221
+//   the jump block of JumpNFMC.sample         nfmc/jump.py:203-243
+//   FixedIMH.sample / AdaptiveIMH.sample      nfmc/imh.py:214-249, 122-150
+#include "launchers.cuh"
+
+#ifndef NFMC_ONLY_E
+#error "compile with -DNFMC_ONLY_E=<slots per half>"
+#endif
+
+namespace nfmc {
+
+template <int E>
+__global__ void __launch_bounds__(kThreads) flow_pass_kernel(FlowArgs A, int mode, const float* __restrict__ in,
+                                                            float* __restrict__ out, float* __restrict__ aux, long long n) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Geom g = make_geom(A.d, A.gs);
+  FlowSmem S = flow_smem_init(smem, A, false);
+  const bool flip = (A.Lc & 1) != 0;
+  const int cpc = kThreads / A.gs;
+  const long long tiles = (n + cpc - 1) / cpc;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long chain_raw = tile * cpc + threadIdx.x / A.gs;
+    const bool active = chain_raw < n;
+    const long long chain = active ? chain_raw : n - 1;
+    float lo[E], hi[E];
+    const float* src = in + chain * (long long)A.d;
+    if (mode == PASS_INVERSE && flip) load_chain_flipped(src, g, lo, hi);
+    else load_chain(src, g, lo, hi);
+    float r;
+    if (mode == PASS_INVERSE) r = flow_inverse<E>(S.F, g, lo, hi, S.scr);
+    else r = flow_forward<E>(S.F, g, lo, hi, S.scr);
+    if (mode == PASS_LOGPROB) r += base_log_prob(g, lo, hi);
+    if (active) {
+      if (out) {
+        float* dst = out + chain * (long long)A.d;
+        if (mode != PASS_INVERSE && flip) store_chain_flipped(dst, g, lo, hi);
+        else store_chain(dst, g, lo, hi);
+      }
+      if (aux && g.j == 0) aux[chain] = r;
+    }
+  }
+}
+
+template <int E>
+__global__ void __launch_bounds__(kThreads) flow_sample_kernel(FlowArgs A, RngArgs R, long long chain0, float* __restrict__ x,
+                                                              float* __restrict__ logq, long long n) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Geom g = make_geom(A.d, A.gs);
+  FlowSmem S = flow_smem_init(smem, A, false);
+  const bool flip = (A.Lc & 1) != 0;
+  const int cpc = kThreads / A.gs;
+  const long long tiles = (n + cpc - 1) / cpc;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long chain_raw = tile * cpc + threadIdx.x / A.gs;
+    const bool active = chain_raw < n;
+    const long long chain = active ? chain_raw : n - 1;
+    float lo[E], hi[E];
+    draw_base<E>(R, g, flip, n, chain, chain0, 0, lo, hi);
+    const float blp = base_log_prob(g, lo, hi);
+    const float ld = flow_inverse<E>(S.F, g, lo, hi, S.scr);
+    if (active) {
+      store_chain(x + chain * (long long)A.d, g, lo, hi);
+      if (logq && g.j == 0) logq[chain] = blp - ld;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// NF jump / IMH.  IMH = n_steps iterations with the state, U(x) and log q(x) kept on chip; the jump is the
+// same kernel with n_steps = 1 and log q(x) computed from x (jump.py:218).
+// ---------------------------------------------------------------------------------------------------------
+
+
+template <int E>
+__global__ void __launch_bounds__(kThreads) jump_kernel(const JumpArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const ChainArgs& C = A.c;
+  const Geom g = make_geom(C.d, C.gs);
+  FlowSmem S = flow_smem_init(smem, A.f, true);
+  const bool flip = (A.f.Lc & 1) != 0;
+  const int cpc = kThreads / C.gs;
+  const long long tiles = (C.n + cpc - 1) / cpc;
+  unsigned int n_acc = 0, n_bad = 0;
+
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long chain_raw = tile * cpc + threadIdx.x / C.gs;
+    const bool active = chain_raw < C.n;
+    const long long chain = active ? chain_raw : C.n - 1;
+    float* row = C.x + chain * (long long)C.d;
+
+    float lo[E], hi[E], m1lo[E], m1hi[E], m2lo[E], m2hi[E];
+    load_chain(row, g, lo, hi);
+#pragma unroll
+    for (int e = 0; e < E; ++e) m1lo[e] = m1hi[e] = m2lo[e] = m2hi[e] = 0.f;
+    float u_x = 0.f, f_x = 0.f;
+    if (A.adjusted) {
+      u_x = pot_prepare_rt<E>(A.pot_kind, C.pot, g, lo, hi).u;                                   // jump.py:212
+      if (!A.recompute_logq && A.logq_x) f_x = __ldg(A.logq_x + chain);                 // imh.py:214
+    }
+    for (int k = 0; k < C.n_steps; ++k) {
+      if (A.adjusted && (A.recompute_logq || !A.logq_x)) {                             // jump.py:218 / imh.py:133
+        float tlo[E], thi[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) { tlo[e] = lo[e]; thi[e] = hi[e]; }
+        const float ld = flow_forward<E>(S.F, g, tlo, thi, S.scr);
+        f_x = base_log_prob(g, tlo, thi) + ld;
+      }
+      // x', log q(x') = flow.sample(n, return_log_prob=True)   (jump.py:205, imh.py:221)
+      float plo[E], phi[E];
+      const uint32_t ubits = draw_base<E>(C.rng, g, flip, C.n, chain, C.chain0, k, plo, phi);
+      const float blp = base_log_prob(g, plo, phi);
+      const float ldi = flow_inverse<E>(S.F, g, plo, phi, S.scr);
+      const float f_p = blp - ldi;
+      bool accept = true;
+      float u_p = 0.f;
+      if (A.adjusted) {
+        u_p = pot_prepare_rt<E>(A.pot_kind, C.pot, g, plo, phi).u;                               // jump.py:213
+        const float log_alpha = (-u_p) - (-u_x) + f_x - f_p;                           // jump.py:219-224, util.py:392
+        float u;
+        if (C.rng.uniforms) u = __ldg(C.rng.uniforms + (long long)k * C.n + chain);
+        else u = uniform_from_bits(__shfl_sync(0xffffffffu, ubits, g.grp_base));
+        accept = logf(u) < log_alpha;                                                  // jump.py:225
+        if (!(fabsf(log_alpha) <= 3.0e38f) && g.j == 0 && active) ++n_bad;
+      }
+#pragma unroll
+      for (int e = 0; e < E; ++e) {                                                    // jump.py:231, imh.py:232
+        lo[e] = accept ? plo[e] : lo[e];
+        hi[e] = accept ? phi[e] : hi[e];
+      }
+      u_x = accept ? u_p : u_x;
+      f_x = accept ? f_p : f_x;                                                        // imh.py:233
+      if (accept && g.j == 0 && active) ++n_acc;
+      accumulate_moments(lo, hi, m1lo, m1hi, m2lo, m2hi);                              // jump.py:240, imh.py:242
+      if (C.sink.samples && active) sink_store(C.sink, g, C.n, chain, k, lo, hi);      // jump.py:243, imh.py:249
+    }
+    if (!active) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) m1lo[e] = m1hi[e] = m2lo[e] = m2hi[e] = 0.f;
+    }
+    flush_moments(g, m1lo, m1hi, m2lo, m2hi, S.st.sx, S.st.sx2);
+    if (active) {
+      store_chain(row, g, lo, hi);
+      if (A.logq_x && g.j == 0) A.logq_x[chain] = f_x;
+    }
+  }
+  n_acc = __reduce_add_sync(0xffffffffu, n_acc);
+  n_bad = __reduce_add_sync(0xffffffffu, n_bad);
+  if ((threadIdx.x & 31) == 0) {
+    if (n_acc) atomicAdd(S.st.cnt + 0, (unsigned long long)n_acc);
+    if (n_bad) atomicAdd(S.st.cnt + 2, (unsigned long long)n_bad);
+  }
+  if (threadIdx.x == 0) {
+    long long mine = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const long long first = tile * cpc;
+      mine += (C.n - first) < cpc ? (C.n - first) : cpc;
+    }
+    atomicAdd(S.st.cnt + 1, (unsigned long long)(mine * C.n_steps));
+  }
+  cta_stats_finish(S.st, C.stats, C.d);
+}
+
+
+template <int E>
+int launch_flow_pass(const FlowArgs& A, int mode, const float* in, float* out, float* aux, long long n, int grid,
+                     size_t smem, cudaStream_t s) {
+  NFMC_SET_SMEM_RET(flow_pass_kernel<E>, smem);
+  flow_pass_kernel<E><<<grid, kThreads, smem, s>>>(A, mode, in, out, aux, n);
+  return check_cuda(cudaGetLastError(), "flow_pass_kernel launch");
+}
+template <int E>
+int launch_flow_sample(const FlowArgs& A, const RngArgs& R, long long chain0, float* x, float* logq, long long n, int grid,
+                       size_t smem, cudaStream_t s) {
+  NFMC_SET_SMEM_RET(flow_sample_kernel<E>, smem);
+  flow_sample_kernel<E><<<grid, kThreads, smem, s>>>(A, R, chain0, x, logq, n);
+  return check_cuda(cudaGetLastError(), "flow_sample_kernel launch");
+}
+template <int E>
+int launch_jump(const JumpArgs& A, int grid, size_t smem, cudaStream_t s) {
+  NFMC_SET_SMEM_RET(jump_kernel<E>, smem);
+  jump_kernel<E><<<grid, kThreads, smem, s>>>(A);
+  return check_cuda(cudaGetLastError(), "jump_kernel launch");
+}
+template int launch_flow_pass<NFMC_ONLY_E>(const FlowArgs&, int, const float*, float*, float*, long long, int, size_t, cudaStream_t);
+template int launch_flow_sample<NFMC_ONLY_E>(const FlowArgs&, const RngArgs&, long long, float*, float*, long long, int, size_t, cudaStream_t);
+template int launch_jump<NFMC_ONLY_E>(const JumpArgs&, int, size_t, cudaStream_t);
+
+}  // namespace nfmc

@@ -1,0 +1,58 @@
+// launchers.cuh -- launch-argument structs and the per-E launcher templates that tie the C-ABI dispatch
+// (local_api.cu / flow_api.cu) to the kernels, which are compiled one translation unit per slots-per-half E
+// (-DNFMC_ONLY_E=<E>) so that the build parallelises.
+#pragma once
+#include "chain_kernel.cuh"
+#include "flow_args.cuh"
+#include "host_common.cuh"
+
+namespace nfmc {
+
+struct LocalArgs {
+  ChainArgs c;
+  float tau;          // step size
+  float sqrt_2tau;    // (float) sqrt(2 * (double) tau)
+  const float* imd;   // inverse mass diagonal [d] or nullptr (= ones)
+  int adjusted;
+  int n_leapfrog;
+};
+
+
+struct JumpArgs {
+  ChainArgs c;
+  FlowArgs f;
+  int pot_kind;
+  float* logq_x;       // [n] cached log q(x) (IMH) or nullptr
+  int recompute_logq;  // compute log q(x) by a forward pass (jump.py:218; AdaptiveIMH imh.py:133)
+  int adjusted;
+};
+
+struct NeutraArgs {
+  ChainArgs c;
+  FlowArgs f;
+  int pot_kind;
+  float tau;
+  const float* imd;
+  int n_leapfrog;
+};
+
+enum { PASS_FORWARD = 0, PASS_INVERSE = 1, PASS_LOGPROB = 2 };
+
+template <int E> int launch_mala(int pot_kind, const LocalArgs& A, int grid, size_t smem, cudaStream_t s);
+template <int E> int launch_hmc(int pot_kind, const LocalArgs& A, int grid, size_t smem, cudaStream_t s);
+template <int E> int launch_flow_pass(const FlowArgs& A, int mode, const float* in, float* out, float* aux, long long n,
+                                      int grid, size_t smem, cudaStream_t s);
+template <int E> int launch_flow_sample(const FlowArgs& A, const RngArgs& R, long long chain0, float* x, float* logq,
+                                        long long n, int grid, size_t smem, cudaStream_t s);
+template <int E> int launch_jump(const JumpArgs& A, int grid, size_t smem, cudaStream_t s);
+template <int E> int launch_neutra_hmc(const NeutraArgs& A, int grid, size_t smem, cudaStream_t s);
+template <int E> int launch_neutra_potential(const FlowArgs& FA, int pot_kind, const PotParams& P, const float* z, float* u,
+                                             float* grad, long long n, int grid, size_t smem, cudaStream_t s);
+
+#define NFMC_SET_SMEM_RET(kern, bytes)                                                                     \
+  do {                                                                                                     \
+    if ((bytes) > 227 * 1024) return set_error("shared-memory plan exceeds 227 KB (conditioner too large for the generic kernel)"); \
+    if ((bytes) > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+  } while (0)
+
+}  // namespace nfmc

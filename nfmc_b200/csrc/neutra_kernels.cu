@@ -1,0 +1,229 @@
+// neutra_kernels.cu -- NeuTra HMC: HMC in the latent space of the flow, gradient through the flow by a
+// hand-written input-VJP (the flow is frozen, so only d/dz is needed).  One translation unit per E.
+//
+// Replaces NeuTra.adjusted_target (nfmc/neutra.py:58-68) evaluated and differentiated by autograd inside
+// HMC.propose (mcmc/hmc.py:40-48,96-126):  U~(z) = U(T^-1 z) - log|det dT^-1/dz|.
+// The flow is invertible, so no activation is stored: the backward sweep walks x -> z again, re-deriving
+// each layer's input from its output while it pulls the gradient back (flow.cuh: flow_unwind).
+// The reference evaluates grad U~ 2L times per step, twice at each interior point; here L+1 times.
+// Outputs (samples, moments) are latent-space quantities, as in the reference.
+#include "launchers.cuh"
+
+#ifndef NFMC_ONLY_E
+#error "compile with -DNFMC_ONLY_E=<slots per half>"
+#endif
+
+namespace nfmc {
+
+// U~(z) and its gradient.  (zlo, zhi) physical-order latent; (glo, ghi) receives dU~/dz.
+template <int E>
+__device__ __forceinline__ float neutra_value_grad(const FlowDesc& F, int pot_kind, const PotParams& P, const Geom& g, const float (&zlo)[E],
+                                                   const float (&zhi)[E], float (&glo)[E], float (&ghi)[E], float* scr,
+                                                   bool want_grad) {
+  float xlo[E], xhi[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) { xlo[e] = zlo[e]; xhi[e] = zhi[e]; }
+  const float ld_inv = flow_inverse<E>(F, g, xlo, xhi, scr);                      // neutra.py:60
+  const PotCtx c = pot_prepare_rt<E>(pot_kind, P, g, xlo, xhi);
+  const float value = -((-c.u) + ld_inv);                                          // neutra.py:62-64
+  if (want_grad) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int kk = g.j + g.gs * e;
+      pot_grad_rt(pot_kind, P, c, g, kk, xlo[e], xhi[e], glo[e], ghi[e]);
+      if (kk >= g.da) glo[e] = 0.f;
+      if (kk >= g.db) ghi[e] = 0.f;
+    }
+    flow_unwind<E>(F, g, xlo, xhi, glo, ghi, scr);
+  }
+  return value;
+}
+
+
+
+template <int E>
+__global__ void __launch_bounds__(kThreads) neutra_hmc_kernel(const NeutraArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const ChainArgs& C = A.c;
+  const Geom g = make_geom(C.d, C.gs);
+  FlowSmem S = flow_smem_init(smem, A.f, true);
+  const bool flip = (A.f.Lc & 1) != 0;
+  const bool unit_mass = (A.imd == nullptr);
+  const int cpc = kThreads / C.gs;
+  const long long tiles = (C.n + cpc - 1) / cpc;
+  const float half_tau = A.tau / 2;
+  unsigned int n_acc = 0, n_bad = 0;
+
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long chain_raw = tile * cpc + threadIdx.x / C.gs;
+    const bool active = chain_raw < C.n;
+    const long long chain = active ? chain_raw : C.n - 1;
+    float* row = C.x + chain * (long long)C.d;
+
+    float lo[E], hi[E], m1lo[E], m1hi[E], m2lo[E], m2hi[E];
+    if (flip) load_chain_flipped(row, g, lo, hi); else load_chain(row, g, lo, hi);
+#pragma unroll
+    for (int e = 0; e < E; ++e) m1lo[e] = m1hi[e] = m2lo[e] = m2hi[e] = 0.f;
+    // per-slot inverse mass (physical order)
+    float mlo[E], mhi[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int kk = g.j + g.gs * e;
+      mlo[e] = mhi[e] = 1.f;
+      if (!unit_mass) {
+        if (kk < g.da) mlo[e] = __ldg(A.imd + (flip ? g.d - 1 - kk : kk));
+        if (kk < g.db) mhi[e] = __ldg(A.imd + (flip ? g.d - 1 - (g.da + kk) : g.da + kk));
+      }
+    }
+
+    for (int k = 0; k < C.n_steps; ++k) {
+      float plo[E], phi[E];
+      uint32_t ubits = 0;
+      {
+        StepNoise<E> nz;
+        if (C.rng.normals) {
+          const float* nr = C.rng.normals + ((long long)k * C.n + chain) * (long long)C.d;
+          if (flip) load_chain_flipped(nr, g, nz.lo, nz.hi); else load_chain(nr, g, nz.lo, nz.hi);
+          nz.ubits = 0;
+        } else {
+          const RngKey key = make_rng_key(C.rng.seed, 0u, C.rng.step0 + (uint64_t)k, (uint64_t)(C.chain0 + chain));
+          draw_step_noise<E>(key, g.j, nz);
+        }
+        ubits = nz.ubits;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int kk = g.j + g.gs * e;
+          plo[e] = (kk < g.da) ? nz.lo[e] : 0.f;
+          phi[e] = (kk < g.db) ? nz.hi[e] : 0.f;
+          if (!unit_mass) {                                                         // hmc.py:100
+            plo[e] *= __fdiv_rn(1.f, sqrtf(mlo[e]));
+            phi[e] *= __fdiv_rn(1.f, sqrtf(mhi[e]));
+          }
+        }
+      }
+      float zlo[E], zhi[E], glo[E], ghi[E];
+      float kin0 = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        zlo[e] = lo[e]; zhi[e] = hi[e];
+        kin0 = fmaf(plo[e] * plo[e], mlo[e], fmaf(phi[e] * phi[e], mhi[e], kin0));
+      }
+      // leapfrog with a single gradient call site: iteration 0 only evaluates at the start point
+      float u0 = 0.f, u1 = 0.f;
+      for (int l = 0; l <= A.n_leapfrog; ++l) {
+        if (l > 0) {
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const int kk = g.j + g.gs * e;
+            plo[e] = fmaf(-half_tau, glo[e], plo[e]);                               // hmc.py:51-53
+            phi[e] = fmaf(-half_tau, ghi[e], phi[e]);
+            zlo[e] = (kk < g.da) ? fmaf(A.tau, plo[e] * mlo[e], zlo[e]) : 0.f;      // hmc.py:56-58
+            zhi[e] = (kk < g.db) ? fmaf(A.tau, phi[e] * mhi[e], zhi[e]) : 0.f;
+          }
+        }
+        u1 = neutra_value_grad<E>(S.F, A.pot_kind, C.pot, g, zlo, zhi, glo, ghi, S.scr, true);
+        if (l == 0) u0 = u1;
+        else {
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            plo[e] = fmaf(-half_tau, glo[e], plo[e]);
+            phi[e] = fmaf(-half_tau, ghi[e], phi[e]);
+          }
+        }
+      }
+      float kin1 = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) kin1 = fmaf(plo[e] * plo[e], mlo[e], fmaf(phi[e] * phi[e], mhi[e], kin1));
+      const float h0 = u0 + 0.5f * group_sum(kin0, g.gs);                           // hmc.py:103-106
+      const float h1 = u1 + 0.5f * group_sum(kin1, g.gs);                           // hmc.py:107-110
+      const float log_acc = -h1 - (-h0);
+      float u;
+      if (C.rng.uniforms) u = __ldg(C.rng.uniforms + (long long)k * C.n + chain);
+      else u = uniform_from_bits(__shfl_sync(0xffffffffu, ubits, g.grp_base));
+      const bool accept = logf(u) < log_acc;                                        // hmc.py:112-113
+      if (!(fabsf(log_acc) <= 3.0e38f) && g.j == 0 && active) ++n_bad;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        lo[e] = accept ? zlo[e] : lo[e];
+        hi[e] = accept ? zhi[e] : hi[e];
+      }
+      if (accept && g.j == 0 && active) ++n_acc;
+      accumulate_moments(lo, hi, m1lo, m1hi, m2lo, m2hi);
+      if (C.sink.samples && active) {
+        const long long idx = C.sink.seen0 + k;
+        if (idx % C.sink.thinning == 0) {
+          const long long first = (C.sink.seen0 + C.sink.thinning - 1) / C.sink.thinning;
+          float* dst = C.sink.samples + ((idx / C.sink.thinning - first) * C.n + chain) * (long long)C.d;
+          if (flip) store_chain_flipped(dst, g, lo, hi); else store_chain(dst, g, lo, hi);
+        }
+      }
+    }
+    if (!active) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) m1lo[e] = m1hi[e] = m2lo[e] = m2hi[e] = 0.f;
+    }
+    flush_moments(g, m1lo, m1hi, m2lo, m2hi, S.st.sx, S.st.sx2, flip);
+    if (active) { if (flip) store_chain_flipped(row, g, lo, hi); else store_chain(row, g, lo, hi); }
+  }
+  n_acc = __reduce_add_sync(0xffffffffu, n_acc);
+  n_bad = __reduce_add_sync(0xffffffffu, n_bad);
+  if ((threadIdx.x & 31) == 0) {
+    if (n_acc) atomicAdd(S.st.cnt + 0, (unsigned long long)n_acc);
+    if (n_bad) atomicAdd(S.st.cnt + 2, (unsigned long long)n_bad);
+  }
+  if (threadIdx.x == 0) {
+    long long mine = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const long long first = tile * cpc;
+      mine += (C.n - first) < cpc ? (C.n - first) : cpc;
+    }
+    atomicAdd(S.st.cnt + 1, (unsigned long long)(mine * C.n_steps));
+  }
+  cta_stats_finish(S.st, C.stats, C.d);
+}
+
+template <int E>
+__global__ void __launch_bounds__(kThreads) neutra_potential_kernel(FlowArgs FA, int pot_kind, PotParams P, const float* __restrict__ z,
+                                                                   float* __restrict__ u, float* __restrict__ grad, long long n) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Geom g = make_geom(FA.d, FA.gs);
+  FlowSmem S = flow_smem_init(smem, FA, false);
+  const bool flip = (FA.Lc & 1) != 0;
+  const int cpc = kThreads / FA.gs;
+  const long long tiles = (n + cpc - 1) / cpc;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long chain_raw = tile * cpc + threadIdx.x / FA.gs;
+    const bool active = chain_raw < n;
+    const long long chain = active ? chain_raw : n - 1;
+    float zlo[E], zhi[E], glo[E], ghi[E];
+    const float* src = z + chain * (long long)FA.d;
+    if (flip) load_chain_flipped(src, g, zlo, zhi); else load_chain(src, g, zlo, zhi);
+    const float v = neutra_value_grad<E>(S.F, pot_kind, P, g, zlo, zhi, glo, ghi, S.scr, grad != nullptr);
+    if (active) {
+      if (g.j == 0) u[chain] = v;
+      if (grad) {
+        float* dst = grad + chain * (long long)FA.d;
+        if (flip) store_chain_flipped(dst, g, glo, ghi); else store_chain(dst, g, glo, ghi);
+      }
+    }
+  }
+}
+
+
+template <int E>
+int launch_neutra_hmc(const NeutraArgs& A, int grid, size_t smem, cudaStream_t s) {
+  NFMC_SET_SMEM_RET(neutra_hmc_kernel<E>, smem);
+  neutra_hmc_kernel<E><<<grid, kThreads, smem, s>>>(A);
+  return check_cuda(cudaGetLastError(), "neutra_hmc_kernel launch");
+}
+template <int E>
+int launch_neutra_potential(const FlowArgs& FA, int pot_kind, const PotParams& P, const float* z, float* u, float* grad,
+                            long long n, int grid, size_t smem, cudaStream_t s) {
+  NFMC_SET_SMEM_RET(neutra_potential_kernel<E>, smem);
+  neutra_potential_kernel<E><<<grid, kThreads, smem, s>>>(FA, pot_kind, P, z, u, grad, n);
+  return check_cuda(cudaGetLastError(), "neutra_potential_kernel launch");
+}
+template int launch_neutra_hmc<NFMC_ONLY_E>(const NeutraArgs&, int, size_t, cudaStream_t);
+template int launch_neutra_potential<NFMC_ONLY_E>(const FlowArgs&, int, const PotParams&, const float*, float*, float*, long long, int, size_t, cudaStream_t);
+
+}  // namespace nfmc

@@ -1,0 +1,385 @@
+"""Oracle (test infrastructure): the reference's sampler arithmetic restated op-for-op in torch fp32 on CPU.
+
+PINNED: ``tests/test_oracle_golden.py`` replays the fixtures in ``tests/golden/`` (made by importing the
+unmodified reference, ``tests/golden/make_golden.py``) through these functions.
+
+Each function cites the reference lines it follows (paths under /root/reference/nfmc/algorithms/sampling/).
+Random numbers come from a *draw source* so the same numbers can be injected into the CUDA kernels
+(the reference has no injection hook; it draws inline from the global generator in this order:
+``mcmc/langevin.py:63,106``, ``mcmc/hmc.py:100,112``, ``nfmc/jump.py:205,225``, ``nfmc/imh.py:221,229``).
+"""
+from __future__ import annotations
+
+import math
+import time
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional
+
+import torch
+
+
+# ---------------------------------------------------------------------------------------------------------
+# draw sources
+# ---------------------------------------------------------------------------------------------------------
+class GlobalDraws:
+    """Draw from torch's global CPU generator exactly as the reference does, optionally recording."""
+
+    def __init__(self, record: bool = False):
+        self.record = record
+        self.normals: List[torch.Tensor] = []
+        self.uniforms: List[torch.Tensor] = []
+
+    def normal(self, n, event_shape):
+        v = torch.randn(size=(n, *event_shape))
+        if self.record:
+            self.normals.append(v.clone())
+        return v
+
+    def uniform(self, n):
+        v = torch.rand(n)
+        if self.record:
+            self.uniforms.append(v.clone())
+        return v
+
+
+class TapeDraws:
+    """Replay pre-drawn numbers (``normals``: list of [n,*event]; ``uniforms``: list of [n])."""
+
+    def __init__(self, normals, uniforms):
+        self.normals = list(normals)
+        self.uniforms = list(uniforms)
+        self.i_n = 0
+        self.i_u = 0
+
+    def normal(self, n, event_shape):
+        v = self.normals[self.i_n]
+        self.i_n += 1
+        assert v.shape == (n, *event_shape)
+        return v.clone()
+
+    def uniform(self, n):
+        v = self.uniforms[self.i_u]
+        self.i_u += 1
+        assert v.shape == (n,)
+        return v.clone()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# bookkeeping (sampling/base.py)
+# ---------------------------------------------------------------------------------------------------------
+class StreamingMean:
+    """``MCMCExpectation.update`` (sampling/base.py:75-95): running mean of f(x) over (iteration, chain)."""
+
+    def __init__(self, f: Callable):
+        self.f = f
+        self.n_seen = 0
+        self.value = 0.0
+
+    def update(self, x: torch.Tensor, event_ndim: int):
+        if x.ndim == event_ndim + 1:
+            x = x[None]
+        n_new = x.shape[0] * x.shape[1]
+        self.value = torch.add(
+            self.n_seen / (self.n_seen + n_new) * self.value,
+            n_new / (self.n_seen + n_new) * torch.mean(self.f(x.detach()), dim=(0, 1)),
+        )
+        self.n_seen += n_new
+
+
+@dataclass
+class RunRef:
+    """What one oracle run returns (the fields of MCMCOutput / MCMCStatistics that carry numbers)."""
+    event_shape: tuple
+    x: torch.Tensor = None                      # last state
+    samples: Optional[torch.Tensor] = None      # [rows, n, *event]
+    n_accepted: int = 0
+    n_attempted: int = 0
+    n_divergences: int = 0
+    n_target_calls: int = 0
+    n_grad_calls: int = 0
+    n_accepted_jumps: int = 0
+    n_attempted_jumps: int = 0
+    first: StreamingMean = field(default_factory=lambda: StreamingMean(lambda v: v))
+    second: StreamingMean = field(default_factory=lambda: StreamingMean(lambda v: v ** 2))
+    rows: list = field(default_factory=list)
+    trace: dict = field(default_factory=dict)   # per-step diagnostics for parity tests
+
+    def observe(self, x: torch.Tensor, store: bool):
+        k = len(self.event_shape)
+        self.first.update(x, k)
+        self.second.update(x, k)
+        if store:
+            blk = x if x.ndim == k + 2 else x[None]
+            self.rows.extend(blk.detach().clone())
+
+    def finish(self, store: bool):
+        if store and self.rows:
+            self.samples = torch.stack(self.rows, dim=0)
+        return self
+
+    @property
+    def mean(self):
+        return self.first.value
+
+    @property
+    def second_moment(self):
+        return self.second.value
+
+    @property
+    def variance(self):
+        return self.second.value - self.first.value ** 2
+
+
+# ---------------------------------------------------------------------------------------------------------
+# util.py:382-392
+# ---------------------------------------------------------------------------------------------------------
+def mh_log_ratio(logp_curr, logp_prime, logq_curr, logq_prime):
+    return logp_prime - logp_curr + logq_curr - logq_prime
+
+
+def value_and_grad(target, x):
+    """``u = target(x)`` and ``grad u.sum()`` by autograd (langevin.py:66-70, hmc.py:40-48)."""
+    with torch.enable_grad():
+        xr = x.detach().clone().requires_grad_(True)
+        u = target(xr)
+        g, = torch.autograd.grad(u.sum(), xr)
+    return u.detach(), g.detach()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# local kernels
+# ---------------------------------------------------------------------------------------------------------
+def langevin_q(x_to, x_from, grad_from, a_diag, tau):
+    """``proposal_potential`` (mcmc/langevin.py:31-42)."""
+    term = x_to - x_from + tau * a_diag.view(1, -1) * grad_from
+    return (term * (1 / a_diag.view(1, -1)) * term).sum(dim=-1) / (4 * tau)
+
+
+def mala_propose(x, target, tau: float, imd: torch.Tensor, draws, adjusted: bool = True, trace=None):
+    """One Langevin proposal (mcmc/langevin.py:61-122).  ``x`` is ``[n, d]`` (Langevin is 1-D-event only, Q8)."""
+    n = x.shape[0]
+    noise = draws.normal(n, x.shape[1:])                                       # :63
+    u_x, g_x = value_and_grad(target, x)                                       # :66-68
+    grad_term = -tau / imd[None].square() * g_x                                # :74
+    noise_term = math.sqrt(2 * tau) / imd[None] * noise                        # :75
+    x_prime = x + grad_term + noise_term                                       # :76
+    if adjusted:
+        u_p, g_p = value_and_grad(target, x_prime)                             # :80-82
+        a = 1 / imd ** 2
+        log_ratio = mh_log_ratio(-u_x, -u_p, -langevin_q(x, x_prime, g_p, a, tau),
+                                 -langevin_q(x_prime, x, g_x, a, tau))         # :88-105
+        u = draws.uniform(n)
+        mask = torch.log(u) < log_ratio                                        # :106
+        calls = grads = 2 * n                                                  # :116-120
+        if trace is not None:
+            trace.setdefault("log_ratio", []).append(log_ratio.clone())
+            trace.setdefault("u_prime", []).append(u_p.clone())
+    else:
+        mask = torch.ones(n, dtype=torch.bool)                                 # :109
+        calls = grads = n
+    if trace is not None:
+        trace.setdefault("x_prime", []).append(x_prime.clone())
+        trace.setdefault("mask", []).append(mask.clone())
+    return x_prime, mask, calls, grads
+
+
+def hmc_propose(x, target, tau: float, imd: torch.Tensor, n_leapfrog: int, draws, adjusted: bool = True,
+                trace=None):
+    """One HMC proposal (mcmc/hmc.py:96-126 with the b-a-b trajectory of :51-77)."""
+    n = x.shape[0]
+    event_shape = x.shape[1:]
+    d = int(math.prod(event_shape))
+
+    def mass_mul(v, diag):                                                     # :26-37
+        return torch.einsum('...i,i->...i', v.reshape(n, d), diag.to(v)).view_as(v)
+
+    p0 = mass_mul(draws.normal(n, event_shape), 1 / imd.sqrt())                # :100
+    xs, p = x, p0
+    for _ in range(n_leapfrog):                                                # :68-71
+        p = p - tau / 2 * value_and_grad(target, xs)[1]                        # :51-53
+        xs = xs + tau * mass_mul(p, imd)                                       # :56-58
+        p = p - tau / 2 * value_and_grad(target, xs)[1]
+    x_prime, p_prime = xs, p
+    if adjusted:
+        h0 = target(x) + 0.5 * mass_mul(p0 ** 2, imd).reshape(n, -1).sum(dim=-1)          # :103-106
+        h1 = target(x_prime) + 0.5 * mass_mul(p_prime ** 2, imd).reshape(n, -1).sum(dim=-1)  # :107-110
+        log_accept = -h1 - (-h0)                                               # :111
+        u = draws.uniform(n)
+        mask = torch.log(u) < log_accept                                       # :112-113
+        if trace is not None:
+            trace.setdefault("log_ratio", []).append(log_accept.detach().clone())
+    else:
+        mask = torch.ones(n, dtype=torch.bool)
+    calls = 2 * n_leapfrog * n + (2 * n if adjusted else 0)                    # :122-125
+    grads = 2 * n_leapfrog * n
+    if trace is not None:
+        trace.setdefault("x_prime", []).append(x_prime.detach().clone())
+        trace.setdefault("mask", []).append(mask.clone())
+    return x_prime.detach(), mask, calls, grads
+
+
+def run_local(x0, propose: Callable, n_steps: int, store: bool = True, trace: bool = False) -> RunRef:
+    """``MCMCSampler.sample`` (mcmc/base.py:56-102) without tuning; ``propose(x, trace) -> (x', mask, calls, grads)``."""
+    n = x0.shape[0]
+    out = RunRef(event_shape=tuple(x0.shape[1:]))
+    x = x0.clone().detach()
+    tr = out.trace if trace else None
+    for _ in range(n_steps):
+        x_prime, mask, calls, grads = propose(x, tr)
+        x = x.detach()
+        x[mask] = x_prime[mask]                                                # :77
+        out.n_target_calls += calls
+        out.n_grad_calls += grads
+        out.n_accepted += int(torch.sum(mask))
+        out.n_attempted += n                                                   # :79-85
+        out.observe(x, store)                                                  # :86,90
+    out.x = x
+    return out.finish(store)
+
+
+def run_mala(x0, target, tau, imd, n_steps, draws, adjusted=True, store=True, trace=False) -> RunRef:
+    return run_local(x0, lambda x, tr: mala_propose(x, target, tau, imd, draws, adjusted, tr), n_steps, store, trace)
+
+
+def run_hmc(x0, target, tau, imd, n_leapfrog, n_steps, draws, adjusted=True, store=True, trace=False) -> RunRef:
+    return run_local(x0, lambda x, tr: hmc_propose(x, target, tau, imd, n_leapfrog, draws, adjusted, tr),
+                     n_steps, store, trace)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# flow-side helpers (draws routed through the draw source instead of ``flow.sample``'s inline randn)
+# ---------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def flow_sample_with_logq(flow, n, draws):
+    """``flow.sample(n, return_log_prob=True)`` (jump.py:205, imh.py:221) with the base draw injected."""
+    z = draws.normal(n, flow.event_shape)
+    x, log_det = flow.bijection.inverse(z)
+    return x, flow.base_log_prob(z) - log_det
+
+
+# ---------------------------------------------------------------------------------------------------------
+# NF outer loops
+# ---------------------------------------------------------------------------------------------------------
+def run_jump(x0, target, flow, inner: str, n_outer: int, n_inner: int, draws, tau: float, imd: torch.Tensor,
+             n_leapfrog: int = 20, adjusted_jumps: bool = True, inner_adjusted: bool = True,
+             store: bool = True, trace: bool = False) -> RunRef:
+    """``JumpNFMC.sample`` (nfmc/jump.py:156-246), frozen flow (``fit_nf=False``)."""
+    n = x0.shape[0]
+    out = RunRef(event_shape=tuple(x0.shape[1:]))
+    x = x0.clone()
+    for _ in range(n_outer):
+        if inner == "mala":
+            loc = run_mala(x, target, tau, imd, n_inner, draws, inner_adjusted, store=True, trace=trace)
+        elif inner == "hmc":
+            loc = run_hmc(x, target, tau, imd, n_leapfrog, n_inner, draws, inner_adjusted, store=True, trace=trace)
+        else:
+            raise ValueError(inner)
+        out.n_accepted += loc.n_accepted
+        out.n_attempted += loc.n_attempted
+        out.n_target_calls += loc.n_target_calls
+        out.n_grad_calls += loc.n_grad_calls                                   # :180-186
+        out.observe(loc.samples, store)                                        # :188-189
+        if trace:
+            for k, v in loc.trace.items():
+                out.trace.setdefault(k, []).extend(v)
+
+        x_prime, f_prime = flow_sample_with_logq(flow, n, draws)               # :205-207
+        x = loc.x.clone()                                                      # :209
+        if adjusted_jumps:
+            with torch.no_grad():
+                u_x = target(x)
+                u_p = target(x_prime)                                          # :212-213
+                out.n_target_calls += 2 * n                                    # :214-216
+                f_x = flow.log_prob(x)                                         # :218
+            log_alpha = mh_log_ratio(-u_x, -u_p, f_x, f_prime)                 # :219-224
+            u = draws.uniform(n)
+            mask = torch.log(u) < log_alpha                                    # :225
+            if trace:
+                out.trace.setdefault("jump_log_alpha", []).append(log_alpha.clone())
+                out.trace.setdefault("jump_x_prime", []).append(x_prime.clone())
+                out.trace.setdefault("jump_mask", []).append(mask.clone())
+        else:
+            mask = torch.ones(n, dtype=torch.bool)                             # :229
+        x[mask] = x_prime[mask]                                                # :231
+        out.n_attempted_jumps += n
+        out.n_accepted_jumps += int(torch.sum(mask))                           # :236-239
+        out.observe(x, store)                                                  # :240,243
+    out.x = x
+    return out.finish(store)
+
+
+def run_fixed_imh(x0, target, flow, n_iterations: int, draws, store: bool = True, trace: bool = False) -> RunRef:
+    """``FixedIMH.sample`` (nfmc/imh.py:200-255)."""
+    n = x0.shape[0]
+    out = RunRef(event_shape=tuple(x0.shape[1:]))
+    x = x0.clone()
+    with torch.no_grad():
+        f_x = flow.log_prob(x)                                                 # :214
+        for _ in range(n_iterations):
+            x_prime, f_prime = flow_sample_with_logq(flow, n, draws)           # :221
+            log_alpha = mh_log_ratio(-target(x), -target(x_prime), f_x, f_prime)   # :223-228
+            u = draws.uniform(n)
+            mask = torch.less(torch.log(u), log_alpha)                         # :229-230
+            x[mask] = x_prime[mask]
+            f_x[mask] = f_prime[mask]                                          # :232-233
+            out.n_target_calls += 2 * n
+            out.n_accepted += int(torch.sum(mask))
+            out.n_attempted += n                                               # :243-247
+            out.observe(x, store)                                              # :242,249
+            if trace:
+                out.trace.setdefault("log_alpha", []).append(log_alpha.clone())
+                out.trace.setdefault("x_prime", []).append(x_prime.clone())
+                out.trace.setdefault("mask", []).append(mask.clone())
+    out.x = x
+    return out.finish(store)
+
+
+def neutra_potential(flow, target):
+    """``NeuTra.adjusted_target`` (nfmc/neutra.py:58-68): U~(z) = U(T^-1 z) - log|det dT^-1/dz|."""
+
+    def adjusted(z):
+        x, log_det_inverse = flow.bijection.inverse(z)
+        log_prob = -target(x)
+        return -(log_prob + log_det_inverse.to(log_prob))
+
+    return adjusted
+
+
+def run_neutra_hmc(z0, target, flow, n_iterations: int, draws, tau: float, imd: torch.Tensor,
+                   n_leapfrog: int = 20, store: bool = True, trace: bool = False) -> RunRef:
+    """``NeuTra.sample`` (nfmc/neutra.py:109-129): HMC on the latent potential; outputs stay in z-space (Q1)."""
+    return run_hmc(z0, neutra_potential(flow, target), tau, imd, n_leapfrog, n_iterations, draws,
+                   adjusted=True, store=store, trace=trace)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# warm-up tuning (mcmc/base.py:142-161, tuning.py:15-41)
+# ---------------------------------------------------------------------------------------------------------
+class DualAveragingRef:
+    def __init__(self, initial_step, target_rate=0.651, kappa=0.75, gamma=0.05, t0=10):
+        self.t = t0
+        self.err = 0.0
+        self.log_avg = math.log(initial_step)
+        self.mu = math.log(10 * initial_step)
+        self.kappa, self.gamma, self.target_rate = kappa, gamma, target_rate
+
+    def step(self, acc_rate: float) -> float:
+        self.err += float(self.target_rate - acc_rate)
+        log_raw = self.mu - self.err / (math.sqrt(self.t) * self.gamma)
+        eta = self.t ** -self.kappa
+        self.log_avg = eta * log_raw + (1 - eta) * self.log_avg
+        self.t += 1
+        return math.exp(self.log_avg)
+
+
+def tune_inv_mass(imd, x, c=1e-3):
+    return c * torch.var(x.flatten(1, -1), dim=0) + (1 - c) * imd
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU timing helper for bench.py's cpu_baseline / --impl reference legs
+# ---------------------------------------------------------------------------------------------------------
+def timed(fn, *args, **kwargs):
+    t0 = time.perf_counter()
+    out = fn(*args, **kwargs)
+    return out, time.perf_counter() - t0

@@ -1,0 +1,63 @@
+"""CPU: pin oracle/samplers_ref.py to outputs of the unmodified reference (tests/golden/, made by make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import load_case, tape, oracle_flow, oracle_target
+from oracle import samplers_ref as R
+
+
+def _check(g, run, jump=False):
+    # the restatement follows the reference op for op, so agreement is to the last bit on the same CPU
+    np.testing.assert_allclose(run.samples.numpy(), g["samples"], rtol=0, atol=0)
+    np.testing.assert_allclose(run.x.numpy(), g["last"], rtol=0, atol=0)
+    np.testing.assert_allclose(np.asarray(run.mean), g["mean"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(np.asarray(run.second_moment), g["second_moment"], rtol=1e-6, atol=1e-7)
+    acc, att, div, grads, calls, jacc, jatt = (int(v) for v in g["counters"])
+    assert (run.n_accepted, run.n_attempted, run.n_divergences) == (acc, att, div)
+    assert (run.n_grad_calls, run.n_target_calls) == (grads, calls)
+    if jump:
+        assert (run.n_accepted_jumps, run.n_attempted_jumps) == (jacc, jatt)
+
+
+@pytest.mark.parametrize("name", ["mala_g0", "mala_fn"])
+def test_mala(name):
+    g = load_case(name)
+    run = R.run_mala(torch.from_numpy(g["x0"]), oracle_target(g), float(g["step"]), torch.from_numpy(g["imd"]),
+                     int(g["K"]), tape(g))
+    _check(g, run)
+
+
+@pytest.mark.parametrize("name", ["hmc_g1", "hmc_rb"])
+def test_hmc(name):
+    g = load_case(name)
+    run = R.run_hmc(torch.from_numpy(g["x0"]), oracle_target(g), float(g["step"]), torch.from_numpy(g["imd"]),
+                    int(g["L"]), int(g["K"]), tape(g))
+    _check(g, run)
+
+
+def test_jump_mala():
+    g = load_case("jump_mala_g0")
+    run = R.run_jump(torch.from_numpy(g["x0"]), oracle_target(g), oracle_flow(g), "mala", int(g["T"]), int(g["K"]),
+                     tape(g), float(g["step"]), torch.from_numpy(g["imd"]))
+    _check(g, run, jump=True)
+
+
+def test_jump_hmc():
+    g = load_case("jump_hmc_gm")
+    run = R.run_jump(torch.from_numpy(g["x0"]), oracle_target(g), oracle_flow(g), "hmc", int(g["T"]), int(g["K"]),
+                     tape(g), float(g["step"]), torch.from_numpy(g["imd"]), n_leapfrog=int(g["L"]))
+    _check(g, run, jump=True)
+
+
+def test_fixed_imh():
+    g = load_case("imh_rb")
+    run = R.run_fixed_imh(torch.from_numpy(g["x0"]), oracle_target(g), oracle_flow(g), int(g["T"]), tape(g))
+    _check(g, run)
+
+
+def test_neutra_hmc():
+    g = load_case("neutra_hmc_fn")
+    run = R.run_neutra_hmc(torch.from_numpy(g["x0"]), oracle_target(g), oracle_flow(g), int(g["T"]), tape(g),
+                           float(g["step"]), torch.from_numpy(g["imd"]), n_leapfrog=int(g["L"]))
+    _check(g, run)
