@@ -1,0 +1,294 @@
+"""Host-side mirror of the ``torchflows`` surface nfmc uses, backed by the sm_100a kernels.
+
+``Flow`` / ``RealNVP`` are parameter containers (``nn.Module``; same ``state_dict`` keys as the oracle's
+restatement) whose operators -- ``log_prob``, ``sample``, ``bijection.forward`` / ``inverse`` -- run on the
+GPU through ``libnfmc_b200.so``.  The call sites they serve in the reference:
+``/root/reference/nfmc/algorithms/sampling/base.py:26`` (default flow), ``nfmc/util.py:280-281``
+(``flow='realnvp'``), ``nfmc/jump.py:205,218``, ``nfmc/imh.py:214,221``, ``nfmc/neutra.py:60``.
+
+Arithmetic convention (see ``oracle/realnvp_ref.py`` -- parity against torchflows itself is unpinned because
+that package is absent): affine pair ``(u_a, u_b)`` -> ``alpha = exp(log(1-m) + u_a/2) + m``, ``m = 1e-3``,
+``beta = u_b/2``; layers ``[Affine] + Lc x [Reverse, Coupling, ActNorm] + [Affine, ActNorm]``.
+
+``pack_realnvp`` folds the reverse permutations into the parameter order so the kernels never permute the
+chain state ("flow blob").
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _native as N
+
+MIN_SCALE = 1e-3
+_LOG_ONE_MINUS_M = math.log(1.0 - MIN_SCALE)
+
+
+def _affine(u_a: torch.Tensor, u_b: torch.Tensor):
+    alpha = torch.exp(_LOG_ONE_MINUS_M + u_a / 2) + MIN_SCALE
+    return alpha, torch.log(alpha), u_b / 2
+
+
+class _Layer(nn.Module):
+    def __init__(self, event_shape):
+        super().__init__()
+        self.event_shape = tuple(int(s) for s in event_shape)
+        self.n_dim = int(math.prod(self.event_shape))
+
+
+class ElementwiseAffine(_Layer):
+    def __init__(self, event_shape):
+        super().__init__(event_shape)
+        self.value = nn.Parameter(torch.zeros(self.n_dim, 2))
+
+
+class ActNorm(ElementwiseAffine):
+    def __init__(self, event_shape):
+        super().__init__(event_shape)
+        self.register_buffer("initialised", torch.tensor(False))
+
+
+class ReversePermutation(_Layer):
+    pass
+
+
+def default_hidden(n_source: int) -> int:
+    return max(int(3 * math.log10(n_source)), 4)
+
+
+class AffineCoupling(_Layer):
+    def __init__(self, event_shape, conditioner_kwargs: Optional[dict] = None, **_ignored):
+        super().__init__(event_shape)
+        ck = dict(conditioner_kwargs or {})
+        self.n_source = self.n_dim // 2
+        self.n_target = self.n_dim - self.n_source
+        self.n_linear = int(ck.get("n_layers", 2))
+        hidden = ck.get("n_hidden", None)
+        self.n_hidden = int(default_hidden(self.n_source) if hidden is None else hidden)
+        if self.n_linear < 1:
+            raise ValueError("conditioner needs at least one linear layer")
+        mods = []
+        if self.n_linear == 1:
+            mods.append(nn.Linear(self.n_source, 2 * self.n_target))
+        else:
+            mods += [nn.Linear(self.n_source, self.n_hidden), nn.Tanh()]
+            for _ in range(self.n_linear - 2):
+                mods += [nn.Linear(self.n_hidden, self.n_hidden), nn.Tanh()]
+            mods.append(nn.Linear(self.n_hidden, 2 * self.n_target))
+        self.net = nn.Sequential(*mods)
+        with torch.no_grad():  # identity map at initialisation
+            self.net[-1].weight.zero_()
+            self.net[-1].bias.zero_()
+
+    def linears(self):
+        return [m for m in self.net if isinstance(m, nn.Linear)]
+
+
+class RealNVP(_Layer):
+    """RealNVP bijection.  ``forward``: data -> latent, ``inverse``: latent -> data; both return ``(y, log_det)``."""
+
+    def __init__(self, event_shape, n_layers: int = 2, edge_list=None, **kwargs):
+        if isinstance(event_shape, int):
+            event_shape = (event_shape,)
+        super().__init__(event_shape)
+        if edge_list is not None:
+            raise NotImplementedError("edge_list couplings are outside the accelerated hot path")
+        if self.n_dim < 2 or self.n_dim > N.MAX_DIM:
+            raise ValueError(f"RealNVP event size must be in [2, {N.MAX_DIM}]")
+        layers = [ElementwiseAffine(event_shape)]
+        for _ in range(int(n_layers)):
+            layers += [ReversePermutation(event_shape), AffineCoupling(event_shape, **kwargs), ActNorm(event_shape)]
+        layers += [ElementwiseAffine(event_shape), ActNorm(event_shape)]
+        self.layers = nn.ModuleList(layers)
+        self.n_coupling = int(n_layers)
+        self._packed = {}  # device -> (version key, blob tensor)
+
+    # -- structure --------------------------------------------------------------------------------------------
+    def couplings(self):
+        return [m for m in self.layers if isinstance(m, AffineCoupling)]
+
+    def conditioner_shape(self) -> Tuple[int, int]:
+        cs = self.couplings()
+        if not cs:
+            return 2, 4
+        return cs[0].n_linear, cs[0].n_hidden
+
+    def _version_key(self):
+        return tuple(p._version for p in self.parameters()) + tuple(id(p) for p in self.parameters())
+
+    def blob(self, device: torch.device) -> torch.Tensor:
+        key = str(device)
+        ver = self._version_key()
+        hit = self._packed.get(key)
+        if hit is None or hit[0] != ver:
+            self._packed[key] = (ver, pack_realnvp(self).to(device))
+        return self._packed[key][1]
+
+    def descriptor(self, device: torch.device):
+        blob = self.blob(device)
+        M, H = self.conditioner_shape()
+        return N.RealNVPDesc(self.n_dim, self.n_coupling, M, H, blob.data_ptr(), blob.numel()), blob
+
+    # -- operators ----------------------------------------------------------------------------------------------
+    def _pass(self, fn_name: str, x: torch.Tensor):
+        dev = N.require_cuda(x.device if x.is_cuda else None)
+        batch = x.shape[: x.ndim - len(self.event_shape)]
+        xd = N.dev_f32(x, dev).reshape(-1, self.n_dim)
+        n = xd.shape[0]
+        y = torch.empty_like(xd)
+        ld = torch.empty(n, device=dev, dtype=torch.float32)
+        desc, keep = self.descriptor(dev)
+        N.check(getattr(N.lib(), fn_name)(C.byref(desc), N.ptr(xd), N.ptr(y), N.ptr(ld), n, N.stream_ptr(dev)))
+        return y.reshape(*batch, *self.event_shape), ld.reshape(batch)
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, context=None):
+        return self._pass("nfmc_realnvp_forward", x)
+
+    @torch.no_grad()
+    def inverse(self, z: torch.Tensor, context=None):
+        return self._pass("nfmc_realnvp_inverse", z)
+
+
+class Flow(nn.Module):
+    """Standard-normal base distribution + bijection."""
+
+    def __init__(self, bijection: RealNVP):
+        super().__init__()
+        if not isinstance(bijection, RealNVP):
+            raise NotImplementedError("the accelerated path supports RealNVP flows only")
+        self.bijection = bijection
+        self.register_buffer("_device_probe", torch.zeros(()))
+        self._sample_calls = 0
+        self._seed = None
+
+    @property
+    def event_shape(self):
+        return self.bijection.event_shape
+
+    def get_device(self) -> torch.device:
+        return self._device_probe.device
+
+    def _compute_device(self) -> torch.device:
+        d = self.get_device()
+        return N.require_cuda(d if d.type == "cuda" else None)
+
+    @torch.no_grad()
+    def log_prob(self, x: torch.Tensor, context=None) -> torch.Tensor:
+        dev = self._compute_device()
+        bij = self.bijection
+        batch = x.shape[: x.ndim - len(bij.event_shape)]
+        xd = N.dev_f32(x, dev).reshape(-1, bij.n_dim)
+        n = xd.shape[0]
+        out = torch.empty(n, device=dev, dtype=torch.float32)
+        desc, keep = bij.descriptor(dev)
+        N.check(N.lib().nfmc_flow_log_prob(C.byref(desc), N.ptr(xd), N.ptr(out), n, N.stream_ptr(dev)))
+        return out.reshape(batch)
+
+    @torch.no_grad()
+    def sample(self, sample_shape, context=None, no_grad: bool = False, return_log_prob: bool = False,
+               seed: Optional[int] = None, z: Optional[torch.Tensor] = None):
+        """Draw from the flow.  ``seed`` keys the Philox stream (default: drawn from torch's global generator);
+        ``z`` injects the base draw instead."""
+        dev = self._compute_device()
+        bij = self.bijection
+        if isinstance(sample_shape, int):
+            sample_shape = (sample_shape,)
+        n = int(math.prod(sample_shape))
+        x = torch.empty(n, bij.n_dim, device=dev, dtype=torch.float32)
+        lq = torch.empty(n, device=dev, dtype=torch.float32)
+        zd = None if z is None else N.dev_f32(z, dev).reshape(n, bij.n_dim)
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (), dtype=torch.int64))
+        rng = N.rng_desc(seed, 0, zd, None)
+        desc, keep = bij.descriptor(dev)
+        N.check(N.lib().nfmc_flow_sample(C.byref(desc), C.byref(rng), 0, N.ptr(x), N.ptr(lq), n, N.stream_ptr(dev)))
+        x = x.reshape(*sample_shape, *bij.event_shape)
+        if return_log_prob:
+            return x, lq.reshape(tuple(sample_shape))
+        return x
+
+    # -- training (not yet native) -------------------------------------------------------
+    def fit(self, *args, **kwargs):
+        raise NotImplementedError("Flow.fit: flow training on the device is the next row of the scope table "
+                                  "(SURVEY.md section 8f); the frozen-flow hot path does not need it")
+
+    def variational_fit(self, *args, **kwargs):
+        raise NotImplementedError("Flow.variational_fit: see Flow.fit")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# packing
+# ------------------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def pack_realnvp(bij: RealNVP) -> torch.Tensor:
+    """Pack a RealNVP into the flat fp32 blob the kernels read (layout: nfmc_b200/csrc/flow.cuh header).
+
+    Reverse permutations are folded in: after r reversals logical position p sits at physical coordinate
+    ``p`` (r even) or ``d-1-p`` (r odd); every per-dimension parameter and every conditioner weight is stored
+    at the physical coordinate.  Coupling l (0-based) follows r = l+1 reversals.
+    """
+    d = bij.n_dim
+    da, db = d // 2, d - d // 2
+    Lc = bij.n_coupling
+    M, H = bij.conditioner_shape()
+    layers = list(bij.layers)
+    parts = []
+    affines = [(layers[0], 0)]
+    for l in range(Lc):
+        affines.append((layers[3 + 3 * l], l + 1))
+    affines += [(layers[-2], Lc), (layers[-1], Lc)]
+    log_const = torch.zeros((), dtype=torch.float32)
+    for layer, r in affines:
+        v = layer.value.detach().to("cpu", torch.float32)
+        alpha, log_alpha, beta = _affine(v[:, 0], v[:, 1])
+        log_const = log_const + log_alpha.sum()
+        if r % 2 == 1:
+            alpha, beta = alpha.flip(0), beta.flip(0)
+        parts += [alpha, beta, 1.0 / alpha]
+    parts.append(torch.stack([log_const, torch.zeros(()), torch.zeros(()), torch.zeros(())]))
+    for l in range(Lc):
+        cpl = layers[2 + 3 * l]
+        if (cpl.n_linear, cpl.n_hidden) != (M, H) and cpl.n_linear > 1:
+            raise ValueError("all couplings must share the conditioner shape")
+        odd = (l + 1) % 2 == 1
+        lin = [(m.weight.detach().to("cpu", torch.float32), m.bias.detach().to("cpu", torch.float32)) for m in cpl.linears()]
+        if M >= 2:
+            w1, b1 = lin[0]                                  # [H, da]
+            parts += [(w1.flip(1) if odd else w1).reshape(-1), b1]
+            for wm, bm in lin[1:-1]:                         # [H_out, H_in] -> [H_in][H_out]
+                parts += [wm.t().contiguous().reshape(-1), bm]
+            wl, bl = lin[-1]                                 # [2*db, H]
+            wl = wl.reshape(db, 2, H).permute(2, 1, 0)       # [H][2][db]
+            bl = bl.reshape(db, 2).t()                       # [2][db]
+            if odd:
+                wl, bl = wl.flip(2), bl.flip(1)
+            parts += [wl.contiguous().reshape(-1), bl.contiguous().reshape(-1)]
+        else:
+            wl, bl = lin[0]                                  # [2*db, da]
+            wl = wl.reshape(db, 2, da).permute(2, 1, 0)      # [da][2][db]
+            bl = bl.reshape(db, 2).t()
+            if odd:
+                wl, bl = wl.flip(0).flip(2), bl.flip(1)
+            parts += [wl.contiguous().reshape(-1), bl.contiguous().reshape(-1)]
+    blob = torch.cat([p.reshape(-1) for p in parts]).contiguous()
+    expect = (Lc + 3) * 3 * d + 4 + Lc * ((da * 2 * db + 2 * db) if M == 1 else
+                                          ((da * H + H) + (M - 2) * (H * H + H) + (H * 2 * db + 2 * db)))
+    assert blob.numel() == expect, (blob.numel(), expect)
+    return blob
+
+
+def create_flow_object(flow_string: str, event_shape, **kwargs) -> Flow:
+    """``'realnvp'`` or ``'realnvp%{json kwargs}'`` -> Flow (the reference's ``nfmc.util.create_flow_object``,
+    /root/reference/nfmc/util.py:189-215,218-281, restricted to the RealNVP family)."""
+    import json
+    name, _, js = flow_string.partition("%")
+    if js:
+        kwargs = {**kwargs, **json.loads(js)}
+    if name.lower() not in ("realnvp", "real_nvp", "rnvp"):
+        raise NotImplementedError(f"flow {name!r}: only 'realnvp' is on the accelerated hot path")
+    return Flow(RealNVP(event_shape, **kwargs))

@@ -1,0 +1,469 @@
+"""Result and configuration records -- the reference's contract, re-implemented on top of device-side sums.
+
+Same class names, fields, properties and meaning as ``/root/reference/nfmc/algorithms/sampling/base.py``
+(``MCMCStatistics`` :126-212, ``MCMCSamples`` :215-271, ``MCMCOutput`` :274-314, kernels / parameters :9-61),
+``mcmc/base.py:105-131``, ``mcmc/langevin.py:10-28``, ``mcmc/hmc.py:10-23``, ``nfmc/jump.py:21-81``,
+``nfmc/neutra.py:19-33`` and ``nfmc/imh.py:13-36``.  The difference is in how the running moments are kept:
+the reference streams a mean over host tensors (``MCMCExpectation.update``, base.py:75-95); here the kernels
+accumulate ``sum x`` / ``sum x^2`` in fp64 on the device and the records hold those sums plus a count, which
+is what makes pooling over GPUs a plain all-reduce.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Tuple, Union
+
+import torch
+
+from .flow import Flow, RealNVP
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# kernels (adaptive state) and parameters (hyper-parameters)
+# ---------------------------------------------------------------------------------------------------------------
+@dataclass
+class MCMCKernel:
+    def __post_init__(self):
+        pass
+
+
+@dataclass
+class NFMCKernel(MCMCKernel):
+    event_shape: Union[Tuple[int, ...], torch.Size]
+    flow: Flow = None
+
+    def __post_init__(self):
+        super().__post_init__()
+        if self.flow is None:
+            self.flow = Flow(RealNVP(self.event_shape))
+
+
+@dataclass
+class IMHKernel(NFMCKernel):
+    pass
+
+
+@dataclass
+class NeuTraKernel(NFMCKernel):
+    pass
+
+
+@dataclass
+class DualAveragingParams:
+    target_acceptance_rate: float = 0.651
+    kappa: float = 0.75
+    gamma: float = 0.05
+    t0: int = 10
+
+
+class DualAveraging:
+    """Nesterov dual averaging of the log step size (reference: sampling/tuning.py:15-41)."""
+
+    def __init__(self, initial_step_size: float, params: DualAveragingParams):
+        self.p = params
+        self.t = params.t0
+        self.error_sum = 0.0
+        self.log_step_averaged = math.log(initial_step_size)
+        self.log_step = math.inf
+        self.mu = math.log(10 * initial_step_size)
+
+    def step(self, acceptance_rate_error: float):
+        self.error_sum += float(acceptance_rate_error)
+        self.log_step = self.mu - self.error_sum / (math.sqrt(self.t) * self.p.gamma)
+        eta = self.t ** -self.p.kappa
+        self.log_step_averaged = eta * self.log_step + (1 - eta) * self.log_step_averaged
+        self.t += 1
+
+    @property
+    def value(self) -> float:
+        return math.exp(self.log_step_averaged)
+
+    def __repr__(self):
+        return f'DA error: {self.error_sum:.2f}'
+
+
+@dataclass
+class MetropolisKernel(MCMCKernel):
+    event_size: int
+    inv_mass_diag: torch.Tensor = None
+    step_size: float = 0.01
+    da: DualAveraging = None
+    da_params: DualAveragingParams = None
+
+    def __post_init__(self):
+        super().__post_init__()
+        if self.inv_mass_diag is None:
+            self.inv_mass_diag = torch.ones(self.event_size)
+        elif tuple(self.inv_mass_diag.shape) != (self.event_size,):
+            raise ValueError("inv_mass_diag must have shape (event_size,)")
+        if self.da_params is None:
+            self.da_params = DualAveragingParams()
+        if self.da is None:
+            self.da = DualAveraging(self.step_size, self.da_params)
+
+    def has_unit_mass(self) -> bool:
+        return bool(torch.all(self.inv_mass_diag == 1.0))
+
+
+@dataclass
+class LangevinKernel(MetropolisKernel):
+    event_size: int = None
+    step_size: Optional[float] = None
+
+    def __post_init__(self):
+        if self.step_size is None:
+            self.step_size = self.event_size ** (-1 / 3)   # reference: mcmc/langevin.py:17-18
+        super().__post_init__()
+
+    def __repr__(self):
+        return (f'log step: {math.log(self.step_size):.2f}, '
+                f'mass norm: {torch.max(torch.abs(self.inv_mass_diag)):.2f}')
+
+
+@dataclass
+class HMCKernel(MetropolisKernel):
+    event_size: int = None
+    n_leapfrog_steps: int = 20
+
+    def __repr__(self):
+        return (f'log step: {math.log(self.step_size):.2f}, leapfrogs: {self.n_leapfrog_steps}, '
+                f'mass norm: {torch.max(torch.abs(self.inv_mass_diag)):.2f}')
+
+
+@dataclass
+class MCMCParameters:
+    n_iterations: int = 100
+    n_warmup_iterations: int = 100
+    tuning: bool = False
+    store_samples: bool = True
+
+    def __post_init__(self):
+        pass
+
+    def tuning_mode(self):
+        self.tuning = True
+
+    def sampling_mode(self):
+        self.tuning = False
+
+
+@dataclass
+class MetropolisParameters(MCMCParameters):
+    tune_inv_mass_diag: bool = True
+    tune_step_size: bool = True
+    adjustment: bool = True
+    imd_adjustment: float = 1e-3
+
+
+@dataclass
+class LangevinParameters(MetropolisParameters):
+    pass
+
+
+@dataclass
+class HMCParameters(MetropolisParameters):
+    pass
+
+
+@dataclass
+class NFMCParameters(MCMCParameters):
+    train_pct: float = 0.7
+    max_train_size: int = 4096
+    max_val_size: int = 4096
+    flow_fit_kwargs: Dict[str, Any] = None
+
+    def __post_init__(self):
+        super().__post_init__()
+        if self.flow_fit_kwargs is None:
+            self.flow_fit_kwargs = dict(early_stopping=True, early_stopping_threshold=50, batch_size='adaptive',
+                                        show_progress=False)
+
+
+@dataclass
+class JumpNFMCParameters(NFMCParameters):
+    adjusted_jumps: bool = True
+    fit_nf: bool = False
+    warmup_fit_kwargs: dict = None
+    n_jumps_before_training: int = 10
+
+    def __post_init__(self):
+        super().__post_init__()
+        if self.warmup_fit_kwargs is None:
+            self.warmup_fit_kwargs = dict(early_stopping=True, early_stopping_threshold=50, keep_best_weights=True,
+                                          n_samples=1, n_epochs=500, lr=0.05)
+
+
+@dataclass
+class NeuTraParameters(NFMCParameters):
+    batch_inverse_size: int = 128
+    warmup_fit_kwargs: dict = None
+
+    def __post_init__(self):
+        # as in the reference (nfmc/neutra.py:24-33) the parent hook is not called: flow_fit_kwargs stays None (Q4)
+        if self.warmup_fit_kwargs is None:
+            self.warmup_fit_kwargs = dict(early_stopping=True, early_stopping_threshold=5000, keep_best_weights=True,
+                                          n_samples=1, n_epochs=50000, lr=0.05)
+
+
+@dataclass
+class IMHParameters(NFMCParameters):
+    train_distribution: str = 'uniform'
+    adaptation_dropoff: float = 0.9999
+    warmup_fit_kwargs: dict = None
+
+    def __post_init__(self):
+        if self.train_distribution not in ('bounded_geom_approx', 'bounded_geom', 'uniform'):
+            raise ValueError(self.train_distribution)
+        if self.warmup_fit_kwargs is None:
+            self.warmup_fit_kwargs = dict(early_stopping=True, early_stopping_threshold=50, keep_best_weights=True,
+                                          n_samples=1, n_epochs=500, lr=0.05, check_for_divergences=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# statistics
+# ---------------------------------------------------------------------------------------------------------------
+class MomentSums:
+    """sum f(x) over every (iteration, chain) pair seen so far, in fp64; E[f(x)] = sum / n_seen."""
+
+    def __init__(self, event_shape):
+        self.event_shape = tuple(event_shape)
+        d = int(math.prod(self.event_shape))
+        self.sum_x = torch.zeros(d, dtype=torch.float64)
+        self.sum_x2 = torch.zeros(d, dtype=torch.float64)
+        self.n_seen = 0
+
+    def add_sums(self, sum_x: torch.Tensor, sum_x2: torch.Tensor, count: int):
+        self.sum_x += sum_x.detach().to("cpu", torch.float64).reshape(-1)
+        self.sum_x2 += sum_x2.detach().to("cpu", torch.float64).reshape(-1)
+        self.n_seen += int(count)
+
+    def update(self, x: torch.Tensor):
+        """Accumulate a block ``[k, n, *event]`` or ``[n, *event]`` (API compatibility with
+        ``MCMCExpectationDict.update``, base.py:110-113)."""
+        k = len(self.event_shape)
+        flat = x.detach().reshape(-1, *x.shape[x.ndim - k:]).reshape(-1, self.sum_x.numel()).to(torch.float64)
+        self.add_sums(flat.sum(0), flat.square().sum(0), flat.shape[0])
+
+    def reset(self):
+        self.sum_x.zero_()
+        self.sum_x2.zero_()
+        self.n_seen = 0
+
+    def first(self):
+        if self.n_seen == 0:
+            return 0.0
+        return (self.sum_x / self.n_seen).to(torch.float32).reshape(self.event_shape)
+
+    def second(self):
+        if self.n_seen == 0:
+            return 0.0
+        return (self.sum_x2 / self.n_seen).to(torch.float32).reshape(self.event_shape)
+
+    # dict-style access used by callers of the reference API: expectations['first_moment'].as_tensor()
+    class _View:
+        def __init__(self, fn):
+            self._fn = fn
+
+        def as_tensor(self):
+            return self._fn()
+
+    def __getitem__(self, key):
+        if key == 'first_moment':
+            return MomentSums._View(self.first)
+        if key == 'second_moment':
+            return MomentSums._View(self.second)
+        raise KeyError(key)
+
+    def as_tensor(self):
+        return {'first_moment': self.first(), 'second_moment': self.second()}
+
+
+@dataclass
+class MCMCStatistics:
+    event_shape: Union[Tuple[int, ...], torch.Size]
+    n_accepted_trajectories: Optional[int] = 0
+    n_attempted_trajectories: Optional[int] = 0
+    n_divergences: Optional[int] = 0
+    n_target_gradient_calls: Optional[int] = 0
+    n_target_calls: Optional[int] = 0
+    elapsed_time_seconds: Optional[float] = 0.0
+    data_transform: callable = lambda v: v
+    expectations: MomentSums = None
+
+    def __post_init__(self):
+        self.expectations = MomentSums(self.event_shape)
+
+    def update_counters(self, n_accepted_trajectories: int = 0, n_attempted_trajectories: int = 0,
+                        n_divergences: int = 0, n_target_gradient_calls: int = 0, n_target_calls: int = 0):
+        self.n_accepted_trajectories = int(self.n_accepted_trajectories + n_accepted_trajectories)
+        self.n_attempted_trajectories = int(self.n_attempted_trajectories + n_attempted_trajectories)
+        self.n_divergences = int(self.n_divergences + n_divergences)
+        self.n_target_gradient_calls = int(self.n_target_gradient_calls + n_target_gradient_calls)
+        self.n_target_calls = int(self.n_target_calls + n_target_calls)
+
+    def update_elapsed_time(self, delta_time_seconds: float):
+        self.elapsed_time_seconds = float(self.elapsed_time_seconds + delta_time_seconds)
+
+    @property
+    def running_first_moment(self):
+        return self.expectations.first()
+
+    @property
+    def running_second_moment(self):
+        return self.expectations.second()
+
+    @property
+    def running_variance(self):
+        return self.running_second_moment - self.running_first_moment ** 2
+
+    @property
+    def acceptance_rate(self):
+        if self.n_attempted_trajectories == 0:
+            return torch.nan
+        return self.n_accepted_trajectories / self.n_attempted_trajectories
+
+    @property
+    def calls_per_second(self):
+        return self.n_target_calls / self.elapsed_time_seconds if self.elapsed_time_seconds > 0 else torch.nan
+
+    @property
+    def grads_per_second(self):
+        return self.n_target_gradient_calls / self.elapsed_time_seconds if self.elapsed_time_seconds > 0 else torch.nan
+
+    def __repr__(self):
+        return (f"acc-rate: {self.acceptance_rate:.2f}, kcalls/s: {self.calls_per_second / 1000:.2f}, "
+                f"kgrads/s: {self.grads_per_second / 1000:.2f}, divergences: {self.n_divergences}")
+
+    def __dict__(self):
+        return dict(n_accepted_trajectories=self.n_accepted_trajectories,
+                    n_attempted_trajectories=self.n_attempted_trajectories, n_divergences=self.n_divergences,
+                    n_target_gradient_calls=self.n_target_gradient_calls, n_target_calls=self.n_target_calls,
+                    elapsed_time_seconds=self.elapsed_time_seconds, grads_per_second=self.grads_per_second,
+                    acceptance_rate=self.acceptance_rate, calls_per_second=self.calls_per_second)
+
+
+@dataclass
+class JumpNFMCStatistics(MCMCStatistics):
+    n_accepted_jumps: int = 0
+    n_attempted_jumps: int = 0
+
+    @property
+    def jump_acceptance_rate(self):
+        if self.n_attempted_jumps == 0:
+            return torch.nan
+        return self.n_accepted_jumps / self.n_attempted_jumps
+
+    def update_counters(self, n_accepted_jumps: int = 0, n_attempted_jumps: int = 0, **kwargs):
+        super().update_counters(**kwargs)
+        self.n_accepted_jumps = int(self.n_accepted_jumps + n_accepted_jumps)
+        self.n_attempted_jumps = int(self.n_attempted_jumps + n_attempted_jumps)
+
+    def __repr__(self):
+        return (f"MCMC acc-rate: {self.acceptance_rate:.2f}, Jump acc-rate: {self.jump_acceptance_rate:.2f}, "
+                f"kcalls/s: {self.calls_per_second / 1000:.2f}, kgrads/s: {self.grads_per_second / 1000:.2f}, "
+                f"divergences: {self.n_divergences}")
+
+    def __dict__(self):
+        return {**super().__dict__(), 'jump_acceptance_rate': self.jump_acceptance_rate}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# samples and output
+# ---------------------------------------------------------------------------------------------------------------
+@dataclass
+class MCMCSamples:
+    event_shape: Union[Tuple[int, ...], torch.Size]
+    store_samples: bool = True
+    n_samples: int = 0
+    last_sample: torch.Tensor = None
+    thinning: int = 1
+    seen_samples: int = 0
+    max_samples: int = None
+    _blocks: List[torch.Tensor] = field(default_factory=list)   # each [k, n, *event], host
+
+    def __getitem__(self, index):
+        if index == -1 or index == self.n_samples - 1:
+            return self.last_sample
+        return self.as_tensor()[index]
+
+    def add(self, x: torch.Tensor, already_thinned: bool = False, n_seen: Optional[int] = None):
+        """Append a block ``[k, n, *event]`` or one state ``[n, *event]`` (reference: base.py:234-263).
+        ``already_thinned``: the device sink applied the thinning rule; ``n_seen`` = steps the block stands for."""
+        k = len(self.event_shape)
+        if x.ndim == k + 1 and tuple(x.shape[1:]) == tuple(self.event_shape):
+            x = x[None]
+        elif not (x.ndim == k + 2 and tuple(x.shape[2:]) == tuple(self.event_shape)):
+            raise ValueError(f"Expected x.shape[1:] or x.shape[2:] to be {self.event_shape}, got {x.shape = }")
+        if not already_thinned or len(x) > 0:
+            self.last_sample = x[-1].detach().clone() if len(x) else self.last_sample
+        if not self.store_samples:
+            return
+        if already_thinned:
+            kept = x
+            self.seen_samples += int(n_seen if n_seen is not None else len(x))
+        else:
+            idx = torch.arange(self.seen_samples, self.seen_samples + len(x))
+            kept = x[(idx % self.thinning) == 0]
+            self.seen_samples += len(x)
+        if len(kept):
+            self._blocks.append(kept.detach().cpu())
+            self.n_samples += len(kept)
+        if self.max_samples is not None and self.n_samples > self.max_samples:
+            full = torch.cat(self._blocks, dim=0)[-self.max_samples:]
+            self._blocks = [full]
+            self.n_samples = len(full)
+
+    def as_tensor(self) -> torch.Tensor:
+        if len(self._blocks) > 1:
+            self._blocks = [torch.cat(self._blocks, dim=0)]
+        return self._blocks[0]
+
+    def reset(self):
+        self._blocks = []
+        self.n_samples = 0
+
+
+@dataclass
+class MCMCOutput:
+    event_shape: Union[Tuple[int, ...], torch.Size]
+    running_samples: MCMCSamples = None
+    statistics: Optional[MCMCStatistics] = None
+    kernel: Optional[MCMCKernel] = None
+    store_samples: bool = True
+    max_samples: int = None
+
+    def __post_init__(self):
+        if self.running_samples is None:
+            self.running_samples = MCMCSamples(self.event_shape, store_samples=self.store_samples,
+                                               max_samples=self.max_samples)
+        if self.statistics is None:
+            self.statistics = MCMCStatistics(self.event_shape)
+
+    @property
+    def samples(self) -> Union[torch.Tensor, None]:
+        if not self.store_samples:
+            return None
+        return self.running_samples.as_tensor()
+
+    def resample(self, n: int) -> torch.Tensor:
+        flat = self.samples.flatten(0, 1)
+        return flat[torch.randint(low=0, high=len(flat), size=(n,))]
+
+    @property
+    def mean(self):
+        return self.statistics.running_first_moment
+
+    @property
+    def variance(self):
+        return self.statistics.running_second_moment - self.statistics.running_first_moment ** 2
+
+    @property
+    def second_moment(self):
+        return self.statistics.running_second_moment
+
+
+class JumpNFMCOutput(MCMCOutput):
+    def __init__(self, event_shape, *args, **kwargs):
+        kwargs['statistics'] = JumpNFMCStatistics(event_shape)
+        super().__init__(event_shape, *args, **kwargs)

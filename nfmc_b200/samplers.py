@@ -1,0 +1,563 @@
+"""Sampler objects with the reference's names and operator contract, driving the sm_100a kernels.
+
+``Sampler.sample(x0, show_progress=True, time_limit_seconds=None) -> MCMCOutput`` and ``.warmup(...)`` are the
+contract of ``/root/reference/nfmc/algorithms/sampling/base.py:317-348``.  The loop bodies these classes
+replace are ``mcmc/base.py:69-99`` (local loop), ``nfmc/jump.py:173-243`` (Jump NFMC), ``nfmc/imh.py:216-252``
+(fixed IMH), ``nfmc/imh.py:122-178`` (adaptive IMH) and ``nfmc/neutra.py:116-129`` (NeuTra).  Chain state
+lives on the GPU for the whole call; results come back as the reference's own record types with host tensors.
+
+Counter formulas (checked against the reference in tests): MALA ``calls = grads = 2n`` per step
+(langevin.py:116-120, ``n`` when unadjusted); HMC ``calls = 2Ln + 2n``, ``grads = 2Ln`` (hmc.py:122-125);
+jump ``calls += 2n``, ``attempted_jumps += n`` (jump.py:214-216,236-239); fixed IMH ``calls += 2n``
+(imh.py:243-247); adaptive IMH books them as gradient calls (imh.py:146, quirk Q3).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import time
+from copy import deepcopy
+from typing import Optional, Tuple, Union
+
+import torch
+
+from . import _native as N
+from .flow import Flow
+from .potentials import Potential, resolve_target
+from .records import (HMCKernel, HMCParameters, IMHKernel, IMHParameters, JumpNFMCOutput, JumpNFMCParameters,
+                      LangevinKernel, LangevinParameters, MCMCKernel, MCMCOutput, MCMCParameters, MetropolisKernel,
+                      MetropolisParameters, NeuTraKernel, NeuTraParameters, NFMCKernel)
+
+try:  # progress bars are optional
+    from tqdm import tqdm
+except Exception:  # pragma: no cover
+    tqdm = None
+
+MAX_DEVICE_SAMPLE_BYTES = 8 << 30  # device-side sample buffer per launch group
+
+
+def _progress(it, desc, show):
+    if show and tqdm is not None:
+        return tqdm(it, desc=desc)
+    return it
+
+
+def draw_seed() -> int:
+    """Philox seed taken from torch's global generator, so ``torch.manual_seed`` makes runs reproducible."""
+    return int(torch.randint(0, 2 ** 62, (), dtype=torch.int64))
+
+
+class DeviceSession:
+    """Device-resident state of one ``sample()`` call: chains, statistics accumulators, RNG counters, timing."""
+
+    def __init__(self, x0: torch.Tensor, event_shape, device=None, seed: Optional[int] = None, chain0: int = 0):
+        self.device = N.require_cuda(device if device is not None else (x0.device if x0.is_cuda else None))
+        self.event_shape = tuple(event_shape)
+        self.d = int(math.prod(self.event_shape))
+        self.n = int(x0.shape[0])
+        self.x = N.dev_f32(x0, self.device).reshape(self.n, self.d).clone()
+        self.moments = torch.zeros(2 * self.d, device=self.device, dtype=torch.float64)
+        self.counts = torch.zeros(8, device=self.device, dtype=torch.int64)   # [0:4] local, [4:8] jump
+        self.seed = draw_seed() if seed is None else int(seed)
+        self.chain0 = int(chain0)
+        self.local_step = 0   # global index of the next local step (Philox stream 0)
+        self.flow_step = 0    # global index of the next flow draw (Philox stream 1)
+        self.stream = N.stream_ptr(self.device)
+        self._t0 = torch.cuda.Event(enable_timing=True)
+        self._t1 = torch.cuda.Event(enable_timing=True)
+        self._keep = []
+
+    # -- descriptors ------------------------------------------------------------------------------------------
+    def stats(self, jump: bool = False) -> N.StatsDesc:
+        base = self.counts.data_ptr() + (32 if jump else 0)
+        return N.StatsDesc(self.moments.data_ptr(), self.moments.data_ptr() + 8 * self.d, base)
+
+    def sink(self, buf: Optional[torch.Tensor], seen0: int, thinning: int) -> Optional[N.SinkDesc]:
+        if buf is None:
+            return None
+        return N.SinkDesc(buf.data_ptr(), seen0, thinning)
+
+    def tic(self):
+        self._t0.record(torch.cuda.current_stream(self.device))
+
+    def toc(self) -> float:
+        self._t1.record(torch.cuda.current_stream(self.device))
+        self._t1.synchronize()
+        return self._t0.elapsed_time(self._t1) * 1e-3
+
+    def read_back(self):
+        """(sum_x, sum_x2, counts) on the host -- one synchronising copy."""
+        m = self.moments.cpu()
+        c = self.counts.cpu()
+        return m[: self.d], m[self.d:], [int(v) for v in c]
+
+
+def _imd_device(kernel: MetropolisKernel, device) -> Optional[torch.Tensor]:
+    return None if kernel.has_unit_mass() else N.dev_f32(kernel.inv_mass_diag, device)
+
+
+def _rows_kept(seen0: int, k: int, thinning: int) -> int:
+    first = (seen0 + thinning - 1) // thinning
+    last = (seen0 + k + thinning - 1) // thinning
+    return last - first
+
+
+class Sampler:
+    def __init__(self, event_shape, target, kernel: MCMCKernel, params: MCMCParameters):
+        self.event_shape = tuple(event_shape)
+        self.event_size = int(math.prod(self.event_shape))
+        self.target = resolve_target(target, self.event_shape)
+        self.kernel = kernel
+        self.params = params
+        self.seed: Optional[int] = None      # fixed Philox seed (None: drawn from torch's global generator per call)
+        self.chain0: int = 0                 # global index of this process's first chain (multi-GPU sharding)
+        self.device = None
+
+    @property
+    def name(self):
+        return "Generic sampler"
+
+    def warmup(self, x0, show_progress=True, time_limit_seconds=None) -> MCMCOutput:
+        raise NotImplementedError
+
+    def sample(self, x0, show_progress=True, time_limit_seconds=None) -> MCMCOutput:
+        raise NotImplementedError
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# local samplers
+# ---------------------------------------------------------------------------------------------------------------
+class MetropolisSampler(Sampler):
+    """Generic local loop (reference: MCMCSampler.sample, mcmc/base.py:56-102) over a fused K-step kernel."""
+
+    #: how many steps one launch may fuse when nothing has to be observed in between
+    max_fused_steps = 1 << 20
+
+    def _launch(self, ses: DeviceSession, n_steps: int, sink, normals=None, uniforms=None):
+        raise NotImplementedError
+
+    def _calls_grads(self, n: int) -> Tuple[int, int]:
+        raise NotImplementedError
+
+    def run_steps(self, ses: DeviceSession, out: MCMCOutput, n_steps: int, store: bool, normals=None, uniforms=None):
+        """Advance all chains ``n_steps`` local steps; book rows / counters into ``out``.  Returns device rows or None."""
+        rs = out.running_samples
+        buf = None
+        sink = None
+        if store:
+            rows = _rows_kept(rs.seen_samples, n_steps, rs.thinning)
+            nbytes = rows * ses.n * ses.d * 4
+            if nbytes > MAX_DEVICE_SAMPLE_BYTES:
+                raise MemoryError(f"storing {rows} x {ses.n} x {ses.d} samples needs {nbytes / 2**30:.1f} GiB on the "
+                                  f"device; use params.store_samples=False (moments and last_sample are still returned)")
+            buf = torch.empty(rows, ses.n, ses.d, device=ses.device, dtype=torch.float32)
+            sink = ses.sink(buf, rs.seen_samples, rs.thinning)
+        self._launch(ses, n_steps, sink, normals, uniforms)
+        ses.local_step += n_steps
+        calls, grads = self._calls_grads(ses.n)
+        out.statistics.update_counters(n_target_calls=calls * n_steps, n_target_gradient_calls=grads * n_steps)
+        return buf
+
+    def update_kernel_from_device(self, ses: DeviceSession, acc_rate: float):
+        """Warm-up adaptation (reference: MetropolisSampler.update_kernel, mcmc/base.py:142-161)."""
+        p: MetropolisParameters = self.params
+        k: MetropolisKernel = self.kernel
+        if ses.n > 1 and p.tune_inv_mass_diag:
+            var = torch.var(ses.x, dim=0).cpu()            # unbiased, across chains, per dimension
+            k.inv_mass_diag = p.imd_adjustment * var + (1 - p.imd_adjustment) * k.inv_mass_diag
+        if p.tune_step_size and p.adjustment:
+            k.da.step(k.da_params.target_acceptance_rate - acc_rate)
+            k.step_size = k.da.value
+
+    def sample(self, x0: torch.Tensor, show_progress: bool = True, time_limit_seconds=None) -> MCMCOutput:
+        event_shape = tuple(x0.shape[1:])
+        out = MCMCOutput(event_shape, store_samples=self.params.store_samples)
+        ses = DeviceSession(x0, event_shape, self.device, self.seed, self.chain0)
+        T = int(self.params.n_iterations)
+        tuning = bool(self.params.tuning)
+        chunk = 1 if (tuning or time_limit_seconds is not None or show_progress) else min(T, self.max_fused_steps)
+        done = 0
+        label = f'{self.name} (tuning)' if tuning else self.name
+        bar = _progress(range(0, T, max(chunk, 1)), label, show_progress)
+        prev_acc = 0
+        for start in bar:
+            if time_limit_seconds is not None and out.statistics.elapsed_time_seconds > time_limit_seconds:
+                break
+            k = min(chunk, T - start)
+            ses.tic()
+            buf = self.run_steps(ses, out, k, self.params.store_samples)
+            dt = ses.toc()
+            out.statistics.update_elapsed_time(dt)
+            if buf is not None:
+                out.running_samples.add(buf.reshape(-1, ses.n, *event_shape), already_thinned=True, n_seen=k)
+            done += k
+            if tuning:
+                acc = int(ses.counts[0])
+                self.update_kernel_from_device(ses, (acc - prev_acc) / (ses.n * k))
+                prev_acc = acc
+        self._finish(ses, out, done)
+        out.kernel = self.kernel
+        return out
+
+    def _finish(self, ses: DeviceSession, out: MCMCOutput, steps_done: int):
+        sx, sx2, cnt = ses.read_back()
+        out.statistics.expectations.add_sums(sx, sx2, ses.n * steps_done)
+        out.statistics.update_counters(n_accepted_trajectories=cnt[0], n_attempted_trajectories=cnt[1])
+        out.statistics.n_nonfinite = cnt[2]
+        out.running_samples.last_sample = ses.x.reshape(ses.n, *out.event_shape).cpu()
+
+    def warmup(self, x0, show_progress=True, time_limit_seconds=None) -> MCMCOutput:
+        """Reference: MCMCSampler.warmup (mcmc/base.py:39-54): tune on a copy, adopt its kernel."""
+        cp = deepcopy(self)
+        cp.params.tuning_mode()
+        cp.params.n_iterations = self.params.n_warmup_iterations
+        out = cp.sample(x0, show_progress=show_progress, time_limit_seconds=time_limit_seconds)
+        self.kernel = cp.kernel
+        new_params = cp.params
+        new_params.n_iterations = self.params.n_iterations
+        self.params = new_params
+        self.params.sampling_mode()
+        return out
+
+
+class Langevin(MetropolisSampler):
+    def __init__(self, event_shape, target, kernel: Optional[LangevinKernel] = None,
+                 params: Optional[LangevinParameters] = None):
+        es = int(math.prod(tuple(event_shape)))
+        super().__init__(event_shape, target, kernel or LangevinKernel(event_size=es), params or LangevinParameters())
+
+    @property
+    def name(self):
+        return 'LMC'
+
+    def _calls_grads(self, n):
+        return (2 * n, 2 * n) if self.params.adjustment else (n, n)
+
+    def _launch(self, ses, n_steps, sink, normals=None, uniforms=None):
+        pot, keep = self.target.descriptor(ses.device)
+        imd = _imd_device(self.kernel, ses.device)
+        rng = N.rng_desc(ses.seed, ses.local_step, normals, uniforms)
+        st = ses.stats()
+        N.check(N.lib().nfmc_mala_steps(C.byref(pot), N.ptr(ses.x), ses.n, n_steps, float(self.kernel.step_size),
+                                        N.ptr(imd), int(bool(self.params.adjustment)), C.byref(rng), ses.chain0,
+                                        C.byref(st), None if sink is None else C.byref(sink), ses.stream))
+
+
+class MALA(Langevin):
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.params.adjustment = True
+
+
+class ULA(Langevin):
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.params.adjustment = False
+
+
+class HMC(MetropolisSampler):
+    def __init__(self, event_shape, target, kernel: Optional[HMCKernel] = None, params: Optional[HMCParameters] = None):
+        es = int(math.prod(tuple(event_shape)))
+        super().__init__(event_shape, target, kernel or HMCKernel(event_size=es), params or HMCParameters())
+
+    @property
+    def name(self):
+        return 'HMC'
+
+    def _calls_grads(self, n):
+        L = int(self.kernel.n_leapfrog_steps)
+        return (2 * L * n + (2 * n if self.params.adjustment else 0), 2 * L * n)
+
+    def _launch(self, ses, n_steps, sink, normals=None, uniforms=None):
+        pot, keep = self.target.descriptor(ses.device)
+        imd = _imd_device(self.kernel, ses.device)
+        rng = N.rng_desc(ses.seed, ses.local_step, normals, uniforms)
+        st = ses.stats()
+        N.check(N.lib().nfmc_hmc_steps(C.byref(pot), N.ptr(ses.x), ses.n, n_steps, float(self.kernel.step_size),
+                                       int(self.kernel.n_leapfrog_steps), N.ptr(imd), int(bool(self.params.adjustment)),
+                                       C.byref(rng), ses.chain0, C.byref(st),
+                                       None if sink is None else C.byref(sink), ses.stream))
+
+
+class UHMC(HMC):
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.params.adjustment = False
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Jump NFMC
+# ---------------------------------------------------------------------------------------------------------------
+class JumpNFMC(Sampler):
+    """K local steps, then one flow-proposal MH jump for every chain, T times (reference: nfmc/jump.py:156-246)."""
+
+    def __init__(self, event_shape, target, inner_sampler: MetropolisSampler, kernel: NFMCKernel = None,
+                 params: JumpNFMCParameters = None):
+        super().__init__(event_shape, target, kernel or NFMCKernel(tuple(event_shape)), params or JumpNFMCParameters())
+        self.inner_sampler = inner_sampler
+
+    @property
+    def name(self):
+        return 'Jump MCMC'
+
+    def jump(self, ses: DeviceSession, sink=None, z=None, uniforms=None):
+        flow: Flow = self.kernel.flow
+        pot, keep = self.target.descriptor(ses.device)
+        fd, keep2 = flow.bijection.descriptor(ses.device)
+        rng = N.rng_desc(ses.seed, ses.flow_step, z, uniforms)
+        st = ses.stats(jump=True)
+        N.check(N.lib().nfmc_jump_step(C.byref(pot), C.byref(fd), N.ptr(ses.x), ses.n,
+                                       int(bool(self.params.adjusted_jumps)), C.byref(rng), ses.chain0, C.byref(st),
+                                       None if sink is None else C.byref(sink), ses.stream))
+        ses.flow_step += 1
+
+    def sample(self, x0: torch.Tensor, show_progress: bool = True, time_limit_seconds=None,
+               normals=None, uniforms=None, jump_z=None, jump_uniforms=None) -> MCMCOutput:
+        """``normals [T,K,n,d]`` / ``uniforms [T,K,n]`` / ``jump_z [T,n,d]`` / ``jump_uniforms [T,n]`` optionally inject
+        the random numbers (parity tests); otherwise they come from the Philox generator."""
+        p: JumpNFMCParameters = self.params
+        inner = self.inner_sampler
+        if not inner.params.store_samples:
+            raise ValueError("Inner sampler in jump HMC must store samples")     # reference: jump.py:163-164
+        if p.fit_nf:
+            raise NotImplementedError("fit_nf=True needs on-device flow training (SURVEY.md section 8f rank 2)")
+        event_shape = tuple(x0.shape[1:])
+        out = JumpNFMCOutput(event_shape=event_shape, store_samples=p.store_samples)
+        ses = DeviceSession(x0, event_shape, self.device, self.seed, self.chain0)
+        K = int(inner.params.n_iterations)
+        T = int(p.n_iterations)
+        store = bool(p.store_samples)
+        rs = out.running_samples
+        done = 0
+        dev = ses.device
+        for i in _progress(range(T), 'Jump MCMC', show_progress):
+            if time_limit_seconds is not None and out.statistics.elapsed_time_seconds >= time_limit_seconds:
+                break
+            ses.tic()
+            nz = None if normals is None else N.dev_f32(normals[i], dev)
+            un = None if uniforms is None else N.dev_f32(uniforms[i], dev)
+            buf = inner.run_steps(ses, out, K, store, nz, un)                       # jump.py:178-189
+            jbuf = None
+            jsink = None
+            if store:
+                seen = rs.seen_samples + K
+                if _rows_kept(seen, 1, rs.thinning):
+                    jbuf = torch.empty(1, ses.n, ses.d, device=dev, dtype=torch.float32)
+                    jsink = ses.sink(jbuf, seen, rs.thinning)
+            jz = None if jump_z is None else N.dev_f32(jump_z[i], dev).reshape(1, ses.n, ses.d)
+            ju = None if jump_uniforms is None else N.dev_f32(jump_uniforms[i], dev).reshape(1, ses.n)
+            self.jump(ses, jsink, jz, ju)                                            # jump.py:203-243
+            if p.adjusted_jumps:
+                out.statistics.update_counters(n_target_calls=2 * ses.n)             # jump.py:214-216
+            out.statistics.update_elapsed_time(ses.toc())
+            if store:
+                rs.add(buf.reshape(-1, ses.n, *event_shape), already_thinned=True, n_seen=K)
+                if jbuf is not None:
+                    rs.add(jbuf.reshape(-1, ses.n, *event_shape), already_thinned=True, n_seen=1)
+                else:
+                    rs.seen_samples += 1
+            done += 1
+        sx, sx2, cnt = ses.read_back()
+        out.statistics.expectations.add_sums(sx, sx2, ses.n * done * (K + 1))
+        out.statistics.update_counters(n_accepted_trajectories=cnt[0], n_attempted_trajectories=cnt[1],
+                                       n_accepted_jumps=cnt[4], n_attempted_jumps=cnt[5])
+        out.statistics.n_nonfinite = cnt[2] + cnt[6]
+        rs.last_sample = ses.x.reshape(ses.n, *event_shape).cpu()
+        out.kernel = self.kernel
+        return out
+
+    def warmup(self, x0, show_progress=True, time_limit_seconds=None) -> MCMCOutput:
+        """Inner-sampler warm-up (step size, mass); the flow-fitting half of the reference's warm-up
+        (jump.py:124-151) needs on-device training and is not done."""
+        limit = None if time_limit_seconds is None else 0.7 * time_limit_seconds
+        self.inner_sampler.params.store_samples = True
+        return self.inner_sampler.warmup(x0, show_progress=show_progress, time_limit_seconds=limit)
+
+
+def _make_inner(cls, event_shape, target, kernel, params):
+    return cls(event_shape, target, kernel, params)
+
+
+class JumpMALA(JumpNFMC):
+    def __init__(self, event_shape, target, kernel=None, params=None, inner_kernel=None, inner_params=None):
+        super().__init__(event_shape, target, MALA(event_shape, target, inner_kernel, inner_params), kernel, params)
+
+
+class JumpULA(JumpNFMC):
+    def __init__(self, event_shape, target, kernel=None, params=None, inner_kernel=None, inner_params=None):
+        super().__init__(event_shape, target, ULA(event_shape, target, inner_kernel, inner_params), kernel, params)
+
+
+class JumpHMC(JumpNFMC):
+    def __init__(self, event_shape, target, kernel=None, params=None, inner_kernel=None, inner_params=None):
+        super().__init__(event_shape, target, HMC(event_shape, target, inner_kernel, inner_params), kernel, params)
+
+
+class JumpUHMC(JumpNFMC):
+    def __init__(self, event_shape, target, kernel=None, params=None, inner_kernel=None, inner_params=None):
+        super().__init__(event_shape, target, UHMC(event_shape, target, inner_kernel, inner_params), kernel, params)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# independence Metropolis-Hastings
+# ---------------------------------------------------------------------------------------------------------------
+class AbstractIMH(Sampler):
+    recompute_logq = False
+
+    def __init__(self, event_shape, target, kernel: Optional[IMHKernel] = None, params: Optional[IMHParameters] = None):
+        super().__init__(event_shape, target, kernel or IMHKernel(tuple(event_shape)), params or IMHParameters())
+
+    def warmup(self, x0, show_progress=True, time_limit_seconds=None) -> MCMCOutput:
+        """The reference fits the flow variationally (imh.py:67-72); training is not on the device yet, so
+        warm-up only draws the initial state from the flow as the reference does afterwards (imh.py:73-75)."""
+        out = MCMCOutput(event_shape=tuple(x0.shape[1:]), store_samples=self.params.store_samples)
+        out.running_samples.add(self.kernel.flow.sample(x0.shape[0]).cpu())
+        return out
+
+    def _run(self, x0, show_progress, time_limit_seconds, store, z=None, uniforms=None) -> MCMCOutput:
+        event_shape = tuple(x0.shape[1:])
+        out = MCMCOutput(event_shape=event_shape, store_samples=store)
+        flow: Flow = self.kernel.flow
+        ses = DeviceSession(x0, event_shape, self.device, self.seed, self.chain0)
+        dev = ses.device
+        T = int(self.params.n_iterations)
+        pot, keep = self.target.descriptor(dev)
+        fd, keep2 = flow.bijection.descriptor(dev)
+        logq = torch.empty(ses.n, device=dev, dtype=torch.float32)
+        ses.tic()
+        if not self.recompute_logq:                                                  # imh.py:214
+            N.check(N.lib().nfmc_flow_log_prob(C.byref(fd), N.ptr(ses.x), N.ptr(logq), ses.n, ses.stream))
+        out.statistics.update_elapsed_time(ses.toc())
+        chunk = 1 if (time_limit_seconds is not None or show_progress) else T
+        rs = out.running_samples
+        done = 0
+        for start in _progress(range(0, T, max(chunk, 1)), self.name, show_progress):
+            if time_limit_seconds is not None and out.statistics.elapsed_time_seconds >= time_limit_seconds:
+                break
+            k = min(chunk, T - start)
+            buf, sink = None, None
+            if store:
+                rows = _rows_kept(rs.seen_samples, k, rs.thinning)
+                if rows * ses.n * ses.d * 4 > MAX_DEVICE_SAMPLE_BYTES:
+                    raise MemoryError("sample buffer too large for the device; use store_samples=False")
+                buf = torch.empty(rows, ses.n, ses.d, device=dev, dtype=torch.float32)
+                sink = ses.sink(buf, rs.seen_samples, rs.thinning)
+            zz = None if z is None else N.dev_f32(z[start:start + k], dev)
+            uu = None if uniforms is None else N.dev_f32(uniforms[start:start + k], dev)
+            rng = N.rng_desc(ses.seed, ses.flow_step, zz, uu)
+            st = ses.stats()
+            ses.tic()
+            N.check(N.lib().nfmc_imh_steps(C.byref(pot), C.byref(fd), N.ptr(ses.x), N.ptr(logq), ses.n, k,
+                                           int(self.recompute_logq), C.byref(rng), ses.chain0, C.byref(st),
+                                           None if sink is None else C.byref(sink), ses.stream))
+            out.statistics.update_elapsed_time(ses.toc())
+            ses.flow_step += k
+            done += k
+            if buf is not None:
+                rs.add(buf.reshape(-1, ses.n, *event_shape), already_thinned=True, n_seen=k)
+        sx, sx2, cnt = ses.read_back()
+        out.statistics.expectations.add_sums(sx, sx2, ses.n * done)
+        out.statistics.update_counters(n_accepted_trajectories=cnt[0], n_attempted_trajectories=cnt[1])
+        if self.recompute_logq:
+            out.statistics.update_counters(n_target_gradient_calls=2 * ses.n * done)  # imh.py:146 (quirk Q3)
+        else:
+            out.statistics.update_counters(n_target_calls=2 * ses.n * done)           # imh.py:243-247
+        rs.last_sample = ses.x.reshape(ses.n, *event_shape).cpu()
+        out.kernel = self.kernel
+        return out
+
+
+class FixedIMH(AbstractIMH):
+    @property
+    def name(self):
+        return "Fixed IMH"
+
+    def sample(self, x0, show_progress=True, time_limit_seconds=None, z=None, uniforms=None) -> MCMCOutput:
+        return self._run(x0, show_progress, time_limit_seconds, self.params.store_samples, z, uniforms)
+
+
+class AdaptiveIMH(AbstractIMH):
+    """Adaptive IMH with the adaptation switched off: the flow-refit step of the reference (imh.py:152-175)
+    needs on-device training.  The MH part follows imh.py:122-150: log q(x) is
+    recomputed every iteration and samples are always stored (quirk Q2)."""
+    recompute_logq = True
+
+    @property
+    def name(self):
+        return "Adaptive IMH"
+
+    def sample(self, x0, show_progress=True, time_limit_seconds=None, z=None, uniforms=None) -> MCMCOutput:
+        return self._run(x0, show_progress, time_limit_seconds, True, z, uniforms)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# NeuTra
+# ---------------------------------------------------------------------------------------------------------------
+class NeuTraHMC(Sampler):
+    """HMC in the flow's latent space on U~(z) = U(T^-1 z) - log|det dT^-1/dz| (reference: nfmc/neutra.py:36-144).
+    Samples and moments are latent-space quantities, exactly as the reference returns them (quirk Q1)."""
+
+    def __init__(self, event_shape, target, inner_kernel: HMCKernel = None, inner_params: HMCParameters = None,
+                 kernel: NeuTraKernel = None, params: NeuTraParameters = None):
+        es = int(math.prod(tuple(event_shape)))
+        super().__init__(event_shape, target, kernel or NeuTraKernel(tuple(event_shape)), params or NeuTraParameters())
+        self.inner_kernel = inner_kernel or HMCKernel(event_size=es)
+        self.inner_params = inner_params or HMCParameters()
+        self.inner_params.n_iterations = self.params.n_iterations
+
+    @property
+    def name(self):
+        return "NeuTra HMC"
+
+    def sample(self, x0, show_progress=True, time_limit_seconds=None, normals=None, uniforms=None) -> MCMCOutput:
+        event_shape = tuple(x0.shape[1:])
+        store = bool(self.params.store_samples)
+        out = MCMCOutput(event_shape, store_samples=store)
+        ses = DeviceSession(x0, event_shape, self.device, self.seed, self.chain0)
+        dev = ses.device
+        T = int(self.params.n_iterations)
+        L = int(self.inner_kernel.n_leapfrog_steps)
+        pot, keep = self.target.descriptor(dev)
+        fd, keep2 = self.kernel.flow.bijection.descriptor(dev)
+        imd = _imd_device(self.inner_kernel, dev)
+        chunk = 1 if (time_limit_seconds is not None or show_progress) else T
+        rs = out.running_samples
+        done = 0
+        for start in _progress(range(0, T, max(chunk, 1)), self.name, show_progress):
+            if time_limit_seconds is not None and out.statistics.elapsed_time_seconds > time_limit_seconds:
+                break
+            k = min(chunk, T - start)
+            buf, sink = None, None
+            if store:
+                rows = _rows_kept(rs.seen_samples, k, rs.thinning)
+                if rows * ses.n * ses.d * 4 > MAX_DEVICE_SAMPLE_BYTES:
+                    raise MemoryError("sample buffer too large for the device; use store_samples=False")
+                buf = torch.empty(rows, ses.n, ses.d, device=dev, dtype=torch.float32)
+                sink = ses.sink(buf, rs.seen_samples, rs.thinning)
+            nz = None if normals is None else N.dev_f32(normals[start:start + k], dev)
+            un = None if uniforms is None else N.dev_f32(uniforms[start:start + k], dev)
+            rng = N.rng_desc(ses.seed, ses.local_step, nz, un)
+            st = ses.stats()
+            ses.tic()
+            N.check(N.lib().nfmc_neutra_hmc_steps(C.byref(pot), C.byref(fd), N.ptr(ses.x), ses.n, k,
+                                                  float(self.inner_kernel.step_size), L, N.ptr(imd), C.byref(rng),
+                                                  ses.chain0, C.byref(st), None if sink is None else C.byref(sink),
+                                                  ses.stream))
+            out.statistics.update_elapsed_time(ses.toc())
+            ses.local_step += k
+            done += k
+            if buf is not None:
+                rs.add(buf.reshape(-1, ses.n, *event_shape), already_thinned=True, n_seen=k)
+        sx, sx2, cnt = ses.read_back()
+        out.statistics.expectations.add_sums(sx, sx2, ses.n * done)
+        out.statistics.update_counters(n_accepted_trajectories=cnt[0], n_attempted_trajectories=cnt[1],
+                                       n_target_calls=(2 * L + 2) * ses.n * done,
+                                       n_target_gradient_calls=2 * L * ses.n * done)   # hmc.py:122-125
+        rs.last_sample = ses.x.reshape(ses.n, *event_shape).cpu()
+        out.kernel = self.inner_kernel
+        out.kernel.flow = self.kernel.flow                                              # neutra.py:128
+        return out
+
+    def warmup(self, x0, show_progress=True, time_limit_seconds=None) -> MCMCOutput:
+        raise NotImplementedError("NeuTra warm-up = variational flow fit + latent HMC tuning (neutra.py:70-107); "
+                                  "flow training on the device is the next scope row (SURVEY.md section 8f)")

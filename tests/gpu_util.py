@@ -1,0 +1,35 @@
+"""Helpers for the GPU parity tests: product objects that mirror an oracle / golden case."""
+import math
+
+import torch
+
+import nfmc_b200
+from nfmc_b200 import potentials as P
+from nfmc_b200.flow import Flow, RealNVP
+from nfmc_b200.records import MCMCOutput
+from nfmc_b200.samplers import DeviceSession
+
+
+def product_flow_from_oracle(oflow) -> Flow:
+    bij = oflow.bijection
+    cpl = [l for l in bij.layers if hasattr(l, "net")]
+    ck = dict(n_layers=cpl[0].n_linear, n_hidden=cpl[0].n_hidden) if cpl else None
+    f = Flow(RealNVP(bij.event_shape, n_layers=bij.n_coupling, conditioner_kwargs=ck))
+    missing = f.load_state_dict(oflow.state_dict(), strict=True)
+    return f.to("cuda").eval()
+
+
+def product_target(name, d):
+    return P.make_potential(str(name), (d,))
+
+
+def run_local_injected(sampler, x0, normals, uniforms, store=True):
+    """K steps of a local sampler with injected noise; returns (samples [K,n,d] on host, session, output)."""
+    K = normals.shape[0]
+    out = MCMCOutput(tuple(x0.shape[1:]), store_samples=store)
+    ses = DeviceSession(x0, tuple(x0.shape[1:]), None, seed=0)
+    dev = ses.device
+    buf = sampler.run_steps(ses, out, K, store, normals.to(dev).contiguous(), uniforms.to(dev).contiguous())
+    torch.cuda.synchronize()
+    sx, sx2, cnt = ses.read_back()
+    return (None if buf is None else buf.cpu()), ses, (sx, sx2, cnt)

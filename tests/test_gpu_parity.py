@@ -1,0 +1,395 @@
+"""B200: the CUDA path (called through the C ABI via nfmc_b200) against the CPU oracle on identical inputs.
+
+Tolerances (BASELINE.json north_star): flow outputs, log-dets, potentials and proposals within rtol 1e-4 (fp32);
+accept / reject decisions agree except for ties within tolerance of the threshold.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import load_case, tape, oracle_flow, oracle_target, CASES
+from oracle import samplers_ref as R
+from oracle.philox_ref import step_noise
+from oracle.potentials_ref import make_potential_ref
+from oracle.realnvp_ref import make_flow
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def close(a, b, rtol=RTOL, atol=1e-5):
+    a, b = torch.as_tensor(a).float().cpu(), torch.as_tensor(b).float().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    assert bool((err <= tol).all()), f"max err {float(err.max()):.3e}, worst tol ratio {float((err / tol).max()):.2f}"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# potentials
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["g0", "g1", "fn", "rb", "gm"])
+@pytest.mark.parametrize("d", [2, 6, 26, 100, 1000])
+def test_potential_value_and_grad(name, d):
+    from gpu_util import product_target
+    torch.manual_seed(d)
+    n = 37
+    x = 0.7 * torch.randn(n, d)
+    ref = make_potential_ref(name, (d,))
+    u_ref, g_ref = R.value_and_grad(ref, x)
+    u, g = product_target(name, d).value_and_grad(x.cuda())
+    scale = 1e-5 * max(1.0, float(u_ref.abs().max()))
+    close(u, u_ref, atol=scale)
+    close(g, g_ref, atol=1e-5 * max(1.0, float(g_ref.abs().max())))
+
+
+def test_potential_odd_dims():
+    from gpu_util import product_target
+    for name in ["g0", "g1", "fn", "gm"]:
+        for d in [3, 7, 25, 101]:
+            x = torch.randn(11, d)
+            u_ref, g_ref = R.value_and_grad(make_potential_ref(name, (d,)), x)
+            u, g = product_target(name, d).value_and_grad(x.cuda())
+            close(u, u_ref, atol=1e-5 * max(1.0, float(u_ref.abs().max())))
+            close(g, g_ref, atol=1e-5 * max(1.0, float(g_ref.abs().max())))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# RealNVP
+# ------------------------------------------------------------------------------------------------------------
+FLOW_CASES = [
+    (6, 2, None), (7, 3, dict(n_layers=3, n_hidden=6)), (8, 1, dict(n_layers=1)), (25, 2, None), (100, 2, None),
+    (100, 4, dict(n_layers=2, n_hidden=64)), (101, 3, dict(n_layers=4, n_hidden=17)), (64, 2, dict(n_layers=2, n_hidden=32)),
+    (1000, 2, None), (9, 3, dict(n_layers=1)),
+]
+
+
+@pytest.mark.parametrize("d,n_layers,ck", FLOW_CASES)
+def test_realnvp_forward_inverse_logprob(d, n_layers, ck):
+    from gpu_util import product_flow_from_oracle
+    torch.manual_seed(d + n_layers)
+    oflow = make_flow((d,), n_layers=n_layers, conditioner_kwargs=ck, perturb=0.1, seed=d)
+    flow = product_flow_from_oracle(oflow)
+    n = 45
+    x = torch.randn(n, d)
+    with torch.no_grad():
+        z_ref, ld_ref = oflow.bijection.forward(x)
+        xi_ref, ldi_ref = oflow.bijection.inverse(x)
+        lp_ref = oflow.log_prob(x)
+    z, ld = flow.bijection.forward(x.cuda())
+    close(z, z_ref)
+    close(ld, ld_ref, atol=1e-4)
+    xi, ldi = flow.bijection.inverse(x.cuda())
+    close(xi, xi_ref, atol=1e-5 * max(1.0, float(xi_ref.abs().max())))
+    close(ldi, ldi_ref, atol=1e-4)
+    close(flow.log_prob(x.cuda()), lp_ref, atol=1e-4 * max(1.0, float(lp_ref.abs().max()) / 100))
+    # round trip on the device
+    xr, ldr = flow.bijection.inverse(z)
+    close(xr, x, atol=2e-5 * max(1.0, float(x.abs().max())))
+    close(ld + ldr, torch.zeros(n), atol=2e-4)
+
+
+@pytest.mark.parametrize("d,n_layers,ck", [(6, 2, None), (7, 3, dict(n_layers=3, n_hidden=6)), (100, 2, None), (25, 3, None)])
+def test_flow_sample_with_injected_base_draw(d, n_layers, ck):
+    from gpu_util import product_flow_from_oracle
+    oflow = make_flow((d,), n_layers=n_layers, conditioner_kwargs=ck, perturb=0.1, seed=d + 1)
+    flow = product_flow_from_oracle(oflow)
+    torch.manual_seed(3)
+    z = torch.randn(33, d)
+    x_ref, lq_ref = R.flow_sample_with_logq(oflow, 33, R.TapeDraws([z], []))
+    x, lq = flow.sample(33, return_log_prob=True, z=z)
+    close(x, x_ref, atol=1e-5 * max(1.0, float(x_ref.abs().max())))
+    close(lq, lq_ref, atol=1e-4 * max(1.0, float(lq_ref.abs().max()) / 100))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# golden cases (outputs of the unmodified reference) with the reference's own random draws injected
+# ------------------------------------------------------------------------------------------------------------
+def _golden_local(name, kind):
+    from gpu_util import product_target, run_local_injected
+    from nfmc_b200.records import LangevinKernel, LangevinParameters, HMCKernel, HMCParameters
+    from nfmc_b200.samplers import MALA, HMC
+    g = load_case(name)
+    d = g["x0"].shape[1]
+    K = int(g["K"])
+    imd = torch.from_numpy(g["imd"])
+    tgt = product_target(g["pot"], d)
+    if kind == "mala":
+        s = MALA((d,), tgt, LangevinKernel(event_size=d, inv_mass_diag=imd, step_size=float(g["step"])), LangevinParameters())
+    else:
+        s = HMC((d,), tgt, HMCKernel(event_size=d, inv_mass_diag=imd, step_size=float(g["step"]), n_leapfrog_steps=int(g["L"])),
+                HMCParameters())
+    normals = torch.stack(g["normals"])
+    uniforms = torch.stack(g["uniforms"])
+    samples, ses, (sx, sx2, cnt) = run_local_injected(s, torch.from_numpy(g["x0"]), normals, uniforms)
+    ref = torch.from_numpy(g["samples"])
+    close(samples, ref, atol=1e-5 * max(1.0, float(ref.abs().max())))
+    acc, att = int(g["counters"][0]), int(g["counters"][1])
+    assert (cnt[0], cnt[1]) == (acc, att)
+    n_seen = ref.shape[0] * ref.shape[1]
+    close(sx / n_seen, g["mean"], atol=1e-5)
+    close(sx2 / n_seen, g["second_moment"], atol=1e-5 * max(1.0, float(np.abs(g["second_moment"]).max())))
+
+
+@pytest.mark.parametrize("name", ["mala_g0", "mala_fn"])
+def test_golden_mala(name):
+    _golden_local(name, "mala")
+
+
+@pytest.mark.parametrize("name", ["hmc_g1", "hmc_rb"])
+def test_golden_hmc(name):
+    _golden_local(name, "hmc")
+
+
+def _check_output(out, g, jump=False):
+    ref = torch.from_numpy(g["samples"])
+    close(out.samples, ref, atol=2e-5 * max(1.0, float(ref.abs().max())))
+    close(out.running_samples.last_sample, g["last"], atol=2e-5 * max(1.0, float(ref.abs().max())))
+    close(out.mean, g["mean"], atol=2e-5)
+    close(out.second_moment, g["second_moment"], atol=2e-5 * max(1.0, float(np.abs(g["second_moment"]).max())))
+    acc, att, div, grads, calls, jacc, jatt = (int(v) for v in g["counters"])
+    st = out.statistics
+    assert (st.n_accepted_trajectories, st.n_attempted_trajectories, st.n_divergences) == (acc, att, div)
+    assert (st.n_target_gradient_calls, st.n_target_calls) == (grads, calls)
+    if jump:
+        assert (st.n_accepted_jumps, st.n_attempted_jumps) == (jacc, jatt)
+
+
+@pytest.mark.parametrize("name,inner", [("jump_mala_g0", "mala"), ("jump_hmc_gm", "hmc")])
+def test_golden_jump(name, inner):
+    from gpu_util import product_target, product_flow_from_oracle
+    from nfmc_b200.records import (LangevinKernel, LangevinParameters, HMCKernel, HMCParameters, NFMCKernel,
+                                   JumpNFMCParameters)
+    from nfmc_b200.samplers import JumpMALA, JumpHMC
+    g = load_case(name)
+    n, d = g["x0"].shape
+    T, K = int(g["T"]), int(g["K"])
+    tgt = product_target(g["pot"], d)
+    flow = product_flow_from_oracle(oracle_flow(g))
+    if inner == "mala":
+        s = JumpMALA((d,), tgt, kernel=NFMCKernel((d,), flow=flow), params=JumpNFMCParameters(n_iterations=T),
+                     inner_kernel=LangevinKernel(event_size=d, step_size=float(g["step"])),
+                     inner_params=LangevinParameters(n_iterations=K))
+    else:
+        s = JumpHMC((d,), tgt, kernel=NFMCKernel((d,), flow=flow), params=JumpNFMCParameters(n_iterations=T),
+                    inner_kernel=HMCKernel(event_size=d, step_size=float(g["step"]), n_leapfrog_steps=int(g["L"])),
+                    inner_params=HMCParameters(n_iterations=K))
+    # reference draw order per outer iteration: K x [normal(n,d), uniform(n)], normal(n,d) [flow base], uniform(n)
+    nn, uu = g["normals"], g["uniforms"]
+    normals = torch.stack([torch.stack(nn[i * (K + 1): i * (K + 1) + K]) for i in range(T)])
+    uniforms = torch.stack([torch.stack(uu[i * (K + 1): i * (K + 1) + K]) for i in range(T)])
+    jump_z = torch.stack([nn[i * (K + 1) + K] for i in range(T)])
+    jump_u = torch.stack([uu[i * (K + 1) + K] for i in range(T)])
+    out = s.sample(torch.from_numpy(g["x0"]), show_progress=False, normals=normals, uniforms=uniforms, jump_z=jump_z,
+                   jump_uniforms=jump_u)
+    _check_output(out, g, jump=True)
+
+
+def test_golden_fixed_imh():
+    from gpu_util import product_target, product_flow_from_oracle
+    from nfmc_b200.records import IMHKernel, IMHParameters
+    from nfmc_b200.samplers import FixedIMH
+    g = load_case("imh_rb")
+    n, d = g["x0"].shape
+    T = int(g["T"])
+    s = FixedIMH((d,), product_target(g["pot"], d), IMHKernel((d,), flow=product_flow_from_oracle(oracle_flow(g))),
+                 IMHParameters(n_iterations=T))
+    out = s.sample(torch.from_numpy(g["x0"]), show_progress=False, z=torch.stack(g["normals"]), uniforms=torch.stack(g["uniforms"]))
+    _check_output(out, g)
+
+
+def test_golden_neutra_hmc():
+    from gpu_util import product_target, product_flow_from_oracle
+    from nfmc_b200.records import HMCKernel, HMCParameters, NeuTraKernel, NeuTraParameters
+    from nfmc_b200.samplers import NeuTraHMC
+    g = load_case("neutra_hmc_fn")
+    n, d = g["x0"].shape
+    T = int(g["T"])
+    s = NeuTraHMC((d,), product_target(g["pot"], d), HMCKernel(event_size=d, step_size=float(g["step"]), n_leapfrog_steps=int(g["L"])),
+                  HMCParameters(), NeuTraKernel((d,), flow=product_flow_from_oracle(oracle_flow(g))), NeuTraParameters(n_iterations=T))
+    out = s.sample(torch.from_numpy(g["x0"]), show_progress=False, normals=torch.stack(g["normals"]),
+                   uniforms=torch.stack(g["uniforms"]))
+    _check_output(out, g)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# NeuTra latent potential and its hand-written gradient against autograd through the oracle flow
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,n_layers,ck,pot", [(6, 2, None, "fn"), (7, 3, dict(n_layers=3, n_hidden=6), "gm"),
+                                               (100, 2, None, "g1"), (25, 3, None, "g0"), (9, 2, dict(n_layers=1), "g0"),
+                                               (64, 2, dict(n_layers=2, n_hidden=32), "rb")])
+def test_neutra_potential_and_gradient(d, n_layers, ck, pot):
+    from gpu_util import product_flow_from_oracle, product_target
+    from nfmc_b200 import _native as N
+    oflow = make_flow((d,), n_layers=n_layers, conditioner_kwargs=ck, perturb=0.1, seed=d + 7)
+    flow = product_flow_from_oracle(oflow)
+    tgt_ref = make_potential_ref(pot, (d,))
+    tgt = product_target(pot, d)
+    torch.manual_seed(d)
+    n = 29
+    z = 0.5 * torch.randn(n, d)
+    u_ref, g_ref = R.value_and_grad(R.neutra_potential(oflow, tgt_ref), z)
+    dev = torch.device("cuda")
+    zd = z.to(dev).contiguous()
+    u = torch.empty(n, device=dev)
+    gr = torch.empty(n, d, device=dev)
+    pd, k1 = tgt.descriptor(dev)
+    fd, k2 = flow.bijection.descriptor(dev)
+    N.check(N.lib().nfmc_neutra_potential(C.byref(pd), C.byref(fd), N.ptr(zd), N.ptr(u), N.ptr(gr), n, N.stream_ptr(dev)))
+    close(u, u_ref, atol=1e-5 * max(1.0, float(u_ref.abs().max())))
+    close(gr, g_ref, atol=2e-5 * max(1.0, float(g_ref.abs().max())))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Philox path
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d", [6, 25, 100, 1000])
+def test_philox_fill_matches_numpy(d):
+    from nfmc_b200 import _native as N
+    dev = torch.device("cuda")
+    n, steps, seed, chain0, step0 = 50, 3, 0x1234567890ABCDEF, 1000, 5
+    for stream in (0, 1):
+        nz = torch.empty(steps, n, d, device=dev)
+        un = torch.empty(steps, n, device=dev)
+        rng = N.rng_desc(seed, step0, None, None)
+        N.check(N.lib().nfmc_rng_fill(C.byref(rng), stream, chain0, d, n, steps, N.ptr(nz), N.ptr(un), N.stream_ptr(dev)))
+        for k in range(steps):
+            z_ref, u_ref = step_noise(seed, stream, step0 + k, chain0, n, d)
+            np.testing.assert_array_equal(un[k].cpu().numpy(), u_ref)              # bits -> uniform: exact
+            err = np.abs(nz[k].cpu().numpy().astype(np.float64) - z_ref)
+            assert err.max() < 2e-5, err.max()                                        # MUFU approximations
+
+
+def test_philox_mode_equals_injected_mode():
+    """The fused kernel drawing its own Philox numbers == the same kernel fed those numbers (d=100, K=6)."""
+    from gpu_util import product_target, run_local_injected
+    from nfmc_b200 import _native as N
+    from nfmc_b200.records import LangevinKernel, LangevinParameters, MCMCOutput
+    from nfmc_b200.samplers import MALA, DeviceSession
+    dev = torch.device("cuda")
+    d, n, K, seed = 100, 300, 6, 99
+    torch.manual_seed(0)
+    x0 = torch.randn(n, d)
+    s = MALA((d,), product_target("g1", d), LangevinKernel(event_size=d, step_size=0.002), LangevinParameters())
+    out = MCMCOutput((d,), store_samples=True)
+    ses = DeviceSession(x0, (d,), None, seed=seed)
+    buf = s.run_steps(ses, out, K, True)
+    nz = torch.empty(K, n, d, device=dev)
+    un = torch.empty(K, n, device=dev)
+    rng = N.rng_desc(seed, 0, None, None)
+    N.check(N.lib().nfmc_rng_fill(C.byref(rng), 0, 0, d, n, K, N.ptr(nz), N.ptr(un), N.stream_ptr(dev)))
+    samples_inj, ses2, stats2 = run_local_injected(s, x0, nz, un)
+    assert torch.equal(buf.cpu(), samples_inj)
+    assert ses.read_back()[2][:2] == stats2[2][:2]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# larger batches: decisions agree except ties, moments agree, ragged tail tiles
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,pot,d,n,K", [("mala", "g1", 100, 1031, 5), ("mala", "gm", 25, 517, 8), ("hmc", "g1", 100, 773, 3),
+                                            ("hmc", "fn", 26, 300, 3), ("mala", "g0", 1000, 67, 3)])
+def test_local_kernels_against_oracle(kind, pot, d, n, K):
+    from gpu_util import product_target, run_local_injected
+    from nfmc_b200.records import LangevinKernel, LangevinParameters, HMCKernel, HMCParameters
+    from nfmc_b200.samplers import MALA, HMC
+    torch.manual_seed(n)
+    x0 = 0.3 * torch.randn(n, d)
+    normals = torch.randn(K, n, d)
+    uniforms = torch.rand(K, n)
+    ref_t = make_potential_ref(pot, (d,))
+    imd = torch.ones(d)
+    if kind == "mala":
+        tau = {"g1": 0.004, "gm": 0.1, "g0": 0.02}[pot]
+        run = R.run_mala(x0, ref_t, tau, imd, K, R.TapeDraws(list(normals), list(uniforms)), trace=True)
+        s = MALA((d,), product_target(pot, d), LangevinKernel(event_size=d, step_size=tau), LangevinParameters())
+    else:
+        tau, L = (0.03, 6) if pot == "g1" else (0.05, 5)
+        run = R.run_hmc(x0, ref_t, tau, imd, L, K, R.TapeDraws(list(normals), list(uniforms)), trace=True)
+        s = HMC((d,), product_target(pot, d), HMCKernel(event_size=d, step_size=tau, n_leapfrog_steps=L), HMCParameters())
+    samples, ses, (sx, sx2, cnt) = run_local_injected(s, x0, normals, uniforms)
+    ref = run.samples
+    # chains whose every decision had a clear margin must match to tolerance; ties may flip a decision
+    lr = torch.stack(run.trace["log_ratio"])                           # [K, n]
+    margin = (lr - torch.log(uniforms)).abs().min(dim=0).values
+    clear = margin > 1e-3 * (1.0 + lr.abs().max(dim=0).values)
+    assert clear.float().mean() > 0.97
+    close(samples[:, clear], ref[:, clear], atol=2e-5 * max(1.0, float(ref.abs().max())))
+    assert abs(cnt[0] - run.n_accepted) <= int((~clear).sum()) * K
+    assert cnt[1] == run.n_attempted
+    if bool(clear.all()):
+        close(sx / (n * K), run.mean, atol=1e-5 * max(1.0, float(ref.abs().max())))
+
+
+def test_jump_and_imh_against_oracle_large():
+    from gpu_util import product_target, product_flow_from_oracle
+    from nfmc_b200.records import IMHKernel, IMHParameters
+    from nfmc_b200.samplers import FixedIMH
+    d, n, T = 100, 1500, 4
+    oflow = make_flow((d,), n_layers=2, perturb=0.05, seed=11)
+    flow = product_flow_from_oracle(oflow)
+    torch.manual_seed(5)
+    x0 = torch.randn(n, d)
+    z = torch.randn(T, n, d)
+    u = torch.rand(T, n)
+    run = R.run_fixed_imh(x0, make_potential_ref("g0", (d,)), oflow, T, R.TapeDraws(list(z), list(u)), trace=True)
+    s = FixedIMH((d,), product_target("g0", d), IMHKernel((d,), flow=flow), IMHParameters(n_iterations=T))
+    out = s.sample(x0, show_progress=False, z=z, uniforms=u)
+    la = torch.stack(run.trace["log_alpha"])
+    clear = ((la - torch.log(u)).abs().min(dim=0).values > 1e-3 * (1 + la.abs().max(dim=0).values))
+    assert clear.float().mean() > 0.97
+    close(out.samples[:, clear], run.samples[:, clear], atol=2e-5 * max(1.0, float(run.samples.abs().max())))
+    assert abs(out.statistics.n_accepted_trajectories - run.n_accepted) <= int((~clear).sum()) * T
+
+
+# ------------------------------------------------------------------------------------------------------------
+# statistical correctness at scale (size-independent properties)
+# ------------------------------------------------------------------------------------------------------------
+def test_mala_moments_converge_on_gaussian():
+    """MALA leaves N(0, 1/w) invariant: after burn-in the pooled moments match the target's."""
+    import nfmc_b200
+    from nfmc_b200.potentials import DiagonalGaussian
+    torch.manual_seed(0)
+    d, n = 100, 16384
+    w = torch.linspace(0.5, 4.0, d)
+    out = nfmc_b200.sample(DiagonalGaussian((d,), w), strategy="mala", n_chains=n, n_iterations=400, show_progress=False,
+                           x0=torch.randn(n, d) / w.sqrt(), param_kwargs=dict(store_samples=False), kernel_kwargs=dict(step_size=0.05))
+    assert out.samples is None
+    var = out.variance
+    assert float((var * w - 1).abs().max()) < 0.03
+    assert float(out.mean.abs().max()) < 0.02
+    assert 0.5 < out.statistics.acceptance_rate < 1.0
+
+
+def test_jump_mala_full_size_properties():
+    """BASELINE-size run (2^17 chains, d=100): counters follow the reference formulas, state finite, G-invariance of
+    the Philox stream (a shard run with chain0 offset reproduces the corresponding rows)."""
+    import nfmc_b200
+    from nfmc_b200.potentials import StandardGaussian
+    from nfmc_b200.flow import create_flow_object
+    d, n, T, K = 100, 1 << 17, 2, 10
+    torch.manual_seed(1)
+    x0 = torch.randn(n, d)
+    flow = create_flow_object("realnvp", (d,))
+    with torch.no_grad():
+        for p in flow.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    s = nfmc_b200.create_sampler(StandardGaussian((d,)), flow=flow, strategy="jump_mala",
+                                 param_kwargs=dict(n_iterations=T, store_samples=False), inner_param_kwargs=dict(n_iterations=K))
+    s.seed = 1234
+    out = s.sample(x0, show_progress=False)
+    st = out.statistics
+    assert st.n_attempted_trajectories == n * T * K and st.n_attempted_jumps == n * T
+    assert st.n_target_calls == 2 * n * K * T + 2 * n * T and st.n_target_gradient_calls == 2 * n * K * T
+    assert st.expectations.n_seen == n * T * (K + 1)
+    last = out.running_samples.last_sample
+    assert last.shape == (n, d) and bool(torch.isfinite(last).all())
+    # shard [4096, 8192) run on its own with chain0 = 4096
+    s2 = nfmc_b200.create_sampler(StandardGaussian((d,)), flow=flow, strategy="jump_mala",
+                                  param_kwargs=dict(n_iterations=T, store_samples=False), inner_param_kwargs=dict(n_iterations=K))
+    s2.seed, s2.chain0 = 1234, 4096
+    out2 = s2.sample(x0[4096:8192], show_progress=False)
+    assert torch.equal(out2.running_samples.last_sample, last[4096:8192])
