@@ -15,7 +15,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnfmc_b200.so")
+LIB_PATH = os.environ.get("NFMC_B200_LIB", os.path.join(_HERE, "libnfmc_b200.so"))
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 # ---- enums / structs (mirror include/nfmc_b200.h) ---------------------------------------------------------

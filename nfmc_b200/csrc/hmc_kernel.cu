@@ -6,6 +6,13 @@
 #error "compile with -DNFMC_ONLY_E=<slots per half>"
 #endif
 
+#ifndef NFMC_MALA_MINB
+#define NFMC_MALA_MINB 4
+#endif
+#ifndef NFMC_HMC_MINB
+#define NFMC_HMC_MINB 4
+#endif
+
 namespace nfmc {
 
 // ---------------------------------------------------------------------------------------------------------
@@ -14,7 +21,7 @@ namespace nfmc {
 // the value is identical, so it is computed once and the two half-kicks are still applied separately.
 // ---------------------------------------------------------------------------------------------------------
 template <int POT, int E>
-__global__ void __launch_bounds__(kThreads) hmc_kernel(const LocalArgs A) {
+__global__ void __launch_bounds__(kThreads, NFMC_HMC_MINB) hmc_kernel(const LocalArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ChainArgs& C = A.c;
   const Geom g = make_geom(C.d, C.gs);

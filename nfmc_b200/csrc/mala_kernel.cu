@@ -10,6 +10,13 @@
 #error "compile with -DNFMC_ONLY_E=<slots per half>"
 #endif
 
+#ifndef NFMC_MALA_MINB
+#define NFMC_MALA_MINB 4
+#endif
+#ifndef NFMC_HMC_MINB
+#define NFMC_HMC_MINB 4
+#endif
+
 namespace nfmc {
 
 // per-dimension coefficients in shared memory when the mass is not the identity
@@ -21,7 +28,7 @@ __device__ __forceinline__ float4 mala_coef(float tau, float s2t, float m) {
 }
 
 template <int POT, int E>
-__global__ void __launch_bounds__(kThreads) mala_kernel(const LocalArgs A) {
+__global__ void __launch_bounds__(kThreads, NFMC_MALA_MINB) mala_kernel(const LocalArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ChainArgs& C = A.c;
   const Geom g = make_geom(C.d, C.gs);
