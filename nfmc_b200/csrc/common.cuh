@@ -62,6 +62,30 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
+// round keys precomputed once per kernel (the seed is launch-constant), so the key schedule costs no issue slots
+struct PhiloxKeys {
+  uint32_t k0[10], k1[10];
+};
+__device__ __forceinline__ PhiloxKeys philox_keys(uint64_t seed) {
+  PhiloxKeys K;
+  uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    K.k0[r] = a; K.k1[r] = b;
+    a += 0x9E3779B9u; b += 0xBB67AE85u;
+  }
+  return K;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys& K) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ K.k0[r], lo1, hi0 ^ c.w ^ K.k1[r], lo0);
+  }
+  return c;
+}
+
 // Counter convention (DESIGN.md "random numbers"):
 //   c.x = quad * 32 + j      quad = index of the 4-word block within this (chain, step, stream), j = lane in group
 //   c.y = stream id | (step >> 32) << 8
@@ -85,11 +109,19 @@ __device__ __forceinline__ RngKey make_rng_key(uint64_t seed, uint32_t stream_id
 __device__ __forceinline__ uint4 rng_quad(const RngKey& k, int quad, int j) {
   return philox4x32_10(make_uint4((uint32_t)(quad * 32 + j), k.cy, k.cz, k.cw), k.key);
 }
+__device__ __forceinline__ uint4 rng_quad(const PhiloxKeys& K, const RngKey& k, int quad, int j) {
+  return philox4x32_10(make_uint4((uint32_t)(quad * 32 + j), k.cy, k.cz, k.cw), K);
+}
 
 __device__ __forceinline__ float uniform_from_bits(uint32_t b) {  // [0,1), 24 bits (torch.rand convention)
   return (float)(b >> 8) * 5.9604644775390625e-8f;
 }
 
+__device__ __forceinline__ float fast_lg2(float v) {  // v is a normal float: no denormal fix-up needed
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
 __device__ __forceinline__ float fast_sqrt(float v) {
   float r;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
@@ -100,7 +132,7 @@ __device__ __forceinline__ float fast_sqrt(float v) {
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
   const float u1 = fmaf(__uint2float_rn(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
   const float th = (__uint_as_float(0x3f800000u | (b >> 9)) - 1.5f) * 6.283185307179586f;  // [-pi, pi)
-  const float r = fast_sqrt(-1.3862943611198906f * __log2f(u1));                             // sqrt(-2 ln u1)
+  const float r = fast_sqrt(-1.3862943611198906f * fast_lg2(u1));                             // sqrt(-2 ln u1)
   float s, c;
   __sincosf(th, &s, &c);
   z0 = r * c;
@@ -132,6 +164,14 @@ __device__ __forceinline__ void draw_step_noise(const RngKey& k, int j, StepNois
       if (e0 + 1 < E) box_muller(w.z, w.w, nz.lo[e0 + 1], nz.hi[e0 + 1]);
     }
   }
+}
+
+// slot validity.  In an EXACT layout (ceil(db/gs) == E) slots e < E-1 are valid in both halves for every lane,
+// so only the last slot needs a runtime test; the compiler folds the rest away.
+template <bool EXACT, int E>
+__device__ __forceinline__ bool slot_ok(int e, int k, int n_half) {
+  if (EXACT && e < E - 1) return true;
+  return k < n_half;
 }
 
 // ---- loads / stores between the row-major [n, d] tensor and the register layout -----------------------

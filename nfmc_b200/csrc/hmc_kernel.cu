@@ -1,44 +1,54 @@
 // hmc_kernel.cu -- fused K-step HMC / UHMC kernel (one translation unit per E).
 // Replaces HMC.propose (mcmc/hmc.py:96-126) and the local loop MCMCSampler.sample (mcmc/base.py:69-99).
+//
+//   p = xi / sqrt(m);  L x [ p -= tau/2 grad U(x);  x += tau p m;  p -= tau/2 grad U(x) ];  H = U + 1/2 sum p^2 m
+//
+// The reference evaluates grad U twice at every interior point of the trajectory (end of leapfrog l, start of
+// leapfrog l+1, hmc.py:69-71).  The value is identical, so it is computed once per point (L+1 evaluations) and the
+// two half-kicks are still applied as two separate roundings.  For potentials whose gradient is elementwise
+// (Gaussians, Rosenbrock pairs) no reduction happens inside the trajectory; U is evaluated at its two ends only.
 #include "launchers.cuh"
 
 #ifndef NFMC_ONLY_E
 #error "compile with -DNFMC_ONLY_E=<slots per half>"
 #endif
 
-#ifndef NFMC_MALA_MINB
-#define NFMC_MALA_MINB 4
-#endif
 #ifndef NFMC_HMC_MINB
 #define NFMC_HMC_MINB 4
 #endif
 
 namespace nfmc {
 
-// ---------------------------------------------------------------------------------------------------------
-// HMC: p = xi / sqrt(m); L x [p -= tau/2 g; x += tau p m; p -= tau/2 g]; H = U + 1/2 sum p^2 m   (hmc.py:96-126)
-// The reference evaluates grad U twice at the same point between consecutive leapfrog steps (hmc.py:69-71);
-// the value is identical, so it is computed once and the two half-kicks are still applied separately.
-// ---------------------------------------------------------------------------------------------------------
-template <int POT, int E>
+// FAST: exact layout, Philox noise, identity mass -- all three known at compile time (single straight-line step body).
+// !FAST: inexact layouts, injected noise and non-identity mass handled by run-time (warp-uniform) tests.
+template <int POT, int E, bool FAST>
 __global__ void __launch_bounds__(kThreads, NFMC_HMC_MINB) hmc_kernel(const LocalArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ChainArgs& C = A.c;
   const Geom g = make_geom(C.d, C.gs);
   CtaStats st = cta_stats_init(smem, C.d);
-  float2* coef = reinterpret_cast<float2*>(smem + ((cta_stats_bytes(C.d) + 15) & ~size_t(15)));
-  const bool unit_mass = (A.imd == nullptr);
+  size_t off = (cta_stats_bytes(C.d) + 15) & ~size_t(15);
+  // per-dimension {1/sqrt(m), m, 0, 0} when the mass is not the identity (hmc.py:100,58,104)
+  float4* coef = reinterpret_cast<float4*>(smem + off);
+  const bool unit_mass = FAST ? true : (A.imd == nullptr);
   if (!unit_mass) {
     for (int i = threadIdx.x; i < C.d; i += blockDim.x) {
       const float m = __ldg(A.imd + i);
-      coef[i] = make_float2(__fdiv_rn(1.f, sqrtf(m)), m);
+      coef[i] = make_float4(__fdiv_rn(1.f, sqrtf(m)), m, 0.f, 0.f);
     }
+    off += (size_t)C.d * sizeof(float4);
     __syncthreads();
   }
+  float4* mom = reinterpret_cast<float4*>(smem + off) + threadIdx.x;
   const int cpc = kThreads / C.gs;
   const long long tiles = (C.n + cpc - 1) / cpc;
   const float half_tau = A.tau / 2;
+  constexpr bool EXACT = FAST;
+  const bool inject = FAST ? false : (C.rng.normals != nullptr);
+  const PhiloxKeys PK = philox_keys(C.rng.seed);
   unsigned int n_acc = 0, n_bad = 0;
+  constexpr int NQ = (E + 2) / 2;
+  constexpr bool CTX = pot_grad_needs_ctx<POT>();
 
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const long long chain_raw = tile * cpc + threadIdx.x / C.gs;
@@ -46,80 +56,92 @@ __global__ void __launch_bounds__(kThreads, NFMC_HMC_MINB) hmc_kernel(const Loca
     const long long chain = active ? chain_raw : C.n - 1;
     float* row = C.x + chain * (long long)C.d;
 
-    float lo[E], hi[E], m1lo[E], m1hi[E], m2lo[E], m2hi[E];
+    float lo[E], hi[E];
     load_chain(row, g, lo, hi);
 #pragma unroll
-    for (int e = 0; e < E; ++e) m1lo[e] = m1hi[e] = m2lo[e] = m2hi[e] = 0.f;
+    for (int e = 0; e < E; ++e) mom[e * kThreads] = make_float4(0.f, 0.f, 0.f, 0.f);
     PotCtx ctx = pot_prepare<POT, E>(C.pot, g, lo, hi);
 
     for (int k = 0; k < C.n_steps; ++k) {
-      float plo[E], phi[E];  // momentum
-      uint32_t ubits = 0;
-      {
-        StepNoise<E> nz;
-        if (C.rng.normals) {
-          const float* nr = C.rng.normals + ((long long)k * C.n + chain) * (long long)C.d;
-          load_chain(nr, g, nz.lo, nz.hi);
-          nz.ubits = 0;
-        } else {
-          const RngKey key = make_rng_key(C.rng.seed, 0u, C.rng.step0 + (uint64_t)k, (uint64_t)(C.chain0 + chain));
-          draw_step_noise<E>(key, g.j, nz);
-        }
-        ubits = nz.ubits;
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          const int kk = g.j + g.gs * e;
-          plo[e] = (kk < g.da) ? nz.lo[e] : 0.f;
-          phi[e] = (kk < g.db) ? nz.hi[e] : 0.f;
-          if (!unit_mass) {
-            plo[e] *= coef[min(kk, g.da - 1 < 0 ? 0 : g.da - 1)].x;
-            phi[e] *= coef[g.da + min(kk, g.db - 1)].x;
-          }
-        }
-      }
-      float xlo[E], xhi[E];
+      const RngKey key = make_rng_key(C.rng.seed, 0u, C.rng.step0 + (uint64_t)k, (uint64_t)(C.chain0 + chain));
+      const float* nrow = inject ? C.rng.normals + ((long long)k * C.n + chain) * (long long)C.d : nullptr;
+      float plo[E], phi[E], xlo[E], xhi[E];
       float kin0 = 0.f;
+      uint32_t ubits = 0;
+      // ---- momentum p = xi / sqrt(m) (hmc.py:100), first half-kick with grad U(x0) (hmc.py:51-53) ------------------
 #pragma unroll
-      for (int e = 0; e < E; ++e) {
-        xlo[e] = lo[e];
-        xhi[e] = hi[e];
-        if (unit_mass) { kin0 = fmaf(plo[e], plo[e], fmaf(phi[e], phi[e], kin0)); }
-        else {
+      for (int q = 0; q < NQ; ++q) {
+        uint4 w = make_uint4(0u, 0u, 0u, 0u);
+        if (!inject) w = rng_quad(PK, key, q, g.j);
+        if (q == 0) ubits = w.x;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int e = 2 * q + hh - 1;
+          if (e < 0 || e >= E) continue;
           const int kk = g.j + g.gs * e;
-          kin0 = fmaf(plo[e] * plo[e], coef[min(kk, g.da - 1 < 0 ? 0 : g.da - 1)].y, kin0);
-          kin0 = fmaf(phi[e] * phi[e], coef[g.da + min(kk, g.db - 1)].y, kin0);
+          const bool vl = slot_ok<EXACT, E>(e, kk, g.da), vh = slot_ok<EXACT, E>(e, kk, g.db);
+          float nlo, nhi;
+          if (inject) {
+            nlo = vl ? __ldg(nrow + kk) : 0.f;
+            nhi = vh ? __ldg(nrow + g.da + kk) : 0.f;
+          } else {
+            box_muller(hh ? w.z : w.x, hh ? w.w : w.y, nlo, nhi);
+          }
+          nlo = vl ? nlo : 0.f;
+          nhi = vh ? nhi : 0.f;
+          float ml = 1.f, mh = 1.f;
+          if (!unit_mass) {
+            const float4 cl = coef[vl ? kk : 0], ch = coef[g.da + (vh ? kk : 0)];
+            nlo *= cl.x; nhi *= ch.x;
+            ml = cl.y; mh = ch.y;
+          }
+          kin0 = fmaf(nlo * nlo, ml, fmaf(nhi * nhi, mh, kin0));
+          float glo, ghi;
+          if (EXACT && e < E - 1) pot_grad<POT, true>(C.pot, ctx, g, kk, lo[e], hi[e], glo, ghi);
+          else pot_grad<POT, false>(C.pot, ctx, g, kk, lo[e], hi[e], glo, ghi);
+          plo[e] = (A.n_leapfrog > 0) ? fmaf(-half_tau, glo, nlo) : nlo;
+          phi[e] = (A.n_leapfrog > 0) ? fmaf(-half_tau, ghi, nhi) : nhi;
+          xlo[e] = lo[e];
+          xhi[e] = hi[e];
         }
       }
+      // ---- trajectory (hmc.py:61-77) -----------------------------------------------------------------------------
       PotCtx cur = ctx;
       for (int l = 0; l < A.n_leapfrog; ++l) {
+        const bool more = l + 1 < A.n_leapfrog;
+        if (CTX) {
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-          const int kk = g.j + g.gs * e;
-          float glo, ghi;
-          pot_grad<POT>(C.pot, cur, g, kk, xlo[e], xhi[e], glo, ghi);
-          plo[e] = fmaf(-half_tau, glo, plo[e]);                                     // hmc.py:51-53
-          phi[e] = fmaf(-half_tau, ghi, phi[e]);
-          if (unit_mass) {
-            xlo[e] = fmaf(A.tau, plo[e], xlo[e]);                                    // hmc.py:56-58
-            xhi[e] = fmaf(A.tau, phi[e], xhi[e]);
-          } else {
-            xlo[e] = fmaf(A.tau, plo[e] * coef[min(kk, g.da - 1 < 0 ? 0 : g.da - 1)].y, xlo[e]);
-            xhi[e] = fmaf(A.tau, phi[e] * coef[g.da + min(kk, g.db - 1)].y, xhi[e]);
+          for (int e = 0; e < E; ++e) {
+            const int kk = g.j + g.gs * e;
+            const bool vl = slot_ok<EXACT, E>(e, kk, g.da), vh = slot_ok<EXACT, E>(e, kk, g.db);
+            float ml = 1.f, mh = 1.f;
+            if (!unit_mass) { ml = coef[vl ? kk : 0].y; mh = coef[g.da + (vh ? kk : 0)].y; }
+            xlo[e] = vl ? fmaf(A.tau, unit_mass ? plo[e] : plo[e] * ml, xlo[e]) : 0.f;      // hmc.py:56-58
+            xhi[e] = vh ? fmaf(A.tau, unit_mass ? phi[e] : phi[e] * mh, xhi[e]) : 0.f;
           }
-          if (kk >= g.da) xlo[e] = 0.f;
-          if (kk >= g.db) xhi[e] = 0.f;
+          cur = pot_prepare<POT, E>(C.pot, g, xlo, xhi);
         }
-        cur = pot_prepare<POT, E>(C.pot, g, xlo, xhi);
 #pragma unroll
         for (int e = 0; e < E; ++e) {
           const int kk = g.j + g.gs * e;
+          const bool vl = slot_ok<EXACT, E>(e, kk, g.da), vh = slot_ok<EXACT, E>(e, kk, g.db);
+          if (!CTX) {
+            float ml = 1.f, mh = 1.f;
+            if (!unit_mass) { ml = coef[vl ? kk : 0].y; mh = coef[g.da + (vh ? kk : 0)].y; }
+            xlo[e] = vl ? fmaf(A.tau, unit_mass ? plo[e] : plo[e] * ml, xlo[e]) : 0.f;
+            xhi[e] = vh ? fmaf(A.tau, unit_mass ? phi[e] : phi[e] * mh, xhi[e]) : 0.f;
+          }
           float glo, ghi;
-          pot_grad<POT>(C.pot, cur, g, kk, xlo[e], xhi[e], glo, ghi);
-          plo[e] = (kk < g.da) ? fmaf(-half_tau, glo, plo[e]) : 0.f;
-          phi[e] = (kk < g.db) ? fmaf(-half_tau, ghi, phi[e]) : 0.f;
+          if (EXACT && e < E - 1) pot_grad<POT, true>(C.pot, cur, g, kk, xlo[e], xhi[e], glo, ghi);
+          else pot_grad<POT, false>(C.pot, cur, g, kk, xlo[e], xhi[e], glo, ghi);
+          float pl = fmaf(-half_tau, glo, plo[e]), ph = fmaf(-half_tau, ghi, phi[e]);       // second half-kick
+          if (more) { pl = fmaf(-half_tau, glo, pl); ph = fmaf(-half_tau, ghi, ph); }         // next step's first
+          plo[e] = vl ? pl : 0.f;
+          phi[e] = vh ? ph : 0.f;
         }
       }
       bool accept = true;
+      if (!CTX && A.n_leapfrog > 0) cur = pot_prepare<POT, E>(C.pot, g, xlo, xhi);
       if (A.adjusted) {
         float kin1 = 0.f;
 #pragma unroll
@@ -127,8 +149,8 @@ __global__ void __launch_bounds__(kThreads, NFMC_HMC_MINB) hmc_kernel(const Loca
           if (unit_mass) { kin1 = fmaf(plo[e], plo[e], fmaf(phi[e], phi[e], kin1)); }
           else {
             const int kk = g.j + g.gs * e;
-            kin1 = fmaf(plo[e] * plo[e], coef[min(kk, g.da - 1 < 0 ? 0 : g.da - 1)].y, kin1);
-            kin1 = fmaf(phi[e] * phi[e], coef[g.da + min(kk, g.db - 1)].y, kin1);
+            const bool vl = slot_ok<EXACT, E>(e, kk, g.da), vh = slot_ok<EXACT, E>(e, kk, g.db);
+            kin1 = fmaf(plo[e] * plo[e], coef[vl ? kk : 0].y, fmaf(phi[e] * phi[e], coef[g.da + (vh ? kk : 0)].y, kin1));
           }
         }
         const float h0 = ctx.u + 0.5f * group_sum(kin0, g.gs);                        // hmc.py:103-106
@@ -144,17 +166,29 @@ __global__ void __launch_bounds__(kThreads, NFMC_HMC_MINB) hmc_kernel(const Loca
       for (int e = 0; e < E; ++e) {
         lo[e] = accept ? xlo[e] : lo[e];
         hi[e] = accept ? xhi[e] : hi[e];
+        float4 m = mom[e * kThreads];
+        m.x += lo[e];
+        m.y += hi[e];
+        m.z = fmaf(lo[e], lo[e], m.z);
+        m.w = fmaf(hi[e], hi[e], m.w);
+        mom[e * kThreads] = m;
       }
       ctx = select_ctx(accept, cur, ctx);
       if (accept && g.j == 0 && active) ++n_acc;
-      accumulate_moments(lo, hi, m1lo, m1hi, m2lo, m2hi);
       if (C.sink.samples && active) sink_store(C.sink, g, C.n, chain, k, lo, hi);
     }
-    if (!active) {
 #pragma unroll
-      for (int e = 0; e < E; ++e) m1lo[e] = m1hi[e] = m2lo[e] = m2hi[e] = 0.f;
+    for (int e = 0; e < E; ++e) {
+      float4 m = mom[e * kThreads];
+      if (!active) m = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int kk = g.j + g.gs * e;
+      const float a = across_groups_sum(m.x, g.gs), b = across_groups_sum(m.y, g.gs);
+      const float c = across_groups_sum(m.z, g.gs), dd = across_groups_sum(m.w, g.gs);
+      if (g.lane < g.gs) {
+        if (kk < g.da) { atomicAdd(st.sx + kk, (double)a); atomicAdd(st.sx2 + kk, (double)c); }
+        if (kk < g.db) { atomicAdd(st.sx + g.da + kk, (double)b); atomicAdd(st.sx2 + g.da + kk, (double)dd); }
+      }
     }
-    flush_moments(g, m1lo, m1hi, m2lo, m2hi, st.sx, st.sx2);
     if (active) store_chain(row, g, lo, hi);
   }
   n_acc = __reduce_add_sync(0xffffffffu, n_acc);
@@ -174,15 +208,19 @@ __global__ void __launch_bounds__(kThreads, NFMC_HMC_MINB) hmc_kernel(const Loca
   cta_stats_finish(st, C.stats, C.d);
 }
 
-
 template <int E>
-int launch_hmc(int pot_kind, const LocalArgs& A, int grid, size_t smem, cudaStream_t s) {
+int launch_hmc(int pot_kind, bool exact, const LocalArgs& A, int grid, size_t smem, cudaStream_t s) {
   NFMC_DISPATCH_POT(pot_kind, {
-    NFMC_SET_SMEM_RET((hmc_kernel<POT, E>), smem);
-    hmc_kernel<POT, E><<<grid, kThreads, smem, s>>>(A);
+    if (exact && !A.c.rng.normals && !A.imd) {
+      NFMC_SET_SMEM_RET((hmc_kernel<POT, E, true>), smem);
+      hmc_kernel<POT, E, true><<<grid, kThreads, smem, s>>>(A);
+    } else {
+      NFMC_SET_SMEM_RET((hmc_kernel<POT, E, false>), smem);
+      hmc_kernel<POT, E, false><<<grid, kThreads, smem, s>>>(A);
+    }
   });
   return check_cuda(cudaGetLastError(), "hmc_kernel launch");
 }
-template int launch_hmc<NFMC_ONLY_E>(int, const LocalArgs&, int, size_t, cudaStream_t);
+template int launch_hmc<NFMC_ONLY_E>(int, bool, const LocalArgs&, int, size_t, cudaStream_t);
 
 }  // namespace nfmc

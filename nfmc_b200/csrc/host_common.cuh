@@ -13,8 +13,9 @@ int check_cuda(cudaError_t e, const char* what);
 int sm_count();
 
 struct Layout {
-  int gs;  // lanes per chain
-  int E;   // slots per half (template value)
+  int gs;      // lanes per chain
+  int E;       // slots per half (template value)
+  bool exact;  // ceil(db / gs) == E: every slot below the last is valid in both halves for every lane
 };
 // smallest power-of-two group such that ceil(db / gs) <= 16, then the smallest instantiated E that fits
 inline bool layout_for_dim(int d, Layout& L) {
@@ -26,6 +27,7 @@ inline bool layout_for_dim(int d, Layout& L) {
   const int e = (db + gs - 1) / gs;
   L.gs = gs;
   L.E = e <= 4 ? 4 : e <= 7 ? 7 : e <= 13 ? 13 : 16;
+  L.exact = (e == L.E);
   return true;
 }
 

@@ -38,8 +38,8 @@ struct NeutraArgs {
 
 enum { PASS_FORWARD = 0, PASS_INVERSE = 1, PASS_LOGPROB = 2 };
 
-template <int E> int launch_mala(int pot_kind, const LocalArgs& A, int grid, size_t smem, cudaStream_t s);
-template <int E> int launch_hmc(int pot_kind, const LocalArgs& A, int grid, size_t smem, cudaStream_t s);
+template <int E> int launch_mala(int pot_kind, bool exact, const LocalArgs& A, int grid, size_t smem, cudaStream_t s);
+template <int E> int launch_hmc(int pot_kind, bool exact, const LocalArgs& A, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_flow_pass(const FlowArgs& A, int mode, const float* in, float* out, float* aux, long long n,
                                       int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_flow_sample(const FlowArgs& A, const RngArgs& R, long long chain0, float* x, float* logq,

@@ -49,9 +49,11 @@ __global__ void __launch_bounds__(kThreads) rng_fill_kernel(RngArgs R, unsigned 
   }
 }
 
-static size_t local_smem_bytes(int d, bool with_mass, size_t per_dim) {
+static size_t local_smem_bytes(int d, bool with_mass, size_t per_dim, int E) {
   size_t b = (cta_stats_bytes_host(d) + 15) & ~size_t(15);
   if (with_mass) b += (size_t)d * per_dim;
+  b = (b + 15) & ~size_t(15);
+  b += (size_t)E * kThreads * sizeof(float4);  // per-lane running moments
   return b;
 }
 
@@ -87,10 +89,10 @@ extern "C" int nfmc_mala_steps(const nfmc_potential* pot, float* x, int64_t n, i
   fill_chain_args(A.c, pot, x, n, n_steps, rng, chain0, stats, sink, L);
   A.tau = step_size; A.sqrt_2tau = (float)sqrt(2.0 * (double)step_size); A.imd = inv_mass_diag;
   A.adjusted = adjusted; A.n_leapfrog = 0;
-  const size_t smem = local_smem_bytes(pot->d, inv_mass_diag != nullptr, sizeof(float4));
+  const size_t smem = local_smem_bytes(pot->d, inv_mass_diag != nullptr, sizeof(float4), L.E);
   const int grid = grid_for(n, L.gs, 4);
   cudaStream_t s = (cudaStream_t)stream;
-  NFMC_DISPATCH_E(L.E, { return launch_mala<E>(pot->kind, A, grid, smem, s); });
+  NFMC_DISPATCH_E(L.E, { return launch_mala<E>(pot->kind, L.exact, A, grid, smem, s); });
   return 0;
 }
 
@@ -105,10 +107,10 @@ extern "C" int nfmc_hmc_steps(const nfmc_potential* pot, float* x, int64_t n, in
   LocalArgs A;
   fill_chain_args(A.c, pot, x, n, n_steps, rng, chain0, stats, sink, L);
   A.tau = step_size; A.sqrt_2tau = 0.f; A.imd = inv_mass_diag; A.adjusted = adjusted; A.n_leapfrog = n_leapfrog;
-  const size_t smem = local_smem_bytes(pot->d, inv_mass_diag != nullptr, sizeof(float2));
+  const size_t smem = local_smem_bytes(pot->d, inv_mass_diag != nullptr, sizeof(float4), L.E);
   const int grid = grid_for(n, L.gs, 4);
   cudaStream_t s = (cudaStream_t)stream;
-  NFMC_DISPATCH_E(L.E, { return launch_hmc<E>(pot->kind, A, grid, smem, s); });
+  NFMC_DISPATCH_E(L.E, { return launch_hmc<E>(pot->kind, L.exact, A, grid, smem, s); });
   return 0;
 }
 

@@ -4,6 +4,10 @@
 // steps, so HBM sees the chain state once on the way in and once on the way out (plus the optional sample
 // sink / injected noise).  Replaces Langevin.propose (mcmc/langevin.py:61-122) and the local loop
 // MCMCSampler.sample (mcmc/base.py:69-99) of the reference.
+//
+// Register budget: 4 CTAs of 128 threads per SM (<= 128 registers).  Live per-lane state is the chain (2E) and
+// the proposal (2E); the noise is consumed Philox quad by quad as it is generated, and the running moments
+// (4E floats per lane) live in shared memory as float4 {sum lo, sum hi, sum lo^2, sum hi^2} per slot.
 #include "launchers.cuh"
 
 #ifndef NFMC_ONLY_E
@@ -13,36 +17,41 @@
 #ifndef NFMC_MALA_MINB
 #define NFMC_MALA_MINB 4
 #endif
-#ifndef NFMC_HMC_MINB
-#define NFMC_HMC_MINB 4
-#endif
 
 namespace nfmc {
 
 // per-dimension coefficients in shared memory when the mass is not the identity
-//   MALA: {c1 = -tau/imd^2, c2 = sqrt(2 tau)/imd, tauA = tau/imd^2, invA = imd^2}   (langevin.py:74-75,95)
-//   HMC : {rs = 1/sqrt(imd), imd, 0, 0}                                              (hmc.py:100,58,104)
+//   {c1 = -tau/imd^2, c2 = sqrt(2 tau)/imd, tauA = tau/imd^2, invA = imd^2}   (langevin.py:74-75,95)
 __device__ __forceinline__ float4 mala_coef(float tau, float s2t, float m) {
   const float a = __fdiv_rn(1.f, m * m);
   return make_float4(-__fdiv_rn(tau, m * m), __fdiv_rn(s2t, m), tau * a, __fdiv_rn(1.f, a));
 }
 
-template <int POT, int E>
+// FAST: exact layout, Philox noise, identity mass -- all three known at compile time (single straight-line step body).
+// !FAST: inexact layouts, injected noise and non-identity mass handled by run-time (warp-uniform) tests.
+template <int POT, int E, bool FAST>
 __global__ void __launch_bounds__(kThreads, NFMC_MALA_MINB) mala_kernel(const LocalArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ChainArgs& C = A.c;
   const Geom g = make_geom(C.d, C.gs);
   CtaStats st = cta_stats_init(smem, C.d);
-  float4* coef = reinterpret_cast<float4*>(smem + ((cta_stats_bytes(C.d) + 15) & ~size_t(15)));
-  const bool unit_mass = (A.imd == nullptr);
+  size_t off = (cta_stats_bytes(C.d) + 15) & ~size_t(15);
+  float4* coef = reinterpret_cast<float4*>(smem + off);
+  const bool unit_mass = FAST ? true : (A.imd == nullptr);
   if (!unit_mass) {
     for (int i = threadIdx.x; i < C.d; i += blockDim.x) coef[i] = mala_coef(A.tau, A.sqrt_2tau, __ldg(A.imd + i));
+    off += (size_t)C.d * sizeof(float4);
     __syncthreads();
   }
+  float4* mom = reinterpret_cast<float4*>(smem + off) + threadIdx.x;  // slot e at mom[e * kThreads]
   const int cpc = kThreads / C.gs;
   const long long tiles = (C.n + cpc - 1) / cpc;
   const float inv4tau = __fdiv_rn(1.f, 4.f * A.tau);
+  constexpr bool EXACT = FAST;
+  const bool inject = FAST ? false : (C.rng.normals != nullptr);
+  const PhiloxKeys PK = philox_keys(C.rng.seed);
   unsigned int n_acc = 0, n_bad = 0;
+  constexpr int NQ = (E + 2) / 2;
 
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const long long chain_raw = tile * cpc + threadIdx.x / C.gs;
@@ -50,67 +59,89 @@ __global__ void __launch_bounds__(kThreads, NFMC_MALA_MINB) mala_kernel(const Lo
     const long long chain = active ? chain_raw : C.n - 1;
     float* row = C.x + chain * (long long)C.d;
 
-    float lo[E], hi[E], m1lo[E], m1hi[E], m2lo[E], m2hi[E];
+    float lo[E], hi[E];
     load_chain(row, g, lo, hi);
 #pragma unroll
-    for (int e = 0; e < E; ++e) m1lo[e] = m1hi[e] = m2lo[e] = m2hi[e] = 0.f;
+    for (int e = 0; e < E; ++e) mom[e * kThreads] = make_float4(0.f, 0.f, 0.f, 0.f);
     PotCtx ctx = pot_prepare<POT, E>(C.pot, g, lo, hi);
 
     for (int k = 0; k < C.n_steps; ++k) {
-      // ---- noise for this step (langevin.py:63) ---------------------------------------------------------
-      StepNoise<E> nz;
-      if (C.rng.normals) {
-        const float* nr = C.rng.normals + ((long long)k * C.n + chain) * (long long)C.d;
-        load_chain(nr, g, nz.lo, nz.hi);
-        nz.ubits = 0;
-      } else {
-        const RngKey key = make_rng_key(C.rng.seed, 0u, C.rng.step0 + (uint64_t)k, (uint64_t)(C.chain0 + chain));
-        draw_step_noise<E>(key, g.j, nz);
-      }
-      // ---- proposal x' = x - tau/m^2 grad U(x) + sqrt(2 tau)/m xi  (langevin.py:74-76) ------------------
+      const RngKey key = make_rng_key(C.rng.seed, 0u, C.rng.step0 + (uint64_t)k, (uint64_t)(C.chain0 + chain));
+      const float* nrow = inject ? C.rng.normals + ((long long)k * C.n + chain) * (long long)C.d : nullptr;
       float plo[E], phi[E];
       float qf = 0.f;
+      uint32_t ubits = 0;
+      // ---- noise (langevin.py:63) consumed quad by quad; proposal x' = x - tau/m^2 grad U + sqrt(2 tau)/m xi (:74-76)
 #pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const int kk = g.j + g.gs * e;
-        float glo, ghi;
-        pot_grad<POT>(C.pot, ctx, g, kk, lo[e], hi[e], glo, ghi);
-        if (unit_mass) {
-          plo[e] = fmaf(A.sqrt_2tau, nz.lo[e], fmaf(-A.tau, glo, lo[e]));
-          phi[e] = fmaf(A.sqrt_2tau, nz.hi[e], fmaf(-A.tau, ghi, hi[e]));
-          const float tl = plo[e] - lo[e] + A.tau * glo, th = phi[e] - hi[e] + A.tau * ghi;  // langevin.py:41
-          if (kk < g.da) qf = fmaf(tl, tl, qf);
-          if (kk < g.db) qf = fmaf(th, th, qf);
-        } else {
-          const float4 cl = coef[min(kk, g.da - 1 < 0 ? 0 : g.da - 1)], ch = coef[g.da + min(kk, g.db - 1)];
-          plo[e] = fmaf(cl.y, nz.lo[e], fmaf(cl.x, glo, lo[e]));
-          phi[e] = fmaf(ch.y, nz.hi[e], fmaf(ch.x, ghi, hi[e]));
-          const float tl = plo[e] - lo[e] + cl.z * glo, th = phi[e] - hi[e] + ch.z * ghi;
-          if (kk < g.da) qf = fmaf(tl * cl.w, tl, qf);
-          if (kk < g.db) qf = fmaf(th * ch.w, th, qf);
+      for (int q = 0; q < NQ; ++q) {
+        uint4 w = make_uint4(0u, 0u, 0u, 0u);
+        if (!inject) w = rng_quad(PK, key, q, g.j);
+        if (q == 0) ubits = w.x;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int e = 2 * q + hh - 1;          // pair p = e + 1 lives in quad p/2, words 2(p%2), 2(p%2)+1
+          if (e < 0 || e >= E) continue;
+          const int kk = g.j + g.gs * e;
+          const bool vl = slot_ok<EXACT, E>(e, kk, g.da), vh = slot_ok<EXACT, E>(e, kk, g.db);
+          float nlo, nhi;
+          if (inject) {
+            nlo = vl ? __ldg(nrow + kk) : 0.f;
+            nhi = vh ? __ldg(nrow + g.da + kk) : 0.f;
+          } else {
+            box_muller(hh ? w.z : w.x, hh ? w.w : w.y, nlo, nhi);
+          }
+          float glo, ghi;
+          if (EXACT && e < E - 1) pot_grad<POT, true>(C.pot, ctx, g, kk, lo[e], hi[e], glo, ghi);
+          else pot_grad<POT, false>(C.pot, ctx, g, kk, lo[e], hi[e], glo, ghi);
+          float pl, ph, tl, th;
+          if (unit_mass) {
+            pl = fmaf(A.sqrt_2tau, nlo, fmaf(-A.tau, glo, lo[e]));
+            ph = fmaf(A.sqrt_2tau, nhi, fmaf(-A.tau, ghi, hi[e]));
+            tl = pl - lo[e] + A.tau * glo;                                     // langevin.py:41
+            th = ph - hi[e] + A.tau * ghi;
+            tl = vl ? tl : 0.f;
+            th = vh ? th : 0.f;
+            qf = fmaf(tl, tl, fmaf(th, th, qf));
+          } else {
+            const float4 cl = coef[vl ? kk : 0], ch = coef[g.da + (vh ? kk : 0)];
+            pl = fmaf(cl.y, nlo, fmaf(cl.x, glo, lo[e]));
+            ph = fmaf(ch.y, nhi, fmaf(ch.x, ghi, hi[e]));
+            tl = pl - lo[e] + cl.z * glo;
+            th = ph - hi[e] + ch.z * ghi;
+            tl = vl ? tl : 0.f;
+            th = vh ? th : 0.f;
+            qf = fmaf(tl * cl.w, tl, fmaf(th * ch.w, th, qf));
+          }
+          plo[e] = vl ? pl : 0.f;
+          phi[e] = vh ? ph : 0.f;
         }
-        if (kk >= g.da) plo[e] = 0.f;
-        if (kk >= g.db) phi[e] = 0.f;
       }
       bool accept = true;
-      PotCtx ctxp = pot_prepare<POT, E>(C.pot, g, plo, phi);  // U(x') (langevin.py:80-82); also next step's ctx
+      const PotCtx ctxp = pot_prepare<POT, E>(C.pot, g, plo, phi);  // U(x') (langevin.py:80-82); also next step's ctx
       if (A.adjusted) {
         // ---- reverse proposal term with grad U(x')  (langevin.py:91-97) ----------------------------------
         float qr = 0.f;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
           const int kk = g.j + g.gs * e;
+          const bool vl = slot_ok<EXACT, E>(e, kk, g.da), vh = slot_ok<EXACT, E>(e, kk, g.db);
           float glo, ghi;
-          pot_grad<POT>(C.pot, ctxp, g, kk, plo[e], phi[e], glo, ghi);
+          if (EXACT && e < E - 1) pot_grad<POT, true>(C.pot, ctxp, g, kk, plo[e], phi[e], glo, ghi);
+          else pot_grad<POT, false>(C.pot, ctxp, g, kk, plo[e], phi[e], glo, ghi);
+          float tl, th;
           if (unit_mass) {
-            const float tl = lo[e] - plo[e] + A.tau * glo, th = hi[e] - phi[e] + A.tau * ghi;
-            if (kk < g.da) qr = fmaf(tl, tl, qr);
-            if (kk < g.db) qr = fmaf(th, th, qr);
+            tl = lo[e] - plo[e] + A.tau * glo;
+            th = hi[e] - phi[e] + A.tau * ghi;
+            tl = vl ? tl : 0.f;
+            th = vh ? th : 0.f;
+            qr = fmaf(tl, tl, fmaf(th, th, qr));
           } else {
-            const float4 cl = coef[min(kk, g.da - 1 < 0 ? 0 : g.da - 1)], ch = coef[g.da + min(kk, g.db - 1)];
-            const float tl = lo[e] - plo[e] + cl.z * glo, th = hi[e] - phi[e] + ch.z * ghi;
-            if (kk < g.da) qr = fmaf(tl * cl.w, tl, qr);
-            if (kk < g.db) qr = fmaf(th * ch.w, th, qr);
+            const float4 cl = coef[vl ? kk : 0], ch = coef[g.da + (vh ? kk : 0)];
+            tl = lo[e] - plo[e] + cl.z * glo;
+            th = hi[e] - phi[e] + ch.z * ghi;
+            tl = vl ? tl : 0.f;
+            th = vh ? th : 0.f;
+            qr = fmaf(tl * cl.w, tl, fmaf(th * ch.w, th, qr));
           }
         }
         qf = group_sum(qf, g.gs) * inv4tau;
@@ -119,26 +150,39 @@ __global__ void __launch_bounds__(kThreads, NFMC_MALA_MINB) mala_kernel(const Lo
         const float log_ratio = (-ctxp.u) - (-ctx.u) + (-qr) - (-qf);
         float u;
         if (C.rng.uniforms) u = __ldg(C.rng.uniforms + (long long)k * C.n + chain);
-        else u = uniform_from_bits(__shfl_sync(0xffffffffu, nz.ubits, g.grp_base));
+        else u = uniform_from_bits(__shfl_sync(0xffffffffu, ubits, g.grp_base));
         accept = logf(u) < log_ratio;                                                    // langevin.py:106
         if (!(fabsf(log_ratio) <= 3.0e38f) && g.j == 0 && active) ++n_bad;
       }
-      // ---- x[mask] = x'[mask]  (mcmc/base.py:77) -----------------------------------------------------------
+      // ---- x[mask] = x'[mask] (mcmc/base.py:77); running moments of the post-accept state (mcmc/base.py:86) ----
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         lo[e] = accept ? plo[e] : lo[e];
         hi[e] = accept ? phi[e] : hi[e];
+        float4 m = mom[e * kThreads];
+        m.x += lo[e];
+        m.y += hi[e];
+        m.z = fmaf(lo[e], lo[e], m.z);
+        m.w = fmaf(hi[e], hi[e], m.w);
+        mom[e * kThreads] = m;
       }
       ctx = select_ctx(accept, ctxp, ctx);
       if (accept && g.j == 0 && active) ++n_acc;
-      accumulate_moments(lo, hi, m1lo, m1hi, m2lo, m2hi);                                // mcmc/base.py:86
       if (C.sink.samples && active) sink_store(C.sink, g, C.n, chain, k, lo, hi);        // mcmc/base.py:90
     }
-    if (!active) {
+    // ---- per-tile flush of the moments: fp32 per-lane sums -> shuffle over the warp's groups -> fp64 shared atomics
 #pragma unroll
-      for (int e = 0; e < E; ++e) m1lo[e] = m1hi[e] = m2lo[e] = m2hi[e] = 0.f;
+    for (int e = 0; e < E; ++e) {
+      float4 m = mom[e * kThreads];
+      if (!active) m = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int kk = g.j + g.gs * e;
+      const float a = across_groups_sum(m.x, g.gs), b = across_groups_sum(m.y, g.gs);
+      const float c = across_groups_sum(m.z, g.gs), dd = across_groups_sum(m.w, g.gs);
+      if (g.lane < g.gs) {
+        if (kk < g.da) { atomicAdd(st.sx + kk, (double)a); atomicAdd(st.sx2 + kk, (double)c); }
+        if (kk < g.db) { atomicAdd(st.sx + g.da + kk, (double)b); atomicAdd(st.sx2 + g.da + kk, (double)dd); }
+      }
     }
-    flush_moments(g, m1lo, m1hi, m2lo, m2hi, st.sx, st.sx2);
     if (active) store_chain(row, g, lo, hi);
   }
   // counters (mcmc/base.py:79-85): one atomic per warp into shared, then one per CTA into global
@@ -152,23 +196,26 @@ __global__ void __launch_bounds__(kThreads, NFMC_MALA_MINB) mala_kernel(const Lo
     long long mine = 0;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       const long long first = tile * cpc;
-      const long long cnt = (C.n - first) < cpc ? (C.n - first) : cpc;
-      mine += cnt;
+      mine += (C.n - first) < cpc ? (C.n - first) : cpc;
     }
     atomicAdd(st.cnt + 1, (unsigned long long)(mine * C.n_steps));
   }
   cta_stats_finish(st, C.stats, C.d);
 }
 
-
 template <int E>
-int launch_mala(int pot_kind, const LocalArgs& A, int grid, size_t smem, cudaStream_t s) {
+int launch_mala(int pot_kind, bool exact, const LocalArgs& A, int grid, size_t smem, cudaStream_t s) {
   NFMC_DISPATCH_POT(pot_kind, {
-    NFMC_SET_SMEM_RET((mala_kernel<POT, E>), smem);
-    mala_kernel<POT, E><<<grid, kThreads, smem, s>>>(A);
+    if (exact && !A.c.rng.normals && !A.imd) {
+      NFMC_SET_SMEM_RET((mala_kernel<POT, E, true>), smem);
+      mala_kernel<POT, E, true><<<grid, kThreads, smem, s>>>(A);
+    } else {
+      NFMC_SET_SMEM_RET((mala_kernel<POT, E, false>), smem);
+      mala_kernel<POT, E, false><<<grid, kThreads, smem, s>>>(A);
+    }
   });
   return check_cuda(cudaGetLastError(), "mala_kernel launch");
 }
-template int launch_mala<NFMC_ONLY_E>(int, const LocalArgs&, int, size_t, cudaStream_t);
+template int launch_mala<NFMC_ONLY_E>(int, bool, const LocalArgs&, int, size_t, cudaStream_t);
 
 }  // namespace nfmc

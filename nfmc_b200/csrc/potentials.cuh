@@ -101,8 +101,9 @@ __device__ __forceinline__ PotCtx pot_prepare(const PotParams& P, const Geom& g,
   return c;
 }
 
-// gradient of slot e: glo = dU/dx[k], ghi = dU/dx[da + k]  (k = j + gs*e); values at invalid slots are ignored
-template <int POT>
+// gradient of slot e: glo = dU/dx[k], ghi = dU/dx[da + k]  (k = j + gs*e); values at invalid slots are ignored.
+// KV: the caller knows the slot is valid in both halves (no clamping of parameter indices needed).
+template <int POT, bool KV = false>
 __device__ __forceinline__ void pot_grad(const PotParams& P, const PotCtx& c, const Geom& g, int k, float vlo, float vhi,
                                          float& glo, float& ghi) {
   if constexpr (POT == NFMC_POT_ISO_GAUSSIAN) {
@@ -110,9 +111,11 @@ __device__ __forceinline__ void pot_grad(const PotParams& P, const PotCtx& c, co
     ghi = P.s0 * vhi;
   } else if constexpr (POT == NFMC_POT_DIAG_GAUSSIAN) {
     const float2* wm = reinterpret_cast<const float2*>(P.params);
-    glo = ghi = 0.f;
-    if (k < g.da) { const float2 p = __ldg(wm + k); glo = p.x * (vlo - p.y); }
-    if (k < g.db) { const float2 p = __ldg(wm + g.da + k); ghi = p.x * (vhi - p.y); }
+    const int kl = KV ? k : min(k, g.da > 0 ? g.da - 1 : 0);
+    const int kh = g.da + (KV ? k : min(k, g.db - 1));
+    const float2 pl = __ldg(wm + kl), ph = __ldg(wm + kh);
+    glo = pl.x * (vlo - pl.y);
+    ghi = ph.x * (vhi - ph.y);
   } else if constexpr (POT == NFMC_POT_FUNNEL) {
     glo = c.b * vlo;
     ghi = c.b * vhi;
@@ -132,6 +135,10 @@ __device__ __forceinline__ void pot_grad(const PotParams& P, const PotCtx& c, co
     else { if (k == 1) ghi = vhi - c.b; }
   }
 }
+
+// does grad U need the chain-level scalars of pot_prepare (i.e. a reduction over the chain)?
+template <int POT>
+constexpr bool pot_grad_needs_ctx() { return POT == NFMC_POT_FUNNEL || POT == NFMC_POT_MIXTURE4; }
 
 // runtime-dispatched versions for the flow-heavy kernels (jump / IMH / NeuTra), where the potential is a small
 // part of the work and templating on it would only multiply compile time
