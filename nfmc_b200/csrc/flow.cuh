@@ -1,95 +1,247 @@
 // flow.cuh -- RealNVP forward / inverse / log-det / input-VJP on the register-resident chain layout.
 //
 // Specification = oracle/realnvp_ref.py (the torchflows surface the reference calls: sampling/base.py:26,
-// util.py:280-281, jump.py:205,218, imh.py:214,221, neutra.py:60).  Generic CUDA-core path: any number of
-// coupling layers Lc, conditioner linear layers M >= 1 and hidden width H.  (Wide conditioners go to the
-// tcgen05 path in cond_tc.cu.)
+// util.py:280-281, jump.py:205,218, imh.py:214,221, neutra.py:60).
 //
-// Physical coordinates.  The flow's reverse permutations are folded into the packed parameters: the chain
-// state is never permuted; instead coupling l (0-based) has its source/target halves swapped when l is even
-// (an odd number of reversals precede it) and every parameter is stored in the coordinate the state actually
-// lives in.  Only the latent z of a flow with odd Lc is flipped, on load/store.
+// Two conditioner code paths:
+//   * small  (M == 2, H <= 8 -- every default conditioner for d <= 1024): hidden units live in registers, weights are
+//     packed hidden-minor and padded to 8 so that one 128-bit load brings four weights; no scratch memory.
+//   * generic (any M >= 1, any H): hidden activations in per-group shared scratch; out-of-line, correctness path.
+//   (Wide conditioners are meant for the tcgen05 path, cond_tc.cu.)
 //
-// Blob layout (fp32), da = d/2, db = d - da, Hs = (M == 1 ? da : H):
-//   [ (Lc+3) elementwise affines ] each 3*d: alpha[d], beta[d], 1/alpha[d]      (order: A0, AN_0..AN_{Lc-1}, A_last, AN_last)
+// Physical coordinates.  The flow's reverse permutations are folded into the packed parameters: the chain state is
+// never permuted; coupling l (0-based) has its source/target halves swapped when l is even (an odd number of
+// reversals precede it) and every parameter is stored in the coordinate the state actually lives in.  Only the
+// latent z of a flow with odd Lc is flipped, on load/store.
+//
+// Blob layout (fp32), da = d/2, db = d - da:
+//   [ (Lc+1) elementwise affines ]  affine 0 = the leading ElementwiseAffine; affine l+1 = the act-norm after coupling l;
+//                                   the last one also absorbs the trailing ElementwiseAffine + ActNorm (composed at
+//                                   pack time).  Each: fwd float2[d] {alpha, beta}, inv float2[d] {beta, 1/alpha}.
 //   [ 4 floats ] [0] = sum over all elementwise affines of sum_i log alpha_i
-//   [ Lc couplings ] each:
-//        M >= 2:  W1[H][da] b1[H] | (M-2) x { Wm[H_in][H_out] bm[H] } | Wl[H][2][db] bl[2][db]
-//        M == 1:  Wl[da][2][db] bl[2][db]
-//   (W1 indexed by packed source index, Wl by packed target index; see pack_realnvp in nfmc_b200/flow.py)
+//   [ Lc couplings ]
+//        small  :  W1T[da][8] | b1[8] | WlT[db][2][8] | bl[db][2] (+pad to 4)  (zero padded in h)
+//        generic:  M >= 2:  W1[H][da] b1[H] | (M-2) x { Wm[H_in][H_out] bm[H] } | Wl[H][2][db] bl[2][db]
+//                  M == 1:  Wl[da][2][db] bl[2][db]
+//   (source / target indices are PACKED physical indices; see pack_realnvp in nfmc_b200/flow.py)
 #pragma once
 #include "common.cuh"
 
 namespace nfmc {
 
+constexpr int kSmallH = 8;
+
 struct FlowDesc {
   const float* blob;
+  unsigned sbase;       // shared-window address of blob[0] when the blob is staged in shared memory
   int d, da, db, Lc, M, H;
-  int Hs;               // width of the last layer's input
-  int off_const;        // (Lc+3)*3*d
+  int small;            // M == 2 && H <= 8
+  int Hs;               // generic path: width of the last layer's input
+  int off_const;        // (Lc+1)*4*d
   int off_coupling;     // off_const + 4
   int coupling_stride;  // floats per coupling
-  int scratch;          // floats of scratch per chain group
+  int scratch;          // generic path: floats of scratch per chain group (0 for small)
 };
 
+__host__ __device__ inline bool flow_is_small(int M, int H) { return M == 2 && H <= kSmallH; }
 __host__ __device__ inline int flow_coupling_floats(int d, int M, int H) {
   const int da = d / 2, db = d - da;
+  if (flow_is_small(M, H)) return da * kSmallH + kSmallH + db * 2 * kSmallH + ((db * 2 + 3) & ~3);
   if (M == 1) return da * 2 * db + 2 * db;
   return (da * H + H) + (M - 2) * (H * H + H) + (H * 2 * db + 2 * db);
 }
 __host__ __device__ inline long long flow_blob_floats(int d, int Lc, int M, int H) {
-  return (long long)(Lc + 3) * 3 * d + 4 + (long long)Lc * flow_coupling_floats(d, M, H);
+  return (long long)(Lc + 1) * 4 * d + 4 + (long long)Lc * flow_coupling_floats(d, M, H);
 }
 __host__ __device__ inline FlowDesc make_flow_desc(const float* blob, int d, int Lc, int M, int H) {
   FlowDesc F;
-  F.blob = blob; F.d = d; F.da = d / 2; F.db = d - F.da; F.Lc = Lc; F.M = M; F.H = H;
+  F.blob = blob; F.sbase = 0u; F.d = d; F.da = d / 2; F.db = d - F.da; F.Lc = Lc; F.M = M; F.H = H;
+  F.small = flow_is_small(M, H) ? 1 : 0;
   F.Hs = (M == 1) ? F.da : H;
-  F.off_const = (Lc + 3) * 3 * d;
+  F.off_const = (Lc + 1) * 4 * d;
   F.off_coupling = F.off_const + 4;
   F.coupling_stride = flow_coupling_floats(d, M, H);
-  F.scratch = ((M - 1 > 1 ? M - 1 : 1) + 2) * F.Hs;
+  F.scratch = F.small ? 0 : ((M - 1 > 1 ? M - 1 : 1) + 2) * F.Hs;
   return F;
 }
 
-__device__ __forceinline__ float precise_tanh(float v) { return tanhf(v); }
+// ---- parameter loads by float offset into the blob.  SB = the blob was staged into shared memory: explicit
+//      ld.shared with 32-bit addresses (the compiler cannot prove the address space through FlowDesc). ------------------
+template <bool SB>
+__device__ __forceinline__ float ldp(const FlowDesc& F, int off) {
+  if (SB) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(F.sbase + 4u * (unsigned)off));
+    return v;
+  }
+  return __ldg(F.blob + off);
+}
+template <bool SB>
+__device__ __forceinline__ float2 ldp2(const FlowDesc& F, int off) {
+  if (SB) {
+    float2 v;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(F.sbase + 4u * (unsigned)off));
+    return v;
+  }
+  return __ldg(reinterpret_cast<const float2*>(F.blob + off));
+}
+template <bool SB>
+__device__ __forceinline__ float4 ldp4(const FlowDesc& F, int off) {
+  if (SB) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(F.sbase + 4u * (unsigned)off));
+    return v;
+  }
+  return __ldg(reinterpret_cast<const float4*>(F.blob + off));
+}
 
-// ---- elementwise affine (A0, act-norms, A_last) ---------------------------------------------------------
-template <int E, bool INV>
+// tanh with absolute error ~1e-7 (the conditioner output feeds a linear layer, so absolute error is what matters)
+__device__ __forceinline__ float fast_tanh(float v) {
+  const float t = __expf(2.f * v);
+  return 1.f - __fdividef(2.f, t + 1.f);
+}
+
+// ---- elementwise affine (branch-free: clamped parameter index, invalid slots stay 0) -----------------------------------
+template <int E, bool INV, bool SB>
 __device__ __forceinline__ void affine_apply(const FlowDesc& F, const Geom& g, int a, float (&lo)[E], float (&hi)[E]) {
-  const float* al = F.blob + (long long)a * 3 * F.d;
-  const float* be = al + F.d;
-  const float* ra = be + F.d;
+  const int base = a * 4 * F.d + (INV ? 2 * F.d : 0);
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     const int k = g.j + g.gs * e;
-    if (k < g.da) lo[e] = INV ? (lo[e] - be[k]) * ra[k] : fmaf(al[k], lo[e], be[k]);
-    if (k < g.db) hi[e] = INV ? (hi[e] - be[g.da + k]) * ra[g.da + k] : fmaf(al[g.da + k], hi[e], be[g.da + k]);
+    const bool vl = k < g.da, vh = k < g.db;
+    const float2 pl = ldp2<SB>(F, base + 2 * (vl ? k : 0));
+    const float2 ph = ldp2<SB>(F, base + 2 * (g.da + (vh ? k : 0)));
+    const float nl = INV ? (lo[e] - pl.x) * pl.y : fmaf(pl.x, lo[e], pl.y);
+    const float nh = INV ? (hi[e] - ph.x) * ph.y : fmaf(ph.x, hi[e], ph.y);
+    lo[e] = vl ? nl : 0.f;
+    hi[e] = vh ? nh : 0.f;
   }
 }
 // undo an inverse affine (state <- alpha*state + beta) while pulling the gradient back (grad <- grad / alpha)
-template <int E>
+template <int E, bool SB>
 __device__ __forceinline__ void affine_unwind(const FlowDesc& F, const Geom& g, int a, float (&lo)[E], float (&hi)[E],
                                               float (&glo)[E], float (&ghi)[E]) {
-  const float* al = F.blob + (long long)a * 3 * F.d;
-  const float* be = al + F.d;
-  const float* ra = be + F.d;
+  const int fw = a * 4 * F.d, iv = fw + 2 * F.d;
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     const int k = g.j + g.gs * e;
-    if (k < g.da) { lo[e] = fmaf(al[k], lo[e], be[k]); glo[e] *= ra[k]; }
-    if (k < g.db) { hi[e] = fmaf(al[g.da + k], hi[e], be[g.da + k]); ghi[e] *= ra[g.da + k]; }
+    const bool vl = k < g.da, vh = k < g.db;
+    const int il = 2 * (vl ? k : 0), ih = 2 * (g.da + (vh ? k : 0));
+    const float2 pl = ldp2<SB>(F, fw + il), ph = ldp2<SB>(F, fw + ih);
+    const float rl = ldp<SB>(F, iv + il + 1), rh = ldp<SB>(F, iv + ih + 1);
+    lo[e] = vl ? fmaf(pl.x, lo[e], pl.y) : 0.f;
+    hi[e] = vh ? fmaf(ph.x, hi[e], ph.y) : 0.f;
+    glo[e] = vl ? glo[e] * rl : 0.f;
+    ghi[e] = vh ? ghi[e] * rh : 0.f;
   }
 }
 
-// ---- conditioner MLP ---------------------------------------------------------------------------------------
-// src[e] holds source element ks = j + gs*e - shift (valid iff 0 <= ks < da).  Targets: slot e of the other half
-// has packed index t = j + gs*e (valid iff t < nt_main), plus, when has_x, one extra target t = da (the middle
-// element of an odd-d chain, which lives in hi[0] of lane 0).  Hidden activations stay in scr for the backward.
+// ---- small conditioner (M == 2, H <= 8): registers only ---------------------------------------------------------------
+// src[e] holds source element ks = j + gs*e - shift (valid iff 0 <= ks < da).  Targets: slot e of the other half has
+// packed index t = j + gs*e (valid iff t < nt_main), plus, when has_x, one extra target t = da (the middle element of
+// an odd-d chain, which physically is hi[0] of lane 0).  hid[] returns the hidden activations (for the backward).
+template <int E, bool SB>
+__device__ __forceinline__ void cond_forward_small(const FlowDesc& F, const Geom& g, int W, const float (&src)[E],
+                                                   int shift, int nt_main, bool has_x, float (&hid)[kSmallH], float (&ua)[E],
+                                                   float (&ub)[E], float& ua_x, float& ub_x) {
+  const int da = F.da, db = F.db;
+  float acc[kSmallH];
+#pragma unroll
+  for (int h = 0; h < kSmallH; ++h) acc[h] = 0.f;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int ks = g.j + g.gs * e - shift;
+    const bool ok = ks >= 0 && ks < da;
+    const float v = ok ? src[e] : 0.f;
+    const int w = W + (ok ? ks : 0) * kSmallH;
+    const float4 w0 = ldp4<SB>(F, w), w1 = ldp4<SB>(F, w + 4);
+    acc[0] = fmaf(w0.x, v, acc[0]); acc[1] = fmaf(w0.y, v, acc[1]); acc[2] = fmaf(w0.z, v, acc[2]); acc[3] = fmaf(w0.w, v, acc[3]);
+    acc[4] = fmaf(w1.x, v, acc[4]); acc[5] = fmaf(w1.y, v, acc[5]); acc[6] = fmaf(w1.z, v, acc[6]); acc[7] = fmaf(w1.w, v, acc[7]);
+  }
+  const int b1 = W + da * kSmallH;
+#pragma unroll
+  for (int h = 0; h < kSmallH; ++h) hid[h] = fast_tanh(group_sum(acc[h], g.gs) + ldp<SB>(F, b1 + h));   // padded h: tanh(0) = 0
+  const int Wl = b1 + kSmallH;
+  const int bl = Wl + db * 2 * kSmallH;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int t = g.j + g.gs * e;
+    const int tc = t < nt_main ? t : 0;
+    const int w = Wl + tc * 2 * kSmallH;
+    const float4 a0 = ldp4<SB>(F, w), a1 = ldp4<SB>(F, w + 4), c0 = ldp4<SB>(F, w + 8), c1 = ldp4<SB>(F, w + 12);
+    const float2 b = ldp2<SB>(F, bl + 2 * tc);
+    float sa = b.x, sb = b.y;
+    sa = fmaf(a0.x, hid[0], sa); sa = fmaf(a0.y, hid[1], sa); sa = fmaf(a0.z, hid[2], sa); sa = fmaf(a0.w, hid[3], sa);
+    sa = fmaf(a1.x, hid[4], sa); sa = fmaf(a1.y, hid[5], sa); sa = fmaf(a1.z, hid[6], sa); sa = fmaf(a1.w, hid[7], sa);
+    sb = fmaf(c0.x, hid[0], sb); sb = fmaf(c0.y, hid[1], sb); sb = fmaf(c0.z, hid[2], sb); sb = fmaf(c0.w, hid[3], sb);
+    sb = fmaf(c1.x, hid[4], sb); sb = fmaf(c1.y, hid[5], sb); sb = fmaf(c1.z, hid[6], sb); sb = fmaf(c1.w, hid[7], sb);
+    ua[e] = sa;
+    ub[e] = sb;
+  }
+  ua_x = ub_x = 0.f;
+  if (has_x) {
+    const int w = Wl + da * 2 * kSmallH;
+    const float2 b = ldp2<SB>(F, bl + 2 * da);
+    float sa = b.x, sb = b.y;
+#pragma unroll
+    for (int h = 0; h < kSmallH; ++h) {
+      sa = fmaf(ldp<SB>(F, w + h), hid[h], sa);
+      sb = fmaf(ldp<SB>(F, w + kSmallH + h), hid[h], sb);
+    }
+    ua_x = sa;
+    ub_x = sb;
+  }
+}
+
+// input-VJP of the small conditioner: dsrc[e] += sum_out d_out * d out / d src[e]
+template <int E, bool SB>
+__device__ __forceinline__ void cond_backward_small(const FlowDesc& F, const Geom& g, int W, int shift, int nt_main,
+                                                    bool has_x, const float (&hid)[kSmallH], const float (&dua)[E],
+                                                    const float (&dub)[E], float dua_x, float dub_x, float (&dsrc)[E]) {
+  const int da = F.da, db = F.db;
+  const int b1 = W + da * kSmallH;
+  const int Wl = b1 + kSmallH;
+  float acc[kSmallH];
+#pragma unroll
+  for (int h = 0; h < kSmallH; ++h) acc[h] = 0.f;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int t = g.j + g.gs * e;
+    const bool ok = t < nt_main;
+    const float va = ok ? dua[e] : 0.f, vb = ok ? dub[e] : 0.f;
+    const int w = Wl + (ok ? t : 0) * 2 * kSmallH;
+    const float4 a0 = ldp4<SB>(F, w), a1 = ldp4<SB>(F, w + 4), c0 = ldp4<SB>(F, w + 8), c1 = ldp4<SB>(F, w + 12);
+    acc[0] = fmaf(a0.x, va, fmaf(c0.x, vb, acc[0])); acc[1] = fmaf(a0.y, va, fmaf(c0.y, vb, acc[1]));
+    acc[2] = fmaf(a0.z, va, fmaf(c0.z, vb, acc[2])); acc[3] = fmaf(a0.w, va, fmaf(c0.w, vb, acc[3]));
+    acc[4] = fmaf(a1.x, va, fmaf(c1.x, vb, acc[4])); acc[5] = fmaf(a1.y, va, fmaf(c1.y, vb, acc[5]));
+    acc[6] = fmaf(a1.z, va, fmaf(c1.z, vb, acc[6])); acc[7] = fmaf(a1.w, va, fmaf(c1.w, vb, acc[7]));
+  }
+  if (has_x && g.j == 0) {
+    const int w = Wl + da * 2 * kSmallH;
+#pragma unroll
+    for (int h = 0; h < kSmallH; ++h) acc[h] = fmaf(ldp<SB>(F, w + h), dua_x, fmaf(ldp<SB>(F, w + kSmallH + h), dub_x, acc[h]));
+  }
+  float dpre[kSmallH];
+#pragma unroll
+  for (int h = 0; h < kSmallH; ++h) dpre[h] = group_sum(acc[h], g.gs) * (1.f - hid[h] * hid[h]);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int ks = g.j + g.gs * e - shift;
+    const bool ok = ks >= 0 && ks < da;
+    const int w = W + (ok ? ks : 0) * kSmallH;
+    const float4 w0 = ldp4<SB>(F, w), w1 = ldp4<SB>(F, w + 4);
+    float s = w0.x * dpre[0];
+    s = fmaf(w0.y, dpre[1], s); s = fmaf(w0.z, dpre[2], s); s = fmaf(w0.w, dpre[3], s);
+    s = fmaf(w1.x, dpre[4], s); s = fmaf(w1.y, dpre[5], s); s = fmaf(w1.z, dpre[6], s); s = fmaf(w1.w, dpre[7], s);
+    if (ok) dsrc[e] += s;
+  }
+}
+
+// ---- generic conditioner MLP (any M, H): out of line, activations in shared scratch ------------------------------------
 template <int E>
-__device__ __forceinline__ void cond_forward(const FlowDesc& F, const Geom& g, int l, const float (&src)[E], int shift,
-                                             int nt_main, bool has_x, float* scr, float (&ua)[E], float (&ub)[E],
-                                             float& ua_x, float& ub_x) {
-  const float* W = F.blob + F.off_coupling + (long long)l * F.coupling_stride;
+__device__ __noinline__ void cond_forward_generic(const FlowDesc& F, const Geom& g, const float* W, const float (&src)[E],
+                                                  int shift, int nt_main, bool has_x, float* scr, float (&ua)[E], float (&ub)[E],
+                                                  float& ua_x, float& ub_x) {
   const int da = F.da, db = F.db, H = F.H;
   __syncwarp();
   const float* last;
@@ -113,7 +265,7 @@ __device__ __forceinline__ void cond_forward(const FlowDesc& F, const Geom& g, i
       for (int u = 0; u < 4; ++u) {
         const float s = group_sum(acc[u], g.gs);
         const int h = h0 + u;
-        if (h < H && g.j == (h & (g.gs - 1))) scr[h] = precise_tanh(s + b1[h]);
+        if (h < H && g.j == (h & (g.gs - 1))) scr[h] = tanhf(s + b1[h]);
       }
     }
     __syncwarp();
@@ -125,7 +277,7 @@ __device__ __forceinline__ void cond_forward(const FlowDesc& F, const Geom& g, i
       for (int hq = g.j; hq < H; hq += g.gs) {
         float acc = bm[hq];
         for (int h = 0; h < H; ++h) acc = fmaf(Wm[h * H + hq], in[h], acc);
-        out[hq] = precise_tanh(acc);
+        out[hq] = tanhf(acc);
       }
       __syncwarp();
       Wm = bm + H;
@@ -143,7 +295,7 @@ __device__ __forceinline__ void cond_forward(const FlowDesc& F, const Geom& g, i
     Wl = W;
   }
   const int Hs = F.Hs;
-  const float* bl = Wl + (long long)Hs * 2 * db;
+  const float* bl = Wl + Hs * 2 * db;
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     const int t = g.j + g.gs * e;
@@ -155,7 +307,7 @@ __device__ __forceinline__ void cond_forward(const FlowDesc& F, const Geom& g, i
   ub_x = has_x ? bl[db + da] : 0.f;
   for (int h = 0; h < Hs; ++h) {
     const float hv = last[h];
-    const float* wa = Wl + (long long)h * 2 * db;
+    const float* wa = Wl + h * 2 * db;
     const float* wb = wa + db;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
@@ -171,12 +323,10 @@ __device__ __forceinline__ void cond_forward(const FlowDesc& F, const Geom& g, i
   }
 }
 
-// input-VJP of the conditioner: dsrc[e] += sum_out d_out * d out / d src[e].  Needs scr as left by cond_forward.
 template <int E>
-__device__ __forceinline__ void cond_backward(const FlowDesc& F, const Geom& g, int l, int shift, int nt_main, bool has_x,
-                                              float* scr, const float (&dua)[E], const float (&dub)[E], float dua_x,
-                                              float dub_x, float (&dsrc)[E]) {
-  const float* W = F.blob + F.off_coupling + (long long)l * F.coupling_stride;
+__device__ __noinline__ void cond_backward_generic(const FlowDesc& F, const Geom& g, const float* W, int shift, int nt_main,
+                                                   bool has_x, float* scr, const float (&dua)[E], const float (&dub)[E],
+                                                   float dua_x, float dub_x, float (&dsrc)[E]) {
   const int da = F.da, db = F.db, H = F.H, Hs = F.Hs;
   float* gA = scr + (F.M - 1 > 1 ? F.M - 1 : 1) * Hs;
   float* gB = gA + Hs;
@@ -184,7 +334,7 @@ __device__ __forceinline__ void cond_backward(const FlowDesc& F, const Geom& g, 
   if (F.M >= 2) {
     const float* W1 = W;
     const float* Wm_first = W + H * da + H;
-    const float* Wl = Wm_first + (long long)(F.M - 2) * (H * H + H);
+    const float* Wl = Wm_first + (F.M - 2) * (H * H + H);
     const float* act_last = scr + (F.M - 2) * H;
     for (int h0 = 0; h0 < H; h0 += 4) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -195,7 +345,7 @@ __device__ __forceinline__ void cond_backward(const FlowDesc& F, const Geom& g, 
 #pragma unroll
           for (int u = 0; u < 4; ++u)
             if (h0 + u < H) {
-              const float* wa = Wl + (long long)(h0 + u) * 2 * db;
+              const float* wa = Wl + (h0 + u) * 2 * db;
               acc[u] = fmaf(wa[t], dua[e], fmaf(wa[db + t], dub[e], acc[u]));
             }
         }
@@ -204,7 +354,7 @@ __device__ __forceinline__ void cond_backward(const FlowDesc& F, const Geom& g, 
 #pragma unroll
         for (int u = 0; u < 4; ++u)
           if (h0 + u < H) {
-            const float* wa = Wl + (long long)(h0 + u) * 2 * db;
+            const float* wa = Wl + (h0 + u) * 2 * db;
             acc[u] = fmaf(wa[da], dua_x, fmaf(wa[db + da], dub_x, acc[u]));
           }
       }
@@ -217,7 +367,7 @@ __device__ __forceinline__ void cond_backward(const FlowDesc& F, const Geom& g, 
     }
     __syncwarp();
     for (int m = F.M - 2; m >= 1; --m) {
-      const float* Wm = Wm_first + (long long)(m - 1) * (H * H + H);
+      const float* Wm = Wm_first + (m - 1) * (H * H + H);
       const float* act_in = scr + (m - 1) * H;
       for (int hq = g.j; hq < H; hq += g.gs) {
         float acc = 0.f;
@@ -239,7 +389,7 @@ __device__ __forceinline__ void cond_backward(const FlowDesc& F, const Geom& g, 
   } else {
     const float* Wl = W;
     for (int ks0 = 0; ks0 < da; ++ks0) {
-      const float* wa = Wl + (long long)ks0 * 2 * db;
+      const float* wa = Wl + ks0 * 2 * db;
       float acc = 0.f;
 #pragma unroll
       for (int e = 0; e < E; ++e) {
@@ -273,7 +423,7 @@ __device__ __forceinline__ void swap_halves(float (&a)[E], float (&b)[E], bool d
 // ---- affine coupling layer l; INV = false: x -> z direction, true: z -> x.  ld accumulates THIS LANE's share of
 //      sum_t log alpha_t (caller group-sums once per pass).  When the source is the high half the two register
 //      arrays are swapped around the layer so that there is a single conditioner call site.
-template <int E, bool INV>
+template <int E, bool INV, bool SB>
 __device__ __forceinline__ void coupling_apply(const FlowDesc& F, const Geom& g, int l, float (&lo)[E], float (&hi)[E],
                                                float* scr, float& ld) {
   float ua[E], ub[E], ua_x, ub_x;
@@ -281,16 +431,22 @@ __device__ __forceinline__ void coupling_apply(const FlowDesc& F, const Geom& g,
   const int shift = src_is_hi ? F.db - F.da : 0;
   const bool has_x = shift > 0;
   const int nt_main = src_is_hi ? F.da : F.db;
+  const int Woff = F.off_coupling + l * F.coupling_stride;
   swap_halves(lo, hi, src_is_hi);  // lo = source array, hi = target array
-  cond_forward<E>(F, g, l, lo, shift, nt_main, has_x, scr, ua, ub, ua_x, ub_x);
+  if (F.small) {
+    float hid[kSmallH];
+    cond_forward_small<E, SB>(F, g, Woff, lo, shift, nt_main, has_x, hid, ua, ub, ua_x, ub_x);
+  } else {
+    cond_forward_generic<E>(F, g, F.blob + Woff, lo, shift, nt_main, has_x, scr, ua, ub, ua_x, ub_x);
+  }
 #pragma unroll
   for (int e = 0; e < E; ++e) {
-    if (g.j + g.gs * e < nt_main) {
-      float al, be;
-      affine_coef(ua[e], ub[e], al, be);
-      hi[e] = INV ? __fdividef(hi[e] - be, al) : fmaf(al, hi[e], be);
-      ld += __logf(al);
-    }
+    const bool ok = g.j + g.gs * e < nt_main;
+    float al, be;
+    affine_coef(ua[e], ub[e], al, be);
+    const float nv = INV ? __fdividef(hi[e] - be, al) : fmaf(al, hi[e], be);
+    hi[e] = ok ? nv : hi[e];
+    ld += ok ? __logf(al) : 0.f;
   }
   if (has_x && g.j == 0) {  // middle element of an odd-d chain: physically hi[0], here slot 0 of the source array
     float al, be;
@@ -305,18 +461,21 @@ __device__ __forceinline__ void coupling_apply(const FlowDesc& F, const Geom& g,
 // the gradient of U~ with respect to it.  On return they hold its INPUT (a, b') and the gradient with respect to
 // that input, where U~ = U(x) - log|det dx/dz| so each coupling contributes + sum log alpha to U~:
 //   b = (b' - beta)/alpha  =>  dU~/dalpha = (1 - gb*b)/alpha,  dU~/dbeta = -gb/alpha,  dU~/db' = gb/alpha.
-template <int E>
+template <int E, bool SB>
 __device__ __forceinline__ void coupling_unwind(const FlowDesc& F, const Geom& g, int l, float (&lo)[E], float (&hi)[E],
                                                 float (&glo)[E], float (&ghi)[E], float* scr) {
   float ua[E], ub[E], ua_x = 0.f, ub_x = 0.f;
   float dua_x = 0.f, dub_x = 0.f;
+  float hid[kSmallH];
   const bool src_is_hi = (l & 1) == 0;
   const int shift = src_is_hi ? F.db - F.da : 0;
   const bool has_x = shift > 0;
   const int nt_main = src_is_hi ? F.da : F.db;
+  const int Woff = F.off_coupling + l * F.coupling_stride;
   swap_halves(lo, hi, src_is_hi);
   swap_halves(glo, ghi, src_is_hi);
-  cond_forward<E>(F, g, l, lo, shift, nt_main, has_x, scr, ua, ub, ua_x, ub_x);
+  if (F.small) cond_forward_small<E, SB>(F, g, Woff, lo, shift, nt_main, has_x, hid, ua, ub, ua_x, ub_x);
+  else cond_forward_generic<E>(F, g, F.blob + Woff, lo, shift, nt_main, has_x, scr, ua, ub, ua_x, ub_x);
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     float da_ = 0.f, db_ = 0.f;
@@ -341,50 +500,45 @@ __device__ __forceinline__ void coupling_unwind(const FlowDesc& F, const Geom& g
     lo[0] = fmaf(al, lo[0], be);
     glo[0] *= ra;
   }
-  cond_backward<E>(F, g, l, shift, nt_main, has_x, scr, ua, ub, dua_x, dub_x, glo);
+  if (F.small) cond_backward_small<E, SB>(F, g, Woff, shift, nt_main, has_x, hid, ua, ub, dua_x, dub_x, glo);
+  else cond_backward_generic<E>(F, g, F.blob + Woff, shift, nt_main, has_x, scr, ua, ub, dua_x, dub_x, glo);
   swap_halves(lo, hi, src_is_hi);
   swap_halves(glo, ghi, src_is_hi);
 }
 
 // ---- whole-flow passes on physical coordinates -------------------------------------------------------------
 // forward: x -> z (physical), returns log|det dz/dx| (group-summed)
-template <int E>
+template <int E, bool SB>
 __device__ __forceinline__ float flow_forward(const FlowDesc& F, const Geom& g, float (&lo)[E], float (&hi)[E], float* scr) {
   float ld = 0.f;
-  affine_apply<E, false>(F, g, 0, lo, hi);
+  affine_apply<E, false, SB>(F, g, 0, lo, hi);
   for (int l = 0; l < F.Lc; ++l) {
-    coupling_apply<E, false>(F, g, l, lo, hi, scr, ld);
-    affine_apply<E, false>(F, g, 1 + l, lo, hi);
+    coupling_apply<E, false, SB>(F, g, l, lo, hi, scr, ld);
+    affine_apply<E, false, SB>(F, g, 1 + l, lo, hi);
   }
-  affine_apply<E, false>(F, g, F.Lc + 1, lo, hi);
-  affine_apply<E, false>(F, g, F.Lc + 2, lo, hi);
-  return group_sum(ld, g.gs) + F.blob[F.off_const];
+  return group_sum(ld, g.gs) + ldp<SB>(F, F.off_const);
 }
 // inverse: z (physical) -> x, returns log|det dx/dz|
-template <int E>
+template <int E, bool SB>
 __device__ __forceinline__ float flow_inverse(const FlowDesc& F, const Geom& g, float (&lo)[E], float (&hi)[E], float* scr) {
   float ld = 0.f;
-  affine_apply<E, true>(F, g, F.Lc + 2, lo, hi);
-  affine_apply<E, true>(F, g, F.Lc + 1, lo, hi);
   for (int l = F.Lc - 1; l >= 0; --l) {
-    affine_apply<E, true>(F, g, 1 + l, lo, hi);
-    coupling_apply<E, true>(F, g, l, lo, hi, scr, ld);
+    affine_apply<E, true, SB>(F, g, 1 + l, lo, hi);
+    coupling_apply<E, true, SB>(F, g, l, lo, hi, scr, ld);
   }
-  affine_apply<E, true>(F, g, 0, lo, hi);
-  return -(group_sum(ld, g.gs) + F.blob[F.off_const]);
+  affine_apply<E, true, SB>(F, g, 0, lo, hi);
+  return -(group_sum(ld, g.gs) + ldp<SB>(F, F.off_const));
 }
 // Given x = T^-1(z) in (lo, hi) and dU/dx in (glo, ghi): walk x -> z, leaving z in (lo, hi) and
 // d/dz [ U(T^-1 z) - log|det dT^-1/dz| ] in (glo, ghi).
-template <int E>
+template <int E, bool SB>
 __device__ __forceinline__ void flow_unwind(const FlowDesc& F, const Geom& g, float (&lo)[E], float (&hi)[E],
                                             float (&glo)[E], float (&ghi)[E], float* scr) {
-  affine_unwind<E>(F, g, 0, lo, hi, glo, ghi);
+  affine_unwind<E, SB>(F, g, 0, lo, hi, glo, ghi);
   for (int l = 0; l < F.Lc; ++l) {
-    coupling_unwind<E>(F, g, l, lo, hi, glo, ghi, scr);
-    affine_unwind<E>(F, g, 1 + l, lo, hi, glo, ghi);
+    coupling_unwind<E, SB>(F, g, l, lo, hi, glo, ghi, scr);
+    affine_unwind<E, SB>(F, g, 1 + l, lo, hi, glo, ghi);
   }
-  affine_unwind<E>(F, g, F.Lc + 1, lo, hi, glo, ghi);
-  affine_unwind<E>(F, g, F.Lc + 2, lo, hi, glo, ghi);
 }
 
 // log N(z; 0, I)  (oracle FlowRef.base_log_prob)

@@ -19,6 +19,7 @@ struct FlowSmem {
   FlowDesc F;
   float* scr;
 };
+template <bool SB>
 __device__ __forceinline__ FlowSmem flow_smem_init(unsigned char* smem, const FlowArgs& A, bool with_stats) {
   FlowSmem S;
   size_t off = 0;
@@ -28,13 +29,14 @@ __device__ __forceinline__ FlowSmem flow_smem_init(unsigned char* smem, const Fl
   }
   float* fbase = reinterpret_cast<float*>(smem + off);
   const float* blob = A.blob;
-  if (A.stage_blob) {
-    for (long long i = threadIdx.x; i < A.blob_floats; i += blockDim.x) fbase[i] = __ldg(A.blob + i);
+  if (SB) {
+    for (int i = threadIdx.x; i < (int)A.blob_floats; i += blockDim.x) fbase[i] = __ldg(A.blob + i);
     blob = fbase;
-    fbase += (A.blob_floats + 3) & ~3ll;
+    fbase += ((int)A.blob_floats + 3) & ~3;
     __syncthreads();
   }
   S.F = make_flow_desc(blob, A.d, A.Lc, A.M, A.H);
+  if (SB) S.F.sbase = (unsigned)__cvta_generic_to_shared(blob);
   S.scr = fbase + (size_t)(threadIdx.x / A.gs) * S.F.scratch;
   return S;
 }

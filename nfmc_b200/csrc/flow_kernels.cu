@@ -15,12 +15,12 @@
 
 namespace nfmc {
 
-template <int E>
+template <int E, bool SB>
 __global__ void __launch_bounds__(kThreads) flow_pass_kernel(FlowArgs A, int mode, const float* __restrict__ in,
                                                             float* __restrict__ out, float* __restrict__ aux, long long n) {
   extern __shared__ __align__(16) unsigned char smem[];
   const Geom g = make_geom(A.d, A.gs);
-  FlowSmem S = flow_smem_init(smem, A, false);
+  FlowSmem S = flow_smem_init<SB>(smem, A, false);
   const bool flip = (A.Lc & 1) != 0;
   const int cpc = kThreads / A.gs;
   const long long tiles = (n + cpc - 1) / cpc;
@@ -33,8 +33,8 @@ __global__ void __launch_bounds__(kThreads) flow_pass_kernel(FlowArgs A, int mod
     if (mode == PASS_INVERSE && flip) load_chain_flipped(src, g, lo, hi);
     else load_chain(src, g, lo, hi);
     float r;
-    if (mode == PASS_INVERSE) r = flow_inverse<E>(S.F, g, lo, hi, S.scr);
-    else r = flow_forward<E>(S.F, g, lo, hi, S.scr);
+    if (mode == PASS_INVERSE) r = flow_inverse<E, SB>(S.F, g, lo, hi, S.scr);
+    else r = flow_forward<E, SB>(S.F, g, lo, hi, S.scr);
     if (mode == PASS_LOGPROB) r += base_log_prob(g, lo, hi);
     if (active) {
       if (out) {
@@ -47,12 +47,12 @@ __global__ void __launch_bounds__(kThreads) flow_pass_kernel(FlowArgs A, int mod
   }
 }
 
-template <int E>
+template <int E, bool SB>
 __global__ void __launch_bounds__(kThreads) flow_sample_kernel(FlowArgs A, RngArgs R, long long chain0, float* __restrict__ x,
                                                               float* __restrict__ logq, long long n) {
   extern __shared__ __align__(16) unsigned char smem[];
   const Geom g = make_geom(A.d, A.gs);
-  FlowSmem S = flow_smem_init(smem, A, false);
+  FlowSmem S = flow_smem_init<SB>(smem, A, false);
   const bool flip = (A.Lc & 1) != 0;
   const int cpc = kThreads / A.gs;
   const long long tiles = (n + cpc - 1) / cpc;
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kThreads) flow_sample_kernel(FlowArgs A, RngAr
     float lo[E], hi[E];
     draw_base<E>(R, g, flip, n, chain, chain0, 0, lo, hi);
     const float blp = base_log_prob(g, lo, hi);
-    const float ld = flow_inverse<E>(S.F, g, lo, hi, S.scr);
+    const float ld = flow_inverse<E, SB>(S.F, g, lo, hi, S.scr);
     if (active) {
       store_chain(x + chain * (long long)A.d, g, lo, hi);
       if (logq && g.j == 0) logq[chain] = blp - ld;
@@ -77,12 +77,12 @@ __global__ void __launch_bounds__(kThreads) flow_sample_kernel(FlowArgs A, RngAr
 // ---------------------------------------------------------------------------------------------------------
 
 
-template <int E>
+template <int E, bool SB>
 __global__ void __launch_bounds__(kThreads) jump_kernel(const JumpArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ChainArgs& C = A.c;
   const Geom g = make_geom(C.d, C.gs);
-  FlowSmem S = flow_smem_init(smem, A.f, true);
+  FlowSmem S = flow_smem_init<SB>(smem, A.f, true);
   const bool flip = (A.f.Lc & 1) != 0;
   const int cpc = kThreads / C.gs;
   const long long tiles = (C.n + cpc - 1) / cpc;
@@ -108,14 +108,14 @@ __global__ void __launch_bounds__(kThreads) jump_kernel(const JumpArgs A) {
         float tlo[E], thi[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) { tlo[e] = lo[e]; thi[e] = hi[e]; }
-        const float ld = flow_forward<E>(S.F, g, tlo, thi, S.scr);
+        const float ld = flow_forward<E, SB>(S.F, g, tlo, thi, S.scr);
         f_x = base_log_prob(g, tlo, thi) + ld;
       }
       // x', log q(x') = flow.sample(n, return_log_prob=True)   (jump.py:205, imh.py:221)
       float plo[E], phi[E];
       const uint32_t ubits = draw_base<E>(C.rng, g, flip, C.n, chain, C.chain0, k, plo, phi);
       const float blp = base_log_prob(g, plo, phi);
-      const float ldi = flow_inverse<E>(S.F, g, plo, phi, S.scr);
+      const float ldi = flow_inverse<E, SB>(S.F, g, plo, phi, S.scr);
       const float f_p = blp - ldi;
       bool accept = true;
       float u_p = 0.f;
@@ -170,21 +170,36 @@ __global__ void __launch_bounds__(kThreads) jump_kernel(const JumpArgs A) {
 template <int E>
 int launch_flow_pass(const FlowArgs& A, int mode, const float* in, float* out, float* aux, long long n, int grid,
                      size_t smem, cudaStream_t s) {
-  NFMC_SET_SMEM_RET(flow_pass_kernel<E>, smem);
-  flow_pass_kernel<E><<<grid, kThreads, smem, s>>>(A, mode, in, out, aux, n);
+  if (A.stage_blob) {
+    NFMC_SET_SMEM_RET((flow_pass_kernel<E, true>), smem);
+    flow_pass_kernel<E, true><<<grid, kThreads, smem, s>>>(A, mode, in, out, aux, n);
+  } else {
+    NFMC_SET_SMEM_RET((flow_pass_kernel<E, false>), smem);
+    flow_pass_kernel<E, false><<<grid, kThreads, smem, s>>>(A, mode, in, out, aux, n);
+  }
   return check_cuda(cudaGetLastError(), "flow_pass_kernel launch");
 }
 template <int E>
 int launch_flow_sample(const FlowArgs& A, const RngArgs& R, long long chain0, float* x, float* logq, long long n, int grid,
                        size_t smem, cudaStream_t s) {
-  NFMC_SET_SMEM_RET(flow_sample_kernel<E>, smem);
-  flow_sample_kernel<E><<<grid, kThreads, smem, s>>>(A, R, chain0, x, logq, n);
+  if (A.stage_blob) {
+    NFMC_SET_SMEM_RET((flow_sample_kernel<E, true>), smem);
+    flow_sample_kernel<E, true><<<grid, kThreads, smem, s>>>(A, R, chain0, x, logq, n);
+  } else {
+    NFMC_SET_SMEM_RET((flow_sample_kernel<E, false>), smem);
+    flow_sample_kernel<E, false><<<grid, kThreads, smem, s>>>(A, R, chain0, x, logq, n);
+  }
   return check_cuda(cudaGetLastError(), "flow_sample_kernel launch");
 }
 template <int E>
 int launch_jump(const JumpArgs& A, int grid, size_t smem, cudaStream_t s) {
-  NFMC_SET_SMEM_RET(jump_kernel<E>, smem);
-  jump_kernel<E><<<grid, kThreads, smem, s>>>(A);
+  if (A.f.stage_blob) {
+    NFMC_SET_SMEM_RET((jump_kernel<E, true>), smem);
+    jump_kernel<E, true><<<grid, kThreads, smem, s>>>(A);
+  } else {
+    NFMC_SET_SMEM_RET((jump_kernel<E, false>), smem);
+    jump_kernel<E, false><<<grid, kThreads, smem, s>>>(A);
+  }
   return check_cuda(cudaGetLastError(), "jump_kernel launch");
 }
 template int launch_flow_pass<NFMC_ONLY_E>(const FlowArgs&, int, const float*, float*, float*, long long, int, size_t, cudaStream_t);

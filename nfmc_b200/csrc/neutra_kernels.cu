@@ -16,14 +16,14 @@
 namespace nfmc {
 
 // U~(z) and its gradient.  (zlo, zhi) physical-order latent; (glo, ghi) receives dU~/dz.
-template <int E>
+template <int E, bool SB>
 __device__ __forceinline__ float neutra_value_grad(const FlowDesc& F, int pot_kind, const PotParams& P, const Geom& g, const float (&zlo)[E],
                                                    const float (&zhi)[E], float (&glo)[E], float (&ghi)[E], float* scr,
                                                    bool want_grad) {
   float xlo[E], xhi[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) { xlo[e] = zlo[e]; xhi[e] = zhi[e]; }
-  const float ld_inv = flow_inverse<E>(F, g, xlo, xhi, scr);                      // neutra.py:60
+  const float ld_inv = flow_inverse<E, SB>(F, g, xlo, xhi, scr);                      // neutra.py:60
   const PotCtx c = pot_prepare_rt<E>(pot_kind, P, g, xlo, xhi);
   const float value = -((-c.u) + ld_inv);                                          // neutra.py:62-64
   if (want_grad) {
@@ -34,19 +34,19 @@ __device__ __forceinline__ float neutra_value_grad(const FlowDesc& F, int pot_ki
       if (kk >= g.da) glo[e] = 0.f;
       if (kk >= g.db) ghi[e] = 0.f;
     }
-    flow_unwind<E>(F, g, xlo, xhi, glo, ghi, scr);
+    flow_unwind<E, SB>(F, g, xlo, xhi, glo, ghi, scr);
   }
   return value;
 }
 
 
 
-template <int E>
+template <int E, bool SB>
 __global__ void __launch_bounds__(kThreads) neutra_hmc_kernel(const NeutraArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ChainArgs& C = A.c;
   const Geom g = make_geom(C.d, C.gs);
-  FlowSmem S = flow_smem_init(smem, A.f, true);
+  FlowSmem S = flow_smem_init<SB>(smem, A.f, true);
   const bool flip = (A.f.Lc & 1) != 0;
   const bool unit_mass = (A.imd == nullptr);
   const int cpc = kThreads / C.gs;
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kThreads) neutra_hmc_kernel(const NeutraArgs A
             zhi[e] = (kk < g.db) ? fmaf(A.tau, phi[e] * mhi[e], zhi[e]) : 0.f;
           }
         }
-        u1 = neutra_value_grad<E>(S.F, A.pot_kind, C.pot, g, zlo, zhi, glo, ghi, S.scr, true);
+        u1 = neutra_value_grad<E, SB>(S.F, A.pot_kind, C.pot, g, zlo, zhi, glo, ghi, S.scr, true);
         if (l == 0) u0 = u1;
         else {
 #pragma unroll
@@ -182,12 +182,12 @@ __global__ void __launch_bounds__(kThreads) neutra_hmc_kernel(const NeutraArgs A
   cta_stats_finish(S.st, C.stats, C.d);
 }
 
-template <int E>
+template <int E, bool SB>
 __global__ void __launch_bounds__(kThreads) neutra_potential_kernel(FlowArgs FA, int pot_kind, PotParams P, const float* __restrict__ z,
                                                                    float* __restrict__ u, float* __restrict__ grad, long long n) {
   extern __shared__ __align__(16) unsigned char smem[];
   const Geom g = make_geom(FA.d, FA.gs);
-  FlowSmem S = flow_smem_init(smem, FA, false);
+  FlowSmem S = flow_smem_init<SB>(smem, FA, false);
   const bool flip = (FA.Lc & 1) != 0;
   const int cpc = kThreads / FA.gs;
   const long long tiles = (n + cpc - 1) / cpc;
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kThreads) neutra_potential_kernel(FlowArgs FA,
     float zlo[E], zhi[E], glo[E], ghi[E];
     const float* src = z + chain * (long long)FA.d;
     if (flip) load_chain_flipped(src, g, zlo, zhi); else load_chain(src, g, zlo, zhi);
-    const float v = neutra_value_grad<E>(S.F, pot_kind, P, g, zlo, zhi, glo, ghi, S.scr, grad != nullptr);
+    const float v = neutra_value_grad<E, SB>(S.F, pot_kind, P, g, zlo, zhi, glo, ghi, S.scr, grad != nullptr);
     if (active) {
       if (g.j == 0) u[chain] = v;
       if (grad) {
@@ -212,15 +212,25 @@ __global__ void __launch_bounds__(kThreads) neutra_potential_kernel(FlowArgs FA,
 
 template <int E>
 int launch_neutra_hmc(const NeutraArgs& A, int grid, size_t smem, cudaStream_t s) {
-  NFMC_SET_SMEM_RET(neutra_hmc_kernel<E>, smem);
-  neutra_hmc_kernel<E><<<grid, kThreads, smem, s>>>(A);
+  if (A.f.stage_blob) {
+    NFMC_SET_SMEM_RET((neutra_hmc_kernel<E, true>), smem);
+    neutra_hmc_kernel<E, true><<<grid, kThreads, smem, s>>>(A);
+  } else {
+    NFMC_SET_SMEM_RET((neutra_hmc_kernel<E, false>), smem);
+    neutra_hmc_kernel<E, false><<<grid, kThreads, smem, s>>>(A);
+  }
   return check_cuda(cudaGetLastError(), "neutra_hmc_kernel launch");
 }
 template <int E>
 int launch_neutra_potential(const FlowArgs& FA, int pot_kind, const PotParams& P, const float* z, float* u, float* grad,
                             long long n, int grid, size_t smem, cudaStream_t s) {
-  NFMC_SET_SMEM_RET(neutra_potential_kernel<E>, smem);
-  neutra_potential_kernel<E><<<grid, kThreads, smem, s>>>(FA, pot_kind, P, z, u, grad, n);
+  if (FA.stage_blob) {
+    NFMC_SET_SMEM_RET((neutra_potential_kernel<E, true>), smem);
+    neutra_potential_kernel<E, true><<<grid, kThreads, smem, s>>>(FA, pot_kind, P, z, u, grad, n);
+  } else {
+    NFMC_SET_SMEM_RET((neutra_potential_kernel<E, false>), smem);
+    neutra_potential_kernel<E, false><<<grid, kThreads, smem, s>>>(FA, pot_kind, P, z, u, grad, n);
+  }
   return check_cuda(cudaGetLastError(), "neutra_potential_kernel launch");
 }
 template int launch_neutra_hmc<NFMC_ONLY_E>(const NeutraArgs&, int, size_t, cudaStream_t);

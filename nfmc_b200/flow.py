@@ -224,32 +224,57 @@ class Flow(nn.Module):
 # ------------------------------------------------------------------------------------------------------------------
 # packing
 # ------------------------------------------------------------------------------------------------------------------
+SMALL_H = 8   # conditioners with 2 linear layers and <= 8 hidden units use the register-resident kernel path
+
+
+def blob_floats(d: int, Lc: int, M: int, H: int) -> int:
+    da, db = d // 2, d - d // 2
+    if M == 2 and H <= SMALL_H:
+        per = da * SMALL_H + SMALL_H + db * 2 * SMALL_H + ((2 * db + 3) // 4) * 4
+    elif M == 1:
+        per = da * 2 * db + 2 * db
+    else:
+        per = (da * H + H) + (M - 2) * (H * H + H) + (H * 2 * db + 2 * db)
+    return (Lc + 1) * 4 * d + 4 + Lc * per
+
+
 @torch.no_grad()
 def pack_realnvp(bij: RealNVP) -> torch.Tensor:
     """Pack a RealNVP into the flat fp32 blob the kernels read (layout: nfmc_b200/csrc/flow.cuh header).
 
     Reverse permutations are folded in: after r reversals logical position p sits at physical coordinate
     ``p`` (r even) or ``d-1-p`` (r odd); every per-dimension parameter and every conditioner weight is stored
-    at the physical coordinate.  Coupling l (0-based) follows r = l+1 reversals.
+    at the physical coordinate.  Coupling l (0-based) follows r = l+1 reversals.  Elementwise affines that are
+    not separated by a coupling (the last act-norm, the trailing ElementwiseAffine and its ActNorm) are composed
+    into one map.
     """
     d = bij.n_dim
     da, db = d // 2, d - d // 2
     Lc = bij.n_coupling
     M, H = bij.conditioner_shape()
+    small = (M == 2 and H <= SMALL_H)
     layers = list(bij.layers)
-    parts = []
-    affines = [(layers[0], 0)]
-    for l in range(Lc):
-        affines.append((layers[3 + 3 * l], l + 1))
-    affines += [(layers[-2], Lc), (layers[-1], Lc)]
-    log_const = torch.zeros((), dtype=torch.float32)
-    for layer, r in affines:
+
+    def phys(layer, r):
         v = layer.value.detach().to("cpu", torch.float32)
         alpha, log_alpha, beta = _affine(v[:, 0], v[:, 1])
-        log_const = log_const + log_alpha.sum()
         if r % 2 == 1:
             alpha, beta = alpha.flip(0), beta.flip(0)
-        parts += [alpha, beta, 1.0 / alpha]
+        return alpha, beta, log_alpha.sum()
+
+    # groups of affines in forward order: group g sits before coupling g (g < Lc) / after the last coupling (g = Lc)
+    groups = [[phys(layers[0], 0)]]
+    for l in range(Lc):
+        groups.append([phys(layers[3 + 3 * l], l + 1)])
+    groups[-1] += [phys(layers[-2], Lc), phys(layers[-1], Lc)]
+    parts = []
+    log_const = torch.zeros((), dtype=torch.float32)
+    for grp in groups:
+        alpha, beta = torch.ones(d), torch.zeros(d)
+        for a, b, ls in grp:                       # y = a * (alpha x + beta) + b
+            alpha, beta = a * alpha, a * beta + b
+            log_const = log_const + ls
+        parts += [torch.stack([alpha, beta], dim=1).reshape(-1), torch.stack([beta, 1.0 / alpha], dim=1).reshape(-1)]
     parts.append(torch.stack([log_const, torch.zeros(()), torch.zeros(()), torch.zeros(())]))
     for l in range(Lc):
         cpl = layers[2 + 3 * l]
@@ -257,7 +282,22 @@ def pack_realnvp(bij: RealNVP) -> torch.Tensor:
             raise ValueError("all couplings must share the conditioner shape")
         odd = (l + 1) % 2 == 1
         lin = [(m.weight.detach().to("cpu", torch.float32), m.bias.detach().to("cpu", torch.float32)) for m in cpl.linears()]
-        if M >= 2:
+        if small:
+            w1, b1 = lin[0]                                  # [H, da]
+            wl, bl = lin[1]                                  # [2*db, H]
+            w1t = torch.zeros(da, SMALL_H)
+            w1t[:, :H] = (w1.flip(1) if odd else w1).t()     # [ks][h]
+            b1p = torch.zeros(SMALL_H)
+            b1p[:H] = b1
+            wlt = torch.zeros(db, 2, SMALL_H)
+            wlt[:, :, :H] = wl.reshape(db, 2, H)             # [t_log][c][h]
+            blt = bl.reshape(db, 2)                          # [t_log][c]
+            if odd:
+                wlt, blt = wlt.flip(0), blt.flip(0)
+            blp = torch.zeros(((2 * db + 3) // 4) * 4)
+            blp[: 2 * db] = blt.reshape(-1)
+            parts += [w1t.reshape(-1), b1p, wlt.reshape(-1), blp]
+        elif M >= 2:
             w1, b1 = lin[0]                                  # [H, da]
             parts += [(w1.flip(1) if odd else w1).reshape(-1), b1]
             for wm, bm in lin[1:-1]:                         # [H_out, H_in] -> [H_in][H_out]
@@ -276,9 +316,7 @@ def pack_realnvp(bij: RealNVP) -> torch.Tensor:
                 wl, bl = wl.flip(0).flip(2), bl.flip(1)
             parts += [wl.contiguous().reshape(-1), bl.contiguous().reshape(-1)]
     blob = torch.cat([p.reshape(-1) for p in parts]).contiguous()
-    expect = (Lc + 3) * 3 * d + 4 + Lc * ((da * 2 * db + 2 * db) if M == 1 else
-                                          ((da * H + H) + (M - 2) * (H * H + H) + (H * 2 * db + 2 * db)))
-    assert blob.numel() == expect, (blob.numel(), expect)
+    assert blob.numel() == blob_floats(d, Lc, M, H), (blob.numel(), blob_floats(d, Lc, M, H))
     return blob
 
 

@@ -66,18 +66,22 @@ def test_flow_state_dict_is_interchangeable_with_oracle():
 
 
 def test_pack_folds_reversals():
-    """Packed affine parameters of layers behind an odd number of reversals are stored flipped."""
-    from nfmc_b200.flow import Flow, RealNVP, pack_realnvp, _affine
+    """Packed affine parameters of layers behind an odd number of reversals are stored flipped; the trailing
+    ElementwiseAffine + ActNorm are composed into the last act-norm."""
+    from nfmc_b200.flow import Flow, RealNVP, pack_realnvp, blob_floats
     f = Flow(RealNVP((6,), n_layers=2))
     with torch.no_grad():
         f.bijection.layers[3].value[:, 1] = torch.arange(6.0)     # act-norm after coupling 0: 1 reversal
         f.bijection.layers[6].value[:, 1] = torch.arange(6.0)     # act-norm after coupling 1: 2 reversals
+        f.bijection.layers[8].value[:, 1] = 2.0                   # trailing act-norm (composed into affine 2)
     blob = pack_realnvp(f.bijection)
     d = 6
-    beta_an0 = blob[1 * 3 * d + d: 1 * 3 * d + 2 * d]
-    beta_an1 = blob[2 * 3 * d + d: 2 * 3 * d + 2 * d]
-    assert torch.equal(beta_an0, (torch.arange(6.0) / 2).flip(0))
-    assert torch.equal(beta_an1, torch.arange(6.0) / 2)
+    assert blob.numel() == blob_floats(6, 2, 2, 4)
+    fwd1 = blob[1 * 4 * d: 1 * 4 * d + 2 * d].reshape(d, 2)       # {alpha, beta} of affine 1
+    fwd2 = blob[2 * 4 * d: 2 * 4 * d + 2 * d].reshape(d, 2)
+    assert torch.allclose(fwd1[:, 1], (torch.arange(6.0) / 2).flip(0))
+    assert torch.allclose(fwd2[:, 1], torch.arange(6.0) / 2 + 1.0)
+    assert torch.allclose(fwd1[:, 0], torch.ones(6), atol=1e-6)
 
 
 def test_records_contract():
