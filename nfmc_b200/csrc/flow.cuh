@@ -17,7 +17,7 @@
 // Blob layout (fp32), da = d/2, db = d - da:
 //   [ (Lc+1) elementwise affines ]  affine 0 = the leading ElementwiseAffine; affine l+1 = the act-norm after coupling l;
 //                                   the last one also absorbs the trailing ElementwiseAffine + ActNorm (composed at
-//                                   pack time).  Each: fwd float2[d] {alpha, beta}, inv float2[d] {beta, 1/alpha}.
+//                                   pack time).  Each: fwd float2[d] {alpha, beta}, inv float2[d] {1/alpha, -beta/alpha}.
 //   [ 4 floats ] [0] = sum over all elementwise affines of sum_i log alpha_i
 //   [ Lc couplings ]
 //        small  :  W1T[da][8] | b1[8] | WlT[db][2][8] | bl[db][2] (+pad to 4)  (zero padded in h)
@@ -101,34 +101,33 @@ __device__ __forceinline__ float fast_tanh(float v) {
   return 1.f - __fdividef(2.f, t + 1.f);
 }
 
-// ---- elementwise affine (branch-free: clamped parameter index, invalid slots stay 0) -----------------------------------
-template <int E, bool INV, bool SB>
-__device__ __forceinline__ void affine_apply(const FlowDesc& F, const Geom& g, int a, float (&lo)[E], float (&hi)[E]) {
-  const int base = a * 4 * F.d + (INV ? 2 * F.d : 0);
+// ---- elementwise affine (branch-free: clamped parameter index, invalid slots stay 0).  Both directions are the same
+//      fma: forward parameters {alpha, beta}, inverse parameters {1/alpha, -beta/alpha}; `inv` only selects the table.
+template <int E, bool SB, bool X>
+__device__ __forceinline__ void affine_apply(const FlowDesc& F, const Geom& g, int a, bool inv, float (&lo)[E], float (&hi)[E]) {
+  const int base = a * 4 * F.d + (inv ? 2 * F.d : 0);
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     const int k = g.j + g.gs * e;
-    const bool vl = k < g.da, vh = k < g.db;
+    const bool vl = slot_ok<X, E>(e, k, g.da), vh = slot_ok<X, E>(e, k, g.db);
     const float2 pl = ldp2<SB>(F, base + 2 * (vl ? k : 0));
     const float2 ph = ldp2<SB>(F, base + 2 * (g.da + (vh ? k : 0)));
-    const float nl = INV ? (lo[e] - pl.x) * pl.y : fmaf(pl.x, lo[e], pl.y);
-    const float nh = INV ? (hi[e] - ph.x) * ph.y : fmaf(ph.x, hi[e], ph.y);
-    lo[e] = vl ? nl : 0.f;
-    hi[e] = vh ? nh : 0.f;
+    lo[e] = vl ? fmaf(pl.x, lo[e], pl.y) : 0.f;
+    hi[e] = vh ? fmaf(ph.x, hi[e], ph.y) : 0.f;
   }
 }
 // undo an inverse affine (state <- alpha*state + beta) while pulling the gradient back (grad <- grad / alpha)
-template <int E, bool SB>
+template <int E, bool SB, bool X>
 __device__ __forceinline__ void affine_unwind(const FlowDesc& F, const Geom& g, int a, float (&lo)[E], float (&hi)[E],
                                               float (&glo)[E], float (&ghi)[E]) {
   const int fw = a * 4 * F.d, iv = fw + 2 * F.d;
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     const int k = g.j + g.gs * e;
-    const bool vl = k < g.da, vh = k < g.db;
+    const bool vl = slot_ok<X, E>(e, k, g.da), vh = slot_ok<X, E>(e, k, g.db);
     const int il = 2 * (vl ? k : 0), ih = 2 * (g.da + (vh ? k : 0));
     const float2 pl = ldp2<SB>(F, fw + il), ph = ldp2<SB>(F, fw + ih);
-    const float rl = ldp<SB>(F, iv + il + 1), rh = ldp<SB>(F, iv + ih + 1);
+    const float rl = ldp<SB>(F, iv + il), rh = ldp<SB>(F, iv + ih);
     lo[e] = vl ? fmaf(pl.x, lo[e], pl.y) : 0.f;
     hi[e] = vh ? fmaf(ph.x, hi[e], ph.y) : 0.f;
     glo[e] = vl ? glo[e] * rl : 0.f;
@@ -140,7 +139,7 @@ __device__ __forceinline__ void affine_unwind(const FlowDesc& F, const Geom& g, 
 // src[e] holds source element ks = j + gs*e - shift (valid iff 0 <= ks < da).  Targets: slot e of the other half has
 // packed index t = j + gs*e (valid iff t < nt_main), plus, when has_x, one extra target t = da (the middle element of
 // an odd-d chain, which physically is hi[0] of lane 0).  hid[] returns the hidden activations (for the backward).
-template <int E, bool SB>
+template <int E, bool SB, bool X>
 __device__ __forceinline__ void cond_forward_small(const FlowDesc& F, const Geom& g, int W, const float (&src)[E],
                                                    int shift, int nt_main, bool has_x, float (&hid)[kSmallH], float (&ua)[E],
                                                    float (&ub)[E], float& ua_x, float& ub_x) {
@@ -151,7 +150,7 @@ __device__ __forceinline__ void cond_forward_small(const FlowDesc& F, const Geom
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     const int ks = g.j + g.gs * e - shift;
-    const bool ok = ks >= 0 && ks < da;
+    const bool ok = (e > 0 || ks >= 0) && slot_ok<X, E>(e, ks, da);   // in an exact layout only slot 0 / the last slot can be invalid
     const float v = ok ? src[e] : 0.f;
     const int w = W + (ok ? ks : 0) * kSmallH;
     const float4 w0 = ldp4<SB>(F, w), w1 = ldp4<SB>(F, w + 4);
@@ -166,7 +165,7 @@ __device__ __forceinline__ void cond_forward_small(const FlowDesc& F, const Geom
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     const int t = g.j + g.gs * e;
-    const int tc = t < nt_main ? t : 0;
+    const int tc = slot_ok<X, E>(e, t, nt_main) ? t : 0;
     const int w = Wl + tc * 2 * kSmallH;
     const float4 a0 = ldp4<SB>(F, w), a1 = ldp4<SB>(F, w + 4), c0 = ldp4<SB>(F, w + 8), c1 = ldp4<SB>(F, w + 12);
     const float2 b = ldp2<SB>(F, bl + 2 * tc);
@@ -194,7 +193,7 @@ __device__ __forceinline__ void cond_forward_small(const FlowDesc& F, const Geom
 }
 
 // input-VJP of the small conditioner: dsrc[e] += sum_out d_out * d out / d src[e]
-template <int E, bool SB>
+template <int E, bool SB, bool X>
 __device__ __forceinline__ void cond_backward_small(const FlowDesc& F, const Geom& g, int W, int shift, int nt_main,
                                                     bool has_x, const float (&hid)[kSmallH], const float (&dua)[E],
                                                     const float (&dub)[E], float dua_x, float dub_x, float (&dsrc)[E]) {
@@ -207,7 +206,7 @@ __device__ __forceinline__ void cond_backward_small(const FlowDesc& F, const Geo
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     const int t = g.j + g.gs * e;
-    const bool ok = t < nt_main;
+    const bool ok = slot_ok<X, E>(e, t, nt_main);
     const float va = ok ? dua[e] : 0.f, vb = ok ? dub[e] : 0.f;
     const int w = Wl + (ok ? t : 0) * 2 * kSmallH;
     const float4 a0 = ldp4<SB>(F, w), a1 = ldp4<SB>(F, w + 4), c0 = ldp4<SB>(F, w + 8), c1 = ldp4<SB>(F, w + 12);
@@ -227,7 +226,7 @@ __device__ __forceinline__ void cond_backward_small(const FlowDesc& F, const Geo
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     const int ks = g.j + g.gs * e - shift;
-    const bool ok = ks >= 0 && ks < da;
+    const bool ok = (e > 0 || ks >= 0) && slot_ok<X, E>(e, ks, da);
     const int w = W + (ok ? ks : 0) * kSmallH;
     const float4 w0 = ldp4<SB>(F, w), w1 = ldp4<SB>(F, w + 4);
     float s = w0.x * dpre[0];
@@ -420,11 +419,12 @@ __device__ __forceinline__ void swap_halves(float (&a)[E], float (&b)[E], bool d
   }
 }
 
-// ---- affine coupling layer l; INV = false: x -> z direction, true: z -> x.  ld accumulates THIS LANE's share of
-//      sum_t log alpha_t (caller group-sums once per pass).  When the source is the high half the two register
-//      arrays are swapped around the layer so that there is a single conditioner call site.
-template <int E, bool INV, bool SB>
-__device__ __forceinline__ void coupling_apply(const FlowDesc& F, const Geom& g, int l, float (&lo)[E], float (&hi)[E],
+// ---- affine coupling layer l; inv = false: x -> z direction, true: z -> x (one code instance for both: the target
+//      update is fma(r, b, s) with (r, s) = (alpha, beta) or (1/alpha, -beta/alpha)).  ld accumulates THIS LANE's share
+//      of sum_t log alpha_t (the caller group-sums once per pass and applies the sign).  When the source is the high
+//      half the two register arrays are swapped around the layer so that there is a single conditioner call site.
+template <int E, bool SB, bool X>
+__device__ __forceinline__ void coupling_apply(const FlowDesc& F, const Geom& g, int l, bool inv, float (&lo)[E], float (&hi)[E],
                                                float* scr, float& ld) {
   float ua[E], ub[E], ua_x, ub_x;
   const bool src_is_hi = (l & 1) == 0;
@@ -435,23 +435,25 @@ __device__ __forceinline__ void coupling_apply(const FlowDesc& F, const Geom& g,
   swap_halves(lo, hi, src_is_hi);  // lo = source array, hi = target array
   if (F.small) {
     float hid[kSmallH];
-    cond_forward_small<E, SB>(F, g, Woff, lo, shift, nt_main, has_x, hid, ua, ub, ua_x, ub_x);
+    cond_forward_small<E, SB, X>(F, g, Woff, lo, shift, nt_main, has_x, hid, ua, ub, ua_x, ub_x);
   } else {
     cond_forward_generic<E>(F, g, F.blob + Woff, lo, shift, nt_main, has_x, scr, ua, ub, ua_x, ub_x);
   }
 #pragma unroll
   for (int e = 0; e < E; ++e) {
-    const bool ok = g.j + g.gs * e < nt_main;
+    const bool ok = slot_ok<X, E>(e, g.j + g.gs * e, nt_main);
     float al, be;
     affine_coef(ua[e], ub[e], al, be);
-    const float nv = INV ? __fdividef(hi[e] - be, al) : fmaf(al, hi[e], be);
-    hi[e] = ok ? nv : hi[e];
+    const float ra = __fdividef(1.f, al);
+    const float r = inv ? ra : al, s = inv ? -be * ra : be;
+    hi[e] = ok ? fmaf(r, hi[e], s) : hi[e];
     ld += ok ? __logf(al) : 0.f;
   }
   if (has_x && g.j == 0) {  // middle element of an odd-d chain: physically hi[0], here slot 0 of the source array
     float al, be;
     affine_coef(ua_x, ub_x, al, be);
-    lo[0] = INV ? __fdividef(lo[0] - be, al) : fmaf(al, lo[0], be);
+    const float ra = __fdividef(1.f, al);
+    lo[0] = fmaf(inv ? ra : al, lo[0], inv ? -be * ra : be);
     ld += __logf(al);
   }
   swap_halves(lo, hi, src_is_hi);
@@ -461,7 +463,7 @@ __device__ __forceinline__ void coupling_apply(const FlowDesc& F, const Geom& g,
 // the gradient of U~ with respect to it.  On return they hold its INPUT (a, b') and the gradient with respect to
 // that input, where U~ = U(x) - log|det dx/dz| so each coupling contributes + sum log alpha to U~:
 //   b = (b' - beta)/alpha  =>  dU~/dalpha = (1 - gb*b)/alpha,  dU~/dbeta = -gb/alpha,  dU~/db' = gb/alpha.
-template <int E, bool SB>
+template <int E, bool SB, bool X>
 __device__ __forceinline__ void coupling_unwind(const FlowDesc& F, const Geom& g, int l, float (&lo)[E], float (&hi)[E],
                                                 float (&glo)[E], float (&ghi)[E], float* scr) {
   float ua[E], ub[E], ua_x = 0.f, ub_x = 0.f;
@@ -474,12 +476,12 @@ __device__ __forceinline__ void coupling_unwind(const FlowDesc& F, const Geom& g
   const int Woff = F.off_coupling + l * F.coupling_stride;
   swap_halves(lo, hi, src_is_hi);
   swap_halves(glo, ghi, src_is_hi);
-  if (F.small) cond_forward_small<E, SB>(F, g, Woff, lo, shift, nt_main, has_x, hid, ua, ub, ua_x, ub_x);
+  if (F.small) cond_forward_small<E, SB, X>(F, g, Woff, lo, shift, nt_main, has_x, hid, ua, ub, ua_x, ub_x);
   else cond_forward_generic<E>(F, g, F.blob + Woff, lo, shift, nt_main, has_x, scr, ua, ub, ua_x, ub_x);
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     float da_ = 0.f, db_ = 0.f;
-    if (g.j + g.gs * e < nt_main) {
+    if (slot_ok<X, E>(e, g.j + g.gs * e, nt_main)) {
       float al, be;
       affine_coef(ua[e], ub[e], al, be);
       const float ra = __fdividef(1.f, al);
@@ -500,44 +502,45 @@ __device__ __forceinline__ void coupling_unwind(const FlowDesc& F, const Geom& g
     lo[0] = fmaf(al, lo[0], be);
     glo[0] *= ra;
   }
-  if (F.small) cond_backward_small<E, SB>(F, g, Woff, shift, nt_main, has_x, hid, ua, ub, dua_x, dub_x, glo);
+  if (F.small) cond_backward_small<E, SB, X>(F, g, Woff, shift, nt_main, has_x, hid, ua, ub, dua_x, dub_x, glo);
   else cond_backward_generic<E>(F, g, F.blob + Woff, shift, nt_main, has_x, scr, ua, ub, dua_x, dub_x, glo);
   swap_halves(lo, hi, src_is_hi);
   swap_halves(glo, ghi, src_is_hi);
 }
 
-// ---- whole-flow passes on physical coordinates -------------------------------------------------------------
-// forward: x -> z (physical), returns log|det dz/dx| (group-summed)
-template <int E, bool SB>
-__device__ __forceinline__ float flow_forward(const FlowDesc& F, const Geom& g, float (&lo)[E], float (&hi)[E], float* scr) {
+// ---- whole-flow pass on physical coordinates: one loop over the 2*Lc+1 layers, walked forwards (x -> z, returns
+//      log|det dz/dx|) or backwards (z -> x, returns log|det dx/dz|).  A single code instance of each layer type, so the
+//      instruction footprint stays small (the jump executes this code once per launch per warp: fetch matters).
+template <int E, bool SB, bool X>
+__device__ __forceinline__ float flow_pass(const FlowDesc& F, const Geom& g, bool inv, float (&lo)[E], float (&hi)[E], float* scr) {
   float ld = 0.f;
-  affine_apply<E, false, SB>(F, g, 0, lo, hi);
-  for (int l = 0; l < F.Lc; ++l) {
-    coupling_apply<E, false, SB>(F, g, l, lo, hi, scr, ld);
-    affine_apply<E, false, SB>(F, g, 1 + l, lo, hi);
+  const int n_ops = 2 * F.Lc + 1;
+#pragma unroll 1
+  for (int i = 0; i < n_ops; ++i) {
+    const int op = inv ? n_ops - 1 - i : i;
+    if (op & 1) coupling_apply<E, SB, X>(F, g, op >> 1, inv, lo, hi, scr, ld);
+    else affine_apply<E, SB, X>(F, g, op >> 1, inv, lo, hi);
   }
-  return group_sum(ld, g.gs) + ldp<SB>(F, F.off_const);
+  const float tot = group_sum(ld, g.gs) + ldp<SB>(F, F.off_const);
+  return inv ? -tot : tot;
 }
-// inverse: z (physical) -> x, returns log|det dx/dz|
-template <int E, bool SB>
+template <int E, bool SB, bool X>
+__device__ __forceinline__ float flow_forward(const FlowDesc& F, const Geom& g, float (&lo)[E], float (&hi)[E], float* scr) {
+  return flow_pass<E, SB, X>(F, g, false, lo, hi, scr);
+}
+template <int E, bool SB, bool X>
 __device__ __forceinline__ float flow_inverse(const FlowDesc& F, const Geom& g, float (&lo)[E], float (&hi)[E], float* scr) {
-  float ld = 0.f;
-  for (int l = F.Lc - 1; l >= 0; --l) {
-    affine_apply<E, true, SB>(F, g, 1 + l, lo, hi);
-    coupling_apply<E, true, SB>(F, g, l, lo, hi, scr, ld);
-  }
-  affine_apply<E, true, SB>(F, g, 0, lo, hi);
-  return -(group_sum(ld, g.gs) + ldp<SB>(F, F.off_const));
+  return flow_pass<E, SB, X>(F, g, true, lo, hi, scr);
 }
 // Given x = T^-1(z) in (lo, hi) and dU/dx in (glo, ghi): walk x -> z, leaving z in (lo, hi) and
 // d/dz [ U(T^-1 z) - log|det dT^-1/dz| ] in (glo, ghi).
-template <int E, bool SB>
+template <int E, bool SB, bool X>
 __device__ __forceinline__ void flow_unwind(const FlowDesc& F, const Geom& g, float (&lo)[E], float (&hi)[E],
                                             float (&glo)[E], float (&ghi)[E], float* scr) {
-  affine_unwind<E, SB>(F, g, 0, lo, hi, glo, ghi);
+  affine_unwind<E, SB, X>(F, g, 0, lo, hi, glo, ghi);
   for (int l = 0; l < F.Lc; ++l) {
-    coupling_unwind<E, SB>(F, g, l, lo, hi, glo, ghi, scr);
-    affine_unwind<E, SB>(F, g, 1 + l, lo, hi, glo, ghi);
+    coupling_unwind<E, SB, X>(F, g, l, lo, hi, glo, ghi, scr);
+    affine_unwind<E, SB, X>(F, g, 1 + l, lo, hi, glo, ghi);
   }
 }
 

@@ -60,8 +60,8 @@ static int launch_jump(const nfmc_potential* pot, const nfmc_realnvp* flow, floa
   A.c.stats = StatsArgs{stats ? stats->sum_x : nullptr, stats ? stats->sum_x2 : nullptr, stats ? stats->counts : nullptr};
   A.c.sink = SinkArgs{sink ? sink->samples : nullptr, sink ? sink->seen0 : 0, (sink && sink->thinning > 0) ? sink->thinning : 1};
   A.logq_x = logq_x; A.recompute_logq = recompute_logq; A.adjusted = adjusted;
-  const size_t smem = plan_flow_smem(A.f, flow, L, true);
-  const int grid = grid_for(n, L.gs, 4);
+  const size_t smem = plan_flow_smem(A.f, flow, L, true, true);
+  const int grid = grid_for(n, L.gs, 3);
   cudaStream_t s = (cudaStream_t)stream;
   A.pot_kind = pot->kind;
   NFMC_DISPATCH_E(L.E, { return launch_jump<E>(A, grid, smem, s); });

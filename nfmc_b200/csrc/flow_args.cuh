@@ -11,6 +11,8 @@ struct FlowArgs {
   const float* blob;
   long long blob_floats;
   int stage_blob;  // copy the blob to shared memory first
+  int exact;       // exact lane layout (host_common.cuh: Layout::exact)
+  int mom_slots;   // per-lane running-moment slots (float4 each) carved after the scratch, 0 if none
 };
 
 // shared-memory plan of the flow kernels: [cta stats] [blob (optional)] [scratch per group]
@@ -18,6 +20,7 @@ struct FlowSmem {
   CtaStats st;
   FlowDesc F;
   float* scr;
+  float4* mom;   // this lane's running moments, slot e at mom[e * kThreads]
 };
 template <bool SB>
 __device__ __forceinline__ FlowSmem flow_smem_init(unsigned char* smem, const FlowArgs& A, bool with_stats) {
@@ -38,6 +41,9 @@ __device__ __forceinline__ FlowSmem flow_smem_init(unsigned char* smem, const Fl
   S.F = make_flow_desc(blob, A.d, A.Lc, A.M, A.H);
   if (SB) S.F.sbase = (unsigned)__cvta_generic_to_shared(blob);
   S.scr = fbase + (size_t)(threadIdx.x / A.gs) * S.F.scratch;
+  float* after = fbase + (size_t)(kThreads / A.gs) * S.F.scratch;
+  after = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(after) + 15) & ~uintptr_t(15));
+  S.mom = reinterpret_cast<float4*>(after) + threadIdx.x;
   return S;
 }
 
@@ -75,15 +81,18 @@ inline int validate_flow(const nfmc_realnvp* f) {
 }
 
 // decide shared-memory plan; returns bytes, sets A.stage_blob
-inline size_t plan_flow_smem(FlowArgs& A, const nfmc_realnvp* f, const Layout& L, bool with_stats) {
+inline size_t plan_flow_smem(FlowArgs& A, const nfmc_realnvp* f, const Layout& L, bool with_stats, bool with_moments = false) {
   A.d = f->d; A.gs = L.gs; A.Lc = f->n_coupling; A.M = f->n_linear; A.H = f->hidden;
   A.blob = f->blob; A.blob_floats = f->blob_floats;
   const FlowDesc F = make_flow_desc(nullptr, A.d, A.Lc, A.M, A.H);
   size_t base = with_stats ? ((cta_stats_bytes_host(A.d) + 15) & ~size_t(15)) : 0;
   const size_t scratch = (size_t)(kThreads / L.gs) * F.scratch * sizeof(float);
   const size_t blob_b = (size_t)((A.blob_floats + 3) & ~3ll) * sizeof(float);
-  A.stage_blob = (base + scratch + blob_b <= 96 * 1024) ? 1 : 0;
-  return base + scratch + (A.stage_blob ? blob_b : 0);
+  A.exact = L.exact ? 1 : 0;
+  A.mom_slots = with_moments ? L.E : 0;
+  const size_t mom_b = with_moments ? (size_t)L.E * kThreads * sizeof(float4) + 16 : 0;
+  A.stage_blob = (base + scratch + blob_b + mom_b <= 72 * 1024) ? 1 : 0;
+  return base + scratch + (A.stage_blob ? blob_b : 0) + mom_b;
 }
 
 

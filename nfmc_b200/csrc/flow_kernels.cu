@@ -15,7 +15,7 @@
 
 namespace nfmc {
 
-template <int E, bool SB>
+template <int E, bool SB, bool X>
 __global__ void __launch_bounds__(kThreads) flow_pass_kernel(FlowArgs A, int mode, const float* __restrict__ in,
                                                             float* __restrict__ out, float* __restrict__ aux, long long n) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -32,9 +32,7 @@ __global__ void __launch_bounds__(kThreads) flow_pass_kernel(FlowArgs A, int mod
     const float* src = in + chain * (long long)A.d;
     if (mode == PASS_INVERSE && flip) load_chain_flipped(src, g, lo, hi);
     else load_chain(src, g, lo, hi);
-    float r;
-    if (mode == PASS_INVERSE) r = flow_inverse<E, SB>(S.F, g, lo, hi, S.scr);
-    else r = flow_forward<E, SB>(S.F, g, lo, hi, S.scr);
+    float r = flow_pass<E, SB, X>(S.F, g, mode == PASS_INVERSE, lo, hi, S.scr);
     if (mode == PASS_LOGPROB) r += base_log_prob(g, lo, hi);
     if (active) {
       if (out) {
@@ -47,7 +45,7 @@ __global__ void __launch_bounds__(kThreads) flow_pass_kernel(FlowArgs A, int mod
   }
 }
 
-template <int E, bool SB>
+template <int E, bool SB, bool X>
 __global__ void __launch_bounds__(kThreads) flow_sample_kernel(FlowArgs A, RngArgs R, long long chain0, float* __restrict__ x,
                                                               float* __restrict__ logq, long long n) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -63,7 +61,7 @@ __global__ void __launch_bounds__(kThreads) flow_sample_kernel(FlowArgs A, RngAr
     float lo[E], hi[E];
     draw_base<E>(R, g, flip, n, chain, chain0, 0, lo, hi);
     const float blp = base_log_prob(g, lo, hi);
-    const float ld = flow_inverse<E, SB>(S.F, g, lo, hi, S.scr);
+    const float ld = flow_inverse<E, SB, X>(S.F, g, lo, hi, S.scr);
     if (active) {
       store_chain(x + chain * (long long)A.d, g, lo, hi);
       if (logq && g.j == 0) logq[chain] = blp - ld;
@@ -77,8 +75,8 @@ __global__ void __launch_bounds__(kThreads) flow_sample_kernel(FlowArgs A, RngAr
 // ---------------------------------------------------------------------------------------------------------
 
 
-template <int E, bool SB>
-__global__ void __launch_bounds__(kThreads) jump_kernel(const JumpArgs A) {
+template <int E, bool SB, bool X>
+__global__ void __launch_bounds__(kThreads, 3) jump_kernel(const JumpArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ChainArgs& C = A.c;
   const Geom g = make_geom(C.d, C.gs);
@@ -94,29 +92,39 @@ __global__ void __launch_bounds__(kThreads) jump_kernel(const JumpArgs A) {
     const long long chain = active ? chain_raw : C.n - 1;
     float* row = C.x + chain * (long long)C.d;
 
-    float lo[E], hi[E], m1lo[E], m1hi[E], m2lo[E], m2hi[E];
+    float lo[E], hi[E];
     load_chain(row, g, lo, hi);
+    const bool multi = C.n_steps > 1;   // one step (NF jump): the moments are flushed straight from the registers
+    if (multi) {
 #pragma unroll
-    for (int e = 0; e < E; ++e) m1lo[e] = m1hi[e] = m2lo[e] = m2hi[e] = 0.f;
+      for (int e = 0; e < E; ++e) S.mom[e * kThreads] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     float u_x = 0.f, f_x = 0.f;
     if (A.adjusted) {
       u_x = pot_prepare_rt<E>(A.pot_kind, C.pot, g, lo, hi).u;                                   // jump.py:212
       if (!A.recompute_logq && A.logq_x) f_x = __ldg(A.logq_x + chain);                 // imh.py:214
     }
     for (int k = 0; k < C.n_steps; ++k) {
-      if (A.adjusted && (A.recompute_logq || !A.logq_x)) {                             // jump.py:218 / imh.py:133
-        float tlo[E], thi[E];
-#pragma unroll
-        for (int e = 0; e < E; ++e) { tlo[e] = lo[e]; thi[e] = hi[e]; }
-        const float ld = flow_forward<E, SB>(S.F, g, tlo, thi, S.scr);
-        f_x = base_log_prob(g, tlo, thi) + ld;
-      }
-      // x', log q(x') = flow.sample(n, return_log_prob=True)   (jump.py:205, imh.py:221)
+      // pass 0: log q(x) by a forward pass on a copy of x (jump.py:218 / imh.py:133), skipped when it is cached;
+      // pass 1: x', log q(x') = flow.sample(n, return_log_prob=True) (jump.py:205, imh.py:221).  One flow_pass call site.
       float plo[E], phi[E];
-      const uint32_t ubits = draw_base<E>(C.rng, g, flip, C.n, chain, C.chain0, k, plo, phi);
-      const float blp = base_log_prob(g, plo, phi);
-      const float ldi = flow_inverse<E, SB>(S.F, g, plo, phi, S.scr);
-      const float f_p = blp - ldi;
+      uint32_t ubits = 0;
+      float f_p = 0.f;
+      const bool need_fx = A.adjusted && (A.recompute_logq || !A.logq_x);
+#pragma unroll 1
+      for (int pass = need_fx ? 0 : 1; pass < 2; ++pass) {
+        float blp = 0.f;
+        if (pass == 0) {
+#pragma unroll
+          for (int e = 0; e < E; ++e) { plo[e] = lo[e]; phi[e] = hi[e]; }
+        } else {
+          ubits = draw_base<E>(C.rng, g, flip, C.n, chain, C.chain0, k, plo, phi);
+          blp = base_log_prob(g, plo, phi);
+        }
+        const float ld = flow_pass<E, SB, X>(S.F, g, pass == 1, plo, phi, S.scr);
+        if (pass == 0) f_x = base_log_prob(g, plo, phi) + ld;
+        else f_p = blp - ld;
+      }
       bool accept = true;
       float u_p = 0.f;
       if (A.adjusted) {
@@ -136,14 +144,28 @@ __global__ void __launch_bounds__(kThreads) jump_kernel(const JumpArgs A) {
       u_x = accept ? u_p : u_x;
       f_x = accept ? f_p : f_x;                                                        // imh.py:233
       if (accept && g.j == 0 && active) ++n_acc;
-      accumulate_moments(lo, hi, m1lo, m1hi, m2lo, m2hi);                              // jump.py:240, imh.py:242
+      if (multi) {                                                                     // jump.py:240, imh.py:242
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          float4 m = S.mom[e * kThreads];
+          m.x += lo[e]; m.y += hi[e]; m.z = fmaf(lo[e], lo[e], m.z); m.w = fmaf(hi[e], hi[e], m.w);
+          S.mom[e * kThreads] = m;
+        }
+      }
       if (C.sink.samples && active) sink_store(C.sink, g, C.n, chain, k, lo, hi);      // jump.py:243, imh.py:249
     }
-    if (!active) {
 #pragma unroll
-      for (int e = 0; e < E; ++e) m1lo[e] = m1hi[e] = m2lo[e] = m2hi[e] = 0.f;
+    for (int e = 0; e < E; ++e) {
+      float4 m = multi ? S.mom[e * kThreads] : make_float4(lo[e], hi[e], lo[e] * lo[e], hi[e] * hi[e]);
+      if (!active) m = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int kk = g.j + g.gs * e;
+      const float a = across_groups_sum(m.x, g.gs), b = across_groups_sum(m.y, g.gs);
+      const float c = across_groups_sum(m.z, g.gs), dd = across_groups_sum(m.w, g.gs);
+      if (g.lane < g.gs) {
+        if (kk < g.da) { atomicAdd(S.st.sx + kk, (double)a); atomicAdd(S.st.sx2 + kk, (double)c); }
+        if (kk < g.db) { atomicAdd(S.st.sx + g.da + kk, (double)b); atomicAdd(S.st.sx2 + g.da + kk, (double)dd); }
+      }
     }
-    flush_moments(g, m1lo, m1hi, m2lo, m2hi, S.st.sx, S.st.sx2);
     if (active) {
       store_chain(row, g, lo, hi);
       if (A.logq_x && g.j == 0) A.logq_x[chain] = f_x;
@@ -170,35 +192,59 @@ __global__ void __launch_bounds__(kThreads) jump_kernel(const JumpArgs A) {
 template <int E>
 int launch_flow_pass(const FlowArgs& A, int mode, const float* in, float* out, float* aux, long long n, int grid,
                      size_t smem, cudaStream_t s) {
-  if (A.stage_blob) {
-    NFMC_SET_SMEM_RET((flow_pass_kernel<E, true>), smem);
-    flow_pass_kernel<E, true><<<grid, kThreads, smem, s>>>(A, mode, in, out, aux, n);
+  // exact-layout specialisations are instantiated for the production shapes (E = 13, 16) only
+  const bool xl = A.exact && (E == 13 || E == 16);
+  if (A.stage_blob && xl) {
+    NFMC_SET_SMEM_RET((flow_pass_kernel<E, true, (E == 13 || E == 16)>), smem);
+    flow_pass_kernel<E, true, (E == 13 || E == 16)><<<grid, kThreads, smem, s>>>(A, mode, in, out, aux, n);
+  } else if (A.stage_blob) {
+    NFMC_SET_SMEM_RET((flow_pass_kernel<E, true, false>), smem);
+    flow_pass_kernel<E, true, false><<<grid, kThreads, smem, s>>>(A, mode, in, out, aux, n);
+  } else if (xl) {
+    NFMC_SET_SMEM_RET((flow_pass_kernel<E, false, (E == 13 || E == 16)>), smem);
+    flow_pass_kernel<E, false, (E == 13 || E == 16)><<<grid, kThreads, smem, s>>>(A, mode, in, out, aux, n);
   } else {
-    NFMC_SET_SMEM_RET((flow_pass_kernel<E, false>), smem);
-    flow_pass_kernel<E, false><<<grid, kThreads, smem, s>>>(A, mode, in, out, aux, n);
+    NFMC_SET_SMEM_RET((flow_pass_kernel<E, false, false>), smem);
+    flow_pass_kernel<E, false, false><<<grid, kThreads, smem, s>>>(A, mode, in, out, aux, n);
   }
   return check_cuda(cudaGetLastError(), "flow_pass_kernel launch");
 }
 template <int E>
 int launch_flow_sample(const FlowArgs& A, const RngArgs& R, long long chain0, float* x, float* logq, long long n, int grid,
                        size_t smem, cudaStream_t s) {
-  if (A.stage_blob) {
-    NFMC_SET_SMEM_RET((flow_sample_kernel<E, true>), smem);
-    flow_sample_kernel<E, true><<<grid, kThreads, smem, s>>>(A, R, chain0, x, logq, n);
+  // exact-layout specialisations are instantiated for the production shapes (E = 13, 16) only
+  const bool xl = A.exact && (E == 13 || E == 16);
+  if (A.stage_blob && xl) {
+    NFMC_SET_SMEM_RET((flow_sample_kernel<E, true, (E == 13 || E == 16)>), smem);
+    flow_sample_kernel<E, true, (E == 13 || E == 16)><<<grid, kThreads, smem, s>>>(A, R, chain0, x, logq, n);
+  } else if (A.stage_blob) {
+    NFMC_SET_SMEM_RET((flow_sample_kernel<E, true, false>), smem);
+    flow_sample_kernel<E, true, false><<<grid, kThreads, smem, s>>>(A, R, chain0, x, logq, n);
+  } else if (xl) {
+    NFMC_SET_SMEM_RET((flow_sample_kernel<E, false, (E == 13 || E == 16)>), smem);
+    flow_sample_kernel<E, false, (E == 13 || E == 16)><<<grid, kThreads, smem, s>>>(A, R, chain0, x, logq, n);
   } else {
-    NFMC_SET_SMEM_RET((flow_sample_kernel<E, false>), smem);
-    flow_sample_kernel<E, false><<<grid, kThreads, smem, s>>>(A, R, chain0, x, logq, n);
+    NFMC_SET_SMEM_RET((flow_sample_kernel<E, false, false>), smem);
+    flow_sample_kernel<E, false, false><<<grid, kThreads, smem, s>>>(A, R, chain0, x, logq, n);
   }
   return check_cuda(cudaGetLastError(), "flow_sample_kernel launch");
 }
 template <int E>
 int launch_jump(const JumpArgs& A, int grid, size_t smem, cudaStream_t s) {
-  if (A.f.stage_blob) {
-    NFMC_SET_SMEM_RET((jump_kernel<E, true>), smem);
-    jump_kernel<E, true><<<grid, kThreads, smem, s>>>(A);
+  // exact-layout specialisations are instantiated for the production shapes (E = 13, 16) only
+  const bool xl = A.f.exact && (E == 13 || E == 16);
+  if (A.f.stage_blob && xl) {
+    NFMC_SET_SMEM_RET((jump_kernel<E, true, (E == 13 || E == 16)>), smem);
+    jump_kernel<E, true, (E == 13 || E == 16)><<<grid, kThreads, smem, s>>>(A);
+  } else if (A.f.stage_blob) {
+    NFMC_SET_SMEM_RET((jump_kernel<E, true, false>), smem);
+    jump_kernel<E, true, false><<<grid, kThreads, smem, s>>>(A);
+  } else if (xl) {
+    NFMC_SET_SMEM_RET((jump_kernel<E, false, (E == 13 || E == 16)>), smem);
+    jump_kernel<E, false, (E == 13 || E == 16)><<<grid, kThreads, smem, s>>>(A);
   } else {
-    NFMC_SET_SMEM_RET((jump_kernel<E, false>), smem);
-    jump_kernel<E, false><<<grid, kThreads, smem, s>>>(A);
+    NFMC_SET_SMEM_RET((jump_kernel<E, false, false>), smem);
+    jump_kernel<E, false, false><<<grid, kThreads, smem, s>>>(A);
   }
   return check_cuda(cudaGetLastError(), "jump_kernel launch");
 }

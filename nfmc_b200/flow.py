@@ -274,7 +274,8 @@ def pack_realnvp(bij: RealNVP) -> torch.Tensor:
         for a, b, ls in grp:                       # y = a * (alpha x + beta) + b
             alpha, beta = a * alpha, a * beta + b
             log_const = log_const + ls
-        parts += [torch.stack([alpha, beta], dim=1).reshape(-1), torch.stack([beta, 1.0 / alpha], dim=1).reshape(-1)]
+        ralpha = 1.0 / alpha
+        parts += [torch.stack([alpha, beta], dim=1).reshape(-1), torch.stack([ralpha, -beta * ralpha], dim=1).reshape(-1)]
     parts.append(torch.stack([log_const, torch.zeros(()), torch.zeros(()), torch.zeros(())]))
     for l in range(Lc):
         cpl = layers[2 + 3 * l]
