@@ -60,6 +60,18 @@ typedef struct nfmc_realnvp {
   int64_t blob_floats;
 } nfmc_realnvp;
 
+/* RealNVP packed for the tensor-core path (cond_tc.cu): bf16 conditioner weights in the UMMA shared-memory image,
+ * fp32 affine tables and biases; M = 2 linear layers, hidden a multiple of 16 in [16, 256], even d <= 128.
+ * Produced by nfmc_b200.flow.pack_realnvp_tc(). */
+typedef struct nfmc_realnvp_tc {
+  int32_t d;
+  int32_t n_coupling;
+  int32_t hidden;
+  int32_t reserved;
+  const void* blob;   /* device */
+  int64_t blob_bytes;
+} nfmc_realnvp_tc;
+
 /* ---- random numbers: counter-based Philox4x32-10, or injected tensors ----------------------------------- */
 typedef struct nfmc_rng {
   uint64_t seed;
@@ -103,6 +115,12 @@ NFMC_API int nfmc_flow_log_prob(const nfmc_realnvp* flow, const float* x, float*
 /* Flow.sample(n, return_log_prob=True) (jump.py:205, imh.py:221): base draw from rng (stream id 1) */
 NFMC_API int nfmc_flow_sample(const nfmc_realnvp* flow, const nfmc_rng* rng, int64_t chain0, float* x, float* log_q,
                      int64_t n, void* stream);
+
+/* the same three operators with the conditioner MLP on the tcgen05 tensor cores (bf16 operands, fp32 accumulate);
+ * mode 0 = forward (out = z, aux = log_det), 1 = inverse (out = x, aux = log_det), 2 = log_prob (aux = log q, out unused) */
+NFMC_API int64_t nfmc_realnvp_tc_blob_bytes(int32_t d, int32_t n_coupling, int32_t hidden);
+NFMC_API int nfmc_flow_tc_pass(const nfmc_realnvp_tc* flow, int32_t mode, const float* in, float* out, float* aux,
+                               int64_t n, void* stream);
 
 /* K Langevin steps for all chains -- Langevin.propose (mcmc/langevin.py:61-122) inside the local loop
  * MCMCSampler.sample (mcmc/base.py:69-99).  inv_mass_diag may be NULL (= ones).  adjusted=0 -> ULA. */

@@ -32,6 +32,11 @@ class RealNVPDesc(C.Structure):
                 ("blob", C.c_void_p), ("blob_floats", C.c_int64)]
 
 
+class RealNVPTcDesc(C.Structure):
+    _fields_ = [("d", C.c_int32), ("n_coupling", C.c_int32), ("hidden", C.c_int32), ("reserved", C.c_int32),
+                ("blob", C.c_void_p), ("blob_bytes", C.c_int64)]
+
+
 class RngDesc(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("step0", C.c_uint64), ("normals", C.c_void_p), ("uniforms", C.c_void_p)]
 
@@ -57,6 +62,8 @@ SIGNATURES = {
     "nfmc_realnvp_forward": (C.c_int, [P(RealNVPDesc), _vp, _vp, _vp, _i64, _vp]),
     "nfmc_realnvp_inverse": (C.c_int, [P(RealNVPDesc), _vp, _vp, _vp, _i64, _vp]),
     "nfmc_flow_log_prob": (C.c_int, [P(RealNVPDesc), _vp, _vp, _i64, _vp]),
+    "nfmc_realnvp_tc_blob_bytes": (_i64, [_i32, _i32, _i32]),
+    "nfmc_flow_tc_pass": (C.c_int, [P(RealNVPTcDesc), _i32, _vp, _vp, _vp, _i64, _vp]),
     "nfmc_flow_sample": (C.c_int, [P(RealNVPDesc), P(RngDesc), _i64, _vp, _vp, _i64, _vp]),
     "nfmc_mala_steps": (C.c_int, [P(PotentialDesc), _vp, _i64, _i32, _f32, _vp, _i32, P(RngDesc), _i64,
                                   P(StatsDesc), P(SinkDesc), _vp]),

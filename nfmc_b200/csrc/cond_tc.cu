@@ -1,0 +1,364 @@
+// cond_tc.cu -- RealNVP passes with the conditioner MLP on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// For wide conditioners (M = 2 linear layers, H a multiple of 16, 16 <= H <= 256, even d <= 128) the two GEMMs of a
+// coupling layer
+//       Hpre[128 x H]  = S[128 x d/2] . W1^T          (K = d/2, zero padded to 64)
+//       U   [128 x 2db] = tanh(Hpre + b1)[128 x H] . Wl^T   (K = H)
+// run as tcgen05.mma (kind::f16, bf16 operands, fp32 accumulators in tensor memory) on tiles of 128 chains.  One CTA
+// of 128 threads owns a tile; thread t owns chain row t, keeps the whole chain state in registers (fp32) and does the
+// fused epilogues straight out of TMEM with tcgen05.ld (its TMEM lane = its row):
+//   epilogue 1: + b1, tanh, -> bf16 -> shared memory in the UMMA K-major layout (A operand of the second GEMM)
+//   epilogue 2: + bl, alpha = exp(c + u_a/2) + m, beta = u_b/2, target <- alpha*target + beta (or the inverse),
+//               log-det accumulation.
+// The weights of a coupling layer (bf16, pre-arranged on the host in the exact shared-memory image) are staged by the
+// TMA engine (cp.async.bulk, mbarrier complete_tx) while the previous epilogue runs.
+//
+// Same specification as the fp32 path (oracle/realnvp_ref.py); parity tolerance is the bf16 one of the north star
+// (rtol 1e-2).  Replaces flow.bijection.forward / inverse / flow.log_prob for wide flows (neutra.py:60, jump.py:218).
+//
+// UMMA operand layout used everywhere (SWIZZLE_NONE, K-major): an [R rows x K] bf16 operand is stored as
+// [K/8][R][8]: 8 consecutive k of one row are 16 contiguous bytes ("core matrix" = 8 rows x 16 B = 128 B contiguous),
+// so  SBO (next 8-row group) = 128 B  and  LBO (next 8-column group) = R * 16 B.
+#include <cuda_bf16.h>
+#include "host_common.cuh"
+
+namespace nfmc {
+
+constexpr int kTcRows = 128;      // chains per tile = UMMA_M
+constexpr int kTcK1 = 64;         // padded source width (d/2 <= 64)
+constexpr int kTcHalf = 64;       // registers per half of the chain state
+constexpr int kTcTmemCols = 512;
+constexpr int kTcCol2 = 256;      // TMEM column of the second accumulator
+
+struct TcArgs {
+  const unsigned char* blob;  // packed: affines fp32 | const | per coupling { W1 image, b1, Wl image, bl }
+  int d, Lc, H, N2p;
+  int mode;                   // 0 forward, 1 inverse, 2 log_prob
+  const float* in;
+  float* out;
+  float* aux;
+  long long n;
+};
+
+__host__ __device__ inline size_t tc_coupling_bytes(int H, int N2p) {
+  return (size_t)kTcK1 * H * 2 + (size_t)H * 4 + (size_t)N2p * H * 2 + (size_t)N2p * 4;
+}
+__host__ __device__ inline size_t tc_affine_bytes(int d, int Lc) { return ((size_t)(Lc + 1) * 4 * d + 4) * 4; }
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// shared-memory matrix descriptor: SWIZZLE_NONE, K-major (see file header)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address      bits [0,14)
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16; // leading byte off.  bits [16,30)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32; // stride byte off.   bits [32,46)
+  d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
+  return d;                                         // layout_type (bits 61..63) = 0: no swizzle
+}
+// instruction descriptor, kind::f16: D = f32, A = B = bf16, both K-major, M x N
+__device__ __forceinline__ uint32_t umma_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------------------------
+// dynamic smem: [A1: 128 x 64 bf16 = 16 KB][hid: 128 x H bf16][weights of one coupling][mbarriers + tmem slot]
+__global__ void __launch_bounds__(kTcRows, 1) flow_tc_kernel(const TcArgs A) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int d = A.d, da = d / 2, H = A.H, N2p = A.N2p, Lc = A.Lc;
+  unsigned char* sA1 = smem;
+  unsigned char* sHid = sA1 + kTcRows * kTcK1 * 2;
+  unsigned char* sW = sHid + (size_t)kTcRows * H * 2;
+  const size_t wbytes = tc_coupling_bytes(H, N2p);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + ((wbytes + 15) & ~size_t(15)));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const uint32_t bar_w = smem_u32(bars), bar_mma = smem_u32(bars + 1);
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTcTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's 32-lane quarter
+
+  const float* aff = reinterpret_cast<const float*>(A.blob);
+  const unsigned char* wblob = A.blob + tc_affine_bytes(d, Lc);
+  const float log_const = __ldg(aff + (Lc + 1) * 4 * d);
+  const bool inv = (A.mode == 1);
+  const bool flip = (Lc & 1) != 0;
+  const uint32_t idesc1 = umma_idesc(kTcRows, H), idesc2 = umma_idesc(kTcRows, N2p);
+  uint32_t ph_w = 0, ph_mma = 0;
+
+  const long long tiles = (A.n + kTcRows - 1) / kTcRows;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long row_raw = tile * kTcRows + tid;
+    const bool active = row_raw < A.n;
+    const long long row = active ? row_raw : A.n - 1;
+    // ---- this thread's chain, fp32, in registers (physical order: flipped latent when Lc is odd) --------------------
+    float lo[kTcHalf], hi[kTcHalf];
+    {
+      const float* src = A.in + row * (long long)d;
+      const bool fl = inv && flip;
+#pragma unroll
+      for (int k = 0; k < kTcHalf; ++k) {
+        lo[k] = (k < da) ? __ldg(src + (fl ? d - 1 - k : k)) : 0.f;
+        hi[k] = (k < da) ? __ldg(src + (fl ? d - 1 - (da + k) : da + k)) : 0.f;
+      }
+    }
+    float ld = 0.f;
+    const int n_ops = 2 * Lc + 1;
+    // first coupling's weights: issue the TMA bulk copy now (the buffer is free: previous tile's GEMMs have completed)
+    const int first_l = inv ? Lc - 1 : 0;
+    if (tid == 0 && Lc > 0) {
+      mbar_expect_tx(bar_w, (uint32_t)wbytes);
+      tma_bulk_load(smem_u32(sW), wblob + (size_t)first_l * wbytes, (uint32_t)wbytes, bar_w);
+    }
+#pragma unroll 1
+    for (int i = 0; i < n_ops; ++i) {
+      const int op = inv ? n_ops - 1 - i : i;
+      if ((op & 1) == 0) {
+        // ---- elementwise affine op>>1 (forward {alpha, beta} or inverse {1/alpha, -beta/alpha}: the same fma) -----------
+        const float* tab = aff + (op >> 1) * 4 * d + (inv ? 2 * d : 0);
+#pragma unroll
+        for (int k = 0; k < kTcHalf; ++k) {
+          if (k < da) {
+            const float2 pl = __ldg(reinterpret_cast<const float2*>(tab) + k);
+            const float2 ph = __ldg(reinterpret_cast<const float2*>(tab) + da + k);
+            lo[k] = fmaf(pl.x, lo[k], pl.y);
+            hi[k] = fmaf(ph.x, hi[k], ph.y);
+          }
+        }
+        continue;
+      }
+      // ---- coupling l: source half S, target half T ----------------------------------------------------------------------
+      const int l = op >> 1;
+      const bool src_is_hi = (l & 1) == 0;
+      // A operand of GEMM 1: this row's source half as bf16, [K1/8][128][8] image
+#pragma unroll
+      for (int kg = 0; kg < kTcK1 / 8; ++kg) {
+        uint4 v;
+        const int k0 = kg * 8;
+        v.x = pack_bf16(src_is_hi ? hi[k0 + 0] : lo[k0 + 0], src_is_hi ? hi[k0 + 1] : lo[k0 + 1]);
+        v.y = pack_bf16(src_is_hi ? hi[k0 + 2] : lo[k0 + 2], src_is_hi ? hi[k0 + 3] : lo[k0 + 3]);
+        v.z = pack_bf16(src_is_hi ? hi[k0 + 4] : lo[k0 + 4], src_is_hi ? hi[k0 + 5] : lo[k0 + 5]);
+        v.w = pack_bf16(src_is_hi ? hi[k0 + 6] : lo[k0 + 6], src_is_hi ? hi[k0 + 7] : lo[k0 + 7]);
+        *reinterpret_cast<uint4*>(sA1 + ((size_t)kg * kTcRows + tid) * 16) = v;
+      }
+      fence_async_smem();      // generic-proxy writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        mbar_wait(bar_w, ph_w);                                   // weights have landed (TMA complete_tx)
+        const uint32_t a0 = smem_u32(sA1), b0 = smem_u32(sW);     // W1 image: [K1/8][H][8]
+#pragma unroll 1
+        for (int kk = 0; kk < kTcK1 / 16; ++kk)
+          umma_f16(tmem_base, umma_desc(a0 + kk * 2 * (kTcRows * 16), kTcRows * 16, 128),
+                   umma_desc(b0 + kk * 2 * (H * 16), H * 16, 128), idesc1, kk > 0);
+        umma_commit(bar_mma);
+      }
+      mbar_wait(bar_w, ph_w);      // every thread observes the TMA completion itself before it reads b1 / bl
+      ph_w ^= 1;
+      mbar_wait(bar_mma, ph_mma);
+      ph_mma ^= 1;
+      tc_fence_after();
+      // ---- epilogue 1: hid = tanh(Hpre + b1) -> bf16 -> A operand image of GEMM 2: [H/8][128][8] ------------------------
+      {
+        const float* b1 = reinterpret_cast<const float*>(sW + (size_t)kTcK1 * H * 2);
+#pragma unroll 1
+        for (int c = 0; c < H / 16; ++c) {
+          float v[16];
+          tmem_ld16(tmem_row + c * 16, v);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = tanh_approx(v[q] + b1[c * 16 + q]);
+          uint4 w0, w1;
+          w0.x = pack_bf16(v[0], v[1]); w0.y = pack_bf16(v[2], v[3]); w0.z = pack_bf16(v[4], v[5]); w0.w = pack_bf16(v[6], v[7]);
+          w1.x = pack_bf16(v[8], v[9]); w1.y = pack_bf16(v[10], v[11]); w1.z = pack_bf16(v[12], v[13]); w1.w = pack_bf16(v[14], v[15]);
+          *reinterpret_cast<uint4*>(sHid + ((size_t)(2 * c) * kTcRows + tid) * 16) = w0;
+          *reinterpret_cast<uint4*>(sHid + ((size_t)(2 * c + 1) * kTcRows + tid) * 16) = w1;
+        }
+      }
+      fence_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sHid), b0 = smem_u32(sW + (size_t)kTcK1 * H * 2 + (size_t)H * 4);  // Wl image [H/8][N2p][8]
+#pragma unroll 1
+        for (int kk = 0; kk < H / 16; ++kk)
+          umma_f16(tmem_base + kTcCol2, umma_desc(a0 + kk * 2 * (kTcRows * 16), kTcRows * 16, 128),
+                   umma_desc(b0 + kk * 2 * (N2p * 16), N2p * 16, 128), idesc2, kk > 0);
+        umma_commit(bar_mma);
+      }
+      mbar_wait(bar_mma, ph_mma);
+      ph_mma ^= 1;
+      tc_fence_after();
+      // ---- epilogue 2: (u_a, u_b) = U + bl -> affine transform of the target half, log-det ------------------------------
+      {
+        const float* bl = reinterpret_cast<const float*>(sW + (size_t)kTcK1 * H * 2 + (size_t)H * 4 + (size_t)N2p * H * 2);
+#pragma unroll
+        for (int c = 0; c < (2 * kTcHalf) / 16; ++c) {      // 16 columns = 8 targets (u_a, u_b interleaved)
+          if (c * 16 < N2p) {
+            float v[16];
+            tmem_ld16(tmem_row + kTcCol2 + c * 16, v);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int t = c * 8 + q;
+              if (t < da) {
+                const float ua = v[2 * q] + bl[2 * t], ub = v[2 * q + 1] + bl[2 * t + 1];
+                const float al = __expf(kLogOneMinusM + 0.5f * ua) + kMinScale, be = 0.5f * ub;
+                const float ra = __fdividef(1.f, al);
+                const float r = inv ? ra : al, s = inv ? -be * ra : be;
+                if (src_is_hi) lo[t] = fmaf(r, lo[t], s);
+                else hi[t] = fmaf(r, hi[t], s);
+                ld += __logf(al);
+              }
+            }
+          }
+        }
+      }
+      // every thread has finished reading the weights (b1, bl) and TMEM: stage the next coupling's weights
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0 && i + 1 < n_ops) {
+        const int next_op = inv ? n_ops - 1 - (i + 2) : i + 2;   // the op after the next affine
+        if (i + 2 < n_ops && (next_op & 1)) {
+          mbar_expect_tx(bar_w, (uint32_t)wbytes);
+          tma_bulk_load(smem_u32(sW), wblob + (size_t)(next_op >> 1) * wbytes, (uint32_t)wbytes, bar_w);
+        }
+      }
+    }
+    // ---- results -----------------------------------------------------------------------------------------------------------
+    float res = ld + log_const;
+    if (inv) res = -res;
+    if (A.mode == 2) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < kTcHalf; ++k) s = fmaf(lo[k], lo[k], fmaf(hi[k], hi[k], s));
+      res += -0.5f * s - 0.5f * (float)d * 1.8378770664093453f;
+    }
+    if (active) {
+      if (A.out) {
+        float* dst = A.out + row * (long long)d;
+        const bool fl = !inv && flip;
+#pragma unroll
+        for (int k = 0; k < kTcHalf; ++k) {
+          if (k < da) {
+            dst[fl ? d - 1 - k : k] = lo[k];
+            dst[fl ? d - 1 - (da + k) : da + k] = hi[k];
+          }
+        }
+      }
+      if (A.aux) A.aux[row] = res;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, kTcTmemCols);
+}
+
+}  // namespace nfmc
+
+using namespace nfmc;
+
+extern "C" int64_t nfmc_realnvp_tc_blob_bytes(int32_t d, int32_t n_coupling, int32_t hidden) {
+  const int N2p = ((d - d / 2) * 2 + 15) & ~15;
+  return (int64_t)(tc_affine_bytes(d, n_coupling) + (size_t)n_coupling * tc_coupling_bytes(hidden, N2p));
+}
+
+extern "C" int nfmc_flow_tc_pass(const nfmc_realnvp_tc* flow, int32_t mode, const float* in, float* out, float* aux,
+                                 int64_t n, void* stream) {
+  if (!flow || !flow->blob || !in || n < 1) return set_error("flow_tc_pass: bad arguments");
+  const int d = flow->d, H = flow->hidden, Lc = flow->n_coupling;
+  if (d < 2 || d > 128 || (d & 1)) return set_error("flow_tc_pass: tensor-core path needs even d <= 128");
+  if (H < 16 || H > 256 || (H & 15)) return set_error("flow_tc_pass: hidden width must be a multiple of 16 in [16, 256]");
+  if (mode < 0 || mode > 2) return set_error("flow_tc_pass: mode must be 0 (forward), 1 (inverse) or 2 (log_prob)");
+  if (flow->blob_bytes != nfmc_realnvp_tc_blob_bytes(d, Lc, H)) return set_error("flow_tc_pass: blob_bytes mismatch");
+  TcArgs A;
+  A.blob = static_cast<const unsigned char*>(flow->blob);
+  A.d = d; A.Lc = Lc; A.H = H; A.N2p = ((d - d / 2) * 2 + 15) & ~15;
+  A.mode = mode; A.in = in; A.out = out; A.aux = aux; A.n = n;
+  const size_t wbytes = (tc_coupling_bytes(H, A.N2p) + 15) & ~size_t(15);
+  const size_t smem = (size_t)kTcRows * kTcK1 * 2 + (size_t)kTcRows * H * 2 + wbytes + 64;
+  if (smem > 227 * 1024) return set_error("flow_tc_pass: shared-memory plan exceeds 227 KB");
+  cudaFuncSetAttribute(flow_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const long long tiles = (n + kTcRows - 1) / kTcRows;
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  flow_tc_kernel<<<grid, kTcRows, smem, (cudaStream_t)stream>>>(A);
+  return check_cuda(cudaGetLastError(), "flow_tc_kernel launch");
+}

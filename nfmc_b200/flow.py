@@ -91,10 +91,16 @@ class AffineCoupling(_Layer):
 class RealNVP(_Layer):
     """RealNVP bijection.  ``forward``: data -> latent, ``inverse``: latent -> data; both return ``(y, log_det)``."""
 
-    def __init__(self, event_shape, n_layers: int = 2, edge_list=None, **kwargs):
+    def __init__(self, event_shape, n_layers: int = 2, edge_list=None, conditioner_dtype: str = "auto", **kwargs):
+        """``conditioner_dtype``: ``'fp32'`` = CUDA-core kernels (rtol 1e-4); ``'bf16'`` = tcgen05 tensor-core kernel
+        (bf16 operands, fp32 accumulate, rtol 1e-2; needs 2 linear layers, hidden a multiple of 16 in [16, 256],
+        even d <= 128); ``'auto'`` = bf16 whenever the shape is eligible."""
         if isinstance(event_shape, int):
             event_shape = (event_shape,)
         super().__init__(event_shape)
+        if conditioner_dtype not in ("auto", "fp32", "bf16"):
+            raise ValueError("conditioner_dtype must be 'auto', 'fp32' or 'bf16'")
+        self.conditioner_dtype = conditioner_dtype
         if edge_list is not None:
             raise NotImplementedError("edge_list couplings are outside the accelerated hot path")
         if self.n_dim < 2 or self.n_dim > N.MAX_DIM:
@@ -106,6 +112,9 @@ class RealNVP(_Layer):
         self.layers = nn.ModuleList(layers)
         self.n_coupling = int(n_layers)
         self._packed = {}  # device -> (version key, blob tensor)
+        self._packed_tc = {}
+        if conditioner_dtype == "bf16" and not tc_eligible(self.n_dim, *self.conditioner_shape()):
+            raise ValueError("conditioner_dtype='bf16' needs 2 linear layers, hidden % 16 == 0 in [16, 256], even d <= 128")
 
     # -- structure --------------------------------------------------------------------------------------------
     def couplings(self):
@@ -128,6 +137,19 @@ class RealNVP(_Layer):
             self._packed[key] = (ver, pack_realnvp(self).to(device))
         return self._packed[key][1]
 
+    def uses_tensor_cores(self) -> bool:
+        return self.conditioner_dtype != "fp32" and tc_eligible(self.n_dim, *self.conditioner_shape())
+
+    def tc_descriptor(self, device: torch.device):
+        key = str(device)
+        ver = self._version_key()
+        hit = self._packed_tc.get(key)
+        if hit is None or hit[0] != ver:
+            self._packed_tc[key] = (ver, pack_realnvp_tc(self).to(device))
+        blob = self._packed_tc[key][1]
+        M, H = self.conditioner_shape()
+        return N.RealNVPTcDesc(self.n_dim, self.n_coupling, H, 0, blob.data_ptr(), blob.numel()), blob
+
     def descriptor(self, device: torch.device):
         blob = self.blob(device)
         M, H = self.conditioner_shape()
@@ -141,8 +163,13 @@ class RealNVP(_Layer):
         n = xd.shape[0]
         y = torch.empty_like(xd)
         ld = torch.empty(n, device=dev, dtype=torch.float32)
-        desc, keep = self.descriptor(dev)
-        N.check(getattr(N.lib(), fn_name)(C.byref(desc), N.ptr(xd), N.ptr(y), N.ptr(ld), n, N.stream_ptr(dev)))
+        if self.uses_tensor_cores():
+            desc, keep = self.tc_descriptor(dev)
+            mode = 0 if fn_name == "nfmc_realnvp_forward" else 1
+            N.check(N.lib().nfmc_flow_tc_pass(C.byref(desc), mode, N.ptr(xd), N.ptr(y), N.ptr(ld), n, N.stream_ptr(dev)))
+        else:
+            desc, keep = self.descriptor(dev)
+            N.check(getattr(N.lib(), fn_name)(C.byref(desc), N.ptr(xd), N.ptr(y), N.ptr(ld), n, N.stream_ptr(dev)))
         return y.reshape(*batch, *self.event_shape), ld.reshape(batch)
 
     @torch.no_grad()
@@ -185,8 +212,12 @@ class Flow(nn.Module):
         xd = N.dev_f32(x, dev).reshape(-1, bij.n_dim)
         n = xd.shape[0]
         out = torch.empty(n, device=dev, dtype=torch.float32)
-        desc, keep = bij.descriptor(dev)
-        N.check(N.lib().nfmc_flow_log_prob(C.byref(desc), N.ptr(xd), N.ptr(out), n, N.stream_ptr(dev)))
+        if bij.uses_tensor_cores():
+            desc, keep = bij.tc_descriptor(dev)
+            N.check(N.lib().nfmc_flow_tc_pass(C.byref(desc), 2, N.ptr(xd), None, N.ptr(out), n, N.stream_ptr(dev)))
+        else:
+            desc, keep = bij.descriptor(dev)
+            N.check(N.lib().nfmc_flow_log_prob(C.byref(desc), N.ptr(xd), N.ptr(out), n, N.stream_ptr(dev)))
         return out.reshape(batch)
 
     @torch.no_grad()
@@ -254,6 +285,26 @@ def pack_realnvp(bij: RealNVP) -> torch.Tensor:
     M, H = bij.conditioner_shape()
     small = (M == 2 and H <= SMALL_H)
     layers = list(bij.layers)
+    parts = [pack_realnvp_affines(bij)]
+    for l in range(Lc):
+        cpl = layers[2 + 3 * l]
+        if (cpl.n_linear, cpl.n_hidden) != (M, H) and cpl.n_linear > 1:
+            raise ValueError("all couplings must share the conditioner shape")
+        odd = (l + 1) % 2 == 1
+        lin = [(m.weight.detach().to("cpu", torch.float32), m.bias.detach().to("cpu", torch.float32)) for m in cpl.linears()]
+        parts += _pack_coupling_fp32(lin, da, db, M, H, small, odd)
+    blob = torch.cat([p.reshape(-1) for p in parts]).contiguous()
+    assert blob.numel() == blob_floats(d, Lc, M, H), (blob.numel(), blob_floats(d, Lc, M, H))
+    return blob
+
+
+@torch.no_grad()
+def pack_realnvp_affines(bij: "RealNVP") -> torch.Tensor:
+    """The elementwise-affine section of the blob: (Lc+1) tables {alpha, beta}[d], {1/alpha, -beta/alpha}[d] in
+    physical coordinates, then 4 floats whose first is the total log-det constant."""
+    d = bij.n_dim
+    Lc = bij.n_coupling
+    layers = list(bij.layers)
 
     def phys(layer, r):
         v = layer.value.detach().to("cpu", torch.float32)
@@ -277,12 +328,12 @@ def pack_realnvp(bij: RealNVP) -> torch.Tensor:
         ralpha = 1.0 / alpha
         parts += [torch.stack([alpha, beta], dim=1).reshape(-1), torch.stack([ralpha, -beta * ralpha], dim=1).reshape(-1)]
     parts.append(torch.stack([log_const, torch.zeros(()), torch.zeros(()), torch.zeros(())]))
-    for l in range(Lc):
-        cpl = layers[2 + 3 * l]
-        if (cpl.n_linear, cpl.n_hidden) != (M, H) and cpl.n_linear > 1:
-            raise ValueError("all couplings must share the conditioner shape")
-        odd = (l + 1) % 2 == 1
-        lin = [(m.weight.detach().to("cpu", torch.float32), m.bias.detach().to("cpu", torch.float32)) for m in cpl.linears()]
+    return torch.cat([p.reshape(-1) for p in parts]).contiguous()
+
+
+def _pack_coupling_fp32(lin, da, db, M, H, small, odd):
+    parts = []
+    if True:
         if small:
             w1, b1 = lin[0]                                  # [H, da]
             wl, bl = lin[1]                                  # [2*db, H]
@@ -316,9 +367,50 @@ def pack_realnvp(bij: RealNVP) -> torch.Tensor:
             if odd:
                 wl, bl = wl.flip(0).flip(2), bl.flip(1)
             parts += [wl.contiguous().reshape(-1), bl.contiguous().reshape(-1)]
-    blob = torch.cat([p.reshape(-1) for p in parts]).contiguous()
-    assert blob.numel() == blob_floats(d, Lc, M, H), (blob.numel(), blob_floats(d, Lc, M, H))
-    return blob
+    return parts
+
+
+def tc_eligible(d: int, M: int, H: int) -> bool:
+    """Shapes the tcgen05 conditioner kernel (csrc/cond_tc.cu) handles."""
+    return M == 2 and d % 2 == 0 and 2 <= d <= 128 and 16 <= H <= 256 and H % 16 == 0
+
+
+@torch.no_grad()
+def pack_realnvp_tc(bij: "RealNVP") -> torch.Tensor:
+    """Pack a RealNVP for the tensor-core path: fp32 affine tables (same as ``pack_realnvp``), then per coupling the
+    bf16 weights in the UMMA shared-memory image ``[K/8][rows][8]`` (K-major, no swizzle) and fp32 biases:
+    ``W1 image [8][H][8]`` (K = d/2 zero padded to 64), ``b1 [H]``, ``Wl image [H/8][N2p][8]`` (row n = 2 t + c,
+    N2p = 2*db rounded up to 16), ``bl [N2p]``.  Reverse permutations are folded in as in ``pack_realnvp``."""
+    d = bij.n_dim
+    da, db = d // 2, d - d // 2
+    Lc = bij.n_coupling
+    M, H = bij.conditioner_shape()
+    if not tc_eligible(d, M, H):
+        raise ValueError("shape not supported by the tensor-core path")
+    n2p = ((2 * db + 15) // 16) * 16
+    base = pack_realnvp_affines(bij)
+    chunks = [base.contiguous().view(torch.uint8)]
+    layers = list(bij.layers)
+    for l in range(Lc):
+        cpl = layers[2 + 3 * l]
+        odd = (l + 1) % 2 == 1
+        (w1, b1), (wl, bl) = [(m.weight.detach().to("cpu", torch.float32), m.bias.detach().to("cpu", torch.float32))
+                              for m in cpl.linears()]
+        w1p = torch.zeros(H, 64)
+        w1p[:, :da] = w1.flip(1) if odd else w1                       # [h][ks]
+        img1 = w1p.reshape(H, 8, 8).permute(1, 0, 2).contiguous()     # [kg][h][8]
+        wl3 = wl.reshape(db, 2, H)                                    # [t_log][c][h]
+        bl2 = bl.reshape(db, 2)
+        if odd:
+            wl3, bl2 = wl3.flip(0), bl2.flip(0)
+        wlp = torch.zeros(n2p, H)
+        wlp[: 2 * db] = wl3.reshape(2 * db, H)                        # row n = 2 t + c
+        img2 = wlp.reshape(n2p, H // 8, 8).permute(1, 0, 2).contiguous()   # [kg][n][8]
+        blp = torch.zeros(n2p)
+        blp[: 2 * db] = bl2.reshape(-1)
+        chunks += [img1.to(torch.bfloat16).view(torch.uint8).reshape(-1), b1.contiguous().view(torch.uint8).reshape(-1),
+                   img2.to(torch.bfloat16).view(torch.uint8).reshape(-1), blp.contiguous().view(torch.uint8).reshape(-1)]
+    return torch.cat([c.reshape(-1) for c in chunks]).contiguous()
 
 
 def create_flow_object(flow_string: str, event_shape, **kwargs) -> Flow:

@@ -10,11 +10,11 @@ from nfmc_b200.records import MCMCOutput
 from nfmc_b200.samplers import DeviceSession
 
 
-def product_flow_from_oracle(oflow) -> Flow:
+def product_flow_from_oracle(oflow, conditioner_dtype="fp32") -> Flow:
     bij = oflow.bijection
     cpl = [l for l in bij.layers if hasattr(l, "net")]
     ck = dict(n_layers=cpl[0].n_linear, n_hidden=cpl[0].n_hidden) if cpl else None
-    f = Flow(RealNVP(bij.event_shape, n_layers=bij.n_coupling, conditioner_kwargs=ck))
+    f = Flow(RealNVP(bij.event_shape, n_layers=bij.n_coupling, conditioner_kwargs=ck, conditioner_dtype=conditioner_dtype))
     missing = f.load_state_dict(oflow.state_dict(), strict=True)
     return f.to("cuda").eval()
 
