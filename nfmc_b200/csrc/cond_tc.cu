@@ -131,16 +131,25 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------------------
-// dynamic smem: [A1: 128 x 64 bf16 = 16 KB][hid: 128 x H bf16][weights of one coupling][mbarriers + tmem slot]
-__global__ void __launch_bounds__(kTcRows, 1) flow_tc_kernel(const TcArgs A) {
+// 512 threads per CTA: thread (r, g) = (tid % 128, tid / 128) works on chain row r of the tile and owns the 16 elements
+// [16 g, 16 g + 16) of each half of that chain (fp32, registers).  Its warp's TMEM lane quarter is (tid % 128) / 32, so
+// the four column groups of a row read disjoint column ranges of the same TMEM lane: 16 warps share the epilogue work.
+// dynamic smem: [A1: 128 x 64 bf16 = 16 KB][hid: 128 x H bf16][weights of one coupling][row reductions][mbarriers]
+constexpr int kTcGroups = 4;
+constexpr int kTcOwn = kTcHalf / kTcGroups;   // 16 elements per half per thread
+constexpr int kTcThreads = kTcRows * kTcGroups;
+
+__global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const TcArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int r = tid & (kTcRows - 1), g = tid >> 7;
   const int d = A.d, da = d / 2, H = A.H, N2p = A.N2p, Lc = A.Lc;
   unsigned char* sA1 = smem;
   unsigned char* sHid = sA1 + kTcRows * kTcK1 * 2;
   unsigned char* sW = sHid + (size_t)kTcRows * H * 2;
   const size_t wbytes = tc_coupling_bytes(H, N2p);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + ((wbytes + 15) & ~size_t(15)));
+  float* sRed = reinterpret_cast<float*>(sW + ((wbytes + 15) & ~size_t(15)));      // [2][4][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 2 * kTcGroups * kTcRows);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   const uint32_t bar_w = smem_u32(bars), bar_mma = smem_u32(bars + 1);
 
@@ -154,7 +163,7 @@ __global__ void __launch_bounds__(kTcRows, 1) flow_tc_kernel(const TcArgs A) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's 32-lane quarter
+  const uint32_t tmem_row = tmem_base + ((uint32_t)((r >> 5) * 32) << 16);   // this warp's 32-lane quarter
 
   const float* aff = reinterpret_cast<const float*>(A.blob);
   const unsigned char* wblob = A.blob + tc_affine_bytes(d, Lc);
@@ -163,26 +172,28 @@ __global__ void __launch_bounds__(kTcRows, 1) flow_tc_kernel(const TcArgs A) {
   const bool flip = (Lc & 1) != 0;
   const uint32_t idesc1 = umma_idesc(kTcRows, H), idesc2 = umma_idesc(kTcRows, N2p);
   uint32_t ph_w = 0, ph_mma = 0;
+  const int e0 = g * kTcOwn;   // first owned element index within a half
 
   const long long tiles = (A.n + kTcRows - 1) / kTcRows;
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const long long row_raw = tile * kTcRows + tid;
+    const long long row_raw = tile * kTcRows + r;
     const bool active = row_raw < A.n;
     const long long row = active ? row_raw : A.n - 1;
-    // ---- this thread's chain, fp32, in registers (physical order: flipped latent when Lc is odd) --------------------
-    float lo[kTcHalf], hi[kTcHalf];
+    // ---- this thread's share of the chain, fp32, in registers (physical order: flipped latent when Lc is odd) ----------
+    float lo[kTcOwn], hi[kTcOwn];
     {
       const float* src = A.in + row * (long long)d;
       const bool fl = inv && flip;
 #pragma unroll
-      for (int k = 0; k < kTcHalf; ++k) {
-        lo[k] = (k < da) ? __ldg(src + (fl ? d - 1 - k : k)) : 0.f;
-        hi[k] = (k < da) ? __ldg(src + (fl ? d - 1 - (da + k) : da + k)) : 0.f;
+      for (int q = 0; q < kTcOwn; ++q) {
+        const int k = e0 + q;
+        lo[q] = (k < da) ? __ldg(src + (fl ? d - 1 - k : k)) : 0.f;
+        hi[q] = (k < da) ? __ldg(src + (fl ? d - 1 - (da + k) : da + k)) : 0.f;
       }
     }
     float ld = 0.f;
     const int n_ops = 2 * Lc + 1;
-    // first coupling's weights: issue the TMA bulk copy now (the buffer is free: previous tile's GEMMs have completed)
+    // first coupling's weights: issue the TMA bulk copy now (the buffer is free: the previous tile has finished with it)
     const int first_l = inv ? Lc - 1 : 0;
     if (tid == 0 && Lc > 0) {
       mbar_expect_tx(bar_w, (uint32_t)wbytes);
@@ -193,14 +204,14 @@ __global__ void __launch_bounds__(kTcRows, 1) flow_tc_kernel(const TcArgs A) {
       const int op = inv ? n_ops - 1 - i : i;
       if ((op & 1) == 0) {
         // ---- elementwise affine op>>1 (forward {alpha, beta} or inverse {1/alpha, -beta/alpha}: the same fma) -----------
-        const float* tab = aff + (op >> 1) * 4 * d + (inv ? 2 * d : 0);
+        const float2* tab = reinterpret_cast<const float2*>(aff + (op >> 1) * 4 * d + (inv ? 2 * d : 0));
 #pragma unroll
-        for (int k = 0; k < kTcHalf; ++k) {
+        for (int q = 0; q < kTcOwn; ++q) {
+          const int k = e0 + q;
           if (k < da) {
-            const float2 pl = __ldg(reinterpret_cast<const float2*>(tab) + k);
-            const float2 ph = __ldg(reinterpret_cast<const float2*>(tab) + da + k);
-            lo[k] = fmaf(pl.x, lo[k], pl.y);
-            hi[k] = fmaf(ph.x, hi[k], ph.y);
+            const float2 pl = __ldg(tab + k), ph = __ldg(tab + da + k);
+            lo[q] = fmaf(pl.x, lo[q], pl.y);
+            hi[q] = fmaf(ph.x, hi[q], ph.y);
           }
         }
         continue;
@@ -208,16 +219,16 @@ __global__ void __launch_bounds__(kTcRows, 1) flow_tc_kernel(const TcArgs A) {
       // ---- coupling l: source half S, target half T ----------------------------------------------------------------------
       const int l = op >> 1;
       const bool src_is_hi = (l & 1) == 0;
-      // A operand of GEMM 1: this row's source half as bf16, [K1/8][128][8] image
+      // A operand of GEMM 1: this thread's 16 source values as bf16 into k-groups 2g, 2g+1 of the [K1/8][128][8] image
 #pragma unroll
-      for (int kg = 0; kg < kTcK1 / 8; ++kg) {
+      for (int h2 = 0; h2 < 2; ++h2) {
         uint4 v;
-        const int k0 = kg * 8;
-        v.x = pack_bf16(src_is_hi ? hi[k0 + 0] : lo[k0 + 0], src_is_hi ? hi[k0 + 1] : lo[k0 + 1]);
-        v.y = pack_bf16(src_is_hi ? hi[k0 + 2] : lo[k0 + 2], src_is_hi ? hi[k0 + 3] : lo[k0 + 3]);
-        v.z = pack_bf16(src_is_hi ? hi[k0 + 4] : lo[k0 + 4], src_is_hi ? hi[k0 + 5] : lo[k0 + 5]);
-        v.w = pack_bf16(src_is_hi ? hi[k0 + 6] : lo[k0 + 6], src_is_hi ? hi[k0 + 7] : lo[k0 + 7]);
-        *reinterpret_cast<uint4*>(sA1 + ((size_t)kg * kTcRows + tid) * 16) = v;
+        const int q0 = h2 * 8;
+        v.x = pack_bf16(src_is_hi ? hi[q0 + 0] : lo[q0 + 0], src_is_hi ? hi[q0 + 1] : lo[q0 + 1]);
+        v.y = pack_bf16(src_is_hi ? hi[q0 + 2] : lo[q0 + 2], src_is_hi ? hi[q0 + 3] : lo[q0 + 3]);
+        v.z = pack_bf16(src_is_hi ? hi[q0 + 4] : lo[q0 + 4], src_is_hi ? hi[q0 + 5] : lo[q0 + 5]);
+        v.w = pack_bf16(src_is_hi ? hi[q0 + 6] : lo[q0 + 6], src_is_hi ? hi[q0 + 7] : lo[q0 + 7]);
+        *reinterpret_cast<uint4*>(sA1 + ((size_t)(2 * g + h2) * kTcRows + r) * 16) = v;
       }
       fence_async_smem();      // generic-proxy writes -> visible to the tensor core (async proxy)
       tc_fence_before();
@@ -237,11 +248,12 @@ __global__ void __launch_bounds__(kTcRows, 1) flow_tc_kernel(const TcArgs A) {
       mbar_wait(bar_mma, ph_mma);
       ph_mma ^= 1;
       tc_fence_after();
-      // ---- epilogue 1: hid = tanh(Hpre + b1) -> bf16 -> A operand image of GEMM 2: [H/8][128][8] ------------------------
+      // ---- epilogue 1: hid = tanh(Hpre + b1) -> bf16 -> A operand image of GEMM 2: [H/8][128][8]; 16-column chunks are
+      //      dealt round-robin to the four column groups -------------------------------------------------------------------
       {
         const float* b1 = reinterpret_cast<const float*>(sW + (size_t)kTcK1 * H * 2);
 #pragma unroll 1
-        for (int c = 0; c < H / 16; ++c) {
+        for (int c = g; c < H / 16; c += kTcGroups) {
           float v[16];
           tmem_ld16(tmem_row + c * 16, v);
 #pragma unroll
@@ -249,8 +261,8 @@ __global__ void __launch_bounds__(kTcRows, 1) flow_tc_kernel(const TcArgs A) {
           uint4 w0, w1;
           w0.x = pack_bf16(v[0], v[1]); w0.y = pack_bf16(v[2], v[3]); w0.z = pack_bf16(v[4], v[5]); w0.w = pack_bf16(v[6], v[7]);
           w1.x = pack_bf16(v[8], v[9]); w1.y = pack_bf16(v[10], v[11]); w1.z = pack_bf16(v[12], v[13]); w1.w = pack_bf16(v[14], v[15]);
-          *reinterpret_cast<uint4*>(sHid + ((size_t)(2 * c) * kTcRows + tid) * 16) = w0;
-          *reinterpret_cast<uint4*>(sHid + ((size_t)(2 * c + 1) * kTcRows + tid) * 16) = w1;
+          *reinterpret_cast<uint4*>(sHid + ((size_t)(2 * c) * kTcRows + r) * 16) = w0;
+          *reinterpret_cast<uint4*>(sHid + ((size_t)(2 * c + 1) * kTcRows + r) * 16) = w1;
         }
       }
       fence_async_smem();
@@ -268,11 +280,12 @@ __global__ void __launch_bounds__(kTcRows, 1) flow_tc_kernel(const TcArgs A) {
       mbar_wait(bar_mma, ph_mma);
       ph_mma ^= 1;
       tc_fence_after();
-      // ---- epilogue 2: (u_a, u_b) = U + bl -> affine transform of the target half, log-det ------------------------------
+      // ---- epilogue 2: (u_a, u_b) = U + bl -> affine transform of this thread's 16 targets (chunks 2g, 2g+1), log-det ----
       {
         const float* bl = reinterpret_cast<const float*>(sW + (size_t)kTcK1 * H * 2 + (size_t)H * 4 + (size_t)N2p * H * 2);
 #pragma unroll
-        for (int c = 0; c < (2 * kTcHalf) / 16; ++c) {      // 16 columns = 8 targets (u_a, u_b interleaved)
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int c = 2 * g + h2;                       // 16 columns = 8 targets (u_a, u_b interleaved)
           if (c * 16 < N2p) {
             float v[16];
             tmem_ld16(tmem_row + kTcCol2 + c * 16, v);
@@ -283,9 +296,9 @@ __global__ void __launch_bounds__(kTcRows, 1) flow_tc_kernel(const TcArgs A) {
                 const float ua = v[2 * q] + bl[2 * t], ub = v[2 * q + 1] + bl[2 * t + 1];
                 const float al = __expf(kLogOneMinusM + 0.5f * ua) + kMinScale, be = 0.5f * ub;
                 const float ra = __fdividef(1.f, al);
-                const float r = inv ? ra : al, s = inv ? -be * ra : be;
-                if (src_is_hi) lo[t] = fmaf(r, lo[t], s);
-                else hi[t] = fmaf(r, hi[t], s);
+                const float rr = inv ? ra : al, ss = inv ? -be * ra : be;
+                if (src_is_hi) lo[h2 * 8 + q] = fmaf(rr, lo[h2 * 8 + q], ss);
+                else hi[h2 * 8 + q] = fmaf(rr, hi[h2 * 8 + q], ss);
                 ld += __logf(al);
               }
             }
@@ -295,37 +308,44 @@ __global__ void __launch_bounds__(kTcRows, 1) flow_tc_kernel(const TcArgs A) {
       // every thread has finished reading the weights (b1, bl) and TMEM: stage the next coupling's weights
       tc_fence_before();
       __syncthreads();
-      if (tid == 0 && i + 1 < n_ops) {
-        const int next_op = inv ? n_ops - 1 - (i + 2) : i + 2;   // the op after the next affine
-        if (i + 2 < n_ops && (next_op & 1)) {
-          mbar_expect_tx(bar_w, (uint32_t)wbytes);
-          tma_bulk_load(smem_u32(sW), wblob + (size_t)(next_op >> 1) * wbytes, (uint32_t)wbytes, bar_w);
-        }
+      if (tid == 0 && i + 2 < n_ops) {
+        const int next_op = inv ? n_ops - 1 - (i + 2) : i + 2;   // the op after the next affine is the next coupling
+        mbar_expect_tx(bar_w, (uint32_t)wbytes);
+        tma_bulk_load(smem_u32(sW), wblob + (size_t)(next_op >> 1) * wbytes, (uint32_t)wbytes, bar_w);
       }
     }
-    // ---- results -----------------------------------------------------------------------------------------------------------
-    float res = ld + log_const;
-    if (inv) res = -res;
+    // ---- results: the four column groups of a row combine their log-det / base-density shares through shared memory ------
+    float sq = 0.f;
     if (A.mode == 2) {
-      float s = 0.f;
 #pragma unroll
-      for (int k = 0; k < kTcHalf; ++k) s = fmaf(lo[k], lo[k], fmaf(hi[k], hi[k], s));
-      res += -0.5f * s - 0.5f * (float)d * 1.8378770664093453f;
+      for (int q = 0; q < kTcOwn; ++q) sq = fmaf(lo[q], lo[q], fmaf(hi[q], hi[q], sq));
     }
-    if (active) {
-      if (A.out) {
-        float* dst = A.out + row * (long long)d;
-        const bool fl = !inv && flip;
+    sRed[g * kTcRows + r] = ld;
+    sRed[(kTcGroups + g) * kTcRows + r] = sq;
+    if (active && A.out) {
+      float* dst = A.out + row * (long long)d;
+      const bool fl = !inv && flip;
 #pragma unroll
-        for (int k = 0; k < kTcHalf; ++k) {
-          if (k < da) {
-            dst[fl ? d - 1 - k : k] = lo[k];
-            dst[fl ? d - 1 - (da + k) : da + k] = hi[k];
-          }
+      for (int q = 0; q < kTcOwn; ++q) {
+        const int k = e0 + q;
+        if (k < da) {
+          dst[fl ? d - 1 - k : k] = lo[q];
+          dst[fl ? d - 1 - (da + k) : da + k] = hi[q];
         }
       }
-      if (A.aux) A.aux[row] = res;
     }
+    __syncthreads();
+    if (g == 0 && active && A.aux) {
+      float res = sRed[r] + sRed[kTcRows + r] + sRed[2 * kTcRows + r] + sRed[3 * kTcRows + r] + log_const;
+      if (inv) res = -res;
+      if (A.mode == 2) {
+        const float s = sRed[(kTcGroups + 0) * kTcRows + r] + sRed[(kTcGroups + 1) * kTcRows + r] +
+                        sRed[(kTcGroups + 2) * kTcRows + r] + sRed[(kTcGroups + 3) * kTcRows + r];
+        res += -0.5f * s - 0.5f * (float)d * 1.8378770664093453f;
+      }
+      A.aux[row] = res;
+    }
+    __syncthreads();
   }
   tc_fence_before();
   __syncthreads();
@@ -354,11 +374,11 @@ extern "C" int nfmc_flow_tc_pass(const nfmc_realnvp_tc* flow, int32_t mode, cons
   A.d = d; A.Lc = Lc; A.H = H; A.N2p = ((d - d / 2) * 2 + 15) & ~15;
   A.mode = mode; A.in = in; A.out = out; A.aux = aux; A.n = n;
   const size_t wbytes = (tc_coupling_bytes(H, A.N2p) + 15) & ~size_t(15);
-  const size_t smem = (size_t)kTcRows * kTcK1 * 2 + (size_t)kTcRows * H * 2 + wbytes + 64;
+  const size_t smem = (size_t)kTcRows * kTcK1 * 2 + (size_t)kTcRows * H * 2 + wbytes + 2 * kTcGroups * kTcRows * sizeof(float) + 64;
   if (smem > 227 * 1024) return set_error("flow_tc_pass: shared-memory plan exceeds 227 KB");
   cudaFuncSetAttribute(flow_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const long long tiles = (n + kTcRows - 1) / kTcRows;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  flow_tc_kernel<<<grid, kTcRows, smem, (cudaStream_t)stream>>>(A);
+  flow_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(A);
   return check_cuda(cudaGetLastError(), "flow_tc_kernel launch");
 }
