@@ -149,7 +149,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const TcArgs A) 
   unsigned char* sW = sHid + (size_t)kTcRows * H * 2;
   const size_t wbytes = tc_coupling_bytes(H, N2p);
   float* sRed = reinterpret_cast<float*>(sW + ((wbytes + 15) & ~size_t(15)));      // [2][4][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 2 * kTcGroups * kTcRows);
+  float* sAff = sRed + 2 * kTcGroups * kTcRows;                                     // (Lc+1)*4*d + 4 floats
+  const int n_aff = (Lc + 1) * 4 * d + 4;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sAff + ((n_aff + 3) & ~3));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   const uint32_t bar_w = smem_u32(bars), bar_mma = smem_u32(bars + 1);
 
@@ -165,9 +167,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const TcArgs A) 
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_row = tmem_base + ((uint32_t)((r >> 5) * 32) << 16);   // this warp's 32-lane quarter
 
-  const float* aff = reinterpret_cast<const float*>(A.blob);
+  for (int i = tid; i < n_aff; i += kTcThreads) sAff[i] = __ldg(reinterpret_cast<const float*>(A.blob) + i);
+  __syncthreads();
+  const float* aff = sAff;
   const unsigned char* wblob = A.blob + tc_affine_bytes(d, Lc);
-  const float log_const = __ldg(aff + (Lc + 1) * 4 * d);
+  const float log_const = aff[(Lc + 1) * 4 * d];
   const bool inv = (A.mode == 1);
   const bool flip = (Lc & 1) != 0;
   const uint32_t idesc1 = umma_idesc(kTcRows, H), idesc2 = umma_idesc(kTcRows, N2p);
@@ -184,11 +188,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const TcArgs A) 
     {
       const float* src = A.in + row * (long long)d;
       const bool fl = inv && flip;
+      if (!fl && (d & 3) == 0 && (da & 1) == 0 && e0 + kTcOwn <= da) {
+        // 64 contiguous bytes per half: 4 x 128-bit for the low half, 8 x 64-bit for the high half (da*4 is 8-byte aligned)
+        const float4* pl = reinterpret_cast<const float4*>(src + e0);
+        const float2* ph = reinterpret_cast<const float2*>(src + da + e0);
 #pragma unroll
-      for (int q = 0; q < kTcOwn; ++q) {
-        const int k = e0 + q;
-        lo[q] = (k < da) ? __ldg(src + (fl ? d - 1 - k : k)) : 0.f;
-        hi[q] = (k < da) ? __ldg(src + (fl ? d - 1 - (da + k) : da + k)) : 0.f;
+        for (int q = 0; q < kTcOwn / 4; ++q) {
+          const float4 v = __ldg(pl + q);
+          lo[4 * q] = v.x; lo[4 * q + 1] = v.y; lo[4 * q + 2] = v.z; lo[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int q = 0; q < kTcOwn / 2; ++q) {
+          const float2 v = __ldg(ph + q);
+          hi[2 * q] = v.x; hi[2 * q + 1] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < kTcOwn; ++q) {
+          const int k = e0 + q;
+          lo[q] = (k < da) ? __ldg(src + (fl ? d - 1 - k : k)) : 0.f;
+          hi[q] = (k < da) ? __ldg(src + (fl ? d - 1 - (da + k) : da + k)) : 0.f;
+        }
       }
     }
     float ld = 0.f;
@@ -209,7 +229,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const TcArgs A) 
         for (int q = 0; q < kTcOwn; ++q) {
           const int k = e0 + q;
           if (k < da) {
-            const float2 pl = __ldg(tab + k), ph = __ldg(tab + da + k);
+            const float2 pl = tab[k], ph = tab[da + k];
             lo[q] = fmaf(pl.x, lo[q], pl.y);
             hi[q] = fmaf(ph.x, hi[q], ph.y);
           }
@@ -325,12 +345,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const TcArgs A) 
     if (active && A.out) {
       float* dst = A.out + row * (long long)d;
       const bool fl = !inv && flip;
+      if (!fl && (d & 3) == 0 && (da & 1) == 0 && e0 + kTcOwn <= da) {
+        float4* pl = reinterpret_cast<float4*>(dst + e0);
+        float2* ph = reinterpret_cast<float2*>(dst + da + e0);
 #pragma unroll
-      for (int q = 0; q < kTcOwn; ++q) {
-        const int k = e0 + q;
-        if (k < da) {
-          dst[fl ? d - 1 - k : k] = lo[q];
-          dst[fl ? d - 1 - (da + k) : da + k] = hi[q];
+        for (int q = 0; q < kTcOwn / 4; ++q) pl[q] = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+#pragma unroll
+        for (int q = 0; q < kTcOwn / 2; ++q) ph[q] = make_float2(hi[2 * q], hi[2 * q + 1]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < kTcOwn; ++q) {
+          const int k = e0 + q;
+          if (k < da) {
+            dst[fl ? d - 1 - k : k] = lo[q];
+            dst[fl ? d - 1 - (da + k) : da + k] = hi[q];
+          }
         }
       }
     }
@@ -374,7 +403,7 @@ extern "C" int nfmc_flow_tc_pass(const nfmc_realnvp_tc* flow, int32_t mode, cons
   A.d = d; A.Lc = Lc; A.H = H; A.N2p = ((d - d / 2) * 2 + 15) & ~15;
   A.mode = mode; A.in = in; A.out = out; A.aux = aux; A.n = n;
   const size_t wbytes = (tc_coupling_bytes(H, A.N2p) + 15) & ~size_t(15);
-  const size_t smem = (size_t)kTcRows * kTcK1 * 2 + (size_t)kTcRows * H * 2 + wbytes + 2 * kTcGroups * kTcRows * sizeof(float) + 64;
+  const size_t smem = (size_t)kTcRows * kTcK1 * 2 + (size_t)kTcRows * H * 2 + wbytes + 2 * kTcGroups * kTcRows * sizeof(float) + (((size_t)(Lc + 1) * 4 * d + 4 + 3) & ~size_t(3)) * sizeof(float) + 64;
   if (smem > 227 * 1024) return set_error("flow_tc_pass: shared-memory plan exceeds 227 KB");
   cudaFuncSetAttribute(flow_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const long long tiles = (n + kTcRows - 1) / kTcRows;
