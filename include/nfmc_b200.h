@@ -122,6 +122,15 @@ NFMC_API int64_t nfmc_realnvp_tc_blob_bytes(int32_t d, int32_t n_coupling, int32
 NFMC_API int nfmc_flow_tc_pass(const nfmc_realnvp_tc* flow, int32_t mode, const float* in, float* out, float* aux,
                                int64_t n, void* stream);
 
+/* one NF jump (or one IMH iteration) for a wide flow: log q(x) and x' = T^-1(z) on the tensor cores, then the accept
+ * step of jump.py:212-231 / imh.py:223-233.  logq_cache [n] (optional) is the IMH cache of log q(x): read unless
+ * recompute_logq, and updated where accepted.  workspace: nfmc_jump_tc_workspace_bytes(d, n) bytes of device memory. */
+NFMC_API int64_t nfmc_jump_tc_workspace_bytes(int32_t d, int64_t n);
+NFMC_API int nfmc_jump_step_tc(const nfmc_potential* pot, const nfmc_realnvp_tc* flow, float* x, float* logq_cache,
+                               int32_t recompute_logq, int64_t n, int32_t adjusted, const nfmc_rng* rng, int64_t chain0,
+                               const nfmc_stats* stats, const nfmc_sink* sink, void* workspace, int64_t workspace_bytes,
+                               void* stream);
+
 /* K Langevin steps for all chains -- Langevin.propose (mcmc/langevin.py:61-122) inside the local loop
  * MCMCSampler.sample (mcmc/base.py:69-99).  inv_mass_diag may be NULL (= ones).  adjusted=0 -> ULA. */
 NFMC_API int nfmc_mala_steps(const nfmc_potential* pot, float* x, int64_t n, int32_t n_steps, float step_size,

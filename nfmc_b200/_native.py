@@ -64,6 +64,9 @@ SIGNATURES = {
     "nfmc_flow_log_prob": (C.c_int, [P(RealNVPDesc), _vp, _vp, _i64, _vp]),
     "nfmc_realnvp_tc_blob_bytes": (_i64, [_i32, _i32, _i32]),
     "nfmc_flow_tc_pass": (C.c_int, [P(RealNVPTcDesc), _i32, _vp, _vp, _vp, _i64, _vp]),
+    "nfmc_jump_tc_workspace_bytes": (_i64, [_i32, _i64]),
+    "nfmc_jump_step_tc": (C.c_int, [P(PotentialDesc), P(RealNVPTcDesc), _vp, _vp, _i32, _i64, _i32, P(RngDesc), _i64,
+                                    P(StatsDesc), P(SinkDesc), _vp, _i64, _vp]),
     "nfmc_flow_sample": (C.c_int, [P(RealNVPDesc), P(RngDesc), _i64, _vp, _vp, _i64, _vp]),
     "nfmc_mala_steps": (C.c_int, [P(PotentialDesc), _vp, _i64, _i32, _f32, _vp, _i32, P(RngDesc), _i64,
                                   P(StatsDesc), P(SinkDesc), _vp]),

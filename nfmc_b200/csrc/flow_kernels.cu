@@ -189,6 +189,91 @@ __global__ void __launch_bounds__(kThreads, 3) jump_kernel(const JumpArgs A) {
 }
 
 
+// ---------------------------------------------------------------------------------------------------------
+// Accept step of a jump whose flow passes ran elsewhere (tensor-core path, cond_tc.cu): given x, the proposal
+// x' = T^-1(z) with log|det dx'/dz|, the base draw z and log q(x), do jump.py:212-231 / imh.py:223-233:
+// U(x), U(x'), log alpha, accept, overwrite, moments, counters.  HBM-bound (3 rows in, 1 row out).
+// ---------------------------------------------------------------------------------------------------------
+template <int E>
+__global__ void __launch_bounds__(kThreads) jump_accept_kernel(const AcceptArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const ChainArgs& C = A.c;
+  const Geom g = make_geom(C.d, C.gs);
+  CtaStats st = cta_stats_init(smem, C.d);
+  const int cpc = kThreads / C.gs;
+  const long long tiles = (C.n + cpc - 1) / cpc;
+  unsigned int n_acc = 0, n_bad = 0;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long chain_raw = tile * cpc + threadIdx.x / C.gs;
+    const bool active = chain_raw < C.n;
+    const long long chain = active ? chain_raw : C.n - 1;
+    float* row = C.x + chain * (long long)C.d;
+    float lo[E], hi[E], plo[E], phi[E];
+    load_chain(row, g, lo, hi);
+    load_chain(A.x_prime + chain * (long long)C.d, g, plo, phi);
+    bool accept = true;
+    float f_p = 0.f;
+    if (A.adjusted) {
+      float zlo[E], zhi[E];
+      load_chain(A.z + chain * (long long)C.d, g, zlo, zhi);       // N(z) is permutation invariant: no flip needed
+      f_p = base_log_prob(g, zlo, zhi) - __ldg(A.ld_inv + chain);   // log q(x')
+      const float f_x = __ldg(A.logq_x + chain);
+      const float u_x = pot_prepare_rt<E>(A.pot_kind, C.pot, g, lo, hi).u;
+      const float u_p = pot_prepare_rt<E>(A.pot_kind, C.pot, g, plo, phi).u;
+      const float log_alpha = (-u_p) - (-u_x) + f_x - f_p;          // jump.py:219-224, util.py:392
+      const float u = __ldg(A.uniforms + chain);
+      accept = logf(u) < log_alpha;                                 // jump.py:225
+      if (!(fabsf(log_alpha) <= 3.0e38f) && g.j == 0 && active) ++n_bad;
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      lo[e] = accept ? plo[e] : lo[e];
+      hi[e] = accept ? phi[e] : hi[e];
+    }
+    if (accept && g.j == 0 && active) ++n_acc;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      float4 m = make_float4(lo[e], hi[e], lo[e] * lo[e], hi[e] * hi[e]);
+      if (!active) m = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int kk = g.j + g.gs * e;
+      const float a = across_groups_sum(m.x, g.gs), b = across_groups_sum(m.y, g.gs);
+      const float c = across_groups_sum(m.z, g.gs), dd = across_groups_sum(m.w, g.gs);
+      if (g.lane < g.gs) {
+        if (kk < g.da) { atomicAdd(st.sx + kk, (double)a); atomicAdd(st.sx2 + kk, (double)c); }
+        if (kk < g.db) { atomicAdd(st.sx + g.da + kk, (double)b); atomicAdd(st.sx2 + g.da + kk, (double)dd); }
+      }
+    }
+    if (active) {
+      store_chain(row, g, lo, hi);
+      if (accept && A.adjusted && A.logq_cache && g.j == 0) A.logq_cache[chain] = f_p;   // imh.py:233
+      if (C.sink.samples) sink_store(C.sink, g, C.n, chain, 0, lo, hi);
+    }
+  }
+  n_acc = __reduce_add_sync(0xffffffffu, n_acc);
+  n_bad = __reduce_add_sync(0xffffffffu, n_bad);
+  if ((threadIdx.x & 31) == 0) {
+    if (n_acc) atomicAdd(st.cnt + 0, (unsigned long long)n_acc);
+    if (n_bad) atomicAdd(st.cnt + 2, (unsigned long long)n_bad);
+  }
+  if (threadIdx.x == 0) {
+    long long mine = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const long long first = tile * cpc;
+      mine += (C.n - first) < cpc ? (C.n - first) : cpc;
+    }
+    atomicAdd(st.cnt + 1, (unsigned long long)mine);
+  }
+  cta_stats_finish(st, C.stats, C.d);
+}
+
+template <int E>
+int launch_jump_accept(const AcceptArgs& A, int grid, size_t smem, cudaStream_t s) {
+  NFMC_SET_SMEM_RET(jump_accept_kernel<E>, smem);
+  jump_accept_kernel<E><<<grid, kThreads, smem, s>>>(A);
+  return check_cuda(cudaGetLastError(), "jump_accept_kernel launch");
+}
+template int launch_jump_accept<NFMC_ONLY_E>(const AcceptArgs&, int, size_t, cudaStream_t);
+
 template <int E>
 int launch_flow_pass(const FlowArgs& A, int mode, const float* in, float* out, float* aux, long long n, int grid,
                      size_t smem, cudaStream_t s) {

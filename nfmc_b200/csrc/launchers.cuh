@@ -27,6 +27,18 @@ struct JumpArgs {
   int adjusted;
 };
 
+struct AcceptArgs {
+  ChainArgs c;
+  int pot_kind;
+  int adjusted;
+  const float* x_prime;   // [n, d] proposal
+  const float* z;         // [n, d] base draw that produced it
+  const float* ld_inv;    // [n] log|det dx'/dz|
+  const float* logq_x;    // [n] log q(x)
+  const float* uniforms;  // [n]
+  float* logq_cache;      // [n] optional: receives log q(x') where accepted (IMH cache)
+};
+
 struct NeutraArgs {
   ChainArgs c;
   FlowArgs f;
@@ -45,6 +57,7 @@ template <int E> int launch_flow_pass(const FlowArgs& A, int mode, const float* 
 template <int E> int launch_flow_sample(const FlowArgs& A, const RngArgs& R, long long chain0, float* x, float* logq,
                                         long long n, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_jump(const JumpArgs& A, int grid, size_t smem, cudaStream_t s);
+template <int E> int launch_jump_accept(const AcceptArgs& A, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_neutra_hmc(const NeutraArgs& A, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_neutra_potential(const FlowArgs& FA, int pot_kind, const PotParams& P, const float* z, float* u,
                                              float* grad, long long n, int grid, size_t smem, cudaStream_t s);

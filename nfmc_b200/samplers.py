@@ -66,6 +66,12 @@ class DeviceSession:
         self._t0 = torch.cuda.Event(enable_timing=True)
         self._t1 = torch.cuda.Event(enable_timing=True)
         self._keep = []
+        self._workspace = None
+
+    def workspace(self, nbytes: int) -> torch.Tensor:
+        if self._workspace is None or self._workspace.numel() < nbytes:
+            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._workspace
 
     # -- descriptors ------------------------------------------------------------------------------------------
     def stats(self, jump: bool = False) -> N.StatsDesc:
@@ -303,12 +309,21 @@ class JumpNFMC(Sampler):
     def jump(self, ses: DeviceSession, sink=None, z=None, uniforms=None):
         flow: Flow = self.kernel.flow
         pot, keep = self.target.descriptor(ses.device)
-        fd, keep2 = flow.bijection.descriptor(ses.device)
         rng = N.rng_desc(ses.seed, ses.flow_step, z, uniforms)
         st = ses.stats(jump=True)
-        N.check(N.lib().nfmc_jump_step(C.byref(pot), C.byref(fd), N.ptr(ses.x), ses.n,
-                                       int(bool(self.params.adjusted_jumps)), C.byref(rng), ses.chain0, C.byref(st),
-                                       None if sink is None else C.byref(sink), ses.stream))
+        sk = None if sink is None else C.byref(sink)
+        if flow.bijection.uses_tensor_cores():                    # wide conditioner: flow passes on tcgen05
+            fd, keep2 = flow.bijection.tc_descriptor(ses.device)
+            nb = N.lib().nfmc_jump_tc_workspace_bytes(ses.d, ses.n)
+            ws = ses.workspace(nb)
+            N.check(N.lib().nfmc_jump_step_tc(C.byref(pot), C.byref(fd), N.ptr(ses.x), None, 1, ses.n,
+                                              int(bool(self.params.adjusted_jumps)), C.byref(rng), ses.chain0,
+                                              C.byref(st), sk, N.ptr(ws), nb, ses.stream))
+        else:
+            fd, keep2 = flow.bijection.descriptor(ses.device)
+            N.check(N.lib().nfmc_jump_step(C.byref(pot), C.byref(fd), N.ptr(ses.x), ses.n,
+                                           int(bool(self.params.adjusted_jumps)), C.byref(rng), ses.chain0, C.byref(st),
+                                           sk, ses.stream))
         ses.flow_step += 1
 
     def sample(self, x0: torch.Tensor, show_progress: bool = True, time_limit_seconds=None,
@@ -422,13 +437,17 @@ class AbstractIMH(Sampler):
         dev = ses.device
         T = int(self.params.n_iterations)
         pot, keep = self.target.descriptor(dev)
-        fd, keep2 = flow.bijection.descriptor(dev)
+        tc = flow.bijection.uses_tensor_cores()
+        fd, keep2 = flow.bijection.tc_descriptor(dev) if tc else flow.bijection.descriptor(dev)
         logq = torch.empty(ses.n, device=dev, dtype=torch.float32)
         ses.tic()
         if not self.recompute_logq:                                                  # imh.py:214
-            N.check(N.lib().nfmc_flow_log_prob(C.byref(fd), N.ptr(ses.x), N.ptr(logq), ses.n, ses.stream))
+            if tc:
+                N.check(N.lib().nfmc_flow_tc_pass(C.byref(fd), 2, N.ptr(ses.x), None, N.ptr(logq), ses.n, ses.stream))
+            else:
+                N.check(N.lib().nfmc_flow_log_prob(C.byref(fd), N.ptr(ses.x), N.ptr(logq), ses.n, ses.stream))
         out.statistics.update_elapsed_time(ses.toc())
-        chunk = 1 if (time_limit_seconds is not None or show_progress) else T
+        chunk = 1 if (tc or time_limit_seconds is not None or show_progress) else T
         rs = out.running_samples
         done = 0
         for start in _progress(range(0, T, max(chunk, 1)), self.name, show_progress):
@@ -447,9 +466,16 @@ class AbstractIMH(Sampler):
             rng = N.rng_desc(ses.seed, ses.flow_step, zz, uu)
             st = ses.stats()
             ses.tic()
-            N.check(N.lib().nfmc_imh_steps(C.byref(pot), C.byref(fd), N.ptr(ses.x), N.ptr(logq), ses.n, k,
-                                           int(self.recompute_logq), C.byref(rng), ses.chain0, C.byref(st),
-                                           None if sink is None else C.byref(sink), ses.stream))
+            if tc:
+                nb = N.lib().nfmc_jump_tc_workspace_bytes(ses.d, ses.n)
+                ws = ses.workspace(nb)
+                N.check(N.lib().nfmc_jump_step_tc(C.byref(pot), C.byref(fd), N.ptr(ses.x), N.ptr(logq),
+                                                  int(self.recompute_logq), ses.n, 1, C.byref(rng), ses.chain0, C.byref(st),
+                                                  None if sink is None else C.byref(sink), N.ptr(ws), nb, ses.stream))
+            else:
+                N.check(N.lib().nfmc_imh_steps(C.byref(pot), C.byref(fd), N.ptr(ses.x), N.ptr(logq), ses.n, k,
+                                               int(self.recompute_logq), C.byref(rng), ses.chain0, C.byref(st),
+                                               None if sink is None else C.byref(sink), ses.stream))
             out.statistics.update_elapsed_time(ses.toc())
             ses.flow_step += k
             done += k
