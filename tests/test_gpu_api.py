@@ -1,0 +1,198 @@
+"""B200: API conformance -- the reference's own smoke tests (/root/reference/test/*.py) restated against nfmc_b200 for the
+strategies on the accelerated path.  Same assertions: return type, sample shapes, finiteness, store_samples semantics,
+flow-string parsing, moment shapes, N-D events, warm-up hand-off."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import nfmc_b200
+from nfmc_b200 import sample, create_sampler
+from nfmc_b200.potentials import StandardGaussian, DiagonalGaussian
+from nfmc_b200.records import MCMCOutput
+
+
+def _g(shape):
+    return StandardGaussian(shape)
+
+
+# /root/reference/test/test_samplers.py:20-40 (test_mcmc), restricted to the local kernels on the hot path
+@pytest.mark.parametrize("name", ["HMC", "UHMC", "MALA", "ULA"])
+def test_mcmc(name):
+    from nfmc_b200 import samplers
+    torch.manual_seed(0)
+    s = getattr(samplers, name)(event_shape=(5,), target=_g((5,)))
+    s.params.n_iterations = 3
+    out = s.sample(x0=torch.randn(4, 5), show_progress=False)
+    assert isinstance(out, MCMCOutput)
+    assert out.samples.shape == (3, 4, 5) and bool(torch.isfinite(out.samples).all())
+
+
+# test_samplers.py:124-145 (test_jump_nfmc)
+@pytest.mark.parametrize("name", ["JumpMALA", "JumpHMC", "JumpUHMC", "JumpULA"])
+def test_jump_nfmc(name):
+    from nfmc_b200 import samplers
+    torch.manual_seed(0)
+    s = getattr(samplers, name)(event_shape=(5,), target=_g((5,)))
+    s.params.n_iterations = 3
+    s.inner_sampler.params.n_iterations = 4
+    out = s.sample(x0=torch.randn(4, 5), show_progress=False)
+    assert isinstance(out, MCMCOutput)
+    assert out.samples.shape == (3 * (4 + 1), 4, 5) and bool(torch.isfinite(out.samples).all())
+
+
+# test_samplers.py:148-172 (test_other_nfmc)
+@pytest.mark.parametrize("name", ["NeuTraHMC", "FixedIMH", "AdaptiveIMH"])
+def test_other_nfmc(name):
+    from nfmc_b200 import samplers
+    torch.manual_seed(0)
+    s = getattr(samplers, name)(event_shape=(5,), target=_g((5,)))
+    s.params.n_iterations = 3
+    out = s.sample(x0=torch.randn(4, 5), show_progress=False)
+    assert isinstance(out, MCMCOutput)
+    assert out.samples.shape == (3, 4, 5) and bool(torch.isfinite(out.samples).all())
+
+
+# test_samplers.py:175-201 (test_sample_wrapper_no_jump)
+@pytest.mark.parametrize("strategy", ["hmc", "uhmc", "ula", "mala", "imh", "neutra_hmc"])
+def test_sample_wrapper_no_jump(strategy):
+    torch.manual_seed(0)
+    out = sample(_g((5,)), event_shape=(5,), strategy=strategy, n_chains=4, n_iterations=3, device=torch.device("cuda"),
+                 show_progress=False)
+    assert isinstance(out, MCMCOutput)
+    assert out.samples.shape == (3, 4, 5) and bool(torch.isfinite(out.samples).all())
+
+
+# test_samplers.py:227-248 (test_sample_wrapper_jump)
+@pytest.mark.parametrize("strategy", ["jump_mala", "jump_ula", "jump_hmc", "jump_uhmc"])
+def test_sample_wrapper_jump(strategy):
+    torch.manual_seed(0)
+    out = sample(_g((5,)), event_shape=(5,), strategy=strategy, n_chains=4, n_iterations=3,
+                 inner_param_kwargs={"n_iterations": 7}, device=torch.device("cuda"), show_progress=False)
+    assert out.samples.shape == (3 * 8, 4, 5) and bool(torch.isfinite(out.samples).all())
+
+
+def test_jump_hmc_default_inner_iterations():
+    """create_sampler forces 5 inner HMC steps for jump_hmc (/root/reference/nfmc/sample.py:161-162)."""
+    out = sample(_g((5,)), strategy="jump_hmc", n_chains=4, n_iterations=2, show_progress=False)
+    assert out.samples.shape == (2 * 6, 4, 5)
+
+
+# test_flow_kwargs.py
+def test_flow_kwargs():
+    torch.manual_seed(0)
+    basic = sample(event_shape=(100,), target=_g((100,)), flow="realnvp", strategy="imh", n_iterations=3, n_warmup_iterations=3,
+                   show_progress=False)
+    adv = sample(event_shape=(100,), target=_g((100,)), flow='realnvp%{"n_layers": 10}', strategy="imh", n_iterations=3,
+                 show_progress=False)
+    adv2 = sample(event_shape=(100,), target=_g((100,)), strategy="imh", n_iterations=3, show_progress=False,
+                  flow='realnvp%{"n_layers": 10, "conditioner_kwargs": {"n_layers": 5, "n_hidden": 100}}', n_chains=16)
+    nb = len(basic.kernel.flow.bijection.layers)
+    assert len(adv.kernel.flow.bijection.layers) > nb and len(adv2.kernel.flow.bijection.layers) > nb
+    assert bool(torch.isfinite(adv2.samples).all())
+
+
+# test_no_sample_storing.py:33-49 (test_sampling)
+@pytest.mark.parametrize("strategy", ["hmc", "uhmc", "ula", "mala", "imh", "fixed_imh", "jump_mala", "jump_ula", "jump_hmc",
+                                      "jump_uhmc", "neutra_hmc"])
+def test_no_sample_storing(strategy):
+    torch.manual_seed(0)
+    s = create_sampler(target=_g((10,)), event_shape=(10,), strategy=strategy, param_kwargs={"store_samples": False})
+    out = s.sample(torch.randn(20, 10), time_limit_seconds=1.0, show_progress=False)
+    assert out.samples is None
+    assert out.running_samples.last_sample is not None and out.running_samples.last_sample.shape == (20, 10)
+
+
+def test_adaptive_imh_ignores_param_kwargs():
+    """Quirk Q2 (/root/reference/nfmc/sample.py:129): adaptive_imh always runs 100 iterations and stores samples."""
+    s = create_sampler(target=_g((10,)), event_shape=(10,), strategy="adaptive_imh", param_kwargs={"store_samples": False, "n_iterations": 3})
+    out = s.sample(torch.randn(8, 10), show_progress=False)
+    assert out.samples.shape == (100, 8, 10)
+    assert out.statistics.n_target_gradient_calls == 2 * 8 * 100 and out.statistics.n_target_calls == 0   # quirk Q3
+
+
+# test_moment_estimation.py
+@pytest.mark.parametrize("strategy", ["hmc", "mala", "imh", "adaptive_imh", "jump_mala", "jump_hmc", "neutra_hmc"])
+def test_moments(strategy):
+    torch.manual_seed(0)
+    out = sample(target=_g((10,)), event_shape=(10,), strategy=strategy, n_iterations=3, n_warmup_iterations=3, show_progress=False)
+    for t in (out.mean, out.second_moment, out.variance, out.statistics.running_first_moment, out.statistics.running_second_moment):
+        assert t.shape == (10,) and bool(t.isfinite().all())
+
+
+def test_moments_diag_gaussian_100d():
+    torch.manual_seed(0)
+    target = DiagonalGaussian((100,), 1.0 / torch.linspace(1.0, 10.0, 100) ** 2)
+    for cls in ("HMC", "NeuTraHMC", "JumpHMC", "AdaptiveIMH"):
+        from nfmc_b200 import samplers
+        s = getattr(samplers, cls)(target.event_shape, target)
+        s.params.n_iterations = 3
+        if cls == "JumpHMC":
+            s.inner_sampler.params.n_iterations = 3
+        out = s.sample(torch.randn(100, 100), show_progress=False)
+        assert out.statistics.running_first_moment.shape == (100,) and bool(out.statistics.running_second_moment.isfinite().all())
+
+
+# test_custom_shapes.py (N-D events)
+@pytest.mark.parametrize("strategy", ["imh", "jump_hmc", "neutra_hmc", "hmc", "jump_mala", "mala"])
+def test_image_shaped_events(strategy):
+    torch.manual_seed(0)
+    out = sample(_g((8, 8)), event_shape=(8, 8), strategy=strategy, n_iterations=2, n_warmup_iterations=2, n_chains=3, warmup=False,
+                 inner_param_kwargs=dict(n_iterations=2), show_progress=False)
+    rows = {"jump_hmc": 6, "jump_mala": 6}.get(strategy, 2)
+    assert out.samples.shape == (rows, 3, 8, 8) and out.mean.shape == (8, 8)
+    assert out.running_samples.last_sample.shape == (3, 8, 8)
+
+
+# test_warmup.py (local samplers + jump): step size and mass adapt, sampling starts from the warm-up state
+@pytest.mark.parametrize("strategy", ["mala", "hmc", "jump_mala", "jump_hmc"])
+def test_warmup_then_sample(strategy):
+    torch.manual_seed(0)
+    s = create_sampler(target=DiagonalGaussian((10,), torch.linspace(0.5, 5.0, 10)), event_shape=(10,), strategy=strategy,
+                       param_kwargs={"n_iterations": 5, "n_warmup_iterations": 30}, inner_param_kwargs={"n_iterations": 4, "n_warmup_iterations": 30})
+    inner = getattr(s, "inner_sampler", s)
+    step0 = inner.kernel.step_size
+    w = s.warmup(torch.randn(64, 10), show_progress=False)
+    assert isinstance(w, MCMCOutput) and w.running_samples.last_sample.shape == (64, 10)
+    assert inner.kernel.step_size != step0 and not inner.kernel.has_unit_mass()
+    assert not inner.params.tuning
+    out = sample(DiagonalGaussian((10,), torch.linspace(0.5, 5.0, 10)), strategy=strategy, n_chains=32, n_iterations=3,
+                 n_warmup_iterations=10, warmup=True, show_progress=False, inner_param_kwargs={"n_iterations": 4, "n_warmup_iterations": 10})
+    assert bool(torch.isfinite(out.samples).all())
+
+
+def test_time_limit_stops_early():
+    s = create_sampler(target=_g((100,)), event_shape=(100,), strategy="jump_mala", param_kwargs={"n_iterations": 100000, "store_samples": False})
+    out = s.sample(torch.randn(4096, 100), time_limit_seconds=0.2, show_progress=False)
+    assert 0 < out.statistics.n_attempted_jumps < 100000 * 4096
+    assert out.statistics.elapsed_time_seconds >= 0.2
+
+
+def test_unsupported_strategy_and_target_raise():
+    with pytest.raises(NotImplementedError):
+        sample(_g((5,)), strategy="tess", n_chains=4, n_iterations=2)
+    with pytest.raises(NotImplementedError):
+        sample(lambda x: (x ** 2).sum(-1), event_shape=(5,), strategy="mala", n_chains=4, n_iterations=2)
+    with pytest.raises(ValueError):
+        nfmc_b200.samplers.JumpMALA((5,), _g((5,)), inner_params=nfmc_b200.records.LangevinParameters(store_samples=False)).sample(torch.randn(3, 5))
+
+
+def test_thinning_and_max_samples():
+    from nfmc_b200.samplers import MALA
+    s = MALA((6,), _g((6,)))
+    s.params.n_iterations = 10
+    out = s.sample(torch.randn(5, 6), show_progress=False)
+    full = out.samples
+    torch.manual_seed(1)
+    # same chain, same seed, with thinning 3: rows 0, 3, 6, 9 of the un-thinned run
+    s2 = MALA((6,), _g((6,)))
+    s2.params.n_iterations = 10
+    s.seed = s2.seed = 77
+    full = s.sample(torch.zeros(5, 6), show_progress=False).samples
+    from nfmc_b200.records import MCMCOutput as MO
+    import nfmc_b200.samplers as S
+    out2 = MO((6,), store_samples=True)
+    out2.running_samples.thinning = 3
+    ses = S.DeviceSession(torch.zeros(5, 6), (6,), None, seed=77)
+    buf = s2.run_steps(ses, out2, 10, True)
+    assert buf.shape[0] == 4 and torch.equal(buf.cpu(), full[0::3])
