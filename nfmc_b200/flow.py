@@ -243,13 +243,17 @@ class Flow(nn.Module):
             return x, lq.reshape(tuple(sample_shape))
         return x
 
-    # -- training (not yet native) -------------------------------------------------------
-    def fit(self, *args, **kwargs):
-        raise NotImplementedError("Flow.fit: flow training on the device is the next row of the scope table "
-                                  "(SURVEY.md section 8f); the frozen-flow hot path does not need it")
+    # -- training (library-backed for now: nfmc_b200/flow_train.py) ------------------------------------------------------
+    def fit(self, x_train, *args, **kwargs):
+        """Maximum-likelihood fit (reference call sites: jump.py:139-151,201; imh.py:171-175).  Raises ``ValueError`` when
+        the loss becomes non-finite, which the callers turn into a weight rollback."""
+        from . import flow_train
+        return flow_train.fit(self, x_train, *args, **kwargs)
 
-    def variational_fit(self, *args, **kwargs):
-        raise NotImplementedError("Flow.variational_fit: see Flow.fit")
+    def variational_fit(self, target_log_prob, *args, **kwargs):
+        """Reverse-KL fit to ``target_log_prob`` (reference call sites: imh.py:67-72, neutra.py:84-91)."""
+        from . import flow_train
+        return flow_train.variational_fit(self, target_log_prob, *args, **kwargs)
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -72,6 +72,12 @@ class Potential:
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         return self.value_and_grad(x, need_grad=False)[0]
 
+    def log_prob_fn(self):
+        """``lambda v: -U(v)``, differentiable in torch with the value / gradient supplied by the CUDA kernel
+        (what the reference passes to ``flow.variational_fit``: imh.py:68, neutra.py:85)."""
+        from .flow_train import target_log_prob_fn
+        return target_log_prob_fn(self)
+
 
 class IsotropicGaussian(Potential):
     """U = 1/2 w sum x_i^2."""

@@ -334,8 +334,6 @@ class JumpNFMC(Sampler):
         inner = self.inner_sampler
         if not inner.params.store_samples:
             raise ValueError("Inner sampler in jump HMC must store samples")     # reference: jump.py:163-164
-        if p.fit_nf:
-            raise NotImplementedError("fit_nf=True needs on-device flow training (SURVEY.md section 8f rank 2)")
         event_shape = tuple(x0.shape[1:])
         out = JumpNFMCOutput(event_shape=event_shape, store_samples=p.store_samples)
         ses = DeviceSession(x0, event_shape, self.device, self.seed, self.chain0)
@@ -351,7 +349,16 @@ class JumpNFMC(Sampler):
             ses.tic()
             nz = None if normals is None else N.dev_f32(normals[i], dev)
             un = None if uniforms is None else N.dev_f32(uniforms[i], dev)
-            buf = inner.run_steps(ses, out, K, store, nz, un)                       # jump.py:178-189
+            need_block = store or (p.fit_nf and i >= p.n_jumps_before_training and K * ses.n * ses.d * 4 <= (2 << 30))
+            buf = inner.run_steps(ses, out, K, need_block, nz, un)                  # jump.py:178-189
+            if p.fit_nf and i >= p.n_jumps_before_training:                         # jump.py:193-201
+                from .flow_train import train_val_split
+                # training rows: the inner (step, chain) block when it fits on the device, else the current states
+                pool = buf if buf is not None else ses.x[None]
+                x_train, x_val = train_val_split(pool, p.train_pct, p.max_train_size, p.max_val_size)
+                self.kernel.flow.fit(x_train=x_train, x_val=x_val, **p.flow_fit_kwargs)
+            if not store:
+                buf = None
             jbuf = None
             jsink = None
             if store:
@@ -382,11 +389,23 @@ class JumpNFMC(Sampler):
         return out
 
     def warmup(self, x0, show_progress=True, time_limit_seconds=None) -> MCMCOutput:
-        """Inner-sampler warm-up (step size, mass); the flow-fitting half of the reference's warm-up
-        (jump.py:124-151) needs on-device training and is not done."""
+        """Reference: JumpNFMC.warmup (jump.py:104-154): tune the inner sampler (70 % of the budget), then fit the flow
+        to the warm-up samples with weight rollback if the fit diverges."""
+        from .flow_train import train_val_split
         limit = None if time_limit_seconds is None else 0.7 * time_limit_seconds
+        t0 = time.time()
         self.inner_sampler.params.store_samples = True
-        return self.inner_sampler.warmup(x0, show_progress=show_progress, time_limit_seconds=limit)
+        out = self.inner_sampler.warmup(x0, show_progress=show_progress, time_limit_seconds=limit)
+        p: JumpNFMCParameters = self.params
+        x_train, x_val = train_val_split(out.samples, p.train_pct, p.max_train_size, p.max_val_size)
+        backup = deepcopy(self.kernel.flow.state_dict())
+        fit_limit = None if time_limit_seconds is None else max(time_limit_seconds - (time.time() - t0), 0.0)
+        try:
+            self.kernel.flow.fit(x_train=x_train, x_val=x_val,
+                                 **{**p.flow_fit_kwargs, "show_progress": show_progress, "time_limit_seconds": fit_limit})
+        except ValueError:
+            self.kernel.flow.load_state_dict(backup)
+        return out
 
 
 def _make_inner(cls, event_shape, target, kernel, params):
@@ -423,13 +442,15 @@ class AbstractIMH(Sampler):
         super().__init__(event_shape, target, kernel or IMHKernel(tuple(event_shape)), params or IMHParameters())
 
     def warmup(self, x0, show_progress=True, time_limit_seconds=None) -> MCMCOutput:
-        """The reference fits the flow variationally (imh.py:67-72); training is not on the device yet, so
-        warm-up only draws the initial state from the flow as the reference does afterwards (imh.py:73-75)."""
+        """Reference: AbstractIMH.warmup (imh.py:60-75): variational fit of the flow to the target, then the initial
+        state is a draw from the fitted flow."""
+        self.kernel.flow.variational_fit(self.target.log_prob_fn(), **self.params.warmup_fit_kwargs,
+                                         show_progress=show_progress, time_limit_seconds=time_limit_seconds)
         out = MCMCOutput(event_shape=tuple(x0.shape[1:]), store_samples=self.params.store_samples)
         out.running_samples.add(self.kernel.flow.sample(x0.shape[0]).cpu())
         return out
 
-    def _run(self, x0, show_progress, time_limit_seconds, store, z=None, uniforms=None) -> MCMCOutput:
+    def _run(self, x0, show_progress, time_limit_seconds, store, z=None, uniforms=None, after_iteration=None) -> MCMCOutput:
         event_shape = tuple(x0.shape[1:])
         out = MCMCOutput(event_shape=event_shape, store_samples=store)
         flow: Flow = self.kernel.flow
@@ -447,7 +468,7 @@ class AbstractIMH(Sampler):
             else:
                 N.check(N.lib().nfmc_flow_log_prob(C.byref(fd), N.ptr(ses.x), N.ptr(logq), ses.n, ses.stream))
         out.statistics.update_elapsed_time(ses.toc())
-        chunk = 1 if (tc or time_limit_seconds is not None or show_progress) else T
+        chunk = 1 if (tc or after_iteration is not None or time_limit_seconds is not None or show_progress) else T
         rs = out.running_samples
         done = 0
         for start in _progress(range(0, T, max(chunk, 1)), self.name, show_progress):
@@ -481,6 +502,10 @@ class AbstractIMH(Sampler):
             done += k
             if buf is not None:
                 rs.add(buf.reshape(-1, ses.n, *event_shape), already_thinned=True, n_seen=k)
+            if after_iteration is not None:
+                after_iteration(start, out)
+                tc2 = flow.bijection.uses_tensor_cores()                              # parameters changed: re-pack
+                fd, keep2 = flow.bijection.tc_descriptor(dev) if tc2 else flow.bijection.descriptor(dev)
         sx, sx2, cnt = ses.read_back()
         out.statistics.expectations.add_sums(sx, sx2, ses.n * done)
         out.statistics.update_counters(n_accepted_trajectories=cnt[0], n_attempted_trajectories=cnt[1])
@@ -503,17 +528,43 @@ class FixedIMH(AbstractIMH):
 
 
 class AdaptiveIMH(AbstractIMH):
-    """Adaptive IMH with the adaptation switched off: the flow-refit step of the reference (imh.py:152-175)
-    needs on-device training.  The MH part follows imh.py:122-150: log q(x) is
-    recomputed every iteration and samples are always stored (quirk Q2)."""
+    """Adaptive IMH (reference: imh.py:78-181).  The MH part follows imh.py:122-150: log q(x) is recomputed every
+    iteration and samples are always stored (quirk Q2).  With ``adapt=True`` (default) the flow is refitted for one
+    epoch on a randomly chosen stored iteration with probability ``adaptation_dropoff**i`` (imh.py:152-175, rollback on
+    ``ValueError``); that needs one launch per iteration.  ``adapt=False`` fuses all iterations into one launch."""
     recompute_logq = True
+    adapt = True
 
     @property
     def name(self):
         return "Adaptive IMH"
 
     def sample(self, x0, show_progress=True, time_limit_seconds=None, z=None, uniforms=None) -> MCMCOutput:
-        return self._run(x0, show_progress, time_limit_seconds, True, z, uniforms)
+        if not self.adapt:
+            return self._run(x0, show_progress, time_limit_seconds, True, z, uniforms)
+        return self._run(x0, show_progress, time_limit_seconds, True, z, uniforms, after_iteration=self._maybe_refit)
+
+    def _maybe_refit(self, i: int, out: MCMCOutput):
+        p: IMHParameters = self.params
+        if float(torch.rand(())) >= p.adaptation_dropoff ** i:                       # imh.py:152-154
+            return
+        n_samples = out.running_samples.n_samples
+        if n_samples == 0:
+            return
+        if p.train_distribution == 'uniform':
+            k = int(torch.randint(0, n_samples, ()))
+        elif p.train_distribution == 'bounded_geom_approx':
+            k = int(torch.randint(max(0, n_samples - 100), n_samples, ()))
+        else:  # bounded_geom (imh.py:39-45)
+            v = torch.arange(0, n_samples)
+            pdf = 0.025 * (1 - 0.025) ** (n_samples - 1 - v) / (1 - (1 - 0.025) ** n_samples)
+            k = int(torch.searchsorted(torch.cumsum(pdf, 0), float(torch.rand(())), right=True).clamp(max=n_samples - 1))
+        x_train = out.running_samples[k]
+        backup = deepcopy(self.kernel.flow.state_dict())
+        try:
+            self.kernel.flow.fit(x_train, n_epochs=1, show_progress=False)            # imh.py:171-175
+        except ValueError:
+            self.kernel.flow.load_state_dict(backup)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -536,17 +587,20 @@ class NeuTraHMC(Sampler):
         return "NeuTra HMC"
 
     def sample(self, x0, show_progress=True, time_limit_seconds=None, normals=None, uniforms=None) -> MCMCOutput:
+        return self._run(x0, int(self.params.n_iterations), False, show_progress, time_limit_seconds, normals, uniforms)
+
+    def _run(self, x0, T, tuning, show_progress=True, time_limit_seconds=None, normals=None, uniforms=None) -> MCMCOutput:
         event_shape = tuple(x0.shape[1:])
         store = bool(self.params.store_samples)
         out = MCMCOutput(event_shape, store_samples=store)
         ses = DeviceSession(x0, event_shape, self.device, self.seed, self.chain0)
         dev = ses.device
-        T = int(self.params.n_iterations)
         L = int(self.inner_kernel.n_leapfrog_steps)
         pot, keep = self.target.descriptor(dev)
         fd, keep2 = self.kernel.flow.bijection.descriptor(dev)
         imd = _imd_device(self.inner_kernel, dev)
-        chunk = 1 if (time_limit_seconds is not None or show_progress) else T
+        chunk = 1 if (tuning or time_limit_seconds is not None or show_progress) else T
+        prev_acc = 0
         rs = out.running_samples
         done = 0
         for start in _progress(range(0, T, max(chunk, 1)), self.name, show_progress):
@@ -574,6 +628,16 @@ class NeuTraHMC(Sampler):
             done += k
             if buf is not None:
                 rs.add(buf.reshape(-1, ses.n, *event_shape), already_thinned=True, n_seen=k)
+            if tuning:                                                                # mcmc/base.py:142-161 on the latent chain
+                ip, ik = self.inner_params, self.inner_kernel
+                acc = int(ses.counts[0])
+                if ses.n > 1 and ip.tune_inv_mass_diag:
+                    ik.inv_mass_diag = ip.imd_adjustment * torch.var(ses.x, dim=0).cpu() + (1 - ip.imd_adjustment) * ik.inv_mass_diag
+                    imd = _imd_device(ik, dev)
+                if ip.tune_step_size and ip.adjustment:
+                    ik.da.step(ik.da_params.target_acceptance_rate - (acc - prev_acc) / (ses.n * k))
+                    ik.step_size = ik.da.value
+                prev_acc = acc
         sx, sx2, cnt = ses.read_back()
         out.statistics.expectations.add_sums(sx, sx2, ses.n * done)
         out.statistics.update_counters(n_accepted_trajectories=cnt[0], n_attempted_trajectories=cnt[1],
@@ -585,5 +649,13 @@ class NeuTraHMC(Sampler):
         return out
 
     def warmup(self, x0, show_progress=True, time_limit_seconds=None) -> MCMCOutput:
-        raise NotImplementedError("NeuTra warm-up = variational flow fit + latent HMC tuning (neutra.py:70-107); "
-                                  "flow training on the device is the next scope row (SURVEY.md section 8f)")
+        """Reference: NeuTra.warmup (neutra.py:70-107): variational fit of the flow (30 % of the budget), then tune the
+        latent HMC (step size by dual averaging, inverse mass by the across-chain variance EMA)."""
+        flow_limit = None if time_limit_seconds is None else 0.3 * time_limit_seconds
+        t0 = time.time()
+        self.kernel.flow.variational_fit(self.target.log_prob_fn(),
+                                         **{"time_limit_seconds": flow_limit, **self.params.warmup_fit_kwargs},
+                                         show_progress=show_progress)
+        left = None if time_limit_seconds is None else max(time_limit_seconds - (time.time() - t0), 0.0)
+        self.inner_params.n_warmup_iterations = self.params.n_warmup_iterations
+        return self._run(x0, int(self.params.n_warmup_iterations), True, show_progress, left)

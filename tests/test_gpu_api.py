@@ -196,3 +196,60 @@ def test_thinning_and_max_samples():
     ses = S.DeviceSession(torch.zeros(5, 6), (6,), None, seed=77)
     buf = s2.run_steps(ses, out2, 10, True)
     assert buf.shape[0] == 4 and torch.equal(buf.cpu(), full[0::3])
+
+
+# ---- flow training hooks (library-backed, nfmc_b200/flow_train.py) -------------------------------------------------------
+def test_flow_fit_improves_likelihood_and_kernels_see_new_weights():
+    from nfmc_b200.flow import create_flow_object
+    torch.manual_seed(0)
+    flow = create_flow_object("realnvp", (6,)).to("cuda")
+    x = 0.3 * torch.randn(2048, 6, device="cuda") + 1.5
+    before = float(flow.log_prob(x).mean())
+    flow.fit(x, n_epochs=60, lr=0.05, batch_size=512)
+    after = float(flow.log_prob(x).mean())                 # log_prob runs the CUDA kernel on the re-packed blob
+    assert after > before + 1.0
+    from nfmc_b200.flow_train import log_prob_autograd
+    with torch.no_grad():
+        ref = float(log_prob_autograd(flow, x).mean())
+    assert abs(after - ref) < 1e-3 * (1 + abs(ref))
+
+
+def test_jump_mala_with_in_loop_flow_fitting():
+    """fit_nf=True (config C5's shape of loop): the flow is refitted inside the sampling loop and jump acceptance rises."""
+    torch.manual_seed(0)
+    target = DiagonalGaussian((8,), torch.full((8,), 4.0), mean=torch.full((8,), 2.0))
+    common = dict(strategy="jump_mala", n_chains=1024, show_progress=False, inner_param_kwargs={"n_iterations": 20},
+                  x0=2.0 + 0.5 * torch.randn(1024, 8))
+    frozen = sample(target, n_iterations=6, param_kwargs={"fit_nf": False}, **common)
+    fitted = sample(target, n_iterations=6, param_kwargs={"fit_nf": True, "n_jumps_before_training": 1,
+                                                           "flow_fit_kwargs": {"n_epochs": 30, "lr": 0.05, "batch_size": 1024}}, **common)
+    assert fitted.statistics.jump_acceptance_rate > frozen.statistics.jump_acceptance_rate + 0.05
+    assert bool(torch.isfinite(fitted.samples).all())
+
+
+def test_imh_and_neutra_warmup_fit_the_flow():
+    torch.manual_seed(0)
+    target = DiagonalGaussian((6,), torch.full((6,), 1.0), mean=torch.full((6,), 1.0))
+    s = create_sampler(target, strategy="imh", param_kwargs={"n_iterations": 5, "warmup_fit_kwargs": {"n_epochs": 150, "lr": 0.05, "n_samples": 256}})
+    w = s.warmup(torch.randn(256, 6), show_progress=False)
+    out = s.sample(w.running_samples.last_sample, show_progress=False)
+    assert out.statistics.acceptance_rate > 0.3            # an untrained (identity) flow gets far less on a shifted target
+    s2 = create_sampler(target, strategy="neutra_hmc", param_kwargs={"n_iterations": 3, "n_warmup_iterations": 10,
+                                                                      "warmup_fit_kwargs": {"n_epochs": 50, "lr": 0.05, "n_samples": 128}})
+    step0 = s2.inner_kernel.step_size
+    w2 = s2.warmup(torch.randn(64, 6), show_progress=False)
+    assert s2.inner_kernel.step_size != step0 and w2.running_samples.last_sample.shape == (64, 6)
+    assert bool(torch.isfinite(s2.sample(w2.running_samples.last_sample, show_progress=False).samples).all())
+
+
+def test_adaptive_imh_refits():
+    torch.manual_seed(0)
+    from nfmc_b200.samplers import AdaptiveIMH
+    target = DiagonalGaussian((6,), torch.full((6,), 1.0), mean=torch.full((6,), 1.0))
+    s = AdaptiveIMH((6,), target)
+    s.params.n_iterations = 12
+    before = {k: v.clone() for k, v in s.kernel.flow.state_dict().items()}
+    out = s.sample(torch.randn(512, 6), show_progress=False)
+    after = s.kernel.flow.state_dict()
+    assert any(not torch.equal(before[k].cpu(), after[k].cpu()) for k in before)
+    assert out.samples.shape == (12, 512, 6)

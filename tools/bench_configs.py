@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Chain-steps/s of every BASELINE.json config that fits one GPU, through the public API (device-resident state,
+store_samples=False).  One JSON line per config.  Not the driver's bench (that is bench.py); numbers go to DESIGN.md."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import nfmc_b200
+from nfmc_b200.potentials import make_potential
+from nfmc_b200.flow import create_flow_object
+
+
+def flow_for(d, spec="realnvp"):
+    torch.manual_seed(0)
+    f = create_flow_object(spec, (d,))
+    with torch.no_grad():
+        for p in f.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    return f
+
+
+def run(name, strategy, pot, d, n, T, K=None, flow_spec="realnvp", **kw):
+    flow = flow_for(d, flow_spec)
+    ik = {} if K is None else {"inner_param_kwargs": {"n_iterations": K}}
+    s = nfmc_b200.create_sampler(make_potential(pot, (d,)), flow=flow, strategy=strategy,
+                                 param_kwargs={"n_iterations": T, "store_samples": False}, **ik, **kw)
+    if hasattr(s, "adapt"):
+        s.adapt = False                      # the refit (flow training) is a separate, library-backed step
+    x0 = torch.randn(n, d, device="cuda") * 0.5
+    s.params.n_iterations = max(1, T // 4)
+    s.sample(x0, show_progress=False)                       # warm-up launch
+    s.params.n_iterations = T
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = s.sample(x0, show_progress=False)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    steps = out.statistics.expectations.n_seen
+    st = out.statistics
+    print(json.dumps({"config": name, "strategy": strategy, "potential": pot, "d": d, "chains": n, "iterations": T, "inner": K,
+                      "flow": flow_spec, "tensor_cores": flow.bijection.uses_tensor_cores(), "seconds": dt,
+                      "chain_steps_per_s": steps / dt, "device_seconds": st.elapsed_time_seconds,
+                      "acc_rate": st.acceptance_rate, "jump_acc_rate": getattr(st, "jump_acceptance_rate", None)}), flush=True)
+
+
+if __name__ == "__main__":
+    wide = 'realnvp%{"n_layers": 4, "conditioner_kwargs": {"n_layers": 2, "n_hidden": 256}}'
+    run("C1 README jump_mala d=25 n=100", "jump_mala", "g0", 25, 100, 200, K=100)
+    run("C2 jump_hmc d=100 n=65536", "jump_hmc", "g1", 100, 65536, 20, K=5)
+    run("C3 neutra_hmc funnel d=100 n=262144", "neutra_hmc", "fn", 100, 262144, 3, inner_kernel_kwargs={"step_size": 0.01})
+    run("C4 imh rosenbrock d=100 n=2^20", "imh", "rb", 100, 1 << 20, 20)
+    run("C4 adaptive_imh(no refit) d=100 n=2^17", "adaptive_imh", "rb", 100, 1 << 17, 100)
+    run("C5-shape jump_mala mixture d=1000 n=131072 (1/8 of 2^20, frozen flow)", "jump_mala", "gm", 1000, 131072, 2, K=100)
+    run("CT jump_mala d=100 n=2^20", "jump_mala", "g0", 100, 1 << 20, 5, K=100)
+    run("wide-flow jump_mala d=100 n=2^20 H=256 Lc=4 (tcgen05)", "jump_mala", "g0", 100, 1 << 20, 5, K=100, flow_spec=wide)
+    run("wide-flow imh d=100 n=2^20 H=256 Lc=4 (tcgen05)", "imh", "g0", 100, 1 << 20, 10, flow_spec=wide)
