@@ -43,6 +43,30 @@ extern "C" int64_t nfmc_jump_workspace_bytes(int32_t d, int64_t n, int64_t blob_
 }
 
 // Host-buffer path: x0 in, final state + pooled statistics out; every copy is inside the call.
+// The chain batch is cut into slabs that are pipelined over three streams -- slab i's H2D copy, its kernels and its
+// D2H copy overlap the neighbours' -- so the PCIe transfers (2 x 4*n*d bytes) hide behind the compute.  Chains keep
+// their global index (chain0 + row), so the result is identical to one big launch.
+namespace {
+struct HostPipe {
+  cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
+  int device = -1;
+};
+thread_local HostPipe g_pipe;
+int ensure_pipe() {
+  int dev = 0;
+  if (int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return e;
+  if (g_pipe.device == dev) return 0;
+  for (int i = 0; i < 3; ++i) {
+    if (int e = check_cuda(cudaStreamCreateWithFlags(&g_pipe.streams[i], cudaStreamNonBlocking), "stream create")) return e;
+    if (int e = check_cuda(cudaEventCreateWithFlags(&g_pipe.join[i], cudaEventDisableTiming), "event create")) return e;
+  }
+  if (int e = check_cuda(cudaEventCreateWithFlags(&g_pipe.fork, cudaEventDisableTiming), "event create")) return e;
+  g_pipe.device = dev;
+  return 0;
+}
+}  // namespace
+
 extern "C" int nfmc_jump_sample_host(const nfmc_potential* pot_h, const float* pot_params_host, int64_t pot_params_floats,
                                      const nfmc_realnvp* flow_h, const float* blob_host, float* x_host, int64_t n,
                                      int32_t inner_kind, int32_t n_outer, int32_t n_inner, float step_size, int32_t n_leapfrog,
@@ -52,6 +76,7 @@ extern "C" int nfmc_jump_sample_host(const nfmc_potential* pot_h, const float* p
   const int d = pot_h->d;
   if (workspace_bytes < nfmc_jump_workspace_bytes(d, n, flow_h->blob_floats)) return set_error("jump_sample_host: workspace too small");
   if (pot_params_floats > 2 * (int64_t)d) return set_error("jump_sample_host: too many potential parameters");
+  if (int e = ensure_pipe()) return e;
   cudaStream_t s = (cudaStream_t)stream;
   unsigned char* w = static_cast<unsigned char*>(workspace);
   float* x_dev = reinterpret_cast<float*>(w); w += align256((size_t)n * d * sizeof(float));
@@ -60,12 +85,13 @@ extern "C" int nfmc_jump_sample_host(const nfmc_potential* pot_h, const float* p
   double* mom_dev = reinterpret_cast<double*>(w); w += align256((size_t)2 * d * sizeof(double));
   unsigned long long* cnt_dev = reinterpret_cast<unsigned long long*>(w);
 
-  if (int e = check_cuda(cudaMemcpyAsync(x_dev, x_host, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, s), "H2D x")) return e;
   if (int e = check_cuda(cudaMemcpyAsync(blob_dev, blob_host, (size_t)flow_h->blob_floats * sizeof(float), cudaMemcpyHostToDevice, s), "H2D blob")) return e;
   if (pot_params_host && pot_params_floats > 0)
     if (int e = check_cuda(cudaMemcpyAsync(pp_dev, pot_params_host, (size_t)pot_params_floats * sizeof(float), cudaMemcpyHostToDevice, s), "H2D pot")) return e;
   cudaMemsetAsync(mom_dev, 0, (size_t)2 * d * sizeof(double), s);
   cudaMemsetAsync(cnt_dev, 0, 8 * sizeof(unsigned long long), s);
+  cudaEventRecord(g_pipe.fork, s);
+  for (int i = 0; i < 3; ++i) cudaStreamWaitEvent(g_pipe.streams[i], g_pipe.fork, 0);
 
   nfmc_potential pot = *pot_h;
   pot.params = (pot_params_host && pot_params_floats > 0) ? pp_dev : nullptr;
@@ -73,16 +99,31 @@ extern "C" int nfmc_jump_sample_host(const nfmc_potential* pot_h, const float* p
   flow.blob = blob_dev;
   nfmc_stats st_local{mom_dev, mom_dev + d, cnt_dev};
   nfmc_stats st_jump{mom_dev, mom_dev + d, cnt_dev + 4};
-  for (int it = 0; it < n_outer; ++it) {
-    nfmc_rng r_local{seed, (uint64_t)it * (uint64_t)n_inner, nullptr, nullptr};
-    nfmc_rng r_jump{seed, (uint64_t)it, nullptr, nullptr};
-    int e = inner_kind == 0
-                ? nfmc_mala_steps(&pot, x_dev, n, n_inner, step_size, nullptr, 1, &r_local, chain0, &st_local, nullptr, stream)
-                : nfmc_hmc_steps(&pot, x_dev, n, n_inner, step_size, n_leapfrog, nullptr, 1, &r_local, chain0, &st_local, nullptr, stream);
-    if (e) return e;
-    if ((e = nfmc_jump_step(&pot, &flow, x_dev, n, 1, &r_jump, chain0, &st_jump, nullptr, stream))) return e;
+  // slabs: a multiple of 1024 chains, at least 32768 each, at most 16 of them
+  int64_t slab = (n + 15) / 16;
+  if (slab < 32768) slab = 32768;
+  slab = (slab + 1023) / 1024 * 1024;
+  int si = 0;
+  for (int64_t first = 0; first < n; first += slab, ++si) {
+    const int64_t cnt = (n - first) < slab ? (n - first) : slab;
+    cudaStream_t ss = g_pipe.streams[si % 3];
+    float* xs = x_dev + first * d;
+    if (int e = check_cuda(cudaMemcpyAsync(xs, x_host + first * d, (size_t)cnt * d * sizeof(float), cudaMemcpyHostToDevice, ss), "H2D x")) return e;
+    for (int it = 0; it < n_outer; ++it) {
+      nfmc_rng r_local{seed, (uint64_t)it * (uint64_t)n_inner, nullptr, nullptr};
+      nfmc_rng r_jump{seed, (uint64_t)it, nullptr, nullptr};
+      int e = inner_kind == 0
+                  ? nfmc_mala_steps(&pot, xs, cnt, n_inner, step_size, nullptr, 1, &r_local, chain0 + first, &st_local, nullptr, ss)
+                  : nfmc_hmc_steps(&pot, xs, cnt, n_inner, step_size, n_leapfrog, nullptr, 1, &r_local, chain0 + first, &st_local, nullptr, ss);
+      if (e) return e;
+      if ((e = nfmc_jump_step(&pot, &flow, xs, cnt, 1, &r_jump, chain0 + first, &st_jump, nullptr, ss))) return e;
+    }
+    if (int e = check_cuda(cudaMemcpyAsync(x_host + first * d, xs, (size_t)cnt * d * sizeof(float), cudaMemcpyDeviceToHost, ss), "D2H x")) return e;
   }
-  if (int e = check_cuda(cudaMemcpyAsync(x_host, x_dev, (size_t)n * d * sizeof(float), cudaMemcpyDeviceToHost, s), "D2H x")) return e;
+  for (int i = 0; i < 3; ++i) {
+    cudaEventRecord(g_pipe.join[i], g_pipe.streams[i]);
+    cudaStreamWaitEvent(s, g_pipe.join[i], 0);
+  }
   if (sum_x_host) cudaMemcpyAsync(sum_x_host, mom_dev, (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, s);
   if (sum_x2_host) cudaMemcpyAsync(sum_x2_host, mom_dev + d, (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, s);
   if (counts_host) cudaMemcpyAsync(counts_host, cnt_dev, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
