@@ -49,6 +49,15 @@ __device__ __forceinline__ float across_groups_sum(float v, int gs) {
   return v;
 }
 
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2): one issue slot for two IEEE fp32 operations.  The
+//      results are bit-identical to the scalar fmaf / * / +; the point is issue bandwidth: these kernels are bound by
+//      instruction issue (Philox integer work competes with the float work for the same slots).
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+
 // ---- Philox4x32-10 (Salmon et al. 2011; same round function / constants as cuRAND and torch) -------------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
@@ -137,6 +146,16 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, fl
   __sincosf(th, &s, &c);
   z0 = r * c;
   z1 = r * s;
+}
+
+// packed variant: returns (z0, z1) with the final scaling as one FMUL2
+__device__ __forceinline__ float2 box_muller2(uint32_t a, uint32_t b) {
+  const float u1 = fmaf(__uint2float_rn(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  const float th = (__uint_as_float(0x3f800000u | (b >> 9)) - 1.5f) * 6.283185307179586f;
+  const float r = fast_sqrt(-1.3862943611198906f * fast_lg2(u1));
+  float s, c;
+  __sincosf(th, &s, &c);
+  return mul2(splat2(r), make_float2(c, s));
 }
 
 // Fill the per-step normals for this lane (E slots per half) and return the accept uniform bits

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <cstdlib>
 #include "../../include/nfmc_b200.h"
 #include "potentials.cuh"
 
@@ -22,7 +23,8 @@ inline bool layout_for_dim(int d, Layout& L) {
   if (d < 1 || d > NFMC_MAX_DIM) return false;
   const int db = d - d / 2;
   int gs = 1;
-  while ((db + gs - 1) / gs > 16) gs <<= 1;
+  static const int max_slots = [] { const char* e = getenv("NFMC_LAYOUT_MAX_SLOTS"); int v = e ? atoi(e) : 16; return (v >= 4 && v <= 16) ? v : 16; }();
+  while ((db + gs - 1) / gs > max_slots) gs <<= 1;
   if (gs > 32) return false;
   const int e = (db + gs - 1) / gs;
   L.gs = gs;
