@@ -109,8 +109,8 @@ extern "C" int nfmc_neutra_hmc_steps(const nfmc_potential* pot, const nfmc_realn
   A.c.stats = StatsArgs{stats ? stats->sum_x : nullptr, stats ? stats->sum_x2 : nullptr, stats ? stats->counts : nullptr};
   A.c.sink = SinkArgs{sink ? sink->samples : nullptr, sink ? sink->seen0 : 0, (sink && sink->thinning > 0) ? sink->thinning : 1};
   A.tau = step_size; A.imd = inv_mass_diag; A.n_leapfrog = n_leapfrog;
-  const size_t smem = plan_flow_smem(A.f, flow, L, true);
-  const int grid = grid_for(n, L.gs, 2);
+  const size_t smem = plan_flow_smem(A.f, flow, L, true, true) + (size_t)pot->d * sizeof(float);   // + inverse-mass table
+  const int grid = grid_for(n, L.gs, 3);
   cudaStream_t s = (cudaStream_t)stream;
   A.pot_kind = pot->kind;
   NFMC_DISPATCH_E(L.E, { return launch_neutra_hmc<E>(A, grid, smem, s); });

@@ -41,14 +41,22 @@ __device__ __forceinline__ float neutra_value_grad(const FlowDesc& F, int pot_ki
 
 
 
+// Register budget: the live per-lane state is the latent z, the momentum p and the gradient g (2E each) plus the flow's
+// working copy; the start state of a step is NOT kept (on rejection it is re-read from global memory, which always holds
+// the current state), the running moments live in shared memory, and a non-identity mass is read from shared memory.
 template <int E, bool SB, bool X>
-__global__ void __launch_bounds__(kThreads) neutra_hmc_kernel(const NeutraArgs A) {
+__global__ void __launch_bounds__(kThreads, 3) neutra_hmc_kernel(const NeutraArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ChainArgs& C = A.c;
   const Geom g = make_geom(C.d, C.gs);
   FlowSmem S = flow_smem_init<SB>(smem, A.f, true);
   const bool flip = (A.f.Lc & 1) != 0;
   const bool unit_mass = (A.imd == nullptr);
+  float* smass = reinterpret_cast<float*>(S.mom - threadIdx.x + (size_t)E * kThreads);   // [d] inverse mass, PHYSICAL order
+  if (!unit_mass) {
+    for (int i = threadIdx.x; i < C.d; i += blockDim.x) smass[i] = __ldg(A.imd + (flip ? C.d - 1 - i : i));
+    __syncthreads();
+  }
   const int cpc = kThreads / C.gs;
   const long long tiles = (C.n + cpc - 1) / cpc;
   const float half_tau = A.tau / 2;
@@ -60,25 +68,15 @@ __global__ void __launch_bounds__(kThreads) neutra_hmc_kernel(const NeutraArgs A
     const long long chain = active ? chain_raw : C.n - 1;
     float* row = C.x + chain * (long long)C.d;
 
-    float lo[E], hi[E], m1lo[E], m1hi[E], m2lo[E], m2hi[E];
-    if (flip) load_chain_flipped(row, g, lo, hi); else load_chain(row, g, lo, hi);
+    float zlo[E], zhi[E];
+    if (flip) load_chain_flipped(row, g, zlo, zhi); else load_chain(row, g, zlo, zhi);
 #pragma unroll
-    for (int e = 0; e < E; ++e) m1lo[e] = m1hi[e] = m2lo[e] = m2hi[e] = 0.f;
-    // per-slot inverse mass (physical order)
-    float mlo[E], mhi[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-      const int kk = g.j + g.gs * e;
-      mlo[e] = mhi[e] = 1.f;
-      if (!unit_mass) {
-        if (kk < g.da) mlo[e] = __ldg(A.imd + (flip ? g.d - 1 - kk : kk));
-        if (kk < g.db) mhi[e] = __ldg(A.imd + (flip ? g.d - 1 - (g.da + kk) : g.da + kk));
-      }
-    }
+    for (int e = 0; e < E; ++e) S.mom[e * kThreads] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     for (int k = 0; k < C.n_steps; ++k) {
       float plo[E], phi[E];
       uint32_t ubits = 0;
+      float kin0 = 0.f;
       {
         StepNoise<E> nz;
         if (C.rng.normals) {
@@ -93,21 +91,19 @@ __global__ void __launch_bounds__(kThreads) neutra_hmc_kernel(const NeutraArgs A
 #pragma unroll
         for (int e = 0; e < E; ++e) {
           const int kk = g.j + g.gs * e;
-          plo[e] = (kk < g.da) ? nz.lo[e] : 0.f;
-          phi[e] = (kk < g.db) ? nz.hi[e] : 0.f;
+          const bool vl = slot_ok<X, E>(e, kk, g.da), vh = slot_ok<X, E>(e, kk, g.db);
+          float pl = vl ? nz.lo[e] : 0.f, ph = vh ? nz.hi[e] : 0.f;
+          float ml = 1.f, mh = 1.f;
           if (!unit_mass) {                                                         // hmc.py:100
-            plo[e] *= __fdiv_rn(1.f, sqrtf(mlo[e]));
-            phi[e] *= __fdiv_rn(1.f, sqrtf(mhi[e]));
+            ml = smass[vl ? kk : 0]; mh = smass[g.da + (vh ? kk : 0)];
+            pl *= __fdiv_rn(1.f, sqrtf(ml));
+            ph *= __fdiv_rn(1.f, sqrtf(mh));
           }
+          plo[e] = pl; phi[e] = ph;
+          kin0 = fmaf(pl * pl, ml, fmaf(ph * ph, mh, kin0));
         }
       }
-      float zlo[E], zhi[E], glo[E], ghi[E];
-      float kin0 = 0.f;
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        zlo[e] = lo[e]; zhi[e] = hi[e];
-        kin0 = fmaf(plo[e] * plo[e], mlo[e], fmaf(phi[e] * phi[e], mhi[e], kin0));
-      }
+      float glo[E], ghi[E];
       // leapfrog with a single gradient call site: iteration 0 only evaluates at the start point
       float u0 = 0.f, u1 = 0.f;
       for (int l = 0; l <= A.n_leapfrog; ++l) {
@@ -115,10 +111,13 @@ __global__ void __launch_bounds__(kThreads) neutra_hmc_kernel(const NeutraArgs A
 #pragma unroll
           for (int e = 0; e < E; ++e) {
             const int kk = g.j + g.gs * e;
+            const bool vl = slot_ok<X, E>(e, kk, g.da), vh = slot_ok<X, E>(e, kk, g.db);
+            float ml = 1.f, mh = 1.f;
+            if (!unit_mass) { ml = smass[vl ? kk : 0]; mh = smass[g.da + (vh ? kk : 0)]; }
             plo[e] = fmaf(-half_tau, glo[e], plo[e]);                               // hmc.py:51-53
             phi[e] = fmaf(-half_tau, ghi[e], phi[e]);
-            zlo[e] = (kk < g.da) ? fmaf(A.tau, plo[e] * mlo[e], zlo[e]) : 0.f;      // hmc.py:56-58
-            zhi[e] = (kk < g.db) ? fmaf(A.tau, phi[e] * mhi[e], zhi[e]) : 0.f;
+            zlo[e] = vl ? fmaf(A.tau, unit_mass ? plo[e] : plo[e] * ml, zlo[e]) : 0.f;   // hmc.py:56-58
+            zhi[e] = vh ? fmaf(A.tau, unit_mass ? phi[e] : phi[e] * mh, zhi[e]) : 0.f;
           }
         }
         u1 = neutra_value_grad<E, SB, X>(S.F, A.pot_kind, C.pot, g, zlo, zhi, glo, ghi, S.scr, true);
@@ -133,7 +132,14 @@ __global__ void __launch_bounds__(kThreads) neutra_hmc_kernel(const NeutraArgs A
       }
       float kin1 = 0.f;
 #pragma unroll
-      for (int e = 0; e < E; ++e) kin1 = fmaf(plo[e] * plo[e], mlo[e], fmaf(phi[e] * phi[e], mhi[e], kin1));
+      for (int e = 0; e < E; ++e) {
+        float ml = 1.f, mh = 1.f;
+        if (!unit_mass) {
+          const int kk = g.j + g.gs * e;
+          ml = smass[slot_ok<X, E>(e, kk, g.da) ? kk : 0]; mh = smass[g.da + (slot_ok<X, E>(e, kk, g.db) ? kk : 0)];
+        }
+        kin1 = fmaf(plo[e] * plo[e], ml, fmaf(phi[e] * phi[e], mh, kin1));
+      }
       const float h0 = u0 + 0.5f * group_sum(kin0, g.gs);                           // hmc.py:103-106
       const float h1 = u1 + 0.5f * group_sum(kin1, g.gs);                           // hmc.py:107-110
       const float log_acc = -h1 - (-h0);
@@ -142,28 +148,41 @@ __global__ void __launch_bounds__(kThreads) neutra_hmc_kernel(const NeutraArgs A
       else u = uniform_from_bits(__shfl_sync(0xffffffffu, ubits, g.grp_base));
       const bool accept = logf(u) < log_acc;                                        // hmc.py:112-113
       if (!(fabsf(log_acc) <= 3.0e38f) && g.j == 0 && active) ++n_bad;
+      // global memory always holds the current state: write the new one if accepted, re-read the old one if rejected
+      if (accept) {
+        if (active) { if (flip) store_chain_flipped(row, g, zlo, zhi); else store_chain(row, g, zlo, zhi); }
+        if (g.j == 0 && active) ++n_acc;
+      } else {
+        if (flip) load_chain_flipped(row, g, zlo, zhi); else load_chain(row, g, zlo, zhi);
+      }
 #pragma unroll
       for (int e = 0; e < E; ++e) {
-        lo[e] = accept ? zlo[e] : lo[e];
-        hi[e] = accept ? zhi[e] : hi[e];
+        float4 m = S.mom[e * kThreads];
+        m.x += zlo[e]; m.y += zhi[e]; m.z = fmaf(zlo[e], zlo[e], m.z); m.w = fmaf(zhi[e], zhi[e], m.w);
+        S.mom[e * kThreads] = m;
       }
-      if (accept && g.j == 0 && active) ++n_acc;
-      accumulate_moments(lo, hi, m1lo, m1hi, m2lo, m2hi);
       if (C.sink.samples && active) {
         const long long idx = C.sink.seen0 + k;
         if (idx % C.sink.thinning == 0) {
           const long long first = (C.sink.seen0 + C.sink.thinning - 1) / C.sink.thinning;
           float* dst = C.sink.samples + ((idx / C.sink.thinning - first) * C.n + chain) * (long long)C.d;
-          if (flip) store_chain_flipped(dst, g, lo, hi); else store_chain(dst, g, lo, hi);
+          if (flip) store_chain_flipped(dst, g, zlo, zhi); else store_chain(dst, g, zlo, zhi);
         }
       }
     }
-    if (!active) {
 #pragma unroll
-      for (int e = 0; e < E; ++e) m1lo[e] = m1hi[e] = m2lo[e] = m2hi[e] = 0.f;
+    for (int e = 0; e < E; ++e) {
+      float4 m = S.mom[e * kThreads];
+      if (!active) m = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int kk = g.j + g.gs * e;
+      const float a = across_groups_sum(m.x, g.gs), b = across_groups_sum(m.y, g.gs);
+      const float c = across_groups_sum(m.z, g.gs), dd = across_groups_sum(m.w, g.gs);
+      if (g.lane < g.gs) {
+        const int il = flip ? g.d - 1 - kk : kk, ih = flip ? g.d - 1 - (g.da + kk) : g.da + kk;
+        if (kk < g.da) { atomicAdd(S.st.sx + il, (double)a); atomicAdd(S.st.sx2 + il, (double)c); }
+        if (kk < g.db) { atomicAdd(S.st.sx + ih, (double)b); atomicAdd(S.st.sx2 + ih, (double)dd); }
+      }
     }
-    flush_moments(g, m1lo, m1hi, m2lo, m2hi, S.st.sx, S.st.sx2, flip);
-    if (active) { if (flip) store_chain_flipped(row, g, lo, hi); else store_chain(row, g, lo, hi); }
   }
   n_acc = __reduce_add_sync(0xffffffffu, n_acc);
   n_bad = __reduce_add_sync(0xffffffffu, n_bad);
