@@ -113,8 +113,8 @@ class RealNVP(_Layer):
         self.n_coupling = int(n_layers)
         self._packed = {}  # device -> (version key, blob tensor)
         self._packed_tc = {}
-        if conditioner_dtype == "bf16" and not tc_eligible(self.n_dim, *self.conditioner_shape()):
-            raise ValueError("conditioner_dtype='bf16' needs 2 linear layers, hidden % 16 == 0 in [16, 256], even d <= 128")
+        if conditioner_dtype == "bf16" and not tc_supported(self.n_dim, *self.conditioner_shape()):
+            raise ValueError("conditioner_dtype='bf16' needs 2 linear layers, hidden <= 256, even d <= 128")
 
     # -- structure --------------------------------------------------------------------------------------------
     def couplings(self):
@@ -138,7 +138,10 @@ class RealNVP(_Layer):
         return self._packed[key][1]
 
     def uses_tensor_cores(self) -> bool:
-        return self.conditioner_dtype != "fp32" and tc_eligible(self.n_dim, *self.conditioner_shape())
+        shape = (self.n_dim, *self.conditioner_shape())
+        if self.conditioner_dtype == "bf16":
+            return tc_supported(*shape)
+        return self.conditioner_dtype == "auto" and tc_eligible(*shape)
 
     def tc_descriptor(self, device: torch.device):
         key = str(device)
@@ -148,7 +151,7 @@ class RealNVP(_Layer):
             self._packed_tc[key] = (ver, pack_realnvp_tc(self).to(device))
         blob = self._packed_tc[key][1]
         M, H = self.conditioner_shape()
-        return N.RealNVPTcDesc(self.n_dim, self.n_coupling, H, 0, blob.data_ptr(), blob.numel()), blob
+        return N.RealNVPTcDesc(self.n_dim, self.n_coupling, _tc_hidden(H), 0, blob.data_ptr(), blob.numel()), blob
 
     def descriptor(self, device: torch.device):
         blob = self.blob(device)
@@ -374,9 +377,19 @@ def _pack_coupling_fp32(lin, da, db, M, H, small, odd):
     return parts
 
 
+def tc_supported(d: int, M: int, H: int) -> bool:
+    """Shapes the tcgen05 conditioner kernel (csrc/cond_tc.cu) can run: the hidden width is zero-padded to a multiple
+    of 16 at pack time, so any H <= 256 works."""
+    return M == 2 and d % 2 == 0 and 2 <= d <= 128 and 1 <= H <= 256
+
+
 def tc_eligible(d: int, M: int, H: int) -> bool:
-    """Shapes the tcgen05 conditioner kernel (csrc/cond_tc.cu) handles."""
-    return M == 2 and d % 2 == 0 and 2 <= d <= 128 and 16 <= H <= 256 and H % 16 == 0
+    """Shapes for which ``conditioner_dtype='auto'`` picks the tensor-core path (wide conditioners)."""
+    return tc_supported(d, M, H) and H >= 16
+
+
+def _tc_hidden(H: int) -> int:
+    return ((H + 15) // 16) * 16
 
 
 @torch.no_grad()
@@ -389,8 +402,9 @@ def pack_realnvp_tc(bij: "RealNVP") -> torch.Tensor:
     da, db = d // 2, d - d // 2
     Lc = bij.n_coupling
     M, H = bij.conditioner_shape()
-    if not tc_eligible(d, M, H):
+    if not tc_supported(d, M, H):
         raise ValueError("shape not supported by the tensor-core path")
+    Hp = _tc_hidden(H)
     n2p = ((2 * db + 15) // 16) * 16
     base = pack_realnvp_affines(bij)
     chunks = [base.contiguous().view(torch.uint8)]
@@ -400,19 +414,21 @@ def pack_realnvp_tc(bij: "RealNVP") -> torch.Tensor:
         odd = (l + 1) % 2 == 1
         (w1, b1), (wl, bl) = [(m.weight.detach().to("cpu", torch.float32), m.bias.detach().to("cpu", torch.float32))
                               for m in cpl.linears()]
-        w1p = torch.zeros(H, 64)
-        w1p[:, :da] = w1.flip(1) if odd else w1                       # [h][ks]
-        img1 = w1p.reshape(H, 8, 8).permute(1, 0, 2).contiguous()     # [kg][h][8]
+        w1p = torch.zeros(Hp, 64)
+        w1p[:H, :da] = w1.flip(1) if odd else w1                      # [h][ks], zero rows for the padded hidden units
+        img1 = w1p.reshape(Hp, 8, 8).permute(1, 0, 2).contiguous()    # [kg][h][8]
+        b1p = torch.zeros(Hp)
+        b1p[:H] = b1
         wl3 = wl.reshape(db, 2, H)                                    # [t_log][c][h]
         bl2 = bl.reshape(db, 2)
         if odd:
             wl3, bl2 = wl3.flip(0), bl2.flip(0)
-        wlp = torch.zeros(n2p, H)
-        wlp[: 2 * db] = wl3.reshape(2 * db, H)                        # row n = 2 t + c
-        img2 = wlp.reshape(n2p, H // 8, 8).permute(1, 0, 2).contiguous()   # [kg][n][8]
+        wlp = torch.zeros(n2p, Hp)
+        wlp[: 2 * db, :H] = wl3.reshape(2 * db, H)                    # row n = 2 t + c
+        img2 = wlp.reshape(n2p, Hp // 8, 8).permute(1, 0, 2).contiguous()  # [kg][n][8]
         blp = torch.zeros(n2p)
         blp[: 2 * db] = bl2.reshape(-1)
-        chunks += [img1.to(torch.bfloat16).view(torch.uint8).reshape(-1), b1.contiguous().view(torch.uint8).reshape(-1),
+        chunks += [img1.to(torch.bfloat16).view(torch.uint8).reshape(-1), b1p.contiguous().view(torch.uint8).reshape(-1),
                    img2.to(torch.bfloat16).view(torch.uint8).reshape(-1), blp.contiguous().view(torch.uint8).reshape(-1)]
     return torch.cat([c.reshape(-1) for c in chunks]).contiguous()
 

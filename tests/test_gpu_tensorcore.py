@@ -14,7 +14,7 @@ def _err(a, b):
 
 
 @pytest.mark.timeout(180)
-@pytest.mark.parametrize("d,n_layers,H,n", [(100, 2, 64, 300), (100, 4, 256, 1000), (64, 3, 16, 129), (128, 2, 128, 77),
+@pytest.mark.parametrize("d,n_layers,H,n", [(100, 2, 5, 700), (26, 3, 40, 100), (100, 2, 64, 300), (100, 4, 256, 1000), (64, 3, 16, 129), (128, 2, 128, 77),
                                            (16, 1, 32, 5), (100, 2, 256, 20000)])
 def test_tc_forward_inverse_logprob(d, n_layers, H, n):
     from gpu_util import product_flow_from_oracle
@@ -45,7 +45,7 @@ def test_tc_forward_inverse_logprob(d, n_layers, H, n):
 def test_tc_rejects_unsupported_shapes():
     from nfmc_b200.flow import Flow, RealNVP
     with pytest.raises(ValueError):
-        RealNVP((100,), conditioner_kwargs=dict(n_layers=2, n_hidden=20), conditioner_dtype="bf16")
+        RealNVP((100,), conditioner_kwargs=dict(n_layers=3, n_hidden=32), conditioner_dtype="bf16")
     with pytest.raises(ValueError):
         RealNVP((101,), conditioner_kwargs=dict(n_layers=2, n_hidden=64), conditioner_dtype="bf16")
     assert not RealNVP((100,)).uses_tensor_cores()           # default H = 5: CUDA-core path
