@@ -42,7 +42,7 @@ def parse():
     p.add_argument("--chains-per-gpu", type=int, default=1 << 20)
     p.add_argument("--inner", type=int, default=None, help="local steps per jump (default 100 for jump_mala, 5 for jump_hmc)")
     p.add_argument("--leapfrog", type=int, default=20)
-    p.add_argument("--cpu-chains", type=int, default=8192, help="chains of the bounded CPU-baseline sample")
+    p.add_argument("--cpu-chains", type=int, default=32768, help="chains of the bounded CPU-baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     return p.parse_args()

@@ -125,5 +125,6 @@ def sample(target, event_shape: Optional[Tuple[int, ...]] = None, flow: Optional
             flat = w.samples.flatten(0, 1)
             x0 = flat[torch.randperm(len(flat))][:n_chains]
         else:
-            x0 = w.running_samples.last_sample
+            rs = w.running_samples                      # stay on the device when the warm-up left its state there
+            x0 = rs.last_sample_device if rs.last_sample_device is not None else rs.last_sample
     return sampler.sample(x0=x0, show_progress=show_progress, time_limit_seconds=sampling_time_limit_seconds)

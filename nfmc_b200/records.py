@@ -371,16 +371,38 @@ class JumpNFMCStatistics(MCMCStatistics):
 # ---------------------------------------------------------------------------------------------------------------
 # samples and output
 # ---------------------------------------------------------------------------------------------------------------
-@dataclass
 class MCMCSamples:
-    event_shape: Union[Tuple[int, ...], torch.Size]
-    store_samples: bool = True
-    n_samples: int = 0
-    last_sample: torch.Tensor = None
-    thinning: int = 1
-    seen_samples: int = 0
-    max_samples: int = None
-    _blocks: List[torch.Tensor] = field(default_factory=list)   # each [k, n, *event], host
+    """Sample store (reference: sampling/base.py:215-271).  Same attributes; ``last_sample`` is materialised on the host
+    lazily -- the sampler leaves the final state on the GPU (``last_sample_device``) and the 4*n*d-byte copy happens only
+    when ``last_sample`` is read (a warm-up -> sampling hand-off never needs it)."""
+
+    def __init__(self, event_shape, store_samples: bool = True, n_samples: int = 0, last_sample: torch.Tensor = None,
+                 thinning: int = 1, seen_samples: int = 0, max_samples: int = None):
+        self.event_shape = tuple(event_shape)
+        self.store_samples = store_samples
+        self.n_samples = n_samples
+        self.thinning = thinning
+        self.seen_samples = seen_samples
+        self.max_samples = max_samples
+        self._blocks: List[torch.Tensor] = []   # each [k, n, *event], host
+        self._last = last_sample
+        self.last_sample_device: Optional[torch.Tensor] = None
+
+    @property
+    def last_sample(self):
+        if self._last is None and self.last_sample_device is not None:
+            self._last = self.last_sample_device.detach().cpu()
+        return self._last
+
+    @last_sample.setter
+    def last_sample(self, value):
+        self._last = value
+        self.last_sample_device = None
+
+    def set_last_device(self, x_dev: torch.Tensor):
+        """Record the final state without copying it to the host."""
+        self._last = None
+        self.last_sample_device = x_dev
 
     def __getitem__(self, index):
         if index == -1 or index == self.n_samples - 1:
@@ -395,8 +417,11 @@ class MCMCSamples:
             x = x[None]
         elif not (x.ndim == k + 2 and tuple(x.shape[2:]) == tuple(self.event_shape)):
             raise ValueError(f"Expected x.shape[1:] or x.shape[2:] to be {self.event_shape}, got {x.shape = }")
-        if not already_thinned or len(x) > 0:
-            self.last_sample = x[-1].detach().clone() if len(x) else self.last_sample
+        if len(x):
+            if x.is_cuda:
+                self.set_last_device(x[-1].detach().clone())
+            else:
+                self.last_sample = x[-1].detach().clone()
         if not self.store_samples:
             return
         if already_thinned:

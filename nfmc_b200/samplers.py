@@ -210,7 +210,7 @@ class MetropolisSampler(Sampler):
         out.statistics.expectations.add_sums(sx, sx2, ses.n * steps_done)
         out.statistics.update_counters(n_accepted_trajectories=cnt[0], n_attempted_trajectories=cnt[1])
         out.statistics.n_nonfinite = cnt[2]
-        out.running_samples.last_sample = ses.x.reshape(ses.n, *out.event_shape).cpu()
+        out.running_samples.set_last_device(ses.x.reshape(ses.n, *out.event_shape))
 
     def warmup(self, x0, show_progress=True, time_limit_seconds=None) -> MCMCOutput:
         """Reference: MCMCSampler.warmup (mcmc/base.py:39-54): tune on a copy, adopt its kernel."""
@@ -384,7 +384,7 @@ class JumpNFMC(Sampler):
         out.statistics.update_counters(n_accepted_trajectories=cnt[0], n_attempted_trajectories=cnt[1],
                                        n_accepted_jumps=cnt[4], n_attempted_jumps=cnt[5])
         out.statistics.n_nonfinite = cnt[2] + cnt[6]
-        rs.last_sample = ses.x.reshape(ses.n, *event_shape).cpu()
+        rs.set_last_device(ses.x.reshape(ses.n, *event_shape))
         out.kernel = self.kernel
         return out
 
@@ -513,7 +513,7 @@ class AbstractIMH(Sampler):
             out.statistics.update_counters(n_target_gradient_calls=2 * ses.n * done)  # imh.py:146 (quirk Q3)
         else:
             out.statistics.update_counters(n_target_calls=2 * ses.n * done)           # imh.py:243-247
-        rs.last_sample = ses.x.reshape(ses.n, *event_shape).cpu()
+        rs.set_last_device(ses.x.reshape(ses.n, *event_shape))
         out.kernel = self.kernel
         return out
 
@@ -643,7 +643,7 @@ class NeuTraHMC(Sampler):
         out.statistics.update_counters(n_accepted_trajectories=cnt[0], n_attempted_trajectories=cnt[1],
                                        n_target_calls=(2 * L + 2) * ses.n * done,
                                        n_target_gradient_calls=2 * L * ses.n * done)   # hmc.py:122-125
-        rs.last_sample = ses.x.reshape(ses.n, *event_shape).cpu()
+        rs.set_last_device(ses.x.reshape(ses.n, *event_shape))
         out.kernel = self.inner_kernel
         out.kernel.flow = self.kernel.flow                                              # neutra.py:128
         return out
