@@ -137,6 +137,12 @@ NFMC_API int nfmc_mala_steps(const nfmc_potential* pot, float* x, int64_t n, int
                     const float* inv_mass_diag, int32_t adjusted, const nfmc_rng* rng, int64_t chain0,
                     const nfmc_stats* stats, const nfmc_sink* sink, void* stream);
 
+/* K random-walk Metropolis steps -- MH.propose (mcmc/mh.py:44-73): x' = x + inv_mass_diag * xi (NULL = ones),
+ * accept iff log u < U(x) - U(x'); adjusted=0 -> RandomWalk (always accept) */
+NFMC_API int nfmc_mh_steps(const nfmc_potential* pot, float* x, int64_t n, int32_t n_steps, const float* inv_mass_diag,
+                  int32_t adjusted, const nfmc_rng* rng, int64_t chain0, const nfmc_stats* stats, const nfmc_sink* sink,
+                  void* stream);
+
 /* K HMC steps -- HMC.propose (mcmc/hmc.py:96-126; trajectory :61-77) inside the same local loop */
 NFMC_API int nfmc_hmc_steps(const nfmc_potential* pot, float* x, int64_t n, int32_t n_steps, float step_size,
                    int32_t n_leapfrog, const float* inv_mass_diag, int32_t adjusted, const nfmc_rng* rng,

@@ -2,7 +2,7 @@
 
 Strategies on the accelerated hot path: ``jump_mala``, ``jump_ula``, ``jump_hmc``, ``jump_uhmc``, ``neutra_hmc``,
 ``imh`` / ``fixed_imh``, ``adaptive_imh`` and the local kernels they are built from (``mala``, ``ula``, ``hmc``,
-``uhmc``).  Everything else the reference lists (``mh``, ``ess``, ``tess``, ``dlmc``, ``nuts`` ...) is outside the
+``uhmc``, ``mh`` / ``jump_mh``).  Everything else the reference lists (``ess``, ``tess``, ``dlmc``, ``nuts``, ``neutra_mh`` ...) is outside the
 scope table and raises ``NotImplementedError`` -- there is no eager fallback.
 """
 from __future__ import annotations
@@ -15,13 +15,13 @@ import torch
 from . import _native as N
 from .flow import Flow, create_flow_object
 from .potentials import Potential, resolve_target
-from .records import (HMCKernel, HMCParameters, IMHKernel, IMHParameters, JumpNFMCParameters, LangevinKernel,
+from .records import (MHKernel, MHParameters, HMCKernel, HMCParameters, IMHKernel, IMHParameters, JumpNFMCParameters, LangevinKernel,
                       LangevinParameters, MCMCOutput, NeuTraKernel, NeuTraParameters, NFMCKernel)
-from .samplers import (HMC, MALA, UHMC, ULA, AdaptiveIMH, FixedIMH, JumpHMC, JumpMALA, JumpUHMC, JumpULA, NeuTraHMC,
+from .samplers import (MH, JumpMH, HMC, MALA, UHMC, ULA, AdaptiveIMH, FixedIMH, JumpHMC, JumpMALA, JumpUHMC, JumpULA, NeuTraHMC,
                        Sampler)
 
-LOCAL_STRATEGIES = ('hmc', 'uhmc', 'ula', 'mala')
-NF_STRATEGIES = ('imh', 'fixed_imh', 'adaptive_imh', 'jump_mala', 'jump_ula', 'jump_hmc', 'jump_uhmc', 'neutra_hmc')
+LOCAL_STRATEGIES = ('hmc', 'uhmc', 'ula', 'mala', 'mh')
+NF_STRATEGIES = ('imh', 'fixed_imh', 'adaptive_imh', 'jump_mala', 'jump_ula', 'jump_hmc', 'jump_uhmc', 'jump_mh', 'neutra_hmc')
 
 
 def get_supported_samplers():
@@ -61,6 +61,8 @@ def create_sampler(target, event_shape: Optional[Tuple[int, ...]] = None, flow: 
             cls = HMC if strategy == 'hmc' else UHMC
             return finish(cls(event_shape, target, HMCKernel(event_size=event_size, **kernel_kwargs),
                               HMCParameters(**param_kwargs)))
+        if strategy == 'mh':
+            return finish(MH(event_shape, target, MHKernel(event_size=event_size, **kernel_kwargs), MHParameters(**param_kwargs)))
         cls = MALA if strategy == 'mala' else ULA
         return finish(cls(event_shape, target, LangevinKernel(event_size=event_size, **kernel_kwargs),
                           LangevinParameters(**param_kwargs)))
@@ -87,6 +89,11 @@ def create_sampler(target, event_shape: Optional[Tuple[int, ...]] = None, flow: 
                           params=JumpNFMCParameters(**param_kwargs),
                           inner_kernel=LangevinKernel(event_size=event_size, **inner_kernel_kwargs),
                           inner_params=LangevinParameters(**inner_param_kwargs)))
+    if strategy == 'jump_mh':
+        return finish(JumpMH(event_shape, target, kernel=NFMCKernel(event_shape, flow=flow_object),
+                             params=JumpNFMCParameters(**param_kwargs),
+                             inner_kernel=MHKernel(event_size=event_size, **inner_kernel_kwargs),
+                             inner_params=MHParameters(**inner_param_kwargs)))
     if strategy in ('jump_hmc', 'jump_uhmc'):
         if strategy == 'jump_hmc' and 'n_iterations' not in inner_param_kwargs:
             inner_param_kwargs['n_iterations'] = 5                                   # reference: sample.py:161-162

@@ -15,6 +15,7 @@ struct LocalArgs {
   const float* imd;   // inverse mass diagonal [d] or nullptr (= ones)
   int adjusted;
   int n_leapfrog;
+  int random_walk;    // 1: random-walk MH proposal x' = x + imd * xi, ratio = U(x) - U(x') (mcmc/mh.py:44-73)
 };
 
 

@@ -88,7 +88,25 @@ extern "C" int nfmc_mala_steps(const nfmc_potential* pot, float* x, int64_t n, i
   LocalArgs A;
   fill_chain_args(A.c, pot, x, n, n_steps, rng, chain0, stats, sink, L);
   A.tau = step_size; A.sqrt_2tau = (float)sqrt(2.0 * (double)step_size); A.imd = inv_mass_diag;
-  A.adjusted = adjusted; A.n_leapfrog = 0;
+  A.adjusted = adjusted; A.n_leapfrog = 0; A.random_walk = 0;
+  const size_t smem = local_smem_bytes(pot->d, inv_mass_diag != nullptr, sizeof(float4), L.E);
+  const int grid = grid_for(n, L.gs, 4);
+  cudaStream_t s = (cudaStream_t)stream;
+  NFMC_DISPATCH_E(L.E, { return launch_mala<E>(pot->kind, L.exact, A, grid, smem, s); });
+  return 0;
+}
+
+extern "C" int nfmc_mh_steps(const nfmc_potential* pot, float* x, int64_t n, int32_t n_steps, const float* inv_mass_diag,
+                             int32_t adjusted, const nfmc_rng* rng, int64_t chain0, const nfmc_stats* stats,
+                             const nfmc_sink* sink, void* stream) {
+  if (int e = validate_pot(pot)) return e;
+  if (!x || n < 1 || n_steps < 0) return set_error("mh_steps: bad x/n/n_steps");
+  if (n_steps == 0) return 0;
+  Layout L;
+  if (!layout_for_dim(pot->d, L)) return set_error("mh_steps: unsupported event size");
+  LocalArgs A;
+  fill_chain_args(A.c, pot, x, n, n_steps, rng, chain0, stats, sink, L);
+  A.tau = 1.f; A.sqrt_2tau = 1.f; A.imd = inv_mass_diag; A.adjusted = adjusted; A.n_leapfrog = 0; A.random_walk = 1;
   const size_t smem = local_smem_bytes(pot->d, inv_mass_diag != nullptr, sizeof(float4), L.E);
   const int grid = grid_for(n, L.gs, 4);
   cudaStream_t s = (cudaStream_t)stream;
@@ -106,7 +124,7 @@ extern "C" int nfmc_hmc_steps(const nfmc_potential* pot, float* x, int64_t n, in
   if (!layout_for_dim(pot->d, L)) return set_error("hmc_steps: unsupported event size");
   LocalArgs A;
   fill_chain_args(A.c, pot, x, n, n_steps, rng, chain0, stats, sink, L);
-  A.tau = step_size; A.sqrt_2tau = 0.f; A.imd = inv_mass_diag; A.adjusted = adjusted; A.n_leapfrog = n_leapfrog;
+  A.tau = step_size; A.sqrt_2tau = 0.f; A.imd = inv_mass_diag; A.adjusted = adjusted; A.n_leapfrog = n_leapfrog; A.random_walk = 0;
   const size_t smem = local_smem_bytes(pot->d, inv_mass_diag != nullptr, sizeof(float4), L.E);
   const int grid = grid_for(n, L.gs, 4);
   cudaStream_t s = (cudaStream_t)stream;

@@ -38,8 +38,12 @@ __global__ void __launch_bounds__(kThreads, NFMC_MALA_MINB) mala_kernel(const Lo
   size_t off = (cta_stats_bytes(C.d) + 15) & ~size_t(15);
   float4* coef = reinterpret_cast<float4*>(smem + off);
   const bool unit_mass = FAST ? true : (A.imd == nullptr);
+  const bool rw = !FAST && A.random_walk;
   if (!unit_mass) {
-    for (int i = threadIdx.x; i < C.d; i += blockDim.x) coef[i] = mala_coef(A.tau, A.sqrt_2tau, __ldg(A.imd + i));
+    for (int i = threadIdx.x; i < C.d; i += blockDim.x) {
+      const float mi = __ldg(A.imd + i);
+      coef[i] = rw ? make_float4(0.f, mi, 0.f, 0.f) : mala_coef(A.tau, A.sqrt_2tau, mi);
+    }
     off += (size_t)C.d * sizeof(float4);
     __syncthreads();
   }
@@ -105,6 +109,9 @@ __global__ void __launch_bounds__(kThreads, NFMC_MALA_MINB) mala_kernel(const Lo
             tv.y = vh ? tv.y : 0.f;
             const float2 qv = fma2(tv, tv, make_float2(qf, qfh));
             qf = qv.x; qfh = qv.y;
+          } else if (rw && unit_mass) {
+            pl = lo[e] + nlo;                                                  // mh.py:52-56 with imd = 1
+            ph = hi[e] + nhi;
           } else if (unit_mass) {
             pl = fmaf(A.sqrt_2tau, nlo, fmaf(-A.tau, glo, lo[e]));
             ph = fmaf(A.sqrt_2tau, nhi, fmaf(-A.tau, ghi, hi[e]));
@@ -165,7 +172,8 @@ __global__ void __launch_bounds__(kThreads, NFMC_MALA_MINB) mala_kernel(const Lo
         qf = group_sum(qf + qfh, g.gs) * inv4tau;
         qr = group_sum(qr + qrh, g.gs) * inv4tau;
         // util.py:392 with target = -U, proposal = -Q   (langevin.py:88-105)
-        const float log_ratio = (-ctxp.u) - (-ctx.u) + (-qr) - (-qf);
+        const float log_ratio = rw ? ((-ctxp.u) - (-ctx.u) + 0.f - 0.f)          // mh.py:59
+                                   : ((-ctxp.u) - (-ctx.u) + (-qr) - (-qf));
         float u;
         if (C.rng.uniforms) u = __ldg(C.rng.uniforms + (long long)k * C.n + chain);
         else u = uniform_from_bits(__shfl_sync(0xffffffffu, ubits, g.grp_base));
@@ -376,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, NFMC_MALA_MINB) mala_fast_kernel(con
 template <int E>
 int launch_mala(int pot_kind, bool exact, const LocalArgs& A, int grid, size_t smem, cudaStream_t s) {
   NFMC_DISPATCH_POT(pot_kind, {
-    if (exact && !A.c.rng.normals && !A.imd) {
+    if (exact && !A.c.rng.normals && !A.imd && !A.random_walk) {
       NFMC_SET_SMEM_RET((mala_fast_kernel<POT, E>), smem);
       mala_fast_kernel<POT, E><<<grid, kThreads, smem, s>>>(A);
     } else {

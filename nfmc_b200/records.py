@@ -132,6 +132,15 @@ class HMCKernel(MetropolisKernel):
 
 
 @dataclass
+class MHKernel(MetropolisKernel):
+    event_size: int = None
+
+    def __repr__(self):
+        return (f'log step: {math.log(self.step_size):.2f}, '
+                f'mass norm: {torch.max(torch.abs(self.inv_mass_diag)):.2f}')
+
+
+@dataclass
 class MCMCParameters:
     n_iterations: int = 100
     n_warmup_iterations: int = 100
@@ -164,6 +173,15 @@ class LangevinParameters(MetropolisParameters):
 @dataclass
 class HMCParameters(MetropolisParameters):
     pass
+
+
+@dataclass
+class MHParameters(MetropolisParameters):
+    imd_adjustment: float = 1e-5
+
+    def __post_init__(self):
+        self.tune_step_size = False          # reference: mcmc/mh.py:22-24
+        self.tune_inv_mass_diag = True
 
 
 @dataclass

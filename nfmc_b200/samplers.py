@@ -24,7 +24,7 @@ import torch
 from . import _native as N
 from .flow import Flow
 from .potentials import Potential, resolve_target
-from .records import (HMCKernel, HMCParameters, IMHKernel, IMHParameters, JumpNFMCOutput, JumpNFMCParameters,
+from .records import (MHKernel, MHParameters, HMCKernel, HMCParameters, IMHKernel, IMHParameters, JumpNFMCOutput, JumpNFMCParameters,
                       LangevinKernel, LangevinParameters, MCMCKernel, MCMCOutput, MCMCParameters, MetropolisKernel,
                       MetropolisParameters, NeuTraKernel, NeuTraParameters, NFMCKernel)
 
@@ -285,6 +285,36 @@ class HMC(MetropolisSampler):
                                        None if sink is None else C.byref(sink), ses.stream))
 
 
+class MH(MetropolisSampler):
+    """Random-walk Metropolis (reference: mcmc/mh.py:27-73): x' = x + inv_mass_diag * xi, accept iff log u < U(x) - U(x')."""
+
+    def __init__(self, event_shape, target, kernel: Optional[MHKernel] = None, params: Optional[MHParameters] = None):
+        es = int(math.prod(tuple(event_shape)))
+        super().__init__(event_shape, target, kernel or MHKernel(event_size=es), params or MHParameters())
+
+    @property
+    def name(self):
+        return 'MH'
+
+    def _calls_grads(self, n):
+        return ((2 * n) if self.params.adjustment else 0, 0)                        # mh.py:68-71
+
+    def _launch(self, ses, n_steps, sink, normals=None, uniforms=None):
+        pot, keep = self.target.descriptor(ses.device)
+        imd = _imd_device(self.kernel, ses.device)
+        rng = N.rng_desc(ses.seed, ses.local_step, normals, uniforms)
+        st = ses.stats()
+        N.check(N.lib().nfmc_mh_steps(C.byref(pot), N.ptr(ses.x), ses.n, n_steps, N.ptr(imd),
+                                      int(bool(self.params.adjustment)), C.byref(rng), ses.chain0, C.byref(st),
+                                      None if sink is None else C.byref(sink), ses.stream))
+
+
+class RandomWalk(MH):
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.params.adjustment = False
+
+
 class UHMC(HMC):
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
@@ -420,6 +450,11 @@ class JumpMALA(JumpNFMC):
 class JumpULA(JumpNFMC):
     def __init__(self, event_shape, target, kernel=None, params=None, inner_kernel=None, inner_params=None):
         super().__init__(event_shape, target, ULA(event_shape, target, inner_kernel, inner_params), kernel, params)
+
+
+class JumpMH(JumpNFMC):
+    def __init__(self, event_shape, target, kernel=None, params=None, inner_kernel=None, inner_params=None):
+        super().__init__(event_shape, target, MH(event_shape, target, inner_kernel, inner_params), kernel, params)
 
 
 class JumpHMC(JumpNFMC):

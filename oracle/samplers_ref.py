@@ -218,6 +218,32 @@ def hmc_propose(x, target, tau: float, imd: torch.Tensor, n_leapfrog: int, draws
     return x_prime.detach(), mask, calls, grads
 
 
+def mh_propose(x, target, imd: torch.Tensor, draws, adjusted: bool = True, trace=None):
+    """One random-walk Metropolis proposal (mcmc/mh.py:44-73)."""
+    n = x.shape[0]
+    noise = torch.multiply(draws.normal(n, (int(math.prod(x.shape[1:])),)), imd[None]).view_as(x)   # :52-55
+    x_prime = x + noise                                                        # :56
+    if adjusted:
+        with torch.no_grad():
+            log_ratio = mh_log_ratio(-target(x), -target(x_prime), 0, 0)       # :59
+        u = draws.uniform(n)
+        mask = torch.log(u) < log_ratio                                        # :60
+        calls = 2 * n
+        if trace is not None:
+            trace.setdefault("log_ratio", []).append(log_ratio.clone())
+    else:
+        mask = torch.ones(n, dtype=torch.bool)
+        calls = 0
+    if trace is not None:
+        trace.setdefault("x_prime", []).append(x_prime.clone())
+        trace.setdefault("mask", []).append(mask.clone())
+    return x_prime.detach(), mask, calls, 0
+
+
+def run_mh(x0, target, imd, n_steps, draws, adjusted=True, store=True, trace=False) -> "RunRef":
+    return run_local(x0, lambda x, tr: mh_propose(x, target, imd, draws, adjusted, tr), n_steps, store, trace)
+
+
 def run_local(x0, propose: Callable, n_steps: int, store: bool = True, trace: bool = False) -> RunRef:
     """``MCMCSampler.sample`` (mcmc/base.py:56-102) without tuning; ``propose(x, trace) -> (x', mask, calls, grads)``."""
     n = x0.shape[0]

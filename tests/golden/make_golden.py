@@ -30,6 +30,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle", "shim"), "/root/reference"):
 
 from nfmc.algorithms.sampling.mcmc.hmc import HMC, HMCKernel, HMCParameters          # noqa: E402
 from nfmc.algorithms.sampling.mcmc.langevin import MALA, LangevinKernel, LangevinParameters  # noqa: E402
+from nfmc.algorithms.sampling.mcmc.mh import MH, MHKernel, MHParameters                     # noqa: E402
 from nfmc.algorithms.sampling.nfmc.imh import FixedIMH, IMHKernel, IMHParameters      # noqa: E402
 from nfmc.algorithms.sampling.nfmc.jump import JumpMALA, JumpHMC, JumpNFMCParameters  # noqa: E402
 from nfmc.algorithms.sampling.nfmc.neutra import NeuTraHMC, NeuTraKernel, NeuTraParameters  # noqa: E402
@@ -199,6 +200,17 @@ def main():
         out = s.sample(x0.clone(), show_progress=False)
     cases["neutra_hmc_fn"] = pack(out, t, x0, dict(pot="fn", step=0.03, imd=np.ones(d, np.float32), T=T, L=L,
                                                     **flow_arrays(flow, 2, 2, 4)))
+
+    # ---- random-walk MH on the mixture, non-trivial proposal scale -------------------------------------------------
+    torch.manual_seed(19)
+    d, n, K = 7, 6, 5
+    target = make_potential_ref("gm", (d,))
+    imd = 0.2 + 0.3 * torch.rand(d)
+    x0 = torch.randn(n, d)
+    s = MH((d,), target, MHKernel(event_size=d, inv_mass_diag=imd.clone()), MHParameters(n_iterations=K))
+    with Tape() as t:
+        out = s.sample(x0.clone(), show_progress=False)
+    cases["mh_gm"] = pack(out, t, x0, dict(pot="gm", imd=imd.numpy(), K=K))
 
     for name, arrays in cases.items():
         path = os.path.join(HERE, f"{name}.npz")

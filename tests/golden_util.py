@@ -9,7 +9,7 @@ from oracle.realnvp_ref import FlowRef, RealNVPRef
 from oracle.samplers_ref import TapeDraws
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["mala_g0", "mala_fn", "hmc_g1", "hmc_rb", "jump_mala_g0", "jump_hmc_gm", "imh_rb", "neutra_hmc_fn"]
+CASES = ["mala_g0", "mala_fn", "hmc_g1", "hmc_rb", "jump_mala_g0", "jump_hmc_gm", "imh_rb", "neutra_hmc_fn", "mh_gm"]
 
 
 def load_case(name):

@@ -17,7 +17,7 @@ def _g(shape):
 
 
 # /root/reference/test/test_samplers.py:20-40 (test_mcmc), restricted to the local kernels on the hot path
-@pytest.mark.parametrize("name", ["HMC", "UHMC", "MALA", "ULA"])
+@pytest.mark.parametrize("name", ["HMC", "UHMC", "MALA", "ULA", "MH", "RandomWalk"])
 def test_mcmc(name):
     from nfmc_b200 import samplers
     torch.manual_seed(0)
@@ -29,7 +29,7 @@ def test_mcmc(name):
 
 
 # test_samplers.py:124-145 (test_jump_nfmc)
-@pytest.mark.parametrize("name", ["JumpMALA", "JumpHMC", "JumpUHMC", "JumpULA"])
+@pytest.mark.parametrize("name", ["JumpMALA", "JumpHMC", "JumpUHMC", "JumpULA", "JumpMH"])
 def test_jump_nfmc(name):
     from nfmc_b200 import samplers
     torch.manual_seed(0)
@@ -54,7 +54,7 @@ def test_other_nfmc(name):
 
 
 # test_samplers.py:175-201 (test_sample_wrapper_no_jump)
-@pytest.mark.parametrize("strategy", ["hmc", "uhmc", "ula", "mala", "imh", "neutra_hmc"])
+@pytest.mark.parametrize("strategy", ["hmc", "uhmc", "ula", "mala", "mh", "imh", "neutra_hmc"])
 def test_sample_wrapper_no_jump(strategy):
     torch.manual_seed(0)
     out = sample(_g((5,)), event_shape=(5,), strategy=strategy, n_chains=4, n_iterations=3, device=torch.device("cuda"),
@@ -64,7 +64,7 @@ def test_sample_wrapper_no_jump(strategy):
 
 
 # test_samplers.py:227-248 (test_sample_wrapper_jump)
-@pytest.mark.parametrize("strategy", ["jump_mala", "jump_ula", "jump_hmc", "jump_uhmc"])
+@pytest.mark.parametrize("strategy", ["jump_mala", "jump_ula", "jump_hmc", "jump_uhmc", "jump_mh"])
 def test_sample_wrapper_jump(strategy):
     torch.manual_seed(0)
     out = sample(_g((5,)), event_shape=(5,), strategy=strategy, n_chains=4, n_iterations=3,

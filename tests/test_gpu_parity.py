@@ -120,6 +120,10 @@ def _golden_local(name, kind):
     tgt = product_target(g["pot"], d)
     if kind == "mala":
         s = MALA((d,), tgt, LangevinKernel(event_size=d, inv_mass_diag=imd, step_size=float(g["step"])), LangevinParameters())
+    elif kind == "mh":
+        from nfmc_b200.records import MHKernel, MHParameters
+        from nfmc_b200.samplers import MH
+        s = MH((d,), tgt, MHKernel(event_size=d, inv_mass_diag=imd), MHParameters())
     else:
         s = HMC((d,), tgt, HMCKernel(event_size=d, inv_mass_diag=imd, step_size=float(g["step"]), n_leapfrog_steps=int(g["L"])),
                 HMCParameters())
@@ -143,6 +147,10 @@ def test_golden_mala(name):
 @pytest.mark.parametrize("name", ["hmc_g1", "hmc_rb"])
 def test_golden_hmc(name):
     _golden_local(name, "hmc")
+
+
+def test_golden_mh():
+    _golden_local("mh_gm", "mh")
 
 
 def _check_output(out, g, jump=False):

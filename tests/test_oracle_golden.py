@@ -61,3 +61,9 @@ def test_neutra_hmc():
     run = R.run_neutra_hmc(torch.from_numpy(g["x0"]), oracle_target(g), oracle_flow(g), int(g["T"]), tape(g),
                            float(g["step"]), torch.from_numpy(g["imd"]), n_leapfrog=int(g["L"]))
     _check(g, run)
+
+
+def test_mh():
+    g = load_case("mh_gm")
+    run = R.run_mh(torch.from_numpy(g["x0"]), oracle_target(g), torch.from_numpy(g["imd"]), int(g["K"]), tape(g))
+    _check(g, run)
