@@ -17,7 +17,6 @@ from __future__ import annotations
 import argparse
 import ctypes as C
 import json
-import math
 import os
 import subprocess
 import sys

@@ -339,42 +339,39 @@ def pack_realnvp_affines(bij: "RealNVP") -> torch.Tensor:
 
 
 def _pack_coupling_fp32(lin, da, db, M, H, small, odd):
-    parts = []
-    if True:
-        if small:
-            w1, b1 = lin[0]                                  # [H, da]
-            wl, bl = lin[1]                                  # [2*db, H]
-            w1t = torch.zeros(da, SMALL_H)
-            w1t[:, :H] = (w1.flip(1) if odd else w1).t()     # [ks][h]
-            b1p = torch.zeros(SMALL_H)
-            b1p[:H] = b1
-            wlt = torch.zeros(db, 2, SMALL_H)
-            wlt[:, :, :H] = wl.reshape(db, 2, H)             # [t_log][c][h]
-            blt = bl.reshape(db, 2)                          # [t_log][c]
-            if odd:
-                wlt, blt = wlt.flip(0), blt.flip(0)
-            blp = torch.zeros(((2 * db + 3) // 4) * 4)
-            blp[: 2 * db] = blt.reshape(-1)
-            parts += [w1t.reshape(-1), b1p, wlt.reshape(-1), blp]
-        elif M >= 2:
-            w1, b1 = lin[0]                                  # [H, da]
-            parts += [(w1.flip(1) if odd else w1).reshape(-1), b1]
-            for wm, bm in lin[1:-1]:                         # [H_out, H_in] -> [H_in][H_out]
-                parts += [wm.t().contiguous().reshape(-1), bm]
-            wl, bl = lin[-1]                                 # [2*db, H]
-            wl = wl.reshape(db, 2, H).permute(2, 1, 0)       # [H][2][db]
-            bl = bl.reshape(db, 2).t()                       # [2][db]
-            if odd:
-                wl, bl = wl.flip(2), bl.flip(1)
-            parts += [wl.contiguous().reshape(-1), bl.contiguous().reshape(-1)]
-        else:
-            wl, bl = lin[0]                                  # [2*db, da]
-            wl = wl.reshape(db, 2, da).permute(2, 1, 0)      # [da][2][db]
-            bl = bl.reshape(db, 2).t()
-            if odd:
-                wl, bl = wl.flip(0).flip(2), bl.flip(1)
-            parts += [wl.contiguous().reshape(-1), bl.contiguous().reshape(-1)]
-    return parts
+    """fp32 weights of one coupling in the kernels' layout (``lin`` = [(weight, bias), ...] of the conditioner's linear
+    layers; ``odd`` = an odd number of reversals precede the coupling, so source / target indices are flipped)."""
+    if small:                                            # M == 2, H <= 8: hidden-minor, zero padded to 8
+        (w1, b1), (wl, bl) = lin                         # [H, da], [2*db, H]
+        w1t = torch.zeros(da, SMALL_H)
+        w1t[:, :H] = (w1.flip(1) if odd else w1).t()     # [ks][h]
+        b1p = torch.zeros(SMALL_H)
+        b1p[:H] = b1
+        wlt = torch.zeros(db, 2, SMALL_H)
+        wlt[:, :, :H] = wl.reshape(db, 2, H)             # [t_log][c][h]
+        blt = bl.reshape(db, 2)                          # [t_log][c]
+        if odd:
+            wlt, blt = wlt.flip(0), blt.flip(0)
+        blp = torch.zeros(((2 * db + 3) // 4) * 4)
+        blp[: 2 * db] = blt.reshape(-1)
+        return [w1t.reshape(-1), b1p, wlt.reshape(-1), blp]
+    if M >= 2:
+        w1, b1 = lin[0]                                  # [H, da]
+        parts = [(w1.flip(1) if odd else w1).reshape(-1), b1]
+        for wm, bm in lin[1:-1]:                         # [H_out, H_in] -> [H_in][H_out]
+            parts += [wm.t().contiguous().reshape(-1), bm]
+        wl, bl = lin[-1]                                 # [2*db, H]
+        wl = wl.reshape(db, 2, H).permute(2, 1, 0)       # [H][2][db]
+        bl = bl.reshape(db, 2).t()                       # [2][db]
+        if odd:
+            wl, bl = wl.flip(2), bl.flip(1)
+        return parts + [wl.contiguous().reshape(-1), bl.contiguous().reshape(-1)]
+    wl, bl = lin[0]                                      # M == 1: [2*db, da]
+    wl = wl.reshape(db, 2, da).permute(2, 1, 0)          # [da][2][db]
+    bl = bl.reshape(db, 2).t()
+    if odd:
+        wl, bl = wl.flip(0).flip(2), bl.flip(1)
+    return [wl.contiguous().reshape(-1), bl.contiguous().reshape(-1)]
 
 
 def tc_supported(d: int, M: int, H: int) -> bool:

@@ -18,7 +18,7 @@ from __future__ import annotations
 import math
 import time
 from copy import deepcopy
-from typing import Callable, Optional, Tuple
+from typing import Callable, Tuple
 
 import torch
 import torch.distributed as dist

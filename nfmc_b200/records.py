@@ -11,7 +11,7 @@ is what makes pooling over GPUs a plain all-reduce.
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Any, Dict, List, Optional, Tuple, Union
 
 import torch

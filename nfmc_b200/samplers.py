@@ -17,13 +17,13 @@ import ctypes as C
 import math
 import time
 from copy import deepcopy
-from typing import Optional, Tuple, Union
+from typing import Optional, Tuple
 
 import torch
 
 from . import _native as N
 from .flow import Flow
-from .potentials import Potential, resolve_target
+from .potentials import resolve_target
 from .records import (MHKernel, MHParameters, HMCKernel, HMCParameters, IMHKernel, IMHParameters, JumpNFMCOutput, JumpNFMCParameters,
                       LangevinKernel, LangevinParameters, MCMCKernel, MCMCOutput, MCMCParameters, MetropolisKernel,
                       MetropolisParameters, NeuTraKernel, NeuTraParameters, NFMCKernel)
