@@ -125,6 +125,14 @@ __device__ __forceinline__ float tanh_approx(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// tanh of two values at once, straight in the bf16 the next GEMM consumes: one MUFU op per pair instead of two
+// (the epilogue is MUFU-bound), and no separate convert/pack.  a -> low half, b -> high half.
+__device__ __forceinline__ uint32_t tanh_bf16x2(float a, float b) {
+  uint32_t p, y;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(b), "f"(a));
+  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(p));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -139,7 +147,12 @@ constexpr int kTcGroups = 4;
 constexpr int kTcOwn = kTcHalf / kTcGroups;   // 16 elements per half per thread
 constexpr int kTcThreads = kTcRows * kTcGroups;
 
-__global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const TcArgs A) {
+// MINB = 2: two CTAs per SM (<= 64 registers per thread, 256 TMEM columns each) so that one tile's epilogue overlaps the
+// other tile's MMAs / TMA waits; possible when H + N2p <= 256 and the shared-memory plan fits twice.
+template <int MINB>
+__global__ void __launch_bounds__(kTcThreads, MINB) flow_tc_kernel(const TcArgs A) {
+  const uint32_t tmem_cols = (MINB == 2) ? 256u : (uint32_t)kTcTmemCols;
+  const uint32_t col2 = (MINB == 2) ? (uint32_t)A.H : (uint32_t)kTcCol2;   // TMEM column of the second accumulator
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
   const int r = tid & (kTcRows - 1), g = tid >> 7;
@@ -160,7 +173,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const TcArgs A) 
     mbar_init(bar_mma, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTcTmemCols);
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -277,10 +290,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const TcArgs A) 
           float v[16];
           tmem_ld16(tmem_row + c * 16, v);
 #pragma unroll
-          for (int q = 0; q < 16; ++q) v[q] = tanh_approx(v[q] + b1[c * 16 + q]);
+          for (int q = 0; q < 16; ++q) v[q] += b1[c * 16 + q];
           uint4 w0, w1;
-          w0.x = pack_bf16(v[0], v[1]); w0.y = pack_bf16(v[2], v[3]); w0.z = pack_bf16(v[4], v[5]); w0.w = pack_bf16(v[6], v[7]);
-          w1.x = pack_bf16(v[8], v[9]); w1.y = pack_bf16(v[10], v[11]); w1.z = pack_bf16(v[12], v[13]); w1.w = pack_bf16(v[14], v[15]);
+          w0.x = tanh_bf16x2(v[0], v[1]); w0.y = tanh_bf16x2(v[2], v[3]); w0.z = tanh_bf16x2(v[4], v[5]); w0.w = tanh_bf16x2(v[6], v[7]);
+          w1.x = tanh_bf16x2(v[8], v[9]); w1.y = tanh_bf16x2(v[10], v[11]); w1.z = tanh_bf16x2(v[12], v[13]); w1.w = tanh_bf16x2(v[14], v[15]);
           *reinterpret_cast<uint4*>(sHid + ((size_t)(2 * c) * kTcRows + r) * 16) = w0;
           *reinterpret_cast<uint4*>(sHid + ((size_t)(2 * c + 1) * kTcRows + r) * 16) = w1;
         }
@@ -293,7 +306,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const TcArgs A) 
         const uint32_t a0 = smem_u32(sHid), b0 = smem_u32(sW + (size_t)kTcK1 * H * 2 + (size_t)H * 4);  // Wl image [H/8][N2p][8]
 #pragma unroll 1
         for (int kk = 0; kk < H / 16; ++kk)
-          umma_f16(tmem_base + kTcCol2, umma_desc(a0 + kk * 2 * (kTcRows * 16), kTcRows * 16, 128),
+          umma_f16(tmem_base + col2, umma_desc(a0 + kk * 2 * (kTcRows * 16), kTcRows * 16, 128),
                    umma_desc(b0 + kk * 2 * (N2p * 16), N2p * 16, 128), idesc2, kk > 0);
         umma_commit(bar_mma);
       }
@@ -308,7 +321,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const TcArgs A) 
           const int c = 2 * g + h2;                       // 16 columns = 8 targets (u_a, u_b interleaved)
           if (c * 16 < N2p) {
             float v[16];
-            tmem_ld16(tmem_row + kTcCol2 + c * 16, v);
+            tmem_ld16(tmem_row + col2 + c * 16, v);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const int t = c * 8 + q;
@@ -378,7 +391,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const TcArgs A) 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, kTcTmemCols);
+  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 }  // namespace nfmc
@@ -405,9 +418,16 @@ extern "C" int nfmc_flow_tc_pass(const nfmc_realnvp_tc* flow, int32_t mode, cons
   const size_t wbytes = (tc_coupling_bytes(H, A.N2p) + 15) & ~size_t(15);
   const size_t smem = (size_t)kTcRows * kTcK1 * 2 + (size_t)kTcRows * H * 2 + wbytes + 2 * kTcGroups * kTcRows * sizeof(float) + (((size_t)(Lc + 1) * 4 * d + 4 + 3) & ~size_t(3)) * sizeof(float) + 64;
   if (smem > 227 * 1024) return set_error("flow_tc_pass: shared-memory plan exceeds 227 KB");
-  cudaFuncSetAttribute(flow_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const long long tiles = (n + kTcRows - 1) / kTcRows;
-  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  flow_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(A);
+  const bool two = (H + A.N2p <= 256) && (2 * (smem + 1024) <= 227 * 1024);
+  const long long cap = (long long)sm_count() * (two ? 2 : 1);
+  const int grid = (int)(tiles < cap ? tiles : cap);
+  if (two) {
+    cudaFuncSetAttribute(flow_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    flow_tc_kernel<2><<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(A);
+  } else {
+    cudaFuncSetAttribute(flow_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    flow_tc_kernel<1><<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(A);
+  }
   return check_cuda(cudaGetLastError(), "flow_tc_kernel launch");
 }
