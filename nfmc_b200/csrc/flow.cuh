@@ -423,7 +423,7 @@ __device__ __forceinline__ void swap_halves(float (&a)[E], float (&b)[E], bool d
 //      update is fma(r, b, s) with (r, s) = (alpha, beta) or (1/alpha, -beta/alpha)).  ld accumulates THIS LANE's share
 //      of sum_t log alpha_t (the caller group-sums once per pass and applies the sign).  When the source is the high
 //      half the two register arrays are swapped around the layer so that there is a single conditioner call site.
-template <int E, bool SB, bool X>
+template <int E, bool SB, bool X, bool SM>
 __device__ __forceinline__ void coupling_apply(const FlowDesc& F, const Geom& g, int l, bool inv, float (&lo)[E], float (&hi)[E],
                                                float* scr, float& ld) {
   float ua[E], ub[E], ua_x, ub_x;
@@ -433,7 +433,7 @@ __device__ __forceinline__ void coupling_apply(const FlowDesc& F, const Geom& g,
   const int nt_main = src_is_hi ? F.da : F.db;
   const int Woff = F.off_coupling + l * F.coupling_stride;
   swap_halves(lo, hi, src_is_hi);  // lo = source array, hi = target array
-  if (F.small) {
+  if constexpr (SM) {
     float hid[kSmallH];
     cond_forward_small<E, SB, X>(F, g, Woff, lo, shift, nt_main, has_x, hid, ua, ub, ua_x, ub_x);
   } else {
@@ -463,7 +463,7 @@ __device__ __forceinline__ void coupling_apply(const FlowDesc& F, const Geom& g,
 // the gradient of U~ with respect to it.  On return they hold its INPUT (a, b') and the gradient with respect to
 // that input, where U~ = U(x) - log|det dx/dz| so each coupling contributes + sum log alpha to U~:
 //   b = (b' - beta)/alpha  =>  dU~/dalpha = (1 - gb*b)/alpha,  dU~/dbeta = -gb/alpha,  dU~/db' = gb/alpha.
-template <int E, bool SB, bool X>
+template <int E, bool SB, bool X, bool SM>
 __device__ __forceinline__ void coupling_unwind(const FlowDesc& F, const Geom& g, int l, float (&lo)[E], float (&hi)[E],
                                                 float (&glo)[E], float (&ghi)[E], float* scr) {
   float ua[E], ub[E], ua_x = 0.f, ub_x = 0.f;
@@ -476,7 +476,7 @@ __device__ __forceinline__ void coupling_unwind(const FlowDesc& F, const Geom& g
   const int Woff = F.off_coupling + l * F.coupling_stride;
   swap_halves(lo, hi, src_is_hi);
   swap_halves(glo, ghi, src_is_hi);
-  if (F.small) cond_forward_small<E, SB, X>(F, g, Woff, lo, shift, nt_main, has_x, hid, ua, ub, ua_x, ub_x);
+  if constexpr (SM) cond_forward_small<E, SB, X>(F, g, Woff, lo, shift, nt_main, has_x, hid, ua, ub, ua_x, ub_x);
   else cond_forward_generic<E>(F, g, F.blob + Woff, lo, shift, nt_main, has_x, scr, ua, ub, ua_x, ub_x);
 #pragma unroll
   for (int e = 0; e < E; ++e) {
@@ -502,7 +502,7 @@ __device__ __forceinline__ void coupling_unwind(const FlowDesc& F, const Geom& g
     lo[0] = fmaf(al, lo[0], be);
     glo[0] *= ra;
   }
-  if (F.small) cond_backward_small<E, SB, X>(F, g, Woff, shift, nt_main, has_x, hid, ua, ub, dua_x, dub_x, glo);
+  if constexpr (SM) cond_backward_small<E, SB, X>(F, g, Woff, shift, nt_main, has_x, hid, ua, ub, dua_x, dub_x, glo);
   else cond_backward_generic<E>(F, g, F.blob + Woff, shift, nt_main, has_x, scr, ua, ub, dua_x, dub_x, glo);
   swap_halves(lo, hi, src_is_hi);
   swap_halves(glo, ghi, src_is_hi);
@@ -511,35 +511,35 @@ __device__ __forceinline__ void coupling_unwind(const FlowDesc& F, const Geom& g
 // ---- whole-flow pass on physical coordinates: one loop over the 2*Lc+1 layers, walked forwards (x -> z, returns
 //      log|det dz/dx|) or backwards (z -> x, returns log|det dx/dz|).  A single code instance of each layer type, so the
 //      instruction footprint stays small (the jump executes this code once per launch per warp: fetch matters).
-template <int E, bool SB, bool X>
+template <int E, bool SB, bool X, bool SM>
 __device__ __forceinline__ float flow_pass(const FlowDesc& F, const Geom& g, bool inv, float (&lo)[E], float (&hi)[E], float* scr) {
   float ld = 0.f;
   const int n_ops = 2 * F.Lc + 1;
 #pragma unroll 1
   for (int i = 0; i < n_ops; ++i) {
     const int op = inv ? n_ops - 1 - i : i;
-    if (op & 1) coupling_apply<E, SB, X>(F, g, op >> 1, inv, lo, hi, scr, ld);
+    if (op & 1) coupling_apply<E, SB, X, SM>(F, g, op >> 1, inv, lo, hi, scr, ld);
     else affine_apply<E, SB, X>(F, g, op >> 1, inv, lo, hi);
   }
   const float tot = group_sum(ld, g.gs) + ldp<SB>(F, F.off_const);
   return inv ? -tot : tot;
 }
-template <int E, bool SB, bool X>
+template <int E, bool SB, bool X, bool SM>
 __device__ __forceinline__ float flow_forward(const FlowDesc& F, const Geom& g, float (&lo)[E], float (&hi)[E], float* scr) {
-  return flow_pass<E, SB, X>(F, g, false, lo, hi, scr);
+  return flow_pass<E, SB, X, SM>(F, g, false, lo, hi, scr);
 }
-template <int E, bool SB, bool X>
+template <int E, bool SB, bool X, bool SM>
 __device__ __forceinline__ float flow_inverse(const FlowDesc& F, const Geom& g, float (&lo)[E], float (&hi)[E], float* scr) {
-  return flow_pass<E, SB, X>(F, g, true, lo, hi, scr);
+  return flow_pass<E, SB, X, SM>(F, g, true, lo, hi, scr);
 }
 // Given x = T^-1(z) in (lo, hi) and dU/dx in (glo, ghi): walk x -> z, leaving z in (lo, hi) and
 // d/dz [ U(T^-1 z) - log|det dT^-1/dz| ] in (glo, ghi).
-template <int E, bool SB, bool X>
+template <int E, bool SB, bool X, bool SM>
 __device__ __forceinline__ void flow_unwind(const FlowDesc& F, const Geom& g, float (&lo)[E], float (&hi)[E],
                                             float (&glo)[E], float (&ghi)[E], float* scr) {
   affine_unwind<E, SB, X>(F, g, 0, lo, hi, glo, ghi);
   for (int l = 0; l < F.Lc; ++l) {
-    coupling_unwind<E, SB, X>(F, g, l, lo, hi, glo, ghi, scr);
+    coupling_unwind<E, SB, X, SM>(F, g, l, lo, hi, glo, ghi, scr);
     affine_unwind<E, SB, X>(F, g, 1 + l, lo, hi, glo, ghi);
   }
 }

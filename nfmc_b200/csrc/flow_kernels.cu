@@ -15,7 +15,7 @@
 
 namespace nfmc {
 
-template <int E, bool SB, bool X>
+template <int E, bool SB, bool X, bool SM>
 __global__ void __launch_bounds__(kThreads) flow_pass_kernel(FlowArgs A, int mode, const float* __restrict__ in,
                                                             float* __restrict__ out, float* __restrict__ aux, long long n) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(kThreads) flow_pass_kernel(FlowArgs A, int mod
     const float* src = in + chain * (long long)A.d;
     if (mode == PASS_INVERSE && flip) load_chain_flipped(src, g, lo, hi);
     else load_chain(src, g, lo, hi);
-    float r = flow_pass<E, SB, X>(S.F, g, mode == PASS_INVERSE, lo, hi, S.scr);
+    float r = flow_pass<E, SB, X, SM>(S.F, g, mode == PASS_INVERSE, lo, hi, S.scr);
     if (mode == PASS_LOGPROB) r += base_log_prob(g, lo, hi);
     if (active) {
       if (out) {
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(kThreads) flow_pass_kernel(FlowArgs A, int mod
   }
 }
 
-template <int E, bool SB, bool X>
+template <int E, bool SB, bool X, bool SM>
 __global__ void __launch_bounds__(kThreads) flow_sample_kernel(FlowArgs A, RngArgs R, long long chain0, float* __restrict__ x,
                                                               float* __restrict__ logq, long long n) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kThreads) flow_sample_kernel(FlowArgs A, RngAr
     float lo[E], hi[E];
     draw_base<E>(R, g, flip, n, chain, chain0, 0, lo, hi);
     const float blp = base_log_prob(g, lo, hi);
-    const float ld = flow_inverse<E, SB, X>(S.F, g, lo, hi, S.scr);
+    const float ld = flow_inverse<E, SB, X, SM>(S.F, g, lo, hi, S.scr);
     if (active) {
       store_chain(x + chain * (long long)A.d, g, lo, hi);
       if (logq && g.j == 0) logq[chain] = blp - ld;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kThreads) flow_sample_kernel(FlowArgs A, RngAr
 // ---------------------------------------------------------------------------------------------------------
 
 
-template <int E, bool SB, bool X>
+template <int E, bool SB, bool X, bool SM>
 __global__ void __launch_bounds__(kThreads, 3) jump_kernel(const JumpArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ChainArgs& C = A.c;
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kThreads, 3) jump_kernel(const JumpArgs A) {
           ubits = draw_base<E>(C.rng, g, flip, C.n, chain, C.chain0, k, plo, phi);
           blp = base_log_prob(g, plo, phi);
         }
-        const float ld = flow_pass<E, SB, X>(S.F, g, pass == 1, plo, phi, S.scr);
+        const float ld = flow_pass<E, SB, X, SM>(S.F, g, pass == 1, plo, phi, S.scr);
         if (pass == 0) f_x = base_log_prob(g, plo, phi) + ld;
         else f_p = blp - ld;
       }
@@ -277,60 +277,63 @@ template int launch_jump_accept<NFMC_ONLY_E>(const AcceptArgs&, int, size_t, cud
 template <int E>
 int launch_flow_pass(const FlowArgs& A, int mode, const float* in, float* out, float* aux, long long n, int grid,
                      size_t smem, cudaStream_t s) {
-  // exact-layout specialisations are instantiated for the production shapes (E = 13, 16) only
-  const bool xl = A.exact && (E == 13 || E == 16);
-  if (A.stage_blob && xl) {
-    NFMC_SET_SMEM_RET((flow_pass_kernel<E, true, (E == 13 || E == 16)>), smem);
-    flow_pass_kernel<E, true, (E == 13 || E == 16)><<<grid, kThreads, smem, s>>>(A, mode, in, out, aux, n);
-  } else if (A.stage_blob) {
-    NFMC_SET_SMEM_RET((flow_pass_kernel<E, true, false>), smem);
-    flow_pass_kernel<E, true, false><<<grid, kThreads, smem, s>>>(A, mode, in, out, aux, n);
-  } else if (xl) {
-    NFMC_SET_SMEM_RET((flow_pass_kernel<E, false, (E == 13 || E == 16)>), smem);
-    flow_pass_kernel<E, false, (E == 13 || E == 16)><<<grid, kThreads, smem, s>>>(A, mode, in, out, aux, n);
-  } else {
-    NFMC_SET_SMEM_RET((flow_pass_kernel<E, false, false>), smem);
-    flow_pass_kernel<E, false, false><<<grid, kThreads, smem, s>>>(A, mode, in, out, aux, n);
-  }
+  // exact-layout specialisations are instantiated for the production shapes (E = 13, 16) only; the generic
+  // (non-small) conditioner path is a separate, single variant per blob placement
+  constexpr bool XE = (E == 13 || E == 16);
+  const bool small = flow_is_small(A.M, A.H);
+  const bool xl = A.exact && XE;
+#define NFMC_LAUNCH(SBv, Xv, Sv)                                                              \
+  do {                                                                                        \
+    NFMC_SET_SMEM_RET((flow_pass_kernel<E, SBv, Xv, Sv>), smem);                                        \
+    flow_pass_kernel<E, SBv, Xv, Sv><<<grid, kThreads, smem, s>>>(A, mode, in, out, aux, n);                              \
+  } while (0)
+  if (!small) { if (A.stage_blob) NFMC_LAUNCH(true, false, false); else NFMC_LAUNCH(false, false, false); }
+  else if (A.stage_blob && xl) NFMC_LAUNCH(true, XE, true);
+  else if (A.stage_blob) NFMC_LAUNCH(true, false, true);
+  else if (xl) NFMC_LAUNCH(false, XE, true);
+  else NFMC_LAUNCH(false, false, true);
+#undef NFMC_LAUNCH
   return check_cuda(cudaGetLastError(), "flow_pass_kernel launch");
 }
 template <int E>
 int launch_flow_sample(const FlowArgs& A, const RngArgs& R, long long chain0, float* x, float* logq, long long n, int grid,
                        size_t smem, cudaStream_t s) {
-  // exact-layout specialisations are instantiated for the production shapes (E = 13, 16) only
-  const bool xl = A.exact && (E == 13 || E == 16);
-  if (A.stage_blob && xl) {
-    NFMC_SET_SMEM_RET((flow_sample_kernel<E, true, (E == 13 || E == 16)>), smem);
-    flow_sample_kernel<E, true, (E == 13 || E == 16)><<<grid, kThreads, smem, s>>>(A, R, chain0, x, logq, n);
-  } else if (A.stage_blob) {
-    NFMC_SET_SMEM_RET((flow_sample_kernel<E, true, false>), smem);
-    flow_sample_kernel<E, true, false><<<grid, kThreads, smem, s>>>(A, R, chain0, x, logq, n);
-  } else if (xl) {
-    NFMC_SET_SMEM_RET((flow_sample_kernel<E, false, (E == 13 || E == 16)>), smem);
-    flow_sample_kernel<E, false, (E == 13 || E == 16)><<<grid, kThreads, smem, s>>>(A, R, chain0, x, logq, n);
-  } else {
-    NFMC_SET_SMEM_RET((flow_sample_kernel<E, false, false>), smem);
-    flow_sample_kernel<E, false, false><<<grid, kThreads, smem, s>>>(A, R, chain0, x, logq, n);
-  }
+  // exact-layout specialisations are instantiated for the production shapes (E = 13, 16) only; the generic
+  // (non-small) conditioner path is a separate, single variant per blob placement
+  constexpr bool XE = (E == 13 || E == 16);
+  const bool small = flow_is_small(A.M, A.H);
+  const bool xl = A.exact && XE;
+#define NFMC_LAUNCH(SBv, Xv, Sv)                                                              \
+  do {                                                                                        \
+    NFMC_SET_SMEM_RET((flow_sample_kernel<E, SBv, Xv, Sv>), smem);                                        \
+    flow_sample_kernel<E, SBv, Xv, Sv><<<grid, kThreads, smem, s>>>(A, R, chain0, x, logq, n);                              \
+  } while (0)
+  if (!small) { if (A.stage_blob) NFMC_LAUNCH(true, false, false); else NFMC_LAUNCH(false, false, false); }
+  else if (A.stage_blob && xl) NFMC_LAUNCH(true, XE, true);
+  else if (A.stage_blob) NFMC_LAUNCH(true, false, true);
+  else if (xl) NFMC_LAUNCH(false, XE, true);
+  else NFMC_LAUNCH(false, false, true);
+#undef NFMC_LAUNCH
   return check_cuda(cudaGetLastError(), "flow_sample_kernel launch");
 }
 template <int E>
 int launch_jump(const JumpArgs& A, int grid, size_t smem, cudaStream_t s) {
-  // exact-layout specialisations are instantiated for the production shapes (E = 13, 16) only
-  const bool xl = A.f.exact && (E == 13 || E == 16);
-  if (A.f.stage_blob && xl) {
-    NFMC_SET_SMEM_RET((jump_kernel<E, true, (E == 13 || E == 16)>), smem);
-    jump_kernel<E, true, (E == 13 || E == 16)><<<grid, kThreads, smem, s>>>(A);
-  } else if (A.f.stage_blob) {
-    NFMC_SET_SMEM_RET((jump_kernel<E, true, false>), smem);
-    jump_kernel<E, true, false><<<grid, kThreads, smem, s>>>(A);
-  } else if (xl) {
-    NFMC_SET_SMEM_RET((jump_kernel<E, false, (E == 13 || E == 16)>), smem);
-    jump_kernel<E, false, (E == 13 || E == 16)><<<grid, kThreads, smem, s>>>(A);
-  } else {
-    NFMC_SET_SMEM_RET((jump_kernel<E, false, false>), smem);
-    jump_kernel<E, false, false><<<grid, kThreads, smem, s>>>(A);
-  }
+  // exact-layout specialisations are instantiated for the production shapes (E = 13, 16) only; the generic
+  // (non-small) conditioner path is a separate, single variant per blob placement
+  constexpr bool XE = (E == 13 || E == 16);
+  const bool small = flow_is_small(A.f.M, A.f.H);
+  const bool xl = A.f.exact && XE;
+#define NFMC_LAUNCH(SBv, Xv, Sv)                                                              \
+  do {                                                                                        \
+    NFMC_SET_SMEM_RET((jump_kernel<E, SBv, Xv, Sv>), smem);                                        \
+    jump_kernel<E, SBv, Xv, Sv><<<grid, kThreads, smem, s>>>(A);                              \
+  } while (0)
+  if (!small) { if (A.f.stage_blob) NFMC_LAUNCH(true, false, false); else NFMC_LAUNCH(false, false, false); }
+  else if (A.f.stage_blob && xl) NFMC_LAUNCH(true, XE, true);
+  else if (A.f.stage_blob) NFMC_LAUNCH(true, false, true);
+  else if (xl) NFMC_LAUNCH(false, XE, true);
+  else NFMC_LAUNCH(false, false, true);
+#undef NFMC_LAUNCH
   return check_cuda(cudaGetLastError(), "jump_kernel launch");
 }
 template int launch_flow_pass<NFMC_ONLY_E>(const FlowArgs&, int, const float*, float*, float*, long long, int, size_t, cudaStream_t);

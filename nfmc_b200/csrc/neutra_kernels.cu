@@ -16,14 +16,14 @@
 namespace nfmc {
 
 // U~(z) and its gradient.  (zlo, zhi) physical-order latent; (glo, ghi) receives dU~/dz.
-template <int E, bool SB, bool X>
+template <int E, bool SB, bool X, bool SM>
 __device__ __forceinline__ float neutra_value_grad(const FlowDesc& F, int pot_kind, const PotParams& P, const Geom& g, const float (&zlo)[E],
                                                    const float (&zhi)[E], float (&glo)[E], float (&ghi)[E], float* scr,
                                                    bool want_grad) {
   float xlo[E], xhi[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) { xlo[e] = zlo[e]; xhi[e] = zhi[e]; }
-  const float ld_inv = flow_inverse<E, SB, X>(F, g, xlo, xhi, scr);                      // neutra.py:60
+  const float ld_inv = flow_inverse<E, SB, X, SM>(F, g, xlo, xhi, scr);                      // neutra.py:60
   const PotCtx c = pot_prepare_rt<E>(pot_kind, P, g, xlo, xhi);
   const float value = -((-c.u) + ld_inv);                                          // neutra.py:62-64
   if (want_grad) {
@@ -34,7 +34,7 @@ __device__ __forceinline__ float neutra_value_grad(const FlowDesc& F, int pot_ki
       if (kk >= g.da) glo[e] = 0.f;
       if (kk >= g.db) ghi[e] = 0.f;
     }
-    flow_unwind<E, SB, X>(F, g, xlo, xhi, glo, ghi, scr);
+    flow_unwind<E, SB, X, SM>(F, g, xlo, xhi, glo, ghi, scr);
   }
   return value;
 }
@@ -44,7 +44,7 @@ __device__ __forceinline__ float neutra_value_grad(const FlowDesc& F, int pot_ki
 // Register budget: the live per-lane state is the latent z, the momentum p and the gradient g (2E each) plus the flow's
 // working copy; the start state of a step is NOT kept (on rejection it is re-read from global memory, which always holds
 // the current state), the running moments live in shared memory, and a non-identity mass is read from shared memory.
-template <int E, bool SB, bool X>
+template <int E, bool SB, bool X, bool SM>
 __global__ void __launch_bounds__(kThreads, 3) neutra_hmc_kernel(const NeutraArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ChainArgs& C = A.c;
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, 3) neutra_hmc_kernel(const NeutraArg
             zhi[e] = vh ? fmaf(A.tau, unit_mass ? phi[e] : phi[e] * mh, zhi[e]) : 0.f;
           }
         }
-        u1 = neutra_value_grad<E, SB, X>(S.F, A.pot_kind, C.pot, g, zlo, zhi, glo, ghi, S.scr, true);
+        u1 = neutra_value_grad<E, SB, X, SM>(S.F, A.pot_kind, C.pot, g, zlo, zhi, glo, ghi, S.scr, true);
         if (l == 0) u0 = u1;
         else {
 #pragma unroll
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(kThreads, 3) neutra_hmc_kernel(const NeutraArg
   cta_stats_finish(S.st, C.stats, C.d);
 }
 
-template <int E, bool SB, bool X>
+template <int E, bool SB, bool X, bool SM>
 __global__ void __launch_bounds__(kThreads) neutra_potential_kernel(FlowArgs FA, int pot_kind, PotParams P, const float* __restrict__ z,
                                                                    float* __restrict__ u, float* __restrict__ grad, long long n) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kThreads) neutra_potential_kernel(FlowArgs FA,
     float zlo[E], zhi[E], glo[E], ghi[E];
     const float* src = z + chain * (long long)FA.d;
     if (flip) load_chain_flipped(src, g, zlo, zhi); else load_chain(src, g, zlo, zhi);
-    const float v = neutra_value_grad<E, SB, X>(S.F, pot_kind, P, g, zlo, zhi, glo, ghi, S.scr, grad != nullptr);
+    const float v = neutra_value_grad<E, SB, X, SM>(S.F, pot_kind, P, g, zlo, zhi, glo, ghi, S.scr, grad != nullptr);
     if (active) {
       if (g.j == 0) u[chain] = v;
       if (grad) {
@@ -231,41 +231,43 @@ __global__ void __launch_bounds__(kThreads) neutra_potential_kernel(FlowArgs FA,
 
 template <int E>
 int launch_neutra_hmc(const NeutraArgs& A, int grid, size_t smem, cudaStream_t s) {
-  // exact-layout specialisations are instantiated for the production shapes (E = 13, 16) only
-  const bool xl = A.f.exact && (E == 13 || E == 16);
-  if (A.f.stage_blob && xl) {
-    NFMC_SET_SMEM_RET((neutra_hmc_kernel<E, true, (E == 13 || E == 16)>), smem);
-    neutra_hmc_kernel<E, true, (E == 13 || E == 16)><<<grid, kThreads, smem, s>>>(A);
-  } else if (A.f.stage_blob) {
-    NFMC_SET_SMEM_RET((neutra_hmc_kernel<E, true, false>), smem);
-    neutra_hmc_kernel<E, true, false><<<grid, kThreads, smem, s>>>(A);
-  } else if (xl) {
-    NFMC_SET_SMEM_RET((neutra_hmc_kernel<E, false, (E == 13 || E == 16)>), smem);
-    neutra_hmc_kernel<E, false, (E == 13 || E == 16)><<<grid, kThreads, smem, s>>>(A);
-  } else {
-    NFMC_SET_SMEM_RET((neutra_hmc_kernel<E, false, false>), smem);
-    neutra_hmc_kernel<E, false, false><<<grid, kThreads, smem, s>>>(A);
-  }
+  // exact-layout specialisations are instantiated for the production shapes (E = 13, 16) only; the generic
+  // (non-small) conditioner path is a separate, single variant per blob placement
+  constexpr bool XE = (E == 13 || E == 16);
+  const bool small = flow_is_small(A.f.M, A.f.H);
+  const bool xl = A.f.exact && XE;
+#define NFMC_LAUNCH(SBv, Xv, Sv)                                                              \
+  do {                                                                                        \
+    NFMC_SET_SMEM_RET((neutra_hmc_kernel<E, SBv, Xv, Sv>), smem);                                        \
+    neutra_hmc_kernel<E, SBv, Xv, Sv><<<grid, kThreads, smem, s>>>(A);                              \
+  } while (0)
+  if (!small) { if (A.f.stage_blob) NFMC_LAUNCH(true, false, false); else NFMC_LAUNCH(false, false, false); }
+  else if (A.f.stage_blob && xl) NFMC_LAUNCH(true, XE, true);
+  else if (A.f.stage_blob) NFMC_LAUNCH(true, false, true);
+  else if (xl) NFMC_LAUNCH(false, XE, true);
+  else NFMC_LAUNCH(false, false, true);
+#undef NFMC_LAUNCH
   return check_cuda(cudaGetLastError(), "neutra_hmc_kernel launch");
 }
 template <int E>
 int launch_neutra_potential(const FlowArgs& FA, int pot_kind, const PotParams& P, const float* z, float* u, float* grad,
                             long long n, int grid, size_t smem, cudaStream_t s) {
-  // exact-layout specialisations are instantiated for the production shapes (E = 13, 16) only
-  const bool xl = FA.exact && (E == 13 || E == 16);
-  if (FA.stage_blob && xl) {
-    NFMC_SET_SMEM_RET((neutra_potential_kernel<E, true, (E == 13 || E == 16)>), smem);
-    neutra_potential_kernel<E, true, (E == 13 || E == 16)><<<grid, kThreads, smem, s>>>(FA, pot_kind, P, z, u, grad, n);
-  } else if (FA.stage_blob) {
-    NFMC_SET_SMEM_RET((neutra_potential_kernel<E, true, false>), smem);
-    neutra_potential_kernel<E, true, false><<<grid, kThreads, smem, s>>>(FA, pot_kind, P, z, u, grad, n);
-  } else if (xl) {
-    NFMC_SET_SMEM_RET((neutra_potential_kernel<E, false, (E == 13 || E == 16)>), smem);
-    neutra_potential_kernel<E, false, (E == 13 || E == 16)><<<grid, kThreads, smem, s>>>(FA, pot_kind, P, z, u, grad, n);
-  } else {
-    NFMC_SET_SMEM_RET((neutra_potential_kernel<E, false, false>), smem);
-    neutra_potential_kernel<E, false, false><<<grid, kThreads, smem, s>>>(FA, pot_kind, P, z, u, grad, n);
-  }
+  // exact-layout specialisations are instantiated for the production shapes (E = 13, 16) only; the generic
+  // (non-small) conditioner path is a separate, single variant per blob placement
+  constexpr bool XE = (E == 13 || E == 16);
+  const bool small = flow_is_small(FA.M, FA.H);
+  const bool xl = FA.exact && XE;
+#define NFMC_LAUNCH(SBv, Xv, Sv)                                                              \
+  do {                                                                                        \
+    NFMC_SET_SMEM_RET((neutra_potential_kernel<E, SBv, Xv, Sv>), smem);                                        \
+    neutra_potential_kernel<E, SBv, Xv, Sv><<<grid, kThreads, smem, s>>>(FA, pot_kind, P, z, u, grad, n);                              \
+  } while (0)
+  if (!small) { if (FA.stage_blob) NFMC_LAUNCH(true, false, false); else NFMC_LAUNCH(false, false, false); }
+  else if (FA.stage_blob && xl) NFMC_LAUNCH(true, XE, true);
+  else if (FA.stage_blob) NFMC_LAUNCH(true, false, true);
+  else if (xl) NFMC_LAUNCH(false, XE, true);
+  else NFMC_LAUNCH(false, false, true);
+#undef NFMC_LAUNCH
   return check_cuda(cudaGetLastError(), "neutra_potential_kernel launch");
 }
 template int launch_neutra_hmc<NFMC_ONLY_E>(const NeutraArgs&, int, size_t, cudaStream_t);
