@@ -77,7 +77,7 @@ typedef struct nfmc_rng {
   uint64_t seed;
   uint64_t step0;        /* global index of the first step of this launch (advance by the steps taken) */
   const float* normals;  /* optional injected N(0,1): [steps, n, d]  (NULL -> Philox) */
-  const float* uniforms; /* optional injected U[0,1): [steps, n]     (NULL -> Philox) */
+  const float* uniforms; /* optional injected U[0,1): [steps, n] (ESS: [steps, n, 2+M]) (NULL -> Philox) */
 } nfmc_rng;
 
 /* ---- statistics accumulated on the device (replaces MCMCExpectation.update, sampling/base.py:75-95, and
@@ -85,7 +85,7 @@ typedef struct nfmc_rng {
 typedef struct nfmc_stats {
   double* sum_x;              /* [d]  += sum over (step, chain) of x after the accept          (or NULL) */
   double* sum_x2;             /* [d]  += sum of x^2                                              (or NULL) */
-  unsigned long long* counts; /* [4]: [0] += accepted, [1] += attempted, [2] += non-finite log-ratios, [3] spare */
+  unsigned long long* counts; /* [4]: [0] += accepted, [1] += attempted, [2] += non-finite log-ratios, [3] ESS only */
 } nfmc_stats;
 
 /* optional sample sink (MCMCSamples.add, sampling/base.py:234-263): rows written for steps whose global
@@ -142,6 +142,14 @@ NFMC_API int nfmc_mala_steps(const nfmc_potential* pot, float* x, int64_t n, int
 NFMC_API int nfmc_mh_steps(const nfmc_potential* pot, float* x, int64_t n, int32_t n_steps, const float* inv_mass_diag,
                   int32_t adjusted, const nfmc_rng* rng, int64_t chain0, const nfmc_stats* stats, const nfmc_sink* sink,
                   void* stream);
+
+/* K elliptical-slice steps with prior N(0, I) -- elliptical_slice_sampling_step (mcmc/ess.py:12-64) wrapped as
+ * ESS.propose (mcmc/ess.py:97-116): `nll` is the negative log-likelihood, at most `max_iterations` bracket rounds per
+ * step, every chain counts as accepted (ess.py:107); counts[3] += chain-steps whose bracket produced a point.
+ * Injected noise (both or neither): rng->normals [steps, n, d] = nu, rng->uniforms [steps, n, 2 + max_iterations] =
+ * {u (:35), theta0 (:39), bracket draws (:58)}. */
+NFMC_API int nfmc_ess_steps(const nfmc_potential* nll, float* x, int64_t n, int32_t n_steps, int32_t max_iterations,
+                   const nfmc_rng* rng, int64_t chain0, const nfmc_stats* stats, const nfmc_sink* sink, void* stream);
 
 /* K HMC steps -- HMC.propose (mcmc/hmc.py:96-126; trajectory :61-77) inside the same local loop */
 NFMC_API int nfmc_hmc_steps(const nfmc_potential* pot, float* x, int64_t n, int32_t n_steps, float step_size,

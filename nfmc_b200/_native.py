@@ -71,6 +71,7 @@ SIGNATURES = {
     "nfmc_mala_steps": (C.c_int, [P(PotentialDesc), _vp, _i64, _i32, _f32, _vp, _i32, P(RngDesc), _i64,
                                   P(StatsDesc), P(SinkDesc), _vp]),
     "nfmc_mh_steps": (C.c_int, [P(PotentialDesc), _vp, _i64, _i32, _vp, _i32, P(RngDesc), _i64, P(StatsDesc), P(SinkDesc), _vp]),
+    "nfmc_ess_steps": (C.c_int, [P(PotentialDesc), _vp, _i64, _i32, _i32, P(RngDesc), _i64, P(StatsDesc), P(SinkDesc), _vp]),
     "nfmc_hmc_steps": (C.c_int, [P(PotentialDesc), _vp, _i64, _i32, _f32, _i32, _vp, _i32, P(RngDesc), _i64,
                                  P(StatsDesc), P(SinkDesc), _vp]),
     "nfmc_jump_step": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _vp, _i64, _i32, P(RngDesc), _i64,

@@ -2,8 +2,8 @@
 
 Strategies on the accelerated hot path: ``jump_mala``, ``jump_ula``, ``jump_hmc``, ``jump_uhmc``, ``neutra_hmc``,
 ``imh`` / ``fixed_imh``, ``adaptive_imh`` and the local kernels they are built from (``mala``, ``ula``, ``hmc``,
-``uhmc``, ``mh`` / ``jump_mh``).  Everything else the reference lists (``ess``, ``tess``, ``dlmc``, ``nuts``, ``neutra_mh`` ...) is outside the
-scope table and raises ``NotImplementedError`` -- there is no eager fallback.
+``uhmc``, ``mh`` / ``jump_mh``, ``ess`` / ``jump_ess``).  Everything else the reference lists (``tess``, ``dlmc``, ``nuts``,
+``neutra_mh`` ...) is outside the scope table and raises ``NotImplementedError`` -- there is no eager fallback.
 """
 from __future__ import annotations
 
@@ -15,13 +15,14 @@ import torch
 from . import _native as N
 from .flow import Flow, create_flow_object
 from .potentials import Potential, resolve_target
-from .records import (MHKernel, MHParameters, HMCKernel, HMCParameters, IMHKernel, IMHParameters, JumpNFMCParameters, LangevinKernel,
+from .records import (ESSKernel, ESSParameters, MHKernel, MHParameters, HMCKernel, HMCParameters, IMHKernel, IMHParameters, JumpNFMCParameters, LangevinKernel,
                       LangevinParameters, MCMCOutput, NeuTraKernel, NeuTraParameters, NFMCKernel)
-from .samplers import (MH, JumpMH, HMC, MALA, UHMC, ULA, AdaptiveIMH, FixedIMH, JumpHMC, JumpMALA, JumpUHMC, JumpULA, NeuTraHMC,
+from .samplers import (ESS, JumpESS, MH, JumpMH, HMC, MALA, UHMC, ULA, AdaptiveIMH, FixedIMH, JumpHMC, JumpMALA, JumpUHMC, JumpULA, NeuTraHMC,
                        Sampler)
 
-LOCAL_STRATEGIES = ('hmc', 'uhmc', 'ula', 'mala', 'mh')
-NF_STRATEGIES = ('imh', 'fixed_imh', 'adaptive_imh', 'jump_mala', 'jump_ula', 'jump_hmc', 'jump_uhmc', 'jump_mh', 'neutra_hmc')
+LOCAL_STRATEGIES = ('hmc', 'uhmc', 'ula', 'mala', 'mh', 'ess')
+NF_STRATEGIES = ('imh', 'fixed_imh', 'adaptive_imh', 'jump_mala', 'jump_ula', 'jump_hmc', 'jump_uhmc', 'jump_mh', 'jump_ess',
+                 'neutra_hmc')
 
 
 def get_supported_samplers():
@@ -61,6 +62,11 @@ def create_sampler(target, event_shape: Optional[Tuple[int, ...]] = None, flow: 
             cls = HMC if strategy == 'hmc' else UHMC
             return finish(cls(event_shape, target, HMCKernel(event_size=event_size, **kernel_kwargs),
                               HMCParameters(**param_kwargs)))
+        if strategy == 'ess':
+            if negative_log_likelihood is None:
+                raise ValueError("Negative log likelihood must be provided")          # reference: sample.py:93-94
+            return finish(ESS(event_shape, target, negative_log_likelihood, ESSKernel(event_shape=event_shape, **kernel_kwargs),
+                              ESSParameters(**param_kwargs)))
         if strategy == 'mh':
             return finish(MH(event_shape, target, MHKernel(event_size=event_size, **kernel_kwargs), MHParameters(**param_kwargs)))
         cls = MALA if strategy == 'mala' else ULA
@@ -94,6 +100,13 @@ def create_sampler(target, event_shape: Optional[Tuple[int, ...]] = None, flow: 
                              params=JumpNFMCParameters(**param_kwargs),
                              inner_kernel=MHKernel(event_size=event_size, **inner_kernel_kwargs),
                              inner_params=MHParameters(**inner_param_kwargs)))
+    if strategy == 'jump_ess':
+        if negative_log_likelihood is None:
+            raise ValueError("Negative log likelihood must be provided")              # reference: sample.py:199-200
+        return finish(JumpESS(event_shape, target, negative_log_likelihood, kernel=NFMCKernel(event_shape, flow=flow_object),
+                              params=JumpNFMCParameters(**param_kwargs),
+                              inner_kernel=ESSKernel(event_shape=event_shape, **inner_kernel_kwargs),
+                              inner_params=ESSParameters(**inner_param_kwargs)))
     if strategy in ('jump_hmc', 'jump_uhmc'):
         if strategy == 'jump_hmc' and 'n_iterations' not in inner_param_kwargs:
             inner_param_kwargs['n_iterations'] = 5                                   # reference: sample.py:161-162

@@ -19,6 +19,11 @@ struct LocalArgs {
 };
 
 
+struct EssArgs {
+  ChainArgs c;          // c.pot is the negative log-likelihood (the prior is N(0, I))
+  int max_iterations;   // bracket-shrinking rounds per step (ESSParameters.max_ess_step_iterations, mcmc/ess.py:73)
+};
+
 struct JumpArgs {
   ChainArgs c;
   FlowArgs f;
@@ -53,6 +58,7 @@ enum { PASS_FORWARD = 0, PASS_INVERSE = 1, PASS_LOGPROB = 2 };
 
 template <int E> int launch_mala(int pot_kind, bool exact, const LocalArgs& A, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_hmc(int pot_kind, bool exact, const LocalArgs& A, int grid, size_t smem, cudaStream_t s);
+template <int E> int launch_ess(int pot_kind, bool exact, const EssArgs& A, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_flow_pass(const FlowArgs& A, int mode, const float* in, float* out, float* aux, long long n,
                                       int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_flow_sample(const FlowArgs& A, const RngArgs& R, long long chain0, float* x, float* logq,

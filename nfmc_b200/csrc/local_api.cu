@@ -114,6 +114,26 @@ extern "C" int nfmc_mh_steps(const nfmc_potential* pot, float* x, int64_t n, int
   return 0;
 }
 
+extern "C" int nfmc_ess_steps(const nfmc_potential* nll, float* x, int64_t n, int32_t n_steps, int32_t max_iterations,
+                              const nfmc_rng* rng, int64_t chain0, const nfmc_stats* stats, const nfmc_sink* sink,
+                              void* stream) {
+  if (int e = validate_pot(nll)) return e;
+  if (!x || n < 1 || n_steps < 0 || max_iterations < 0) return set_error("ess_steps: bad x/n/n_steps/max_iterations");
+  if (rng && ((rng->normals == nullptr) != (rng->uniforms == nullptr)))
+    return set_error("ess_steps: inject both normals [steps,n,d] and uniforms [steps,n,2+max_iterations], or neither");
+  if (n_steps == 0) return 0;
+  Layout L;
+  if (!layout_for_dim(nll->d, L)) return set_error("ess_steps: unsupported event size");
+  EssArgs A;
+  fill_chain_args(A.c, nll, x, n, n_steps, rng, chain0, stats, sink, L);
+  A.max_iterations = max_iterations;
+  const size_t smem = local_smem_bytes(nll->d, false, 0, L.E);
+  const int grid = grid_for(n, L.gs, 4);
+  cudaStream_t s = (cudaStream_t)stream;
+  NFMC_DISPATCH_E(L.E, { return launch_ess<E>(nll->kind, L.exact, A, grid, smem, s); });
+  return 0;
+}
+
 extern "C" int nfmc_hmc_steps(const nfmc_potential* pot, float* x, int64_t n, int32_t n_steps, float step_size,
                               int32_t n_leapfrog, const float* inv_mass_diag, int32_t adjusted, const nfmc_rng* rng,
                               int64_t chain0, const nfmc_stats* stats, const nfmc_sink* sink, void* stream) {

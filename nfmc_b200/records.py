@@ -141,6 +141,21 @@ class MHKernel(MetropolisKernel):
 
 
 @dataclass
+class ESSKernel(MCMCKernel):
+    """Reference: mcmc/ess.py:67-70.  Only the identity prior covariance (``cov=None``) runs on the device path."""
+    event_shape: tuple = None
+    cov: torch.Tensor = None
+
+    def __post_init__(self):
+        super().__post_init__()
+        if self.cov is not None:
+            raise NotImplementedError("ESSKernel: only cov=None (identity prior covariance) is supported on the device path")
+
+    def __repr__(self):
+        return 'ESS kernel (identity prior covariance)'
+
+
+@dataclass
 class MCMCParameters:
     n_iterations: int = 100
     n_warmup_iterations: int = 100
@@ -155,6 +170,11 @@ class MCMCParameters:
 
     def sampling_mode(self):
         self.tuning = False
+
+
+@dataclass
+class ESSParameters(MCMCParameters):
+    max_ess_step_iterations: int = 5          # reference: mcmc/ess.py:73-75
 
 
 @dataclass

@@ -24,7 +24,7 @@ import torch
 from . import _native as N
 from .flow import Flow
 from .potentials import resolve_target
-from .records import (MHKernel, MHParameters, HMCKernel, HMCParameters, IMHKernel, IMHParameters, JumpNFMCOutput, JumpNFMCParameters,
+from .records import (ESSKernel, ESSParameters, MHKernel, MHParameters, HMCKernel, HMCParameters, IMHKernel, IMHParameters, JumpNFMCOutput, JumpNFMCParameters,
                       LangevinKernel, LangevinParameters, MCMCKernel, MCMCOutput, MCMCParameters, MetropolisKernel,
                       MetropolisParameters, NeuTraKernel, NeuTraParameters, NFMCKernel)
 
@@ -145,6 +145,10 @@ class MetropolisSampler(Sampler):
     def _calls_grads(self, n: int) -> Tuple[int, int]:
         raise NotImplementedError
 
+    def begin_stage(self, ses: DeviceSession, init_normals=None):
+        """Called once before a run of local steps (a ``sample()`` call, or each local stage of Jump NFMC).  ESS
+        restarts from the prior here (mcmc/ess.py:126); every other kernel continues from the session state."""
+
     def run_steps(self, ses: DeviceSession, out: MCMCOutput, n_steps: int, store: bool, normals=None, uniforms=None):
         """Advance all chains ``n_steps`` local steps; book rows / counters into ``out``.  Returns device rows or None."""
         rs = out.running_samples
@@ -179,6 +183,7 @@ class MetropolisSampler(Sampler):
         event_shape = tuple(x0.shape[1:])
         out = MCMCOutput(event_shape, store_samples=self.params.store_samples)
         ses = DeviceSession(x0, event_shape, self.device, self.seed, self.chain0)
+        self.begin_stage(ses)
         T = int(self.params.n_iterations)
         tuning = bool(self.params.tuning)
         chunk = 1 if (tuning or time_limit_seconds is not None or show_progress) else min(T, self.max_fused_steps)
@@ -309,6 +314,44 @@ class MH(MetropolisSampler):
                                       None if sink is None else C.byref(sink), ses.stream))
 
 
+class ESS(MetropolisSampler):
+    """Elliptical slice sampling with prior N(0, I) (reference: mcmc/ess.py:78-127).  ``negative_log_likelihood`` is the
+    potential the slice is taken on; ``target`` is carried for the API only (the reference never evaluates it either).
+    As in the reference, ``x0`` only supplies the number of chains: the run starts from a fresh prior draw
+    (ess.py:126), and every step counts as accepted (ess.py:107)."""
+
+    def __init__(self, event_shape, target, negative_log_likelihood, kernel: Optional[ESSKernel] = None,
+                 params: Optional[ESSParameters] = None):
+        super().__init__(event_shape, target, kernel or ESSKernel(tuple(event_shape)), params or ESSParameters())
+        self.negative_log_likelihood = resolve_target(negative_log_likelihood, self.event_shape)
+
+    @property
+    def name(self):
+        return 'ESS'
+
+    def _calls_grads(self, n):
+        return ((int(self.params.max_ess_step_iterations) + 1) * n, 0)            # ess.py:114-115
+
+    def update_kernel_from_device(self, ses, acc_rate):                             # ess.py:118-119: nothing to tune
+        pass
+
+    def begin_stage(self, ses: DeviceSession, init_normals=None):
+        if init_normals is not None:
+            ses.x.copy_(N.dev_f32(init_normals, ses.device).reshape(ses.n, ses.d))
+            return
+        # Philox stream 3 = prior restarts, keyed by the index of the next local step
+        rng = N.rng_desc(ses.seed, ses.local_step)
+        N.check(N.lib().nfmc_rng_fill(C.byref(rng), 3, ses.chain0, ses.d, ses.n, 1, N.ptr(ses.x), None, ses.stream))
+
+    def _launch(self, ses, n_steps, sink, normals=None, uniforms=None):
+        pot, keep = self.negative_log_likelihood.descriptor(ses.device)
+        rng = N.rng_desc(ses.seed, ses.local_step, normals, uniforms)
+        st = ses.stats()
+        N.check(N.lib().nfmc_ess_steps(C.byref(pot), N.ptr(ses.x), ses.n, n_steps,
+                                       int(self.params.max_ess_step_iterations), C.byref(rng), ses.chain0, C.byref(st),
+                                       None if sink is None else C.byref(sink), ses.stream))
+
+
 class RandomWalk(MH):
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
@@ -357,9 +400,10 @@ class JumpNFMC(Sampler):
         ses.flow_step += 1
 
     def sample(self, x0: torch.Tensor, show_progress: bool = True, time_limit_seconds=None,
-               normals=None, uniforms=None, jump_z=None, jump_uniforms=None) -> MCMCOutput:
+               normals=None, uniforms=None, jump_z=None, jump_uniforms=None, stage_normals=None) -> MCMCOutput:
         """``normals [T,K,n,d]`` / ``uniforms [T,K,n]`` / ``jump_z [T,n,d]`` / ``jump_uniforms [T,n]`` optionally inject
-        the random numbers (parity tests); otherwise they come from the Philox generator."""
+        the random numbers (parity tests); otherwise they come from the Philox generator.  ``stage_normals [T,n,d]``:
+        the prior draw each ESS local stage restarts from (jump_ess only)."""
         p: JumpNFMCParameters = self.params
         inner = self.inner_sampler
         if not inner.params.store_samples:
@@ -380,6 +424,7 @@ class JumpNFMC(Sampler):
             nz = None if normals is None else N.dev_f32(normals[i], dev)
             un = None if uniforms is None else N.dev_f32(uniforms[i], dev)
             need_block = store or (p.fit_nf and i >= p.n_jumps_before_training and K * ses.n * ses.d * 4 <= (2 << 30))
+            inner.begin_stage(ses, None if stage_normals is None else stage_normals[i])
             buf = inner.run_steps(ses, out, K, need_block, nz, un)                  # jump.py:178-189
             if p.fit_nf and i >= p.n_jumps_before_training:                         # jump.py:193-201
                 from .flow_train import train_val_split
@@ -455,6 +500,16 @@ class JumpULA(JumpNFMC):
 class JumpMH(JumpNFMC):
     def __init__(self, event_shape, target, kernel=None, params=None, inner_kernel=None, inner_params=None):
         super().__init__(event_shape, target, MH(event_shape, target, inner_kernel, inner_params), kernel, params)
+
+
+class JumpESS(JumpNFMC):
+    """Reference: jump.py:309-319.  Note the reference quirk kept here: the ESS local stage ignores the state left by
+    the jump and restarts from the prior every outer iteration (ess.py:126)."""
+
+    def __init__(self, event_shape, target, negative_log_likelihood, kernel=None, params=None, inner_kernel=None,
+                 inner_params=None):
+        super().__init__(event_shape, target, ESS(event_shape, target, negative_log_likelihood, inner_kernel, inner_params),
+                         kernel, params)
 
 
 class JumpHMC(JumpNFMC):

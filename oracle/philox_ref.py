@@ -92,3 +92,22 @@ def step_noise(seed: int, stream: int, step: int, chain0: int, n: int, d: int):
             if k < db:
                 normals[:, da + k] = z1
     return normals, uniforms
+
+
+def scalar_uniforms(seed: int, stream: int, step: int, chain0: int, n: int, count: int):
+    """``count`` per-chain uniforms [n, count] (float32) for one step: word i % 4 of counter quad i // 4 on lane j = 0 --
+    the layout the elliptical-slice kernel uses for {u, theta0, bracket draws} with stream = 2 (csrc/ess_kernel.cu)."""
+    key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
+    chains = (np.arange(n, dtype=np.uint64) + np.uint64(chain0)).astype(np.uint32)
+    out = np.zeros((n, count), dtype=np.float32)
+    for q in range((count + 3) // 4):
+        ctr = np.zeros((n, 4), dtype=np.uint32)
+        ctr[:, 0] = np.uint32(q * 32)
+        ctr[:, 1] = np.uint32((stream | ((step >> 32) << 8)) & 0xFFFFFFFF)
+        ctr[:, 2] = np.uint32(step & 0xFFFFFFFF)
+        ctr[:, 3] = chains
+        w = philox4x32_10(ctr, key)
+        for i in range(4):
+            if 4 * q + i < count:
+                out[:, 4 * q + i] = (w[:, i] >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+    return out

@@ -6,7 +6,8 @@ unmodified reference, ``tests/golden/make_golden.py``) through these functions.
 Each function cites the reference lines it follows (paths under /root/reference/nfmc/algorithms/sampling/).
 Random numbers come from a *draw source* so the same numbers can be injected into the CUDA kernels
 (the reference has no injection hook; it draws inline from the global generator in this order:
-``mcmc/langevin.py:63,106``, ``mcmc/hmc.py:100,112``, ``nfmc/jump.py:205,225``, ``nfmc/imh.py:221,229``).
+``mcmc/langevin.py:63,106``, ``mcmc/hmc.py:100,112``, ``mcmc/ess.py:32,35,39,58,126``, ``nfmc/jump.py:205,225``,
+``nfmc/imh.py:221,229``).
 """
 from __future__ import annotations
 
@@ -244,6 +245,52 @@ def run_mh(x0, target, imd, n_steps, draws, adjusted=True, store=True, trace=Fal
     return run_local(x0, lambda x, tr: mh_propose(x, target, imd, draws, adjusted, tr), n_steps, store, trace)
 
 
+def ess_propose(f, nll, max_iterations: int, draws, trace=None):
+    """One elliptical-slice step with identity prior covariance (mcmc/ess.py:12-64) wrapped as ``ESS.propose``
+    (mcmc/ess.py:97-116): the returned mask is all ones ("technical hack", :107), chains whose bracket never
+    produced an acceptable point within ``max_iterations`` keep their state.
+
+    The reference updates ``f`` in place through the alias ``f_proposed = f`` (:43,50); a chain accepted in an earlier
+    round therefore feeds its *new* state into later ``f_prime`` evaluations, whose result is discarded (:50 only
+    assigns to chains not accepted before) -- so the outcome is "first acceptable point wins", restated here without
+    the aliasing.
+    """
+    n = f.shape[0]
+    ev = tuple(f.shape[1:])
+    ones = [1] * len(ev)
+    nu = draws.normal(n, ev)                                                   # :32 (cov = None -> util.py:411)
+    u = draws.uniform(n)                                                       # :35
+    with torch.no_grad():
+        log_y = -nll(f) + torch.log(u)                                         # :36
+    theta = draws.uniform(n).view(n, *ones) * 2 * torch.pi                     # :39
+    theta_min = theta - 2 * torch.pi                                           # :40
+    theta_max = theta.clone()                                                  # :41 (alias of theta; rebound at :59)
+    accepted = torch.zeros(n, dtype=torch.bool)
+    out = f.clone()
+    for _ in range(max_iterations):
+        f_prime = out * torch.cos(theta) + nu * torch.sin(theta)               # :46
+        with torch.no_grad():
+            upd = -nll(f_prime) > log_y                                        # :47
+        take = upd & (~accepted)
+        out[take] = f_prime[take]                                              # :50
+        neg = theta < 0                                                        # :53
+        theta_min = torch.where(neg, theta, theta_min)                         # :54
+        theta_max = torch.where(~neg, theta, theta_max)                        # :55
+        theta = draws.uniform(n).view(n, *ones) * (theta_max - theta_min) + theta_min   # :58-59
+        accepted = accepted | upd                                              # :62
+    if trace is not None:
+        trace.setdefault("ess_accepted", []).append(accepted.clone())
+    mask = torch.ones(n, dtype=torch.bool)                                     # :107
+    return out.detach(), mask, (max_iterations + 1) * n, 0                     # :114-116
+
+
+def run_ess(x0, nll, n_steps, draws, max_iterations: int = 5, store=True, trace=False) -> "RunRef":
+    """``ESS.sample`` (mcmc/ess.py:121-127): the given ``x0`` only supplies the number of chains -- the run starts
+    from a fresh prior draw."""
+    x0 = draws.normal(x0.shape[0], tuple(x0.shape[1:]))                        # :126
+    return run_local(x0, lambda x, tr: ess_propose(x, nll, max_iterations, draws, tr), n_steps, store, trace)
+
+
 def run_local(x0, propose: Callable, n_steps: int, store: bool = True, trace: bool = False) -> RunRef:
     """``MCMCSampler.sample`` (mcmc/base.py:56-102) without tuning; ``propose(x, trace) -> (x', mask, calls, grads)``."""
     n = x0.shape[0]
@@ -288,7 +335,7 @@ def flow_sample_with_logq(flow, n, draws):
 # ---------------------------------------------------------------------------------------------------------
 def run_jump(x0, target, flow, inner: str, n_outer: int, n_inner: int, draws, tau: float, imd: torch.Tensor,
              n_leapfrog: int = 20, adjusted_jumps: bool = True, inner_adjusted: bool = True,
-             store: bool = True, trace: bool = False) -> RunRef:
+             store: bool = True, trace: bool = False, nll=None, max_ess_iterations: int = 5) -> RunRef:
     """``JumpNFMC.sample`` (nfmc/jump.py:156-246), frozen flow (``fit_nf=False``)."""
     n = x0.shape[0]
     out = RunRef(event_shape=tuple(x0.shape[1:]))
@@ -298,6 +345,8 @@ def run_jump(x0, target, flow, inner: str, n_outer: int, n_inner: int, draws, ta
             loc = run_mala(x, target, tau, imd, n_inner, draws, inner_adjusted, store=True, trace=trace)
         elif inner == "hmc":
             loc = run_hmc(x, target, tau, imd, n_leapfrog, n_inner, draws, inner_adjusted, store=True, trace=trace)
+        elif inner == "ess":      # JumpESS (jump.py:309-319): every local stage restarts from the prior (ess.py:126)
+            loc = run_ess(x, nll, n_inner, draws, max_ess_iterations, store=True, trace=trace)
         else:
             raise ValueError(inner)
         out.n_accepted += loc.n_accepted

@@ -31,8 +31,9 @@ for p in (ROOT, os.path.join(ROOT, "oracle", "shim"), "/root/reference"):
 from nfmc.algorithms.sampling.mcmc.hmc import HMC, HMCKernel, HMCParameters          # noqa: E402
 from nfmc.algorithms.sampling.mcmc.langevin import MALA, LangevinKernel, LangevinParameters  # noqa: E402
 from nfmc.algorithms.sampling.mcmc.mh import MH, MHKernel, MHParameters                     # noqa: E402
+from nfmc.algorithms.sampling.mcmc.ess import ESS, ESSKernel, ESSParameters                 # noqa: E402
 from nfmc.algorithms.sampling.nfmc.imh import FixedIMH, IMHKernel, IMHParameters      # noqa: E402
-from nfmc.algorithms.sampling.nfmc.jump import JumpMALA, JumpHMC, JumpNFMCParameters  # noqa: E402
+from nfmc.algorithms.sampling.nfmc.jump import JumpMALA, JumpHMC, JumpESS, JumpNFMCParameters  # noqa: E402
 from nfmc.algorithms.sampling.nfmc.neutra import NeuTraHMC, NeuTraKernel, NeuTraParameters  # noqa: E402
 from nfmc.algorithms.sampling.base import NFMCKernel                                   # noqa: E402
 
@@ -211,6 +212,30 @@ def main():
     with Tape() as t:
         out = s.sample(x0.clone(), show_progress=False)
     cases["mh_gm"] = pack(out, t, x0, dict(pot="gm", imd=imd.numpy(), K=K))
+
+    # ---- elliptical slice sampling: N(0, I) prior x funnel "likelihood" (x0 only supplies n: ess.py:126) ----------
+    torch.manual_seed(20)
+    d, n, K, M = 7, 6, 4, 5
+    nll = make_potential_ref("fn", (d,))
+    x0 = torch.randn(n, d)
+    s = ESS((d,), nll, nll, ESSKernel(event_shape=(d,)), ESSParameters(n_iterations=K, max_ess_step_iterations=M))
+    with Tape() as t:
+        out = s.sample(x0.clone(), show_progress=False)
+    cases["ess_fn"] = pack(out, t, x0, dict(pot="fn", K=K, M=M))
+
+    # ---- jump_ess: every local stage restarts from the prior; jump against the mixture target -----------------
+    torch.manual_seed(21)
+    d, n, T, K, M = 6, 5, 2, 3, 4
+    target = make_potential_ref("gm", (d,))
+    nll = make_potential_ref("rb", (d,))
+    flow = make_flow((d,), n_layers=2, perturb=0.1, seed=104)
+    x0 = torch.randn(n, d)
+    s = JumpESS((d,), target, nll, kernel=NFMCKernel((d,), flow=flow), params=JumpNFMCParameters(n_iterations=T),
+                inner_kernel=ESSKernel(event_shape=(d,)),
+                inner_params=ESSParameters(n_iterations=K, max_ess_step_iterations=M))
+    with Tape() as t:
+        out = s.sample(x0.clone(), show_progress=False)
+    cases["jump_ess_gm"] = pack(out, t, x0, dict(pot="gm", nll="rb", K=K, T=T, M=M, **flow_arrays(flow, 2, 2, 4)))
 
     for name, arrays in cases.items():
         path = os.path.join(HERE, f"{name}.npz")

@@ -9,7 +9,8 @@ from oracle.realnvp_ref import FlowRef, RealNVPRef
 from oracle.samplers_ref import TapeDraws
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["mala_g0", "mala_fn", "hmc_g1", "hmc_rb", "jump_mala_g0", "jump_hmc_gm", "imh_rb", "neutra_hmc_fn", "mh_gm"]
+CASES = ["mala_g0", "mala_fn", "hmc_g1", "hmc_rb", "jump_mala_g0", "jump_hmc_gm", "imh_rb", "neutra_hmc_fn", "mh_gm",
+         "ess_fn", "jump_ess_gm"]
 
 
 def load_case(name):
@@ -21,7 +22,8 @@ def load_case(name):
 
 
 def tape(g):
-    return TapeDraws(g["normals"], g["uniforms"])
+    # the reference draws some uniforms as [n, 1] (mcmc/ess.py:39,58): same numbers, flattened for the tape
+    return TapeDraws(g["normals"], [u.reshape(-1) for u in g["uniforms"]])
 
 
 def oracle_flow(g):

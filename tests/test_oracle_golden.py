@@ -67,3 +67,19 @@ def test_mh():
     g = load_case("mh_gm")
     run = R.run_mh(torch.from_numpy(g["x0"]), oracle_target(g), torch.from_numpy(g["imd"]), int(g["K"]), tape(g))
     _check(g, run)
+
+
+def test_ess():
+    g = load_case("ess_fn")
+    run = R.run_ess(torch.from_numpy(g["x0"]), oracle_target(g), int(g["K"]), tape(g), max_iterations=int(g["M"]))
+    _check(g, run)
+
+
+def test_jump_ess():
+    from oracle.potentials_ref import make_potential_ref
+    g = load_case("jump_ess_gm")
+    d = g["x0"].shape[1]
+    run = R.run_jump(torch.from_numpy(g["x0"]), oracle_target(g), oracle_flow(g), "ess", int(g["T"]), int(g["K"]),
+                     tape(g), 0.0, torch.ones(d), nll=make_potential_ref(str(g["nll"]), (d,)),
+                     max_ess_iterations=int(g["M"]))
+    _check(g, run, jump=True)
