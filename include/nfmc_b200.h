@@ -180,6 +180,39 @@ NFMC_API int nfmc_neutra_potential(const nfmc_potential* pot, const nfmc_realnvp
 NFMC_API int nfmc_rng_fill(const nfmc_rng* rng, int32_t stream_id, int64_t chain0, int32_t d, int64_t n, int32_t n_steps,
                   float* normals, float* uniforms, void* stream);
 
+/* ---- flow training on the device (register-resident conditioner path: n_linear = 2, hidden <= 8) -----------------
+ * Replaces the autograd + AdamW loop behind flow.fit (nfmc/jump.py:139-151,201; nfmc/imh.py:171-175) and
+ * flow.variational_fit (nfmc/imh.py:67-72; nfmc/neutra.py:84-91); torchflows itself is absent, its optimiser settings
+ * are the kwargs the reference passes (lr = 0.05, AdamW).
+ * theta = the module parameters in state_dict order:
+ *   affine_0.value[d][2] | Lc x { W1[H][d/2] b1[H] Wl[2(d-d/2)][H] bl[2(d-d/2)] actnorm.value[d][2] } |
+ *   affine_T.value[d][2] | actnorm_T.value[d][2]                      (nfmc_flow_param_count floats, -1 = unsupported) */
+NFMC_API int64_t nfmc_flow_param_count(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden);
+/* theta -> kernel blob (same layout nfmc_b200.flow.pack_realnvp produces on the host) */
+NFMC_API int nfmc_flow_pack(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden, const float* theta, float* blob,
+                   void* stream);
+/* maximum likelihood: *loss (+)= -sum_i log q(x[rows[i]]), grad_blob[blob_floats] (+)= its gradient in blob layout;
+ * rows may be NULL (= 0..n-1); accumulate = 0 zeroes grad_blob and *loss first */
+NFMC_API int nfmc_flow_nll_grad(const nfmc_realnvp* flow, const float* x, const int64_t* rows, int64_t n, float* grad_blob,
+                       double* loss, int32_t accumulate, void* stream);
+/* reverse KL: z_i ~ N(0, I) (Philox stream 1 at rng->step0, or rng->normals [n, d]), x_i = T^-1(z_i),
+ * *loss (+)= sum_i [log q(x_i) + U(x_i)], grad_blob (+)= its gradient (through x_i, grad U included) */
+NFMC_API int nfmc_flow_kl_grad(const nfmc_potential* pot, const nfmc_realnvp* flow, const nfmc_rng* rng, int64_t chain0,
+                      int64_t n, float* grad_blob, double* loss, int32_t accumulate, void* stream);
+/* blob-layout gradient -> gradient with respect to theta (chain rule through the merged affines), times `scale` */
+NFMC_API int nfmc_flow_grad_unpack(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden, const float* theta,
+                          const float* grad_blob, float scale, float* grad_theta, void* stream);
+/* one AdamW update (torch.optim.AdamW semantics); step counts from 1 */
+NFMC_API int nfmc_adamw_step(float* theta, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int32_t step, void* stream);
+/* one epoch of minibatch maximum likelihood on one GPU: for each batch of perm[n]: pack, loss + gradient, unpack with
+ * 1/batch, AdamW (steps step0+1, ...); losses[batch] = summed loss of the batch; blob / grad_blob / grad_theta are
+ * scratch of blob_floats / blob_floats / param_count floats */
+NFMC_API int nfmc_flow_fit_epoch(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden, float* theta, float* exp_avg,
+                        float* exp_avg_sq, float* blob, float* grad_blob, float* grad_theta, double* losses,
+                        const float* x, const int64_t* perm, int64_t n, int64_t batch_size, float lr, float beta1,
+                        float beta2, float eps, float weight_decay, int32_t step0, void* stream);
+
 /* ---- host-buffer entry point (end-to-end measurement; the call a reference-side plugin would make) ------
  * Runs `n_outer` iterations of [n_inner local steps (kind 0 = MALA, 1 = HMC) + one NF jump] on host data:
  * copies x_host [n,d] to the device, runs, copies the final state back into x_host, and returns the pooled

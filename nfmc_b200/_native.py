@@ -81,6 +81,14 @@ SIGNATURES = {
     "nfmc_neutra_hmc_steps": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _vp, _i64, _i32, _f32, _i32, _vp,
                                         P(RngDesc), _i64, P(StatsDesc), P(SinkDesc), _vp]),
     "nfmc_neutra_potential": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _vp, _vp, _vp, _i64, _vp]),
+    "nfmc_flow_param_count": (_i64, [_i32, _i32, _i32, _i32]),
+    "nfmc_flow_pack": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "nfmc_flow_nll_grad": (C.c_int, [P(RealNVPDesc), _vp, _vp, _i64, _vp, _vp, _i32, _vp]),
+    "nfmc_flow_kl_grad": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), P(RngDesc), _i64, _i64, _vp, _vp, _i32, _vp]),
+    "nfmc_flow_grad_unpack": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _f32, _vp, _vp]),
+    "nfmc_adamw_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp]),
+    "nfmc_flow_fit_epoch": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64,
+                                      _f32, _f32, _f32, _f32, _f32, _i32, _vp]),
     "nfmc_rng_fill": (C.c_int, [P(RngDesc), _i32, _i64, _i32, _i64, _i32, _vp, _vp, _vp]),
     "nfmc_jump_workspace_bytes": (_i64, [_i32, _i64, _i64]),
     "nfmc_jump_sample_host": (C.c_int, [P(PotentialDesc), _vp, _i64, P(RealNVPDesc), _vp, _vp, _i64, _i32, _i32, _i32,

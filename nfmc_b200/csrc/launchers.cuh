@@ -54,6 +54,20 @@ struct NeutraArgs {
   int n_leapfrog;
 };
 
+struct TrainArgs {
+  FlowArgs f;             // blob = packed parameters (small conditioner path only)
+  float* grad;            // [blob_floats] gradient accumulator in blob layout
+  double* loss;           // [1] += sum over rows of the per-row loss (or nullptr)
+  const float* x;         // maximum likelihood: data [*, d]
+  const long long* rows;  // maximum likelihood: optional row indices [n] into x (a shuffled minibatch)
+  long long n;            // rows in this launch
+  int kl;                 // 1: reverse KL (base draw from rng, potential below); 0: maximum likelihood
+  int pot_kind;
+  PotParams pot;
+  RngArgs rng;
+  long long chain0;
+};
+
 enum { PASS_FORWARD = 0, PASS_INVERSE = 1, PASS_LOGPROB = 2 };
 
 template <int E> int launch_mala(int pot_kind, bool exact, const LocalArgs& A, int grid, size_t smem, cudaStream_t s);
@@ -63,6 +77,7 @@ template <int E> int launch_flow_pass(const FlowArgs& A, int mode, const float* 
                                       int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_flow_sample(const FlowArgs& A, const RngArgs& R, long long chain0, float* x, float* logq,
                                         long long n, int grid, size_t smem, cudaStream_t s);
+template <int E> int launch_flow_train(const TrainArgs& A, int grid, cudaStream_t s);
 template <int E> int launch_jump(const JumpArgs& A, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_jump_accept(const AcceptArgs& A, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_neutra_hmc(const NeutraArgs& A, int grid, size_t smem, cudaStream_t s);

@@ -1,0 +1,241 @@
+// train_kernels.cu -- RealNVP training on the device (one translation unit per E): per-row loss and the gradient with
+// respect to every flow parameter for the two objectives the reference trains flows with,
+//   * maximum likelihood,  L = -sum_i log q(x_i)             -- Flow.fit            (jump.py:139-151,201; imh.py:171-175)
+//   * reverse KL,          L =  sum_i [log q(x_i) + U(x_i)],  x_i = T^-1(z_i), z_i ~ N(0, I)
+//                                                            -- Flow.variational_fit (imh.py:67-72; neutra.py:84-91)
+// for the register-resident conditioner path (M = 2, H <= 8: every default conditioner).
+//
+// No activation is stored.  After the pass that produces the loss (x -> z for maximum likelihood, z -> x for reverse
+// KL) the chain walks the layers back in the opposite order; a layer's input is re-derived from its output (the flow is
+// invertible) while the cotangent is pulled through it and the layer's parameter gradients are emitted.  Both
+// directions share one formulation: in pass direction every layer acts as  y = r*x + s  and contributes  -log r  to the
+// loss, with (r, s) = (alpha, beta) going x -> z and (1/alpha, -beta/alpha) going z -> x; so
+//   dL/dr = g_y*x - 1/r,  dL/ds = g_y,  g_x = g_y*r,
+// converted to (dalpha, dbeta) and, for couplings, pushed through the conditioner MLP.
+//
+// Gradients are accumulated IN BLOB LAYOUT (the forward tables of the merged elementwise affines and the packed
+// conditioner weights): lanes of a warp that own the same parameter are summed with shuffles, then one atomicAdd per
+// warp and parameter.  train_param_kernels (api side) maps blob gradients back to module parameters.
+#include "launchers.cuh"
+
+#ifndef NFMC_ONLY_E
+#error "compile with -DNFMC_ONLY_E=<slots per half>"
+#endif
+
+namespace nfmc {
+
+// v = this lane's contribution to a parameter that is owned by lane position j (same parameter on lanes j, j+gs, ...)
+__device__ __forceinline__ void emit(float* G, int off, float v, const Geom& g, bool ok) {
+  const float s = across_groups_sum(v, g.gs);
+  if (g.lane < g.gs && ok) atomicAdd(G + off, s);
+}
+// v = a per-chain value (identical on the lanes of a group): counted once per group
+__device__ __forceinline__ void emit_chain(float* G, int off, float v, const Geom& g) {
+  const float s = across_groups_sum(g.j == 0 ? v : 0.f, g.gs);
+  if (g.lane == 0) atomicAdd(G + off, s);
+}
+
+// (y, gy) = output of the layer and dL/dy  ->  (x, gx); returns (dalpha, dbeta)
+__device__ __forceinline__ float2 affine_back(bool inv, float act, float alpha, float beta, float ralpha, float& y, float& gy) {
+  const float r = inv ? ralpha : alpha;
+  const float xin = inv ? fmaf(alpha, y, beta) : (y - beta) * ralpha;
+  const float dr = gy * xin - act * (inv ? alpha : ralpha);
+  const float ds = gy;
+  const float dal = inv ? (ds * beta - dr) * ralpha * ralpha : dr;
+  const float dbe = inv ? -ds * ralpha : ds;
+  y = xin;
+  gy *= r;
+  return make_float2(dal, dbe);
+}
+
+template <int E>
+__device__ __forceinline__ void affine_train(const FlowDesc& F, const Geom& g, int a, bool inv, float act, float (&lo)[E],
+                                             float (&hi)[E], float (&glo)[E], float (&ghi)[E], float* G) {
+  const int fw = a * 4 * F.d, iv = fw + 2 * F.d;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int k = g.j + g.gs * e;
+    const bool vl = k < g.da, vh = k < g.db;
+    const int il = 2 * (vl ? k : 0), ih = 2 * (g.da + (vh ? k : 0));
+    const float2 pl = ldp2<false>(F, fw + il), ph = ldp2<false>(F, fw + ih);
+    const float rl = ldp<false>(F, iv + il), rh = ldp<false>(F, iv + ih);
+    float2 dl = affine_back(inv, act, pl.x, pl.y, rl, lo[e], glo[e]);
+    float2 dh = affine_back(inv, act, ph.x, ph.y, rh, hi[e], ghi[e]);
+    if (!vl) { lo[e] = 0.f; glo[e] = 0.f; dl = make_float2(0.f, 0.f); }
+    if (!vh) { hi[e] = 0.f; ghi[e] = 0.f; dh = make_float2(0.f, 0.f); }
+    emit(G, fw + il, dl.x, g, vl);
+    emit(G, fw + il + 1, dl.y, g, vl);
+    emit(G, fw + ih, dh.x, g, vh);
+    emit(G, fw + ih + 1, dh.y, g, vh);
+  }
+}
+
+// conditioner backward with weight gradients (small path); dsrc[e] += input-VJP
+template <int E>
+__device__ __forceinline__ void cond_backward_small_train(const FlowDesc& F, const Geom& g, int W, int shift, int nt_main,
+                                                          bool has_x, const float (&hid)[kSmallH], const float (&src)[E],
+                                                          const float (&dua)[E], const float (&dub)[E], float dua_x,
+                                                          float dub_x, float (&dsrc)[E], float* G) {
+  const int da = F.da, db = F.db, H = F.H;
+  const int b1 = W + da * kSmallH;
+  const int Wl = b1 + kSmallH;
+  const int bl = Wl + db * 2 * kSmallH;
+  float acc[kSmallH];
+#pragma unroll
+  for (int h = 0; h < kSmallH; ++h) acc[h] = 0.f;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int t = g.j + g.gs * e;
+    const bool ok = t < nt_main;
+    const float va = ok ? dua[e] : 0.f, vb = ok ? dub[e] : 0.f;
+    const int w = Wl + (ok ? t : 0) * 2 * kSmallH;
+#pragma unroll
+    for (int h = 0; h < kSmallH; ++h) {
+      acc[h] = fmaf(ldp<false>(F, w + h), va, fmaf(ldp<false>(F, w + kSmallH + h), vb, acc[h]));
+      if (h < H) {                                   // d/dWl[t][c][h] = hid[h] * d out[t][c]
+        emit(G, w + h, hid[h] * va, g, ok);
+        emit(G, w + kSmallH + h, hid[h] * vb, g, ok);
+      }
+    }
+    emit(G, bl + 2 * (ok ? t : 0), va, g, ok);
+    emit(G, bl + 2 * (ok ? t : 0) + 1, vb, g, ok);
+  }
+  if (has_x) {                                       // the extra target t = da lives on lane j = 0 of each group
+    const int w = Wl + da * 2 * kSmallH;
+    const float va = g.j == 0 ? dua_x : 0.f, vb = g.j == 0 ? dub_x : 0.f;
+#pragma unroll
+    for (int h = 0; h < kSmallH; ++h) {
+      acc[h] = fmaf(ldp<false>(F, w + h), va, fmaf(ldp<false>(F, w + kSmallH + h), vb, acc[h]));
+      if (h < H) {
+        emit_chain(G, w + h, hid[h] * dua_x, g);
+        emit_chain(G, w + kSmallH + h, hid[h] * dub_x, g);
+      }
+    }
+    emit_chain(G, bl + 2 * da, dua_x, g);
+    emit_chain(G, bl + 2 * da + 1, dub_x, g);
+  }
+  float dpre[kSmallH];
+#pragma unroll
+  for (int h = 0; h < kSmallH; ++h) {
+    dpre[h] = group_sum(acc[h], g.gs) * (1.f - hid[h] * hid[h]);
+    if (h < H) emit_chain(G, b1 + h, dpre[h], g);
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int ks = g.j + g.gs * e - shift;
+    const bool ok = ks >= 0 && ks < da;
+    const int w = W + (ok ? ks : 0) * kSmallH;
+    const float v = ok ? src[e] : 0.f;
+    float s = 0.f;
+#pragma unroll
+    for (int h = 0; h < kSmallH; ++h) {
+      s = fmaf(ldp<false>(F, w + h), dpre[h], s);
+      if (h < H) emit(G, w + h, v * dpre[h], g, ok);  // d/dW1[h][ks] = src[ks] * dpre[h]
+    }
+    if (ok) dsrc[e] += s;
+  }
+}
+
+template <int E>
+__device__ __forceinline__ void coupling_train(const FlowDesc& F, const Geom& g, int l, bool inv, float act, float (&lo)[E],
+                                               float (&hi)[E], float (&glo)[E], float (&ghi)[E], float* G) {
+  float ua[E], ub[E], ua_x = 0.f, ub_x = 0.f, dua_x = 0.f, dub_x = 0.f;
+  float hid[kSmallH];
+  const bool src_is_hi = (l & 1) == 0;
+  const int shift = src_is_hi ? F.db - F.da : 0;
+  const bool has_x = shift > 0;
+  const int nt_main = src_is_hi ? F.da : F.db;
+  const int Woff = F.off_coupling + l * F.coupling_stride;
+  swap_halves(lo, hi, src_is_hi);
+  swap_halves(glo, ghi, src_is_hi);
+  cond_forward_small<E, false, false>(F, g, Woff, lo, shift, nt_main, has_x, hid, ua, ub, ua_x, ub_x);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    float d_ua = 0.f, d_ub = 0.f;
+    if (g.j + g.gs * e < nt_main) {
+      float al, be;
+      affine_coef(ua[e], ub[e], al, be);
+      const float2 dd = affine_back(inv, act, al, be, __fdividef(1.f, al), hi[e], ghi[e]);
+      d_ua = dd.x * (al - kMinScale) * 0.5f;
+      d_ub = 0.5f * dd.y;
+    }
+    ua[e] = d_ua;
+    ub[e] = d_ub;
+  }
+  if (has_x && g.j == 0) {
+    float al, be;
+    affine_coef(ua_x, ub_x, al, be);
+    const float2 dd = affine_back(inv, act, al, be, __fdividef(1.f, al), lo[0], glo[0]);
+    dua_x = dd.x * (al - kMinScale) * 0.5f;
+    dub_x = 0.5f * dd.y;
+  }
+  cond_backward_small_train<E>(F, g, Woff, shift, nt_main, has_x, hid, lo, ua, ub, dua_x, dub_x, glo, G);
+  swap_halves(lo, hi, src_is_hi);
+  swap_halves(glo, ghi, src_is_hi);
+}
+
+// walk the layers back: `inv` = direction of the pass that produced (lo, hi)
+template <int E>
+__device__ __forceinline__ void flow_train_sweep(const FlowDesc& F, const Geom& g, bool inv, float act, float (&lo)[E],
+                                                 float (&hi)[E], float (&glo)[E], float (&ghi)[E], float* G) {
+  const int n_ops = 2 * F.Lc + 1;
+#pragma unroll 1
+  for (int i = 0; i < n_ops; ++i) {
+    const int op = inv ? i : n_ops - 1 - i;
+    if (op & 1) coupling_train<E>(F, g, op >> 1, inv, act, lo, hi, glo, ghi, G);
+    else affine_train<E>(F, g, op >> 1, inv, act, lo, hi, glo, ghi, G);
+  }
+}
+
+template <int E>
+__global__ void __launch_bounds__(kThreads, 2) flow_train_kernel(const TrainArgs A) {
+  const Geom g = make_geom(A.f.d, A.f.gs);
+  const FlowDesc F = make_flow_desc(A.f.blob, A.f.d, A.f.Lc, A.f.M, A.f.H);
+  const int cpc = kThreads / A.f.gs;
+  const long long tiles = (A.n + cpc - 1) / cpc;
+  const bool flip = (A.f.Lc & 1) != 0;
+  double loss = 0.0;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long chain_raw = tile * cpc + threadIdx.x / A.f.gs;
+    const bool active = chain_raw < A.n;
+    const long long chain = active ? chain_raw : A.n - 1;
+    const float act = active ? 1.f : 0.f;
+    float lo[E], hi[E], glo[E], ghi[E];
+    float li;
+    if (!A.kl) {
+      const long long row = A.rows ? A.rows[chain] : chain;
+      load_chain(A.x + row * (long long)A.f.d, g, lo, hi);
+      const float ld = flow_pass<E, false, false, true>(F, g, false, lo, hi, nullptr);
+      li = -(base_log_prob(g, lo, hi) + ld);                                   // -log q(x)
+#pragma unroll
+      for (int e = 0; e < E; ++e) { glo[e] = act * lo[e]; ghi[e] = act * hi[e]; }   // d/dz of |z|^2 / 2
+      flow_train_sweep<E>(F, g, false, act, lo, hi, glo, ghi, A.grad);
+    } else {
+      draw_base(A.rng, g, flip, A.n, chain, A.chain0, 0, lo, hi);
+      const float lbase = base_log_prob(g, lo, hi);
+      const float ld_inv = flow_pass<E, false, false, true>(F, g, true, lo, hi, nullptr);
+      const PotCtx c = pot_prepare_rt<E>(A.pot_kind, A.pot, g, lo, hi);
+      li = lbase - ld_inv + c.u;                                                // log q(x) + U(x)
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int kk = g.j + g.gs * e;
+        pot_grad_rt(A.pot_kind, A.pot, c, g, kk, lo[e], hi[e], glo[e], ghi[e]);
+        glo[e] = kk < g.da ? act * glo[e] : 0.f;
+        ghi[e] = kk < g.db ? act * ghi[e] : 0.f;
+      }
+      flow_train_sweep<E>(F, g, true, act, lo, hi, glo, ghi, A.grad);
+    }
+    if (active && g.j == 0) loss += (double)li;
+  }
+  for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+  if ((threadIdx.x & 31) == 0 && A.loss) atomicAdd(A.loss, loss);
+}
+
+template <int E>
+int launch_flow_train(const TrainArgs& A, int grid, cudaStream_t s) {
+  flow_train_kernel<E><<<grid, kThreads, 0, s>>>(A);
+  return check_cuda(cudaGetLastError(), "flow_train_kernel launch");
+}
+template int launch_flow_train<NFMC_ONLY_E>(const TrainArgs&, int, cudaStream_t);
+
+}  // namespace nfmc

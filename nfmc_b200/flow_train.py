@@ -1,11 +1,14 @@
 """Flow training on the device: ``Flow.fit`` (maximum likelihood) and ``Flow.variational_fit`` (reverse KL).
 
-Status ("next" row): functional, **library-backed**.  The sampling hot path is the
-hand-written kernels; training needs gradients with respect to the *parameters* (wgrad), which the kernels do not
-provide yet, so the optimisation step here runs a differentiable torch restatement of the same RealNVP arithmetic on
-the GPU (autograd + AdamW).  What is native already: the target's value / gradient inside ``variational_fit`` come
-from ``nfmc_potential_eval`` through a custom autograd function, and after every fit the packed blobs are rebuilt so
-the samplers keep using the CUDA kernels.  Multi-GPU: gradients are all-reduced (NCCL) once per optimiser step.
+Status: for the default conditioners (2 linear layers, <= 8 hidden units -- the
+register-resident kernel path) training runs **natively**: ``csrc/train_kernels.cu`` computes the loss and the gradient
+with respect to every flow parameter in one launch (reversible backward sweep, no stored activations),
+``csrc/train_api.cu`` packs the parameters, maps the gradient back to module order and applies AdamW; one C call per
+epoch on a single GPU, per-step calls with an NCCL all-reduce of the gradient in between on several.  Only the one-off
+data-dependent ActNorm initialisation uses the torch restatement below.  Other conditioner shapes (wide / deep) fall
+back to the **library-backed** loop (torch autograd + AdamW on the GPU over the same restatement); the target's value /
+gradient inside ``variational_fit`` then come from ``nfmc_potential_eval`` through a custom autograd function.  After
+every fit the packed blobs are rebuilt so the samplers keep using the CUDA kernels.
 
 Reference call sites: ``flow.fit`` -- /root/reference/nfmc/algorithms/sampling/nfmc/jump.py:139-151,201 and
 nfmc/imh.py:171-175; ``flow.variational_fit`` -- nfmc/imh.py:67-72 and nfmc/neutra.py:84-91;
@@ -15,13 +18,17 @@ nfmc/imh.py:171-175; ``flow.variational_fit`` -- nfmc/imh.py:67-72 and nfmc/neut
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
+import os
 import time
 from copy import deepcopy
-from typing import Callable, Tuple
+from typing import Callable, Optional, Tuple
 
 import torch
 import torch.distributed as dist
+
+from . import _native as N
 
 MIN_SCALE = 1e-3
 _LOG_ONE_MINUS_M = math.log(1.0 - MIN_SCALE)
@@ -110,7 +117,9 @@ class _PotentialFn(torch.autograd.Function):
 
 def target_log_prob_fn(potential) -> Callable:
     """``lambda v: -target(v)`` of the reference (imh.py:68, neutra.py:85), differentiable through the native kernel."""
-    return lambda v: _PotentialFn.apply(v.reshape(v.shape[0], -1), potential)
+    fn = lambda v: _PotentialFn.apply(v.reshape(v.shape[0], -1), potential)   # noqa: E731
+    fn.potential = potential          # lets variational_fit take the native reverse-KL kernel
+    return fn
 
 
 def _sync_grads(params):
@@ -124,6 +133,200 @@ def _sync_grads(params):
                 n = p.grad.numel()
                 p.grad.copy_(flat[off:off + n].view_as(p.grad))
                 off += n
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# native training (csrc/train_kernels.cu, csrc/train_api.cu)
+# ---------------------------------------------------------------------------------------------------------------
+ADAMW = dict(beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01)     # torch.optim.AdamW defaults
+
+
+def native_supported(flow) -> bool:
+    """The native kernels cover conditioners with 2 linear layers and <= 8 hidden units (every default conditioner)."""
+    if os.environ.get("NFMC_B200_LIBRARY_TRAINING") == "1":
+        return False
+    bij = flow.bijection
+    M, H = bij.conditioner_shape()
+    same = all((c.n_linear, c.n_hidden) == (M, H) for c in bij.couplings())
+    return same and N.lib().nfmc_flow_param_count(bij.n_dim, bij.n_coupling, M, H) > 0
+
+
+def _world() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+class NativeTrainer:
+    """Flat parameter vector + AdamW state on the device, driven through the C ABI."""
+
+    def __init__(self, flow, dev, lr: float):
+        self.flow, self.dev, self.lr = flow, dev, float(lr)
+        bij = flow.bijection
+        self.d, self.Lc = bij.n_dim, bij.n_coupling
+        self.M, self.H = bij.conditioner_shape()
+        self.params = [p for p in bij.parameters()]
+        self.theta = torch.cat([p.detach().reshape(-1) for p in self.params]).to(dev, torch.float32).contiguous()
+        P = N.lib().nfmc_flow_param_count(self.d, self.Lc, self.M, self.H)
+        if P != self.theta.numel():
+            raise RuntimeError(f"parameter count mismatch: module {self.theta.numel()} vs native {P}")
+        from .flow import blob_floats
+        nb = blob_floats(self.d, self.Lc, self.M, self.H)
+        self.m = torch.zeros_like(self.theta)
+        self.v = torch.zeros_like(self.theta)
+        self.blob = torch.empty(nb, device=dev, dtype=torch.float32)
+        self.gblob = torch.empty(nb, device=dev, dtype=torch.float32)
+        self.gtheta = torch.empty_like(self.theta)
+        self.loss = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.step = 0
+        self.stream = N.stream_ptr(dev)
+
+    def desc(self) -> N.RealNVPDesc:
+        return N.RealNVPDesc(self.d, self.Lc, self.M, self.H, self.blob.data_ptr(), self.blob.numel())
+
+    def pack(self):
+        N.check(N.lib().nfmc_flow_pack(self.d, self.Lc, self.M, self.H, N.ptr(self.theta), N.ptr(self.blob), self.stream))
+
+    def unpack(self, scale: float):
+        N.check(N.lib().nfmc_flow_grad_unpack(self.d, self.Lc, self.M, self.H, N.ptr(self.theta), N.ptr(self.gblob),
+                                              float(scale), N.ptr(self.gtheta), self.stream))
+
+    def sync_grad(self):
+        if _world() > 1:
+            dist.all_reduce(self.gtheta)
+            self.gtheta /= _world()
+
+    def adamw(self):
+        self.step += 1
+        N.check(N.lib().nfmc_adamw_step(N.ptr(self.theta), N.ptr(self.gtheta), N.ptr(self.m), N.ptr(self.v),
+                                        self.theta.numel(), self.lr, ADAMW["beta1"], ADAMW["beta2"], ADAMW["eps"],
+                                        ADAMW["weight_decay"], self.step, self.stream))
+
+    def nll_step(self, x: torch.Tensor, rows: Optional[torch.Tensor], n: int):
+        """One optimiser step on ``x[rows]`` (maximum likelihood); ``self.loss`` holds the summed loss afterwards."""
+        self.pack()
+        d = self.desc()
+        N.check(N.lib().nfmc_flow_nll_grad(C.byref(d), N.ptr(x), None if rows is None else rows.data_ptr(), n,
+                                           N.ptr(self.gblob), N.ptr(self.loss), 0, self.stream))
+        self.unpack(1.0 / n)
+        self.sync_grad()
+        self.adamw()
+
+    def nll_epoch(self, x: torch.Tensor, perm: torch.Tensor, batch_size: int, losses: torch.Tensor):
+        n = perm.numel()
+        if _world() > 1:
+            for b, i in enumerate(range(0, n, batch_size)):
+                m = min(batch_size, n - i)
+                self.nll_step(x, perm[i:i + m], m)
+                losses[b] = self.loss[0]
+            return
+        N.check(N.lib().nfmc_flow_fit_epoch(self.d, self.Lc, self.M, self.H, N.ptr(self.theta), N.ptr(self.m), N.ptr(self.v),
+                                            N.ptr(self.blob), N.ptr(self.gblob), N.ptr(self.gtheta), N.ptr(losses),
+                                            N.ptr(x), perm.data_ptr(), n, batch_size, self.lr, ADAMW["beta1"],
+                                            ADAMW["beta2"], ADAMW["eps"], ADAMW["weight_decay"], self.step, self.stream))
+        self.step += (n + batch_size - 1) // batch_size
+
+    def kl_step(self, potential, n_samples: int, seed: int, step0: int, z: Optional[torch.Tensor] = None):
+        self.pack()
+        d = self.desc()
+        pot, keep = potential.descriptor(self.dev)
+        rng = N.rng_desc(seed, step0, z, None)
+        chain0 = (dist.get_rank() * n_samples) if _world() > 1 else 0
+        N.check(N.lib().nfmc_flow_kl_grad(C.byref(pot), C.byref(d), C.byref(rng), chain0, n_samples, N.ptr(self.gblob),
+                                          N.ptr(self.loss), 0, self.stream))
+        self.unpack(1.0 / n_samples)
+        self.sync_grad()
+        self.adamw()
+
+    def mean_nll(self, x: torch.Tensor) -> torch.Tensor:
+        """-mean log q(x) under the current theta (device scalar)."""
+        self.pack()
+        d = self.desc()
+        lq = torch.empty(x.shape[0], device=self.dev, dtype=torch.float32)
+        N.check(N.lib().nfmc_flow_log_prob(C.byref(d), N.ptr(x), N.ptr(lq), x.shape[0], self.stream))
+        return -lq.double().mean()
+
+    @torch.no_grad()
+    def write_back(self, theta: Optional[torch.Tensor] = None):
+        theta = self.theta if theta is None else theta
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            p.copy_(theta[off:off + k].view_as(p))
+            off += k
+
+
+def _init_actnorms(flow, x_first: torch.Tensor):
+    """One-off data-dependent ActNorm initialisation (torch restatement; runs once per flow lifetime)."""
+    from .flow import ActNorm
+    if any(isinstance(l, ActNorm) and not bool(l.initialised) for l in flow.bijection.layers):
+        with torch.no_grad():
+            forward_autograd(flow.bijection, x_first, training=True)
+
+
+def _fit_native(flow, dev, x_train, x_val, n_epochs, lr, batch_size, shuffle, keep_best_weights, early_stopping,
+                early_stopping_threshold, time_limit_seconds):
+    n = len(x_train)
+    _init_actnorms(flow, x_train[:batch_size])
+    tr = NativeTrainer(flow, dev, lr)
+    n_batches = (n + batch_size - 1) // batch_size
+    losses = torch.zeros(n_batches, device=dev, dtype=torch.float64)
+    ref = x_val if x_val is not None and len(x_val) else x_train
+    best, since_best = math.inf, 0
+    best_theta = tr.theta.clone() if keep_best_weights else None
+    t0 = time.time()
+    try:
+        for _ in range(n_epochs):
+            if time_limit_seconds is not None and time.time() - t0 > time_limit_seconds:
+                break
+            perm = torch.randperm(n, device=dev) if shuffle else torch.arange(n, device=dev)
+            tr.nll_epoch(x_train, perm, batch_size, losses)
+            score_t = tr.mean_nll(ref)
+            score, train_sum = (float(v) for v in torch.stack([score_t, losses.sum()]).cpu())   # the epoch's one sync
+            if not math.isfinite(train_sum):
+                raise ValueError("Flow training diverged")                 # the reference rolls back on ValueError
+            if score < best:
+                best, since_best = score, 0
+                if keep_best_weights:
+                    best_theta.copy_(tr.theta)
+            else:
+                since_best += 1
+                if early_stopping and since_best >= early_stopping_threshold:
+                    break
+        tr.write_back(best_theta if keep_best_weights and math.isfinite(best) else None)
+    finally:
+        flow.eval()
+
+
+def _variational_fit_native(flow, dev, potential, n_epochs, lr, n_samples, early_stopping, early_stopping_threshold,
+                            keep_best_weights, check_for_divergences, time_limit_seconds):
+    tr = NativeTrainer(flow, dev, lr)
+    seed = int(torch.randint(0, 2 ** 62, (), dtype=torch.int64))
+    best, since_best = math.inf, 0
+    best_theta = tr.theta.clone() if keep_best_weights else None
+    prev = tr.theta.clone()
+    t0 = time.time()
+    try:
+        for epoch in range(n_epochs):
+            if time_limit_seconds is not None and time.time() - t0 > time_limit_seconds:
+                break
+            prev.copy_(tr.theta)
+            tr.kl_step(potential, n_samples, seed, epoch)
+            val = float(tr.loss[0]) / n_samples            # loss of the parameters BEFORE this step (as autograd reports it)
+            if not math.isfinite(val):
+                tr.theta.copy_(prev)
+                if check_for_divergences:
+                    break
+                raise ValueError("Flow training diverged")
+            if val < best:
+                best, since_best = val, 0
+                if keep_best_weights:
+                    best_theta.copy_(prev)
+            else:
+                since_best += 1
+                if early_stopping and since_best >= early_stopping_threshold:
+                    break
+        tr.write_back(best_theta if keep_best_weights and math.isfinite(best) else None)
+    finally:
+        flow.eval()
 
 
 def train_val_split(x: torch.Tensor, train_pct: float, max_train_size: int, max_val_size: int, shuffle: bool = True):
@@ -150,6 +353,11 @@ def fit(flow, x_train, n_epochs: int = 500, lr: float = 0.05, batch_size=None, s
         batch_size = max(32, min(1024, n // 10 if n >= 320 else n))
     if batch_size is None:
         batch_size = n
+    batch_size = int(batch_size)
+    if native_supported(flow):
+        return _fit_native(flow, dev, x_train.contiguous(), None if x_val is None else x_val.contiguous(), n_epochs, lr,
+                           batch_size, shuffle, keep_best_weights, early_stopping, early_stopping_threshold,
+                           time_limit_seconds)
     params = [p for p in flow.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=lr)
     best, best_state, since_best = math.inf, None, 0
@@ -192,6 +400,11 @@ def variational_fit(flow, target_log_prob: Callable, n_epochs: int = 500, lr: fl
     dev = flow._compute_device()
     flow.to(dev)
     d = flow.bijection.n_dim
+    potential = getattr(target_log_prob, "potential", None)
+    if potential is not None and native_supported(flow):
+        return _variational_fit_native(flow, dev, potential, n_epochs, lr, int(n_samples), early_stopping,
+                                       early_stopping_threshold, keep_best_weights, check_for_divergences,
+                                       time_limit_seconds)
     params = [p for p in flow.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=lr)
     best, best_state, since_best = math.inf, None, 0

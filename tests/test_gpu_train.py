@@ -1,0 +1,191 @@
+"""B200: native flow training (csrc/train_kernels.cu, csrc/train_api.cu) against torch autograd over the same RealNVP
+arithmetic (nfmc_b200/flow_train.py: forward_autograd / inverse_autograd) and torch.optim.AdamW.
+
+Reference call sites of the training these kernels replace: nfmc/jump.py:139-151,201, nfmc/imh.py:67-72,171-175,
+nfmc/neutra.py:84-91.  Tolerances: gradients agree to 2e-4 of the largest gradient entry (fp32 sums over the batch in a
+different order, MUFU exp/log/tanh in the kernel).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(6, 2, 4), (7, 3, 6), (25, 2, None), (100, 2, None), (9, 1, 8), (64, 4, 8), (1000, 1, None), (33, 0, 4)]
+
+
+def _flow(d, Lc, H, seed=0, scale=0.15):
+    from nfmc_b200.flow import Flow, RealNVP
+    torch.manual_seed(seed)
+    ck = None if H is None else dict(n_layers=2, n_hidden=H)
+    f = Flow(RealNVP((d,), n_layers=Lc, conditioner_kwargs=ck, conditioner_dtype="fp32"))
+    with torch.no_grad():
+        for p in f.parameters():
+            p.add_(scale * torch.randn_like(p))
+        for l in f.bijection.layers:
+            if hasattr(l, "initialised"):
+                l.initialised.fill_(True)
+    return f.to("cuda").eval()
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+@pytest.mark.parametrize("d,Lc,H", SHAPES)
+def test_device_pack_matches_host_pack(d, Lc, H):
+    from nfmc_b200.flow import pack_realnvp
+    from nfmc_b200.flow_train import NativeTrainer
+    f = _flow(d, Lc, H)
+    tr = NativeTrainer(f, torch.device("cuda"), 0.05)
+    tr.pack()
+    ref = pack_realnvp(f.bijection)
+    got = tr.blob.cpu()
+    assert got.shape == ref.shape
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("d,Lc,H", SHAPES)
+def test_nll_gradient_matches_autograd(d, Lc, H):
+    from nfmc_b200 import _native as N
+    from nfmc_b200.flow_train import NativeTrainer, log_prob_autograd
+    f = _flow(d, Lc, H, seed=d)
+    dev = torch.device("cuda")
+    n = 137
+    x = torch.randn(n, d, device=dev) * 1.3 + 0.2
+    rows = torch.randperm(n, device=dev)[:101]
+    params = list(f.bijection.parameters())
+    with torch.enable_grad():
+        loss = -log_prob_autograd(f, x[rows]).sum()
+        grads = torch.autograd.grad(loss, params)
+    ref = torch.cat([g.reshape(-1) for g in grads])
+    tr = NativeTrainer(f, dev, 0.05)
+    tr.pack()
+    desc = tr.desc()
+    N.check(N.lib().nfmc_flow_nll_grad(C.byref(desc), N.ptr(x), rows.data_ptr(), rows.numel(), N.ptr(tr.gblob),
+                                       N.ptr(tr.loss), 0, tr.stream))
+    tr.unpack(1.0)
+    assert abs(float(tr.loss[0]) - float(loss.detach())) <= 1e-4 * abs(float(loss.detach()))
+    assert _rel(tr.gtheta, ref) < 2e-4, _rel(tr.gtheta, ref)
+    # per-tensor check so that small gradients (biases, act-norms) are not hidden behind the weights
+    off = 0
+    for p, g in zip(params, grads):
+        k = p.numel()
+        assert _rel(tr.gtheta[off:off + k], g.reshape(-1)) < 1e-3, (tuple(p.shape), off)
+        off += k
+
+
+@pytest.mark.parametrize("d,Lc,H,pot", [(6, 2, 4, "fn"), (7, 3, 6, "gm"), (100, 2, None, "g1"), (26, 2, 8, "rb"),
+                                        (25, 1, None, "g0"), (1000, 1, None, "gm")])
+def test_reverse_kl_gradient_matches_autograd(d, Lc, H, pot):
+    from nfmc_b200 import _native as N
+    from nfmc_b200 import potentials as P
+    from nfmc_b200.flow_train import NativeTrainer, inverse_autograd, target_log_prob_fn
+    f = _flow(d, Lc, H, seed=3 * d, scale=0.1)
+    dev = torch.device("cuda")
+    n = 77
+    z = torch.randn(n, d, device=dev)
+    potential = P.make_potential(pot, (d,))
+    tlp = target_log_prob_fn(potential)
+    params = list(f.bijection.parameters())
+    with torch.enable_grad():
+        x, ld = inverse_autograd(f.bijection, z)
+        log_q = (-0.5 * z.square()).sum(dim=1) - 0.5 * d * math.log(2 * math.pi) - ld
+        loss = (log_q - tlp(x)).sum()
+        grads = torch.autograd.grad(loss, params)
+    ref = torch.cat([g.reshape(-1) for g in grads])
+    tr = NativeTrainer(f, dev, 0.05)
+    tr.pack()
+    desc = tr.desc()
+    pd, keep = potential.descriptor(dev)
+    rng = N.rng_desc(0, 0, z, None)
+    N.check(N.lib().nfmc_flow_kl_grad(C.byref(pd), C.byref(desc), C.byref(rng), 0, n, N.ptr(tr.gblob), N.ptr(tr.loss), 0,
+                                      tr.stream))
+    tr.unpack(1.0)
+    assert abs(float(tr.loss[0]) - float(loss.detach())) <= 2e-4 * max(1.0, abs(float(loss.detach())))
+    assert _rel(tr.gtheta, ref) < 5e-4, _rel(tr.gtheta, ref)
+
+
+def test_adamw_matches_torch():
+    from nfmc_b200 import _native as N
+    dev = torch.device("cuda")
+    torch.manual_seed(1)
+    n = 5000
+    theta = torch.randn(n, device=dev)
+    p = torch.nn.Parameter(theta.clone())
+    opt = torch.optim.AdamW([p], lr=0.05)
+    m, v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    for step in range(1, 6):
+        g = torch.randn(n, device=dev) * (0.1 * step)
+        p.grad = g.clone()
+        opt.step()
+        N.check(N.lib().nfmc_adamw_step(N.ptr(theta), N.ptr(g), N.ptr(m), N.ptr(v), n, 0.05, 0.9, 0.999, 1e-8, 0.01, step,
+                                        N.stream_ptr(dev)))
+    np.testing.assert_allclose(theta.cpu().numpy(), p.detach().cpu().numpy(), rtol=2e-5, atol=2e-6)
+
+
+def _gaussian_data(n, d, seed):
+    g = torch.Generator().manual_seed(seed)
+    mu = torch.linspace(-1.0, 1.0, d)
+    sd = torch.linspace(0.5, 2.0, d)
+    return mu + sd * torch.randn(n, d, generator=g)
+
+
+def test_native_fit_tracks_library_fit(monkeypatch):
+    """Same data, same shuffles: a few epochs of the native loop land where the autograd loop lands."""
+    from nfmc_b200.flow import Flow, RealNVP
+    d = 20
+    x = _gaussian_data(3000, d, 0).cuda()
+    xv = _gaussian_data(1000, d, 1).cuda()
+    scores = {}
+    for mode in ("native", "library"):
+        if mode == "library":
+            monkeypatch.setenv("NFMC_B200_LIBRARY_TRAINING", "1")
+        torch.manual_seed(11)
+        f = Flow(RealNVP((d,), n_layers=2)).to("cuda")
+        before = float(-f.log_prob(xv).mean())
+        f.fit(x, x_val=xv, n_epochs=6, lr=0.02, batch_size=500)
+        after = float(-f.log_prob(xv).mean())
+        assert after < before - 1.0
+        scores[mode] = after
+    assert abs(scores["native"] - scores["library"]) < 0.05 * abs(scores["library"]), scores
+
+
+def test_native_fit_early_stopping_and_rollback():
+    from nfmc_b200.flow import Flow, RealNVP
+    d = 12
+    x = _gaussian_data(2000, d, 2).cuda()
+    torch.manual_seed(0)
+    f = Flow(RealNVP((d,), n_layers=2)).to("cuda")
+    f.fit(x, n_epochs=400, lr=0.05, batch_size="adaptive", early_stopping=True, early_stopping_threshold=5)
+    nll = float(-f.log_prob(x).mean())
+    # entropy of the generating Gaussian: the fitted flow must be close to it
+    sd = torch.linspace(0.5, 2.0, d)
+    h = float(0.5 * d * (1 + math.log(2 * math.pi)) + sd.log().sum())
+    assert nll < h + 0.6, (nll, h)
+    with pytest.raises(ValueError):
+        bad = x.clone()
+        bad[0, 0] = float("nan")
+        Flow(RealNVP((d,), n_layers=2)).to("cuda").fit(bad, n_epochs=3, lr=0.05, batch_size=500)
+
+
+def test_native_variational_fit_reduces_reverse_kl():
+    from nfmc_b200 import potentials as P
+    from nfmc_b200.flow import Flow, RealNVP
+    d = 10
+    potential = P.make_potential("g1", (d,))            # sigma_i from 0.1 to 100: far from the standard-normal start
+    torch.manual_seed(4)
+    f = Flow(RealNVP((d,), n_layers=2)).to("cuda")
+
+    def reverse_kl():
+        xs, lq = f.sample(4096, return_log_prob=True, seed=7)
+        return float((lq + potential(xs)).mean())
+
+    before = reverse_kl()
+    f.variational_fit(potential.log_prob_fn(), n_epochs=300, lr=0.05, n_samples=64)
+    after = reverse_kl()
+    assert after < before - 5.0, (before, after)
