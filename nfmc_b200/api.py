@@ -141,10 +141,11 @@ def sample(target, event_shape: Optional[Tuple[int, ...]] = None, flow: Optional
         x0 = torch.randn(size=(n_chains, *tuple(event_shape)))                      # reference: sample.py:305
     if warmup:
         w = sampler.warmup(x0=x0, show_progress=show_progress, time_limit_seconds=warmup_time_limit_seconds)
-        if w.samples is not None:
-            flat = w.samples.flatten(0, 1)
-            x0 = flat[torch.randperm(len(flat))][:n_chains]
-        else:
-            rs = w.running_samples                      # stay on the device when the warm-up left its state there
+        rs = w.running_samples
+        if w.store_samples:
+            pool = rs.device_tensor()                   # shuffle on the GPU when the warm-up samples live there
+            flat = (pool if pool is not None else w.samples).flatten(0, 1)
+            x0 = flat[torch.randperm(len(flat), device=flat.device)[:n_chains]]   # reference: sample.py:309-311
+        else:                                           # stay on the device when the warm-up left its state there
             x0 = rs.last_sample_device if rs.last_sample_device is not None else rs.last_sample
     return sampler.sample(x0=x0, show_progress=show_progress, time_limit_seconds=sampling_time_limit_seconds)

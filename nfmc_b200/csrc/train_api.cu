@@ -212,7 +212,10 @@ int launch_train(const nfmc_realnvp* flow, TrainArgs& A, int64_t n, float* grad,
     if (loss) if (int e = check_cuda(cudaMemsetAsync(loss, 0, sizeof(double), s), "zero loss")) return e;
   }
   const int grid = grid_for(n, L.gs, 2);
-  NFMC_DISPATCH_E(L.E, { return launch_flow_train<E>(A, grid, s); });
+  // CTA-local accumulation pays once a CTA sees several warps' worth of rows and the accumulator fits beside the L1
+  const int64_t tiles = (n + kThreads / L.gs - 1) / (kThreads / L.gs);
+  const bool shared_grad = tiles >= 4 * (int64_t)grid && (size_t)flow->blob_floats * sizeof(float) <= 96 * 1024;
+  NFMC_DISPATCH_E(L.E, { return launch_flow_train<E>(A, grid, shared_grad, s); });
   return 0;
 }
 

@@ -24,15 +24,29 @@
 
 namespace nfmc {
 
+// Gradient accumulator: the global blob-layout array, or (SG) a per-CTA copy in shared memory that is flushed once at
+// the end of the kernel -- for large batches this turns one global atomic per warp and parameter into one per CTA.
+template <bool SG>
+struct GradSink {
+  float* g;        // global accumulator
+  unsigned sbase;  // shared-window address of the CTA-local accumulator (SG only)
+  __device__ __forceinline__ void add(int off, float v) const {
+    if (SG) asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(sbase + 4u * (unsigned)off), "f"(v) : "memory");
+    else atomicAdd(g + off, v);
+  }
+};
+
 // v = this lane's contribution to a parameter that is owned by lane position j (same parameter on lanes j, j+gs, ...)
-__device__ __forceinline__ void emit(float* G, int off, float v, const Geom& g, bool ok) {
+template <bool SG>
+__device__ __forceinline__ void emit(const GradSink<SG>& G, int off, float v, const Geom& g, bool ok) {
   const float s = across_groups_sum(v, g.gs);
-  if (g.lane < g.gs && ok) atomicAdd(G + off, s);
+  if (g.lane < g.gs && ok) G.add(off, s);
 }
 // v = a per-chain value (identical on the lanes of a group): counted once per group
-__device__ __forceinline__ void emit_chain(float* G, int off, float v, const Geom& g) {
+template <bool SG>
+__device__ __forceinline__ void emit_chain(const GradSink<SG>& G, int off, float v, const Geom& g) {
   const float s = across_groups_sum(g.j == 0 ? v : 0.f, g.gs);
-  if (g.lane == 0) atomicAdd(G + off, s);
+  if (g.lane == 0) G.add(off, s);
 }
 
 // (y, gy) = output of the layer and dL/dy  ->  (x, gx); returns (dalpha, dbeta)
@@ -48,9 +62,9 @@ __device__ __forceinline__ float2 affine_back(bool inv, float act, float alpha, 
   return make_float2(dal, dbe);
 }
 
-template <int E>
+template <int E, bool SG>
 __device__ __forceinline__ void affine_train(const FlowDesc& F, const Geom& g, int a, bool inv, float act, float (&lo)[E],
-                                             float (&hi)[E], float (&glo)[E], float (&ghi)[E], float* G) {
+                                             float (&hi)[E], float (&glo)[E], float (&ghi)[E], const GradSink<SG>& G) {
   const int fw = a * 4 * F.d, iv = fw + 2 * F.d;
 #pragma unroll
   for (int e = 0; e < E; ++e) {
@@ -71,11 +85,11 @@ __device__ __forceinline__ void affine_train(const FlowDesc& F, const Geom& g, i
 }
 
 // conditioner backward with weight gradients (small path); dsrc[e] += input-VJP
-template <int E>
+template <int E, bool SG>
 __device__ __forceinline__ void cond_backward_small_train(const FlowDesc& F, const Geom& g, int W, int shift, int nt_main,
                                                           bool has_x, const float (&hid)[kSmallH], const float (&src)[E],
                                                           const float (&dua)[E], const float (&dub)[E], float dua_x,
-                                                          float dub_x, float (&dsrc)[E], float* G) {
+                                                          float dub_x, float (&dsrc)[E], const GradSink<SG>& G) {
   const int da = F.da, db = F.db, H = F.H;
   const int b1 = W + da * kSmallH;
   const int Wl = b1 + kSmallH;
@@ -136,9 +150,9 @@ __device__ __forceinline__ void cond_backward_small_train(const FlowDesc& F, con
   }
 }
 
-template <int E>
+template <int E, bool SG>
 __device__ __forceinline__ void coupling_train(const FlowDesc& F, const Geom& g, int l, bool inv, float act, float (&lo)[E],
-                                               float (&hi)[E], float (&glo)[E], float (&ghi)[E], float* G) {
+                                               float (&hi)[E], float (&glo)[E], float (&ghi)[E], const GradSink<SG>& G) {
   float ua[E], ub[E], ua_x = 0.f, ub_x = 0.f, dua_x = 0.f, dub_x = 0.f;
   float hid[kSmallH];
   const bool src_is_hi = (l & 1) == 0;
@@ -169,26 +183,35 @@ __device__ __forceinline__ void coupling_train(const FlowDesc& F, const Geom& g,
     dua_x = dd.x * (al - kMinScale) * 0.5f;
     dub_x = 0.5f * dd.y;
   }
-  cond_backward_small_train<E>(F, g, Woff, shift, nt_main, has_x, hid, lo, ua, ub, dua_x, dub_x, glo, G);
+  cond_backward_small_train<E, SG>(F, g, Woff, shift, nt_main, has_x, hid, lo, ua, ub, dua_x, dub_x, glo, G);
   swap_halves(lo, hi, src_is_hi);
   swap_halves(glo, ghi, src_is_hi);
 }
 
 // walk the layers back: `inv` = direction of the pass that produced (lo, hi)
-template <int E>
+template <int E, bool SG>
 __device__ __forceinline__ void flow_train_sweep(const FlowDesc& F, const Geom& g, bool inv, float act, float (&lo)[E],
-                                                 float (&hi)[E], float (&glo)[E], float (&ghi)[E], float* G) {
+                                                 float (&hi)[E], float (&glo)[E], float (&ghi)[E], const GradSink<SG>& G) {
   const int n_ops = 2 * F.Lc + 1;
 #pragma unroll 1
   for (int i = 0; i < n_ops; ++i) {
     const int op = inv ? i : n_ops - 1 - i;
-    if (op & 1) coupling_train<E>(F, g, op >> 1, inv, act, lo, hi, glo, ghi, G);
-    else affine_train<E>(F, g, op >> 1, inv, act, lo, hi, glo, ghi, G);
+    if (op & 1) coupling_train<E, SG>(F, g, op >> 1, inv, act, lo, hi, glo, ghi, G);
+    else affine_train<E, SG>(F, g, op >> 1, inv, act, lo, hi, glo, ghi, G);
   }
 }
 
-template <int E>
+template <int E, bool SG>
 __global__ void __launch_bounds__(kThreads, 2) flow_train_kernel(const TrainArgs A) {
+  extern __shared__ __align__(16) float sgrad[];
+  GradSink<SG> G;
+  G.g = A.grad;
+  G.sbase = 0u;
+  if (SG) {
+    for (int i = threadIdx.x; i < (int)A.f.blob_floats; i += blockDim.x) sgrad[i] = 0.f;
+    G.sbase = (unsigned)__cvta_generic_to_shared(sgrad);
+    __syncthreads();
+  }
   const Geom g = make_geom(A.f.d, A.f.gs);
   const FlowDesc F = make_flow_desc(A.f.blob, A.f.d, A.f.Lc, A.f.M, A.f.H);
   const int cpc = kThreads / A.f.gs;
@@ -209,7 +232,7 @@ __global__ void __launch_bounds__(kThreads, 2) flow_train_kernel(const TrainArgs
       li = -(base_log_prob(g, lo, hi) + ld);                                   // -log q(x)
 #pragma unroll
       for (int e = 0; e < E; ++e) { glo[e] = act * lo[e]; ghi[e] = act * hi[e]; }   // d/dz of |z|^2 / 2
-      flow_train_sweep<E>(F, g, false, act, lo, hi, glo, ghi, A.grad);
+      flow_train_sweep<E, SG>(F, g, false, act, lo, hi, glo, ghi, G);
     } else {
       draw_base(A.rng, g, flip, A.n, chain, A.chain0, 0, lo, hi);
       const float lbase = base_log_prob(g, lo, hi);
@@ -223,19 +246,33 @@ __global__ void __launch_bounds__(kThreads, 2) flow_train_kernel(const TrainArgs
         glo[e] = kk < g.da ? act * glo[e] : 0.f;
         ghi[e] = kk < g.db ? act * ghi[e] : 0.f;
       }
-      flow_train_sweep<E>(F, g, true, act, lo, hi, glo, ghi, A.grad);
+      flow_train_sweep<E, SG>(F, g, true, act, lo, hi, glo, ghi, G);
     }
     if (active && g.j == 0) loss += (double)li;
   }
   for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
   if ((threadIdx.x & 31) == 0 && A.loss) atomicAdd(A.loss, loss);
+  if (SG) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < (int)A.f.blob_floats; i += blockDim.x) {
+      const float v = sgrad[i];
+      if (v != 0.f) atomicAdd(A.grad + i, v);
+    }
+  }
 }
 
+// shared_grad: accumulate per CTA in shared memory (smem = blob_floats * 4 bytes); chosen by the caller for large batches
 template <int E>
-int launch_flow_train(const TrainArgs& A, int grid, cudaStream_t s) {
-  flow_train_kernel<E><<<grid, kThreads, 0, s>>>(A);
+int launch_flow_train(const TrainArgs& A, int grid, bool shared_grad, cudaStream_t s) {
+  if (shared_grad) {
+    const size_t smem = (size_t)A.f.blob_floats * sizeof(float);
+    NFMC_SET_SMEM_RET((flow_train_kernel<E, true>), smem);
+    flow_train_kernel<E, true><<<grid, kThreads, smem, s>>>(A);
+  } else {
+    flow_train_kernel<E, false><<<grid, kThreads, 0, s>>>(A);
+  }
   return check_cuda(cudaGetLastError(), "flow_train_kernel launch");
 }
-template int launch_flow_train<NFMC_ONLY_E>(const TrainArgs&, int, cudaStream_t);
+template int launch_flow_train<NFMC_ONLY_E>(const TrainArgs&, int, bool, cudaStream_t);
 
 }  // namespace nfmc

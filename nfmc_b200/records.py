@@ -11,6 +11,7 @@ is what makes pooling over GPUs a plain all-reduce.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Any, Dict, List, Optional, Tuple, Union
 
@@ -409,10 +410,18 @@ class JumpNFMCStatistics(MCMCStatistics):
 # ---------------------------------------------------------------------------------------------------------------
 # samples and output
 # ---------------------------------------------------------------------------------------------------------------
+DEVICE_SAMPLE_BUDGET_BYTES = int(os.environ.get("NFMC_B200_DEVICE_SAMPLE_BYTES", 48 << 30))
+PINNED_HOST_LIMIT_BYTES = 8 << 30
+
+
 class MCMCSamples:
-    """Sample store (reference: sampling/base.py:215-271).  Same attributes; ``last_sample`` is materialised on the host
-    lazily -- the sampler leaves the final state on the GPU (``last_sample_device``) and the 4*n*d-byte copy happens only
-    when ``last_sample`` is read (a warm-up -> sampling hand-off never needs it)."""
+    """Sample store (reference: sampling/base.py:215-271).  Same attributes and semantics (thinning, ``max_samples``
+    window, ``last_sample``), different residency: blocks written by the kernels' sample sink **stay on the GPU** (up
+    to ``NFMC_B200_DEVICE_SAMPLE_BYTES``, default 48 GiB of the 180 GB of HBM; beyond that they spill to the host as they
+    arrive) and the host tensor the reference would have built with one ``.cpu()`` per iteration is materialised once,
+    on demand, by ``as_tensor()`` -- through a pinned buffer, all copies in flight together.  Consumers on the device
+    (flow refits ``imh.py:152-175``, warm-up hand-off ``sample.py:307-313``) use ``row()`` / ``device_tensor()`` and
+    never touch the host.  ``last_sample`` is materialised lazily in the same way."""
 
     def __init__(self, event_shape, store_samples: bool = True, n_samples: int = 0, last_sample: torch.Tensor = None,
                  thinning: int = 1, seen_samples: int = 0, max_samples: int = None):
@@ -422,7 +431,8 @@ class MCMCSamples:
         self.thinning = thinning
         self.seen_samples = seen_samples
         self.max_samples = max_samples
-        self._blocks: List[torch.Tensor] = []   # each [k, n, *event], host
+        self._blocks: List[torch.Tensor] = []   # each [k, n, *event]; on the device while the budget allows, else host
+        self._device_bytes = 0
         self._last = last_sample
         self.last_sample_device: Optional[torch.Tensor] = None
 
@@ -442,14 +452,26 @@ class MCMCSamples:
         self._last = None
         self.last_sample_device = x_dev
 
+    def row(self, index: int) -> torch.Tensor:
+        """Stored iteration ``index`` as ``[n, *event]`` wherever it lives (device or host), without materialising the
+        whole store."""
+        if index < 0:
+            index += self.n_samples
+        for blk in self._blocks:
+            if index < len(blk):
+                return blk[index]
+            index -= len(blk)
+        raise IndexError("sample index out of range")
+
     def __getitem__(self, index):
         if index == -1 or index == self.n_samples - 1:
             return self.last_sample
-        return self.as_tensor()[index]
+        return self.row(index)
 
     def add(self, x: torch.Tensor, already_thinned: bool = False, n_seen: Optional[int] = None):
         """Append a block ``[k, n, *event]`` or one state ``[n, *event]`` (reference: base.py:234-263).
-        ``already_thinned``: the device sink applied the thinning rule; ``n_seen`` = steps the block stands for."""
+        ``already_thinned``: ``x`` is a buffer the device sink filled under the thinning rule (owned by the store from
+        here on); ``n_seen`` = steps the block stands for."""
         k = len(self.event_shape)
         if x.ndim == k + 1 and tuple(x.shape[1:]) == tuple(self.event_shape):
             x = x[None]
@@ -463,27 +485,65 @@ class MCMCSamples:
         if not self.store_samples:
             return
         if already_thinned:
-            kept = x
+            kept = x.detach()
             self.seen_samples += int(n_seen if n_seen is not None else len(x))
         else:
             idx = torch.arange(self.seen_samples, self.seen_samples + len(x))
-            kept = x[(idx % self.thinning) == 0]
+            kept = x.detach()[(idx % self.thinning) == 0]      # advanced indexing: a copy, never a view of live state
             self.seen_samples += len(x)
         if len(kept):
-            self._blocks.append(kept.detach().cpu())
+            nbytes = kept.numel() * kept.element_size()
+            if kept.is_cuda and self._device_bytes + nbytes <= DEVICE_SAMPLE_BUDGET_BYTES:
+                self._device_bytes += nbytes
+            else:
+                kept = kept.cpu()
+            self._blocks.append(kept)
             self.n_samples += len(kept)
-        if self.max_samples is not None and self.n_samples > self.max_samples:
-            full = torch.cat(self._blocks, dim=0)[-self.max_samples:]
-            self._blocks = [full]
-            self.n_samples = len(full)
+        if self.max_samples is not None and self.n_samples > self.max_samples:   # keep the last max_samples rows
+            drop = self.n_samples - self.max_samples
+            while drop > 0:
+                blk = self._blocks[0]
+                if len(blk) <= drop:
+                    self._blocks.pop(0)
+                    drop -= len(blk)
+                    if blk.is_cuda:
+                        self._device_bytes -= blk.numel() * blk.element_size()
+                else:
+                    self._blocks[0] = blk[drop:]
+                    drop = 0
+            self.n_samples = self.max_samples
 
-    def as_tensor(self) -> torch.Tensor:
+    def device_tensor(self) -> Optional[torch.Tensor]:
+        """All stored iterations ``[n_samples, n, *event]`` on the GPU, or ``None`` if some block spilled to the host."""
+        if not self._blocks or not all(b.is_cuda for b in self._blocks):
+            return None
         if len(self._blocks) > 1:
             self._blocks = [torch.cat(self._blocks, dim=0)]
         return self._blocks[0]
 
+    def as_tensor(self) -> torch.Tensor:
+        """The host tensor ``[n_samples, n, *event]`` (what the reference's ``torch.stack(self._running)`` returns)."""
+        if not self._blocks:
+            raise RuntimeError("no samples stored")
+        if len(self._blocks) == 1 and not self._blocks[0].is_cuda:
+            return self._blocks[0]
+        shape = (sum(len(b) for b in self._blocks), *self._blocks[0].shape[1:])
+        nbytes = 4 * int(torch.Size(shape).numel())
+        any_cuda = any(b.is_cuda for b in self._blocks)
+        host = torch.empty(shape, dtype=torch.float32, pin_memory=bool(any_cuda and nbytes <= PINNED_HOST_LIMIT_BYTES))
+        off = 0
+        for b in self._blocks:
+            host[off:off + len(b)].copy_(b, non_blocking=True)
+            off += len(b)
+        if any_cuda:
+            torch.cuda.synchronize()
+        self._blocks = [host]
+        self._device_bytes = 0
+        return host
+
     def reset(self):
         self._blocks = []
+        self._device_bytes = 0
         self.n_samples = 0
 
 

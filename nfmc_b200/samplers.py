@@ -472,7 +472,9 @@ class JumpNFMC(Sampler):
         self.inner_sampler.params.store_samples = True
         out = self.inner_sampler.warmup(x0, show_progress=show_progress, time_limit_seconds=limit)
         p: JumpNFMCParameters = self.params
-        x_train, x_val = train_val_split(out.samples, p.train_pct, p.max_train_size, p.max_val_size)
+        pool = out.running_samples.device_tensor()          # warm-up samples stay on the GPU when they fit
+        x_train, x_val = train_val_split(pool if pool is not None else out.samples, p.train_pct, p.max_train_size,
+                                         p.max_val_size)
         backup = deepcopy(self.kernel.flow.state_dict())
         fit_limit = None if time_limit_seconds is None else max(time_limit_seconds - (time.time() - t0), 0.0)
         try:
@@ -537,7 +539,7 @@ class AbstractIMH(Sampler):
         self.kernel.flow.variational_fit(self.target.log_prob_fn(), **self.params.warmup_fit_kwargs,
                                          show_progress=show_progress, time_limit_seconds=time_limit_seconds)
         out = MCMCOutput(event_shape=tuple(x0.shape[1:]), store_samples=self.params.store_samples)
-        out.running_samples.add(self.kernel.flow.sample(x0.shape[0]).cpu())
+        out.running_samples.add(self.kernel.flow.sample(x0.shape[0]))
         return out
 
     def _run(self, x0, show_progress, time_limit_seconds, store, z=None, uniforms=None, after_iteration=None) -> MCMCOutput:

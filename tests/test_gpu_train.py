@@ -110,6 +110,28 @@ def test_reverse_kl_gradient_matches_autograd(d, Lc, H, pot):
     assert _rel(tr.gtheta, ref) < 5e-4, _rel(tr.gtheta, ref)
 
 
+def test_nll_gradient_large_batch_shared_accumulation():
+    """Batches of many tiles per CTA accumulate in shared memory and flush once (train_api.cu: shared_grad)."""
+    from nfmc_b200 import _native as N
+    from nfmc_b200.flow_train import NativeTrainer, log_prob_autograd
+    d, n = 100, 70001
+    f = _flow(d, 2, None, seed=5)
+    dev = torch.device("cuda")
+    x = torch.randn(n, d, device=dev)
+    params = list(f.bijection.parameters())
+    with torch.enable_grad():
+        loss = -log_prob_autograd(f, x).sum()
+        grads = torch.autograd.grad(loss, params)
+    ref = torch.cat([g.reshape(-1) for g in grads])
+    tr = NativeTrainer(f, dev, 0.05)
+    tr.pack()
+    desc = tr.desc()
+    N.check(N.lib().nfmc_flow_nll_grad(C.byref(desc), N.ptr(x), None, n, N.ptr(tr.gblob), N.ptr(tr.loss), 0, tr.stream))
+    tr.unpack(1.0)
+    assert abs(float(tr.loss[0]) - float(loss.detach())) <= 1e-4 * abs(float(loss.detach()))
+    assert _rel(tr.gtheta, ref) < 5e-4, _rel(tr.gtheta, ref)
+
+
 def test_adamw_matches_torch():
     from nfmc_b200 import _native as N
     dev = torch.device("cuda")

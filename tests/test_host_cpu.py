@@ -127,3 +127,39 @@ def test_dual_averaging_matches_oracle():
         a.step(0.651 - acc)
         v = b.step(acc)
         assert abs(a.value - v) < 1e-12
+
+
+def test_sample_store_matches_reference_semantics():
+    """MCMCSamples.add / thinning / max_samples window / indexing (reference: sampling/base.py:215-271), restated as a
+    plain list and compared block by block, for single states and multi-row blocks."""
+    import torch
+    from nfmc_b200.records import MCMCSamples
+
+    def reference_store(blocks, thinning, max_samples):
+        running, seen = [], 0
+        for x in blocks:
+            x = x[None] if x.ndim == 2 else x
+            mask = (torch.arange(seen, seen + len(x)) % thinning) == 0
+            seen += len(x)
+            running.extend(x[mask])
+            if max_samples is not None:
+                running = running[-max_samples:]
+        return torch.stack(running) if running else None
+
+    torch.manual_seed(0)
+    blocks = [torch.randn(4, 3), torch.randn(5, 4, 3), torch.randn(1, 4, 3), torch.randn(4, 3), torch.randn(7, 4, 3)]
+    for thinning in (1, 2, 3):
+        for max_samples in (None, 4, 100):
+            rs = MCMCSamples((3,), thinning=thinning, max_samples=max_samples)
+            for b in blocks:
+                rs.add(b)
+            ref = reference_store(blocks, thinning, max_samples)
+            assert rs.n_samples == len(ref)
+            for i in range(len(ref)):
+                assert torch.equal(rs.row(i), ref[i])
+            assert torch.equal(rs.as_tensor(), ref)
+            assert torch.equal(rs.last_sample, blocks[-1][-1])
+            assert torch.equal(rs[-1], blocks[-1][-1])
+    rs = MCMCSamples((3,), store_samples=False)
+    rs.add(blocks[0])
+    assert rs.n_samples == 0 and torch.equal(rs.last_sample, blocks[0])

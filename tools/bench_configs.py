@@ -18,13 +18,17 @@ def flow_for(d, spec="realnvp"):
     return f
 
 
-def run(name, strategy, pot, d, n, T, K=None, flow_spec="realnvp", **kw):
+def run(name, strategy, pot, d, n, T, K=None, flow_spec="realnvp", adapt=False, fit_nf=False, **kw):
     flow = flow_for(d, flow_spec)
     ik = {} if K is None else {"inner_param_kwargs": {"n_iterations": K}}
-    s = nfmc_b200.create_sampler(make_potential(pot, (d,)), flow=flow, strategy=strategy,
-                                 param_kwargs={"n_iterations": T, "store_samples": False}, **ik, **kw)
+    pk = {"n_iterations": T, "store_samples": False}
+    if fit_nf:
+        pk.update(fit_nf=True, n_jumps_before_training=0)
+    s = nfmc_b200.create_sampler(make_potential(pot, (d,)), flow=flow, strategy=strategy, param_kwargs=pk, **ik, **kw)
     if hasattr(s, "adapt"):
-        s.adapt = False                      # the refit (flow training) is a separate, library-backed step
+        s.adapt = adapt                      # False: MH part only (all iterations fused into one launch)
+    if strategy == "adaptive_imh":
+        s.params.n_iterations = T            # the reference drops param_kwargs for adaptive_imh (quirk Q2)
     x0 = torch.randn(n, d, device="cuda") * 0.5
     s.params.n_iterations = max(1, T // 4)
     s.sample(x0, show_progress=False)                       # warm-up launch
@@ -49,6 +53,9 @@ if __name__ == "__main__":
     run("C3 neutra_hmc funnel d=100 n=262144", "neutra_hmc", "fn", 100, 262144, 3, inner_kernel_kwargs={"step_size": 0.01})
     run("C4 imh rosenbrock d=100 n=2^20", "imh", "rb", 100, 1 << 20, 20)
     run("C4 adaptive_imh(no refit) d=100 n=2^17", "adaptive_imh", "rb", 100, 1 << 17, 100)
+    run("C4 adaptive_imh WITH per-iteration refit d=100 n=2^17", "adaptive_imh", "rb", 100, 1 << 17, 24, adapt=True)
+    run("C5-shape jump_mala mixture d=1000 n=131072 fit_nf=True (flow refit every outer iteration)", "jump_mala", "gm", 1000,
+        131072, 2, K=100, fit_nf=True)
     run("C5-shape jump_mala mixture d=1000 n=131072 (1/8 of 2^20, frozen flow)", "jump_mala", "gm", 1000, 131072, 2, K=100)
     run("CT jump_mala d=100 n=2^20", "jump_mala", "g0", 100, 1 << 20, 5, K=100)
     run("wide-flow jump_mala d=100 n=2^20 H=256 Lc=4 (tcgen05)", "jump_mala", "g0", 100, 1 << 20, 5, K=100, flow_spec=wide)
