@@ -3,6 +3,13 @@
 
 using namespace nfmc;
 
+#ifndef NFMC_NEUTRA_CTAS
+#define NFMC_NEUTRA_CTAS 2   // resident CTAs per SM of neutra_hmc_kernel (its __launch_bounds__)
+#endif
+#ifndef NFMC_JUMP_CTAS
+#define NFMC_JUMP_CTAS 3     // ... of jump_kernel
+#endif
+
 
 static int flow_pass(const nfmc_realnvp* flow, int mode, const float* in, float* out, float* aux, int64_t n, void* stream) {
   if (int e = validate_flow(flow)) return e;
@@ -61,7 +68,7 @@ static int launch_jump(const nfmc_potential* pot, const nfmc_realnvp* flow, floa
   A.c.sink = SinkArgs{sink ? sink->samples : nullptr, sink ? sink->seen0 : 0, (sink && sink->thinning > 0) ? sink->thinning : 1};
   A.logq_x = logq_x; A.recompute_logq = recompute_logq; A.adjusted = adjusted;
   const size_t smem = plan_flow_smem(A.f, flow, L, true, true);
-  const int grid = grid_for(n, L.gs, 3);
+  const int grid = grid_for(n, L.gs, NFMC_JUMP_CTAS);
   cudaStream_t s = (cudaStream_t)stream;
   A.pot_kind = pot->kind;
   NFMC_DISPATCH_E(L.E, { return launch_jump<E>(A, grid, smem, s); });
@@ -110,7 +117,7 @@ extern "C" int nfmc_neutra_hmc_steps(const nfmc_potential* pot, const nfmc_realn
   A.c.sink = SinkArgs{sink ? sink->samples : nullptr, sink ? sink->seen0 : 0, (sink && sink->thinning > 0) ? sink->thinning : 1};
   A.tau = step_size; A.imd = inv_mass_diag; A.n_leapfrog = n_leapfrog;
   const size_t smem = plan_flow_smem(A.f, flow, L, true, true) + (size_t)pot->d * sizeof(float);   // + inverse-mass table
-  const int grid = grid_for(n, L.gs, 3);
+  const int grid = grid_for(n, L.gs, NFMC_NEUTRA_CTAS);
   cudaStream_t s = (cudaStream_t)stream;
   A.pot_kind = pot->kind;
   NFMC_DISPATCH_E(L.E, { return launch_neutra_hmc<E>(A, grid, smem, s); });

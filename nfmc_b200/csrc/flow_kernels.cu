@@ -13,6 +13,10 @@
 #error "compile with -DNFMC_ONLY_E=<slots per half>"
 #endif
 
+#ifndef NFMC_JUMP_MINB
+#define NFMC_JUMP_MINB 3
+#endif
+
 namespace nfmc {
 
 template <int E, bool SB, bool X, bool SM>
@@ -76,7 +80,7 @@ __global__ void __launch_bounds__(kThreads) flow_sample_kernel(FlowArgs A, RngAr
 
 
 template <int E, bool SB, bool X, bool SM>
-__global__ void __launch_bounds__(kThreads, 3) jump_kernel(const JumpArgs A) {
+__global__ void __launch_bounds__(kThreads, NFMC_JUMP_MINB) jump_kernel(const JumpArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ChainArgs& C = A.c;
   const Geom g = make_geom(C.d, C.gs);

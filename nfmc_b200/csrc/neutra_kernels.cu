@@ -13,6 +13,10 @@
 #error "compile with -DNFMC_ONLY_E=<slots per half>"
 #endif
 
+#ifndef NFMC_NEUTRA_MINB
+#define NFMC_NEUTRA_MINB 2
+#endif
+
 namespace nfmc {
 
 // U~(z) and its gradient.  (zlo, zhi) physical-order latent; (glo, ghi) receives dU~/dz.
@@ -45,7 +49,7 @@ __device__ __forceinline__ float neutra_value_grad(const FlowDesc& F, int pot_ki
 // working copy; the start state of a step is NOT kept (on rejection it is re-read from global memory, which always holds
 // the current state), the running moments live in shared memory, and a non-identity mass is read from shared memory.
 template <int E, bool SB, bool X, bool SM>
-__global__ void __launch_bounds__(kThreads, 3) neutra_hmc_kernel(const NeutraArgs A) {
+__global__ void __launch_bounds__(kThreads, NFMC_NEUTRA_MINB) neutra_hmc_kernel(const NeutraArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ChainArgs& C = A.c;
   const Geom g = make_geom(C.d, C.gs);

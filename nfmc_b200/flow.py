@@ -134,8 +134,26 @@ class RealNVP(_Layer):
         ver = self._version_key()
         hit = self._packed.get(key)
         if hit is None or hit[0] != ver:
-            self._packed[key] = (ver, pack_realnvp(self).to(device))
+            self._packed[key] = (ver, self._pack_on(device))
         return self._packed[key][1]
+
+    def _pack_on(self, device: torch.device) -> torch.Tensor:
+        """Packed blob on ``device``.  Parameters that already live on that GPU are packed there by ``nfmc_flow_pack``
+        (one launch; this is the path after every flow refit); otherwise on the host by ``pack_realnvp``."""
+        params = list(self.parameters())
+        M, H = self.conditioner_shape()
+        same = all((c.n_linear, c.n_hidden) == (M, H) for c in self.couplings())
+        device = torch.device(device)
+        idx = device.index if device.index is not None else (torch.cuda.current_device() if device.type == 'cuda' else None)
+        on_dev = device.type == 'cuda' and all(p.is_cuda and p.device.index == idx for p in params)
+        if params and same and on_dev and M == 2 and H <= SMALL_H:
+            P = N.lib().nfmc_flow_param_count(self.n_dim, self.n_coupling, M, H)
+            theta = torch.cat([p.detach().reshape(-1) for p in params]).to(torch.float32).contiguous()
+            if P == theta.numel():
+                blob = torch.empty(blob_floats(self.n_dim, self.n_coupling, M, H), device=device, dtype=torch.float32)
+                N.check(N.lib().nfmc_flow_pack(self.n_dim, self.n_coupling, M, H, N.ptr(theta), N.ptr(blob), N.stream_ptr(device)))
+                return blob
+        return pack_realnvp(self).to(device)
 
     def uses_tensor_cores(self) -> bool:
         shape = (self.n_dim, *self.conditioner_shape())

@@ -464,8 +464,8 @@ class MCMCSamples:
         raise IndexError("sample index out of range")
 
     def __getitem__(self, index):
-        if index == -1 or index == self.n_samples - 1:
-            return self.last_sample
+        if index == -1 or index == self.n_samples - 1:      # reference: base.py:229-232 (the last SEEN state)
+            return self.last_sample_device if self.last_sample_device is not None else self.last_sample
         return self.row(index)
 
     def add(self, x: torch.Tensor, already_thinned: bool = False, n_seen: Optional[int] = None):
