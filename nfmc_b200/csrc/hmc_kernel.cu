@@ -208,12 +208,189 @@ __global__ void __launch_bounds__(kThreads, NFMC_HMC_MINB) hmc_kernel(const Loca
   cta_stats_finish(st, C.stats, C.d);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// FAST kernel: exact layout, Philox noise, identity mass.  Same arithmetic as hmc_kernel<.., true> (bit-identical
+// results), with the state, momentum and trajectory point held as float2 {lo[e], hi[e]} pairs so that the leapfrog
+// updates issue as packed FFMA2 (two fp32 operations per slot and instruction): the trajectory is pure fp32 issue.
+// ---------------------------------------------------------------------------------------------------------
+template <int POT, int E>
+__global__ void __launch_bounds__(kThreads, NFMC_HMC_MINB) hmc_fast_kernel(const LocalArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const ChainArgs& C = A.c;
+  const Geom g = make_geom(C.d, C.gs);
+  CtaStats st = cta_stats_init(smem, C.d);
+  const size_t off = (cta_stats_bytes(C.d) + 15) & ~size_t(15);
+  float4* mom = reinterpret_cast<float4*>(smem + off) + threadIdx.x;
+  const int cpc = kThreads / C.gs;
+  const long long tiles = (C.n + cpc - 1) / cpc;
+  const float half_tau = A.tau / 2;
+  const float2 TAU = splat2(A.tau), NHT = splat2(-half_tau);
+  const PhiloxKeys PK = philox_keys(C.rng.seed);
+  unsigned int n_acc = 0, n_bad = 0;
+  constexpr int NQ = (E + 2) / 2;
+  constexpr bool CTX = pot_grad_needs_ctx<POT>();
+  const int k_last = g.j + g.gs * (E - 1);
+  const bool vl_last = k_last < g.da, vh_last = k_last < g.db;   // only the last slot can be invalid in an exact layout
+
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long chain_raw = tile * cpc + threadIdx.x / C.gs;
+    const bool active = chain_raw < C.n;
+    const long long chain = active ? chain_raw : C.n - 1;
+    float* row = C.x + chain * (long long)C.d;
+
+    float2 x[E];
+    {
+      float lo[E], hi[E];
+      load_chain(row, g, lo, hi);
+#pragma unroll
+      for (int e = 0; e < E; ++e) x[e] = make_float2(lo[e], hi[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) mom[e * kThreads] = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto prepare = [&](const float2 (&v)[E]) {
+      float lo[E], hi[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) { lo[e] = v[e].x; hi[e] = v[e].y; }
+      return pot_prepare<POT, E>(C.pot, g, lo, hi);
+    };
+    auto grad = [&](const PotCtx& c, int e, float2 v) {
+      if constexpr (POT == NFMC_POT_ISO_GAUSSIAN) {
+        return mul2(splat2(C.pot.s0), v);
+      } else {
+        float glo, ghi;
+        if (e < E - 1) pot_grad<POT, true>(C.pot, c, g, g.j + g.gs * e, v.x, v.y, glo, ghi);
+        else pot_grad<POT, false>(C.pot, c, g, g.j + g.gs * e, v.x, v.y, glo, ghi);
+        return make_float2(glo, ghi);
+      }
+    };
+    auto mask_last = [&](int e, float2 v) {
+      if (e == E - 1) { v.x = vl_last ? v.x : 0.f; v.y = vh_last ? v.y : 0.f; }
+      return v;
+    };
+    PotCtx ctx = prepare(x);
+
+    for (int k = 0; k < C.n_steps; ++k) {
+      const RngKey key = make_rng_key(C.rng.seed, 0u, C.rng.step0 + (uint64_t)k, (uint64_t)(C.chain0 + chain));
+      float2 p[E], xt[E];
+      float kin0 = 0.f;
+      uint32_t ubits = 0;
+      // ---- momentum p = xi (hmc.py:100), first half-kick with grad U(x0) (hmc.py:51-53) ---------------------------------
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const uint4 w = rng_quad(PK, key, q, g.j);
+        if (q == 0) ubits = w.x;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int e = 2 * q + hh - 1;
+          if (e < 0 || e >= E) continue;
+          float nlo, nhi;
+          box_muller(hh ? w.z : w.x, hh ? w.w : w.y, nlo, nhi);
+          const float2 nz = mask_last(e, make_float2(nlo, nhi));
+          kin0 = fmaf(nz.x * nz.x, 1.f, fmaf(nz.y * nz.y, 1.f, kin0));
+          const float2 gv = grad(ctx, e, x[e]);
+          p[e] = (A.n_leapfrog > 0) ? fma2(NHT, gv, nz) : nz;
+          xt[e] = x[e];
+        }
+      }
+      // ---- trajectory (hmc.py:61-77) -----------------------------------------------------------------------------
+      PotCtx cur = ctx;
+      for (int l = 0; l < A.n_leapfrog; ++l) {
+        const bool more = l + 1 < A.n_leapfrog;
+        if (CTX) {
+#pragma unroll
+          for (int e = 0; e < E; ++e) xt[e] = mask_last(e, fma2(TAU, p[e], xt[e]));          // hmc.py:56-58
+          cur = prepare(xt);
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          if (!CTX) xt[e] = mask_last(e, fma2(TAU, p[e], xt[e]));
+          const float2 gv = grad(cur, e, xt[e]);
+          float2 pv = fma2(NHT, gv, p[e]);                                                  // second half-kick
+          if (more) pv = fma2(NHT, gv, pv);                                                 // next step's first
+          p[e] = mask_last(e, pv);
+        }
+      }
+      bool accept = true;
+      if (!CTX && A.n_leapfrog > 0) cur = prepare(xt);
+      if (A.adjusted) {
+        float kin1 = 0.f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) kin1 = fmaf(p[e].x, p[e].x, fmaf(p[e].y, p[e].y, kin1));
+        const float h0 = ctx.u + 0.5f * group_sum(kin0, g.gs);                        // hmc.py:103-106
+        const float h1 = cur.u + 0.5f * group_sum(kin1, g.gs);                        // hmc.py:107-110
+        const float log_acc = -h1 - (-h0);                                            // hmc.py:111
+        const float u = uniform_from_bits(__shfl_sync(0xffffffffu, ubits, g.grp_base));
+        accept = logf(u) < log_acc;                                                   // hmc.py:112-113
+        if (!(fabsf(log_acc) <= 3.0e38f) && g.j == 0 && active) ++n_bad;
+      }
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        x[e].x = accept ? xt[e].x : x[e].x;
+        x[e].y = accept ? xt[e].y : x[e].y;
+        const float4 m = mom[e * kThreads];
+        const float2 m1 = add2(make_float2(m.x, m.y), x[e]), m2 = fma2(x[e], x[e], make_float2(m.z, m.w));
+        mom[e * kThreads] = make_float4(m1.x, m1.y, m2.x, m2.y);
+      }
+      ctx = select_ctx(accept, cur, ctx);
+      if (accept && g.j == 0 && active) ++n_acc;
+      if (C.sink.samples && active) {
+        float lo[E], hi[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) { lo[e] = x[e].x; hi[e] = x[e].y; }
+        sink_store(C.sink, g, C.n, chain, k, lo, hi);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      float4 m = mom[e * kThreads];
+      if (!active) m = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int kk = g.j + g.gs * e;
+      const float a = across_groups_sum(m.x, g.gs), b = across_groups_sum(m.y, g.gs);
+      const float c = across_groups_sum(m.z, g.gs), dd = across_groups_sum(m.w, g.gs);
+      if (g.lane < g.gs) {
+        if (kk < g.da) { atomicAdd(st.sx + kk, (double)a); atomicAdd(st.sx2 + kk, (double)c); }
+        if (kk < g.db) { atomicAdd(st.sx + g.da + kk, (double)b); atomicAdd(st.sx2 + g.da + kk, (double)dd); }
+      }
+    }
+    if (active) {
+      float lo[E], hi[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) { lo[e] = x[e].x; hi[e] = x[e].y; }
+      store_chain(row, g, lo, hi);
+    }
+  }
+  n_acc = __reduce_add_sync(0xffffffffu, n_acc);
+  n_bad = __reduce_add_sync(0xffffffffu, n_bad);
+  if ((threadIdx.x & 31) == 0) {
+    if (n_acc) atomicAdd(st.cnt + 0, (unsigned long long)n_acc);
+    if (n_bad) atomicAdd(st.cnt + 2, (unsigned long long)n_bad);
+  }
+  if (threadIdx.x == 0) {
+    long long mine = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const long long first = tile * cpc;
+      mine += (C.n - first) < cpc ? (C.n - first) : cpc;
+    }
+    atomicAdd(st.cnt + 1, (unsigned long long)(mine * C.n_steps));
+  }
+  cta_stats_finish(st, C.stats, C.d);
+}
+
 template <int E>
 int launch_hmc(int pot_kind, bool exact, const LocalArgs& A, int grid, size_t smem, cudaStream_t s) {
   NFMC_DISPATCH_POT(pot_kind, {
     if (exact && !A.c.rng.normals && !A.imd) {
-      NFMC_SET_SMEM_RET((hmc_kernel<POT, E, true>), smem);
-      hmc_kernel<POT, E, true><<<grid, kThreads, smem, s>>>(A);
+      // measured (2^20 chains, d = 100, L = 20, ms per step, packed vs scalar): iso 0.62 / 0.67, funnel 1.02 / 1.19,
+      // mixture 1.71 / 1.81, diagonal 1.11 / 0.88, Rosenbrock 0.84 / 0.77 -- potentials whose gradient reads
+      // per-dimension parameters or pairs elements keep the scalar kernel
+      constexpr bool PACKED = POT == NFMC_POT_ISO_GAUSSIAN || POT == NFMC_POT_FUNNEL || POT == NFMC_POT_MIXTURE4;
+      if constexpr (PACKED) {
+        NFMC_SET_SMEM_RET((hmc_fast_kernel<POT, E>), smem);
+        hmc_fast_kernel<POT, E><<<grid, kThreads, smem, s>>>(A);
+      } else {
+        NFMC_SET_SMEM_RET((hmc_kernel<POT, E, true>), smem);
+        hmc_kernel<POT, E, true><<<grid, kThreads, smem, s>>>(A);
+      }
     } else {
       NFMC_SET_SMEM_RET((hmc_kernel<POT, E, false>), smem);
       hmc_kernel<POT, E, false><<<grid, kThreads, smem, s>>>(A);

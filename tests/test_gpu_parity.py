@@ -295,6 +295,30 @@ def test_philox_mode_equals_injected_mode():
     assert ses.read_back()[2][:2] == stats2[2][:2]
 
 
+def test_hmc_philox_mode_equals_injected_mode():
+    """The packed-fp32x2 HMC kernel drawing its own Philox numbers == the generic kernel fed those numbers."""
+    from gpu_util import product_target, run_local_injected
+    from nfmc_b200 import _native as N
+    from nfmc_b200.records import HMCKernel, HMCParameters, MCMCOutput
+    from nfmc_b200.samplers import HMC, DeviceSession
+    dev = torch.device("cuda")
+    for pot, d, tau in (("g1", 100, 0.02), ("fn", 26, 0.05), ("g0", 1000, 0.05)):
+        n, K, L, seed = 300, 4, 7, 99
+        torch.manual_seed(0)
+        x0 = 0.3 * torch.randn(n, d)
+        s = HMC((d,), product_target(pot, d), HMCKernel(event_size=d, step_size=tau, n_leapfrog_steps=L), HMCParameters())
+        out = MCMCOutput((d,), store_samples=True)
+        ses = DeviceSession(x0, (d,), None, seed=seed)
+        buf = s.run_steps(ses, out, K, True)
+        nz = torch.empty(K, n, d, device=dev)
+        un = torch.empty(K, n, device=dev)
+        rng = N.rng_desc(seed, 0, None, None)
+        N.check(N.lib().nfmc_rng_fill(C.byref(rng), 0, 0, d, n, K, N.ptr(nz), N.ptr(un), N.stream_ptr(dev)))
+        samples_inj, ses2, stats2 = run_local_injected(s, x0, nz, un)
+        assert torch.equal(buf.cpu(), samples_inj), pot
+        assert ses.read_back()[2][:2] == stats2[2][:2]
+
+
 # ------------------------------------------------------------------------------------------------------------
 # larger batches: decisions agree except ties, moments agree, ragged tail tiles
 # ------------------------------------------------------------------------------------------------------------
