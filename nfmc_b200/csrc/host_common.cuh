@@ -33,6 +33,23 @@ inline bool layout_for_dim(int d, Layout& L) {
   return true;
 }
 
+// most lanes per chain: the smallest instantiated E whose group still fits a warp.  For latency-bound launches (a
+// training minibatch is a few hundred rows) the serial work per lane is what matters, not lane efficiency.
+inline bool layout_wide(int d, Layout& L) {
+  if (d < 1 || d > NFMC_MAX_DIM) return false;
+  const int db = d - d / 2;
+  const int Es[4] = {4, 7, 13, 16};
+  for (int i = 0; i < 4; ++i) {
+    int gs = 1;
+    while ((db + gs - 1) / gs > Es[i]) gs <<= 1;
+    if (gs <= 32) {
+      L.gs = gs; L.E = Es[i]; L.exact = ((db + gs - 1) / gs == Es[i]);
+      return true;
+    }
+  }
+  return false;
+}
+
 inline PotParams pot_params(const nfmc_potential* p) {
   PotParams P;
   P.params = p->params;

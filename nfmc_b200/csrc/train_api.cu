@@ -202,8 +202,10 @@ int launch_train(const nfmc_realnvp* flow, TrainArgs& A, int64_t n, float* grad,
   if (int e = validate_flow(flow)) return e;
   if (int e = check_train_shape(flow->d, flow->n_coupling, flow->n_linear, flow->hidden)) return e;
   if (!grad || n < 1) return set_error("flow training: bad grad / n");
-  Layout L;
+  Layout L, W;
   if (!layout_for_dim(flow->d, L)) return set_error("flow training: unsupported event size");
+  // a minibatch that fits one wave even at the widest layout is latency-bound: spread each row over more lanes
+  if (layout_wide(flow->d, W) && (n * W.gs + kThreads - 1) / kThreads <= 2 * (int64_t)sm_count()) L = W;
   plan_flow_smem(A.f, flow, L, false);
   A.f.stage_blob = 0;
   A.grad = grad; A.loss = loss; A.n = n;
