@@ -34,6 +34,15 @@ struct GradSink {
     if (SG) asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(sbase + 4u * (unsigned)off), "f"(v) : "memory");
     else atomicAdd(g + off, v);
   }
+  // contiguous parameters (off even / a multiple of 4): one vector reduction to global memory (REDG.ADD.F32x2 / x4)
+  __device__ __forceinline__ void add2(int off, float a, float b) const {
+    if (SG) { add(off, a); add(off + 1, b); }
+    else asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(g + off), "f"(a), "f"(b) : "memory");
+  }
+  __device__ __forceinline__ void add4(int off, float a, float b, float c, float d) const {
+    if (SG) { add(off, a); add(off + 1, b); add(off + 2, c); add(off + 3, d); }
+    else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g + off), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+  }
 };
 
 // v = this lane's contribution to a parameter that is owned by lane position j (same parameter on lanes j, j+gs, ...)
@@ -47,6 +56,33 @@ template <bool SG>
 __device__ __forceinline__ void emit_chain(const GradSink<SG>& G, int off, float v, const Geom& g) {
   const float s = across_groups_sum(g.j == 0 ? v : 0.f, g.gs);
   if (g.lane == 0) G.add(off, s);
+}
+
+template <bool SG>
+__device__ __forceinline__ void emit2(const GradSink<SG>& G, int off, float a, float b, const Geom& g, bool ok) {
+  const float sa = across_groups_sum(a, g.gs), sb = across_groups_sum(b, g.gs);
+  if (g.lane < g.gs && ok) G.add2(off, sa, sb);
+}
+// eight contiguous parameters (one hidden-minor weight row)
+template <bool SG>
+__device__ __forceinline__ void emit8(const GradSink<SG>& G, int off, const float (&v)[kSmallH], float scale, const Geom& g, bool ok) {
+  float s[kSmallH];
+#pragma unroll
+  for (int h = 0; h < kSmallH; ++h) s[h] = across_groups_sum(v[h] * scale, g.gs);
+  if (g.lane < g.gs && ok) {
+    G.add4(off, s[0], s[1], s[2], s[3]);
+    G.add4(off + 4, s[4], s[5], s[6], s[7]);
+  }
+}
+template <bool SG>
+__device__ __forceinline__ void emit8_chain(const GradSink<SG>& G, int off, const float (&v)[kSmallH], float scale, const Geom& g) {
+  float s[kSmallH];
+#pragma unroll
+  for (int h = 0; h < kSmallH; ++h) s[h] = across_groups_sum(g.j == 0 ? v[h] * scale : 0.f, g.gs);
+  if (g.lane == 0) {
+    G.add4(off, s[0], s[1], s[2], s[3]);
+    G.add4(off + 4, s[4], s[5], s[6], s[7]);
+  }
 }
 
 // (y, gy) = output of the layer and dL/dy  ->  (x, gx); returns (dalpha, dbeta)
@@ -77,10 +113,8 @@ __device__ __forceinline__ void affine_train(const FlowDesc& F, const Geom& g, i
     float2 dh = affine_back(inv, act, ph.x, ph.y, rh, hi[e], ghi[e]);
     if (!vl) { lo[e] = 0.f; glo[e] = 0.f; dl = make_float2(0.f, 0.f); }
     if (!vh) { hi[e] = 0.f; ghi[e] = 0.f; dh = make_float2(0.f, 0.f); }
-    emit(G, fw + il, dl.x, g, vl);
-    emit(G, fw + il + 1, dl.y, g, vl);
-    emit(G, fw + ih, dh.x, g, vh);
-    emit(G, fw + ih + 1, dh.y, g, vh);
+    emit2(G, fw + il, dl.x, dl.y, g, vl);
+    emit2(G, fw + ih, dh.x, dh.y, g, vh);
   }
 }
 
@@ -90,7 +124,7 @@ __device__ __forceinline__ void cond_backward_small_train(const FlowDesc& F, con
                                                           bool has_x, const float (&hid)[kSmallH], const float (&src)[E],
                                                           const float (&dua)[E], const float (&dub)[E], float dua_x,
                                                           float dub_x, float (&dsrc)[E], const GradSink<SG>& G) {
-  const int da = F.da, db = F.db, H = F.H;
+  const int da = F.da, db = F.db;
   const int b1 = W + da * kSmallH;
   const int Wl = b1 + kSmallH;
   const int bl = Wl + db * 2 * kSmallH;
@@ -104,36 +138,27 @@ __device__ __forceinline__ void cond_backward_small_train(const FlowDesc& F, con
     const float va = ok ? dua[e] : 0.f, vb = ok ? dub[e] : 0.f;
     const int w = Wl + (ok ? t : 0) * 2 * kSmallH;
 #pragma unroll
-    for (int h = 0; h < kSmallH; ++h) {
+    for (int h = 0; h < kSmallH; ++h)
       acc[h] = fmaf(ldp<false>(F, w + h), va, fmaf(ldp<false>(F, w + kSmallH + h), vb, acc[h]));
-      if (h < H) {                                   // d/dWl[t][c][h] = hid[h] * d out[t][c]
-        emit(G, w + h, hid[h] * va, g, ok);
-        emit(G, w + kSmallH + h, hid[h] * vb, g, ok);
-      }
-    }
-    emit(G, bl + 2 * (ok ? t : 0), va, g, ok);
-    emit(G, bl + 2 * (ok ? t : 0) + 1, vb, g, ok);
+    emit8(G, w, hid, va, g, ok);                     // d/dWl[t][c][h] = hid[h] * d out[t][c]  (padded h: hid = 0)
+    emit8(G, w + kSmallH, hid, vb, g, ok);
+    emit2(G, bl + 2 * (ok ? t : 0), va, vb, g, ok);
   }
   if (has_x) {                                       // the extra target t = da lives on lane j = 0 of each group
     const int w = Wl + da * 2 * kSmallH;
     const float va = g.j == 0 ? dua_x : 0.f, vb = g.j == 0 ? dub_x : 0.f;
 #pragma unroll
-    for (int h = 0; h < kSmallH; ++h) {
+    for (int h = 0; h < kSmallH; ++h)
       acc[h] = fmaf(ldp<false>(F, w + h), va, fmaf(ldp<false>(F, w + kSmallH + h), vb, acc[h]));
-      if (h < H) {
-        emit_chain(G, w + h, hid[h] * dua_x, g);
-        emit_chain(G, w + kSmallH + h, hid[h] * dub_x, g);
-      }
-    }
+    emit8_chain(G, w, hid, dua_x, g);
+    emit8_chain(G, w + kSmallH, hid, dub_x, g);
     emit_chain(G, bl + 2 * da, dua_x, g);
     emit_chain(G, bl + 2 * da + 1, dub_x, g);
   }
   float dpre[kSmallH];
 #pragma unroll
-  for (int h = 0; h < kSmallH; ++h) {
-    dpre[h] = group_sum(acc[h], g.gs) * (1.f - hid[h] * hid[h]);
-    if (h < H) emit_chain(G, b1 + h, dpre[h], g);
-  }
+  for (int h = 0; h < kSmallH; ++h) dpre[h] = group_sum(acc[h], g.gs) * (1.f - hid[h] * hid[h]);
+  emit8_chain(G, b1, dpre, 1.f, g);
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     const int ks = g.j + g.gs * e - shift;
@@ -142,10 +167,8 @@ __device__ __forceinline__ void cond_backward_small_train(const FlowDesc& F, con
     const float v = ok ? src[e] : 0.f;
     float s = 0.f;
 #pragma unroll
-    for (int h = 0; h < kSmallH; ++h) {
-      s = fmaf(ldp<false>(F, w + h), dpre[h], s);
-      if (h < H) emit(G, w + h, v * dpre[h], g, ok);  // d/dW1[h][ks] = src[ks] * dpre[h]
-    }
+    for (int h = 0; h < kSmallH; ++h) s = fmaf(ldp<false>(F, w + h), dpre[h], s);
+    emit8(G, w, dpre, v, g, ok);                      // d/dW1[h][ks] = src[ks] * dpre[h]
     if (ok) dsrc[e] += s;
   }
 }
