@@ -211,3 +211,54 @@ def test_native_variational_fit_reduces_reverse_kl():
     f.variational_fit(potential.log_prob_fn(), n_epochs=300, lr=0.05, n_samples=64)
     after = reverse_kl()
     assert after < before - 5.0, (before, after)
+
+
+def test_training_kernels_edge_cases():
+    """Single row, repeated row indices, minimal event size, accumulate = 1, Philox reproducibility of the reverse-KL draw."""
+    from nfmc_b200 import _native as N
+    from nfmc_b200 import potentials as P
+    from nfmc_b200.flow_train import NativeTrainer, log_prob_autograd
+    dev = torch.device("cuda")
+    for d, Lc, H in [(2, 1, 4), (3, 2, 5)]:
+        f = _flow(d, Lc, H, seed=d)
+        x = torch.randn(5, d, device=dev)
+        params = list(f.bijection.parameters())
+        tr = NativeTrainer(f, dev, 0.05)
+        tr.pack()
+        desc = tr.desc()
+        # one row
+        rows = torch.tensor([3], device=dev)
+        with torch.enable_grad():
+            ref = torch.cat([g.reshape(-1) for g in torch.autograd.grad(-log_prob_autograd(f, x[rows]).sum(), params)])
+        N.check(N.lib().nfmc_flow_nll_grad(C.byref(desc), N.ptr(x), rows.data_ptr(), 1, N.ptr(tr.gblob), N.ptr(tr.loss), 0, tr.stream))
+        tr.unpack(1.0)
+        assert _rel(tr.gtheta, ref) < 5e-4
+        # repeated indices, in two accumulating launches == one launch over all of them
+        rows = torch.tensor([0, 0, 4, 1, 4, 4, 2], device=dev)
+        with torch.enable_grad():
+            loss = -log_prob_autograd(f, x[rows]).sum()
+            ref = torch.cat([g.reshape(-1) for g in torch.autograd.grad(loss, params)])
+        N.check(N.lib().nfmc_flow_nll_grad(C.byref(desc), N.ptr(x), rows.data_ptr(), 3, N.ptr(tr.gblob), N.ptr(tr.loss), 0, tr.stream))
+        N.check(N.lib().nfmc_flow_nll_grad(C.byref(desc), N.ptr(x), rows[3:].contiguous().data_ptr(), 4, N.ptr(tr.gblob),
+                                           N.ptr(tr.loss), 1, tr.stream))
+        tr.unpack(1.0)
+        assert _rel(tr.gtheta, ref) < 5e-4
+        assert abs(float(tr.loss[0]) - float(loss.detach())) <= 1e-4 * abs(float(loss.detach()))
+    # reverse KL with the kernel's own Philox draw: same (seed, step) -> same loss and gradient, next step -> different
+    d = 10
+    f = _flow(d, 2, None, seed=1)
+    tr = NativeTrainer(f, dev, 0.05)
+    tr.pack()
+    desc = tr.desc()
+    pd, keep = P.make_potential("fn", (d,)).descriptor(dev)
+    out = []
+    for step0 in (5, 5, 6):
+        rng = N.rng_desc(1234, step0, None, None)
+        N.check(N.lib().nfmc_flow_kl_grad(C.byref(pd), C.byref(desc), C.byref(rng), 0, 64, N.ptr(tr.gblob), N.ptr(tr.loss), 0, tr.stream))
+        out.append((float(tr.loss[0]), tr.gblob.clone()))
+    assert out[0][0] == out[1][0] and torch.allclose(out[0][1], out[1][1], rtol=1e-5, atol=1e-6)
+    assert out[0][0] != out[2][0]
+    # errors are reported
+    bad = N.RealNVPDesc(d, 2, 3, 16, tr.blob.data_ptr(), tr.blob.numel())
+    assert N.lib().nfmc_flow_nll_grad(C.byref(bad), N.ptr(torch.zeros(4, d, device=dev)), None, 4, N.ptr(tr.gblob), None, 0, tr.stream) != 0
+    assert N.lib().nfmc_flow_param_count(d, 2, 3, 16) == -1
