@@ -155,6 +155,18 @@ def _world() -> int:
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
+def _out_of_time(t0: float, limit, dev) -> bool:
+    """Time-limit test that every rank answers the same way (a rank leaving the loop alone would hang the others)."""
+    if limit is None:
+        return False
+    over = time.time() - t0 > limit
+    if _world() > 1:
+        flag = torch.tensor([1.0 if over else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        over = bool(flag.item() > 0)
+    return over
+
+
 class NativeTrainer:
     """Flat parameter vector + AdamW state on the device, driven through the C ABI."""
 
@@ -165,6 +177,8 @@ class NativeTrainer:
         self.M, self.H = bij.conditioner_shape()
         self.params = [p for p in bij.parameters()]
         self.theta = torch.cat([p.detach().reshape(-1) for p in self.params]).to(dev, torch.float32).contiguous()
+        if _world() > 1:                      # data parallel: every rank starts from rank 0's parameters (this also makes
+            dist.broadcast(self.theta, src=0)  # the data-dependent ActNorm initialisation rank 0's)
         P = N.lib().nfmc_flow_param_count(self.d, self.Lc, self.M, self.H)
         if P != self.theta.numel():
             raise RuntimeError(f"parameter count mismatch: module {self.theta.numel()} vs native {P}")
@@ -275,12 +289,15 @@ def _fit_native(flow, dev, x_train, x_val, n_epochs, lr, batch_size, shuffle, ke
     t0 = time.time()
     try:
         for _ in range(n_epochs):
-            if time_limit_seconds is not None and time.time() - t0 > time_limit_seconds:
+            if _out_of_time(t0, time_limit_seconds, dev):
                 break
             perm = torch.randperm(n, device=dev) if shuffle else torch.arange(n, device=dev)
             tr.nll_epoch(x_train, perm, batch_size, losses)
-            score_t = tr.mean_nll(ref)
-            score, train_sum = (float(v) for v in torch.stack([score_t, losses.sum()]).cpu())   # the epoch's one sync
+            pair = torch.stack([tr.mean_nll(ref), losses.sum()])
+            if _world() > 1:                   # every rank must take the same keep-best / early-stopping decisions
+                dist.all_reduce(pair)
+                pair /= _world()
+            score, train_sum = (float(v) for v in pair.cpu())                                  # the epoch's one sync
             if not math.isfinite(train_sum):
                 raise ValueError("Flow training diverged")                 # the reference rolls back on ValueError
             if score < best:
@@ -306,10 +323,13 @@ def _variational_fit_native(flow, dev, potential, n_epochs, lr, n_samples, early
     t0 = time.time()
     try:
         for epoch in range(n_epochs):
-            if time_limit_seconds is not None and time.time() - t0 > time_limit_seconds:
+            if _out_of_time(t0, time_limit_seconds, dev):
                 break
             prev.copy_(tr.theta)
             tr.kl_step(potential, n_samples, seed, epoch)
+            if _world() > 1:
+                dist.all_reduce(tr.loss)
+                tr.loss /= _world()
             val = float(tr.loss[0]) / n_samples            # loss of the parameters BEFORE this step (as autograd reports it)
             if not math.isfinite(val):
                 tr.theta.copy_(prev)
@@ -359,6 +379,11 @@ def fit(flow, x_train, n_epochs: int = 500, lr: float = 0.05, batch_size=None, s
                            batch_size, shuffle, keep_best_weights, early_stopping, early_stopping_threshold,
                            time_limit_seconds)
     params = [p for p in flow.parameters() if p.requires_grad]
+    if _world() > 1:
+        _init_actnorms(flow, x_train[:batch_size])
+        with torch.no_grad():
+            for p in params:
+                dist.broadcast(p, src=0)
     opt = torch.optim.AdamW(params, lr=lr)
     best, best_state, since_best = math.inf, None, 0
     t0 = time.time()
@@ -366,7 +391,7 @@ def fit(flow, x_train, n_epochs: int = 500, lr: float = 0.05, batch_size=None, s
     try:
         with torch.enable_grad():
             for _ in range(n_epochs):
-                if time_limit_seconds is not None and time.time() - t0 > time_limit_seconds:
+                if _out_of_time(t0, time_limit_seconds, dev):
                     break
                 perm = torch.randperm(n, device=dev) if shuffle else torch.arange(n, device=dev)
                 for i in range(0, n, batch_size):
@@ -379,7 +404,11 @@ def fit(flow, x_train, n_epochs: int = 500, lr: float = 0.05, batch_size=None, s
                     opt.step()
                 with torch.no_grad():
                     ref = x_val if x_val is not None and len(x_val) else x_train
-                    score = float(-log_prob_autograd(flow, ref).mean())
+                    score_t = -log_prob_autograd(flow, ref).mean()
+                    if _world() > 1:
+                        dist.all_reduce(score_t)
+                        score_t /= _world()
+                    score = float(score_t)
                 if score < best:
                     best, since_best = score, 0
                     if keep_best_weights:
@@ -413,7 +442,7 @@ def variational_fit(flow, target_log_prob: Callable, n_epochs: int = 500, lr: fl
     try:
         with torch.enable_grad():
             for _ in range(n_epochs):
-                if time_limit_seconds is not None and time.time() - t0 > time_limit_seconds:
+                if _out_of_time(t0, time_limit_seconds, dev):
                     break
                 opt.zero_grad(set_to_none=True)
                 z = torch.randn(n_samples, d, device=dev)
