@@ -1,6 +1,9 @@
 // api.cu -- error plumbing, device queries and the host-buffer end-to-end entry point of the C ABI.
 #include <cstring>
 #include <string>
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
 #include "host_common.cuh"
 #include "flow.cuh"
 
@@ -99,13 +102,30 @@ extern "C" int nfmc_jump_sample_host(const nfmc_potential* pot_h, const float* p
   flow.blob = blob_dev;
   nfmc_stats st_local{mom_dev, mom_dev + d, cnt_dev};
   nfmc_stats st_jump{mom_dev, mom_dev + d, cnt_dev + 4};
-  // slabs: a multiple of 1024 chains, at least 32768 each, at most 16 of them
-  int64_t slab = (n + 15) / 16;
-  if (slab < 32768) slab = 32768;
-  slab = (slab + 1023) / 1024 * 1024;
+  // slabs: whole waves of BOTH persistent kernels (local steps run 4 CTAs/SM, the jump 3), so that no launch ends on a
+  // partial wave: unit = lcm(4, 3) * SMs CTAs = 12 * SMs * (128 / gs) chains; at least 32768 chains, at most ~24 slabs
+  Layout L;
+  if (!layout_for_dim(d, L)) return set_error("jump_sample_host: unsupported event size");
+  const int64_t unit = 12ll * sm_count() * (kThreads / L.gs);
+  int64_t slab = unit * ((32768 + unit - 1) / unit);
+  while ((n + slab - 1) / slab > 24) slab += unit;
+  if (const char* ev = getenv("NFMC_SLAB_CHAINS")) { const long long v = atoll(ev); if (v >= 1024) slab = v; }
+  // ramp: the first and the last slabs are a quarter / a half of a regular one, so that the copy nothing can overlap with
+  // (H2D of the first slab, D2H of the last) is short
+  std::vector<int64_t> sizes;
+  {
+    const int64_t q = std::max<int64_t>(slab / 4 / 1024 * 1024, 1024), h = std::max<int64_t>(slab / 2 / 1024 * 1024, 1024);
+    int64_t left = n;
+    const bool ramp = n >= 4 * slab;
+    if (ramp) { sizes.push_back(q); sizes.push_back(h); left -= q + h; }
+    const int64_t tail = ramp ? q + h : 0;
+    while (left - tail > 0) { const int64_t c = std::min<int64_t>(slab, left - tail); sizes.push_back(c); left -= c; }
+    if (ramp) { sizes.push_back(h); sizes.push_back(q); }
+  }
   int si = 0;
-  for (int64_t first = 0; first < n; first += slab, ++si) {
-    const int64_t cnt = (n - first) < slab ? (n - first) : slab;
+  int64_t first = 0;
+  for (size_t k = 0; k < sizes.size(); first += sizes[k], ++k, ++si) {
+    const int64_t cnt = sizes[k];
     cudaStream_t ss = g_pipe.streams[si % 3];
     float* xs = x_dev + first * d;
     if (int e = check_cuda(cudaMemcpyAsync(xs, x_host + first * d, (size_t)cnt * d * sizeof(float), cudaMemcpyHostToDevice, ss), "H2D x")) return e;
