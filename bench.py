@@ -237,14 +237,19 @@ def native_arm(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def step_launch(it):
+        """One step of the hot path: K local steps + 1 NF jump for every chain, through the whole-run entry point (chains
+        cut into slabs spread over several streams so that kernels of different slabs overlap)."""
+        N.check(lib.nfmc_jump_sample_device(C.byref(pd), C.byref(fd), N.ptr(x), n, w["kind"], 1, K, float(w["step"]), w["L"],
+                                            None, 1, 1, seed, it * K, it, chain0, C.byref(st_local), C.byref(st_jump), stream))
+
     it = 0
     for _ in range(args.warmup):
-        local_launch(it)
-        jump_launch(it)
+        step_launch(it)
         it += 1
     barrier()
 
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -253,19 +258,34 @@ def native_arm(args):
         if flush is not None:
             flush.fill_(s & 0xFF)
         ev[s][0].record()
-        local_launch(it)
+        step_launch(it)
         ev[s][1].record()
-        jump_launch(it)
-        ev[s][2].record()
         it += 1
     barrier()
     clk = clocks.stop() if rank == 0 else None
-    t_local = sum(e[0].elapsed_time(e[1]) for e in ev) * 1e-3
-    t_total = sum(e[0].elapsed_time(e[2]) for e in ev) * 1e-3
-    tt = torch.tensor([t_total, t_local], device=dev, dtype=torch.float64)
+    t_total = sum(e[0].elapsed_time(e[1]) for e in ev) * 1e-3
+
+    # ---- roofline pass: inside the timed region the launches of different slabs overlap, so a per-launch duration is not
+    #      defined there; the dominant kernel is timed here, right after it, alone on the stream, on the same buffers:
+    #      one full-batch launch of K local steps per step, then the jump launch --------------------------------------
+    r_steps = max(3, min(args.steps, 10))
+    evr = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(r_steps)]
+    for s in range(r_steps):
+        if flush is not None:
+            flush.fill_(s & 0xFF)
+        evr[s][0].record()
+        local_launch(it)
+        evr[s][1].record()
+        jump_launch(it)
+        evr[s][2].record()
+        it += 1
+    barrier()
+    t_local = sum(e[0].elapsed_time(e[1]) for e in evr) * 1e-3 / r_steps * args.steps     # per-launch time x steps
+    t_serial = sum(e[0].elapsed_time(e[2]) for e in evr) * 1e-3 / r_steps * args.steps
+    tt = torch.tensor([t_total, t_local, t_serial], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_total, t_local = float(tt[0]), float(tt[1])
+    t_total, t_local, t_serial = float(tt[0]), float(tt[1]), float(tt[2])
     chain_steps = (K + 1) * n * args.steps * world
     value = chain_steps / t_total
 
@@ -333,12 +353,15 @@ def native_arm(args):
         "roofline": {"bound": "hbm", "kernel": "mala_kernel" if w["kind"] == 0 else "hmc_kernel",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "kernel_ms_per_launch": 1e3 * t_launch,
-                     "kernel_share_of_step": t_local / t_total,
+                     "kernel_share_of_step": t_local / t_serial,
+                     "serial_ms_per_step": 1e3 * t_serial / args.steps,
+                     "timing": "CUDA events around single-stream full-batch launches of the kernel, run right after the timed "
+                               "region on the same buffers (inside the timed region launches of different slabs overlap)",
                      "note": "algorithmic bytes = 8*d per chain-step (state read+write, SURVEY 8d) x K*n chain-steps per launch; "
                              "the kernel keeps the state on chip for all K steps, so real DRAM traffic is ~8*d*n per launch and the "
                              "kernel is bound by fp32/integer issue (Philox + Box-Muller), see DESIGN.md"},
         "e2e": e2e,
-        "gpu_launches": 2 * args.steps,
+        "gpu_launches": 2 * int(lib.nfmc_jump_sample_slabs(d, n, 0)) * args.steps,
         "clocks": clk,
         "acceptance": {"local": acc[0] / max(acc[1], 1), "jump": acc[4] / max(acc[5], 1)},
     }

@@ -213,6 +213,20 @@ NFMC_API int nfmc_flow_fit_epoch(int32_t d, int32_t n_coupling, int32_t n_linear
                         const float* x, const int64_t* perm, int64_t n, int64_t batch_size, float lr, float beta1,
                         float beta2, float eps, float weight_decay, int32_t step0, void* stream);
 
+/* ---- whole-run entry points --------------------------------------------------------------------------------------
+ * JumpNFMC.sample (nfmc/jump.py:156-246) for device-resident chains: n_outer x [n_inner local steps (inner_kind 0 =
+ * Langevin, 1 = HMC, 2 = random-walk Metropolis) + one NF jump], Philox noise, no sample sink.  The batch is cut into
+ * slabs spread over internal streams so that kernels of different slabs overlap; chains keep their global index, the
+ * result equals per-iteration nfmc_*_steps + nfmc_jump_step calls with rng step0 = local_step0 + it*n_inner / jump_step0
+ * + it.  Asynchronous: work is forked from and joined back into `stream`. */
+/* number of slabs (= kernel launches per local stage / per jump) the two whole-run entry points cut n chains into */
+NFMC_API int64_t nfmc_jump_sample_slabs(int32_t d, int64_t n, int32_t host_buffers);
+NFMC_API int nfmc_jump_sample_device(const nfmc_potential* pot, const nfmc_realnvp* flow, float* x, int64_t n,
+                            int32_t inner_kind, int32_t n_outer, int32_t n_inner, float step_size, int32_t n_leapfrog,
+                            const float* inv_mass_diag, int32_t local_adjusted, int32_t jump_adjusted, uint64_t seed,
+                            uint64_t local_step0, uint64_t jump_step0, int64_t chain0, const nfmc_stats* local_stats,
+                            const nfmc_stats* jump_stats, void* stream);
+
 /* ---- host-buffer entry point (end-to-end measurement; the call a reference-side plugin would make) ------
  * Runs `n_outer` iterations of [n_inner local steps (kind 0 = MALA, 1 = HMC) + one NF jump] on host data:
  * copies x_host [n,d] to the device, runs, copies the final state back into x_host, and returns the pooled

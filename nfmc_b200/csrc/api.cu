@@ -45,22 +45,25 @@ extern "C" int64_t nfmc_jump_workspace_bytes(int32_t d, int64_t n, int64_t blob_
                    align256((size_t)2 * d * sizeof(float)) + align256((size_t)2 * d * sizeof(double)) + align256(8 * sizeof(unsigned long long)));
 }
 
-// Host-buffer path: x0 in, final state + pooled statistics out; every copy is inside the call.
-// The chain batch is cut into slabs that are pipelined over three streams -- slab i's H2D copy, its kernels and its
-// D2H copy overlap the neighbours' -- so the PCIe transfers (2 x 4*n*d bytes) hide behind the compute.  Chains keep
-// their global index (chain0 + row), so the result is identical to one big launch.
+// Slab pipeline shared by the two whole-run entry points.  The chain batch is cut into slabs that are spread over four
+// streams.  With host buffers, slab i's H2D copy, its kernels and its D2H copy overlap the neighbours', so the PCIe
+// transfers (2 x 4*n*d bytes) hide behind the compute.  With device-resident chains the point is the kernels themselves:
+// CTAs of the latency-bound jump kernel of one slab run beside CTAs of the issue-bound local kernel of another and fill
+// issue slots those leave idle (measured at d = 100, 2^20 chains: 20.6 -> 19.4 ms per outer iteration).  Chains keep
+// their global index (chain0 + row), so the result is identical to one big launch per kernel.
 namespace {
-struct HostPipe {
-  cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
+constexpr int kPipeStreams = 4;
+struct Pipe {
+  cudaStream_t streams[kPipeStreams] = {};
+  cudaEvent_t fork = nullptr, join[kPipeStreams] = {};
   int device = -1;
 };
-thread_local HostPipe g_pipe;
+thread_local Pipe g_pipe;
 int ensure_pipe() {
   int dev = 0;
   if (int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return e;
   if (g_pipe.device == dev) return 0;
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < kPipeStreams; ++i) {
     if (int e = check_cuda(cudaStreamCreateWithFlags(&g_pipe.streams[i], cudaStreamNonBlocking), "stream create")) return e;
     if (int e = check_cuda(cudaEventCreateWithFlags(&g_pipe.join[i], cudaEventDisableTiming), "event create")) return e;
   }
@@ -68,7 +71,99 @@ int ensure_pipe() {
   g_pipe.device = dev;
   return 0;
 }
+
+struct RunSpec {
+  int inner_kind;        // 0 = Langevin, 1 = HMC, 2 = random-walk Metropolis
+  int n_outer, n_inner;
+  float step_size;
+  int n_leapfrog;
+  const float* inv_mass_diag;   // device or nullptr
+  int local_adjusted, jump_adjusted;
+  uint64_t seed, local_step0, jump_step0;
+  int64_t chain0;
+};
+
+// slab sizes: whole waves of BOTH persistent kernels (local steps run 4 CTAs/SM, the jump 3), so that no launch ends on
+// a partial wave: unit = lcm(4, 3) * SMs CTAs = 12 * SMs * (128 / gs) chains; at least 32768 chains, at most ~24 slabs.
+// With host copies the first and the last slabs are a quarter / a half of a regular one, so that the copy nothing can
+// overlap with (H2D of the first slab, D2H of the last) is short.
+int plan_slabs(int d, int64_t n, bool ramp_wanted, std::vector<int64_t>& sizes) {
+  Layout L;
+  if (!layout_for_dim(d, L)) return set_error("jump_sample: unsupported event size");
+  const int64_t unit = 12ll * sm_count() * (kThreads / L.gs);
+  int64_t slab = unit * ((32768 + unit - 1) / unit);
+  while ((n + slab - 1) / slab > 24) slab += unit;
+  if (const char* ev = getenv("NFMC_SLAB_CHAINS")) { const long long v = atoll(ev); if (v >= 1024) slab = v; }
+  const int64_t q = std::max<int64_t>(slab / 4 / 1024 * 1024, 1024), h = std::max<int64_t>(slab / 2 / 1024 * 1024, 1024);
+  int64_t left = n;
+  const bool ramp = ramp_wanted && n >= 4 * slab;
+  if (ramp) { sizes.push_back(q); sizes.push_back(h); left -= q + h; }
+  const int64_t tail = ramp ? q + h : 0;
+  while (left - tail > 0) { const int64_t c = std::min<int64_t>(slab, left - tail); sizes.push_back(c); left -= c; }
+  if (ramp) { sizes.push_back(h); sizes.push_back(q); }
+  return 0;
+}
+
+// enqueue the whole run; `s` is forked into the pipe streams and joined again (no host synchronisation here)
+int run_pipeline(const nfmc_potential& pot, const nfmc_realnvp& flow, float* x_dev, float* x_host, int64_t n, const RunSpec& R,
+                 const nfmc_stats* st_local, const nfmc_stats* st_jump, cudaStream_t s) {
+  if (int e = ensure_pipe()) return e;
+  const int d = pot.d;
+  std::vector<int64_t> sizes;
+  if (int e = plan_slabs(d, n, x_host != nullptr, sizes)) return e;
+  cudaEventRecord(g_pipe.fork, s);
+  for (int i = 0; i < kPipeStreams; ++i) cudaStreamWaitEvent(g_pipe.streams[i], g_pipe.fork, 0);
+  int64_t first = 0;
+  for (size_t k = 0; k < sizes.size(); first += sizes[k], ++k) {
+    const int64_t cnt = sizes[k];
+    cudaStream_t ss = g_pipe.streams[k % kPipeStreams];
+    float* xs = x_dev + first * d;
+    if (x_host)
+      if (int e = check_cuda(cudaMemcpyAsync(xs, x_host + first * d, (size_t)cnt * d * sizeof(float), cudaMemcpyHostToDevice, ss), "H2D x")) return e;
+    for (int it = 0; it < R.n_outer; ++it) {
+      nfmc_rng r_local{R.seed, R.local_step0 + (uint64_t)it * (uint64_t)R.n_inner, nullptr, nullptr};
+      nfmc_rng r_jump{R.seed, R.jump_step0 + (uint64_t)it, nullptr, nullptr};
+      int e;
+      if (R.inner_kind == 0)
+        e = nfmc_mala_steps(&pot, xs, cnt, R.n_inner, R.step_size, R.inv_mass_diag, R.local_adjusted, &r_local, R.chain0 + first, st_local, nullptr, ss);
+      else if (R.inner_kind == 1)
+        e = nfmc_hmc_steps(&pot, xs, cnt, R.n_inner, R.step_size, R.n_leapfrog, R.inv_mass_diag, R.local_adjusted, &r_local, R.chain0 + first, st_local, nullptr, ss);
+      else
+        e = nfmc_mh_steps(&pot, xs, cnt, R.n_inner, R.inv_mass_diag, R.local_adjusted, &r_local, R.chain0 + first, st_local, nullptr, ss);
+      if (e) return e;
+      if ((e = nfmc_jump_step(&pot, &flow, xs, cnt, R.jump_adjusted, &r_jump, R.chain0 + first, st_jump, nullptr, ss))) return e;
+    }
+    if (x_host)
+      if (int e = check_cuda(cudaMemcpyAsync(x_host + first * d, xs, (size_t)cnt * d * sizeof(float), cudaMemcpyDeviceToHost, ss), "D2H x")) return e;
+  }
+  for (int i = 0; i < kPipeStreams; ++i) {
+    cudaEventRecord(g_pipe.join[i], g_pipe.streams[i]);
+    cudaStreamWaitEvent(s, g_pipe.join[i], 0);
+  }
+  return 0;
+}
 }  // namespace
+
+extern "C" int64_t nfmc_jump_sample_slabs(int32_t d, int64_t n, int32_t host_buffers) {
+  std::vector<int64_t> sizes;
+  if (n < 1 || plan_slabs(d, n, host_buffers != 0, sizes)) return -1;
+  return (int64_t)sizes.size();
+}
+
+extern "C" int nfmc_jump_sample_device(const nfmc_potential* pot, const nfmc_realnvp* flow, float* x, int64_t n,
+                                       int32_t inner_kind, int32_t n_outer, int32_t n_inner, float step_size,
+                                       int32_t n_leapfrog, const float* inv_mass_diag, int32_t local_adjusted,
+                                       int32_t jump_adjusted, uint64_t seed, uint64_t local_step0, uint64_t jump_step0,
+                                       int64_t chain0, const nfmc_stats* local_stats, const nfmc_stats* jump_stats,
+                                       void* stream) {
+  if (int e = validate_pot(pot)) return e;
+  if (!flow || !flow->blob || !x || n < 1) return set_error("jump_sample_device: NULL / empty argument");
+  if (pot->d != flow->d) return set_error("jump_sample_device: potential and flow event sizes differ");
+  if (inner_kind < 0 || inner_kind > 2 || n_outer < 0 || n_inner < 0) return set_error("jump_sample_device: bad inner_kind / iteration counts");
+  const RunSpec R{inner_kind, n_outer, n_inner, step_size, n_leapfrog, inv_mass_diag, local_adjusted, jump_adjusted,
+                  seed, local_step0, jump_step0, chain0};
+  return run_pipeline(*pot, *flow, x, nullptr, n, R, local_stats, jump_stats, (cudaStream_t)stream);
+}
 
 extern "C" int nfmc_jump_sample_host(const nfmc_potential* pot_h, const float* pot_params_host, int64_t pot_params_floats,
                                      const nfmc_realnvp* flow_h, const float* blob_host, float* x_host, int64_t n,
@@ -79,7 +174,7 @@ extern "C" int nfmc_jump_sample_host(const nfmc_potential* pot_h, const float* p
   const int d = pot_h->d;
   if (workspace_bytes < nfmc_jump_workspace_bytes(d, n, flow_h->blob_floats)) return set_error("jump_sample_host: workspace too small");
   if (pot_params_floats > 2 * (int64_t)d) return set_error("jump_sample_host: too many potential parameters");
-  if (int e = ensure_pipe()) return e;
+  if (inner_kind < 0 || inner_kind > 1) return set_error("jump_sample_host: inner_kind must be 0 (MALA) or 1 (HMC)");
   cudaStream_t s = (cudaStream_t)stream;
   unsigned char* w = static_cast<unsigned char*>(workspace);
   float* x_dev = reinterpret_cast<float*>(w); w += align256((size_t)n * d * sizeof(float));
@@ -93,57 +188,15 @@ extern "C" int nfmc_jump_sample_host(const nfmc_potential* pot_h, const float* p
     if (int e = check_cuda(cudaMemcpyAsync(pp_dev, pot_params_host, (size_t)pot_params_floats * sizeof(float), cudaMemcpyHostToDevice, s), "H2D pot")) return e;
   cudaMemsetAsync(mom_dev, 0, (size_t)2 * d * sizeof(double), s);
   cudaMemsetAsync(cnt_dev, 0, 8 * sizeof(unsigned long long), s);
-  cudaEventRecord(g_pipe.fork, s);
-  for (int i = 0; i < 3; ++i) cudaStreamWaitEvent(g_pipe.streams[i], g_pipe.fork, 0);
 
   nfmc_potential pot = *pot_h;
   pot.params = (pot_params_host && pot_params_floats > 0) ? pp_dev : nullptr;
   nfmc_realnvp flow = *flow_h;
   flow.blob = blob_dev;
-  nfmc_stats st_local{mom_dev, mom_dev + d, cnt_dev};
-  nfmc_stats st_jump{mom_dev, mom_dev + d, cnt_dev + 4};
-  // slabs: whole waves of BOTH persistent kernels (local steps run 4 CTAs/SM, the jump 3), so that no launch ends on a
-  // partial wave: unit = lcm(4, 3) * SMs CTAs = 12 * SMs * (128 / gs) chains; at least 32768 chains, at most ~24 slabs
-  Layout L;
-  if (!layout_for_dim(d, L)) return set_error("jump_sample_host: unsupported event size");
-  const int64_t unit = 12ll * sm_count() * (kThreads / L.gs);
-  int64_t slab = unit * ((32768 + unit - 1) / unit);
-  while ((n + slab - 1) / slab > 24) slab += unit;
-  if (const char* ev = getenv("NFMC_SLAB_CHAINS")) { const long long v = atoll(ev); if (v >= 1024) slab = v; }
-  // ramp: the first and the last slabs are a quarter / a half of a regular one, so that the copy nothing can overlap with
-  // (H2D of the first slab, D2H of the last) is short
-  std::vector<int64_t> sizes;
-  {
-    const int64_t q = std::max<int64_t>(slab / 4 / 1024 * 1024, 1024), h = std::max<int64_t>(slab / 2 / 1024 * 1024, 1024);
-    int64_t left = n;
-    const bool ramp = n >= 4 * slab;
-    if (ramp) { sizes.push_back(q); sizes.push_back(h); left -= q + h; }
-    const int64_t tail = ramp ? q + h : 0;
-    while (left - tail > 0) { const int64_t c = std::min<int64_t>(slab, left - tail); sizes.push_back(c); left -= c; }
-    if (ramp) { sizes.push_back(h); sizes.push_back(q); }
-  }
-  int si = 0;
-  int64_t first = 0;
-  for (size_t k = 0; k < sizes.size(); first += sizes[k], ++k, ++si) {
-    const int64_t cnt = sizes[k];
-    cudaStream_t ss = g_pipe.streams[si % 3];
-    float* xs = x_dev + first * d;
-    if (int e = check_cuda(cudaMemcpyAsync(xs, x_host + first * d, (size_t)cnt * d * sizeof(float), cudaMemcpyHostToDevice, ss), "H2D x")) return e;
-    for (int it = 0; it < n_outer; ++it) {
-      nfmc_rng r_local{seed, (uint64_t)it * (uint64_t)n_inner, nullptr, nullptr};
-      nfmc_rng r_jump{seed, (uint64_t)it, nullptr, nullptr};
-      int e = inner_kind == 0
-                  ? nfmc_mala_steps(&pot, xs, cnt, n_inner, step_size, nullptr, 1, &r_local, chain0 + first, &st_local, nullptr, ss)
-                  : nfmc_hmc_steps(&pot, xs, cnt, n_inner, step_size, n_leapfrog, nullptr, 1, &r_local, chain0 + first, &st_local, nullptr, ss);
-      if (e) return e;
-      if ((e = nfmc_jump_step(&pot, &flow, xs, cnt, 1, &r_jump, chain0 + first, &st_jump, nullptr, ss))) return e;
-    }
-    if (int e = check_cuda(cudaMemcpyAsync(x_host + first * d, xs, (size_t)cnt * d * sizeof(float), cudaMemcpyDeviceToHost, ss), "D2H x")) return e;
-  }
-  for (int i = 0; i < 3; ++i) {
-    cudaEventRecord(g_pipe.join[i], g_pipe.streams[i]);
-    cudaStreamWaitEvent(s, g_pipe.join[i], 0);
-  }
+  const nfmc_stats st_local{mom_dev, mom_dev + d, cnt_dev};
+  const nfmc_stats st_jump{mom_dev, mom_dev + d, cnt_dev + 4};
+  const RunSpec R{inner_kind, n_outer, n_inner, step_size, n_leapfrog, nullptr, 1, 1, seed, 0, 0, chain0};
+  if (int e = run_pipeline(pot, flow, x_dev, x_host, n, R, &st_local, &st_jump, s)) return e;
   if (sum_x_host) cudaMemcpyAsync(sum_x_host, mom_dev, (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, s);
   if (sum_x2_host) cudaMemcpyAsync(sum_x2_host, mom_dev + d, (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, s);
   if (counts_host) cudaMemcpyAsync(counts_host, cnt_dev, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);

@@ -379,6 +379,17 @@ class JumpNFMC(Sampler):
     def name(self):
         return 'Jump MCMC'
 
+    def _fused_inner_kind(self):
+        """inner_kind of nfmc_jump_sample_device for this inner sampler, or None if it has no fused whole-run path."""
+        inner = self.inner_sampler
+        if isinstance(inner, Langevin):
+            return 0
+        if isinstance(inner, HMC):
+            return 1
+        if isinstance(inner, MH):
+            return 2
+        return None
+
     def jump(self, ses: DeviceSession, sink=None, z=None, uniforms=None):
         flow: Flow = self.kernel.flow
         pot, keep = self.target.descriptor(ses.device)
@@ -417,6 +428,30 @@ class JumpNFMC(Sampler):
         rs = out.running_samples
         done = 0
         dev = ses.device
+        kind = self._fused_inner_kind()
+        if (kind is not None and T > 0 and not store and not p.fit_nf and time_limit_seconds is None and not show_progress
+                and all(v is None for v in (normals, uniforms, jump_z, jump_uniforms, stage_normals))
+                and not self.kernel.flow.bijection.uses_tensor_cores()):
+            # whole run in one call (nfmc_jump_sample_device): slabs of chains pipelined over several streams so that the
+            # jump kernel of one slab overlaps the local kernel of another; same Philox steps as the loop below
+            pot, keep = self.target.descriptor(dev)
+            fd, keep2 = self.kernel.flow.bijection.descriptor(dev)
+            imd = _imd_device(inner.kernel, dev)
+            st_l, st_j = ses.stats(), ses.stats(jump=True)
+            ses.tic()
+            N.check(N.lib().nfmc_jump_sample_device(
+                C.byref(pot), C.byref(fd), N.ptr(ses.x), ses.n, kind, T, K, float(inner.kernel.step_size),
+                int(getattr(inner.kernel, 'n_leapfrog_steps', 0)), N.ptr(imd), int(bool(inner.params.adjustment)),
+                int(bool(p.adjusted_jumps)), ses.seed & 0xFFFFFFFFFFFFFFFF, ses.local_step, ses.flow_step, ses.chain0,
+                C.byref(st_l), C.byref(st_j), ses.stream))
+            out.statistics.update_elapsed_time(ses.toc())
+            ses.local_step += T * K
+            ses.flow_step += T
+            calls, grads = inner._calls_grads(ses.n)
+            out.statistics.update_counters(n_target_calls=calls * K * T + (2 * ses.n * T if p.adjusted_jumps else 0),
+                                           n_target_gradient_calls=grads * K * T)
+            done = T
+            T = 0                                                                   # nothing left for the loop below
         for i in _progress(range(T), 'Jump MCMC', show_progress):
             if time_limit_seconds is not None and out.statistics.elapsed_time_seconds >= time_limit_seconds:
                 break

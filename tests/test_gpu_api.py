@@ -1,6 +1,7 @@
 """B200: API conformance -- the reference's own smoke tests (/root/reference/test/*.py) restated against nfmc_b200 for the
 strategies on the accelerated path.  Same assertions: return type, sample shapes, finiteness, store_samples semantics,
 flow-string parsing, moment shapes, N-D events, warm-up hand-off."""
+import numpy as np
 import pytest
 import torch
 
@@ -253,3 +254,38 @@ def test_adaptive_imh_refits():
     after = s.kernel.flow.state_dict()
     assert any(not torch.equal(before[k].cpu(), after[k].cpu()) for k in before)
     assert out.samples.shape == (12, 512, 6)
+
+
+@pytest.mark.parametrize("strategy,inner", [("jump_mala", dict(n_iterations=6)), ("jump_hmc", dict(n_iterations=2)),
+                                            ("jump_mh", dict(n_iterations=5)), ("jump_ula", dict(n_iterations=4))])
+def test_fused_whole_run_equals_per_iteration_loop(strategy, inner):
+    """store_samples=False runs go through nfmc_jump_sample_device (slabs over several streams); a time limit forces the
+    per-iteration loop.  Same Philox steps, so states, moments and every counter agree exactly."""
+    import nfmc_b200
+    from nfmc_b200.flow import create_flow_object
+    from nfmc_b200.potentials import make_potential
+    d, n, T = 26, 70001, 3
+    outs = []
+    for limit in (None, 1e9):
+        torch.manual_seed(3)
+        flow = create_flow_object("realnvp", (d,))
+        with torch.no_grad():
+            for p in flow.parameters():
+                p.add_(0.05 * torch.randn_like(p))
+        s = nfmc_b200.create_sampler(make_potential("rb", (d,)), flow=flow, strategy=strategy,
+                                     param_kwargs={"n_iterations": T, "store_samples": False}, inner_param_kwargs=dict(inner),
+                                     inner_kernel_kwargs={} if strategy == "jump_mh" else {"step_size": 0.02})
+        s.seed = 77
+        x0 = 0.5 * torch.randn(n, d)
+        outs.append(s.sample(x0, show_progress=False, time_limit_seconds=limit))
+    a, b = outs
+    la, lb = a.running_samples.last_sample, b.running_samples.last_sample
+    assert torch.equal(torch.isnan(la), torch.isnan(lb))          # unadjusted chains may blow up -- identically
+    assert torch.equal(torch.nan_to_num(la), torch.nan_to_num(lb))
+    sa, sb = a.statistics, b.statistics
+    for f in ("n_accepted_trajectories", "n_attempted_trajectories", "n_accepted_jumps", "n_attempted_jumps", "n_target_calls",
+              "n_target_gradient_calls", "n_divergences"):
+        assert getattr(sa, f) == getattr(sb, f), f
+    if not bool(torch.isnan(la).any()):
+        np.testing.assert_allclose(np.asarray(a.mean), np.asarray(b.mean), rtol=0, atol=1e-6)
+        np.testing.assert_allclose(np.asarray(a.second_moment), np.asarray(b.second_moment), rtol=1e-6, atol=1e-6)
