@@ -164,12 +164,17 @@ __global__ void __launch_bounds__(kTcThreads, MINB) flow_tc_kernel(const TcArgs 
   float* sRed = reinterpret_cast<float*>(sW + ((wbytes + 15) & ~size_t(15)));      // [2][4][128]
   float* sAff = sRed + 2 * kTcGroups * kTcRows;                                     // (Lc+1)*4*d + 4 floats
   const int n_aff = (Lc + 1) * 4 * d + 4;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sAff + ((n_aff + 3) & ~3));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-  const uint32_t bar_w = smem_u32(bars), bar_mma = smem_u32(bars + 1);
+  float* sBias = sAff + ((n_aff + 3) & ~3);                                         // Lc x {b1[H], bl[N2p]}: every coupling's biases
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + (size_t)Lc * (H + N2p));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  // weights of a coupling arrive as two TMA transactions -- the W1 image and the Wl image -- each re-issued for the NEXT
+  // coupling as soon as the GEMM that reads it has completed, i.e. underneath the epilogues
+  const uint32_t bar_w1 = smem_u32(bars), bar_mma = smem_u32(bars + 1), bar_wl = smem_u32(bars + 2);
+  const size_t w1_bytes = (size_t)kTcK1 * H * 2, wl_off = w1_bytes + (size_t)H * 4, wl_bytes = (size_t)N2p * H * 2;
 
   if (tid == 0) {
-    mbar_init(bar_w, 1);
+    mbar_init(bar_w1, 1);
+    mbar_init(bar_wl, 1);
     mbar_init(bar_mma, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -181,14 +186,19 @@ __global__ void __launch_bounds__(kTcThreads, MINB) flow_tc_kernel(const TcArgs 
   const uint32_t tmem_row = tmem_base + ((uint32_t)((r >> 5) * 32) << 16);   // this warp's 32-lane quarter
 
   for (int i = tid; i < n_aff; i += kTcThreads) sAff[i] = __ldg(reinterpret_cast<const float*>(A.blob) + i);
+  const unsigned char* wblob = A.blob + tc_affine_bytes(d, Lc);
+  for (int i = tid; i < Lc * (H + N2p); i += kTcThreads) {
+    const int l = i / (H + N2p), k = i % (H + N2p);
+    const unsigned char* cb = wblob + (size_t)l * wbytes;
+    sBias[i] = __ldg(reinterpret_cast<const float*>(k < H ? cb + w1_bytes : cb + wl_off + wl_bytes) + (k < H ? k : k - H));
+  }
   __syncthreads();
   const float* aff = sAff;
-  const unsigned char* wblob = A.blob + tc_affine_bytes(d, Lc);
   const float log_const = aff[(Lc + 1) * 4 * d];
   const bool inv = (A.mode == 1);
   const bool flip = (Lc & 1) != 0;
   const uint32_t idesc1 = umma_idesc(kTcRows, H), idesc2 = umma_idesc(kTcRows, N2p);
-  uint32_t ph_w = 0, ph_mma = 0;
+  uint32_t ph_w1 = 0, ph_wl = 0, ph_mma = 0;   // weight phases are tracked by the issuing thread only
   const int e0 = g * kTcOwn;   // first owned element index within a half
 
   const long long tiles = (A.n + kTcRows - 1) / kTcRows;
@@ -228,9 +238,12 @@ __global__ void __launch_bounds__(kTcThreads, MINB) flow_tc_kernel(const TcArgs 
     const int n_ops = 2 * Lc + 1;
     // first coupling's weights: issue the TMA bulk copy now (the buffer is free: the previous tile has finished with it)
     const int first_l = inv ? Lc - 1 : 0;
-    if (tid == 0 && Lc > 0) {
-      mbar_expect_tx(bar_w, (uint32_t)wbytes);
-      tma_bulk_load(smem_u32(sW), wblob + (size_t)first_l * wbytes, (uint32_t)wbytes, bar_w);
+    const bool more_tiles = tile + gridDim.x < tiles;
+    if (tid == 0 && Lc > 0 && tile == (long long)blockIdx.x) {       // later tiles: prefetched by the previous tile
+      mbar_expect_tx(bar_w1, (uint32_t)w1_bytes);
+      tma_bulk_load(smem_u32(sW), wblob + (size_t)first_l * wbytes, (uint32_t)w1_bytes, bar_w1);
+      mbar_expect_tx(bar_wl, (uint32_t)wl_bytes);
+      tma_bulk_load(smem_u32(sW + wl_off), wblob + (size_t)first_l * wbytes + wl_off, (uint32_t)wl_bytes, bar_wl);
     }
 #pragma unroll 1
     for (int i = 0; i < n_ops; ++i) {
@@ -252,6 +265,8 @@ __global__ void __launch_bounds__(kTcThreads, MINB) flow_tc_kernel(const TcArgs 
       // ---- coupling l: source half S, target half T ----------------------------------------------------------------------
       const int l = op >> 1;
       const bool src_is_hi = (l & 1) == 0;
+      // the coupling whose weights are staged next: the next one of this tile, else the first one of this CTA's next tile
+      const int next_l = (i + 2 < n_ops) ? ((inv ? n_ops - 1 - (i + 2) : i + 2) >> 1) : (more_tiles ? first_l : -1);
       // A operand of GEMM 1: this thread's 16 source values as bf16 into k-groups 2g, 2g+1 of the [K1/8][128][8] image
 #pragma unroll
       for (int h2 = 0; h2 < 2; ++h2) {
@@ -268,7 +283,8 @@ __global__ void __launch_bounds__(kTcThreads, MINB) flow_tc_kernel(const TcArgs 
       __syncthreads();
       if (tid == 0) {
         tc_fence_after();
-        mbar_wait(bar_w, ph_w);                                   // weights have landed (TMA complete_tx)
+        mbar_wait(bar_w1, ph_w1);                                 // W1 image has landed (TMA complete_tx)
+        ph_w1 ^= 1;
         const uint32_t a0 = smem_u32(sA1), b0 = smem_u32(sW);     // W1 image: [K1/8][H][8]
 #pragma unroll 1
         for (int kk = 0; kk < kTcK1 / 16; ++kk)
@@ -276,15 +292,17 @@ __global__ void __launch_bounds__(kTcThreads, MINB) flow_tc_kernel(const TcArgs 
                    umma_desc(b0 + kk * 2 * (H * 16), H * 16, 128), idesc1, kk > 0);
         umma_commit(bar_mma);
       }
-      mbar_wait(bar_w, ph_w);      // every thread observes the TMA completion itself before it reads b1 / bl
-      ph_w ^= 1;
       mbar_wait(bar_mma, ph_mma);
       ph_mma ^= 1;
       tc_fence_after();
+      if (tid == 0 && next_l >= 0) {                              // GEMM 1 is done with the W1 image: stage the next one
+        mbar_expect_tx(bar_w1, (uint32_t)w1_bytes);
+        tma_bulk_load(smem_u32(sW), wblob + (size_t)next_l * wbytes, (uint32_t)w1_bytes, bar_w1);
+      }
       // ---- epilogue 1: hid = tanh(Hpre + b1) -> bf16 -> A operand image of GEMM 2: [H/8][128][8]; 16-column chunks are
       //      dealt round-robin to the four column groups -------------------------------------------------------------------
       {
-        const float* b1 = reinterpret_cast<const float*>(sW + (size_t)kTcK1 * H * 2);
+        const float* b1 = sBias + (size_t)l * (H + N2p);
 #pragma unroll 1
         for (int c = g; c < H / 16; c += kTcGroups) {
           float v[16];
@@ -303,7 +321,9 @@ __global__ void __launch_bounds__(kTcThreads, MINB) flow_tc_kernel(const TcArgs 
       __syncthreads();
       if (tid == 0) {
         tc_fence_after();
-        const uint32_t a0 = smem_u32(sHid), b0 = smem_u32(sW + (size_t)kTcK1 * H * 2 + (size_t)H * 4);  // Wl image [H/8][N2p][8]
+        mbar_wait(bar_wl, ph_wl);                                 // Wl image has landed
+        ph_wl ^= 1;
+        const uint32_t a0 = smem_u32(sHid), b0 = smem_u32(sW + wl_off);  // Wl image [H/8][N2p][8]
 #pragma unroll 1
         for (int kk = 0; kk < H / 16; ++kk)
           umma_f16(tmem_base + col2, umma_desc(a0 + kk * 2 * (kTcRows * 16), kTcRows * 16, 128),
@@ -313,9 +333,13 @@ __global__ void __launch_bounds__(kTcThreads, MINB) flow_tc_kernel(const TcArgs 
       mbar_wait(bar_mma, ph_mma);
       ph_mma ^= 1;
       tc_fence_after();
+      if (tid == 0 && next_l >= 0) {                              // GEMM 2 is done with the Wl image: stage the next one
+        mbar_expect_tx(bar_wl, (uint32_t)wl_bytes);
+        tma_bulk_load(smem_u32(sW + wl_off), wblob + (size_t)next_l * wbytes + wl_off, (uint32_t)wl_bytes, bar_wl);
+      }
       // ---- epilogue 2: (u_a, u_b) = U + bl -> affine transform of this thread's 16 targets (chunks 2g, 2g+1), log-det ----
       {
-        const float* bl = reinterpret_cast<const float*>(sW + (size_t)kTcK1 * H * 2 + (size_t)H * 4 + (size_t)N2p * H * 2);
+        const float* bl = sBias + (size_t)l * (H + N2p) + H;
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
           const int c = 2 * g + h2;                       // 16 columns = 8 targets (u_a, u_b interleaved)
@@ -338,14 +362,9 @@ __global__ void __launch_bounds__(kTcThreads, MINB) flow_tc_kernel(const TcArgs 
           }
         }
       }
-      // every thread has finished reading the weights (b1, bl) and TMEM: stage the next coupling's weights
+      // every thread has finished reading TMEM before the next coupling's GEMM 1 overwrites the accumulators
       tc_fence_before();
       __syncthreads();
-      if (tid == 0 && i + 2 < n_ops) {
-        const int next_op = inv ? n_ops - 1 - (i + 2) : i + 2;   // the op after the next affine is the next coupling
-        mbar_expect_tx(bar_w, (uint32_t)wbytes);
-        tma_bulk_load(smem_u32(sW), wblob + (size_t)(next_op >> 1) * wbytes, (uint32_t)wbytes, bar_w);
-      }
     }
     // ---- results: the four column groups of a row combine their log-det / base-density shares through shared memory ------
     float sq = 0.f;
@@ -416,7 +435,8 @@ extern "C" int nfmc_flow_tc_pass(const nfmc_realnvp_tc* flow, int32_t mode, cons
   A.d = d; A.Lc = Lc; A.H = H; A.N2p = ((d - d / 2) * 2 + 15) & ~15;
   A.mode = mode; A.in = in; A.out = out; A.aux = aux; A.n = n;
   const size_t wbytes = (tc_coupling_bytes(H, A.N2p) + 15) & ~size_t(15);
-  const size_t smem = (size_t)kTcRows * kTcK1 * 2 + (size_t)kTcRows * H * 2 + wbytes + 2 * kTcGroups * kTcRows * sizeof(float) + (((size_t)(Lc + 1) * 4 * d + 4 + 3) & ~size_t(3)) * sizeof(float) + 64;
+  const size_t smem = (size_t)kTcRows * kTcK1 * 2 + (size_t)kTcRows * H * 2 + wbytes + 2 * kTcGroups * kTcRows * sizeof(float) +
+                      (((size_t)(Lc + 1) * 4 * d + 4 + 3) & ~size_t(3)) * sizeof(float) + (size_t)Lc * (H + A.N2p) * sizeof(float) + 64;
   if (smem > 227 * 1024) return set_error("flow_tc_pass: shared-memory plan exceeds 227 KB");
   const long long tiles = (n + kTcRows - 1) / kTcRows;
   const bool two = (H + A.N2p <= 256) && (2 * (smem + 1024) <= 227 * 1024);
