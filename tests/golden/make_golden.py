@@ -237,6 +237,31 @@ def main():
         out = s.sample(x0.clone(), show_progress=False)
     cases["jump_ess_gm"] = pack(out, t, x0, dict(pot="gm", nll="rb", K=K, T=T, M=M, **flow_arrays(flow, 2, 2, 4)))
 
+    # ---- production shape (d = 100: the exact 4-lane x 13-slot layout, default conditioner H = 5) ------------------------
+    torch.manual_seed(22)
+    d, n, T, K = 100, 40, 2, 4
+    target = make_potential_ref("g1", (d,))
+    flow = make_flow((d,), n_layers=2, perturb=0.05, seed=105)
+    x0 = 0.1 * torch.randn(n, d)
+    s = JumpMALA((d,), target, kernel=NFMCKernel((d,), flow=flow), params=JumpNFMCParameters(n_iterations=T),
+                 inner_kernel=LangevinKernel(event_size=d, step_size=0.004), inner_params=LangevinParameters(n_iterations=K))
+    with Tape() as t:
+        out = s.sample(x0.clone(), show_progress=False)
+    cases["jump_mala_g1_d100"] = pack(out, t, x0, dict(pot="g1", step=0.004, imd=np.ones(d, np.float32), K=K, T=T,
+                                                        **flow_arrays(flow, 2, 2, 5)))
+
+    torch.manual_seed(23)
+    d, n, T, L = 100, 12, 2, 3
+    target = make_potential_ref("fn", (d,))
+    flow = make_flow((d,), n_layers=2, perturb=0.05, seed=106)
+    x0 = 0.3 * torch.randn(n, d)
+    s = NeuTraHMC((d,), target, HMCKernel(event_size=d, step_size=0.01, n_leapfrog_steps=L), HMCParameters(),
+                  NeuTraKernel((d,), flow=flow), NeuTraParameters(n_iterations=T))
+    with Tape() as t:
+        out = s.sample(x0.clone(), show_progress=False)
+    cases["neutra_hmc_fn_d100"] = pack(out, t, x0, dict(pot="fn", step=0.01, imd=np.ones(d, np.float32), T=T, L=L,
+                                                         **flow_arrays(flow, 2, 2, 5)))
+
     for name, arrays in cases.items():
         path = os.path.join(HERE, f"{name}.npz")
         np.savez_compressed(path, **arrays)

@@ -167,7 +167,7 @@ def _check_output(out, g, jump=False):
         assert (st.n_accepted_jumps, st.n_attempted_jumps) == (jacc, jatt)
 
 
-@pytest.mark.parametrize("name,inner", [("jump_mala_g0", "mala"), ("jump_hmc_gm", "hmc")])
+@pytest.mark.parametrize("name,inner", [("jump_mala_g0", "mala"), ("jump_hmc_gm", "hmc"), ("jump_mala_g1_d100", "mala")])
 def test_golden_jump(name, inner):
     from gpu_util import product_target, product_flow_from_oracle
     from nfmc_b200.records import (LangevinKernel, LangevinParameters, HMCKernel, HMCParameters, NFMCKernel,
@@ -210,11 +210,12 @@ def test_golden_fixed_imh():
     _check_output(out, g)
 
 
-def test_golden_neutra_hmc():
+@pytest.mark.parametrize("name", ["neutra_hmc_fn", "neutra_hmc_fn_d100"])
+def test_golden_neutra_hmc(name):
     from gpu_util import product_target, product_flow_from_oracle
     from nfmc_b200.records import HMCKernel, HMCParameters, NeuTraKernel, NeuTraParameters
     from nfmc_b200.samplers import NeuTraHMC
-    g = load_case("neutra_hmc_fn")
+    g = load_case(name)
     n, d = g["x0"].shape
     T = int(g["T"])
     s = NeuTraHMC((d,), product_target(g["pot"], d), HMCKernel(event_size=d, step_size=float(g["step"]), n_leapfrog_steps=int(g["L"])),

@@ -36,8 +36,9 @@ def test_hmc(name):
     _check(g, run)
 
 
-def test_jump_mala():
-    g = load_case("jump_mala_g0")
+@pytest.mark.parametrize("name", ["jump_mala_g0", "jump_mala_g1_d100"])
+def test_jump_mala(name):
+    g = load_case(name)
     run = R.run_jump(torch.from_numpy(g["x0"]), oracle_target(g), oracle_flow(g), "mala", int(g["T"]), int(g["K"]),
                      tape(g), float(g["step"]), torch.from_numpy(g["imd"]))
     _check(g, run, jump=True)
@@ -56,8 +57,9 @@ def test_fixed_imh():
     _check(g, run)
 
 
-def test_neutra_hmc():
-    g = load_case("neutra_hmc_fn")
+@pytest.mark.parametrize("name", ["neutra_hmc_fn", "neutra_hmc_fn_d100"])
+def test_neutra_hmc(name):
+    g = load_case(name)
     run = R.run_neutra_hmc(torch.from_numpy(g["x0"]), oracle_target(g), oracle_flow(g), int(g["T"]), tape(g),
                            float(g["step"]), torch.from_numpy(g["imd"]), n_leapfrog=int(g["L"]))
     _check(g, run)
