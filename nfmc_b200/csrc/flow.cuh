@@ -423,9 +423,15 @@ __device__ __forceinline__ void swap_halves(float (&a)[E], float (&b)[E], bool d
 //      update is fma(r, b, s) with (r, s) = (alpha, beta) or (1/alpha, -beta/alpha)).  ld accumulates THIS LANE's share
 //      of sum_t log alpha_t (the caller group-sums once per pass and applies the sign).  When the source is the high
 //      half the two register arrays are swapped around the layer so that there is a single conditioner call site.
+// Conditioner stash (NeuTra): the inverse pass keeps each coupling's conditioner outputs {u_a[E], u_b[E], hid[8], u_a_x,
+// u_b_x} in per-thread shared memory (element i at stash[i * kThreads]) and the backward sweep reads them back instead of
+// evaluating the conditioner a second time on the same input.
+template <int E>
+__host__ __device__ constexpr int cond_stash_floats() { return 2 * E + kSmallH + 2; }
+
 template <int E, bool SB, bool X, bool SM>
 __device__ __forceinline__ void coupling_apply(const FlowDesc& F, const Geom& g, int l, bool inv, float (&lo)[E], float (&hi)[E],
-                                               float* scr, float& ld) {
+                                               float* scr, float& ld, float* stash = nullptr) {
   float ua[E], ub[E], ua_x, ub_x;
   const bool src_is_hi = (l & 1) == 0;
   const int shift = src_is_hi ? F.db - F.da : 0;
@@ -436,6 +442,14 @@ __device__ __forceinline__ void coupling_apply(const FlowDesc& F, const Geom& g,
   if constexpr (SM) {
     float hid[kSmallH];
     cond_forward_small<E, SB, X>(F, g, Woff, lo, shift, nt_main, has_x, hid, ua, ub, ua_x, ub_x);
+    if (stash) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) { stash[e * kThreads] = ua[e]; stash[(E + e) * kThreads] = ub[e]; }
+#pragma unroll
+      for (int h = 0; h < kSmallH; ++h) stash[(2 * E + h) * kThreads] = hid[h];
+      stash[(2 * E + kSmallH) * kThreads] = ua_x;
+      stash[(2 * E + kSmallH + 1) * kThreads] = ub_x;
+    }
   } else {
     cond_forward_generic<E>(F, g, F.blob + Woff, lo, shift, nt_main, has_x, scr, ua, ub, ua_x, ub_x);
   }
@@ -465,7 +479,7 @@ __device__ __forceinline__ void coupling_apply(const FlowDesc& F, const Geom& g,
 //   b = (b' - beta)/alpha  =>  dU~/dalpha = (1 - gb*b)/alpha,  dU~/dbeta = -gb/alpha,  dU~/db' = gb/alpha.
 template <int E, bool SB, bool X, bool SM>
 __device__ __forceinline__ void coupling_unwind(const FlowDesc& F, const Geom& g, int l, float (&lo)[E], float (&hi)[E],
-                                                float (&glo)[E], float (&ghi)[E], float* scr) {
+                                                float (&glo)[E], float (&ghi)[E], float* scr, const float* stash = nullptr) {
   float ua[E], ub[E], ua_x = 0.f, ub_x = 0.f;
   float dua_x = 0.f, dub_x = 0.f;
   float hid[kSmallH];
@@ -476,8 +490,20 @@ __device__ __forceinline__ void coupling_unwind(const FlowDesc& F, const Geom& g
   const int Woff = F.off_coupling + l * F.coupling_stride;
   swap_halves(lo, hi, src_is_hi);
   swap_halves(glo, ghi, src_is_hi);
-  if constexpr (SM) cond_forward_small<E, SB, X>(F, g, Woff, lo, shift, nt_main, has_x, hid, ua, ub, ua_x, ub_x);
-  else cond_forward_generic<E>(F, g, F.blob + Woff, lo, shift, nt_main, has_x, scr, ua, ub, ua_x, ub_x);
+  if constexpr (SM) {
+    if (stash) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) { ua[e] = stash[e * kThreads]; ub[e] = stash[(E + e) * kThreads]; }
+#pragma unroll
+      for (int h = 0; h < kSmallH; ++h) hid[h] = stash[(2 * E + h) * kThreads];
+      ua_x = stash[(2 * E + kSmallH) * kThreads];
+      ub_x = stash[(2 * E + kSmallH + 1) * kThreads];
+    } else {
+      cond_forward_small<E, SB, X>(F, g, Woff, lo, shift, nt_main, has_x, hid, ua, ub, ua_x, ub_x);
+    }
+  } else {
+    cond_forward_generic<E>(F, g, F.blob + Woff, lo, shift, nt_main, has_x, scr, ua, ub, ua_x, ub_x);
+  }
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     float da_ = 0.f, db_ = 0.f;
@@ -512,13 +538,16 @@ __device__ __forceinline__ void coupling_unwind(const FlowDesc& F, const Geom& g
 //      log|det dz/dx|) or backwards (z -> x, returns log|det dx/dz|).  A single code instance of each layer type, so the
 //      instruction footprint stays small (the jump executes this code once per launch per warp: fetch matters).
 template <int E, bool SB, bool X, bool SM>
-__device__ __forceinline__ float flow_pass(const FlowDesc& F, const Geom& g, bool inv, float (&lo)[E], float (&hi)[E], float* scr) {
+__device__ __forceinline__ float flow_pass(const FlowDesc& F, const Geom& g, bool inv, float (&lo)[E], float (&hi)[E], float* scr,
+                                           float* stash = nullptr) {
   float ld = 0.f;
   const int n_ops = 2 * F.Lc + 1;
 #pragma unroll 1
   for (int i = 0; i < n_ops; ++i) {
     const int op = inv ? n_ops - 1 - i : i;
-    if (op & 1) coupling_apply<E, SB, X, SM>(F, g, op >> 1, inv, lo, hi, scr, ld);
+    if (op & 1)
+      coupling_apply<E, SB, X, SM>(F, g, op >> 1, inv, lo, hi, scr, ld,
+                                   stash ? stash + (size_t)(op >> 1) * cond_stash_floats<E>() * kThreads : nullptr);
     else affine_apply<E, SB, X>(F, g, op >> 1, inv, lo, hi);
   }
   const float tot = group_sum(ld, g.gs) + ldp<SB>(F, F.off_const);
@@ -529,17 +558,19 @@ __device__ __forceinline__ float flow_forward(const FlowDesc& F, const Geom& g, 
   return flow_pass<E, SB, X, SM>(F, g, false, lo, hi, scr);
 }
 template <int E, bool SB, bool X, bool SM>
-__device__ __forceinline__ float flow_inverse(const FlowDesc& F, const Geom& g, float (&lo)[E], float (&hi)[E], float* scr) {
-  return flow_pass<E, SB, X, SM>(F, g, true, lo, hi, scr);
+__device__ __forceinline__ float flow_inverse(const FlowDesc& F, const Geom& g, float (&lo)[E], float (&hi)[E], float* scr,
+                                              float* stash = nullptr) {
+  return flow_pass<E, SB, X, SM>(F, g, true, lo, hi, scr, stash);
 }
 // Given x = T^-1(z) in (lo, hi) and dU/dx in (glo, ghi): walk x -> z, leaving z in (lo, hi) and
 // d/dz [ U(T^-1 z) - log|det dT^-1/dz| ] in (glo, ghi).
 template <int E, bool SB, bool X, bool SM>
 __device__ __forceinline__ void flow_unwind(const FlowDesc& F, const Geom& g, float (&lo)[E], float (&hi)[E],
-                                            float (&glo)[E], float (&ghi)[E], float* scr) {
+                                            float (&glo)[E], float (&ghi)[E], float* scr, const float* stash = nullptr) {
   affine_unwind<E, SB, X>(F, g, 0, lo, hi, glo, ghi);
   for (int l = 0; l < F.Lc; ++l) {
-    coupling_unwind<E, SB, X, SM>(F, g, l, lo, hi, glo, ghi, scr);
+    coupling_unwind<E, SB, X, SM>(F, g, l, lo, hi, glo, ghi, scr,
+                                  stash ? stash + (size_t)l * cond_stash_floats<E>() * kThreads : nullptr);
     affine_unwind<E, SB, X>(F, g, 1 + l, lo, hi, glo, ghi);
   }
 }

@@ -116,7 +116,12 @@ extern "C" int nfmc_neutra_hmc_steps(const nfmc_potential* pot, const nfmc_realn
   A.c.stats = StatsArgs{stats ? stats->sum_x : nullptr, stats ? stats->sum_x2 : nullptr, stats ? stats->counts : nullptr};
   A.c.sink = SinkArgs{sink ? sink->samples : nullptr, sink ? sink->seen0 : 0, (sink && sink->thinning > 0) ? sink->thinning : 1};
   A.tau = step_size; A.imd = inv_mass_diag; A.n_leapfrog = n_leapfrog;
-  const size_t smem = plan_flow_smem(A.f, flow, L, true, true) + (size_t)pot->d * sizeof(float);   // + inverse-mass table
+  size_t smem = plan_flow_smem(A.f, flow, L, true, true) + (size_t)((pot->d + 3) & ~3) * sizeof(float);   // + inverse-mass table
+  // conditioner stash: the inverse pass keeps every coupling's conditioner outputs for the backward sweep (small path
+  // only), if two CTAs of that size still fit an SM
+  const size_t stash_b = (size_t)flow->n_coupling * (2 * L.E + kSmallH + 2) * kThreads * sizeof(float);
+  A.stash = (flow_is_small(flow->n_linear, flow->hidden) && NFMC_NEUTRA_CTAS * (smem + stash_b + 1024) <= 227 * 1024) ? 1 : 0;
+  if (A.stash) smem += stash_b;
   const int grid = grid_for(n, L.gs, NFMC_NEUTRA_CTAS);
   cudaStream_t s = (cudaStream_t)stream;
   A.pot_kind = pot->kind;

@@ -52,6 +52,7 @@ struct NeutraArgs {
   float tau;
   const float* imd;
   int n_leapfrog;
+  int stash;   // shared memory holds a conditioner stash (flow.cuh) behind the mass table
 };
 
 struct TrainArgs {

@@ -23,11 +23,11 @@ namespace nfmc {
 template <int E, bool SB, bool X, bool SM>
 __device__ __forceinline__ float neutra_value_grad(const FlowDesc& F, int pot_kind, const PotParams& P, const Geom& g, const float (&zlo)[E],
                                                    const float (&zhi)[E], float (&glo)[E], float (&ghi)[E], float* scr,
-                                                   bool want_grad) {
+                                                   bool want_grad, float* stash = nullptr) {
   float xlo[E], xhi[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) { xlo[e] = zlo[e]; xhi[e] = zhi[e]; }
-  const float ld_inv = flow_inverse<E, SB, X, SM>(F, g, xlo, xhi, scr);                      // neutra.py:60
+  const float ld_inv = flow_inverse<E, SB, X, SM>(F, g, xlo, xhi, scr, want_grad ? stash : nullptr);   // neutra.py:60
   const PotCtx c = pot_prepare_rt<E>(pot_kind, P, g, xlo, xhi);
   const float value = -((-c.u) + ld_inv);                                          // neutra.py:62-64
   if (want_grad) {
@@ -38,7 +38,7 @@ __device__ __forceinline__ float neutra_value_grad(const FlowDesc& F, int pot_ki
       if (kk >= g.da) glo[e] = 0.f;
       if (kk >= g.db) ghi[e] = 0.f;
     }
-    flow_unwind<E, SB, X, SM>(F, g, xlo, xhi, glo, ghi, scr);
+    flow_unwind<E, SB, X, SM>(F, g, xlo, xhi, glo, ghi, scr, stash);
   }
   return value;
 }
@@ -61,6 +61,8 @@ __global__ void __launch_bounds__(kThreads, NFMC_NEUTRA_MINB) neutra_hmc_kernel(
     for (int i = threadIdx.x; i < C.d; i += blockDim.x) smass[i] = __ldg(A.imd + (flip ? C.d - 1 - i : i));
     __syncthreads();
   }
+  // conditioner stash (flow.cuh): Lc x cond_stash_floats x 128 floats behind the mass table, when the host found room
+  float* stash = (SM && A.stash) ? smass + ((C.d + 3) & ~3) + threadIdx.x : nullptr;
   const int cpc = kThreads / C.gs;
   const long long tiles = (C.n + cpc - 1) / cpc;
   const float half_tau = A.tau / 2;
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(kThreads, NFMC_NEUTRA_MINB) neutra_hmc_kernel(
             zhi[e] = vh ? fmaf(A.tau, unit_mass ? phi[e] : phi[e] * mh, zhi[e]) : 0.f;
           }
         }
-        u1 = neutra_value_grad<E, SB, X, SM>(S.F, A.pot_kind, C.pot, g, zlo, zhi, glo, ghi, S.scr, true);
+        u1 = neutra_value_grad<E, SB, X, SM>(S.F, A.pot_kind, C.pot, g, zlo, zhi, glo, ghi, S.scr, true, stash);
         if (l == 0) u0 = u1;
         else {
 #pragma unroll
