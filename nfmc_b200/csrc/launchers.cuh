@@ -62,6 +62,7 @@ struct TrainArgs {
   const float* x;         // maximum likelihood: data [*, d]
   const long long* rows;  // maximum likelihood: optional row indices [n] into x (a shuffled minibatch)
   long long n;            // rows in this launch
+  int stash;              // keep the conditioner outputs of the loss pass in shared memory for the backward sweep
   int kl;                 // 1: reverse KL (base draw from rng, potential below); 0: maximum likelihood
   int pot_kind;
   PotParams pot;

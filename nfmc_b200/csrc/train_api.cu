@@ -217,6 +217,8 @@ int launch_train(const nfmc_realnvp* flow, TrainArgs& A, int64_t n, float* grad,
   // CTA-local accumulation pays once a CTA sees several warps' worth of rows and the accumulator fits beside the L1
   const int64_t tiles = (n + kThreads / L.gs - 1) / (kThreads / L.gs);
   const bool shared_grad = tiles >= 4 * (int64_t)grid && (size_t)flow->blob_floats * sizeof(float) <= 96 * 1024;
+  const size_t stash_b = (size_t)flow->n_coupling * (2 * L.E + kSmallH + 2) * kThreads * sizeof(float);
+  A.stash = (stash_b + (shared_grad ? (size_t)flow->blob_floats * sizeof(float) : 0) <= 100 * 1024) ? 1 : 0;
   NFMC_DISPATCH_E(L.E, { return launch_flow_train<E>(A, grid, shared_grad, s); });
   return 0;
 }

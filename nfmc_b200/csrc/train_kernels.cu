@@ -175,7 +175,8 @@ __device__ __forceinline__ void cond_backward_small_train(const FlowDesc& F, con
 
 template <int E, bool SG>
 __device__ __forceinline__ void coupling_train(const FlowDesc& F, const Geom& g, int l, bool inv, float act, float (&lo)[E],
-                                               float (&hi)[E], float (&glo)[E], float (&ghi)[E], const GradSink<SG>& G) {
+                                               float (&hi)[E], float (&glo)[E], float (&ghi)[E], const GradSink<SG>& G,
+                                               const float* stash) {
   float ua[E], ub[E], ua_x = 0.f, ub_x = 0.f, dua_x = 0.f, dub_x = 0.f;
   float hid[kSmallH];
   const bool src_is_hi = (l & 1) == 0;
@@ -185,7 +186,16 @@ __device__ __forceinline__ void coupling_train(const FlowDesc& F, const Geom& g,
   const int Woff = F.off_coupling + l * F.coupling_stride;
   swap_halves(lo, hi, src_is_hi);
   swap_halves(glo, ghi, src_is_hi);
-  cond_forward_small<E, false, false>(F, g, Woff, lo, shift, nt_main, has_x, hid, ua, ub, ua_x, ub_x);
+  if (stash) {                                       // conditioner outputs kept by the pass that produced the loss
+#pragma unroll
+    for (int e = 0; e < E; ++e) { ua[e] = stash[e * kThreads]; ub[e] = stash[(E + e) * kThreads]; }
+#pragma unroll
+    for (int h = 0; h < kSmallH; ++h) hid[h] = stash[(2 * E + h) * kThreads];
+    ua_x = stash[(2 * E + kSmallH) * kThreads];
+    ub_x = stash[(2 * E + kSmallH + 1) * kThreads];
+  } else {
+    cond_forward_small<E, false, false>(F, g, Woff, lo, shift, nt_main, has_x, hid, ua, ub, ua_x, ub_x);
+  }
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     float d_ua = 0.f, d_ub = 0.f;
@@ -214,12 +224,15 @@ __device__ __forceinline__ void coupling_train(const FlowDesc& F, const Geom& g,
 // walk the layers back: `inv` = direction of the pass that produced (lo, hi)
 template <int E, bool SG>
 __device__ __forceinline__ void flow_train_sweep(const FlowDesc& F, const Geom& g, bool inv, float act, float (&lo)[E],
-                                                 float (&hi)[E], float (&glo)[E], float (&ghi)[E], const GradSink<SG>& G) {
+                                                 float (&hi)[E], float (&glo)[E], float (&ghi)[E], const GradSink<SG>& G,
+                                                 const float* stash) {
   const int n_ops = 2 * F.Lc + 1;
 #pragma unroll 1
   for (int i = 0; i < n_ops; ++i) {
     const int op = inv ? i : n_ops - 1 - i;
-    if (op & 1) coupling_train<E, SG>(F, g, op >> 1, inv, act, lo, hi, glo, ghi, G);
+    if (op & 1)
+      coupling_train<E, SG>(F, g, op >> 1, inv, act, lo, hi, glo, ghi, G,
+                            stash ? stash + (size_t)(op >> 1) * cond_stash_floats<E>() * kThreads : nullptr);
     else affine_train<E, SG>(F, g, op >> 1, inv, act, lo, hi, glo, ghi, G);
   }
 }
@@ -240,6 +253,8 @@ __global__ void __launch_bounds__(kThreads, 2) flow_train_kernel(const TrainArgs
   const int cpc = kThreads / A.f.gs;
   const long long tiles = (A.n + cpc - 1) / cpc;
   const bool flip = (A.f.Lc & 1) != 0;
+  // conditioner stash (flow.cuh) behind the optional shared accumulator
+  float* stash = A.stash ? sgrad + (SG ? (((int)A.f.blob_floats + 3) & ~3) : 0) + threadIdx.x : nullptr;
   double loss = 0.0;
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const long long chain_raw = tile * cpc + threadIdx.x / A.f.gs;
@@ -251,15 +266,15 @@ __global__ void __launch_bounds__(kThreads, 2) flow_train_kernel(const TrainArgs
     if (!A.kl) {
       const long long row = A.rows ? A.rows[chain] : chain;
       load_chain(A.x + row * (long long)A.f.d, g, lo, hi);
-      const float ld = flow_pass<E, false, false, true>(F, g, false, lo, hi, nullptr);
+      const float ld = flow_pass<E, false, false, true>(F, g, false, lo, hi, nullptr, stash);
       li = -(base_log_prob(g, lo, hi) + ld);                                   // -log q(x)
 #pragma unroll
       for (int e = 0; e < E; ++e) { glo[e] = act * lo[e]; ghi[e] = act * hi[e]; }   // d/dz of |z|^2 / 2
-      flow_train_sweep<E, SG>(F, g, false, act, lo, hi, glo, ghi, G);
+      flow_train_sweep<E, SG>(F, g, false, act, lo, hi, glo, ghi, G, stash);
     } else {
       draw_base(A.rng, g, flip, A.n, chain, A.chain0, 0, lo, hi);
       const float lbase = base_log_prob(g, lo, hi);
-      const float ld_inv = flow_pass<E, false, false, true>(F, g, true, lo, hi, nullptr);
+      const float ld_inv = flow_pass<E, false, false, true>(F, g, true, lo, hi, nullptr, stash);
       const PotCtx c = pot_prepare_rt<E>(A.pot_kind, A.pot, g, lo, hi);
       li = lbase - ld_inv + c.u;                                                // log q(x) + U(x)
 #pragma unroll
@@ -269,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 2) flow_train_kernel(const TrainArgs
         glo[e] = kk < g.da ? act * glo[e] : 0.f;
         ghi[e] = kk < g.db ? act * ghi[e] : 0.f;
       }
-      flow_train_sweep<E, SG>(F, g, true, act, lo, hi, glo, ghi, G);
+      flow_train_sweep<E, SG>(F, g, true, act, lo, hi, glo, ghi, G, stash);
     }
     if (active && g.j == 0) loss += (double)li;
   }
@@ -287,12 +302,14 @@ __global__ void __launch_bounds__(kThreads, 2) flow_train_kernel(const TrainArgs
 // shared_grad: accumulate per CTA in shared memory (smem = blob_floats * 4 bytes); chosen by the caller for large batches
 template <int E>
 int launch_flow_train(const TrainArgs& A, int grid, bool shared_grad, cudaStream_t s) {
+  const size_t stash_b = A.stash ? (size_t)A.f.Lc * cond_stash_floats<E>() * kThreads * sizeof(float) : 0;
   if (shared_grad) {
-    const size_t smem = (size_t)A.f.blob_floats * sizeof(float);
+    const size_t smem = (size_t)((A.f.blob_floats + 3) & ~3ll) * sizeof(float) + stash_b;
     NFMC_SET_SMEM_RET((flow_train_kernel<E, true>), smem);
     flow_train_kernel<E, true><<<grid, kThreads, smem, s>>>(A);
   } else {
-    flow_train_kernel<E, false><<<grid, kThreads, 0, s>>>(A);
+    NFMC_SET_SMEM_RET((flow_train_kernel<E, false>), stash_b);
+    flow_train_kernel<E, false><<<grid, kThreads, stash_b, s>>>(A);
   }
   return check_cuda(cudaGetLastError(), "flow_train_kernel launch");
 }
