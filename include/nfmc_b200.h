@@ -171,6 +171,13 @@ NFMC_API int nfmc_imh_steps(const nfmc_potential* pot, const nfmc_realnvp* flow,
 NFMC_API int nfmc_neutra_hmc_steps(const nfmc_potential* pot, const nfmc_realnvp* flow, float* z, int64_t n, int32_t n_steps,
                           float step_size, int32_t n_leapfrog, const float* inv_mass_diag, const nfmc_rng* rng,
                           int64_t chain0, const nfmc_stats* stats, const nfmc_sink* sink, void* stream);
+/* T random-walk Metropolis steps in the latent space of the flow -- NeuTraMH (nfmc/neutra.py:147-159) = MH.propose
+ * (mcmc/mh.py:44-73) on NeuTra.adjusted_target: z' = z + inv_mass_diag * xi (NULL = ones), accept iff
+ * log u < U~(z) - U~(z'); adjusted = 0 -> plain random walk */
+NFMC_API int nfmc_neutra_mh_steps(const nfmc_potential* pot, const nfmc_realnvp* flow, float* z, int64_t n, int32_t n_steps,
+                         const float* inv_mass_diag, int32_t adjusted, const nfmc_rng* rng, int64_t chain0,
+                         const nfmc_stats* stats, const nfmc_sink* sink, void* stream);
+
 /* latent potential and its gradient (for tests): u [n], grad [n,d] (grad may be NULL) */
 NFMC_API int nfmc_neutra_potential(const nfmc_potential* pot, const nfmc_realnvp* flow, const float* z, float* u, float* grad,
                           int64_t n, void* stream);

@@ -2,8 +2,8 @@
 
 Strategies on the accelerated hot path: ``jump_mala``, ``jump_ula``, ``jump_hmc``, ``jump_uhmc``, ``neutra_hmc``,
 ``imh`` / ``fixed_imh``, ``adaptive_imh`` and the local kernels they are built from (``mala``, ``ula``, ``hmc``,
-``uhmc``, ``mh`` / ``jump_mh``, ``ess`` / ``jump_ess``).  Everything else the reference lists (``tess``, ``dlmc``, ``nuts``,
-``neutra_mh`` ...) is outside the scope table and raises ``NotImplementedError`` -- there is no eager fallback.
+``uhmc``, ``mh`` / ``jump_mh`` / ``neutra_mh``, ``ess`` / ``jump_ess``).  Everything else the reference lists (``tess``, ``dlmc``,
+``nuts`` ...) is outside the scope table and raises ``NotImplementedError`` -- there is no eager fallback.
 """
 from __future__ import annotations
 
@@ -17,12 +17,12 @@ from .flow import Flow, create_flow_object
 from .potentials import Potential, resolve_target
 from .records import (ESSKernel, ESSParameters, MHKernel, MHParameters, HMCKernel, HMCParameters, IMHKernel, IMHParameters, JumpNFMCParameters, LangevinKernel,
                       LangevinParameters, MCMCOutput, NeuTraKernel, NeuTraParameters, NFMCKernel)
-from .samplers import (ESS, JumpESS, MH, JumpMH, HMC, MALA, UHMC, ULA, AdaptiveIMH, FixedIMH, JumpHMC, JumpMALA, JumpUHMC, JumpULA, NeuTraHMC,
+from .samplers import (ESS, JumpESS, MH, JumpMH, NeuTraMH, HMC, MALA, UHMC, ULA, AdaptiveIMH, FixedIMH, JumpHMC, JumpMALA, JumpUHMC, JumpULA, NeuTraHMC,
                        Sampler)
 
 LOCAL_STRATEGIES = ('hmc', 'uhmc', 'ula', 'mala', 'mh', 'ess')
 NF_STRATEGIES = ('imh', 'fixed_imh', 'adaptive_imh', 'jump_mala', 'jump_ula', 'jump_hmc', 'jump_uhmc', 'jump_mh', 'jump_ess',
-                 'neutra_hmc')
+                 'neutra_hmc', 'neutra_mh')
 
 
 def get_supported_samplers():
@@ -115,6 +115,10 @@ def create_sampler(target, event_shape: Optional[Tuple[int, ...]] = None, flow: 
                           params=JumpNFMCParameters(**param_kwargs),
                           inner_kernel=HMCKernel(event_size=event_size, **inner_kernel_kwargs),
                           inner_params=HMCParameters(**inner_param_kwargs)))
+    if strategy == 'neutra_mh':                                                          # reference: sample.py:232-237
+        return finish(NeuTraMH(event_shape, target, MHKernel(event_size=event_size, **inner_kernel_kwargs),
+                               MHParameters(**inner_param_kwargs), NeuTraKernel(event_shape, flow=flow_object),
+                               NeuTraParameters(**param_kwargs)))
     # neutra_hmc
     return finish(NeuTraHMC(event_shape, target, HMCKernel(event_size=event_size, **inner_kernel_kwargs),
                             HMCParameters(**inner_param_kwargs), NeuTraKernel(event_shape, flow=flow_object),

@@ -115,7 +115,7 @@ extern "C" int nfmc_neutra_hmc_steps(const nfmc_potential* pot, const nfmc_realn
   A.c.rng = RngArgs{rng ? rng->seed : 0, rng ? rng->step0 : 0, rng ? rng->normals : nullptr, rng ? rng->uniforms : nullptr};
   A.c.stats = StatsArgs{stats ? stats->sum_x : nullptr, stats ? stats->sum_x2 : nullptr, stats ? stats->counts : nullptr};
   A.c.sink = SinkArgs{sink ? sink->samples : nullptr, sink ? sink->seen0 : 0, (sink && sink->thinning > 0) ? sink->thinning : 1};
-  A.tau = step_size; A.imd = inv_mass_diag; A.n_leapfrog = n_leapfrog;
+  A.tau = step_size; A.imd = inv_mass_diag; A.n_leapfrog = n_leapfrog; A.adjusted = 1;
   size_t smem = plan_flow_smem(A.f, flow, L, true, true) + (size_t)((pot->d + 3) & ~3) * sizeof(float);   // + inverse-mass table
   // conditioner stash: the inverse pass keeps every coupling's conditioner outputs for the backward sweep (small path
   // only), if two CTAs of that size still fit an SM
@@ -126,6 +126,31 @@ extern "C" int nfmc_neutra_hmc_steps(const nfmc_potential* pot, const nfmc_realn
   cudaStream_t s = (cudaStream_t)stream;
   A.pot_kind = pot->kind;
   NFMC_DISPATCH_E(L.E, { return launch_neutra_hmc<E>(A, grid, smem, s); });
+  return 0;
+}
+
+extern "C" int nfmc_neutra_mh_steps(const nfmc_potential* pot, const nfmc_realnvp* flow, float* z, int64_t n, int32_t n_steps,
+                                    const float* inv_mass_diag, int32_t adjusted, const nfmc_rng* rng, int64_t chain0,
+                                    const nfmc_stats* stats, const nfmc_sink* sink, void* stream) {
+  if (int e = validate_pot(pot)) return e;
+  if (int e = validate_flow(flow)) return e;
+  if (pot->d != flow->d) return set_error("neutra_mh: potential and flow event sizes differ");
+  if (!z || n < 1 || n_steps < 0) return set_error("neutra_mh: bad z/n/n_steps");
+  if (n_steps == 0) return 0;
+  Layout L;
+  if (!layout_for_dim(pot->d, L)) return set_error("neutra_mh: unsupported event size");
+  NeutraArgs A;
+  A.c.pot = pot_params(pot);
+  A.c.x = z; A.c.n = n; A.c.chain0 = chain0; A.c.d = pot->d; A.c.gs = L.gs; A.c.n_steps = n_steps;
+  A.c.rng = RngArgs{rng ? rng->seed : 0, rng ? rng->step0 : 0, rng ? rng->normals : nullptr, rng ? rng->uniforms : nullptr};
+  A.c.stats = StatsArgs{stats ? stats->sum_x : nullptr, stats ? stats->sum_x2 : nullptr, stats ? stats->counts : nullptr};
+  A.c.sink = SinkArgs{sink ? sink->samples : nullptr, sink ? sink->seen0 : 0, (sink && sink->thinning > 0) ? sink->thinning : 1};
+  A.tau = 0.f; A.imd = inv_mass_diag; A.n_leapfrog = 0; A.stash = 0; A.adjusted = adjusted;
+  A.pot_kind = pot->kind;
+  const size_t smem = plan_flow_smem(A.f, flow, L, true, true) + (size_t)((pot->d + 3) & ~3) * sizeof(float);
+  const int grid = grid_for(n, L.gs, 3);
+  cudaStream_t s = (cudaStream_t)stream;
+  NFMC_DISPATCH_E(L.E, { return launch_neutra_mh<E>(A, grid, smem, s); });
   return 0;
 }
 

@@ -53,6 +53,7 @@ struct NeutraArgs {
   const float* imd;
   int n_leapfrog;
   int stash;   // shared memory holds a conditioner stash (flow.cuh) behind the mass table
+  int adjusted;  // NeuTra MH only: 0 = plain random walk
 };
 
 struct TrainArgs {
@@ -83,6 +84,7 @@ template <int E> int launch_flow_train(const TrainArgs& A, int grid, bool shared
 template <int E> int launch_jump(const JumpArgs& A, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_jump_accept(const AcceptArgs& A, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_neutra_hmc(const NeutraArgs& A, int grid, size_t smem, cudaStream_t s);
+template <int E> int launch_neutra_mh(const NeutraArgs& A, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_neutra_potential(const FlowArgs& FA, int pot_kind, const PotParams& P, const float* z, float* u,
                                              float* grad, long long n, int grid, size_t smem, cudaStream_t s);
 

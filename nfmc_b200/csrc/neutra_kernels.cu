@@ -235,6 +235,120 @@ __global__ void __launch_bounds__(kThreads) neutra_potential_kernel(FlowArgs FA,
 }
 
 
+// ---------------------------------------------------------------------------------------------------------
+// NeuTra MH (nfmc/neutra.py:147-159): random-walk Metropolis (mcmc/mh.py:44-73) in the latent space on U~.  One inverse
+// pass + one potential per step, no gradient; U~ of the current state is carried (the reference re-evaluates it, to the
+// same value).  z' = z + inv_mass_diag * xi; accept iff log u < U~(z) - U~(z').
+// ---------------------------------------------------------------------------------------------------------
+template <int E, bool SB, bool X, bool SM>
+__global__ void __launch_bounds__(kThreads, 3) neutra_mh_kernel(const NeutraArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const ChainArgs& C = A.c;
+  const Geom g = make_geom(C.d, C.gs);
+  FlowSmem S = flow_smem_init<SB>(smem, A.f, true);
+  const bool flip = (A.f.Lc & 1) != 0;
+  const bool unit_mass = (A.imd == nullptr);
+  float* smass = reinterpret_cast<float*>(S.mom - threadIdx.x + (size_t)E * kThreads);   // [d] proposal scale, PHYSICAL order
+  if (!unit_mass) {
+    for (int i = threadIdx.x; i < C.d; i += blockDim.x) smass[i] = __ldg(A.imd + (flip ? C.d - 1 - i : i));
+    __syncthreads();
+  }
+  const int cpc = kThreads / C.gs;
+  const long long tiles = (C.n + cpc - 1) / cpc;
+  unsigned int n_acc = 0, n_bad = 0;
+
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long chain_raw = tile * cpc + threadIdx.x / C.gs;
+    const bool active = chain_raw < C.n;
+    const long long chain = active ? chain_raw : C.n - 1;
+    float* row = C.x + chain * (long long)C.d;
+    float zlo[E], zhi[E], dlo[E], dhi[E];
+    if (flip) load_chain_flipped(row, g, zlo, zhi); else load_chain(row, g, zlo, zhi);
+#pragma unroll
+    for (int e = 0; e < E; ++e) S.mom[e * kThreads] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float u_cur = neutra_value_grad<E, SB, X, SM>(S.F, A.pot_kind, C.pot, g, zlo, zhi, dlo, dhi, S.scr, false);
+
+    for (int k = 0; k < C.n_steps; ++k) {
+      StepNoise<E> nz;
+      if (C.rng.normals) {
+        const float* nr = C.rng.normals + ((long long)k * C.n + chain) * (long long)C.d;
+        if (flip) load_chain_flipped(nr, g, nz.lo, nz.hi); else load_chain(nr, g, nz.lo, nz.hi);
+        nz.ubits = 0;
+      } else {
+        const RngKey key = make_rng_key(C.rng.seed, 0u, C.rng.step0 + (uint64_t)k, (uint64_t)(C.chain0 + chain));
+        draw_step_noise<E>(key, g.j, nz);
+      }
+      float plo[E], phi[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int kk = g.j + g.gs * e;
+        const bool vl = slot_ok<X, E>(e, kk, g.da), vh = slot_ok<X, E>(e, kk, g.db);
+        const float ml = unit_mass ? 1.f : smass[vl ? kk : 0], mh = unit_mass ? 1.f : smass[g.da + (vh ? kk : 0)];
+        plo[e] = vl ? zlo[e] + nz.lo[e] * ml : 0.f;                                  // mh.py:52-56
+        phi[e] = vh ? zhi[e] + nz.hi[e] * mh : 0.f;
+      }
+      bool accept = true;
+      float u_p = u_cur;
+      if (A.adjusted) {
+        u_p = neutra_value_grad<E, SB, X, SM>(S.F, A.pot_kind, C.pot, g, plo, phi, dlo, dhi, S.scr, false);
+        const float log_ratio = (-u_p) - (-u_cur) + 0.f - 0.f;                       // mh.py:59
+        float u;
+        if (C.rng.uniforms) u = __ldg(C.rng.uniforms + (long long)k * C.n + chain);
+        else u = uniform_from_bits(__shfl_sync(0xffffffffu, nz.ubits, g.grp_base));
+        accept = logf(u) < log_ratio;                                                // mh.py:60
+        if (!(fabsf(log_ratio) <= 3.0e38f) && g.j == 0 && active) ++n_bad;
+      }
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        zlo[e] = accept ? plo[e] : zlo[e];
+        zhi[e] = accept ? phi[e] : zhi[e];
+        float4 m = S.mom[e * kThreads];
+        m.x += zlo[e]; m.y += zhi[e]; m.z = fmaf(zlo[e], zlo[e], m.z); m.w = fmaf(zhi[e], zhi[e], m.w);
+        S.mom[e * kThreads] = m;
+      }
+      u_cur = accept ? u_p : u_cur;
+      if (accept && g.j == 0 && active) ++n_acc;
+      if (C.sink.samples && active) {
+        const long long idx = C.sink.seen0 + k;
+        if (idx % C.sink.thinning == 0) {
+          const long long first = (C.sink.seen0 + C.sink.thinning - 1) / C.sink.thinning;
+          float* dst = C.sink.samples + ((idx / C.sink.thinning - first) * C.n + chain) * (long long)C.d;
+          if (flip) store_chain_flipped(dst, g, zlo, zhi); else store_chain(dst, g, zlo, zhi);
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      float4 m = S.mom[e * kThreads];
+      if (!active) m = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int kk = g.j + g.gs * e;
+      const float a = across_groups_sum(m.x, g.gs), b = across_groups_sum(m.y, g.gs);
+      const float c = across_groups_sum(m.z, g.gs), dd = across_groups_sum(m.w, g.gs);
+      if (g.lane < g.gs) {
+        const int il = flip ? g.d - 1 - kk : kk, ih = flip ? g.d - 1 - (g.da + kk) : g.da + kk;
+        if (kk < g.da) { atomicAdd(S.st.sx + il, (double)a); atomicAdd(S.st.sx2 + il, (double)c); }
+        if (kk < g.db) { atomicAdd(S.st.sx + ih, (double)b); atomicAdd(S.st.sx2 + ih, (double)dd); }
+      }
+    }
+    if (active) { if (flip) store_chain_flipped(row, g, zlo, zhi); else store_chain(row, g, zlo, zhi); }
+  }
+  n_acc = __reduce_add_sync(0xffffffffu, n_acc);
+  n_bad = __reduce_add_sync(0xffffffffu, n_bad);
+  if ((threadIdx.x & 31) == 0) {
+    if (n_acc) atomicAdd(S.st.cnt + 0, (unsigned long long)n_acc);
+    if (n_bad) atomicAdd(S.st.cnt + 2, (unsigned long long)n_bad);
+  }
+  if (threadIdx.x == 0) {
+    long long mine = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const long long first = tile * cpc;
+      mine += (C.n - first) < cpc ? (C.n - first) : cpc;
+    }
+    atomicAdd(S.st.cnt + 1, (unsigned long long)(mine * C.n_steps));
+  }
+  cta_stats_finish(S.st, C.stats, C.d);
+}
+
 template <int E>
 int launch_neutra_hmc(const NeutraArgs& A, int grid, size_t smem, cudaStream_t s) {
   // exact-layout specialisations are instantiated for the production shapes (E = 13, 16) only; the generic
@@ -277,6 +391,26 @@ int launch_neutra_potential(const FlowArgs& FA, int pot_kind, const PotParams& P
   return check_cuda(cudaGetLastError(), "neutra_potential_kernel launch");
 }
 template int launch_neutra_hmc<NFMC_ONLY_E>(const NeutraArgs&, int, size_t, cudaStream_t);
+
+template <int E>
+int launch_neutra_mh(const NeutraArgs& A, int grid, size_t smem, cudaStream_t s) {
+  constexpr bool XE = (E == 13 || E == 16);
+  const bool small = flow_is_small(A.f.M, A.f.H);
+  const bool xl = A.f.exact && XE;
+#define NFMC_LAUNCH(SBv, Xv, Sv)                                                   \
+  do {                                                                             \
+    NFMC_SET_SMEM_RET((neutra_mh_kernel<E, SBv, Xv, Sv>), smem);                   \
+    neutra_mh_kernel<E, SBv, Xv, Sv><<<grid, kThreads, smem, s>>>(A);              \
+  } while (0)
+  if (!small) { if (A.f.stage_blob) NFMC_LAUNCH(true, false, false); else NFMC_LAUNCH(false, false, false); }
+  else if (A.f.stage_blob && xl) NFMC_LAUNCH(true, XE, true);
+  else if (A.f.stage_blob) NFMC_LAUNCH(true, false, true);
+  else if (xl) NFMC_LAUNCH(false, XE, true);
+  else NFMC_LAUNCH(false, false, true);
+#undef NFMC_LAUNCH
+  return check_cuda(cudaGetLastError(), "neutra_mh_kernel launch");
+}
+template int launch_neutra_mh<NFMC_ONLY_E>(const NeutraArgs&, int, size_t, cudaStream_t);
 template int launch_neutra_potential<NFMC_ONLY_E>(const FlowArgs&, int, const PotParams&, const float*, float*, float*, long long, int, size_t, cudaStream_t);
 
 }  // namespace nfmc

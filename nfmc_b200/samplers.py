@@ -722,7 +722,6 @@ class NeuTraHMC(Sampler):
         out = MCMCOutput(event_shape, store_samples=store)
         ses = DeviceSession(x0, event_shape, self.device, self.seed, self.chain0)
         dev = ses.device
-        L = int(self.inner_kernel.n_leapfrog_steps)
         pot, keep = self.target.descriptor(dev)
         fd, keep2 = self.kernel.flow.bijection.descriptor(dev)
         imd = _imd_device(self.inner_kernel, dev)
@@ -746,10 +745,7 @@ class NeuTraHMC(Sampler):
             rng = N.rng_desc(ses.seed, ses.local_step, nz, un)
             st = ses.stats()
             ses.tic()
-            N.check(N.lib().nfmc_neutra_hmc_steps(C.byref(pot), C.byref(fd), N.ptr(ses.x), ses.n, k,
-                                                  float(self.inner_kernel.step_size), L, N.ptr(imd), C.byref(rng),
-                                                  ses.chain0, C.byref(st), None if sink is None else C.byref(sink),
-                                                  ses.stream))
+            self._launch_latent(ses, pot, fd, k, imd, rng, st, sink)
             out.statistics.update_elapsed_time(ses.toc())
             ses.local_step += k
             done += k
@@ -767,13 +763,24 @@ class NeuTraHMC(Sampler):
                 prev_acc = acc
         sx, sx2, cnt = ses.read_back()
         out.statistics.expectations.add_sums(sx, sx2, ses.n * done)
+        calls, grads = self._calls_grads(ses.n)
         out.statistics.update_counters(n_accepted_trajectories=cnt[0], n_attempted_trajectories=cnt[1],
-                                       n_target_calls=(2 * L + 2) * ses.n * done,
-                                       n_target_gradient_calls=2 * L * ses.n * done)   # hmc.py:122-125
+                                       n_target_calls=calls * done, n_target_gradient_calls=grads * done)
+        out.statistics.n_nonfinite = cnt[2]
         rs.set_last_device(ses.x.reshape(ses.n, *event_shape))
         out.kernel = self.inner_kernel
         out.kernel.flow = self.kernel.flow                                              # neutra.py:128
         return out
+
+    def _launch_latent(self, ses, pot, fd, k, imd, rng, st, sink):
+        N.check(N.lib().nfmc_neutra_hmc_steps(C.byref(pot), C.byref(fd), N.ptr(ses.x), ses.n, k,
+                                              float(self.inner_kernel.step_size), int(self.inner_kernel.n_leapfrog_steps),
+                                              N.ptr(imd), C.byref(rng), ses.chain0, C.byref(st),
+                                              None if sink is None else C.byref(sink), ses.stream))
+
+    def _calls_grads(self, n):
+        L = int(self.inner_kernel.n_leapfrog_steps)
+        return (2 * L + 2) * n, 2 * L * n                                             # hmc.py:122-125
 
     def warmup(self, x0, show_progress=True, time_limit_seconds=None) -> MCMCOutput:
         """Reference: NeuTra.warmup (neutra.py:70-107): variational fit of the flow (30 % of the budget), then tune the
@@ -786,3 +793,25 @@ class NeuTraHMC(Sampler):
         left = None if time_limit_seconds is None else max(time_limit_seconds - (time.time() - t0), 0.0)
         self.inner_params.n_warmup_iterations = self.params.n_warmup_iterations
         return self._run(x0, int(self.params.n_warmup_iterations), True, show_progress, left)
+
+
+class NeuTraMH(NeuTraHMC):
+    """Random-walk Metropolis in the flow's latent space (reference: nfmc/neutra.py:147-159 = MH.propose, mcmc/mh.py:44-73,
+    on ``NeuTra.adjusted_target``).  Shares the outer loop, warm-up and output conventions of :class:`NeuTraHMC`."""
+
+    def __init__(self, event_shape, target, inner_kernel: MHKernel = None, inner_params: MHParameters = None,
+                 kernel: NeuTraKernel = None, params: NeuTraParameters = None):
+        es = int(math.prod(tuple(event_shape)))
+        super().__init__(event_shape, target, inner_kernel or MHKernel(event_size=es), inner_params or MHParameters(), kernel, params)
+
+    @property
+    def name(self):
+        return "NeuTra MH"
+
+    def _launch_latent(self, ses, pot, fd, k, imd, rng, st, sink):
+        N.check(N.lib().nfmc_neutra_mh_steps(C.byref(pot), C.byref(fd), N.ptr(ses.x), ses.n, k, N.ptr(imd),
+                                             int(bool(self.inner_params.adjustment)), C.byref(rng), ses.chain0, C.byref(st),
+                                             None if sink is None else C.byref(sink), ses.stream))
+
+    def _calls_grads(self, n):
+        return ((2 * n) if self.inner_params.adjustment else 0), 0                     # mh.py:68-71

@@ -427,6 +427,12 @@ def run_neutra_hmc(z0, target, flow, n_iterations: int, draws, tau: float, imd: 
                    adjusted=True, store=store, trace=trace)
 
 
+def run_neutra_mh(z0, target, flow, n_iterations: int, draws, imd: torch.Tensor, adjusted: bool = True,
+                  store: bool = True, trace: bool = False) -> RunRef:
+    """``NeuTraMH`` (nfmc/neutra.py:147-159): random-walk Metropolis (mcmc/mh.py:44-73) on the latent potential."""
+    return run_mh(z0, neutra_potential(flow, target), imd, n_iterations, draws, adjusted=adjusted, store=store, trace=trace)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # warm-up tuning (mcmc/base.py:142-161, tuning.py:15-41)
 # ---------------------------------------------------------------------------------------------------------

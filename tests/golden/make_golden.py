@@ -34,7 +34,7 @@ from nfmc.algorithms.sampling.mcmc.mh import MH, MHKernel, MHParameters         
 from nfmc.algorithms.sampling.mcmc.ess import ESS, ESSKernel, ESSParameters                 # noqa: E402
 from nfmc.algorithms.sampling.nfmc.imh import FixedIMH, IMHKernel, IMHParameters      # noqa: E402
 from nfmc.algorithms.sampling.nfmc.jump import JumpMALA, JumpHMC, JumpESS, JumpNFMCParameters  # noqa: E402
-from nfmc.algorithms.sampling.nfmc.neutra import NeuTraHMC, NeuTraKernel, NeuTraParameters  # noqa: E402
+from nfmc.algorithms.sampling.nfmc.neutra import NeuTraHMC, NeuTraMH, NeuTraKernel, NeuTraParameters  # noqa: E402
 from nfmc.algorithms.sampling.base import NFMCKernel                                   # noqa: E402
 
 from oracle.potentials_ref import make_potential_ref                                   # noqa: E402
@@ -261,6 +261,19 @@ def main():
         out = s.sample(x0.clone(), show_progress=False)
     cases["neutra_hmc_fn_d100"] = pack(out, t, x0, dict(pot="fn", step=0.01, imd=np.ones(d, np.float32), T=T, L=L,
                                                          **flow_arrays(flow, 2, 2, 5)))
+
+    # ---- NeuTra MH: random-walk Metropolis in the latent space, non-trivial proposal scale ---------------------------------
+    torch.manual_seed(24)
+    d, n, T = 7, 6, 5
+    target = make_potential_ref("gm", (d,))
+    flow = make_flow((d,), n_layers=3, perturb=0.1, seed=107)
+    imd = 0.2 + 0.3 * torch.rand(d)
+    x0 = 0.5 * torch.randn(n, d)
+    s = NeuTraMH((d,), target, MHKernel(event_size=d, inv_mass_diag=imd.clone()), MHParameters(),
+                 NeuTraKernel((d,), flow=flow), NeuTraParameters(n_iterations=T))
+    with Tape() as t:
+        out = s.sample(x0.clone(), show_progress=False)
+    cases["neutra_mh_gm"] = pack(out, t, x0, dict(pot="gm", imd=imd.numpy(), T=T, **flow_arrays(flow, 3, 2, 4)))
 
     for name, arrays in cases.items():
         path = os.path.join(HERE, f"{name}.npz")

@@ -225,6 +225,46 @@ def test_golden_neutra_hmc(name):
     _check_output(out, g)
 
 
+def test_golden_neutra_mh():
+    from gpu_util import product_target, product_flow_from_oracle
+    from nfmc_b200.records import MHKernel, MHParameters, NeuTraKernel, NeuTraParameters
+    from nfmc_b200.samplers import NeuTraMH
+    g = load_case("neutra_mh_gm")
+    n, d = g["x0"].shape
+    T = int(g["T"])
+    s = NeuTraMH((d,), product_target(g["pot"], d), MHKernel(event_size=d, inv_mass_diag=torch.from_numpy(g["imd"])), MHParameters(),
+                 NeuTraKernel((d,), flow=product_flow_from_oracle(oracle_flow(g))), NeuTraParameters(n_iterations=T))
+    out = s.sample(torch.from_numpy(g["x0"]), show_progress=False, normals=torch.stack(g["normals"]),
+                   uniforms=torch.stack(g["uniforms"]))
+    _check_output(out, g)
+
+
+def test_neutra_mh_against_oracle_large():
+    """d = 100 (production layout), ragged tile, Philox-free: injected noise; decisions agree except ties."""
+    from gpu_util import product_target, product_flow_from_oracle
+    from nfmc_b200.records import MHKernel, MHParameters, NeuTraKernel, NeuTraParameters
+    from nfmc_b200.samplers import NeuTraMH
+    from oracle.realnvp_ref import make_flow
+    d, n, T = 100, 301, 4
+    torch.manual_seed(2)
+    oflow = make_flow((d,), n_layers=2, perturb=0.05, seed=9)
+    z0 = 0.5 * torch.randn(n, d)
+    normals, uniforms = torch.randn(T, n, d), torch.rand(T, n)
+    imd = torch.full((d,), 0.05)
+    run = R.run_neutra_mh(z0, make_potential_ref("g1", (d,)), oflow, T, R.TapeDraws(list(normals), list(uniforms)), imd, trace=True)
+    s = NeuTraMH((d,), product_target("g1", d), MHKernel(event_size=d, inv_mass_diag=imd), MHParameters(),
+                 NeuTraKernel((d,), flow=product_flow_from_oracle(oflow)), NeuTraParameters(n_iterations=T))
+    out = s.sample(z0, show_progress=False, normals=normals, uniforms=uniforms)
+    lr = torch.stack(run.trace["log_ratio"])
+    margin = (lr - torch.log(uniforms)).abs().min(dim=0).values
+    clear = margin > 1e-3 * (1.0 + lr.abs().max(dim=0).values)
+    assert clear.float().mean() > 0.9
+    ref = run.samples
+    close(out.samples[:, clear], ref[:, clear], atol=5e-5 * max(1.0, float(ref.abs().max())))
+    assert abs(out.statistics.n_accepted_trajectories - run.n_accepted) <= int((~clear).sum()) * T
+    assert out.statistics.n_target_calls == run.n_target_calls and out.statistics.n_target_gradient_calls == 0
+
+
 # ------------------------------------------------------------------------------------------------------------
 # NeuTra latent potential and its hand-written gradient against autograd through the oracle flow
 # ------------------------------------------------------------------------------------------------------------

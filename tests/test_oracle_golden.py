@@ -85,3 +85,10 @@ def test_jump_ess():
                      tape(g), 0.0, torch.ones(d), nll=make_potential_ref(str(g["nll"]), (d,)),
                      max_ess_iterations=int(g["M"]))
     _check(g, run, jump=True)
+
+
+def test_neutra_mh():
+    g = load_case("neutra_mh_gm")
+    run = R.run_neutra_mh(torch.from_numpy(g["x0"]), oracle_target(g), oracle_flow(g), int(g["T"]), tape(g),
+                          torch.from_numpy(g["imd"]))
+    _check(g, run)
