@@ -264,7 +264,7 @@ class Flow(nn.Module):
             return x, lq.reshape(tuple(sample_shape))
         return x
 
-    # -- training (library-backed for now: nfmc_b200/flow_train.py) ------------------------------------------------------
+    # -- training (nfmc_b200/flow_train.py: native kernels for the default conditioners, torch autograd otherwise) ---------
     def fit(self, x_train, *args, **kwargs):
         """Maximum-likelihood fit (reference call sites: jump.py:139-151,201; imh.py:171-175).  Raises ``ValueError`` when
         the loss becomes non-finite, which the callers turn into a weight rollback."""

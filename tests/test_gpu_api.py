@@ -199,7 +199,7 @@ def test_thinning_and_max_samples():
     assert buf.shape[0] == 4 and torch.equal(buf.cpu(), full[0::3])
 
 
-# ---- flow training hooks (library-backed, nfmc_b200/flow_train.py) -------------------------------------------------------
+# ---- flow training hooks (nfmc_b200/flow_train.py; the default conditioners train on the native kernels) ----------------
 def test_flow_fit_improves_likelihood_and_kernels_see_new_weights():
     from nfmc_b200.flow import create_flow_object
     torch.manual_seed(0)
