@@ -289,3 +289,19 @@ def test_fused_whole_run_equals_per_iteration_loop(strategy, inner):
     if not bool(torch.isnan(la).any()):
         np.testing.assert_allclose(np.asarray(a.mean), np.asarray(b.mean), rtol=0, atol=1e-6)
         np.testing.assert_allclose(np.asarray(a.second_moment), np.asarray(b.second_moment), rtol=1e-6, atol=1e-6)
+
+
+def test_full_pipeline_recovers_target_moments():
+    """warm-up (tuning + flow fit) then jump_mala on an anisotropic Gaussian: the pooled moments land on the target's, and
+    the fitted flow makes the NF jumps useful (a sizeable share is accepted)."""
+    d, n = 10, 2048
+    torch.manual_seed(12)
+    sig = torch.logspace(-0.5, 0.5, d)                           # standard deviations 0.32 .. 3.2
+    target = DiagonalGaussian((d,), precision=1.0 / sig ** 2, mean=torch.linspace(-1.0, 1.0, d))
+    out = sample(target, strategy="jump_mala", flow="realnvp", n_chains=n, n_iterations=30, n_warmup_iterations=40,
+                 warmup=True, show_progress=False, inner_param_kwargs=dict(n_iterations=20),
+                 param_kwargs=dict(store_samples=False))
+    mean, var = np.asarray(out.mean), np.asarray(out.variance)
+    assert np.abs((mean - np.linspace(-1.0, 1.0, d)) / sig.numpy()).max() < 0.1, mean
+    np.testing.assert_allclose(var, sig.numpy() ** 2, rtol=0.15)
+    assert out.statistics.jump_acceptance_rate > 0.2, out.statistics.jump_acceptance_rate
