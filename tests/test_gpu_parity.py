@@ -64,7 +64,8 @@ def test_potential_odd_dims():
 FLOW_CASES = [
     (6, 2, None), (7, 3, dict(n_layers=3, n_hidden=6)), (8, 1, dict(n_layers=1)), (25, 2, None), (100, 2, None),
     (100, 4, dict(n_layers=2, n_hidden=64)), (101, 3, dict(n_layers=4, n_hidden=17)), (64, 2, dict(n_layers=2, n_hidden=32)),
-    (1000, 2, None), (9, 3, dict(n_layers=1)),
+    (1000, 2, None), (9, 3, dict(n_layers=1)), (1023, 3, None), (1024, 2, None), (2, 2, None), (3, 1, None), (33, 2, None),
+    (57, 3, dict(n_layers=2, n_hidden=7)), (209, 2, None),
 ]
 
 
@@ -364,7 +365,8 @@ def test_hmc_philox_mode_equals_injected_mode():
 # larger batches: decisions agree except ties, moments agree, ragged tail tiles
 # ------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind,pot,d,n,K", [("mala", "g1", 100, 1031, 5), ("mala", "gm", 25, 517, 8), ("hmc", "g1", 100, 773, 3),
-                                            ("hmc", "fn", 26, 300, 3), ("mala", "g0", 1000, 67, 3)])
+                                            ("hmc", "fn", 26, 300, 3), ("mala", "g0", 1000, 67, 3), ("mala", "gm", 1023, 37, 3),
+                                            ("hmc", "g1", 1024, 33, 2), ("mala", "fn", 3, 129, 4), ("hmc", "rb", 2, 65, 3)])
 def test_local_kernels_against_oracle(kind, pot, d, n, K):
     from gpu_util import product_target, run_local_injected
     from nfmc_b200.records import LangevinKernel, LangevinParameters, HMCKernel, HMCParameters
@@ -376,11 +378,11 @@ def test_local_kernels_against_oracle(kind, pot, d, n, K):
     ref_t = make_potential_ref(pot, (d,))
     imd = torch.ones(d)
     if kind == "mala":
-        tau = {"g1": 0.004, "gm": 0.1, "g0": 0.02}[pot]
+        tau = {"g1": 0.004, "gm": 0.1, "g0": 0.02, "fn": 0.05}[pot]
         run = R.run_mala(x0, ref_t, tau, imd, K, R.TapeDraws(list(normals), list(uniforms)), trace=True)
         s = MALA((d,), product_target(pot, d), LangevinKernel(event_size=d, step_size=tau), LangevinParameters())
     else:
-        tau, L = (0.03, 6) if pot == "g1" else (0.05, 5)
+        tau, L = (0.03, 6) if pot == "g1" else (0.01, 5) if pot == "rb" else (0.05, 5)
         run = R.run_hmc(x0, ref_t, tau, imd, L, K, R.TapeDraws(list(normals), list(uniforms)), trace=True)
         s = HMC((d,), product_target(pot, d), HMCKernel(event_size=d, step_size=tau, n_leapfrog_steps=L), HMCParameters())
     samples, ses, (sx, sx2, cnt) = run_local_injected(s, x0, normals, uniforms)

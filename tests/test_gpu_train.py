@@ -14,7 +14,8 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-SHAPES = [(6, 2, 4), (7, 3, 6), (25, 2, None), (100, 2, None), (9, 1, 8), (64, 4, 8), (1000, 1, None), (33, 0, 4)]
+SHAPES = [(6, 2, 4), (7, 3, 6), (25, 2, None), (100, 2, None), (9, 1, 8), (64, 4, 8), (1000, 1, None), (33, 0, 4),
+          (1023, 2, None), (2, 2, 4), (3, 3, 5)]
 
 
 def _flow(d, Lc, H, seed=0, scale=0.15):
