@@ -399,8 +399,10 @@ def tc_supported(d: int, M: int, H: int) -> bool:
 
 
 def tc_eligible(d: int, M: int, H: int) -> bool:
-    """Shapes for which ``conditioner_dtype='auto'`` picks the tensor-core path (wide conditioners)."""
-    return tc_supported(d, M, H) and H >= 16
+    """Shapes for which ``conditioner_dtype='auto'`` picks the tensor-core path: every 2-layer conditioner wider than the
+    register-resident path covers (H > 8; the hidden width is zero-padded to a multiple of 16).  The alternative for
+    9 <= H <= 15 would be the generic CUDA-core path, which is an order of magnitude slower."""
+    return tc_supported(d, M, H) and H > SMALL_H
 
 
 def _tc_hidden(H: int) -> int:

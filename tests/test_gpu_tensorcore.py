@@ -104,3 +104,25 @@ def test_tc_jump_mala_through_api():
     assert st.n_attempted_jumps == 3 * 2048 and st.n_attempted_trajectories == 15 * 2048
     # identity flow at initialisation: proposals are N(0, I) draws against N(0, I/2): some are accepted
     assert 0 < st.n_accepted_jumps < st.n_attempted_jumps
+
+
+def test_auto_dtype_routes_mid_width_conditioners_to_tensor_cores():
+    """H in 9..15 (2 linear layers, even d <= 128) is padded to 16 and runs on tcgen05 under conditioner_dtype='auto';
+    the result matches the fp32 CUDA-core path to bf16 tolerance."""
+    from nfmc_b200.flow import Flow, RealNVP
+    d, n = 64, 513
+    torch.manual_seed(5)
+    ck = dict(n_layers=2, n_hidden=12)
+    f_auto = Flow(RealNVP((d,), n_layers=2, conditioner_kwargs=ck))
+    with torch.no_grad():
+        for p in f_auto.parameters():
+            p.add_(0.1 * torch.randn_like(p))
+    f_fp32 = Flow(RealNVP((d,), n_layers=2, conditioner_kwargs=ck, conditioner_dtype="fp32"))
+    f_fp32.load_state_dict(f_auto.state_dict())
+    f_auto, f_fp32 = f_auto.to("cuda"), f_fp32.to("cuda")
+    assert f_auto.bijection.uses_tensor_cores() and not f_fp32.bijection.uses_tensor_cores()
+    x = torch.randn(n, d, device="cuda")
+    za, la = f_auto.bijection.forward(x)
+    zf, lf = f_fp32.bijection.forward(x)
+    assert float((za - zf).abs().max()) < 2e-2 * max(1.0, float(zf.abs().max()))
+    assert float((la - lf).abs().max()) < 5e-2 * max(1.0, float(lf.abs().max()))
