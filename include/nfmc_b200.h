@@ -171,6 +171,15 @@ NFMC_API int nfmc_imh_steps(const nfmc_potential* pot, const nfmc_realnvp* flow,
 NFMC_API int nfmc_neutra_hmc_steps(const nfmc_potential* pot, const nfmc_realnvp* flow, float* z, int64_t n, int32_t n_steps,
                           float step_size, int32_t n_leapfrog, const float* inv_mass_diag, const nfmc_rng* rng,
                           int64_t chain0, const nfmc_stats* stats, const nfmc_sink* sink, void* stream);
+/* T transport-elliptical-slice steps -- transport_elliptical_slice_sampling_step (nfmc/tess.py:15-75, identity
+ * covariance) inside TESS.sample (nfmc/tess.py:151-188).  u [n, d] is the latent chain state (updated in place); the
+ * statistics and the sample sink receive the data-space points x = T^-1(u) of every step; counts[0] += chains whose bracket
+ * produced a point, counts[1] += n per step.  Injected noise (both or neither): rng->normals [steps, n, d] = v,
+ * rng->uniforms [steps, n, 2 + max_iterations] = {w (:41), theta_n -- a NORMAL draw (:45) --, bracket uniforms (:69)}. */
+NFMC_API int nfmc_tess_steps(const nfmc_potential* pot, const nfmc_realnvp* flow, float* u, int64_t n, int32_t n_steps,
+                    int32_t max_iterations, const nfmc_rng* rng, int64_t chain0, const nfmc_stats* stats,
+                    const nfmc_sink* sink, void* stream);
+
 /* T random-walk Metropolis steps in the latent space of the flow -- NeuTraMH (nfmc/neutra.py:147-159) = MH.propose
  * (mcmc/mh.py:44-73) on NeuTra.adjusted_target: z' = z + inv_mass_diag * xi (NULL = ones), accept iff
  * log u < U~(z) - U~(z'); adjusted = 0 -> plain random walk */

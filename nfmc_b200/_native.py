@@ -80,6 +80,8 @@ SIGNATURES = {
                                  P(StatsDesc), P(SinkDesc), _vp]),
     "nfmc_neutra_hmc_steps": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _vp, _i64, _i32, _f32, _i32, _vp,
                                         P(RngDesc), _i64, P(StatsDesc), P(SinkDesc), _vp]),
+    "nfmc_tess_steps": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _vp, _i64, _i32, _i32, P(RngDesc), _i64, P(StatsDesc),
+                                  P(SinkDesc), _vp]),
     "nfmc_neutra_mh_steps": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _vp, _i64, _i32, _vp, _i32, P(RngDesc), _i64,
                                        P(StatsDesc), P(SinkDesc), _vp]),
     "nfmc_neutra_potential": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _vp, _vp, _vp, _i64, _vp]),

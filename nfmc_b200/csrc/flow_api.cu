@@ -154,6 +154,33 @@ extern "C" int nfmc_neutra_mh_steps(const nfmc_potential* pot, const nfmc_realnv
   return 0;
 }
 
+extern "C" int nfmc_tess_steps(const nfmc_potential* pot, const nfmc_realnvp* flow, float* u, int64_t n, int32_t n_steps,
+                               int32_t max_iterations, const nfmc_rng* rng, int64_t chain0, const nfmc_stats* stats,
+                               const nfmc_sink* sink, void* stream) {
+  if (int e = validate_pot(pot)) return e;
+  if (int e = validate_flow(flow)) return e;
+  if (pot->d != flow->d) return set_error("tess: potential and flow event sizes differ");
+  if (!u || n < 1 || n_steps < 0 || max_iterations < 0) return set_error("tess: bad u/n/n_steps/max_iterations");
+  if (rng && ((rng->normals == nullptr) != (rng->uniforms == nullptr)))
+    return set_error("tess: inject both normals [steps,n,d] and uniforms [steps,n,2+max_iterations], or neither");
+  if (n_steps == 0) return 0;
+  Layout L;
+  if (!layout_for_dim(pot->d, L)) return set_error("tess: unsupported event size");
+  TessArgs A;
+  A.c.pot = pot_params(pot);
+  A.c.x = u; A.c.n = n; A.c.chain0 = chain0; A.c.d = pot->d; A.c.gs = L.gs; A.c.n_steps = n_steps;
+  A.c.rng = RngArgs{rng ? rng->seed : 0, rng ? rng->step0 : 0, rng ? rng->normals : nullptr, rng ? rng->uniforms : nullptr};
+  A.c.stats = StatsArgs{stats ? stats->sum_x : nullptr, stats ? stats->sum_x2 : nullptr, stats ? stats->counts : nullptr};
+  A.c.sink = SinkArgs{sink ? sink->samples : nullptr, sink ? sink->seen0 : 0, (sink && sink->thinning > 0) ? sink->thinning : 1};
+  A.pot_kind = pot->kind;
+  A.max_iterations = max_iterations;
+  const size_t smem = plan_flow_smem(A.f, flow, L, true, true) + (size_t)4 * L.E * kThreads * sizeof(float);   // + step outcome (x, u)
+  const int grid = grid_for(n, L.gs, 2);
+  cudaStream_t s = (cudaStream_t)stream;
+  NFMC_DISPATCH_E(L.E, { return launch_tess<E>(A, grid, smem, s); });
+  return 0;
+}
+
 extern "C" int nfmc_neutra_potential(const nfmc_potential* pot, const nfmc_realnvp* flow, const float* z, float* u, float* grad,
                                      int64_t n, void* stream) {
   if (int e = validate_pot(pot)) return e;

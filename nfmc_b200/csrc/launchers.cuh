@@ -71,6 +71,13 @@ struct TrainArgs {
   long long chain0;
 };
 
+struct TessArgs {
+  ChainArgs c;          // c.x = latent state u; c.pot = the potential of tess.py's `potential` argument
+  FlowArgs f;
+  int pot_kind;
+  int max_iterations;   // bracket rounds per step (TESSParameters.max_ess_step_iterations)
+};
+
 enum { PASS_FORWARD = 0, PASS_INVERSE = 1, PASS_LOGPROB = 2 };
 
 template <int E> int launch_mala(int pot_kind, bool exact, const LocalArgs& A, int grid, size_t smem, cudaStream_t s);
@@ -84,6 +91,7 @@ template <int E> int launch_flow_train(const TrainArgs& A, int grid, bool shared
 template <int E> int launch_jump(const JumpArgs& A, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_jump_accept(const AcceptArgs& A, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_neutra_hmc(const NeutraArgs& A, int grid, size_t smem, cudaStream_t s);
+template <int E> int launch_tess(const TessArgs& A, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_neutra_mh(const NeutraArgs& A, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_neutra_potential(const FlowArgs& FA, int pot_kind, const PotParams& P, const float* z, float* u,
                                              float* grad, long long n, int grid, size_t smem, cudaStream_t s);

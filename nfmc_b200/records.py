@@ -234,6 +234,24 @@ class JumpNFMCParameters(NFMCParameters):
 
 
 @dataclass
+class TESSKernel(NFMCKernel):
+    """Reference: nfmc/tess.py:78-80 (ESSKernel + NFMCKernel).  Only the identity covariance runs on the device path."""
+    cov: torch.Tensor = None
+
+    def __post_init__(self):
+        super().__post_init__()
+        if self.cov is not None:
+            raise NotImplementedError("TESSKernel: only cov=None (identity covariance) is supported on the device path")
+
+
+@dataclass
+class TESSParameters(NFMCParameters):
+    """Reference: nfmc/tess.py:83-85 (ESSParameters + NFMCParameters)."""
+    max_ess_step_iterations: int = 5
+    n_warmup_iterations: int = 20
+
+
+@dataclass
 class NeuTraParameters(NFMCParameters):
     batch_inverse_size: int = 128
     warmup_fit_kwargs: dict = None

@@ -24,7 +24,7 @@ import torch
 from . import _native as N
 from .flow import Flow
 from .potentials import resolve_target
-from .records import (ESSKernel, ESSParameters, MHKernel, MHParameters, HMCKernel, HMCParameters, IMHKernel, IMHParameters, JumpNFMCOutput, JumpNFMCParameters,
+from .records import (TESSKernel, TESSParameters, ESSKernel, ESSParameters, MHKernel, MHParameters, HMCKernel, HMCParameters, IMHKernel, IMHParameters, JumpNFMCOutput, JumpNFMCParameters,
                       LangevinKernel, LangevinParameters, MCMCKernel, MCMCOutput, MCMCParameters, MetropolisKernel,
                       MetropolisParameters, NeuTraKernel, NeuTraParameters, NFMCKernel)
 
@@ -815,3 +815,112 @@ class NeuTraMH(NeuTraHMC):
 
     def _calls_grads(self, n):
         return ((2 * n) if self.inner_params.adjustment else 0), 0                     # mh.py:68-71
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# transport elliptical slice sampling
+# ---------------------------------------------------------------------------------------------------------------
+class TESS(Sampler):
+    """Transport elliptical slice sampling (reference: nfmc/tess.py:88-188).  The chain state is the latent ``u``
+    (``sample`` starts it at ``x0``, as the reference does); recorded samples and moments are the data-space points
+    ``x = T^-1(u)``.  ``negative_log_likelihood`` is the potential the slice is taken on (tess.py passes it as
+    ``potential``); ``target`` is carried for the API only."""
+
+    def __init__(self, event_shape, target, negative_log_likelihood, kernel: Optional[TESSKernel] = None,
+                 params: Optional[TESSParameters] = None):
+        super().__init__(event_shape, target, kernel or TESSKernel(tuple(event_shape)), params or TESSParameters())
+        self.negative_log_likelihood = resolve_target(negative_log_likelihood, self.event_shape)
+
+    @property
+    def name(self):
+        return "TESS"
+
+    def _steps(self, ses: DeviceSession, k: int, sink, normals=None, uniforms=None):
+        pot, keep = self.negative_log_likelihood.descriptor(ses.device)
+        fd, keep2 = self.kernel.flow.bijection.descriptor(ses.device)
+        rng = N.rng_desc(ses.seed, ses.local_step, normals, uniforms)
+        st = ses.stats()
+        N.check(N.lib().nfmc_tess_steps(C.byref(pot), C.byref(fd), N.ptr(ses.x), ses.n, k,
+                                        int(self.params.max_ess_step_iterations), C.byref(rng), ses.chain0, C.byref(st),
+                                        None if sink is None else C.byref(sink), ses.stream))
+        ses.local_step += k
+
+    def sample(self, x0, show_progress=True, time_limit_seconds=None, normals=None, uniforms=None) -> MCMCOutput:
+        """``normals [T,n,d]`` / ``uniforms [T,n,2+M]`` optionally inject the random numbers (parity tests)."""
+        event_shape = tuple(x0.shape[1:])
+        store = bool(self.params.store_samples)
+        out = MCMCOutput(event_shape, store_samples=store)
+        ses = DeviceSession(x0, event_shape, self.device, self.seed, self.chain0)      # u = x0 (tess.py:163)
+        dev = ses.device
+        T = int(self.params.n_iterations)
+        M = int(self.params.max_ess_step_iterations)
+        chunk = 1 if (time_limit_seconds is not None or show_progress) else T
+        rs = out.running_samples
+        done = 0
+        for start in _progress(range(0, T, max(chunk, 1)), 'TESS sampling', show_progress):
+            if time_limit_seconds is not None and out.statistics.elapsed_time_seconds >= time_limit_seconds:
+                break
+            k = min(chunk, T - start)
+            buf, sink = None, None
+            if store:
+                rows = _rows_kept(rs.seen_samples, k, rs.thinning)
+                if rows * ses.n * ses.d * 4 > MAX_DEVICE_SAMPLE_BYTES:
+                    raise MemoryError("sample buffer too large for the device; use store_samples=False")
+                buf = torch.empty(rows, ses.n, ses.d, device=dev, dtype=torch.float32)
+                sink = ses.sink(buf, rs.seen_samples, rs.thinning)
+            nz = None if normals is None else N.dev_f32(normals[start:start + k], dev)
+            un = None if uniforms is None else N.dev_f32(uniforms[start:start + k], dev)
+            ses.tic()
+            self._steps(ses, k, sink, nz, un)
+            out.statistics.update_elapsed_time(ses.toc())
+            done += k
+            if buf is not None:
+                rs.add(buf.reshape(-1, ses.n, *event_shape), already_thinned=True, n_seen=k)
+        sx, sx2, cnt = ses.read_back()
+        out.statistics.expectations.add_sums(sx, sx2, ses.n * done)
+        out.statistics.update_counters(n_accepted_trajectories=cnt[0], n_attempted_trajectories=cnt[1],
+                                       n_target_calls=(M + 1) * ses.n * done)          # tess.py:174-178
+        self.latent_state = ses.x.reshape(ses.n, *event_shape)                         # the chains' final u (device)
+        if not store or rs.n_samples == 0:
+            # last_sample = the last recorded x: one more inverse pass on the final latent state
+            rs.set_last_device(self.kernel.flow.bijection.inverse(self.latent_state)[0])
+        out.kernel = self.kernel
+        return out
+
+    def warmup(self, x0, show_progress=True, time_limit_seconds=None) -> MCMCOutput:
+        """Reference: TESS.warmup (tess.py:101-149): start from a prior draw, alternate one TESS step with a flow fit on
+        the step's data-space points (shuffled, split by ``train_pct``); the warm-up output records the LATENT states."""
+        from .flow_train import train_val_split
+        event_shape = tuple(x0.shape[1:])
+        p: TESSParameters = self.params
+        out = MCMCOutput(event_shape, store_samples=p.store_samples)
+        ses = DeviceSession(x0, event_shape, self.device, self.seed, self.chain0)
+        rng = N.rng_desc(ses.seed, 0)                                                  # u ~ N(0, I) (tess.py:112), stream 3
+        N.check(N.lib().nfmc_rng_fill(C.byref(rng), 3, ses.chain0, ses.d, ses.n, 1, N.ptr(ses.x), None, ses.stream))
+        M = int(p.max_ess_step_iterations)
+        done = 0
+        x_buf = torch.empty(1, ses.n, ses.d, device=ses.device, dtype=torch.float32)
+        u_sum = torch.zeros(2, ses.d, dtype=torch.float64)
+        t_all = 0.0
+        for _ in _progress(range(int(p.n_warmup_iterations)), '[Warmup] TESS', show_progress):
+            if time_limit_seconds is not None and t_all >= time_limit_seconds:
+                break
+            t0 = time.time()
+            ses.tic()
+            self._steps(ses, 1, ses.sink(x_buf, 0, 1))
+            ses.toc()
+            u = ses.x.reshape(ses.n, *event_shape)
+            out.running_samples.add(u.clone())                                       # tess.py:128-129 (latent states)
+            ud = ses.x.double()
+            u_sum += torch.stack([ud.sum(0), ud.square().sum(0)]).cpu()
+            done += 1
+            x_train, x_val = train_val_split(x_buf, p.train_pct, ses.n, ses.n)         # tess.py:138-142 (no size cap)
+            self.kernel.flow.fit(x_train, x_val=x_val, **p.flow_fit_kwargs)
+            t_all += time.time() - t0
+        _, _, cnt = ses.read_back()
+        out.statistics.expectations.add_sums(u_sum[0], u_sum[1], ses.n * done)
+        out.statistics.update_counters(n_accepted_trajectories=cnt[0], n_attempted_trajectories=cnt[1],
+                                       n_target_calls=(M + 1) * ses.n * done)
+        out.statistics.update_elapsed_time(t_all)
+        out.kernel = self.kernel
+        return out

@@ -434,6 +434,64 @@ def run_neutra_mh(z0, target, flow, n_iterations: int, draws, imd: torch.Tensor,
 
 
 # ---------------------------------------------------------------------------------------------------------
+# transport elliptical slice sampling (nfmc/tess.py)
+# ---------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def tess_step(u, flow, potential, max_iterations: int, draws, trace=None):
+    """``transport_elliptical_slice_sampling_step`` (nfmc/tess.py:15-75), identity covariance.  Quirks kept: the initial
+    angle is a NORMAL draw times 2 pi (:44), the log-det enters ``log_pi_hat`` with the sign of :31, and ``theta_max``
+    aliases the initial angle (:48), so a negative initial angle collapses the bracket onto itself."""
+    n = u.shape[0]
+    ev = tuple(u.shape[1:])
+    ones = [1] * len(ev)
+
+    def log_pi_hat(inp):
+        x, log_det = flow.bijection.inverse(inp)
+        return -potential(x) - log_det                                          # :29-32
+
+    v = draws.normal(n, ev)                                                      # :38
+    w = draws.uniform(n)                                                         # :41
+    log_s = log_pi_hat(u) + flow.base_log_prob(v) + w.log()                      # :42
+    theta = (draws.normal(n, ()) * (2 * torch.pi)).view(n, *ones)                # :45-47
+    theta_min, theta_max = theta - 2 * torch.pi, theta.clone()                   # :48
+    accepted = torch.zeros(n, dtype=torch.bool)
+    u_prop = u.clone()
+    x_prop = flow.bijection.inverse(u_prop)[0]                                   # :51-52
+    for _ in range(max_iterations):
+        u_prime = u * torch.cos(theta) + v * torch.sin(theta)                    # :54
+        v_prime = v * torch.cos(theta) - u * torch.sin(theta)                    # :55
+        x_prime = flow.bijection.inverse(u_prime)[0]                             # :56
+        upd = (log_pi_hat(u_prime) + flow.base_log_prob(v_prime)) > log_s        # :57
+        take = upd & (~accepted)
+        x_prop[take] = x_prime[take]                                             # :60
+        u_prop[take] = u_prime[take]                                             # :61
+        neg = theta < 0                                                          # :64
+        theta_min = torch.where(neg, theta, theta_min)                           # :65
+        theta_max = torch.where(~neg, theta, theta_max)                          # :66
+        theta = draws.uniform(n).view(n, *ones) * (theta_max - theta_min) + theta_min   # :69-70
+        accepted = accepted | upd                                                # :73
+    return x_prop.detach(), u_prop.detach(), accepted
+
+
+def run_tess(x0, potential, flow, n_iterations: int, draws, max_iterations: int = 5, store: bool = True) -> RunRef:
+    """``TESS.sample`` (nfmc/tess.py:151-188): the chain state is the latent ``u`` (initialised with ``x0``), the recorded
+    samples / moments are the data-space points ``x``; every iteration books ``(max_iterations + 1) n`` target calls."""
+    n = x0.shape[0]
+    out = RunRef(event_shape=tuple(x0.shape[1:]))
+    u = x0.clone()
+    x = None
+    for _ in range(n_iterations):
+        x, u, mask = tess_step(u, flow, potential, max_iterations, draws)
+        out.n_target_calls += (max_iterations + 1) * n                            # :174-178
+        out.n_accepted += int(torch.sum(mask))
+        out.n_attempted += n
+        out.observe(x, store)                                                    # :179-180
+    out.x = x
+    out.trace["u"] = u
+    return out.finish(store)
+
+
+# ---------------------------------------------------------------------------------------------------------
 # warm-up tuning (mcmc/base.py:142-161, tuning.py:15-41)
 # ---------------------------------------------------------------------------------------------------------
 class DualAveragingRef:

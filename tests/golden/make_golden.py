@@ -36,6 +36,7 @@ from nfmc.algorithms.sampling.nfmc.imh import FixedIMH, IMHKernel, IMHParameters
 from nfmc.algorithms.sampling.nfmc.jump import JumpMALA, JumpHMC, JumpESS, JumpNFMCParameters  # noqa: E402
 from nfmc.algorithms.sampling.nfmc.neutra import NeuTraHMC, NeuTraMH, NeuTraKernel, NeuTraParameters  # noqa: E402
 from nfmc.algorithms.sampling.base import NFMCKernel                                   # noqa: E402
+from nfmc.algorithms.sampling.nfmc.tess import TESS, TESSKernel, TESSParameters       # noqa: E402
 
 from oracle.potentials_ref import make_potential_ref                                   # noqa: E402
 from oracle.realnvp_ref import make_flow                                               # noqa: E402
@@ -274,6 +275,17 @@ def main():
     with Tape() as t:
         out = s.sample(x0.clone(), show_progress=False)
     cases["neutra_mh_gm"] = pack(out, t, x0, dict(pot="gm", imd=imd.numpy(), T=T, **flow_arrays(flow, 3, 2, 4)))
+
+    # ---- transport elliptical slice sampling, frozen flow (3 couplings: the latent is flipped in physical order) ---------
+    torch.manual_seed(25)
+    d, n, T, M = 7, 6, 4, 5
+    nll = make_potential_ref("fn", (d,))
+    flow = make_flow((d,), n_layers=3, perturb=0.1, seed=108)
+    x0 = 0.5 * torch.randn(n, d)
+    s = TESS((d,), nll, nll, TESSKernel((d,), flow=flow), TESSParameters(n_iterations=T, max_ess_step_iterations=M))
+    with Tape() as t:
+        out = s.sample(x0.clone(), show_progress=False)
+    cases["tess_fn"] = pack(out, t, x0, dict(pot="fn", T=T, M=M, **flow_arrays(flow, 3, 2, 4)))
 
     for name, arrays in cases.items():
         path = os.path.join(HERE, f"{name}.npz")

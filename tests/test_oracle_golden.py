@@ -92,3 +92,10 @@ def test_neutra_mh():
     run = R.run_neutra_mh(torch.from_numpy(g["x0"]), oracle_target(g), oracle_flow(g), int(g["T"]), tape(g),
                           torch.from_numpy(g["imd"]))
     _check(g, run)
+
+
+def test_tess():
+    g = load_case("tess_fn")
+    # draw order per iteration: normal(n,d) = v, uniform(n) = w, normal(n) = theta, then M x uniform(n,1)
+    run = R.run_tess(torch.from_numpy(g["x0"]), oracle_target(g), oracle_flow(g), int(g["T"]), tape(g), max_iterations=int(g["M"]))
+    _check(g, run)
