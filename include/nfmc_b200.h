@@ -229,6 +229,15 @@ NFMC_API int nfmc_flow_fit_epoch(int32_t d, int32_t n_coupling, int32_t n_linear
                         const float* x, const int64_t* perm, int64_t n, int64_t batch_size, float lr, float beta1,
                         float beta2, float eps, float weight_decay, int32_t step0, void* stream);
 
+/* ---- deterministic Langevin Monte Carlo (nfmc/dlmc.py:44-119): its three particle updates; the MH correction that follows
+ * each of them is nfmc_imh_steps(..., n_steps = 1, recompute_logq = 1) and the refit is nfmc_flow_fit_epoch ------------- */
+/* x <- x - step * grad U(x)                                        (dlmc.py:60-62, the initial update) */
+NFMC_API int nfmc_potential_step(const nfmc_potential* pot, float* x, int64_t n, float step, void* stream);
+/* x <- x - step * grad_x [ U(x) + log q(x) ]                       (dlmc.py:86-88; grad log q by the reversible sweep) */
+NFMC_API int nfmc_dlmc_update(const nfmc_potential* pot, const nfmc_realnvp* flow, float* x, int64_t n, float step, void* stream);
+/* z <- z - step * (grad - z), elementwise over `count` floats       (dlmc.py:84, the latent update between T and T^-1) */
+NFMC_API int nfmc_dlmc_latent_update(float* z, const float* grad, float step, int64_t count, void* stream);
+
 /* ---- whole-run entry points --------------------------------------------------------------------------------------
  * JumpNFMC.sample (nfmc/jump.py:156-246) for device-resident chains: n_outer x [n_inner local steps (inner_kind 0 =
  * Langevin, 1 = HMC, 2 = random-walk Metropolis) + one NF jump], Philox noise, no sample sink.  The batch is cut into

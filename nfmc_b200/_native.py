@@ -94,6 +94,9 @@ SIGNATURES = {
     "nfmc_flow_fit_epoch": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64,
                                       _f32, _f32, _f32, _f32, _f32, _i32, _vp]),
     "nfmc_rng_fill": (C.c_int, [P(RngDesc), _i32, _i64, _i32, _i64, _i32, _vp, _vp, _vp]),
+    "nfmc_potential_step": (C.c_int, [P(PotentialDesc), _vp, _i64, _f32, _vp]),
+    "nfmc_dlmc_update": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _vp, _i64, _f32, _vp]),
+    "nfmc_dlmc_latent_update": (C.c_int, [_vp, _vp, _f32, _i64, _vp]),
     "nfmc_jump_sample_slabs": (_i64, [_i32, _i64, _i32]),
     "nfmc_jump_sample_device": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _vp, _i64, _i32, _i32, _i32, _f32, _i32, _vp, _i32,
                                           _i32, C.c_uint64, C.c_uint64, C.c_uint64, _i64, P(StatsDesc), P(StatsDesc), _vp]),

@@ -2,7 +2,7 @@
 
 Strategies on the accelerated hot path: ``jump_mala``, ``jump_ula``, ``jump_hmc``, ``jump_uhmc``, ``neutra_hmc``,
 ``imh`` / ``fixed_imh``, ``adaptive_imh`` and the local kernels they are built from (``mala``, ``ula``, ``hmc``,
-``uhmc``, ``mh`` / ``jump_mh`` / ``neutra_mh``, ``ess`` / ``jump_ess``).  ``tess``.  Everything else the reference lists (``dlmc``, ``nuts`` ...) is outside the scope table and raises ``NotImplementedError`` -- there is no eager fallback.
+``uhmc``, ``mh`` / ``jump_mh`` / ``neutra_mh``, ``ess`` / ``jump_ess``).  ``tess``, ``dlmc`` -- every strategy of the reference's ``get_supported_samplers()``.  Anything else (``nuts`` ...) is outside the scope table and raises ``NotImplementedError`` -- there is no eager fallback.
 """
 from __future__ import annotations
 
@@ -14,14 +14,14 @@ import torch
 from . import _native as N
 from .flow import Flow, create_flow_object
 from .potentials import Potential, resolve_target
-from .records import (TESSKernel, TESSParameters, ESSKernel, ESSParameters, MHKernel, MHParameters, HMCKernel, HMCParameters, IMHKernel, IMHParameters, JumpNFMCParameters, LangevinKernel,
+from .records import (DLMCKernel, DLMCParameters, TESSKernel, TESSParameters, ESSKernel, ESSParameters, MHKernel, MHParameters, HMCKernel, HMCParameters, IMHKernel, IMHParameters, JumpNFMCParameters, LangevinKernel,
                       LangevinParameters, MCMCOutput, NeuTraKernel, NeuTraParameters, NFMCKernel)
-from .samplers import (TESS, ESS, JumpESS, MH, JumpMH, NeuTraMH, HMC, MALA, UHMC, ULA, AdaptiveIMH, FixedIMH, JumpHMC, JumpMALA, JumpUHMC, JumpULA, NeuTraHMC,
+from .samplers import (DLMC, TESS, ESS, JumpESS, MH, JumpMH, NeuTraMH, HMC, MALA, UHMC, ULA, AdaptiveIMH, FixedIMH, JumpHMC, JumpMALA, JumpUHMC, JumpULA, NeuTraHMC,
                        Sampler)
 
 LOCAL_STRATEGIES = ('hmc', 'uhmc', 'ula', 'mala', 'mh', 'ess')
 NF_STRATEGIES = ('imh', 'fixed_imh', 'adaptive_imh', 'jump_mala', 'jump_ula', 'jump_hmc', 'jump_uhmc', 'jump_mh', 'jump_ess',
-                 'neutra_hmc', 'neutra_mh', 'tess')
+                 'neutra_hmc', 'neutra_mh', 'tess', 'dlmc')
 
 
 def get_supported_samplers():
@@ -119,6 +119,11 @@ def create_sampler(target, event_shape: Optional[Tuple[int, ...]] = None, flow: 
             raise ValueError("Negative log likelihood must be provided")
         return finish(TESS(event_shape, target, negative_log_likelihood, TESSKernel(event_shape, flow=flow_object),
                            TESSParameters(**param_kwargs)))
+    if strategy == 'dlmc':                                                               # reference: sample.py:220-225
+        if negative_log_likelihood is None:
+            raise ValueError("Negative log likelihood must be provided")
+        return finish(DLMC(event_shape, target, negative_log_likelihood, DLMCKernel(event_shape, flow=flow_object),
+                           DLMCParameters(**param_kwargs)))
     if strategy == 'neutra_mh':                                                          # reference: sample.py:232-237
         return finish(NeuTraMH(event_shape, target, MHKernel(event_size=event_size, **inner_kernel_kwargs),
                                MHParameters(**inner_param_kwargs), NeuTraKernel(event_shape, flow=flow_object),

@@ -69,6 +69,8 @@ struct TrainArgs {
   PotParams pot;
   RngArgs rng;
   long long chain0;
+  float* x_rw;            // DLMC update: particles [n, d], updated in place
+  float step;             // DLMC update: step size
 };
 
 struct TessArgs {
@@ -91,6 +93,7 @@ template <int E> int launch_flow_train(const TrainArgs& A, int grid, bool shared
 template <int E> int launch_jump(const JumpArgs& A, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_jump_accept(const AcceptArgs& A, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_neutra_hmc(const NeutraArgs& A, int grid, size_t smem, cudaStream_t s);
+template <int E> int launch_flow_dlmc(const TrainArgs& A, int grid, cudaStream_t s);
 template <int E> int launch_tess(const TessArgs& A, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_neutra_mh(const NeutraArgs& A, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_neutra_potential(const FlowArgs& FA, int pot_kind, const PotParams& P, const float* z, float* u,

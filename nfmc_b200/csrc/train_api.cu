@@ -191,6 +191,37 @@ __global__ void adamw_kernel(float* __restrict__ theta, const float* __restrict_
   }
 }
 
+// x <- x - step * grad U(x)   (nfmc/dlmc.py:60-62)
+template <int POT, int E>
+__global__ void __launch_bounds__(kThreads) potential_step_kernel(PotParams P, float* __restrict__ x, long long n, int d, int gs, float step) {
+  const Geom g = make_geom(d, gs);
+  const int cpc = kThreads / gs;
+  const long long tiles = (n + cpc - 1) / cpc;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long chain_raw = tile * cpc + threadIdx.x / gs;
+    const bool active = chain_raw < n;
+    const long long chain = active ? chain_raw : n - 1;
+    float* row = x + chain * (long long)d;
+    float lo[E], hi[E];
+    load_chain(row, g, lo, hi);
+    const PotCtx c = pot_prepare<POT, E>(P, g, lo, hi);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      float ul, uh;
+      pot_grad<POT, false>(P, c, g, g.j + g.gs * e, lo[e], hi[e], ul, uh);
+      lo[e] = __fsub_rn(lo[e], __fmul_rn(step, ul));
+      hi[e] = __fsub_rn(hi[e], __fmul_rn(step, uh));
+    }
+    if (active) store_chain(row, g, lo, hi);
+  }
+}
+
+// z <- z - step * (grad - z)   (nfmc/dlmc.py:84, elementwise over n*d)
+__global__ void latent_update_kernel(float* __restrict__ z, const float* __restrict__ grad, float step, long long count) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+    z[i] = __fsub_rn(z[i], __fmul_rn(step, __fsub_rn(grad[i], z[i])));
+}
+
 int check_train_shape(int d, int Lc, int M, int H) {
   if (d < 2 || d > NFMC_MAX_DIM || Lc < 0) return set_error("flow training: bad d / n_coupling");
   if (!flow_is_small(M, H) || H < 1)
@@ -305,4 +336,46 @@ extern "C" int nfmc_flow_fit_epoch(int32_t d, int32_t n_coupling, int32_t n_line
     if (int e = nfmc_adamw_step(theta, grad_theta, exp_avg, exp_avg_sq, P, lr, beta1, beta2, eps, weight_decay, ++step, stream)) return e;
   }
   return 0;
+}
+
+// ---- deterministic Langevin Monte Carlo pieces (nfmc/dlmc.py:44-119) ------------------------------------------------
+extern "C" int nfmc_potential_step(const nfmc_potential* pot, float* x, int64_t n, float step, void* stream) {
+  if (int e = validate_pot(pot)) return e;
+  if (!x || n < 1) return set_error("potential_step: bad arguments");
+  Layout L;
+  if (!layout_for_dim(pot->d, L)) return set_error("potential_step: unsupported event size");
+  const PotParams P = pot_params(pot);
+  const int grid = grid_for(n, L.gs, 8);
+  cudaStream_t s = (cudaStream_t)stream;
+  NFMC_DISPATCH_POT(pot->kind, NFMC_DISPATCH_E(L.E, {
+    potential_step_kernel<POT, E><<<grid, kThreads, 0, s>>>(P, x, n, pot->d, L.gs, step);
+  }));
+  return check_cuda(cudaGetLastError(), "potential_step_kernel launch");
+}
+
+extern "C" int nfmc_dlmc_update(const nfmc_potential* pot, const nfmc_realnvp* flow, float* x, int64_t n, float step, void* stream) {
+  if (int e = validate_pot(pot)) return e;
+  if (int e = validate_flow(flow)) return e;
+  if (int e = check_train_shape(flow->d, flow->n_coupling, flow->n_linear, flow->hidden)) return e;
+  if (pot->d != flow->d) return set_error("dlmc_update: potential and flow event sizes differ");
+  if (!x || n < 1) return set_error("dlmc_update: bad arguments");
+  Layout L;
+  if (!layout_for_dim(flow->d, L)) return set_error("dlmc_update: unsupported event size");
+  TrainArgs A{};
+  plan_flow_smem(A.f, flow, L, false);
+  A.f.stage_blob = 0;
+  A.n = n; A.x_rw = x; A.step = step; A.pot_kind = pot->kind; A.pot = pot_params(pot);
+  const size_t stash_b = (size_t)flow->n_coupling * (2 * L.E + kSmallH + 2) * kThreads * sizeof(float);
+  A.stash = stash_b <= 100 * 1024 ? 1 : 0;
+  const int grid = grid_for(n, L.gs, 2);
+  cudaStream_t s = (cudaStream_t)stream;
+  NFMC_DISPATCH_E(L.E, { return launch_flow_dlmc<E>(A, grid, s); });
+  return 0;
+}
+
+extern "C" int nfmc_dlmc_latent_update(float* z, const float* grad, float step, int64_t count, void* stream) {
+  if (!z || !grad || count < 1) return set_error("dlmc_latent_update: bad arguments");
+  const int grid = (int)std::min<long long>((count + 255) / 256, 8ll * sm_count());
+  latent_update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z, grad, step, count);
+  return check_cuda(cudaGetLastError(), "latent_update_kernel launch");
 }

@@ -30,6 +30,7 @@ template <bool SG>
 struct GradSink {
   float* g;        // global accumulator
   unsigned sbase;  // shared-window address of the CTA-local accumulator (SG only)
+  bool off;        // no parameter gradients wanted (input-gradient-only sweep): the emitters return at once
   __device__ __forceinline__ void add(int off, float v) const {
     if (SG) asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(sbase + 4u * (unsigned)off), "f"(v) : "memory");
     else atomicAdd(g + off, v);
@@ -48,24 +49,28 @@ struct GradSink {
 // v = this lane's contribution to a parameter that is owned by lane position j (same parameter on lanes j, j+gs, ...)
 template <bool SG>
 __device__ __forceinline__ void emit(const GradSink<SG>& G, int off, float v, const Geom& g, bool ok) {
+  if (G.off) return;
   const float s = across_groups_sum(v, g.gs);
   if (g.lane < g.gs && ok) G.add(off, s);
 }
 // v = a per-chain value (identical on the lanes of a group): counted once per group
 template <bool SG>
 __device__ __forceinline__ void emit_chain(const GradSink<SG>& G, int off, float v, const Geom& g) {
+  if (G.off) return;
   const float s = across_groups_sum(g.j == 0 ? v : 0.f, g.gs);
   if (g.lane == 0) G.add(off, s);
 }
 
 template <bool SG>
 __device__ __forceinline__ void emit2(const GradSink<SG>& G, int off, float a, float b, const Geom& g, bool ok) {
+  if (G.off) return;
   const float sa = across_groups_sum(a, g.gs), sb = across_groups_sum(b, g.gs);
   if (g.lane < g.gs && ok) G.add2(off, sa, sb);
 }
 // eight contiguous parameters (one hidden-minor weight row)
 template <bool SG>
 __device__ __forceinline__ void emit8(const GradSink<SG>& G, int off, const float (&v)[kSmallH], float scale, const Geom& g, bool ok) {
+  if (G.off) return;
   float s[kSmallH];
 #pragma unroll
   for (int h = 0; h < kSmallH; ++h) s[h] = across_groups_sum(v[h] * scale, g.gs);
@@ -76,6 +81,7 @@ __device__ __forceinline__ void emit8(const GradSink<SG>& G, int off, const floa
 }
 template <bool SG>
 __device__ __forceinline__ void emit8_chain(const GradSink<SG>& G, int off, const float (&v)[kSmallH], float scale, const Geom& g) {
+  if (G.off) return;
   float s[kSmallH];
 #pragma unroll
   for (int h = 0; h < kSmallH; ++h) s[h] = across_groups_sum(g.j == 0 ? v[h] * scale : 0.f, g.gs);
@@ -243,6 +249,7 @@ __global__ void __launch_bounds__(kThreads, 2) flow_train_kernel(const TrainArgs
   GradSink<SG> G;
   G.g = A.grad;
   G.sbase = 0u;
+  G.off = false;
   if (SG) {
     for (int i = threadIdx.x; i < (int)A.f.blob_floats; i += blockDim.x) sgrad[i] = 0.f;
     G.sbase = (unsigned)__cvta_generic_to_shared(sgrad);
@@ -299,6 +306,44 @@ __global__ void __launch_bounds__(kThreads, 2) flow_train_kernel(const TrainArgs
   }
 }
 
+// One deterministic-Langevin update of every particle (nfmc/dlmc.py:86-88): x <- x - step * grad_x [ U(x) + log q(x) ].
+// grad_x log q comes from the same reversible sweep as the training gradient with the parameter emitters switched off
+// (the cotangent that reaches the input is d(-log q)/dx); grad U is the closed form.
+template <int E>
+__global__ void __launch_bounds__(kThreads, 2) flow_dlmc_kernel(const TrainArgs A) {
+  extern __shared__ __align__(16) float sgrad[];
+  GradSink<false> G;
+  G.g = nullptr; G.sbase = 0u; G.off = true;
+  const Geom g = make_geom(A.f.d, A.f.gs);
+  const FlowDesc F = make_flow_desc(A.f.blob, A.f.d, A.f.Lc, A.f.M, A.f.H);
+  const int cpc = kThreads / A.f.gs;
+  const long long tiles = (A.n + cpc - 1) / cpc;
+  float* stash = A.stash ? sgrad + threadIdx.x : nullptr;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long chain_raw = tile * cpc + threadIdx.x / A.f.gs;
+    const bool active = chain_raw < A.n;
+    const long long chain = active ? chain_raw : A.n - 1;
+    float* row = A.x_rw + chain * (long long)A.f.d;
+    float lo[E], hi[E], glo[E], ghi[E];
+    load_chain(row, g, lo, hi);
+    flow_pass<E, false, false, true>(F, g, false, lo, hi, nullptr, stash);          // z
+#pragma unroll
+    for (int e = 0; e < E; ++e) { glo[e] = lo[e]; ghi[e] = hi[e]; }                    // d(-log q)/dz = z
+    flow_train_sweep<E, false>(F, g, false, 1.f, lo, hi, glo, ghi, G, stash);          // -> d(-log q)/dx
+    load_chain(row, g, lo, hi);                                                        // the exact x, not the re-derived one
+    const PotCtx c = pot_prepare_rt<E>(A.pot_kind, A.pot, g, lo, hi);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int kk = g.j + g.gs * e;
+      float ul, uh;
+      pot_grad_rt(A.pot_kind, A.pot, c, g, kk, lo[e], hi[e], ul, uh);
+      lo[e] = __fsub_rn(lo[e], __fmul_rn(A.step, __fsub_rn(ul, glo[e])));            // grad = grad U + grad log q
+      hi[e] = __fsub_rn(hi[e], __fmul_rn(A.step, __fsub_rn(uh, ghi[e])));
+    }
+    if (active) store_chain(row, g, lo, hi);
+  }
+}
+
 // shared_grad: accumulate per CTA in shared memory (smem = blob_floats * 4 bytes); chosen by the caller for large batches
 template <int E>
 int launch_flow_train(const TrainArgs& A, int grid, bool shared_grad, cudaStream_t s) {
@@ -314,5 +359,14 @@ int launch_flow_train(const TrainArgs& A, int grid, bool shared_grad, cudaStream
   return check_cuda(cudaGetLastError(), "flow_train_kernel launch");
 }
 template int launch_flow_train<NFMC_ONLY_E>(const TrainArgs&, int, bool, cudaStream_t);
+
+template <int E>
+int launch_flow_dlmc(const TrainArgs& A, int grid, cudaStream_t s) {
+  const size_t stash_b = A.stash ? (size_t)A.f.Lc * cond_stash_floats<E>() * kThreads * sizeof(float) : 0;
+  NFMC_SET_SMEM_RET((flow_dlmc_kernel<E>), stash_b);
+  flow_dlmc_kernel<E><<<grid, kThreads, stash_b, s>>>(A);
+  return check_cuda(cudaGetLastError(), "flow_dlmc_kernel launch");
+}
+template int launch_flow_dlmc<NFMC_ONLY_E>(const TrainArgs&, int, cudaStream_t);
 
 }  // namespace nfmc

@@ -234,6 +234,16 @@ class JumpNFMCParameters(NFMCParameters):
 
 
 @dataclass
+class DLMCKernel(NFMCKernel):
+    step_size: float = 0.05                      # reference: nfmc/dlmc.py:12-14
+
+
+@dataclass
+class DLMCParameters(NFMCParameters):
+    latent_updates: bool = False                 # reference: nfmc/dlmc.py:17-19
+
+
+@dataclass
 class TESSKernel(NFMCKernel):
     """Reference: nfmc/tess.py:78-80 (ESSKernel + NFMCKernel).  Only the identity covariance runs on the device path."""
     cov: torch.Tensor = None

@@ -24,7 +24,7 @@ import torch
 from . import _native as N
 from .flow import Flow
 from .potentials import resolve_target
-from .records import (TESSKernel, TESSParameters, ESSKernel, ESSParameters, MHKernel, MHParameters, HMCKernel, HMCParameters, IMHKernel, IMHParameters, JumpNFMCOutput, JumpNFMCParameters,
+from .records import (DLMCKernel, DLMCParameters, TESSKernel, TESSParameters, ESSKernel, ESSParameters, MHKernel, MHParameters, HMCKernel, HMCParameters, IMHKernel, IMHParameters, JumpNFMCOutput, JumpNFMCParameters,
                       LangevinKernel, LangevinParameters, MCMCKernel, MCMCOutput, MCMCParameters, MetropolisKernel,
                       MetropolisParameters, NeuTraKernel, NeuTraParameters, NFMCKernel)
 
@@ -922,5 +922,98 @@ class TESS(Sampler):
         out.statistics.update_counters(n_accepted_trajectories=cnt[0], n_attempted_trajectories=cnt[1],
                                        n_target_calls=(M + 1) * ses.n * done)
         out.statistics.update_elapsed_time(t_all)
+        out.kernel = self.kernel
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# deterministic Langevin Monte Carlo
+# ---------------------------------------------------------------------------------------------------------------
+class DLMC(Sampler):
+    """Deterministic Langevin Monte Carlo (reference: nfmc/dlmc.py:22-119): particles take one gradient step on
+    ``U + log q`` (or, with ``latent_updates``, the step of dlmc.py:81-85 between ``T`` and ``T^-1``) with the flow ``q``
+    refitted to the particles every iteration, followed by a flow-proposal MH correction.  ``negative_log_likelihood``
+    only drives the initial update (dlmc.py:60-62), as in the reference."""
+
+    def __init__(self, event_shape, target, negative_log_likelihood, kernel: Optional[DLMCKernel] = None,
+                 params: Optional[DLMCParameters] = None):
+        super().__init__(event_shape, target, kernel or DLMCKernel(tuple(event_shape)), params or DLMCParameters())
+        self.negative_log_likelihood = resolve_target(negative_log_likelihood, self.event_shape)
+
+    @property
+    def name(self):
+        return "DLMC"
+
+    def warmup(self, x0, show_progress=True, time_limit_seconds=None) -> MCMCOutput:
+        out = MCMCOutput(event_shape=tuple(x0.shape[1:]), store_samples=self.params.store_samples)   # dlmc.py:37-42
+        out.running_samples.add(x0)
+        return out
+
+    def sample(self, x0, show_progress=True, time_limit_seconds=None, z=None, uniforms=None, refit: bool = True) -> MCMCOutput:
+        """``z [T,n,d]`` / ``uniforms [T,n]`` optionally inject the proposal draws; ``refit=False`` freezes the flow
+        (parity tests: the refit is an optimiser run, everything else is pinned to the reference)."""
+        from .flow_train import train_val_split
+        p: DLMCParameters = self.params
+        flow: Flow = self.kernel.flow
+        if flow.bijection.uses_tensor_cores() or N.lib().nfmc_flow_param_count(
+                flow.bijection.n_dim, flow.bijection.n_coupling, *flow.bijection.conditioner_shape()) < 0:
+            raise NotImplementedError("dlmc needs the gradient of log q: conditioners with 2 linear layers and <= 8 hidden units")
+        event_shape = tuple(x0.shape[1:])
+        store = bool(p.store_samples)
+        out = MCMCOutput(event_shape, store_samples=store)
+        ses = DeviceSession(x0, event_shape, self.device, self.seed, self.chain0)
+        dev = ses.device
+        eps = float(self.kernel.step_size)
+        tgt, keep = self.target.descriptor(dev)
+        nll, keep_n = self.negative_log_likelihood.descriptor(dev)
+        logq = torch.empty(ses.n, device=dev, dtype=torch.float32)
+        rs = out.running_samples
+        ses.tic()
+        N.check(N.lib().nfmc_potential_step(C.byref(nll), N.ptr(ses.x), ses.n, eps, ses.stream))      # dlmc.py:60-62
+        out.statistics.update_counters(n_target_calls=ses.n, n_target_gradient_calls=ses.n)
+        out.statistics.update_elapsed_time(ses.toc())
+        done = 0
+        for i in _progress(range(int(p.n_iterations)), 'DLMC sampling', show_progress):
+            if time_limit_seconds is not None and out.statistics.elapsed_time_seconds >= time_limit_seconds:
+                break
+            t0 = time.time()
+            if refit:                                                                              # dlmc.py:73-79
+                x_train, x_val = train_val_split(ses.x, p.train_pct, p.max_train_size, p.max_val_size)
+                flow.fit(x_train, x_val=x_val, **p.flow_fit_kwargs)
+            fd, keep_f = flow.bijection.descriptor(dev)
+            if p.latent_updates:                                                                   # dlmc.py:81-85
+                zz, _ = flow.bijection.forward(ses.x)
+                _, grad = self.target.value_and_grad(ses.x)
+                N.check(N.lib().nfmc_dlmc_latent_update(N.ptr(zz), N.ptr(grad), eps, zz.numel(), ses.stream))
+                ses.x.copy_(flow.bijection.inverse(zz)[0])
+            else:                                                                                  # dlmc.py:86-88
+                N.check(N.lib().nfmc_dlmc_update(C.byref(tgt), C.byref(fd), N.ptr(ses.x), ses.n, eps, ses.stream))
+            out.statistics.update_counters(n_target_calls=ses.n, n_target_gradient_calls=ses.n)
+            buf, sink = None, None
+            if store:
+                if _rows_kept(rs.seen_samples, 1, rs.thinning):
+                    buf = torch.empty(1, ses.n, ses.d, device=dev, dtype=torch.float32)
+                    sink = ses.sink(buf, rs.seen_samples, rs.thinning)
+            zi = None if z is None else N.dev_f32(z[i], dev).reshape(1, ses.n, ses.d)
+            ui = None if uniforms is None else N.dev_f32(uniforms[i], dev).reshape(1, ses.n)
+            rng = N.rng_desc(ses.seed, ses.flow_step, zi, ui)
+            st = ses.stats()
+            N.check(N.lib().nfmc_imh_steps(C.byref(tgt), C.byref(fd), N.ptr(ses.x), N.ptr(logq), ses.n, 1, 1, C.byref(rng),
+                                           ses.chain0, C.byref(st), None if sink is None else C.byref(sink), ses.stream))
+            ses.flow_step += 1
+            out.statistics.update_counters(n_target_calls=2 * ses.n)                               # dlmc.py:109-113
+            done += 1
+            if store:
+                if buf is not None:
+                    rs.add(buf.reshape(-1, ses.n, *event_shape), already_thinned=True, n_seen=1)
+                else:
+                    rs.seen_samples += 1
+            torch.cuda.current_stream(dev).synchronize()
+            out.statistics.update_elapsed_time(time.time() - t0)
+        sx, sx2, cnt = ses.read_back()
+        out.statistics.expectations.add_sums(sx, sx2, ses.n * done)
+        out.statistics.update_counters(n_accepted_trajectories=cnt[0], n_attempted_trajectories=cnt[1])
+        out.statistics.n_nonfinite = cnt[2]
+        rs.set_last_device(ses.x.reshape(ses.n, *event_shape))
         out.kernel = self.kernel
         return out

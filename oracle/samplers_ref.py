@@ -492,6 +492,49 @@ def run_tess(x0, potential, flow, n_iterations: int, draws, max_iterations: int 
 
 
 # ---------------------------------------------------------------------------------------------------------
+# deterministic Langevin Monte Carlo (nfmc/dlmc.py)
+# ---------------------------------------------------------------------------------------------------------
+def run_dlmc(x0, target, nll, flow, n_iterations: int, draws, step_size: float = 0.05, latent_updates: bool = False,
+             fit: Optional[Callable] = None, store: bool = True) -> RunRef:
+    """``DLMC.sample`` (nfmc/dlmc.py:44-119).  ``fit(flow, x)`` stands for the per-iteration flow refit (:73-79); ``None``
+    keeps the flow frozen (what the golden fixture pins -- the refit itself is torchflows' optimiser)."""
+    n = x0.shape[0]
+    out = RunRef(event_shape=tuple(x0.shape[1:]))
+    _, g = value_and_grad(nll, x0)
+    x = (x0 - step_size * g).detach()                                             # :60-62
+    out.n_target_calls += n
+    out.n_grad_calls += n                                                          # :64-67
+    for _ in range(n_iterations):
+        if fit is not None:
+            fit(flow, x)
+        if latent_updates:                                                         # :81-85
+            with torch.no_grad():
+                z, _ = flow.bijection.forward(x)
+            _, g = value_and_grad(target, x)
+            z = z - step_size * (g - z)
+            with torch.no_grad():
+                x, _ = flow.bijection.inverse(z)
+        else:                                                                      # :86-88
+            _, g = value_and_grad(lambda v: target(v) + flow.log_prob(v), x)
+            x = x - step_size * g
+        out.n_target_calls += n
+        out.n_grad_calls += n                                                      # :90-93
+        x_tilde, _ = flow_sample_with_logq(flow, n, draws)                         # :94
+        with torch.no_grad():
+            log_alpha = mh_log_ratio(-target(x), -target(x_tilde), flow.log_prob(x), flow.log_prob(x_tilde))   # :95-100
+        u = draws.uniform(n)
+        mask = torch.log(u) < log_alpha                                            # :101-102
+        x = x.detach().clone()
+        x[mask] = x_tilde[mask]                                                    # :103
+        out.observe(x, store)                                                      # :107-108
+        out.n_target_calls += 2 * n
+        out.n_accepted += int(torch.sum(mask))
+        out.n_attempted += n                                                       # :109-113
+    out.x = x
+    return out.finish(store)
+
+
+# ---------------------------------------------------------------------------------------------------------
 # warm-up tuning (mcmc/base.py:142-161, tuning.py:15-41)
 # ---------------------------------------------------------------------------------------------------------
 class DualAveragingRef:

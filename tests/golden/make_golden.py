@@ -37,6 +37,7 @@ from nfmc.algorithms.sampling.nfmc.jump import JumpMALA, JumpHMC, JumpESS, JumpN
 from nfmc.algorithms.sampling.nfmc.neutra import NeuTraHMC, NeuTraMH, NeuTraKernel, NeuTraParameters  # noqa: E402
 from nfmc.algorithms.sampling.base import NFMCKernel                                   # noqa: E402
 from nfmc.algorithms.sampling.nfmc.tess import TESS, TESSKernel, TESSParameters       # noqa: E402
+from nfmc.algorithms.sampling.nfmc.dlmc import DLMC, DLMCKernel, DLMCParameters       # noqa: E402
 
 from oracle.potentials_ref import make_potential_ref                                   # noqa: E402
 from oracle.realnvp_ref import make_flow                                               # noqa: E402
@@ -286,6 +287,22 @@ def main():
     with Tape() as t:
         out = s.sample(x0.clone(), show_progress=False)
     cases["tess_fn"] = pack(out, t, x0, dict(pot="fn", T=T, M=M, **flow_arrays(flow, 3, 2, 4)))
+
+    # ---- deterministic Langevin Monte Carlo with the per-iteration refit switched off (the refit is torchflows' optimiser,
+    #      absent here; everything else of dlmc.py:44-119 is pinned), both update rules ---------------------------------
+    for tag, latent, seed in (("dlmc_gm", False, 26), ("dlmc_latent_gm", True, 27)):
+        torch.manual_seed(seed)
+        d, n, T = 6, 7, 4
+        target = make_potential_ref("gm", (d,))
+        nll = make_potential_ref("g0", (d,))
+        flow = make_flow((d,), n_layers=2, perturb=0.1, seed=109)
+        flow.fit = lambda *a, **k: None
+        x0 = torch.randn(n, d)
+        s = DLMC((d,), target, nll, DLMCKernel((d,), flow=flow, step_size=0.05),
+                 DLMCParameters(n_iterations=T, latent_updates=latent))
+        with Tape() as t:
+            out = s.sample(x0.clone(), show_progress=False)
+        cases[tag] = pack(out, t, x0, dict(pot="gm", nll="g0", T=T, step=0.05, latent=int(latent), **flow_arrays(flow, 2, 2, 4)))
 
     for name, arrays in cases.items():
         path = os.path.join(HERE, f"{name}.npz")

@@ -99,3 +99,13 @@ def test_tess():
     # draw order per iteration: normal(n,d) = v, uniform(n) = w, normal(n) = theta, then M x uniform(n,1)
     run = R.run_tess(torch.from_numpy(g["x0"]), oracle_target(g), oracle_flow(g), int(g["T"]), tape(g), max_iterations=int(g["M"]))
     _check(g, run)
+
+
+@pytest.mark.parametrize("name", ["dlmc_gm", "dlmc_latent_gm"])
+def test_dlmc(name):
+    from oracle.potentials_ref import make_potential_ref
+    g = load_case(name)
+    d = g["x0"].shape[1]
+    run = R.run_dlmc(torch.from_numpy(g["x0"]), oracle_target(g), make_potential_ref(str(g["nll"]), (d,)), oracle_flow(g),
+                     int(g["T"]), tape(g), step_size=float(g["step"]), latent_updates=bool(int(g["latent"])))
+    _check(g, run)
