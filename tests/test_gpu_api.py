@@ -171,7 +171,10 @@ def test_time_limit_stops_early():
 
 def test_unsupported_strategy_and_target_raise():
     with pytest.raises(NotImplementedError):
-        sample(_g((5,)), strategy="tess", n_chains=4, n_iterations=2)
+        sample(_g((5,)), strategy="nuts", n_chains=4, n_iterations=2)
+    assert sorted(nfmc_b200.get_supported_samplers()) == sorted([
+        "hmc", "uhmc", "ula", "mala", "mh", "ess", "imh", "fixed_imh", "adaptive_imh", "jump_mala", "jump_ula", "jump_hmc",
+        "jump_uhmc", "jump_ess", "jump_mh", "neutra_mh", "neutra_hmc", "tess", "dlmc"])        # reference: util.py:421-444
     with pytest.raises(NotImplementedError):
         sample(lambda x: (x ** 2).sum(-1), event_shape=(5,), strategy="mala", n_chains=4, n_iterations=2)
     with pytest.raises(ValueError):
