@@ -308,3 +308,58 @@ def test_full_pipeline_recovers_target_moments():
     assert np.abs((mean - np.linspace(-1.0, 1.0, d)) / sig.numpy()).max() < 0.1, mean
     np.testing.assert_allclose(var, sig.numpy() ** 2, rtol=0.15)
     assert out.statistics.jump_acceptance_rate > 0.2, out.statistics.jump_acceptance_rate
+
+
+# ---- the rest of the reference's sampler suite (test_samplers.py:57-140,204-262), restated ---------------------------------
+def test_ess_class():                                                        # test_samplers.py:57-74
+    from nfmc_b200.samplers import ESS
+    torch.manual_seed(0)
+    s = ESS(event_shape=(5,), target=_g((5,)), negative_log_likelihood=_g((5,)))
+    s.params.n_iterations = 3
+    out = s.sample(x0=torch.randn(4, 5), show_progress=False)
+    assert isinstance(out, MCMCOutput)
+    assert out.samples.shape == (3, 4, 5) and bool(torch.isfinite(out.samples).all())
+
+
+def test_jump_ess_class():                                                   # test_samplers.py:77-96
+    from nfmc_b200.samplers import JumpESS
+    torch.manual_seed(0)
+    s = JumpESS(event_shape=(5,), target=_g((5,)), negative_log_likelihood=_g((5,)))
+    s.params.n_iterations = 3
+    out = s.sample(x0=torch.randn(4, 5), show_progress=False)
+    assert out.samples.shape == (3 * (s.inner_sampler.params.n_iterations + 1), 4, 5)
+    assert bool(torch.isfinite(out.samples).all())
+
+
+@pytest.mark.parametrize("name", ["TESS", "DLMC"])
+def test_nfmc_with_nll(name):                                                # test_samplers.py:99-120
+    from nfmc_b200 import samplers
+    torch.manual_seed(0)
+    s = getattr(samplers, name)(event_shape=(5,), target=_g((5,)), negative_log_likelihood=_g((5,)))
+    s.params.n_iterations = 3
+    out = s.sample(x0=torch.randn(4, 5), show_progress=False)
+    assert isinstance(out, MCMCOutput)
+    assert out.samples.shape == (3, 4, 5) and bool(torch.isfinite(out.samples).all())
+
+
+@pytest.mark.parametrize("strategy", ["dlmc", "tess", "ess"])
+def test_sample_wrapper_nll(strategy):                                       # test_samplers.py:204-224
+    torch.manual_seed(0)
+    out = sample(_g((5,)), event_shape=(5,), strategy=strategy, negative_log_likelihood=_g((5,)), n_chains=4, n_iterations=3,
+                 device=torch.device("cuda"), show_progress=False)
+    assert isinstance(out, MCMCOutput)
+    assert out.samples.shape == (3, 4, 5) and bool(torch.isfinite(out.samples).all())
+
+
+def test_sample_wrapper_jump_ess():                                          # test_samplers.py:250-272
+    torch.manual_seed(0)
+    out = sample(_g((5,)), event_shape=(5,), strategy="jump_ess", negative_log_likelihood=_g((5,)), n_chains=4, n_iterations=3,
+                 inner_param_kwargs={"n_iterations": 7}, device=torch.device("cuda"), show_progress=False)
+    assert out.samples.shape == (3 * 8, 4, 5) and bool(torch.isfinite(out.samples).all())
+
+
+def test_neutra_mh_wrapper():
+    torch.manual_seed(0)
+    out = sample(_g((5,)), event_shape=(5,), strategy="neutra_mh", n_chains=4, n_iterations=3, device=torch.device("cuda"),
+                 show_progress=False)
+    assert out.samples.shape == (3, 4, 5) and bool(torch.isfinite(out.samples).all())
