@@ -24,7 +24,10 @@ def run(name, strategy, pot, d, n, T, K=None, flow_spec="realnvp", adapt=False, 
     pk = {"n_iterations": T, "store_samples": False}
     if fit_nf:
         pk.update(fit_nf=True, n_jumps_before_training=0)
-    s = nfmc_b200.create_sampler(make_potential(pot, (d,)), flow=flow, strategy=strategy, param_kwargs=pk, **ik, **kw)
+    if strategy in ("ess", "jump_ess", "tess", "dlmc"):
+        kw = dict(kw, negative_log_likelihood=make_potential(pot, (d,)))
+    s = nfmc_b200.create_sampler(make_potential(pot, (d,)), flow=None if strategy == "ess" else flow, strategy=strategy,
+                                 param_kwargs=pk, **ik, **kw)
     if hasattr(s, "adapt"):
         s.adapt = adapt                      # False: MH part only (all iterations fused into one launch)
     if strategy == "adaptive_imh":
@@ -58,5 +61,9 @@ if __name__ == "__main__":
         131072, 2, K=100, fit_nf=True)
     run("C5-shape jump_mala mixture d=1000 n=131072 (1/8 of 2^20, frozen flow)", "jump_mala", "gm", 1000, 131072, 2, K=100)
     run("CT jump_mala d=100 n=2^20", "jump_mala", "g0", 100, 1 << 20, 5, K=100)
+    run("ess funnel-likelihood d=100 n=2^20", "ess", "fn", 100, 1 << 20, 20)
+    run("tess funnel d=100 n=2^18 (frozen flow)", "tess", "fn", 100, 1 << 18, 10)
+    run("neutra_mh funnel d=100 n=2^20", "neutra_mh", "fn", 100, 1 << 20, 20)
+    run("dlmc mixture d=100 n=2^17 (refit every iteration)", "dlmc", "gm", 100, 1 << 17, 4)
     run("wide-flow jump_mala d=100 n=2^20 H=256 Lc=4 (tcgen05)", "jump_mala", "g0", 100, 1 << 20, 5, K=100, flow_spec=wide)
     run("wide-flow imh d=100 n=2^20 H=256 Lc=4 (tcgen05)", "imh", "g0", 100, 1 << 20, 10, flow_spec=wide)
