@@ -215,6 +215,7 @@ def native_arm(args):
     st_local = N.StatsDesc(moments.data_ptr(), moments.data_ptr() + 8 * d, counts.data_ptr())
     st_jump = N.StatsDesc(moments.data_ptr(), moments.data_ptr() + 8 * d, counts.data_ptr() + 32)
     stream = N.stream_ptr(dev)
+    logq_scratch = torch.empty(n, device=dev, dtype=torch.float32)     # log q(x) between the two kernels of the NF jump
     flush = None
     if n * d * 4 <= 126e6:
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -230,7 +231,8 @@ def native_arm(args):
 
     def jump_launch(it):
         rng = N.rng_desc(seed, it, None, None)
-        N.check(lib.nfmc_jump_step(C.byref(pd), C.byref(fd), N.ptr(x), n, 1, C.byref(rng), chain0, C.byref(st_jump), None, stream))
+        N.check(lib.nfmc_jump_step2(C.byref(pd), C.byref(fd), N.ptr(x), N.ptr(logq_scratch), n, 1, C.byref(rng), chain0,
+                                    C.byref(st_jump), None, stream))
 
     def barrier():
         if world > 1:
@@ -241,7 +243,8 @@ def native_arm(args):
         """One step of the hot path: K local steps + 1 NF jump for every chain, through the whole-run entry point (chains
         cut into slabs spread over several streams so that kernels of different slabs overlap)."""
         N.check(lib.nfmc_jump_sample_device(C.byref(pd), C.byref(fd), N.ptr(x), n, w["kind"], 1, K, float(w["step"]), w["L"],
-                                            None, 1, 1, seed, it * K, it, chain0, C.byref(st_local), C.byref(st_jump), stream))
+                                            None, 1, 1, seed, it * K, it, chain0, C.byref(st_local), C.byref(st_jump), N.ptr(logq_scratch),
+                                            stream))
 
     it = 0
     for _ in range(args.warmup):
@@ -361,7 +364,7 @@ def native_arm(args):
                              "the kernel keeps the state on chip for all K steps, so real DRAM traffic is ~8*d*n per launch and the "
                              "kernel is bound by fp32/integer issue (Philox + Box-Muller), see DESIGN.md"},
         "e2e": e2e,
-        "gpu_launches": 2 * int(lib.nfmc_jump_sample_slabs(d, n, 0)) * args.steps,
+        "gpu_launches": 3 * int(lib.nfmc_jump_sample_slabs(d, n, 0)) * args.steps,
         "clocks": clk,
         "acceptance": {"local": acc[0] / max(acc[1], 1), "jump": acc[4] / max(acc[5], 1)},
     }

@@ -76,6 +76,8 @@ SIGNATURES = {
                                  P(StatsDesc), P(SinkDesc), _vp]),
     "nfmc_jump_step": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _vp, _i64, _i32, P(RngDesc), _i64,
                                  P(StatsDesc), P(SinkDesc), _vp]),
+    "nfmc_jump_step2": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _vp, _vp, _i64, _i32, P(RngDesc), _i64,
+                                  P(StatsDesc), P(SinkDesc), _vp]),
     "nfmc_imh_steps": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _vp, _vp, _i64, _i32, _i32, P(RngDesc), _i64,
                                  P(StatsDesc), P(SinkDesc), _vp]),
     "nfmc_neutra_hmc_steps": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _vp, _i64, _i32, _f32, _i32, _vp,
@@ -99,7 +101,7 @@ SIGNATURES = {
     "nfmc_dlmc_latent_update": (C.c_int, [_vp, _vp, _f32, _i64, _vp]),
     "nfmc_jump_sample_slabs": (_i64, [_i32, _i64, _i32]),
     "nfmc_jump_sample_device": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _vp, _i64, _i32, _i32, _i32, _f32, _i32, _vp, _i32,
-                                          _i32, C.c_uint64, C.c_uint64, C.c_uint64, _i64, P(StatsDesc), P(StatsDesc), _vp]),
+                                          _i32, C.c_uint64, C.c_uint64, C.c_uint64, _i64, P(StatsDesc), P(StatsDesc), _vp, _vp]),
     "nfmc_jump_workspace_bytes": (_i64, [_i32, _i64, _i64]),
     "nfmc_jump_sample_host": (C.c_int, [P(PotentialDesc), _vp, _i64, P(RealNVPDesc), _vp, _vp, _i64, _i32, _i32, _i32,
                                         _f32, _i32, _u64, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),

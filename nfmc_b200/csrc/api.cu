@@ -42,7 +42,8 @@ static inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 extern "C" int64_t nfmc_jump_workspace_bytes(int32_t d, int64_t n, int64_t blob_floats) {
   return (int64_t)(align256((size_t)n * d * sizeof(float)) + align256((size_t)blob_floats * sizeof(float)) +
-                   align256((size_t)2 * d * sizeof(float)) + align256((size_t)2 * d * sizeof(double)) + align256(8 * sizeof(unsigned long long)));
+                   align256((size_t)2 * d * sizeof(float)) + align256((size_t)2 * d * sizeof(double)) + align256(8 * sizeof(unsigned long long)) +
+                   align256((size_t)n * sizeof(float)));
 }
 
 // Slab pipeline shared by the two whole-run entry points.  The chain batch is cut into slabs that are spread over four
@@ -83,8 +84,8 @@ struct RunSpec {
   int64_t chain0;
 };
 
-// slab sizes: whole waves of BOTH persistent kernels (local steps run 4 CTAs/SM, the jump 3), so that no launch ends on
-// a partial wave: unit = lcm(4, 3) * SMs CTAs = 12 * SMs * (128 / gs) chains; at least 32768 chains, at most ~24 slabs.
+// slab sizes: about 1.25 x [12 * SMs CTAs' worth of chains] (12 = lcm of the kernels' 4 and 3 CTAs per SM), at least 32768
+// chains, at most ~24 slabs -- large enough that a launch spans several waves, small enough that ~15 slabs interleave.
 // With host copies the first and the last slabs are a quarter / a half of a regular one, so that the copy nothing can
 // overlap with (H2D of the first slab, D2H of the last) is short.
 int plan_slabs(int d, int64_t n, bool ramp_wanted, std::vector<int64_t>& sizes) {
@@ -92,6 +93,9 @@ int plan_slabs(int d, int64_t n, bool ramp_wanted, std::vector<int64_t>& sizes) 
   if (!layout_for_dim(d, L)) return set_error("jump_sample: unsupported event size");
   const int64_t unit = 12ll * sm_count() * (kThreads / L.gs);
   int64_t slab = unit * ((32768 + unit - 1) / unit);
+  // measured (2^20 chains, d = 100, unit = 56832 chains; device-resident / host-buffer chain-steps/s): 1 unit 5.68e9 /
+  // 4.95e9, 1.25 units 5.73e9 / 5.46e9, 1.5 units 5.73e9 / 5.33e9, 2 units 5.55e9 / 5.27e9, 2.5 units 5.76e9 / 5.10e9
+  slab = (slab * 5 / 4 + 1023) / 1024 * 1024;
   while ((n + slab - 1) / slab > 24) slab += unit;
   if (const char* ev = getenv("NFMC_SLAB_CHAINS")) { const long long v = atoll(ev); if (v >= 1024) slab = v; }
   const int64_t q = std::max<int64_t>(slab / 4 / 1024 * 1024, 1024), h = std::max<int64_t>(slab / 2 / 1024 * 1024, 1024);
@@ -106,7 +110,7 @@ int plan_slabs(int d, int64_t n, bool ramp_wanted, std::vector<int64_t>& sizes) 
 
 // enqueue the whole run; `s` is forked into the pipe streams and joined again (no host synchronisation here)
 int run_pipeline(const nfmc_potential& pot, const nfmc_realnvp& flow, float* x_dev, float* x_host, int64_t n, const RunSpec& R,
-                 const nfmc_stats* st_local, const nfmc_stats* st_jump, cudaStream_t s) {
+                 const nfmc_stats* st_local, const nfmc_stats* st_jump, float* logq_scratch, cudaStream_t s) {
   if (int e = ensure_pipe()) return e;
   const int d = pot.d;
   std::vector<int64_t> sizes;
@@ -131,7 +135,8 @@ int run_pipeline(const nfmc_potential& pot, const nfmc_realnvp& flow, float* x_d
       else
         e = nfmc_mh_steps(&pot, xs, cnt, R.n_inner, R.inv_mass_diag, R.local_adjusted, &r_local, R.chain0 + first, st_local, nullptr, ss);
       if (e) return e;
-      if ((e = nfmc_jump_step(&pot, &flow, xs, cnt, R.jump_adjusted, &r_jump, R.chain0 + first, st_jump, nullptr, ss))) return e;
+      if ((e = nfmc_jump_step2(&pot, &flow, xs, logq_scratch ? logq_scratch + first : nullptr, cnt, R.jump_adjusted, &r_jump,
+                               R.chain0 + first, st_jump, nullptr, ss))) return e;
     }
     if (x_host)
       if (int e = check_cuda(cudaMemcpyAsync(x_host + first * d, xs, (size_t)cnt * d * sizeof(float), cudaMemcpyDeviceToHost, ss), "D2H x")) return e;
@@ -155,14 +160,15 @@ extern "C" int nfmc_jump_sample_device(const nfmc_potential* pot, const nfmc_rea
                                        int32_t n_leapfrog, const float* inv_mass_diag, int32_t local_adjusted,
                                        int32_t jump_adjusted, uint64_t seed, uint64_t local_step0, uint64_t jump_step0,
                                        int64_t chain0, const nfmc_stats* local_stats, const nfmc_stats* jump_stats,
-                                       void* stream) {
+                                       float* logq_scratch, void* stream) {
   if (int e = validate_pot(pot)) return e;
   if (!flow || !flow->blob || !x || n < 1) return set_error("jump_sample_device: NULL / empty argument");
   if (pot->d != flow->d) return set_error("jump_sample_device: potential and flow event sizes differ");
   if (inner_kind < 0 || inner_kind > 2 || n_outer < 0 || n_inner < 0) return set_error("jump_sample_device: bad inner_kind / iteration counts");
+  if (jump_adjusted && !logq_scratch) return set_error("jump_sample_device: logq_scratch (n floats) is required for adjusted jumps");
   const RunSpec R{inner_kind, n_outer, n_inner, step_size, n_leapfrog, inv_mass_diag, local_adjusted, jump_adjusted,
                   seed, local_step0, jump_step0, chain0};
-  return run_pipeline(*pot, *flow, x, nullptr, n, R, local_stats, jump_stats, (cudaStream_t)stream);
+  return run_pipeline(*pot, *flow, x, nullptr, n, R, local_stats, jump_stats, logq_scratch, (cudaStream_t)stream);
 }
 
 extern "C" int nfmc_jump_sample_host(const nfmc_potential* pot_h, const float* pot_params_host, int64_t pot_params_floats,
@@ -181,7 +187,8 @@ extern "C" int nfmc_jump_sample_host(const nfmc_potential* pot_h, const float* p
   float* blob_dev = reinterpret_cast<float*>(w); w += align256((size_t)flow_h->blob_floats * sizeof(float));
   float* pp_dev = reinterpret_cast<float*>(w); w += align256((size_t)2 * d * sizeof(float));
   double* mom_dev = reinterpret_cast<double*>(w); w += align256((size_t)2 * d * sizeof(double));
-  unsigned long long* cnt_dev = reinterpret_cast<unsigned long long*>(w);
+  unsigned long long* cnt_dev = reinterpret_cast<unsigned long long*>(w); w += align256(8 * sizeof(unsigned long long));
+  float* logq_dev = reinterpret_cast<float*>(w);
 
   if (int e = check_cuda(cudaMemcpyAsync(blob_dev, blob_host, (size_t)flow_h->blob_floats * sizeof(float), cudaMemcpyHostToDevice, s), "H2D blob")) return e;
   if (pot_params_host && pot_params_floats > 0)
@@ -196,7 +203,7 @@ extern "C" int nfmc_jump_sample_host(const nfmc_potential* pot_h, const float* p
   const nfmc_stats st_local{mom_dev, mom_dev + d, cnt_dev};
   const nfmc_stats st_jump{mom_dev, mom_dev + d, cnt_dev + 4};
   const RunSpec R{inner_kind, n_outer, n_inner, step_size, n_leapfrog, nullptr, 1, 1, seed, 0, 0, chain0};
-  if (int e = run_pipeline(pot, flow, x_dev, x_host, n, R, &st_local, &st_jump, s)) return e;
+  if (int e = run_pipeline(pot, flow, x_dev, x_host, n, R, &st_local, &st_jump, logq_dev, s)) return e;
   if (sum_x_host) cudaMemcpyAsync(sum_x_host, mom_dev, (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, s);
   if (sum_x2_host) cudaMemcpyAsync(sum_x2_host, mom_dev + d, (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, s);
   if (counts_host) cudaMemcpyAsync(counts_host, cnt_dev, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);

@@ -80,6 +80,34 @@ extern "C" int nfmc_jump_step(const nfmc_potential* pot, const nfmc_realnvp* flo
   return launch_jump(pot, flow, x, nullptr, n, 1, 1, adjusted, rng, chain0, stats, sink, stream);
 }
 
+// The NF jump as two kernels: log q(x) by a forward pass into `logq_scratch` [n], then proposal + accept with x loaded
+// after the inverse pass (flow_kernels.cu: jump_propose_accept_kernel).  Same results as nfmc_jump_step.
+extern "C" int nfmc_jump_step2(const nfmc_potential* pot, const nfmc_realnvp* flow, float* x, float* logq_scratch, int64_t n,
+                               int32_t adjusted, const nfmc_rng* rng, int64_t chain0, const nfmc_stats* stats,
+                               const nfmc_sink* sink, void* stream) {
+  if (int e = validate_pot(pot)) return e;
+  if (int e = validate_flow(flow)) return e;
+  if (pot->d != flow->d) return set_error("jump_step2: potential and flow event sizes differ");
+  if (!x || n < 1 || (adjusted && !logq_scratch)) return set_error("jump_step2: bad x / n / logq_scratch");
+  if (adjusted)
+    if (int e = flow_pass(flow, PASS_LOGPROB, x, nullptr, logq_scratch, n, stream)) return e;       // jump.py:218
+  Layout L;
+  if (!layout_for_dim(pot->d, L)) return set_error("jump_step2: unsupported event size");
+  JumpArgs A;
+  A.c.pot = pot_params(pot);
+  A.c.x = x; A.c.n = n; A.c.chain0 = chain0; A.c.d = pot->d; A.c.gs = L.gs; A.c.n_steps = 1;
+  A.c.rng = RngArgs{rng ? rng->seed : 0, rng ? rng->step0 : 0, rng ? rng->normals : nullptr, rng ? rng->uniforms : nullptr};
+  A.c.stats = StatsArgs{stats ? stats->sum_x : nullptr, stats ? stats->sum_x2 : nullptr, stats ? stats->counts : nullptr};
+  A.c.sink = SinkArgs{sink ? sink->samples : nullptr, sink ? sink->seen0 : 0, (sink && sink->thinning > 0) ? sink->thinning : 1};
+  A.logq_x = logq_scratch; A.recompute_logq = 0; A.adjusted = adjusted;
+  A.pot_kind = pot->kind;
+  const size_t smem = plan_flow_smem(A.f, flow, L, true, false);
+  const int grid = grid_for(n, L.gs, 3);
+  cudaStream_t s = (cudaStream_t)stream;
+  NFMC_DISPATCH_E(L.E, { return launch_jump_propose_accept<E>(A, grid, smem, s); });
+  return 0;
+}
+
 extern "C" int nfmc_imh_steps(const nfmc_potential* pot, const nfmc_realnvp* flow, float* x, float* log_q_x, int64_t n,
                               int32_t n_steps, int32_t recompute_logq, const nfmc_rng* rng, int64_t chain0,
                               const nfmc_stats* stats, const nfmc_sink* sink, void* stream) {

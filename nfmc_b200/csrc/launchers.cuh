@@ -91,6 +91,7 @@ template <int E> int launch_flow_sample(const FlowArgs& A, const RngArgs& R, lon
                                         long long n, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_flow_train(const TrainArgs& A, int grid, bool shared_grad, cudaStream_t s);
 template <int E> int launch_jump(const JumpArgs& A, int grid, size_t smem, cudaStream_t s);
+template <int E> int launch_jump_propose_accept(const JumpArgs& A, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_jump_accept(const AcceptArgs& A, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_neutra_hmc(const NeutraArgs& A, int grid, size_t smem, cudaStream_t s);
 template <int E> int launch_flow_dlmc(const TrainArgs& A, int grid, cudaStream_t s);
