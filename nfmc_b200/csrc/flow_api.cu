@@ -101,7 +101,7 @@ extern "C" int nfmc_jump_step2(const nfmc_potential* pot, const nfmc_realnvp* fl
   A.c.sink = SinkArgs{sink ? sink->samples : nullptr, sink ? sink->seen0 : 0, (sink && sink->thinning > 0) ? sink->thinning : 1};
   A.logq_x = logq_scratch; A.recompute_logq = 0; A.adjusted = adjusted;
   A.pot_kind = pot->kind;
-  const size_t smem = plan_flow_smem(A.f, flow, L, true, false);
+  const size_t smem = plan_flow_smem(A.f, flow, L, true, true);
   const int grid = grid_for(n, L.gs, 3);
   cudaStream_t s = (cudaStream_t)stream;
   NFMC_DISPATCH_E(L.E, { return launch_jump_propose_accept<E>(A, grid, smem, s); });

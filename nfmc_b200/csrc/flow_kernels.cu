@@ -210,6 +210,9 @@ __global__ void __launch_bounds__(kThreads, 3) jump_propose_accept_kernel(const 
   const int cpc = kThreads / C.gs;
   const long long tiles = (C.n + cpc - 1) / cpc;
   unsigned int n_acc = 0, n_bad = 0;
+  // running moments: per-lane fp32 sums in shared memory over all of this CTA's tiles, reduced across the warp once at the end
+#pragma unroll
+  for (int e = 0; e < E; ++e) S.mom[e * kThreads] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const long long chain_raw = tile * cpc + threadIdx.x / C.gs;
@@ -244,19 +247,26 @@ __global__ void __launch_bounds__(kThreads, 3) jump_propose_accept_kernel(const 
     }
     if (accept && g.j == 0 && active) ++n_acc;
     if (C.sink.samples && active) sink_store(C.sink, g, C.n, chain, 0, lo, hi);                 // jump.py:243
+    if (active) {
 #pragma unroll
-    for (int e = 0; e < E; ++e) {                                                               // jump.py:240
-      float4 m = make_float4(lo[e], hi[e], lo[e] * lo[e], hi[e] * hi[e]);
-      if (!active) m = make_float4(0.f, 0.f, 0.f, 0.f);
-      const int kk = g.j + g.gs * e;
-      const float a = across_groups_sum(m.x, g.gs), b = across_groups_sum(m.y, g.gs);
-      const float c = across_groups_sum(m.z, g.gs), dd = across_groups_sum(m.w, g.gs);
-      if (g.lane < g.gs) {
-        if (kk < g.da) { atomicAdd(S.st.sx + kk, (double)a); atomicAdd(S.st.sx2 + kk, (double)c); }
-        if (kk < g.db) { atomicAdd(S.st.sx + g.da + kk, (double)b); atomicAdd(S.st.sx2 + g.da + kk, (double)dd); }
+      for (int e = 0; e < E; ++e) {                                                             // jump.py:240
+        float4 m = S.mom[e * kThreads];
+        m.x += lo[e]; m.y += hi[e]; m.z = fmaf(lo[e], lo[e], m.z); m.w = fmaf(hi[e], hi[e], m.w);
+        S.mom[e * kThreads] = m;
       }
     }
     if (active && accept) store_chain(row, g, lo, hi);
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const float4 m = S.mom[e * kThreads];
+    const int kk = g.j + g.gs * e;
+    const float a = across_groups_sum(m.x, g.gs), b = across_groups_sum(m.y, g.gs);
+    const float c = across_groups_sum(m.z, g.gs), dd = across_groups_sum(m.w, g.gs);
+    if (g.lane < g.gs) {
+      if (kk < g.da) { atomicAdd(S.st.sx + kk, (double)a); atomicAdd(S.st.sx2 + kk, (double)c); }
+      if (kk < g.db) { atomicAdd(S.st.sx + g.da + kk, (double)b); atomicAdd(S.st.sx2 + g.da + kk, (double)dd); }
+    }
   }
   n_acc = __reduce_add_sync(0xffffffffu, n_acc);
   n_bad = __reduce_add_sync(0xffffffffu, n_bad);
@@ -372,7 +382,7 @@ int launch_flow_pass(const FlowArgs& A, int mode, const float* in, float* out, f
 #define NFMC_LAUNCH(SBv, Xv, Sv)                                                              \
   do {                                                                                        \
     NFMC_SET_SMEM_RET((flow_pass_kernel<E, SBv, Xv, Sv>), smem);                                        \
-    flow_pass_kernel<E, SBv, Xv, Sv><<<grid, kThreads, smem, s>>>(A, mode, in, out, aux, n);                              \
+    flow_pass_kernel<E, SBv, Xv, Sv><<<occupancy_grid(flow_pass_kernel<E, SBv, Xv, Sv>, smem, n, A.gs), kThreads, smem, s>>>(A, mode, in, out, aux, n);                              \
   } while (0)
   if (!small) { if (A.stage_blob) NFMC_LAUNCH(true, false, false); else NFMC_LAUNCH(false, false, false); }
   else if (A.stage_blob && xl) NFMC_LAUNCH(true, XE, true);
@@ -393,7 +403,7 @@ int launch_flow_sample(const FlowArgs& A, const RngArgs& R, long long chain0, fl
 #define NFMC_LAUNCH(SBv, Xv, Sv)                                                              \
   do {                                                                                        \
     NFMC_SET_SMEM_RET((flow_sample_kernel<E, SBv, Xv, Sv>), smem);                                        \
-    flow_sample_kernel<E, SBv, Xv, Sv><<<grid, kThreads, smem, s>>>(A, R, chain0, x, logq, n);                              \
+    flow_sample_kernel<E, SBv, Xv, Sv><<<occupancy_grid(flow_sample_kernel<E, SBv, Xv, Sv>, smem, n, A.gs), kThreads, smem, s>>>(A, R, chain0, x, logq, n);                              \
   } while (0)
   if (!small) { if (A.stage_blob) NFMC_LAUNCH(true, false, false); else NFMC_LAUNCH(false, false, false); }
   else if (A.stage_blob && xl) NFMC_LAUNCH(true, XE, true);
@@ -413,7 +423,7 @@ int launch_jump(const JumpArgs& A, int grid, size_t smem, cudaStream_t s) {
 #define NFMC_LAUNCH(SBv, Xv, Sv)                                                              \
   do {                                                                                        \
     NFMC_SET_SMEM_RET((jump_kernel<E, SBv, Xv, Sv>), smem);                                        \
-    jump_kernel<E, SBv, Xv, Sv><<<grid, kThreads, smem, s>>>(A);                              \
+    jump_kernel<E, SBv, Xv, Sv><<<occupancy_grid(jump_kernel<E, SBv, Xv, Sv>, smem, A.c.n, A.c.gs), kThreads, smem, s>>>(A);                              \
   } while (0)
   if (!small) { if (A.f.stage_blob) NFMC_LAUNCH(true, false, false); else NFMC_LAUNCH(false, false, false); }
   else if (A.f.stage_blob && xl) NFMC_LAUNCH(true, XE, true);
@@ -433,7 +443,7 @@ int launch_jump_propose_accept(const JumpArgs& A, int grid, size_t smem, cudaStr
 #define NFMC_LAUNCH(SBv, Xv, Sv)                                                              \
   do {                                                                                        \
     NFMC_SET_SMEM_RET((jump_propose_accept_kernel<E, SBv, Xv, Sv>), smem);                                        \
-    jump_propose_accept_kernel<E, SBv, Xv, Sv><<<grid, kThreads, smem, s>>>(A);                              \
+    jump_propose_accept_kernel<E, SBv, Xv, Sv><<<occupancy_grid(jump_propose_accept_kernel<E, SBv, Xv, Sv>, smem, A.c.n, A.c.gs), kThreads, smem, s>>>(A);                              \
   } while (0)
   if (!small) { if (A.f.stage_blob) NFMC_LAUNCH(true, false, false); else NFMC_LAUNCH(false, false, false); }
   else if (A.f.stage_blob && xl) NFMC_LAUNCH(true, XE, true);

@@ -33,6 +33,18 @@ inline bool layout_for_dim(int d, Layout& L) {
   return true;
 }
 
+// persistent grid sized from what the kernel can actually keep resident (its registers and shared memory decide, not a
+// guess): min(tiles, resident CTAs per SM x SMs).  A grid larger than that leaves a partial second wave behind.
+template <typename K>
+inline int occupancy_grid(K kernel, size_t smem, int64_t n, int gs) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int64_t chains_per_cta = kThreads / gs;
+  const int64_t tiles = (n + chains_per_cta - 1) / chains_per_cta;
+  const int64_t cap = (int64_t)sm_count() * per_sm;
+  return (int)(tiles < cap ? tiles : cap);
+}
+
 // most lanes per chain: the smallest instantiated E whose group still fits a warp.  For latency-bound launches (a
 // training minibatch is a few hundred rows) the serial work per lane is what matters, not lane efficiency.
 inline bool layout_wide(int d, Layout& L) {

@@ -359,7 +359,7 @@ int launch_neutra_hmc(const NeutraArgs& A, int grid, size_t smem, cudaStream_t s
 #define NFMC_LAUNCH(SBv, Xv, Sv)                                                              \
   do {                                                                                        \
     NFMC_SET_SMEM_RET((neutra_hmc_kernel<E, SBv, Xv, Sv>), smem);                                        \
-    neutra_hmc_kernel<E, SBv, Xv, Sv><<<grid, kThreads, smem, s>>>(A);                              \
+    neutra_hmc_kernel<E, SBv, Xv, Sv><<<occupancy_grid(neutra_hmc_kernel<E, SBv, Xv, Sv>, smem, A.c.n, A.c.gs), kThreads, smem, s>>>(A);                              \
   } while (0)
   if (!small) { if (A.f.stage_blob) NFMC_LAUNCH(true, false, false); else NFMC_LAUNCH(false, false, false); }
   else if (A.f.stage_blob && xl) NFMC_LAUNCH(true, XE, true);
@@ -380,7 +380,7 @@ int launch_neutra_potential(const FlowArgs& FA, int pot_kind, const PotParams& P
 #define NFMC_LAUNCH(SBv, Xv, Sv)                                                              \
   do {                                                                                        \
     NFMC_SET_SMEM_RET((neutra_potential_kernel<E, SBv, Xv, Sv>), smem);                                        \
-    neutra_potential_kernel<E, SBv, Xv, Sv><<<grid, kThreads, smem, s>>>(FA, pot_kind, P, z, u, grad, n);                              \
+    neutra_potential_kernel<E, SBv, Xv, Sv><<<occupancy_grid(neutra_potential_kernel<E, SBv, Xv, Sv>, smem, n, FA.gs), kThreads, smem, s>>>(FA, pot_kind, P, z, u, grad, n);                              \
   } while (0)
   if (!small) { if (FA.stage_blob) NFMC_LAUNCH(true, false, false); else NFMC_LAUNCH(false, false, false); }
   else if (FA.stage_blob && xl) NFMC_LAUNCH(true, XE, true);
@@ -400,7 +400,7 @@ int launch_neutra_mh(const NeutraArgs& A, int grid, size_t smem, cudaStream_t s)
 #define NFMC_LAUNCH(SBv, Xv, Sv)                                                   \
   do {                                                                             \
     NFMC_SET_SMEM_RET((neutra_mh_kernel<E, SBv, Xv, Sv>), smem);                   \
-    neutra_mh_kernel<E, SBv, Xv, Sv><<<grid, kThreads, smem, s>>>(A);              \
+    neutra_mh_kernel<E, SBv, Xv, Sv><<<occupancy_grid(neutra_mh_kernel<E, SBv, Xv, Sv>, smem, A.c.n, A.c.gs), kThreads, smem, s>>>(A);              \
   } while (0)
   if (!small) { if (A.f.stage_blob) NFMC_LAUNCH(true, false, false); else NFMC_LAUNCH(false, false, false); }
   else if (A.f.stage_blob && xl) NFMC_LAUNCH(true, XE, true);

@@ -183,7 +183,7 @@ int launch_tess(const TessArgs& A, int grid, size_t smem, cudaStream_t s) {
 #define NFMC_LAUNCH(SBv, Xv, Sv)                                          \
   do {                                                                    \
     NFMC_SET_SMEM_RET((tess_kernel<E, SBv, Xv, Sv>), smem);               \
-    tess_kernel<E, SBv, Xv, Sv><<<grid, kThreads, smem, s>>>(A);          \
+    tess_kernel<E, SBv, Xv, Sv><<<occupancy_grid(tess_kernel<E, SBv, Xv, Sv>, smem, A.c.n, A.c.gs), kThreads, smem, s>>>(A);          \
   } while (0)
   if (!small) { if (A.f.stage_blob) NFMC_LAUNCH(true, false, false); else NFMC_LAUNCH(false, false, false); }
   else if (A.f.stage_blob && xl) NFMC_LAUNCH(true, XE, true);
