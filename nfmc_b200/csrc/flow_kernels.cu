@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kThreads) flow_pass_kernel(FlowArgs A, int mod
 }
 
 template <int E, bool SB, bool X, bool SM>
-__global__ void __launch_bounds__(kThreads) flow_sample_kernel(FlowArgs A, RngArgs R, long long chain0, float* __restrict__ x,
+__global__ void __launch_bounds__(kThreads, 3) flow_sample_kernel(FlowArgs A, RngArgs R, long long chain0, float* __restrict__ x,
                                                               float* __restrict__ logq, long long n) {
   extern __shared__ __align__(16) unsigned char smem[];
   const Geom g = make_geom(A.d, A.gs);
@@ -245,7 +245,10 @@ __global__ void __launch_bounds__(kThreads, 3) jump_propose_accept_kernel(const 
       lo[e] = accept ? plo[e] : lo[e];
       hi[e] = accept ? phi[e] : hi[e];
     }
-    if (accept && g.j == 0 && active) ++n_acc;
+    if (accept && g.j == 0 && active) {
+      ++n_acc;
+      if (A.logq_x && A.adjusted) A.logq_x[chain] = f_p;                                        // imh.py:233 (the log q(x) cache)
+    }
     if (C.sink.samples && active) sink_store(C.sink, g, C.n, chain, 0, lo, hi);                 // jump.py:243
     if (active) {
 #pragma unroll
