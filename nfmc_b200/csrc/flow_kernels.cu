@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(kThreads) jump_accept_kernel(const AcceptArgs 
 template <int E>
 int launch_jump_accept(const AcceptArgs& A, int grid, size_t smem, cudaStream_t s) {
   NFMC_SET_SMEM_RET(jump_accept_kernel<E>, smem);
-  jump_accept_kernel<E><<<grid, kThreads, smem, s>>>(A);
+  jump_accept_kernel<E><<<occupancy_grid(jump_accept_kernel<E>, smem, A.c.n, A.c.gs), kThreads, smem, s>>>(A);
   return check_cuda(cudaGetLastError(), "jump_accept_kernel launch");
 }
 template int launch_jump_accept<NFMC_ONLY_E>(const AcceptArgs&, int, size_t, cudaStream_t);

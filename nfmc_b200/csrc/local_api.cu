@@ -158,10 +158,9 @@ extern "C" int nfmc_potential_eval(const nfmc_potential* pot, const float* x, fl
   Layout L;
   if (!layout_for_dim(pot->d, L)) return set_error("potential_eval: unsupported event size");
   const PotParams P = pot_params(pot);
-  const int grid = grid_for(n, L.gs, 8);
   cudaStream_t s = (cudaStream_t)stream;
   NFMC_DISPATCH_POT(pot->kind, NFMC_DISPATCH_E(L.E, {
-    potential_kernel<POT, E><<<grid, kThreads, 0, s>>>(P, x, u, grad, n, pot->d, L.gs);
+    potential_kernel<POT, E><<<occupancy_grid(potential_kernel<POT, E>, 0, n, L.gs), kThreads, 0, s>>>(P, x, u, grad, n, pot->d, L.gs);
   }));
   return check_cuda(cudaGetLastError(), "potential_kernel launch");
 }
@@ -172,8 +171,7 @@ extern "C" int nfmc_rng_fill(const nfmc_rng* rng, int32_t stream_id, int64_t cha
   Layout L;
   if (!layout_for_dim(d, L)) return set_error("rng_fill: unsupported event size");
   RngArgs R{rng->seed, rng->step0, nullptr, nullptr};
-  const int grid = grid_for(n, L.gs, 8);
   cudaStream_t s = (cudaStream_t)stream;
-  NFMC_DISPATCH_E(L.E, { rng_fill_kernel<E><<<grid, kThreads, 0, s>>>(R, (unsigned)stream_id, chain0, d, L.gs, n, n_steps, normals, uniforms); });
+  NFMC_DISPATCH_E(L.E, { rng_fill_kernel<E><<<occupancy_grid(rng_fill_kernel<E>, 0, n, L.gs), kThreads, 0, s>>>(R, (unsigned)stream_id, chain0, d, L.gs, n, n_steps, normals, uniforms); });
   return check_cuda(cudaGetLastError(), "rng_fill_kernel launch");
 }

@@ -345,10 +345,9 @@ extern "C" int nfmc_potential_step(const nfmc_potential* pot, float* x, int64_t 
   Layout L;
   if (!layout_for_dim(pot->d, L)) return set_error("potential_step: unsupported event size");
   const PotParams P = pot_params(pot);
-  const int grid = grid_for(n, L.gs, 8);
   cudaStream_t s = (cudaStream_t)stream;
   NFMC_DISPATCH_POT(pot->kind, NFMC_DISPATCH_E(L.E, {
-    potential_step_kernel<POT, E><<<grid, kThreads, 0, s>>>(P, x, n, pot->d, L.gs, step);
+    potential_step_kernel<POT, E><<<occupancy_grid(potential_step_kernel<POT, E>, 0, n, L.gs), kThreads, 0, s>>>(P, x, n, pot->d, L.gs, step);
   }));
   return check_cuda(cudaGetLastError(), "potential_step_kernel launch");
 }

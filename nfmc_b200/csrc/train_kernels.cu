@@ -351,10 +351,10 @@ int launch_flow_train(const TrainArgs& A, int grid, bool shared_grad, cudaStream
   if (shared_grad) {
     const size_t smem = (size_t)((A.f.blob_floats + 3) & ~3ll) * sizeof(float) + stash_b;
     NFMC_SET_SMEM_RET((flow_train_kernel<E, true>), smem);
-    flow_train_kernel<E, true><<<grid, kThreads, smem, s>>>(A);
+    flow_train_kernel<E, true><<<occupancy_grid(flow_train_kernel<E, true>, smem, A.n, A.f.gs), kThreads, smem, s>>>(A);
   } else {
     NFMC_SET_SMEM_RET((flow_train_kernel<E, false>), stash_b);
-    flow_train_kernel<E, false><<<grid, kThreads, stash_b, s>>>(A);
+    flow_train_kernel<E, false><<<occupancy_grid(flow_train_kernel<E, false>, stash_b, A.n, A.f.gs), kThreads, stash_b, s>>>(A);
   }
   return check_cuda(cudaGetLastError(), "flow_train_kernel launch");
 }
@@ -364,7 +364,7 @@ template <int E>
 int launch_flow_dlmc(const TrainArgs& A, int grid, cudaStream_t s) {
   const size_t stash_b = A.stash ? (size_t)A.f.Lc * cond_stash_floats<E>() * kThreads * sizeof(float) : 0;
   NFMC_SET_SMEM_RET((flow_dlmc_kernel<E>), stash_b);
-  flow_dlmc_kernel<E><<<grid, kThreads, stash_b, s>>>(A);
+  flow_dlmc_kernel<E><<<occupancy_grid(flow_dlmc_kernel<E>, stash_b, A.n, A.f.gs), kThreads, stash_b, s>>>(A);
   return check_cuda(cudaGetLastError(), "flow_dlmc_kernel launch");
 }
 template int launch_flow_dlmc<NFMC_ONLY_E>(const TrainArgs&, int, cudaStream_t);
