@@ -159,10 +159,10 @@ int launch_ess(int pot_kind, bool exact, const EssArgs& A, int grid, size_t smem
   NFMC_DISPATCH_POT(pot_kind, {
     if (exact) {
       NFMC_SET_SMEM_RET((ess_kernel<POT, E, true>), smem);
-      ess_kernel<POT, E, true><<<grid, kThreads, smem, s>>>(A);
+      ess_kernel<POT, E, true><<<occupancy_grid(ess_kernel<POT, E, true>, smem, A.c.n, A.c.gs), kThreads, smem, s>>>(A);
     } else {
       NFMC_SET_SMEM_RET((ess_kernel<POT, E, false>), smem);
-      ess_kernel<POT, E, false><<<grid, kThreads, smem, s>>>(A);
+      ess_kernel<POT, E, false><<<occupancy_grid(ess_kernel<POT, E, false>, smem, A.c.n, A.c.gs), kThreads, smem, s>>>(A);
     }
   });
   return check_cuda(cudaGetLastError(), "ess_kernel launch");

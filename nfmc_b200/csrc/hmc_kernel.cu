@@ -386,14 +386,14 @@ int launch_hmc(int pot_kind, bool exact, const LocalArgs& A, int grid, size_t sm
       constexpr bool PACKED = POT == NFMC_POT_ISO_GAUSSIAN || POT == NFMC_POT_FUNNEL || POT == NFMC_POT_MIXTURE4;
       if constexpr (PACKED) {
         NFMC_SET_SMEM_RET((hmc_fast_kernel<POT, E>), smem);
-        hmc_fast_kernel<POT, E><<<grid, kThreads, smem, s>>>(A);
+        hmc_fast_kernel<POT, E><<<occupancy_grid(hmc_fast_kernel<POT, E>, smem, A.c.n, A.c.gs), kThreads, smem, s>>>(A);
       } else {
         NFMC_SET_SMEM_RET((hmc_kernel<POT, E, true>), smem);
-        hmc_kernel<POT, E, true><<<grid, kThreads, smem, s>>>(A);
+        hmc_kernel<POT, E, true><<<occupancy_grid(hmc_kernel<POT, E, true>, smem, A.c.n, A.c.gs), kThreads, smem, s>>>(A);
       }
     } else {
       NFMC_SET_SMEM_RET((hmc_kernel<POT, E, false>), smem);
-      hmc_kernel<POT, E, false><<<grid, kThreads, smem, s>>>(A);
+      hmc_kernel<POT, E, false><<<occupancy_grid(hmc_kernel<POT, E, false>, smem, A.c.n, A.c.gs), kThreads, smem, s>>>(A);
     }
   });
   return check_cuda(cudaGetLastError(), "hmc_kernel launch");

@@ -386,10 +386,10 @@ int launch_mala(int pot_kind, bool exact, const LocalArgs& A, int grid, size_t s
   NFMC_DISPATCH_POT(pot_kind, {
     if (exact && !A.c.rng.normals && !A.imd && !A.random_walk) {
       NFMC_SET_SMEM_RET((mala_fast_kernel<POT, E>), smem);
-      mala_fast_kernel<POT, E><<<grid, kThreads, smem, s>>>(A);
+      mala_fast_kernel<POT, E><<<occupancy_grid(mala_fast_kernel<POT, E>, smem, A.c.n, A.c.gs), kThreads, smem, s>>>(A);
     } else {
       NFMC_SET_SMEM_RET((mala_kernel<POT, E, false>), smem);
-      mala_kernel<POT, E, false><<<grid, kThreads, smem, s>>>(A);
+      mala_kernel<POT, E, false><<<occupancy_grid(mala_kernel<POT, E, false>, smem, A.c.n, A.c.gs), kThreads, smem, s>>>(A);
     }
   });
   return check_cuda(cudaGetLastError(), "mala_kernel launch");
