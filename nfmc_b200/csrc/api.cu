@@ -95,8 +95,11 @@ int plan_slabs(int d, int64_t n, bool ramp_wanted, std::vector<int64_t>& sizes) 
   int64_t slab = unit * ((32768 + unit - 1) / unit);
   // measured (2^20 chains, d = 100, unit = 56832 chains; device-resident / host-buffer chain-steps/s): 1 unit 5.68e9 /
   // 4.95e9, 1.25 units 5.73e9 / 5.46e9, 1.5 units 5.73e9 / 5.33e9, 2 units 5.55e9 / 5.27e9, 2.5 units 5.76e9 / 5.10e9
-  slab = (slab * 5 / 4 + 1023) / 1024 * 1024;
-  while ((n + slab - 1) / slab > 24) slab += unit;
+  // and, after the jump became two kernels (device / host): 0.67 units 5.81e9 / 5.63e9, 1.25 units 5.85e9 / 5.50e9,
+  // 2 units 5.92e9 / 5.38e9 -- large slabs suit device-resident chains (fewer launch tails), small ones the host path
+  // (shorter copies at both ends, finer interleaving of copy and compute)
+  slab = ramp_wanted ? std::max<int64_t>(32768, (slab * 2 / 3 + 1023) / 1024 * 1024) : slab * 2;
+  while ((n + slab - 1) / slab > 32) slab += unit;
   if (const char* ev = getenv("NFMC_SLAB_CHAINS")) { const long long v = atoll(ev); if (v >= 1024) slab = v; }
   const int64_t q = std::max<int64_t>(slab / 4 / 1024 * 1024, 1024), h = std::max<int64_t>(slab / 2 / 1024 * 1024, 1024);
   int64_t left = n;
