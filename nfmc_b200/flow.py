@@ -411,10 +411,18 @@ def _tc_hidden(H: int) -> int:
 
 @torch.no_grad()
 def pack_realnvp_tc(bij: "RealNVP") -> torch.Tensor:
-    """Pack a RealNVP for the tensor-core path: fp32 affine tables (same as ``pack_realnvp``), then per coupling the
-    bf16 weights in the UMMA shared-memory image ``[K/8][rows][8]`` (K-major, no swizzle) and fp32 biases:
-    ``W1 image [8][H][8]`` (K = d/2 zero padded to 64), ``b1 [H]``, ``Wl image [H/8][N2p][8]`` (row n = 2 t + c,
-    N2p = 2*db rounded up to 16), ``bl [N2p]``.  Reverse permutations are folded in as in ``pack_realnvp``."""
+    """Pack a RealNVP for the tensor-core path (csrc/tc_common.cuh): fp32 affine tables (same as ``pack_realnvp``),
+    then per coupling, bf16 weights in the UMMA shared-memory image ``[K/8][rows][8]`` (K-major, no swizzle):
+
+    * ``W1 image [K1/8][Hp][8]``, K1 = d/2 + 2 rounded up to 16: columns k < d/2 hold W1, column d/2 holds b1 rounded to
+      bf16 and column d/2 + 1 the rounding remainder (the kernel feeds constant ones there, so the bias rides on the GEMM
+      with ~16 bits);
+    * ``Wl' image [Hp/8][N2p][8]`` (row n = 2 t + c, N2p = 2*db rounded up to 16) with the scale rows multiplied by
+      log2(e)/2 and the shift rows by 1/2;
+    * ``bl' [N2p]`` fp32: ``(bl_a / 2 + log(1 - m)) * log2(e)`` and ``bl_b / 2``, so that the kernel's
+      ``alpha = 2^(u_a') + m``, ``beta = u_b'`` equal ``exp(log(1-m) + u_a/2) + m``, ``u_b/2`` of the specification.
+    Reverse permutations are folded in as in ``pack_realnvp``."""
+    import math
     d = bij.n_dim
     da, db = d // 2, d - d // 2
     Lc = bij.n_coupling
@@ -423,6 +431,9 @@ def pack_realnvp_tc(bij: "RealNVP") -> torch.Tensor:
         raise ValueError("shape not supported by the tensor-core path")
     Hp = _tc_hidden(H)
     n2p = ((2 * db + 15) // 16) * 16
+    k1 = ((da + 2 + 15) // 16) * 16
+    log2e = 1.0 / math.log(2.0)
+    c = math.log1p(-MIN_SCALE)
     base = pack_realnvp_affines(bij)
     chunks = [base.contiguous().view(torch.uint8)]
     layers = list(bij.layers)
@@ -431,23 +442,28 @@ def pack_realnvp_tc(bij: "RealNVP") -> torch.Tensor:
         odd = (l + 1) % 2 == 1
         (w1, b1), (wl, bl) = [(m.weight.detach().to("cpu", torch.float32), m.bias.detach().to("cpu", torch.float32))
                               for m in cpl.linears()]
-        w1p = torch.zeros(Hp, 64)
+        w1p = torch.zeros(Hp, k1)
         w1p[:H, :da] = w1.flip(1) if odd else w1                      # [h][ks], zero rows for the padded hidden units
-        img1 = w1p.reshape(Hp, 8, 8).permute(1, 0, 2).contiguous()    # [kg][h][8]
-        b1p = torch.zeros(Hp)
-        b1p[:H] = b1
-        wl3 = wl.reshape(db, 2, H)                                    # [t_log][c][h]
-        bl2 = bl.reshape(db, 2)
+        b1_hi = b1.to(torch.bfloat16).to(torch.float32)
+        w1p[:H, da] = b1_hi
+        w1p[:H, da + 1] = b1 - b1_hi
+        img1 = w1p.reshape(Hp, k1 // 8, 8).permute(1, 0, 2).contiguous()   # [kg][h][8]
+        wl3 = wl.reshape(db, 2, H).clone()                            # [t_log][c][h]
+        bl2 = bl.reshape(db, 2).clone()
         if odd:
             wl3, bl2 = wl3.flip(0), bl2.flip(0)
+        wl3[:, 0, :] *= 0.5 * log2e
+        wl3[:, 1, :] *= 0.5
         wlp = torch.zeros(n2p, Hp)
         wlp[: 2 * db, :H] = wl3.reshape(2 * db, H)                    # row n = 2 t + c
         img2 = wlp.reshape(n2p, Hp // 8, 8).permute(1, 0, 2).contiguous()  # [kg][n][8]
-        blp = torch.zeros(n2p)
-        blp[: 2 * db] = bl2.reshape(-1)
-        chunks += [img1.to(torch.bfloat16).view(torch.uint8).reshape(-1), b1p.contiguous().view(torch.uint8).reshape(-1),
-                   img2.to(torch.bfloat16).view(torch.uint8).reshape(-1), blp.contiguous().view(torch.uint8).reshape(-1)]
-    return torch.cat([c.reshape(-1) for c in chunks]).contiguous()
+        blp = torch.zeros(n2p // 2, 2)
+        blp[:, 0] = c * log2e                                         # padded targets: alpha = 1, beta = 0
+        blp[:db, 0] = (0.5 * bl2[:, 0] + c) * log2e
+        blp[:db, 1] = 0.5 * bl2[:, 1]
+        chunks += [img1.to(torch.bfloat16).view(torch.uint8).reshape(-1), img2.to(torch.bfloat16).view(torch.uint8).reshape(-1),
+                   blp.contiguous().view(torch.uint8).reshape(-1)]
+    return torch.cat([c_.reshape(-1) for c_ in chunks]).contiguous()
 
 
 def create_flow_object(flow_string: str, event_shape, **kwargs) -> Flow:
