@@ -197,6 +197,14 @@ NFMC_API int nfmc_neutra_mh_steps(const nfmc_potential* pot, const nfmc_realnvp*
 NFMC_API int nfmc_neutra_potential(const nfmc_potential* pot, const nfmc_realnvp* flow, const float* z, float* u, float* grad,
                           int64_t n, void* stream);
 
+/* Warm-up adaptation on the device -- replaces MetropolisSampler.update_kernel (/root/reference/nfmc/algorithms/sampling/
+ * mcmc/base.py:142-161).  nfmc_chain_sums: sums[0:d] = sum over chains of x, sums[d:2d] = sum of x^2 (fp64), sums[2d] =
+ * counts[0] (accepted so far; 0 when counts is NULL), sums[2d+1] = n.  A multi-GPU caller all-reduces the 2d+2 doubles,
+ * then nfmc_tune_inv_mass applies imd <- c * var + (1 - c) * imd with the unbiased variance of the pooled sums
+ * (no change when fewer than two chains, base.py:150). */
+NFMC_API int nfmc_chain_sums(const float* x, int64_t n, int32_t d, double* sums, const uint64_t* counts, void* stream);
+NFMC_API int nfmc_tune_inv_mass(const double* sums, int32_t d, float imd_adjustment, float* inv_mass_diag, void* stream);
+
 /* the numbers the Philox path would draw (for parity tests): normals [steps, n, d], uniforms [steps, n];
  * stream_id 0 = local kernels, 1 = flow base draw */
 NFMC_API int nfmc_rng_fill(const nfmc_rng* rng, int32_t stream_id, int64_t chain0, int32_t d, int64_t n, int32_t n_steps,

@@ -74,6 +74,8 @@ SIGNATURES = {
     "nfmc_ess_steps": (C.c_int, [P(PotentialDesc), _vp, _i64, _i32, _i32, P(RngDesc), _i64, P(StatsDesc), P(SinkDesc), _vp]),
     "nfmc_hmc_steps": (C.c_int, [P(PotentialDesc), _vp, _i64, _i32, _f32, _i32, _vp, _i32, P(RngDesc), _i64,
                                  P(StatsDesc), P(SinkDesc), _vp]),
+    "nfmc_chain_sums": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
+    "nfmc_tune_inv_mass": (C.c_int, [_vp, _i32, _f32, _vp, _vp]),
     "nfmc_jump_step": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _vp, _i64, _i32, P(RngDesc), _i64,
                                  P(StatsDesc), P(SinkDesc), _vp]),
     "nfmc_jump_step2": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _vp, _vp, _i64, _i32, P(RngDesc), _i64,

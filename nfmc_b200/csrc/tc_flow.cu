@@ -51,94 +51,142 @@ struct TcArgs {
 };
 
 // ---- the kernel ----------------------------------------------------------------------------------------------------
-template <bool INV>
-__global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const TcArgs A) {
+template <bool INV, bool STAGED>
+__global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const __grid_constant__ TcArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   TcSmem sm = tc_carve(smem, A.S);
   const int tid = threadIdx.x, warp = tid >> 5;
   const TcShape& S = A.S;
   const int d = S.d, da = d / 2, Lc = S.Lc;
 
-  const uint32_t tmem_base = tc_prologue(sm, A.blob, S);
+  tc_prologue(sm, A.blob, S);
   const long long tiles = (A.n + kTcRows - 1) / kTcRows;
   const long long pairs = (tiles + 1) / 2;
   long long my_pairs = 0;
   if ((long long)blockIdx.x < pairs) my_pairs = (pairs - 1 - blockIdx.x) / gridDim.x + 1;
   const uint32_t total_uses = (uint32_t)(my_pairs * Lc);
 
-  if (warp == kTcEpiWarps) {
-    // ================================ control warp ==================================================================
-    if ((tid & 31) == 0) {
-      TcControl ctl(sm, S, A.blob, tmem_base, total_uses, INV ? 1u : 0u);
-      ctl.prime();
-      for (long long p = 0; p < my_pairs; ++p) {
-        // pull the NEXT pair's rows towards L2 while this pair computes
-        const long long next_row0 = ((long long)blockIdx.x + (p + 1) * gridDim.x) * 2 * kTcRows;
-        if (p + 1 < my_pairs) {
-          long long rows = A.n - next_row0;
-          if (rows > 2 * kTcRows) rows = 2 * kTcRows;
-          const size_t bytes = ((size_t)rows * d * sizeof(float)) & ~size_t(15);
-          const float* src = A.in + next_row0 * d;
-          if (bytes >= 16 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) tma_prefetch_l2(src, (uint32_t)bytes);
-        }
-        for (int i = 0; i < Lc; ++i) ctl.coupling();
+  if (warp >= kTcEpiWarps) {
+    // ================================ service warps (uniform control flow, one elected lane issues) ================
+    reg_dealloc<kTcRegsService>();
+    const bool lead = elect_one();
+    if (warp == kTcWarpMma) {
+      TcMma mma(sm, S, INV ? 1u : 0u, lead);
+      for (uint32_t u = 0; u < total_uses; ++u) mma.coupling();
+    } else if (warp == kTcWarpWeights) {
+      tc_weight_loader(sm, S, A.blob, total_uses, INV ? 1u : 0u, lead);
+    } else if (warp == kTcWarpTiles) {
+      if (lead) {
+        if (STAGED) tc_x_loader(sm, S, A.in, A.out, A.n, my_pairs);
+        else tc_tile_prefetch(A.in, A.n, d, my_pairs);
       }
     }
     __syncwarp();
   } else {
     // ================================ epilogue warps ================================================================
-    const int r = tid & (kTcRows - 1), g = tid >> 7;
+    reg_alloc<kTcRegsEpi>();
+    const int r = tid & (kTcRows - 1), g = tid >> 7, q = (tid >> 5) & 3, lane = tid & 31;
     const int e0 = g * kTcOwn;
-    const uint32_t lane_off = (uint32_t)((r >> 5) * 32) << 16;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     TcEpiSync sync(sm);
     const bool flip = (Lc & 1) != 0;
+    const bool fl_in = INV && flip, fl_out = !INV && flip;
     float st[2][2][kTcOwn];   // [tile][half][q]
 
     for (long long p = 0; p < my_pairs; ++p) {
-      const long long row0 = ((long long)blockIdx.x + p * gridDim.x) * 2 * kTcRows + r;   // tile t: row0 + 128 t
+      const long long tile0 = ((long long)blockIdx.x + p * gridDim.x) * 2;
+      { TcEpiSync& sy = sync; TC_TRACE_EPI(39); }
+      if (STAGED) {
+        // ---- boundary p: take the input of this pair out of the tile buffers, leave the previous pair's output there -
+        const bool have_out = p > 0 && A.out != nullptr;
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const long long rr = row0 + t * kTcRows;
-        tc_load_state(A.in + (rr < A.n ? rr : A.n - 1) * (long long)d, d, da, e0, INV && flip, st[t][0], st[t][1]);
+        for (int t = 0; t < 2; ++t) {
+          float* row = reinterpret_cast<float*>(sm.x(t)) + (size_t)r * d;
+          mbar_wait(sync.bar(kTcBarXFull + t), (uint32_t)(p & 1));
+          tc_row_exchange(row, d, da, e0, fl_in, fl_out, have_out, st[t][0], st[t][1]);
+          if (have_out) fence_async_smem();
+          mbar_arrive(sync.bar(kTcBarXReady + t));
+          tc_pass_begin<INV>(sm, S, sync, t, r, g, st[t][0], st[t][1]);
+        }
+      } else {
+        // ---- input: global -> tensor memory (fragment layout) -> registers (row layout) ---------------------------
+        {
+          TcTileBuf B0, B1;
+          tc_tile_in_issue(A.in + tile0 * kTcRows * (long long)d, A.n - tile0 * kTcRows, d, fl_in, q, g, lane, B0);
+          tc_tile_in_issue(A.in + (tile0 + 1) * kTcRows * (long long)d, A.n - (tile0 + 1) * kTcRows, d, fl_in, q, g, lane, B1);
+          tc_tile_in_commit(0, d, q, g, B0);
+          tc_tile_in_commit(kTcRegion, d, q, g, B1);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        tc_epi_barrier();
+        tc_fence_after();
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          tc_tile_in_rows(lane_off + t * kTcRegion, da, g, st[t][0], st[t][1]);
+          tc_pass_begin<INV>(sm, S, sync, t, r, g, st[t][0], st[t][1]);
+        }
       }
       float ld2[2] = {0.f, 0.f};
       { TcEpiSync& sy = sync; TC_TRACE_EPI(40); }
-      tc_run_pass<INV>(sm, S, sync, tmem_base + lane_off, r, g, st, ld2);
+      tc_pass_couplings<INV>(sm, S, sync, lane_off, r, g, st, ld2);
 
       // ---- results ------------------------------------------------------------------------------------------------
       { TcEpiSync& sy = sync; TC_TRACE_EPI(41); }
+      const bool frag_out = A.out != nullptr && !STAGED;
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        const long long rr = row0 + t * kTcRows;
         float sq = 0.f;
         if (A.mode == 2) {
 #pragma unroll
-          for (int q = 0; q < kTcOwn; ++q)
-            if (e0 + q < da) sq = fmaf(st[t][0][q], st[t][0][q], fmaf(st[t][1][q], st[t][1][q], sq));
+          for (int i = 0; i < kTcOwn; ++i)
+            if (e0 + i < da) sq = fmaf(st[t][0][i], st[t][0][i], fmaf(st[t][1][i], st[t][1][i], sq));
         }
         sm.red[(t * 2 + 0) * kTcGroups * kTcRows + g * kTcRows + r] = ld2[t];
         sm.red[(t * 2 + 1) * kTcGroups * kTcRows + g * kTcRows + r] = sq;
-        if (rr < A.n && A.out) tc_store_state(A.out + rr * (long long)d, d, da, e0, !INV && flip, st[t][0], st[t][1]);
+        if (frag_out) tc_tile_out_rows(lane_off + t * kTcRegion, da, g, st[t][0], st[t][1]);
+      }
+      if (frag_out) {
+        tmem_wait_st();
+        tc_fence_before();
       }
       tc_epi_barrier();
+      if (frag_out) {
+        tc_fence_after();
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+          tc_tile_out_store(A.out + (tile0 + t) * kTcRows * (long long)d, A.n - (tile0 + t) * kTcRows, d, fl_out, t * kTcRegion, q, g, lane);
+      }
       // 512 threads, 256 rows: thread (r, g) with g < 2 finishes row r of tile g
-      if (A.aux && g < 2 && row0 + g * kTcRows < A.n) {
+      if (A.aux && g < 2 && (tile0 + g) * kTcRows + r < A.n) {
         const float* rd = sm.red + (g * 2) * kTcGroups * kTcRows;
-        float res = (rd[r] + rd[kTcRows + r] + rd[2 * kTcRows + r] + rd[3 * kTcRows + r]) * 0.6931471805599453f +
-                    sm.aff[(Lc + 1) * 4 * d];
+        float res = (rd[r] + rd[kTcRows + r] + rd[2 * kTcRows + r] + rd[3 * kTcRows + r]) * 0.6931471805599453f + sm.log_const;
         if (INV) res = -res;
         if (A.mode == 2) {
           const float* rs = rd + kTcGroups * kTcRows;
           const float s = rs[r] + rs[kTcRows + r] + rs[2 * kTcRows + r] + rs[3 * kTcRows + r];
           res += -0.5f * s - 0.5f * (float)d * 1.8378770664093453f;
         }
-        A.aux[row0 + g * kTcRows] = res;
+        A.aux[(tile0 + g) * kTcRows + r] = res;
       }
-      tc_epi_barrier();
+      tc_epi_barrier();      // the scratch (it aliases the A1 image) is rewritten by the next pass
       { TcEpiSync& sy = sync; TC_TRACE_EPI(42); }
     }
+    if (STAGED && my_pairs > 0) {
+      // ---- last boundary: the output of the last pair goes into the tile buffers ---------------------------------------
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (A.out) {
+          float* row = reinterpret_cast<float*>(sm.x(t)) + (size_t)r * d;
+          tc_row_write_half<0>(row, d, da, e0, fl_out, st[t][0]);
+          tc_row_write_half<1>(row, d, da, e0, fl_out, st[t][1]);
+          fence_async_smem();
+        }
+        mbar_arrive(sync.bar(kTcBarXReady + t));
+      }
+    }
   }
-  tc_epilogue_dealloc(tmem_base);
+  tc_epilogue_dealloc(0u);
 }
 
 }  // namespace nfmc
@@ -164,17 +212,18 @@ extern "C" int nfmc_flow_tc_pass(const nfmc_realnvp_tc* flow, int32_t mode, cons
   TcArgs A;
   if (int e = tc_validate(flow, A.S, "flow_tc_pass")) return e;
   size_t smem = 0;
-  if (!tc_plan_smem(A.S, 0, smem)) return set_error("flow_tc_pass: shared-memory plan exceeds 227 KB");
+  const bool staged_ok = (flow->d & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (!tc_plan_smem(A.S, 0, smem, staged_ok)) return set_error("flow_tc_pass: shared-memory plan exceeds 227 KB");
+  if ((reinterpret_cast<uintptr_t>(in) & 7) || (reinterpret_cast<uintptr_t>(out) & 7)) return set_error("flow_tc_pass: in / out must be 8-byte aligned");
   A.blob = static_cast<const unsigned char*>(flow->blob);
   A.mode = mode; A.in = in; A.out = out; A.aux = aux; A.n = n;
   const long long pairs = ((n + kTcRows - 1) / kTcRows + 1) / 2;
   const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
-  if (mode == 1) {
-    cudaFuncSetAttribute(flow_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    flow_tc_kernel<true><<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(A);
-  } else {
-    cudaFuncSetAttribute(flow_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    flow_tc_kernel<false><<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(A);
-  }
+  auto launch = [&](auto kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(A);
+  };
+  if (A.S.nx == 2) { if (mode == 1) launch(flow_tc_kernel<true, true>); else launch(flow_tc_kernel<false, true>); }
+  else { if (mode == 1) launch(flow_tc_kernel<true, false>); else launch(flow_tc_kernel<false, false>); }
   return check_cuda(cudaGetLastError(), "flow_tc_kernel launch");
 }

@@ -42,6 +42,12 @@ class GlobalDraws:
             self.uniforms.append(v.clone())
         return v
 
+    def uniform_scalar(self):
+        v = torch.rand(size=())
+        if self.record:
+            self.uniforms.append(v.clone())
+        return v
+
 
 class TapeDraws:
     """Replay pre-drawn numbers (``normals``: list of [n,*event]; ``uniforms``: list of [n])."""
@@ -63,6 +69,12 @@ class TapeDraws:
         self.i_u += 1
         assert v.shape == (n,)
         return v.clone()
+
+    def uniform_scalar(self):
+        v = self.uniforms[self.i_u]
+        self.i_u += 1
+        assert v.numel() == 1
+        return v.reshape(()).clone()
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -545,6 +557,15 @@ class DualAveragingRef:
         self.mu = math.log(10 * initial_step)
         self.kappa, self.gamma, self.target_rate = kappa, gamma, target_rate
 
+    def step_error(self, error) -> float:
+        """``DualAveraging.step`` (tuning.py:25-38) with the acceptance-rate error the caller computed."""
+        self.err += float(error)
+        log_raw = self.mu - self.err / (math.sqrt(self.t) * self.gamma)
+        eta = self.t ** -self.kappa
+        self.log_avg = eta * log_raw + (1 - eta) * self.log_avg
+        self.t += 1
+        return math.exp(self.log_avg)
+
     def step(self, acc_rate: float) -> float:
         self.err += float(self.target_rate - acc_rate)
         log_raw = self.mu - self.err / (math.sqrt(self.t) * self.gamma)
@@ -556,6 +577,65 @@ class DualAveragingRef:
 
 def tune_inv_mass(imd, x, c=1e-3):
     return c * torch.var(x.flatten(1, -1), dim=0) + (1 - c) * imd
+
+
+def run_tuned(x0, target, kind: str, tau: float, imd: torch.Tensor, n_steps: int, draws, n_leapfrog: int = 20,
+              imd_adjustment: float = 1e-3, store: bool = True) -> RunRef:
+    """``MCMCSampler.sample`` with ``params.tuning`` (mcmc/base.py:56-102): after every iteration
+    ``MetropolisSampler.update_kernel`` (mcmc/base.py:142-161) moves the inverse-mass diagonal towards the across-chain
+    variance and the step size by dual averaging (tuning.py:15-41).  ``kind``: ``'mala'`` or ``'hmc'``.  The run carries
+    ``step_traj`` / ``imd_traj``: the kernel after each iteration."""
+    n = x0.shape[0]
+    out = RunRef(event_shape=tuple(x0.shape[1:]))
+    out.step_traj, out.imd_traj = [], []
+    x = x0.clone().detach()
+    imd = imd.clone()
+    da = DualAveragingRef(tau)
+    for _ in range(n_steps):
+        if kind == "mala":
+            x_prime, mask, calls, grads = mala_propose(x, target, tau, imd, draws, True, None)
+        else:
+            x_prime, mask, calls, grads = hmc_propose(x, target, tau, imd, n_leapfrog, draws, True, None)
+        x = x.detach()
+        x[mask] = x_prime[mask]                                                # :77
+        out.n_target_calls += calls
+        out.n_grad_calls += grads
+        out.n_accepted += int(torch.sum(mask))
+        out.n_attempted += n
+        out.observe(x, store)
+        if n > 1:
+            imd = tune_inv_mass(imd, x, imd_adjustment)                        # :150-155
+        error = da.target_rate - torch.mean(mask.float())                      # :157-158 (a float32 tensor, as there)
+        tau = da.step_error(error)                                             # :159-160
+        out.step_traj.append(tau)
+        out.imd_traj.append(imd.clone())
+    out.x = x
+    return out.finish(store)
+
+
+@torch.no_grad()
+def run_adaptive_imh(x0, target, flow, n_iterations: int, draws, store: bool = True) -> RunRef:
+    """``AdaptiveIMH.sample`` (nfmc/imh.py:102-181) with the refit switched off: both proposal densities are recomputed
+    every iteration (:133-134), the counters book ``2 n`` GRADIENT calls (:146, the reference's own bookkeeping), and one
+    extra scalar uniform decides whether a refit would happen (:151-153)."""
+    n = x0.shape[0]
+    out = RunRef(event_shape=tuple(x0.shape[1:]))
+    x = x0.clone()
+    for i in range(n_iterations):
+        z = draws.normal(n, flow.event_shape)                                  # flow.sample(n, no_grad=True) :128
+        x_prime, _ = flow.bijection.inverse(z)
+        log_alpha = mh_log_ratio(-target(x), -target(x_prime), flow.log_prob(x), flow.log_prob(x_prime))   # :130-135
+        log_u = draws.uniform(n).log().to(log_alpha)                           # :136
+        mask = torch.less(log_u, log_alpha)
+        x[mask] = x_prime[mask]                                                # :138
+        x = x.detach()
+        out.observe(x, store)                                                  # :144,150
+        out.n_grad_calls += 2 * n                                              # :146
+        out.n_accepted += int(torch.sum(mask))
+        out.n_attempted += n
+        draws.uniform_scalar()                                                 # u_prime :152
+    out.x = x
+    return out.finish(store)
 
 
 # ---------------------------------------------------------------------------------------------------------

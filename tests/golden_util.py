@@ -11,7 +11,10 @@ from oracle.samplers_ref import TapeDraws
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["mala_g0", "mala_fn", "hmc_g1", "hmc_rb", "jump_mala_g0", "jump_hmc_gm", "imh_rb", "neutra_hmc_fn", "mh_gm",
          "ess_fn", "jump_ess_gm", "jump_mala_g1_d100", "neutra_hmc_fn_d100",
-         "neutra_mh_gm", "tess_fn", "dlmc_gm", "dlmc_latent_gm"]
+         "neutra_mh_gm", "tess_fn", "dlmc_gm", "dlmc_latent_gm",
+         # round 2 (make_golden_r02.py): warm-up trajectories, unadjusted kernels, adaptive IMH, BASELINE config shapes
+         "mala_tune_g1", "hmc_tune_fn", "ula_g0", "uhmc_gm", "adaptive_imh_rb", "jump_hmc_g1_d100", "imh_rb_d100",
+         "jump_mala_gm_d1000"]
 
 
 def load_case(name):

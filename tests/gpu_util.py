@@ -33,3 +33,20 @@ def run_local_injected(sampler, x0, normals, uniforms, store=True):
     torch.cuda.synchronize()
     sx, sx2, cnt = ses.read_back()
     return (None if buf is None else buf.cpu()), ses, (sx, sx2, cnt)
+
+
+def oracle_flow_from_product(flow, device=None):
+    """The ORACLE RealNVP (oracle/realnvp_ref.py) carrying the product flow's parameters -- the reference the training
+    kernels are differentiated against (torch autograd through the oracle's own forward / inverse), on `device`."""
+    from oracle.realnvp_ref import FlowRef, RealNVPRef
+    bij = flow.bijection
+    M, H = bij.conditioner_shape()
+    ck = dict(n_layers=M, n_hidden=H) if bij.n_coupling > 0 else None
+    oflow = FlowRef(RealNVPRef(bij.event_shape, n_layers=bij.n_coupling, conditioner_kwargs=ck))
+    oflow.load_state_dict({k: v.detach().clone() for k, v in flow.state_dict().items()}, strict=True)
+    for l in oflow.bijection.layers:
+        if hasattr(l, "initialised"):
+            l.initialised.fill_(True)
+    oflow = oflow.to(device if device is not None else next(flow.parameters()).device).eval()
+    assert [tuple(p.shape) for p in oflow.bijection.parameters()] == [tuple(p.shape) for p in flow.bijection.parameters()]
+    return oflow

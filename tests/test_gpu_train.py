@@ -1,5 +1,5 @@
-"""B200: native flow training (csrc/train_kernels.cu, csrc/train_api.cu) against torch autograd over the same RealNVP
-arithmetic (nfmc_b200/flow_train.py: forward_autograd / inverse_autograd) and torch.optim.AdamW.
+"""B200: native flow training (csrc/train_kernels.cu, csrc/train_api.cu) against torch autograd through the ORACLE RealNVP
+(oracle/realnvp_ref.py: FlowRef.log_prob / bijection.inverse, carrying the same parameters) and torch.optim.AdamW.
 
 Reference call sites of the training these kernels replace: nfmc/jump.py:139-151,201, nfmc/imh.py:67-72,171-175,
 nfmc/neutra.py:84-91.  Tolerances: gradients agree to 2e-4 of the largest gradient entry (fp32 sums over the batch in a
@@ -53,15 +53,17 @@ def test_device_pack_matches_host_pack(d, Lc, H):
 @pytest.mark.parametrize("d,Lc,H", SHAPES)
 def test_nll_gradient_matches_autograd(d, Lc, H):
     from nfmc_b200 import _native as N
-    from nfmc_b200.flow_train import NativeTrainer, log_prob_autograd
+    from gpu_util import oracle_flow_from_product
+    from nfmc_b200.flow_train import NativeTrainer
     f = _flow(d, Lc, H, seed=d)
+    oflow = oracle_flow_from_product(f)
     dev = torch.device("cuda")
     n = 137
     x = torch.randn(n, d, device=dev) * 1.3 + 0.2
     rows = torch.randperm(n, device=dev)[:101]
-    params = list(f.bijection.parameters())
+    params = list(oflow.bijection.parameters())
     with torch.enable_grad():
-        loss = -log_prob_autograd(f, x[rows]).sum()
+        loss = -oflow.log_prob(x[rows]).sum()
         grads = torch.autograd.grad(loss, params)
     ref = torch.cat([g.reshape(-1) for g in grads])
     tr = NativeTrainer(f, dev, 0.05)
@@ -85,16 +87,20 @@ def test_nll_gradient_matches_autograd(d, Lc, H):
 def test_reverse_kl_gradient_matches_autograd(d, Lc, H, pot):
     from nfmc_b200 import _native as N
     from nfmc_b200 import potentials as P
-    from nfmc_b200.flow_train import NativeTrainer, inverse_autograd, target_log_prob_fn
+    from gpu_util import oracle_flow_from_product
+    from oracle.potentials_ref import make_potential_ref
+    from nfmc_b200.flow_train import NativeTrainer
     f = _flow(d, Lc, H, seed=3 * d, scale=0.1)
+    oflow = oracle_flow_from_product(f)
     dev = torch.device("cuda")
     n = 77
     z = torch.randn(n, d, device=dev)
     potential = P.make_potential(pot, (d,))
-    tlp = target_log_prob_fn(potential)
-    params = list(f.bijection.parameters())
+    upot = make_potential_ref(pot, (d,))
+    tlp = lambda x_: -upot(x_.cpu()).to(x_.device)      # the oracle potentials keep their parameters on the host
+    params = list(oflow.bijection.parameters())
     with torch.enable_grad():
-        x, ld = inverse_autograd(f.bijection, z)
+        x, ld = oflow.bijection.inverse(z)
         log_q = (-0.5 * z.square()).sum(dim=1) - 0.5 * d * math.log(2 * math.pi) - ld
         loss = (log_q - tlp(x)).sum()
         grads = torch.autograd.grad(loss, params)
@@ -114,14 +120,16 @@ def test_reverse_kl_gradient_matches_autograd(d, Lc, H, pot):
 def test_nll_gradient_large_batch_shared_accumulation():
     """Batches of many tiles per CTA accumulate in shared memory and flush once (train_api.cu: shared_grad)."""
     from nfmc_b200 import _native as N
-    from nfmc_b200.flow_train import NativeTrainer, log_prob_autograd
+    from gpu_util import oracle_flow_from_product
+    from nfmc_b200.flow_train import NativeTrainer
     d, n = 100, 70001
     f = _flow(d, 2, None, seed=5)
+    oflow = oracle_flow_from_product(f)
     dev = torch.device("cuda")
     x = torch.randn(n, d, device=dev)
-    params = list(f.bijection.parameters())
+    params = list(oflow.bijection.parameters())
     with torch.enable_grad():
-        loss = -log_prob_autograd(f, x).sum()
+        loss = -oflow.log_prob(x).sum()
         grads = torch.autograd.grad(loss, params)
     ref = torch.cat([g.reshape(-1) for g in grads])
     tr = NativeTrainer(f, dev, 0.05)
@@ -218,26 +226,28 @@ def test_training_kernels_edge_cases():
     """Single row, repeated row indices, minimal event size, accumulate = 1, Philox reproducibility of the reverse-KL draw."""
     from nfmc_b200 import _native as N
     from nfmc_b200 import potentials as P
-    from nfmc_b200.flow_train import NativeTrainer, log_prob_autograd
+    from gpu_util import oracle_flow_from_product
+    from nfmc_b200.flow_train import NativeTrainer
     dev = torch.device("cuda")
     for d, Lc, H in [(2, 1, 4), (3, 2, 5)]:
         f = _flow(d, Lc, H, seed=d)
+        oflow = oracle_flow_from_product(f)
         x = torch.randn(5, d, device=dev)
-        params = list(f.bijection.parameters())
+        params = list(oflow.bijection.parameters())
         tr = NativeTrainer(f, dev, 0.05)
         tr.pack()
         desc = tr.desc()
         # one row
         rows = torch.tensor([3], device=dev)
         with torch.enable_grad():
-            ref = torch.cat([g.reshape(-1) for g in torch.autograd.grad(-log_prob_autograd(f, x[rows]).sum(), params)])
+            ref = torch.cat([g.reshape(-1) for g in torch.autograd.grad(-oflow.log_prob(x[rows]).sum(), params)])
         N.check(N.lib().nfmc_flow_nll_grad(C.byref(desc), N.ptr(x), rows.data_ptr(), 1, N.ptr(tr.gblob), N.ptr(tr.loss), 0, tr.stream))
         tr.unpack(1.0)
         assert _rel(tr.gtheta, ref) < 5e-4
         # repeated indices, in two accumulating launches == one launch over all of them
         rows = torch.tensor([0, 0, 4, 1, 4, 4, 2], device=dev)
         with torch.enable_grad():
-            loss = -log_prob_autograd(f, x[rows]).sum()
+            loss = -oflow.log_prob(x[rows]).sum()
             ref = torch.cat([g.reshape(-1) for g in torch.autograd.grad(loss, params)])
         N.check(N.lib().nfmc_flow_nll_grad(C.byref(desc), N.ptr(x), rows.data_ptr(), 3, N.ptr(tr.gblob), N.ptr(tr.loss), 0, tr.stream))
         N.check(N.lib().nfmc_flow_nll_grad(C.byref(desc), N.ptr(x), rows[3:].contiguous().data_ptr(), 4, N.ptr(tr.gblob),

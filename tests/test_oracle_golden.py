@@ -36,7 +36,7 @@ def test_hmc(name):
     _check(g, run)
 
 
-@pytest.mark.parametrize("name", ["jump_mala_g0", "jump_mala_g1_d100"])
+@pytest.mark.parametrize("name", ["jump_mala_g0", "jump_mala_g1_d100", "jump_mala_gm_d1000"])
 def test_jump_mala(name):
     g = load_case(name)
     run = R.run_jump(torch.from_numpy(g["x0"]), oracle_target(g), oracle_flow(g), "mala", int(g["T"]), int(g["K"]),
@@ -44,15 +44,17 @@ def test_jump_mala(name):
     _check(g, run, jump=True)
 
 
-def test_jump_hmc():
-    g = load_case("jump_hmc_gm")
+@pytest.mark.parametrize("name", ["jump_hmc_gm", "jump_hmc_g1_d100"])
+def test_jump_hmc(name):
+    g = load_case(name)
     run = R.run_jump(torch.from_numpy(g["x0"]), oracle_target(g), oracle_flow(g), "hmc", int(g["T"]), int(g["K"]),
                      tape(g), float(g["step"]), torch.from_numpy(g["imd"]), n_leapfrog=int(g["L"]))
     _check(g, run, jump=True)
 
 
-def test_fixed_imh():
-    g = load_case("imh_rb")
+@pytest.mark.parametrize("name", ["imh_rb", "imh_rb_d100"])
+def test_fixed_imh(name):
+    g = load_case(name)
     run = R.run_fixed_imh(torch.from_numpy(g["x0"]), oracle_target(g), oracle_flow(g), int(g["T"]), tape(g))
     _check(g, run)
 
@@ -108,4 +110,36 @@ def test_dlmc(name):
     d = g["x0"].shape[1]
     run = R.run_dlmc(torch.from_numpy(g["x0"]), oracle_target(g), make_potential_ref(str(g["nll"]), (d,)), oracle_flow(g),
                      int(g["T"]), tape(g), step_size=float(g["step"]), latent_updates=bool(int(g["latent"])))
+    _check(g, run)
+
+
+# ---- round 2: warm-up trajectories, unadjusted kernels, adaptive IMH ----------------------------------------------------
+@pytest.mark.parametrize("name,kind", [("mala_tune_g1", "mala"), ("hmc_tune_fn", "hmc")])
+def test_warmup_trajectory(name, kind):
+    """mcmc/base.py:142-161 + tuning.py:15-41: the step size and inverse-mass diagonal after EVERY warm-up iteration."""
+    g = load_case(name)
+    run = R.run_tuned(torch.from_numpy(g["x0"]), oracle_target(g), kind, float(g["step"]), torch.from_numpy(g["imd"]),
+                      int(g["K"]), tape(g), n_leapfrog=int(g["L"]) if "L" in g else 20)
+    _check(g, run)
+    np.testing.assert_allclose(np.array(run.step_traj), g["step_traj"], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(torch.stack(run.imd_traj).numpy(), g["imd_traj"], rtol=0, atol=0)
+
+
+def test_ula():
+    g = load_case("ula_g0")
+    run = R.run_mala(torch.from_numpy(g["x0"]), oracle_target(g), float(g["step"]), torch.from_numpy(g["imd"]),
+                     int(g["K"]), tape(g), adjusted=False)
+    _check(g, run)
+
+
+def test_uhmc():
+    g = load_case("uhmc_gm")
+    run = R.run_hmc(torch.from_numpy(g["x0"]), oracle_target(g), float(g["step"]), torch.from_numpy(g["imd"]),
+                    int(g["L"]), int(g["K"]), tape(g), adjusted=False)
+    _check(g, run)
+
+
+def test_adaptive_imh():
+    g = load_case("adaptive_imh_rb")
+    run = R.run_adaptive_imh(torch.from_numpy(g["x0"]), oracle_target(g), oracle_flow(g), int(g["T"]), tape(g))
     _check(g, run)
