@@ -887,8 +887,9 @@ __device__ __forceinline__ void tc_epi1(uint32_t trow, int Hp, int g) {
 }
 
 // epilogue 2 of one tile: (u_a', u_b') = U + bl' -> alpha = 2^u_a' + m, beta = u_b'; affine update of this thread's 16
-// targets; log2-determinant accumulation (one lg2 per four scales; scales are >= m, so the product of four cannot
-// underflow, and it cannot overflow while every scale is below 1e9 -- otherwise the slow branch takes them one by one).
+// targets; log2-determinant accumulation from pairwise products of the scales (one lg2 per two scales; the inverse
+// direction needs the same products for its reciprocals: one rcp per two).  Scales are >= m = 1e-3, so a product cannot
+// underflow; it overflows only if both scales exceed 1e19, where the log-determinant is reported as +inf.
 template <bool INV>
 __device__ __forceinline__ void tc_epi2_chunk(const uint32_t (&v)[8], const float4 bA, const float4 bB, float* tgt, float& ld2) {
   const float a0 = fast_ex2(__uint_as_float(v[0]) + bA.x) + kMinScale, a1 = fast_ex2(__uint_as_float(v[2]) + bA.z) + kMinScale;
@@ -896,27 +897,19 @@ __device__ __forceinline__ void tc_epi2_chunk(const uint32_t (&v)[8], const floa
   const float ub0 = __uint_as_float(v[1]) + bA.y, ub1 = __uint_as_float(v[3]) + bA.w;
   const float ub2 = __uint_as_float(v[5]) + bB.y, ub3 = __uint_as_float(v[7]) + bB.w;
   const float p01 = a0 * a1, p23 = a2 * a3;
-  const bool tame = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)) < 1e9f;
   if (INV) {
-    float r0, r1, r2, r3;
-    if (tame) {
-      const float r01 = fast_rcp(p01), r23 = fast_rcp(p23);
-      r0 = r01 * a1; r1 = r01 * a0; r2 = r23 * a3; r3 = r23 * a2;
-    } else {
-      r0 = fast_rcp(a0); r1 = fast_rcp(a1); r2 = fast_rcp(a2); r3 = fast_rcp(a3);
-    }
-    tgt[0] = (tgt[0] - ub0) * r0;
-    tgt[1] = (tgt[1] - ub1) * r1;
-    tgt[2] = (tgt[2] - ub2) * r2;
-    tgt[3] = (tgt[3] - ub3) * r3;
+    const float r01 = fast_rcp(p01), r23 = fast_rcp(p23);
+    tgt[0] = (tgt[0] - ub0) * (r01 * a1);
+    tgt[1] = (tgt[1] - ub1) * (r01 * a0);
+    tgt[2] = (tgt[2] - ub2) * (r23 * a3);
+    tgt[3] = (tgt[3] - ub3) * (r23 * a2);
   } else {
     tgt[0] = fmaf(a0, tgt[0], ub0);
     tgt[1] = fmaf(a1, tgt[1], ub1);
     tgt[2] = fmaf(a2, tgt[2], ub2);
     tgt[3] = fmaf(a3, tgt[3], ub3);
   }
-  if (tame) ld2 += fast_lg2(p01 * p23);
-  else ld2 += (lg2_any(a0) + lg2_any(a1)) + (lg2_any(a2) + lg2_any(a3));
+  ld2 += lg2_any(p01) + lg2_any(p23);
 }
 template <bool INV>
 __device__ __forceinline__ void tc_epi2(uint32_t tcol_u, const float* bl, int N2p, int g, float (&tgt)[kTcOwn], float& ld2) {
