@@ -271,6 +271,11 @@ extern "C" int64_t nfmc_jump_tc_workspace_bytes(int32_t d, int64_t n) {
   return (int64_t)(2 * row + 3 * vec);
 }
 
+// tc_jump.cu: the whole jump as one kernel; -1 = not eligible (shape / alignment / shared memory)
+int nfmc_jump_step_tc_fused(const nfmc_potential* pot, const nfmc_realnvp_tc* flow, float* x, float* logq_cache, int recompute_logq,
+                            int64_t n, int adjusted, const nfmc_rng* rng, int64_t chain0, const nfmc_stats* stats,
+                            const nfmc_sink* sink, void* stream);
+
 extern "C" int nfmc_jump_step_tc(const nfmc_potential* pot, const nfmc_realnvp_tc* flow, float* x, float* logq_cache,
                                  int32_t recompute_logq, int64_t n, int32_t adjusted, const nfmc_rng* rng, int64_t chain0,
                                  const nfmc_stats* stats, const nfmc_sink* sink, void* workspace, int64_t workspace_bytes,
@@ -278,6 +283,11 @@ extern "C" int nfmc_jump_step_tc(const nfmc_potential* pot, const nfmc_realnvp_t
   if (int e = validate_pot(pot)) return e;
   if (!flow || !x || !rng || !workspace || n < 1) return set_error("jump_step_tc: bad arguments");
   if (pot->d != flow->d) return set_error("jump_step_tc: potential and flow event sizes differ");
+  const bool no_fused = getenv("NFMC_TC_NO_FUSED_JUMP") != nullptr;             // A-B tests: compose the jump from separate launches
+  if (!no_fused) {
+    const int rc = nfmc_jump_step_tc_fused(pot, flow, x, logq_cache, recompute_logq, n, adjusted, rng, chain0, stats, sink, stream);
+    if (rc >= 0) return rc;
+  }
   if (workspace_bytes < nfmc_jump_tc_workspace_bytes(pot->d, n)) return set_error("jump_step_tc: workspace too small");
   const int d = pot->d;
   const size_t row = ((size_t)n * d * sizeof(float) + 255) & ~size_t(255), vec = ((size_t)n * sizeof(float) + 255) & ~size_t(255);

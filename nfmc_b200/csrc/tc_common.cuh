@@ -585,6 +585,10 @@ struct TcEpiSync {
   __device__ __forceinline__ uint32_t bar(int which) const { return bars + which * 8; }
 };
 
+// slot k of a half that is not a chain coordinate: the constant-one columns of GEMM 1 sit at k = d/2 and d/2 + 1,
+// everything else is zero
+__device__ __forceinline__ float tc_pad_value(int k, int da) { return (k == da || k == da + 1) ? 1.f : 0.f; }
+
 // ---- chain tiles: global memory <-> registers, transposed through tensor memory ---------------------------------------
 // The compute layout gives thread (r, g) sixteen consecutive elements of each half of chain row r, so a warp-wide
 // global access in that layout touches 32 different rows with 16 bytes each: 32 L1 lines per instruction and half-used

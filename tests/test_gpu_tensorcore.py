@@ -126,3 +126,68 @@ def test_auto_dtype_routes_mid_width_conditioners_to_tensor_cores():
     zf, lf = f_fp32.bijection.forward(x)
     assert float((za - zf).abs().max()) < 2e-2 * max(1.0, float(zf.abs().max()))
     assert float((la - lf).abs().max()) < 5e-2 * max(1.0, float(lf.abs().max()))
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("d,Lc,H,pot,n", [(100, 2, 64, "gm", 3000), (100, 3, 32, "rb", 1111), (64, 4, 256, "fn", 700),
+                                          (100, 4, 256, "g1", 70000), (32, 2, 16, "g0", 257)])
+def test_tc_fused_jump_equals_composed_launches(monkeypatch, d, Lc, H, pot, n):
+    """The one-kernel tensor-core jump (csrc/tc_jump.cu) against the same jump composed from separate launches (TC log_prob,
+    Philox fill, TC inverse, CUDA-core accept kernel): same Philox numbers, same pass arithmetic -- so the proposals are
+    identical and the states differ only where the two evaluations of log alpha (different summation orders) straddle
+    log u.  Counters, moments, the log q cache and the sample sink follow."""
+    import ctypes as C
+    from gpu_util import product_flow_from_oracle, product_target
+    from nfmc_b200 import _native as N
+    oflow = make_flow((d,), n_layers=Lc, conditioner_kwargs=dict(n_layers=2, n_hidden=H), perturb=0.03, seed=7)
+    flow = product_flow_from_oracle(oflow, conditioner_dtype="bf16")
+    dev = torch.device("cuda")
+    tgt = product_target(pot, d)
+    pd, keep = tgt.descriptor(dev)
+    fd, keep2 = flow.bijection.tc_descriptor(dev)
+    torch.manual_seed(1)
+    x0 = (0.6 * torch.randn(n, d)).to(dev)
+    res = {}
+    for mode in ("fused", "composed"):
+        if mode == "composed":
+            monkeypatch.setenv("NFMC_TC_NO_FUSED_JUMP", "1")
+        else:
+            monkeypatch.delenv("NFMC_TC_NO_FUSED_JUMP", raising=False)
+        out = {}
+        for use_cache in (False, True):
+            x = x0.clone()
+            mom = torch.zeros(2 * d, device=dev, dtype=torch.float64)
+            cnt = torch.zeros(8, device=dev, dtype=torch.int64)
+            st = N.StatsDesc(mom.data_ptr(), mom.data_ptr() + 8 * d, cnt.data_ptr())
+            sink_buf = torch.full((n, d), float("nan"), device=dev)
+            sink = N.SinkDesc(sink_buf.data_ptr(), 0, 1)
+            cache = flow.log_prob(x).contiguous() if use_cache else None
+            nb = N.lib().nfmc_jump_tc_workspace_bytes(d, n)
+            ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+            # with an odd number of couplings the composed path treats the Philox fill as the LOGICAL latent and the fused
+            # kernel (like the CUDA-core kernels, flow_args.cuh: draw_base) as the physical one -- the same distribution, but
+            # not the same numbers: inject the draws there
+            gen = torch.Generator().manual_seed(5)
+            for step in range(2):
+                zin = torch.randn(n, d, generator=gen).to(dev) if Lc % 2 else None
+                uin = torch.rand(n, generator=gen).to(dev) if Lc % 2 else None
+                rng = N.rng_desc(1234, step, zin, uin)
+                N.check(N.lib().nfmc_jump_step_tc(C.byref(pd), C.byref(fd), N.ptr(x), None if cache is None else N.ptr(cache), 0, n, 1,
+                                                  C.byref(rng), 17, C.byref(st), C.byref(sink), N.ptr(ws), nb, N.stream_ptr(dev)))
+            torch.cuda.synchronize()
+            out[use_cache] = (x.cpu(), mom.cpu(), cnt.cpu(), sink_buf.cpu(), None if cache is None else cache.cpu())
+        res[mode] = out
+    for use_cache in (False, True):
+        xf, mf, cf, sf, qf = res["fused"][use_cache]
+        xc, mc, cc, sc, qc = res["composed"][use_cache]
+        same = (xf == xc).all(dim=1)
+        assert float(same.float().mean()) > 0.995, float(same.float().mean())          # decisions agree except near-ties
+        assert bool(torch.isfinite(xf).all())
+        assert torch.equal(sf, xf)                                                       # the sink holds the post-jump state
+        assert int(cf[1]) == 2 * n and abs(int(cf[0]) - int(cc[0])) <= int((~same).sum()) * 2
+        assert int(cf[0]) < 2 * n and (int(cf[0]) > 0) == (int(cc[0]) > 0)
+        # moments: identical up to the rows whose decision differs
+        tol = 1e-6 * n + 2.0 * float((~same).sum()) * float(xc.abs().max()) ** 2 + 1e-3
+        assert float((mf - mc).abs().max()) <= tol * max(1.0, float(xc.abs().max())), float((mf - mc).abs().max())
+        if use_cache:
+            assert float((qf[same] - qc[same]).abs().max()) < 1e-3 * (1 + float(qc.abs().max()))

@@ -50,6 +50,16 @@ def run(name, strategy, pot, d, n, T, K=None, flow_spec="realnvp", adapt=False, 
 
 
 if __name__ == "__main__":
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None, help="run only the configs whose name contains this string")
+    only = ap.parse_args().only
+    _run = run
+
+    def run(name, *a, **k):      # noqa: F811
+        if only is None or only in name:
+            _run(name, *a, **k)
+
     wide = 'realnvp%{"n_layers": 4, "conditioner_kwargs": {"n_layers": 2, "n_hidden": 256}}'
     run("C1 README jump_mala d=25 n=100", "jump_mala", "g0", 25, 100, 200, K=100)
     run("C2 jump_hmc d=100 n=65536", "jump_hmc", "g1", 100, 65536, 20, K=5)
@@ -67,3 +77,4 @@ if __name__ == "__main__":
     run("dlmc mixture d=100 n=2^17 (refit every iteration)", "dlmc", "gm", 100, 1 << 17, 4)
     run("wide-flow jump_mala d=100 n=2^20 H=256 Lc=4 (tcgen05)", "jump_mala", "g0", 100, 1 << 20, 5, K=100, flow_spec=wide)
     run("wide-flow imh d=100 n=2^20 H=256 Lc=4 (tcgen05)", "imh", "g0", 100, 1 << 20, 10, flow_spec=wide)
+    run("wide-flow jump_mala K=1 (jump-dominated) d=100 n=2^20 H=256 Lc=4 (tcgen05)", "jump_mala", "g0", 100, 1 << 20, 10, K=1, flow_spec=wide)
