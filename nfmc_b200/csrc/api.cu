@@ -57,19 +57,24 @@ constexpr int kPipeStreams = 4;
 struct Pipe {
   cudaStream_t streams[kPipeStreams] = {};
   cudaEvent_t fork = nullptr, join[kPipeStreams] = {};
-  int device = -1;
+  bool ready = false;
 };
-thread_local Pipe g_pipe;
-int ensure_pipe() {
+constexpr int kMaxDevices = 64;
+thread_local Pipe g_pipes[kMaxDevices];          // one set of side streams per device (and host thread), created once
+int ensure_pipe(Pipe*& out) {
   int dev = 0;
   if (int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return e;
-  if (g_pipe.device == dev) return 0;
-  for (int i = 0; i < kPipeStreams; ++i) {
-    if (int e = check_cuda(cudaStreamCreateWithFlags(&g_pipe.streams[i], cudaStreamNonBlocking), "stream create")) return e;
-    if (int e = check_cuda(cudaEventCreateWithFlags(&g_pipe.join[i], cudaEventDisableTiming), "event create")) return e;
+  if (dev < 0 || dev >= kMaxDevices) return set_error("jump_sample: device ordinal out of range");
+  Pipe& p = g_pipes[dev];
+  if (!p.ready) {
+    for (int i = 0; i < kPipeStreams; ++i) {
+      if (int e = check_cuda(cudaStreamCreateWithFlags(&p.streams[i], cudaStreamNonBlocking), "stream create")) return e;
+      if (int e = check_cuda(cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming), "event create")) return e;
+    }
+    if (int e = check_cuda(cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming), "event create")) return e;
+    p.ready = true;
   }
-  if (int e = check_cuda(cudaEventCreateWithFlags(&g_pipe.fork, cudaEventDisableTiming), "event create")) return e;
-  g_pipe.device = dev;
+  out = &p;
   return 0;
 }
 
@@ -111,44 +116,48 @@ int plan_slabs(int d, int64_t n, bool ramp_wanted, std::vector<int64_t>& sizes) 
   return 0;
 }
 
-// enqueue the whole run; `s` is forked into the pipe streams and joined again (no host synchronisation here)
+// enqueue the whole run; `s` is forked into the pipe streams and joined again (no host synchronisation here).  Whatever
+// happens in between -- including an error half-way through the slabs -- the side streams are joined back into `s` before
+// returning, so the caller's later work on `s` never races with slabs still in flight.
 int run_pipeline(const nfmc_potential& pot, const nfmc_realnvp& flow, float* x_dev, float* x_host, int64_t n, const RunSpec& R,
                  const nfmc_stats* st_local, const nfmc_stats* st_jump, float* logq_scratch, cudaStream_t s) {
-  if (int e = ensure_pipe()) return e;
+  Pipe* pipe = nullptr;
+  if (int e = ensure_pipe(pipe)) return e;
   const int d = pot.d;
   std::vector<int64_t> sizes;
   if (int e = plan_slabs(d, n, x_host != nullptr, sizes)) return e;
-  cudaEventRecord(g_pipe.fork, s);
-  for (int i = 0; i < kPipeStreams; ++i) cudaStreamWaitEvent(g_pipe.streams[i], g_pipe.fork, 0);
+  if (int e = check_cuda(cudaEventRecord(pipe->fork, s), "fork record")) return e;
+  for (int i = 0; i < kPipeStreams; ++i)
+    if (int e = check_cuda(cudaStreamWaitEvent(pipe->streams[i], pipe->fork, 0), "fork wait")) return e;
+  int err = 0;
   int64_t first = 0;
-  for (size_t k = 0; k < sizes.size(); first += sizes[k], ++k) {
+  for (size_t k = 0; k < sizes.size() && !err; first += sizes[k], ++k) {
     const int64_t cnt = sizes[k];
-    cudaStream_t ss = g_pipe.streams[k % kPipeStreams];
+    cudaStream_t ss = pipe->streams[k % kPipeStreams];
     float* xs = x_dev + first * d;
-    if (x_host)
-      if (int e = check_cuda(cudaMemcpyAsync(xs, x_host + first * d, (size_t)cnt * d * sizeof(float), cudaMemcpyHostToDevice, ss), "H2D x")) return e;
-    for (int it = 0; it < R.n_outer; ++it) {
+    if (x_host) err = check_cuda(cudaMemcpyAsync(xs, x_host + first * d, (size_t)cnt * d * sizeof(float), cudaMemcpyHostToDevice, ss), "H2D x");
+    for (int it = 0; it < R.n_outer && !err; ++it) {
       nfmc_rng r_local{R.seed, R.local_step0 + (uint64_t)it * (uint64_t)R.n_inner, nullptr, nullptr};
       nfmc_rng r_jump{R.seed, R.jump_step0 + (uint64_t)it, nullptr, nullptr};
-      int e;
       if (R.inner_kind == 0)
-        e = nfmc_mala_steps(&pot, xs, cnt, R.n_inner, R.step_size, R.inv_mass_diag, R.local_adjusted, &r_local, R.chain0 + first, st_local, nullptr, ss);
+        err = nfmc_mala_steps(&pot, xs, cnt, R.n_inner, R.step_size, R.inv_mass_diag, R.local_adjusted, &r_local, R.chain0 + first, st_local, nullptr, ss);
       else if (R.inner_kind == 1)
-        e = nfmc_hmc_steps(&pot, xs, cnt, R.n_inner, R.step_size, R.n_leapfrog, R.inv_mass_diag, R.local_adjusted, &r_local, R.chain0 + first, st_local, nullptr, ss);
+        err = nfmc_hmc_steps(&pot, xs, cnt, R.n_inner, R.step_size, R.n_leapfrog, R.inv_mass_diag, R.local_adjusted, &r_local, R.chain0 + first, st_local, nullptr, ss);
       else
-        e = nfmc_mh_steps(&pot, xs, cnt, R.n_inner, R.inv_mass_diag, R.local_adjusted, &r_local, R.chain0 + first, st_local, nullptr, ss);
-      if (e) return e;
-      if ((e = nfmc_jump_step2(&pot, &flow, xs, logq_scratch ? logq_scratch + first : nullptr, cnt, R.jump_adjusted, &r_jump,
-                               R.chain0 + first, st_jump, nullptr, ss))) return e;
+        err = nfmc_mh_steps(&pot, xs, cnt, R.n_inner, R.inv_mass_diag, R.local_adjusted, &r_local, R.chain0 + first, st_local, nullptr, ss);
+      if (!err)
+        err = nfmc_jump_step2(&pot, &flow, xs, logq_scratch ? logq_scratch + first : nullptr, cnt, R.jump_adjusted, &r_jump,
+                              R.chain0 + first, st_jump, nullptr, ss);
     }
-    if (x_host)
-      if (int e = check_cuda(cudaMemcpyAsync(x_host + first * d, xs, (size_t)cnt * d * sizeof(float), cudaMemcpyDeviceToHost, ss), "D2H x")) return e;
+    if (x_host && !err)
+      err = check_cuda(cudaMemcpyAsync(x_host + first * d, xs, (size_t)cnt * d * sizeof(float), cudaMemcpyDeviceToHost, ss), "D2H x");
   }
-  for (int i = 0; i < kPipeStreams; ++i) {
-    cudaEventRecord(g_pipe.join[i], g_pipe.streams[i]);
-    cudaStreamWaitEvent(s, g_pipe.join[i], 0);
+  for (int i = 0; i < kPipeStreams; ++i) {        // always join, also on error
+    const int e1 = check_cuda(cudaEventRecord(pipe->join[i], pipe->streams[i]), "join record");
+    const int e2 = e1 ? e1 : check_cuda(cudaStreamWaitEvent(s, pipe->join[i], 0), "join wait");
+    if (!err) err = e2;
   }
-  return 0;
+  return err;
 }
 }  // namespace
 

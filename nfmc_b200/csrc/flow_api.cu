@@ -50,6 +50,8 @@ extern "C" int nfmc_flow_sample(const nfmc_realnvp* flow, const nfmc_rng* rng, i
   return 0;
 }
 
+namespace nfmc { int validate_injected(const nfmc_rng* rng, int adjusted, const char* who); }
+
 static int launch_jump(const nfmc_potential* pot, const nfmc_realnvp* flow, float* x, float* logq_x, int64_t n,
                        int32_t n_steps, int32_t recompute_logq, int32_t adjusted, const nfmc_rng* rng, int64_t chain0,
                        const nfmc_stats* stats, const nfmc_sink* sink, void* stream) {
@@ -57,6 +59,7 @@ static int launch_jump(const nfmc_potential* pot, const nfmc_realnvp* flow, floa
   if (int e = validate_flow(flow)) return e;
   if (pot->d != flow->d) return set_error("jump: potential and flow event sizes differ");
   if (!x || n < 1 || n_steps < 0) return set_error("jump: bad x/n/n_steps");
+  if (int e = validate_injected(rng, adjusted, "jump")) return e;
   if (n_steps == 0) return 0;
   Layout L;
   if (!layout_for_dim(pot->d, L)) return set_error("jump: unsupported event size");
@@ -108,6 +111,7 @@ extern "C" int nfmc_jump_step2(const nfmc_potential* pot, const nfmc_realnvp* fl
   if (int e = validate_flow(flow)) return e;
   if (pot->d != flow->d) return set_error("jump_step2: potential and flow event sizes differ");
   if (!x || n < 1 || (adjusted && !logq_scratch)) return set_error("jump_step2: bad x / n / logq_scratch");
+  if (int e = validate_injected(rng, adjusted, "jump_step2")) return e;
   if (adjusted)
     if (int e = flow_pass(flow, PASS_LOGPROB, x, nullptr, logq_scratch, n, stream)) return e;       // jump.py:218
   return jump_second_half(pot, flow, x, logq_scratch, n, adjusted, rng, chain0, stats, sink, stream);
@@ -125,6 +129,7 @@ extern "C" int nfmc_imh_steps(const nfmc_potential* pot, const nfmc_realnvp* flo
   if (int e = validate_flow(flow)) return e;
   if (pot->d != flow->d) return set_error("imh_steps: potential and flow event sizes differ");
   if (!x || n < 1 || n_steps < 0) return set_error("imh_steps: bad x/n/n_steps");
+  if (int e = validate_injected(rng, 1, "imh_steps")) return e;
   Layout L;
   if (log_q_x && layout_for_dim(pot->d, L) && n * L.gs / kThreads >= 6ll * sm_count()) {
     for (int32_t i = 0; i < n_steps; ++i) {
@@ -283,6 +288,7 @@ extern "C" int nfmc_jump_step_tc(const nfmc_potential* pot, const nfmc_realnvp_t
   if (int e = validate_pot(pot)) return e;
   if (!flow || !x || !rng || !workspace || n < 1) return set_error("jump_step_tc: bad arguments");
   if (pot->d != flow->d) return set_error("jump_step_tc: potential and flow event sizes differ");
+  if (int e = validate_injected(rng, adjusted, "jump_step_tc")) return e;
   const bool no_fused = getenv("NFMC_TC_NO_FUSED_JUMP") != nullptr;             // A-B tests: compose the jump from separate launches
   if (!no_fused) {
     const int rc = nfmc_jump_step_tc_fused(pot, flow, x, logq_cache, recompute_logq, n, adjusted, rng, chain0, stats, sink, stream);

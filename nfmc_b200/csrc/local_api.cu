@@ -57,6 +57,17 @@ static size_t local_smem_bytes(int d, bool with_mass, size_t per_dim, int E) {
   return b;
 }
 
+// Injected random numbers: an ADJUSTED kernel consumes normals [steps, n, d] and uniforms [steps, n] together -- with only
+// the normals injected the accept uniform would silently be 0 (always accept), with only the uniforms the proposal noise
+// would come from Philox against the caller's intent.  Unadjusted kernels take normals alone.
+int validate_injected(const nfmc_rng* rng, int adjusted, const char* who) {
+  if (!rng) return 0;
+  const bool zn = rng->normals != nullptr, un = rng->uniforms != nullptr;
+  if (adjusted ? (zn != un) : (un && !zn))
+    return set_error(std::string(who) + ": inject both normals [steps,n,d] and uniforms [steps,n], or neither");
+  return 0;
+}
+
 static int fill_chain_args(ChainArgs& C, const nfmc_potential* pot, float* x, int64_t n, int32_t n_steps,
                            const nfmc_rng* rng, int64_t chain0, const nfmc_stats* stats, const nfmc_sink* sink,
                            const Layout& L) {
@@ -81,6 +92,7 @@ extern "C" int nfmc_mala_steps(const nfmc_potential* pot, float* x, int64_t n, i
                                const nfmc_stats* stats, const nfmc_sink* sink, void* stream) {
   if (int e = validate_pot(pot)) return e;
   if (!x || n < 1 || n_steps < 0) return set_error("mala_steps: bad x/n/n_steps");
+  if (int e = validate_injected(rng, adjusted, "mala_steps")) return e;
   if (!(step_size > 0.f)) return set_error("mala_steps: step_size must be positive");
   if (n_steps == 0) return 0;
   Layout L;
@@ -101,6 +113,7 @@ extern "C" int nfmc_mh_steps(const nfmc_potential* pot, float* x, int64_t n, int
                              const nfmc_sink* sink, void* stream) {
   if (int e = validate_pot(pot)) return e;
   if (!x || n < 1 || n_steps < 0) return set_error("mh_steps: bad x/n/n_steps");
+  if (int e = validate_injected(rng, adjusted, "mh_steps")) return e;
   if (n_steps == 0) return 0;
   Layout L;
   if (!layout_for_dim(pot->d, L)) return set_error("mh_steps: unsupported event size");
@@ -139,6 +152,7 @@ extern "C" int nfmc_hmc_steps(const nfmc_potential* pot, float* x, int64_t n, in
                               int64_t chain0, const nfmc_stats* stats, const nfmc_sink* sink, void* stream) {
   if (int e = validate_pot(pot)) return e;
   if (!x || n < 1 || n_steps < 0 || n_leapfrog < 0) return set_error("hmc_steps: bad x/n/n_steps/n_leapfrog");
+  if (int e = validate_injected(rng, adjusted, "hmc_steps")) return e;
   if (n_steps == 0) return 0;
   Layout L;
   if (!layout_for_dim(pot->d, L)) return set_error("hmc_steps: unsupported event size");

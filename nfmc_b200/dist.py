@@ -65,13 +65,26 @@ def sample_sharded(sampler, x0_global: torch.Tensor, show_progress: bool = False
     sampler.chain0 = first
     if hasattr(sampler, "inner_sampler"):
         sampler.inner_sampler.chain0 = first
-    if sampler.seed is None:
+    # Every rank must use the same Philox seed (chains are keyed by global index).  A seed drawn here is valid for THIS call
+    # only: each call restarts its step counters at 0, so keeping it would replay the same noise on the next call
+    # (warm-up then sampling, or a loop continuing from last_sample).  A seed the user fixed is advanced per call by
+    # Sampler.session_seed().
+    targets = [sampler] + ([sampler.inner_sampler] if hasattr(sampler, "inner_sampler") else [])
+    drawn = sampler.seed is None
+    if drawn:
         seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64)
         if world > 1:
             t = seed.cuda() if dist.get_backend(group) == "nccl" else seed
             dist.broadcast(t, src=0, group=group)
             seed = t.cpu()
-        sampler.seed = int(seed)
-    out = sampler.sample(x0_global[first:first + count], show_progress=show_progress,
-                         time_limit_seconds=time_limit_seconds, **inject)
+        saved = [(s_, s_.seed, getattr(s_, "_n_sessions", 0)) for s_ in targets]
+        for s_ in targets:
+            s_.seed, s_._n_sessions = int(seed), 0
+    try:
+        out = sampler.sample(x0_global[first:first + count], show_progress=show_progress,
+                             time_limit_seconds=time_limit_seconds, **inject)
+    finally:
+        if drawn:
+            for s_, old_seed, old_n in saved:
+                s_.seed, s_._n_sessions = old_seed, old_n
     return pool_statistics(out, group)

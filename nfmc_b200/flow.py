@@ -184,13 +184,14 @@ class RealNVP(_Layer):
         n = xd.shape[0]
         y = torch.empty_like(xd)
         ld = torch.empty(n, device=dev, dtype=torch.float32)
-        if self.uses_tensor_cores():
-            desc, keep = self.tc_descriptor(dev)
-            mode = 0 if fn_name == "nfmc_realnvp_forward" else 1
-            N.check(N.lib().nfmc_flow_tc_pass(C.byref(desc), mode, N.ptr(xd), N.ptr(y), N.ptr(ld), n, N.stream_ptr(dev)))
-        else:
-            desc, keep = self.descriptor(dev)
-            N.check(getattr(N.lib(), fn_name)(C.byref(desc), N.ptr(xd), N.ptr(y), N.ptr(ld), n, N.stream_ptr(dev)))
+        with torch.cuda.device(dev):           # the C entry points launch on the current device
+            if self.uses_tensor_cores():
+                desc, keep = self.tc_descriptor(dev)
+                mode = 0 if fn_name == "nfmc_realnvp_forward" else 1
+                N.check(N.lib().nfmc_flow_tc_pass(C.byref(desc), mode, N.ptr(xd), N.ptr(y), N.ptr(ld), n, N.stream_ptr(dev)))
+            else:
+                desc, keep = self.descriptor(dev)
+                N.check(getattr(N.lib(), fn_name)(C.byref(desc), N.ptr(xd), N.ptr(y), N.ptr(ld), n, N.stream_ptr(dev)))
         return y.reshape(*batch, *self.event_shape), ld.reshape(batch)
 
     @torch.no_grad()
@@ -233,12 +234,13 @@ class Flow(nn.Module):
         xd = N.dev_f32(x, dev).reshape(-1, bij.n_dim)
         n = xd.shape[0]
         out = torch.empty(n, device=dev, dtype=torch.float32)
-        if bij.uses_tensor_cores():
-            desc, keep = bij.tc_descriptor(dev)
-            N.check(N.lib().nfmc_flow_tc_pass(C.byref(desc), 2, N.ptr(xd), None, N.ptr(out), n, N.stream_ptr(dev)))
-        else:
-            desc, keep = bij.descriptor(dev)
-            N.check(N.lib().nfmc_flow_log_prob(C.byref(desc), N.ptr(xd), N.ptr(out), n, N.stream_ptr(dev)))
+        with torch.cuda.device(dev):           # the C entry points launch on the current device
+            if bij.uses_tensor_cores():
+                desc, keep = bij.tc_descriptor(dev)
+                N.check(N.lib().nfmc_flow_tc_pass(C.byref(desc), 2, N.ptr(xd), None, N.ptr(out), n, N.stream_ptr(dev)))
+            else:
+                desc, keep = bij.descriptor(dev)
+                N.check(N.lib().nfmc_flow_log_prob(C.byref(desc), N.ptr(xd), N.ptr(out), n, N.stream_ptr(dev)))
         return out.reshape(batch)
 
     @torch.no_grad()
@@ -258,7 +260,8 @@ class Flow(nn.Module):
             seed = int(torch.randint(0, 2 ** 62, (), dtype=torch.int64))
         rng = N.rng_desc(seed, 0, zd, None)
         desc, keep = bij.descriptor(dev)
-        N.check(N.lib().nfmc_flow_sample(C.byref(desc), C.byref(rng), 0, N.ptr(x), N.ptr(lq), n, N.stream_ptr(dev)))
+        with torch.cuda.device(dev):
+            N.check(N.lib().nfmc_flow_sample(C.byref(desc), C.byref(rng), 0, N.ptr(x), N.ptr(lq), n, N.stream_ptr(dev)))
         x = x.reshape(*sample_shape, *bij.event_shape)
         if return_log_prob:
             return x, lq.reshape(tuple(sample_shape))

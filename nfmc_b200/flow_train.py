@@ -279,6 +279,15 @@ def _init_actnorms(flow, x_first: torch.Tensor):
 def _fit_native(flow, dev, x_train, x_val, n_epochs, lr, batch_size, shuffle, keep_best_weights, early_stopping,
                 early_stopping_threshold, time_limit_seconds):
     n = len(x_train)
+    if _world() > 1:
+        # every rank issues one gradient all-reduce per minibatch: agree on the training-set size first (shard remainders
+        # and the train/val split can leave the ranks a few rows apart), otherwise the collectives would not pair up
+        t = torch.tensor([n], device=dev, dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        n = int(t)
+        if n < 1:
+            raise ValueError("flow.fit: a rank has no training rows")
+        x_train = x_train[:n]
     _init_actnorms(flow, x_train[:batch_size])
     tr = NativeTrainer(flow, dev, lr)
     n_batches = (n + batch_size - 1) // batch_size

@@ -66,7 +66,8 @@ class Potential:
         u = torch.empty(n, device=dev, dtype=torch.float32)
         g = torch.empty_like(xd) if need_grad else None
         desc, keep = self.descriptor(dev)
-        N.check(N.lib().nfmc_potential_eval(C.byref(desc), N.ptr(xd), N.ptr(u), N.ptr(g), n, N.stream_ptr(dev)))
+        with torch.cuda.device(dev):           # the C entry point launches on the current device
+            N.check(N.lib().nfmc_potential_eval(C.byref(desc), N.ptr(xd), N.ptr(u), N.ptr(g), n, N.stream_ptr(dev)))
         return u, (None if g is None else g.reshape(x.shape))
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:

@@ -104,6 +104,8 @@ class MetropolisKernel(MCMCKernel):
             self.da = DualAveraging(self.step_size, self.da_params)
 
     def has_unit_mass(self) -> bool:
+        if self.inv_mass_diag.is_cuda:           # device-resident during warm-up: never the untouched default, and no sync
+            return False
         return bool(torch.all(self.inv_mass_diag == 1.0))
 
 

@@ -104,6 +104,42 @@ class DeviceSession:
         return m[: self.d], m[self.d:], [int(v) for v in c]
 
 
+class _DeviceTuner:
+    """Warm-up adaptation with the state on the device (reference: MetropolisSampler.update_kernel, mcmc/base.py:142-161;
+    DualAveraging, tuning.py:15-41).  Per warm-up iteration: ``nfmc_chain_sums`` (sum x, sum x^2 per coordinate over this
+    rank's chains, the accepted count, n), one all-reduce of those 2d+2 doubles when several ranks sample together
+    (every rank ends up with the same inverse mass and the same step size), ``nfmc_tune_inv_mass`` (unbiased
+    variance -> EMA into the device-resident inverse-mass diagonal) and one 16-byte read for the scalar dual-averaging
+    update, which stays on the host as in the reference."""
+
+    def __init__(self, ses: "DeviceSession", kernel: MetropolisKernel):
+        self.sums = torch.empty(2 * ses.d + 2, dtype=torch.float64, device=ses.device)
+        self.imd = N.dev_f32(kernel.inv_mass_diag, ses.device).clone()
+        self.prev_acc = 0.0
+
+    def update(self, ses: "DeviceSession", kernel: MetropolisKernel, params: MetropolisParameters, n_steps: int):
+        import numpy as np
+        import torch.distributed as dist
+        d = ses.d
+        N.check(N.lib().nfmc_chain_sums(N.ptr(ses.x), ses.n, d, N.ptr(self.sums), C.c_void_p(ses.counts.data_ptr()), ses.stream))
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.sums)
+        if params.tune_inv_mass_diag:
+            N.check(N.lib().nfmc_tune_inv_mass(N.ptr(self.sums), d, float(params.imd_adjustment), N.ptr(self.imd), ses.stream))
+            kernel.inv_mass_diag = self.imd                  # stays on the device until the warm-up ends
+        if params.tune_step_size and params.adjustment:
+            acc, n_total = (float(v) for v in self.sums[2 * d:].cpu())
+            # the reference forms mean(mask.float()) and the error in fp32 (base.py:157-158)
+            rate = np.float32(acc - self.prev_acc) / np.float32(n_total * n_steps)
+            self.prev_acc = acc
+            kernel.da.step(float(np.float32(kernel.da_params.target_acceptance_rate) - rate))
+            kernel.step_size = kernel.da.value
+
+    def finish(self, kernel: MetropolisKernel):
+        if kernel.inv_mass_diag is self.imd:
+            kernel.inv_mass_diag = self.imd.cpu()             # the records keep the reference's host tensor
+
+
 def _imd_device(kernel: MetropolisKernel, device) -> Optional[torch.Tensor]:
     return None if kernel.has_unit_mass() else N.dev_f32(kernel.inv_mass_diag, device)
 
@@ -112,6 +148,21 @@ def _rows_kept(seen0: int, k: int, thinning: int) -> int:
     first = (seen0 + thinning - 1) // thinning
     last = (seen0 + k + thinning - 1) // thinning
     return last - first
+
+
+def _device_scoped(fn):
+    """Run a public sampler method with its device current: the C entry points size grids, create their side streams
+    and launch on the CURRENT device, while tensors and the torch stream live on the sampler's device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, x0, *args, **kwargs):
+        dev = N.require_cuda(self.device if self.device is not None else (x0.device if torch.is_tensor(x0) and x0.is_cuda else None))
+        with torch.cuda.device(dev):
+            return fn(self, x0, *args, **kwargs)
+
+    wrapper._device_scoped = True
+    return wrapper
 
 
 class Sampler:
@@ -124,6 +175,24 @@ class Sampler:
         self.seed: Optional[int] = None      # fixed Philox seed (None: drawn from torch's global generator per call)
         self.chain0: int = 0                 # global index of this process's first chain (multi-GPU sharding)
         self.device = None
+        self._n_sessions = 0
+
+    def __init_subclass__(cls, **kwargs):
+        super().__init_subclass__(**kwargs)
+        for name in ("sample", "warmup"):
+            fn = cls.__dict__.get(name)
+            if fn is not None and not getattr(fn, "_device_scoped", False):
+                setattr(cls, name, _device_scoped(fn))
+
+    def session_seed(self) -> Optional[int]:
+        """Philox seed of the next ``sample()`` / ``warmup()`` call.  Every call starts its step counters at 0, so a fixed
+        ``self.seed`` is advanced by the call index (a run of warm-up then sampling, or a loop continuing from
+        ``last_sample``, must not replay the same noise); ``None`` lets the session draw a fresh seed."""
+        if self.seed is None:
+            return None
+        k = self._n_sessions
+        self._n_sessions += 1
+        return (int(self.seed) + k * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF
 
     @property
     def name(self):
@@ -174,47 +243,42 @@ class MetropolisSampler(Sampler):
         out.statistics.update_counters(n_target_calls=calls * n_steps, n_target_gradient_calls=grads * n_steps)
         return buf
 
-    def update_kernel_from_device(self, ses: DeviceSession, acc_rate: float):
-        """Warm-up adaptation (reference: MetropolisSampler.update_kernel, mcmc/base.py:142-161)."""
-        p: MetropolisParameters = self.params
-        k: MetropolisKernel = self.kernel
-        if ses.n > 1 and p.tune_inv_mass_diag:
-            var = torch.var(ses.x, dim=0).cpu()            # unbiased, across chains, per dimension
-            k.inv_mass_diag = p.imd_adjustment * var + (1 - p.imd_adjustment) * k.inv_mass_diag
-        if p.tune_step_size and p.adjustment:
-            k.da.step(k.da_params.target_acceptance_rate - acc_rate)
-            k.step_size = k.da.value
-
-    def sample(self, x0: torch.Tensor, show_progress: bool = True, time_limit_seconds=None) -> MCMCOutput:
+    def sample(self, x0: torch.Tensor, show_progress: bool = True, time_limit_seconds=None, normals=None, uniforms=None) -> MCMCOutput:
+        """``normals [T,n,d]`` / ``uniforms [T,n]`` optionally inject the random numbers (parity tests)."""
         event_shape = tuple(x0.shape[1:])
         out = MCMCOutput(event_shape, store_samples=self.params.store_samples)
-        ses = DeviceSession(x0, event_shape, self.device, self.seed, self.chain0)
+        ses = DeviceSession(x0, event_shape, self.device, self.session_seed(), self.chain0)
         self.begin_stage(ses)
         T = int(self.params.n_iterations)
-        tuning = bool(self.params.tuning)
+        tuning = bool(self.params.tuning) and self.tunable
         chunk = 1 if (tuning or time_limit_seconds is not None or show_progress) else min(T, self.max_fused_steps)
         done = 0
-        label = f'{self.name} (tuning)' if tuning else self.name
+        label = f'{self.name} (tuning)' if self.params.tuning else self.name
         bar = _progress(range(0, T, max(chunk, 1)), label, show_progress)
-        prev_acc = 0
+        tuner = _DeviceTuner(ses, self.kernel) if tuning else None
         for start in bar:
             if time_limit_seconds is not None and out.statistics.elapsed_time_seconds > time_limit_seconds:
                 break
             k = min(chunk, T - start)
+            nz = None if normals is None else N.dev_f32(normals[start:start + k], ses.device)
+            un = None if uniforms is None else N.dev_f32(uniforms[start:start + k], ses.device)
             ses.tic()
-            buf = self.run_steps(ses, out, k, self.params.store_samples)
+            buf = self.run_steps(ses, out, k, self.params.store_samples, nz, un)
             dt = ses.toc()
             out.statistics.update_elapsed_time(dt)
             if buf is not None:
                 out.running_samples.add(buf.reshape(-1, ses.n, *event_shape), already_thinned=True, n_seen=k)
             done += k
-            if tuning:
-                acc = int(ses.counts[0])
-                self.update_kernel_from_device(ses, (acc - prev_acc) / (ses.n * k))
-                prev_acc = acc
+            if tuner is not None:                                # mcmc/base.py:92-96
+                tuner.update(ses, self.kernel, self.params, k)
+        if tuner is not None:
+            tuner.finish(self.kernel)
         self._finish(ses, out, done)
         out.kernel = self.kernel
         return out
+
+    #: ESS has nothing to tune (mcmc/ess.py:118-119)
+    tunable = True
 
     def _finish(self, ses: DeviceSession, out: MCMCOutput, steps_done: int):
         sx, sx2, cnt = ses.read_back()
@@ -338,8 +402,7 @@ class ESS(MetropolisSampler):
     def _calls_grads(self, n):
         return ((int(self.params.max_ess_step_iterations) + 1) * n, 0)            # ess.py:114-115
 
-    def update_kernel_from_device(self, ses, acc_rate):                             # ess.py:118-119: nothing to tune
-        pass
+    tunable = False                                                                  # ess.py:118-119: nothing to tune
 
     def begin_stage(self, ses: DeviceSession, init_normals=None):
         if init_normals is not None:
@@ -428,7 +491,7 @@ class JumpNFMC(Sampler):
             raise ValueError("Inner sampler in jump HMC must store samples")     # reference: jump.py:163-164
         event_shape = tuple(x0.shape[1:])
         out = JumpNFMCOutput(event_shape=event_shape, store_samples=p.store_samples)
-        ses = DeviceSession(x0, event_shape, self.device, self.seed, self.chain0)
+        ses = DeviceSession(x0, event_shape, self.device, self.session_seed(), self.chain0)
         K = int(inner.params.n_iterations)
         T = int(p.n_iterations)
         store = bool(p.store_samples)
@@ -588,7 +651,7 @@ class AbstractIMH(Sampler):
         event_shape = tuple(x0.shape[1:])
         out = MCMCOutput(event_shape=event_shape, store_samples=store)
         flow: Flow = self.kernel.flow
-        ses = DeviceSession(x0, event_shape, self.device, self.seed, self.chain0)
+        ses = DeviceSession(x0, event_shape, self.device, self.session_seed(), self.chain0)
         dev = ses.device
         T = int(self.params.n_iterations)
         pot, keep = self.target.descriptor(dev)
@@ -727,13 +790,13 @@ class NeuTraHMC(Sampler):
         event_shape = tuple(x0.shape[1:])
         store = bool(self.params.store_samples)
         out = MCMCOutput(event_shape, store_samples=store)
-        ses = DeviceSession(x0, event_shape, self.device, self.seed, self.chain0)
+        ses = DeviceSession(x0, event_shape, self.device, self.session_seed(), self.chain0)
         dev = ses.device
         pot, keep = self.target.descriptor(dev)
         fd, keep2 = self.kernel.flow.bijection.descriptor(dev)
         imd = _imd_device(self.inner_kernel, dev)
         chunk = 1 if (tuning or time_limit_seconds is not None or show_progress) else T
-        prev_acc = 0
+        tuner = None
         rs = out.running_samples
         done = 0
         for start in _progress(range(0, T, max(chunk, 1)), self.name, show_progress):
@@ -759,15 +822,12 @@ class NeuTraHMC(Sampler):
             if buf is not None:
                 rs.add(buf.reshape(-1, ses.n, *event_shape), already_thinned=True, n_seen=k)
             if tuning:                                                                # mcmc/base.py:142-161 on the latent chain
-                ip, ik = self.inner_params, self.inner_kernel
-                acc = int(ses.counts[0])
-                if ses.n > 1 and ip.tune_inv_mass_diag:
-                    ik.inv_mass_diag = ip.imd_adjustment * torch.var(ses.x, dim=0).cpu() + (1 - ip.imd_adjustment) * ik.inv_mass_diag
-                    imd = _imd_device(ik, dev)
-                if ip.tune_step_size and ip.adjustment:
-                    ik.da.step(ik.da_params.target_acceptance_rate - (acc - prev_acc) / (ses.n * k))
-                    ik.step_size = ik.da.value
-                prev_acc = acc
+                if tuner is None:
+                    tuner = _DeviceTuner(ses, self.inner_kernel)
+                tuner.update(ses, self.inner_kernel, self.inner_params, k)
+                imd = _imd_device(self.inner_kernel, dev)
+        if tuner is not None:
+            tuner.finish(self.inner_kernel)
         sx, sx2, cnt = ses.read_back()
         out.statistics.expectations.add_sums(sx, sx2, ses.n * done)
         calls, grads = self._calls_grads(ses.n)
@@ -857,7 +917,7 @@ class TESS(Sampler):
         event_shape = tuple(x0.shape[1:])
         store = bool(self.params.store_samples)
         out = MCMCOutput(event_shape, store_samples=store)
-        ses = DeviceSession(x0, event_shape, self.device, self.seed, self.chain0)      # u = x0 (tess.py:163)
+        ses = DeviceSession(x0, event_shape, self.device, self.session_seed(), self.chain0)      # u = x0 (tess.py:163)
         dev = ses.device
         T = int(self.params.n_iterations)
         M = int(self.params.max_ess_step_iterations)
@@ -901,7 +961,7 @@ class TESS(Sampler):
         event_shape = tuple(x0.shape[1:])
         p: TESSParameters = self.params
         out = MCMCOutput(event_shape, store_samples=p.store_samples)
-        ses = DeviceSession(x0, event_shape, self.device, self.seed, self.chain0)
+        ses = DeviceSession(x0, event_shape, self.device, self.session_seed(), self.chain0)
         rng = N.rng_desc(ses.seed, 0)                                                  # u ~ N(0, I) (tess.py:112), stream 3
         N.check(N.lib().nfmc_rng_fill(C.byref(rng), 3, ses.chain0, ses.d, ses.n, 1, N.ptr(ses.x), None, ses.stream))
         M = int(p.max_ess_step_iterations)
@@ -968,7 +1028,7 @@ class DLMC(Sampler):
         event_shape = tuple(x0.shape[1:])
         store = bool(p.store_samples)
         out = MCMCOutput(event_shape, store_samples=store)
-        ses = DeviceSession(x0, event_shape, self.device, self.seed, self.chain0)
+        ses = DeviceSession(x0, event_shape, self.device, self.session_seed(), self.chain0)
         dev = ses.device
         eps = float(self.kernel.step_size)
         tgt, keep = self.target.descriptor(dev)

@@ -29,7 +29,7 @@ def run_local_injected(sampler, x0, normals, uniforms, store=True):
     out = MCMCOutput(tuple(x0.shape[1:]), store_samples=store)
     ses = DeviceSession(x0, tuple(x0.shape[1:]), None, seed=0)
     dev = ses.device
-    buf = sampler.run_steps(ses, out, K, store, normals.to(dev).contiguous(), uniforms.to(dev).contiguous())
+    buf = sampler.run_steps(ses, out, K, store, normals.to(dev).contiguous(), None if uniforms is None else uniforms.to(dev).contiguous())
     torch.cuda.synchronize()
     sx, sx2, cnt = ses.read_back()
     return (None if buf is None else buf.cpu()), ses, (sx, sx2, cnt)

@@ -121,6 +121,13 @@ def _golden_local(name, kind):
     tgt = product_target(g["pot"], d)
     if kind == "mala":
         s = MALA((d,), tgt, LangevinKernel(event_size=d, inv_mass_diag=imd, step_size=float(g["step"])), LangevinParameters())
+    elif kind == "ula":
+        from nfmc_b200.samplers import ULA
+        s = ULA((d,), tgt, LangevinKernel(event_size=d, inv_mass_diag=imd, step_size=float(g["step"])), LangevinParameters())
+    elif kind == "uhmc":
+        from nfmc_b200.samplers import UHMC
+        s = UHMC((d,), tgt, HMCKernel(event_size=d, inv_mass_diag=imd, step_size=float(g["step"]), n_leapfrog_steps=int(g["L"])),
+                 HMCParameters())
     elif kind == "mh":
         from nfmc_b200.records import MHKernel, MHParameters
         from nfmc_b200.samplers import MH
@@ -129,7 +136,7 @@ def _golden_local(name, kind):
         s = HMC((d,), tgt, HMCKernel(event_size=d, inv_mass_diag=imd, step_size=float(g["step"]), n_leapfrog_steps=int(g["L"])),
                 HMCParameters())
     normals = torch.stack(g["normals"])
-    uniforms = torch.stack(g["uniforms"])
+    uniforms = torch.stack(g["uniforms"]) if g["uniforms"] else None         # the unadjusted kernels draw no uniforms
     samples, ses, (sx, sx2, cnt) = run_local_injected(s, torch.from_numpy(g["x0"]), normals, uniforms)
     ref = torch.from_numpy(g["samples"])
     close(samples, ref, atol=1e-5 * max(1.0, float(ref.abs().max())))
@@ -154,6 +161,49 @@ def test_golden_mh():
     _golden_local("mh_gm", "mh")
 
 
+def test_golden_ula():
+    _golden_local("ula_g0", "ula")          # langevin.py:131-134
+
+
+def test_golden_uhmc():
+    _golden_local("uhmc_gm", "uhmc")        # hmc.py:129-132
+
+
+@pytest.mark.parametrize("name,kind", [("mala_tune_g1", "mala"), ("hmc_tune_fn", "hmc")])
+def test_golden_warmup_trajectory(name, kind):
+    """Warm-up (mcmc/base.py:39-54,142-161; tuning.py:15-41) with the reference's draws injected: the step size and the
+    inverse-mass diagonal after EVERY iteration follow the reference's trajectory (the across-chain variance comes from
+    fp64 sums on the device, the reference's from torch.var in fp32)."""
+    from gpu_util import product_target
+    from nfmc_b200.records import LangevinKernel, LangevinParameters, HMCKernel, HMCParameters
+    from nfmc_b200.samplers import MALA, HMC, _DeviceTuner
+    g = load_case(name)
+    d, K = g["x0"].shape[1], int(g["K"])
+    tgt = product_target(g["pot"], d)
+    if kind == "mala":
+        s = MALA((d,), tgt, LangevinKernel(event_size=d, step_size=float(g["step"])), LangevinParameters(n_iterations=K))
+    else:
+        s = HMC((d,), tgt, HMCKernel(event_size=d, step_size=float(g["step"]), n_leapfrog_steps=int(g["L"])), HMCParameters(n_iterations=K))
+    s.params.tuning_mode()
+    steps, imds = [], []
+    orig = _DeviceTuner.update
+
+    def recording(self, ses, kernel, params, n_steps):
+        orig(self, ses, kernel, params, n_steps)
+        steps.append(float(kernel.step_size))
+        imds.append(kernel.inv_mass_diag.detach().cpu().clone())
+
+    _DeviceTuner.update = recording
+    try:
+        out = s.sample(torch.from_numpy(g["x0"]), show_progress=False, normals=torch.stack(g["normals"]), uniforms=torch.stack(g["uniforms"]))
+    finally:
+        _DeviceTuner.update = orig
+    _check_output(out, g)
+    np.testing.assert_allclose(np.array(steps), g["step_traj"], rtol=2e-5)
+    np.testing.assert_allclose(torch.stack(imds).numpy(), g["imd_traj"], rtol=2e-5, atol=1e-7)
+    assert not s.kernel.inv_mass_diag.is_cuda and abs(float(s.kernel.step_size) - float(g["step_traj"][-1])) < 2e-5 * float(g["step_traj"][-1])
+
+
 def _check_output(out, g, jump=False):
     ref = torch.from_numpy(g["samples"])
     close(out.samples, ref, atol=2e-5 * max(1.0, float(ref.abs().max())))
@@ -168,7 +218,8 @@ def _check_output(out, g, jump=False):
         assert (st.n_accepted_jumps, st.n_attempted_jumps) == (jacc, jatt)
 
 
-@pytest.mark.parametrize("name,inner", [("jump_mala_g0", "mala"), ("jump_hmc_gm", "hmc"), ("jump_mala_g1_d100", "mala")])
+@pytest.mark.parametrize("name,inner", [("jump_mala_g0", "mala"), ("jump_hmc_gm", "hmc"), ("jump_mala_g1_d100", "mala"),
+                                        ("jump_hmc_g1_d100", "hmc"), ("jump_mala_gm_d1000", "mala")])
 def test_golden_jump(name, inner):
     from gpu_util import product_target, product_flow_from_oracle
     from nfmc_b200.records import (LangevinKernel, LangevinParameters, HMCKernel, HMCParameters, NFMCKernel,
@@ -198,11 +249,29 @@ def test_golden_jump(name, inner):
     _check_output(out, g, jump=True)
 
 
-def test_golden_fixed_imh():
+def test_golden_adaptive_imh():
+    """AdaptiveIMH.sample (imh.py:102-181) with the refit switched off as in the fixture: log q recomputed every iteration,
+    2 n GRADIENT calls booked per iteration (imh.py:146), every iteration stored."""
+    from gpu_util import product_target, product_flow_from_oracle
+    from nfmc_b200.records import IMHKernel, IMHParameters
+    from nfmc_b200.samplers import AdaptiveIMH
+    g = load_case("adaptive_imh_rb")
+    n, d = g["x0"].shape
+    T = int(g["T"])
+    s = AdaptiveIMH((d,), product_target(g["pot"], d), IMHKernel((d,), flow=product_flow_from_oracle(oracle_flow(g))),
+                    IMHParameters(n_iterations=T))
+    s.adapt = False
+    # tape per iteration: uniform(n) for the accept test, then one scalar uniform for the refit decision (imh.py:152)
+    out = s.sample(torch.from_numpy(g["x0"]), show_progress=False, z=torch.stack(g["normals"]), uniforms=torch.stack(g["uniforms"][0::2]))
+    _check_output(out, g)
+
+
+@pytest.mark.parametrize("name", ["imh_rb", "imh_rb_d100"])
+def test_golden_fixed_imh(name):
     from gpu_util import product_target, product_flow_from_oracle
     from nfmc_b200.records import IMHKernel, IMHParameters
     from nfmc_b200.samplers import FixedIMH
-    g = load_case("imh_rb")
+    g = load_case(name)
     n, d = g["x0"].shape
     T = int(g["T"])
     s = FixedIMH((d,), product_target(g["pot"], d), IMHKernel((d,), flow=product_flow_from_oracle(oracle_flow(g))),
