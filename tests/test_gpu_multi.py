@@ -60,6 +60,15 @@ def _worker(rank, world, port, q):
         gathered = [torch.empty_like(theta) for _ in range(world)]
         dist.all_gather(gathered, theta)
         res.update(before=before, after=after, theta_spread=float((gathered[0] - gathered[1]).abs().max()))
+        # ---- sharded warm-up: the per-iteration all-reduce keeps every rank's kernel identical --------------------
+        from nfmc_b200.records import LangevinKernel, LangevinParameters
+        from nfmc_b200.samplers import MALA
+        w = MALA((d,), make_potential("g1", (d,)), LangevinKernel(event_size=d, step_size=0.05), LangevinParameters(n_iterations=12))
+        w.device = torch.device("cuda", rank)
+        w.seed = 77
+        w.params.tuning_mode()
+        sample_sharded(w, x0)
+        res.update(tuned_step=float(w.kernel.step_size), tuned_imd=w.kernel.inv_mass_diag.cpu().numpy())
         q.put((rank, res))
     finally:
         dist.destroy_process_group()
@@ -104,3 +113,14 @@ def test_two_gpu_sharding_and_training():
         np.testing.assert_allclose(r["second"], np.asarray(ref.second_moment), rtol=1e-6, atol=1e-6)
         assert r["theta_spread"] == 0.0
         assert r["after"] < r["before"] - 1.0
+    # warm-up: both ranks hold the same tuned kernel, and it equals the single-GPU warm-up over all chains
+    from nfmc_b200.records import LangevinKernel, LangevinParameters
+    from nfmc_b200.samplers import MALA
+    w = MALA((d,), make_potential("g1", (d,)), LangevinKernel(event_size=d, step_size=0.05), LangevinParameters(n_iterations=12))
+    w.seed = 77
+    w.params.tuning_mode()
+    w.sample(x0, show_progress=False)
+    assert res[0]["tuned_step"] == res[1]["tuned_step"]
+    np.testing.assert_array_equal(res[0]["tuned_imd"], res[1]["tuned_imd"])
+    assert abs(res[0]["tuned_step"] - float(w.kernel.step_size)) <= 1e-9 * float(w.kernel.step_size)
+    np.testing.assert_allclose(res[0]["tuned_imd"], w.kernel.inv_mass_diag.cpu().numpy(), rtol=1e-6)
