@@ -243,6 +243,38 @@ NFMC_API int nfmc_flow_fit_epoch(int32_t d, int32_t n_coupling, int32_t n_linear
                         const float* x, const int64_t* perm, int64_t n, int64_t batch_size, float lr, float beta1,
                         float beta2, float eps, float weight_decay, int32_t step0, void* stream);
 
+/* ---- flow training for wide / deep conditioners (any n_linear in [1, 16], any hidden): csrc/train_wide.cu ------------
+ * Same role as the block above (flow.fit: nfmc/jump.py:139-151,201, nfmc/imh.py:171-175; flow.variational_fit:
+ * nfmc/imh.py:67-72, nfmc/neutra.py:84-91) for every conditioner shape the register-resident kernels do not cover.
+ * Works directly in module order: theta = affine_0.value[d][2] | Lc x { linear_0 {W[out][in], b[out]} ... linear_{M-1}
+ * | actnorm.value[d][2] } | affine_T.value[d][2] | actnorm_T.value[d][2]; gradients come back in the same order. */
+NFMC_API int64_t nfmc_flow_wide_param_count(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden);
+/* maximum likelihood: *loss (+)= -sum_i log q(x[rows[i]]), grad_theta (+)= its gradient; rows may be NULL; grad_x
+ * (optional, [n, d]) receives d(-log q)/dx; accumulate = 0 zeroes grad_theta and *loss first */
+NFMC_API int nfmc_flow_wide_nll_grad(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden, const float* theta,
+                            const float* x, const int64_t* rows, int64_t n, float* grad_theta, double* loss,
+                            float* grad_x, int32_t accumulate, void* stream);
+/* one fp32 pass straight from theta: inverse = 0: x -> z, log|det dz/dx|; 1: z -> x, log|det dx/dz| (log_det may be NULL) */
+NFMC_API int nfmc_flow_wide_pass(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden, const float* theta,
+                        int32_t inverse, const float* in, float* out, float* log_det, int64_t n, void* stream);
+/* backward sweep of a pass whose OUTPUT y [n, d] and output cotangent grad_y [n, d] are given (reverse KL: inverse = 1,
+ * y = x = T^-1(z), grad_y = grad U(x)): grad_theta (+)= d/dtheta [ sum_i (grad_y . y)(theta) -/+ log|det| ], i.e. the
+ * gradient of sum_i [U(x_i) - log|det dx/dz|] (inverse = 1) or of sum_i [f(z_i) - log|det dz/dx|] (inverse = 0);
+ * grad_in (optional) = the cotangent that reaches the pass input */
+NFMC_API int nfmc_flow_wide_sweep(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden, const float* theta,
+                         int32_t inverse, const float* y, const float* grad_y, int64_t n, float* grad_theta,
+                         float* grad_in, int32_t accumulate, void* stream);
+/* AdamW with the gradient multiplied by grad_scale first (1 / batch) */
+NFMC_API int nfmc_adamw_step_scaled(float* theta, const float* grad, float grad_scale, float* exp_avg, float* exp_avg_sq,
+                           int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                           void* stream);
+/* one epoch of minibatch maximum likelihood on one GPU (per batch of perm[n]: loss + gradient, AdamW);
+ * losses[batch] = summed loss of the batch; grad_theta is scratch of param_count floats */
+NFMC_API int nfmc_flow_wide_fit_epoch(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden, float* theta,
+                             float* exp_avg, float* exp_avg_sq, float* grad_theta, double* losses, const float* x,
+                             const int64_t* perm, int64_t n, int64_t batch_size, float lr, float beta1, float beta2,
+                             float eps, float weight_decay, int32_t step0, void* stream);
+
 /* ---- deterministic Langevin Monte Carlo (nfmc/dlmc.py:44-119): its three particle updates; the MH correction that follows
  * each of them is nfmc_imh_steps(..., n_steps = 1, recompute_logq = 1) and the refit is nfmc_flow_fit_epoch ------------- */
 /* x <- x - step * grad U(x)                                        (dlmc.py:60-62, the initial update) */

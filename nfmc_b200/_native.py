@@ -97,6 +97,13 @@ SIGNATURES = {
     "nfmc_adamw_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp]),
     "nfmc_flow_fit_epoch": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64,
                                       _f32, _f32, _f32, _f32, _f32, _i32, _vp]),
+    "nfmc_flow_wide_param_count": (_i64, [_i32, _i32, _i32, _i32]),
+    "nfmc_flow_wide_nll_grad": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
+    "nfmc_flow_wide_pass": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "nfmc_flow_wide_sweep": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _i32, _vp]),
+    "nfmc_adamw_step_scaled": (C.c_int, [_vp, _vp, _f32, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp]),
+    "nfmc_flow_wide_fit_epoch": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64,
+                                           _f32, _f32, _f32, _f32, _f32, _i32, _vp]),
     "nfmc_rng_fill": (C.c_int, [P(RngDesc), _i32, _i64, _i32, _i64, _i32, _vp, _vp, _vp]),
     "nfmc_potential_step": (C.c_int, [P(PotentialDesc), _vp, _i64, _f32, _vp]),
     "nfmc_dlmc_update": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _vp, _i64, _f32, _vp]),

@@ -1,14 +1,17 @@
 """Flow training on the device: ``Flow.fit`` (maximum likelihood) and ``Flow.variational_fit`` (reverse KL).
 
-Status: for the default conditioners (2 linear layers, <= 8 hidden units -- the
-register-resident kernel path) training runs **natively**: ``csrc/train_kernels.cu`` computes the loss and the gradient
-with respect to every flow parameter in one launch (reversible backward sweep, no stored activations),
-``csrc/train_api.cu`` packs the parameters, maps the gradient back to module order and applies AdamW; one C call per
-epoch on a single GPU, per-step calls with an NCCL all-reduce of the gradient in between on several.  Only the one-off
-data-dependent ActNorm initialisation uses the torch restatement below.  Other conditioner shapes (wide / deep) fall
-back to the **library-backed** loop (torch autograd + AdamW on the GPU over the same restatement); the target's value /
-gradient inside ``variational_fit`` then come from ``nfmc_potential_eval`` through a custom autograd function.  After
-every fit the packed blobs are rebuilt so the samplers keep using the CUDA kernels.
+Status: training runs **natively** for every conditioner shape.
+* default conditioners (2 linear layers, <= 8 hidden units -- the register-resident kernel path):
+  ``csrc/train_kernels.cu`` computes the loss and the gradient with respect to every flow parameter in one launch
+  (reversible backward sweep, no stored activations), ``csrc/train_api.cu`` packs the parameters, maps the gradient back
+  to module order and applies AdamW; one C call per epoch on a single GPU, per-step calls with an NCCL all-reduce of the
+  gradient in between on several.
+* wide / deep conditioners (any number of linear layers, any hidden width): ``csrc/train_wide.cu`` -- row tiles in shared
+  memory, forward / dgrad / wgrad contractions as register-blocked fp32 loops, parameters and gradients in module order
+  (no pack / unpack); reverse KL = fp32 pass kernel + ``nfmc_potential_eval`` + backward-sweep kernel.
+There is no torch-autograd training loop in the product.  ``forward_autograd`` / ``inverse_autograd`` below are the torch
+restatement used for the one-off data-dependent ActNorm initialisation and by the tests.  After every fit the packed blobs
+are rebuilt so the samplers keep using the CUDA kernels.
 
 Reference call sites: ``flow.fit`` -- /root/reference/nfmc/algorithms/sampling/nfmc/jump.py:139-151,201 and
 nfmc/imh.py:171-175; ``flow.variational_fit`` -- nfmc/imh.py:67-72 and nfmc/neutra.py:84-91;
@@ -22,7 +25,6 @@ import ctypes as C
 import math
 import os
 import time
-from copy import deepcopy
 from typing import Callable, Optional, Tuple
 
 import torch
@@ -122,33 +124,38 @@ def target_log_prob_fn(potential) -> Callable:
     return fn
 
 
-def _sync_grads(params):
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        flat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
-        dist.all_reduce(flat)
-        flat /= dist.get_world_size()
-        off = 0
-        for p in params:
-            if p.grad is not None:
-                n = p.grad.numel()
-                p.grad.copy_(flat[off:off + n].view_as(p.grad))
-                off += n
-
-
 # ---------------------------------------------------------------------------------------------------------------
 # native training (csrc/train_kernels.cu, csrc/train_api.cu)
 # ---------------------------------------------------------------------------------------------------------------
 ADAMW = dict(beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01)     # torch.optim.AdamW defaults
 
 
-def native_supported(flow) -> bool:
-    """The native kernels cover conditioners with 2 linear layers and <= 8 hidden units (every default conditioner)."""
-    if os.environ.get("NFMC_B200_LIBRARY_TRAINING") == "1":
-        return False
+def _same_shape(flow):
     bij = flow.bijection
     M, H = bij.conditioner_shape()
-    same = all((c.n_linear, c.n_hidden) == (M, H) for c in bij.couplings())
-    return same and N.lib().nfmc_flow_param_count(bij.n_dim, bij.n_coupling, M, H) > 0
+    return all((c.n_linear, c.n_hidden) == (M, H) for c in bij.couplings()), M, H
+
+
+def native_supported(flow) -> bool:
+    """The register-resident kernels cover conditioners with 2 linear layers and <= 8 hidden units (every default one)."""
+    if os.environ.get("NFMC_B200_WIDE_TRAINING") == "1":          # tests: force the wide kernel on a default flow
+        return False
+    same, M, H = _same_shape(flow)
+    bij = flow.bijection
+    return same and M == 2 and H <= 8 and N.lib().nfmc_flow_param_count(bij.n_dim, bij.n_coupling, M, H) > 0
+
+
+def wide_supported(flow) -> bool:
+    """Every other shape goes to csrc/train_wide.cu (all couplings must share one conditioner shape)."""
+    same, M, H = _same_shape(flow)
+    bij = flow.bijection
+    return same and N.lib().nfmc_flow_wide_param_count(bij.n_dim, bij.n_coupling, M, H) > 0
+
+
+def _unsupported(flow):
+    same, M, H = _same_shape(flow)
+    return NotImplementedError(f"flow training: conditioner shape (n_layers={M}, n_hidden={H}, uniform={same}) is outside the "
+                               "native kernels; there is no eager fallback")
 
 
 def _world() -> int:
@@ -268,6 +275,102 @@ class NativeTrainer:
             off += k
 
 
+class WideTrainer(NativeTrainer):
+    """Same driver for wide / deep conditioners (csrc/train_wide.cu): theta and its gradient stay in module order."""
+
+    def __init__(self, flow, dev, lr: float):
+        self.flow, self.dev, self.lr = flow, dev, float(lr)
+        bij = flow.bijection
+        self.d, self.Lc = bij.n_dim, bij.n_coupling
+        self.M, self.H = bij.conditioner_shape()
+        self.params = [p for p in bij.parameters()]
+        self.theta = torch.cat([p.detach().reshape(-1) for p in self.params]).to(dev, torch.float32).contiguous()
+        if _world() > 1:
+            dist.broadcast(self.theta, src=0)
+        P = N.lib().nfmc_flow_wide_param_count(self.d, self.Lc, self.M, self.H)
+        if P != self.theta.numel():
+            raise RuntimeError(f"parameter count mismatch: module {self.theta.numel()} vs native {P}")
+        self.m = torch.zeros_like(self.theta)
+        self.v = torch.zeros_like(self.theta)
+        self.gtheta = torch.empty_like(self.theta)
+        self.loss = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.step = 0
+        self.stream = N.stream_ptr(dev)
+
+    def _shape(self):
+        return self.d, self.Lc, self.M, self.H
+
+    def adamw_scaled(self, scale: float):
+        self.step += 1
+        N.check(N.lib().nfmc_adamw_step_scaled(N.ptr(self.theta), N.ptr(self.gtheta), float(scale), N.ptr(self.m), N.ptr(self.v),
+                                               self.theta.numel(), self.lr, ADAMW["beta1"], ADAMW["beta2"], ADAMW["eps"],
+                                               ADAMW["weight_decay"], self.step, self.stream))
+
+    def nll_grad(self, x: torch.Tensor, rows: Optional[torch.Tensor], n: int, grad_x: Optional[torch.Tensor] = None):
+        N.check(N.lib().nfmc_flow_wide_nll_grad(*self._shape(), N.ptr(self.theta), N.ptr(x), None if rows is None else rows.data_ptr(),
+                                                n, N.ptr(self.gtheta), N.ptr(self.loss), N.ptr(grad_x), 0, self.stream))
+
+    def nll_step(self, x: torch.Tensor, rows: Optional[torch.Tensor], n: int):
+        self.nll_grad(x, rows, n)
+        self.sync_grad()
+        self.adamw_scaled(1.0 / n)
+
+    def nll_epoch(self, x: torch.Tensor, perm: torch.Tensor, batch_size: int, losses: torch.Tensor):
+        n = perm.numel()
+        if _world() > 1:
+            for b, i in enumerate(range(0, n, batch_size)):
+                m = min(batch_size, n - i)
+                self.nll_step(x, perm[i:i + m], m)
+                losses[b] = self.loss[0]
+            return
+        N.check(N.lib().nfmc_flow_wide_fit_epoch(*self._shape(), N.ptr(self.theta), N.ptr(self.m), N.ptr(self.v), N.ptr(self.gtheta),
+                                                 N.ptr(losses), N.ptr(x), perm.data_ptr(), n, batch_size, self.lr, ADAMW["beta1"],
+                                                 ADAMW["beta2"], ADAMW["eps"], ADAMW["weight_decay"], self.step, self.stream))
+        self.step += (n + batch_size - 1) // batch_size
+
+    def run_pass(self, v: torch.Tensor, inverse: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+        """fp32 pass under the current theta: (output [n, d], log|det| [n])."""
+        n = v.shape[0]
+        out = torch.empty_like(v)
+        ld = torch.empty(n, device=self.dev, dtype=torch.float32)
+        N.check(N.lib().nfmc_flow_wide_pass(*self._shape(), N.ptr(self.theta), 1 if inverse else 0, N.ptr(v), N.ptr(out), N.ptr(ld),
+                                            n, self.stream))
+        return out, ld
+
+    def kl_step(self, potential, n_samples: int, seed: int, step0: int, z: Optional[torch.Tensor] = None):
+        """One reverse-KL step: z ~ N(0, I) (Philox stream 1, as the register-resident kernel draws it), x = T^-1(z) by the
+        pass kernel, U and grad U by the potential kernel, then the backward sweep and AdamW.  ``self.loss`` = sum_i
+        [log q(x_i) + U(x_i)] under the parameters before the step."""
+        d = self.d
+        if z is None:
+            z = torch.empty(n_samples, d, device=self.dev, dtype=torch.float32)
+            rng = N.rng_desc(seed, step0, None, None)
+            chain0 = (dist.get_rank() * n_samples) if _world() > 1 else 0
+            N.check(N.lib().nfmc_rng_fill(C.byref(rng), 1, chain0, d, n_samples, 1, N.ptr(z), None, self.stream))
+        x, ld_inv = self.run_pass(z, inverse=True)
+        u, gu = potential.value_and_grad(x, need_grad=True)
+        gu = gu.reshape(n_samples, d).contiguous()
+        log_q = (-0.5 * z.square()).sum(dim=1) - 0.5 * d * math.log(2 * math.pi) - ld_inv
+        self.loss[0] = (log_q + u).double().sum()
+        N.check(N.lib().nfmc_flow_wide_sweep(*self._shape(), N.ptr(self.theta), 1, N.ptr(x), N.ptr(gu), n_samples, N.ptr(self.gtheta),
+                                             None, 0, self.stream))
+        self.sync_grad()
+        self.adamw_scaled(1.0 / n_samples)
+
+    def mean_nll(self, x: torch.Tensor) -> torch.Tensor:
+        z, ld = self.run_pass(x, inverse=False)
+        lq = (-0.5 * z.square()).sum(dim=1) - 0.5 * self.d * math.log(2 * math.pi) + ld
+        return -lq.double().mean()
+
+
+def make_trainer(flow, dev, lr: float) -> NativeTrainer:
+    if native_supported(flow):
+        return NativeTrainer(flow, dev, lr)
+    if wide_supported(flow):
+        return WideTrainer(flow, dev, lr)
+    raise _unsupported(flow)
+
+
 def _init_actnorms(flow, x_first: torch.Tensor):
     """One-off data-dependent ActNorm initialisation (torch restatement; runs once per flow lifetime)."""
     from .flow import ActNorm
@@ -289,7 +392,7 @@ def _fit_native(flow, dev, x_train, x_val, n_epochs, lr, batch_size, shuffle, ke
             raise ValueError("flow.fit: a rank has no training rows")
         x_train = x_train[:n]
     _init_actnorms(flow, x_train[:batch_size])
-    tr = NativeTrainer(flow, dev, lr)
+    tr = make_trainer(flow, dev, lr)
     n_batches = (n + batch_size - 1) // batch_size
     losses = torch.zeros(n_batches, device=dev, dtype=torch.float64)
     ref = x_val if x_val is not None and len(x_val) else x_train
@@ -324,7 +427,7 @@ def _fit_native(flow, dev, x_train, x_val, n_epochs, lr, batch_size, shuffle, ke
 
 def _variational_fit_native(flow, dev, potential, n_epochs, lr, n_samples, early_stopping, early_stopping_threshold,
                             keep_best_weights, check_for_divergences, time_limit_seconds):
-    tr = NativeTrainer(flow, dev, lr)
+    tr = make_trainer(flow, dev, lr)
     seed = int(torch.randint(0, 2 ** 62, (), dtype=torch.int64))
     best, since_best = math.inf, 0
     best_theta = tr.theta.clone() if keep_best_weights else None
@@ -383,53 +486,9 @@ def fit(flow, x_train, n_epochs: int = 500, lr: float = 0.05, batch_size=None, s
     if batch_size is None:
         batch_size = n
     batch_size = int(batch_size)
-    if native_supported(flow):
-        return _fit_native(flow, dev, x_train.contiguous(), None if x_val is None else x_val.contiguous(), n_epochs, lr,
-                           batch_size, shuffle, keep_best_weights, early_stopping, early_stopping_threshold,
-                           time_limit_seconds)
-    params = [p for p in flow.parameters() if p.requires_grad]
-    if _world() > 1:
-        _init_actnorms(flow, x_train[:batch_size])
-        with torch.no_grad():
-            for p in params:
-                dist.broadcast(p, src=0)
-    opt = torch.optim.AdamW(params, lr=lr)
-    best, best_state, since_best = math.inf, None, 0
-    t0 = time.time()
-    flow.train()
-    try:
-        with torch.enable_grad():
-            for _ in range(n_epochs):
-                if _out_of_time(t0, time_limit_seconds, dev):
-                    break
-                perm = torch.randperm(n, device=dev) if shuffle else torch.arange(n, device=dev)
-                for i in range(0, n, batch_size):
-                    opt.zero_grad(set_to_none=True)
-                    loss = -log_prob_autograd(flow, x_train[perm[i:i + batch_size]], training=True).mean()
-                    if not torch.isfinite(loss):
-                        raise ValueError("Flow training diverged")          # the reference rolls back on ValueError
-                    loss.backward()
-                    _sync_grads(params)
-                    opt.step()
-                with torch.no_grad():
-                    ref = x_val if x_val is not None and len(x_val) else x_train
-                    score_t = -log_prob_autograd(flow, ref).mean()
-                    if _world() > 1:
-                        dist.all_reduce(score_t)
-                        score_t /= _world()
-                    score = float(score_t)
-                if score < best:
-                    best, since_best = score, 0
-                    if keep_best_weights:
-                        best_state = deepcopy(flow.state_dict())
-                else:
-                    since_best += 1
-                    if early_stopping and since_best >= early_stopping_threshold:
-                        break
-        if keep_best_weights and best_state is not None:
-            flow.load_state_dict(best_state)
-    finally:
-        flow.eval()
+    return _fit_native(flow, dev, x_train.contiguous(), None if x_val is None else x_val.contiguous(), n_epochs, lr,
+                       batch_size, shuffle, keep_best_weights, early_stopping, early_stopping_threshold,
+                       time_limit_seconds)
 
 
 def variational_fit(flow, target_log_prob: Callable, n_epochs: int = 500, lr: float = 0.05, n_samples: int = 1,
@@ -439,42 +498,9 @@ def variational_fit(flow, target_log_prob: Callable, n_epochs: int = 500, lr: fl
     flow.to(dev)
     d = flow.bijection.n_dim
     potential = getattr(target_log_prob, "potential", None)
-    if potential is not None and native_supported(flow):
-        return _variational_fit_native(flow, dev, potential, n_epochs, lr, int(n_samples), early_stopping,
-                                       early_stopping_threshold, keep_best_weights, check_for_divergences,
-                                       time_limit_seconds)
-    params = [p for p in flow.parameters() if p.requires_grad]
-    opt = torch.optim.AdamW(params, lr=lr)
-    best, best_state, since_best = math.inf, None, 0
-    t0 = time.time()
-    flow.train()
-    try:
-        with torch.enable_grad():
-            for _ in range(n_epochs):
-                if _out_of_time(t0, time_limit_seconds, dev):
-                    break
-                opt.zero_grad(set_to_none=True)
-                z = torch.randn(n_samples, d, device=dev)
-                x, ld = inverse_autograd(flow.bijection, z)
-                log_q = (-0.5 * z.square()).sum(dim=1) - 0.5 * d * math.log(2 * math.pi) - ld
-                loss = (log_q - target_log_prob(x)).mean()
-                if not torch.isfinite(loss):
-                    if check_for_divergences:
-                        break
-                    raise ValueError("Flow training diverged")
-                loss.backward()
-                _sync_grads(params)
-                opt.step()
-                val = float(loss.detach())
-                if val < best:
-                    best, since_best = val, 0
-                    if keep_best_weights:
-                        best_state = deepcopy(flow.state_dict())
-                else:
-                    since_best += 1
-                    if early_stopping and since_best >= early_stopping_threshold:
-                        break
-        if keep_best_weights and best_state is not None:
-            flow.load_state_dict(best_state)
-    finally:
-        flow.eval()
+    if potential is None:
+        raise NotImplementedError("variational_fit needs a target built from nfmc_b200.potentials (target_log_prob_fn): "
+                                  "arbitrary Python callables cannot be fused and there is no eager fallback")
+    return _variational_fit_native(flow, dev, potential, n_epochs, lr, int(n_samples), early_stopping,
+                                   early_stopping_threshold, keep_best_weights, check_for_divergences,
+                                   time_limit_seconds)
