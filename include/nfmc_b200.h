@@ -131,6 +131,24 @@ NFMC_API int nfmc_jump_step_tc(const nfmc_potential* pot, const nfmc_realnvp_tc*
                                const nfmc_stats* stats, const nfmc_sink* sink, void* workspace, int64_t workspace_bytes,
                                void* stream);
 
+/* ---- NeuTra on the tensor cores (csrc/tc_neutra.cu): U~(z) = U(T^-1 z) - log|det dT^-1/dz| (nfmc/neutra.py:58-68) and
+ * its gradient with the conditioner forward AND its input-VJP (dgrad) on tcgen05.  blob_t = the transposed weight images
+ * of nfmc_b200.flow.pack_realnvp_tc_transposed() (nfmc_neutra_tc_transposed_bytes bytes; -1 = shape not eligible: needs
+ * hidden % 32 == 0, d % 4 == 0 and a shared-memory plan within 227 KB). */
+NFMC_API int64_t nfmc_neutra_tc_transposed_bytes(int32_t d, int32_t n_coupling, int32_t hidden);
+NFMC_API int64_t nfmc_neutra_tc_workspace_bytes(int32_t d, int64_t n);
+/* value u [n] and gradient grad [n, d] of U~ at z [n, d]; x [n, d] and ld [n] receive T^-1(z) and log|det dx/dz| */
+NFMC_API int nfmc_neutra_potential_tc(const nfmc_potential* pot, const nfmc_realnvp_tc* flow, const void* blob_t, int64_t blob_t_bytes,
+                             const float* z, float* x, float* ld, float* u, float* grad, int64_t n, void* stream);
+/* T NeuTra-HMC iterations (HMC.propose, mcmc/hmc.py:96-126, on the latent potential; same contract as
+ * nfmc_neutra_hmc_steps): per step the momentum draw, L + 1 tensor-core gradient evaluations with the leapfrog updates
+ * of hmc.py:51-58 between them, the accept test of hmc.py:103-113, moments / counters / sink of the latent state */
+NFMC_API int nfmc_neutra_hmc_steps_tc(const nfmc_potential* pot, const nfmc_realnvp_tc* flow, const void* blob_t, int64_t blob_t_bytes,
+                             float* z, int64_t n, int32_t n_steps, float step_size, int32_t n_leapfrog,
+                             const float* inv_mass_diag, int32_t adjusted, const nfmc_rng* rng, int64_t chain0,
+                             const nfmc_stats* stats, const nfmc_sink* sink, void* workspace, int64_t workspace_bytes,
+                             void* stream);
+
 /* K Langevin steps for all chains -- Langevin.propose (mcmc/langevin.py:61-122) inside the local loop
  * MCMCSampler.sample (mcmc/base.py:69-99).  inv_mass_diag may be NULL (= ones).  adjusted=0 -> ULA. */
 NFMC_API int nfmc_mala_steps(const nfmc_potential* pot, float* x, int64_t n, int32_t n_steps, float step_size,

@@ -89,6 +89,11 @@ SIGNATURES = {
     "nfmc_neutra_mh_steps": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _vp, _i64, _i32, _vp, _i32, P(RngDesc), _i64,
                                        P(StatsDesc), P(SinkDesc), _vp]),
     "nfmc_neutra_potential": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _vp, _vp, _vp, _i64, _vp]),
+    "nfmc_neutra_tc_transposed_bytes": (_i64, [_i32, _i32, _i32]),
+    "nfmc_neutra_tc_workspace_bytes": (_i64, [_i32, _i64]),
+    "nfmc_neutra_potential_tc": (C.c_int, [P(PotentialDesc), P(RealNVPTcDesc), _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "nfmc_neutra_hmc_steps_tc": (C.c_int, [P(PotentialDesc), P(RealNVPTcDesc), _vp, _i64, _vp, _i64, _i32, _f32, _i32, _vp, _i32,
+                                           P(RngDesc), _i64, P(StatsDesc), P(SinkDesc), _vp, _i64, _vp]),
     "nfmc_flow_param_count": (_i64, [_i32, _i32, _i32, _i32]),
     "nfmc_flow_pack": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "nfmc_flow_nll_grad": (C.c_int, [P(RealNVPDesc), _vp, _vp, _i64, _vp, _vp, _i32, _vp]),

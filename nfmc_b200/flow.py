@@ -171,6 +171,18 @@ class RealNVP(_Layer):
         M, H = self.conditioner_shape()
         return N.RealNVPTcDesc(self.n_dim, self.n_coupling, _tc_hidden(H), 0, blob.data_ptr(), blob.numel()), blob
 
+    def tc_transposed(self, device: torch.device) -> torch.Tensor:
+        """Transposed weight images for the tensor-core NeuTra kernel (``pack_realnvp_tc_transposed``), cached per device."""
+        key = str(device) + "/T"
+        ver = self._version_key()
+        hit = self._packed_tc.get(key)
+        if hit is None or hit[0] != ver:
+            self._packed_tc[key] = (ver, pack_realnvp_tc_transposed(self).to(device))
+        return self._packed_tc[key][1]
+
+    def uses_tensor_cores_for_neutra(self) -> bool:
+        return self.uses_tensor_cores() and neutra_tc_supported(self.n_dim, *self.conditioner_shape(), self.n_coupling)
+
     def descriptor(self, device: torch.device):
         blob = self.blob(device)
         M, H = self.conditioner_shape()
@@ -439,34 +451,79 @@ def pack_realnvp_tc(bij: "RealNVP") -> torch.Tensor:
     c = math.log1p(-MIN_SCALE)
     base = pack_realnvp_affines(bij)
     chunks = [base.contiguous().view(torch.uint8)]
-    layers = list(bij.layers)
     for l in range(Lc):
-        cpl = layers[2 + 3 * l]
-        odd = (l + 1) % 2 == 1
-        (w1, b1), (wl, bl) = [(m.weight.detach().to("cpu", torch.float32), m.bias.detach().to("cpu", torch.float32))
-                              for m in cpl.linears()]
-        w1p = torch.zeros(Hp, k1)
-        w1p[:H, :da] = w1.flip(1) if odd else w1                      # [h][ks], zero rows for the padded hidden units
-        b1_hi = b1.to(torch.bfloat16).to(torch.float32)
-        w1p[:H, da] = b1_hi
-        w1p[:H, da + 1] = b1 - b1_hi
+        w1p, wlp, blp = _tc_coupling_matrices(bij, l)
         img1 = w1p.reshape(Hp, k1 // 8, 8).permute(1, 0, 2).contiguous()   # [kg][h][8]
-        wl3 = wl.reshape(db, 2, H).clone()                            # [t_log][c][h]
-        bl2 = bl.reshape(db, 2).clone()
-        if odd:
-            wl3, bl2 = wl3.flip(0), bl2.flip(0)
-        wl3[:, 0, :] *= 0.5 * log2e
-        wl3[:, 1, :] *= 0.5
-        wlp = torch.zeros(n2p, Hp)
-        wlp[: 2 * db, :H] = wl3.reshape(2 * db, H)                    # row n = 2 t + c
         img2 = wlp.reshape(n2p, Hp // 8, 8).permute(1, 0, 2).contiguous()  # [kg][n][8]
-        blp = torch.zeros(n2p // 2, 2)
-        blp[:, 0] = c * log2e                                         # padded targets: alpha = 1, beta = 0
-        blp[:db, 0] = (0.5 * bl2[:, 0] + c) * log2e
-        blp[:db, 1] = 0.5 * bl2[:, 1]
         chunks += [img1.to(torch.bfloat16).view(torch.uint8).reshape(-1), img2.to(torch.bfloat16).view(torch.uint8).reshape(-1),
                    blp.contiguous().view(torch.uint8).reshape(-1)]
     return torch.cat([c_.reshape(-1) for c_ in chunks]).contiguous()
+
+
+@torch.no_grad()
+def _tc_coupling_matrices(bij: "RealNVP", l: int):
+    """The padded fp32 matrices behind coupling l's tensor-core images: ``W1aug [Hp][K1]`` (W1 | b1_hi | b1_lo, zero
+    padded), ``Wl' [N2p][Hp]`` (row n = 2 t + c, constants folded) and ``bl' [N2p/2][2]``."""
+    import math
+    d = bij.n_dim
+    da, db = d // 2, d - d // 2
+    M, H = bij.conditioner_shape()
+    Hp = _tc_hidden(H)
+    n2p = ((2 * db + 15) // 16) * 16
+    k1 = ((da + 2 + 15) // 16) * 16
+    log2e = 1.0 / math.log(2.0)
+    c = math.log1p(-MIN_SCALE)
+    cpl = list(bij.layers)[2 + 3 * l]
+    odd = (l + 1) % 2 == 1
+    (w1, b1), (wl, bl) = [(m.weight.detach().to("cpu", torch.float32), m.bias.detach().to("cpu", torch.float32))
+                          for m in cpl.linears()]
+    w1p = torch.zeros(Hp, k1)
+    w1p[:H, :da] = w1.flip(1) if odd else w1                      # [h][ks], zero rows for the padded hidden units
+    b1_hi = b1.to(torch.bfloat16).to(torch.float32)
+    w1p[:H, da] = b1_hi
+    w1p[:H, da + 1] = b1 - b1_hi
+    wl3 = wl.reshape(db, 2, H).clone()                            # [t_log][c][h]
+    bl2 = bl.reshape(db, 2).clone()
+    if odd:
+        wl3, bl2 = wl3.flip(0), bl2.flip(0)
+    wl3[:, 0, :] *= 0.5 * log2e
+    wl3[:, 1, :] *= 0.5
+    wlp = torch.zeros(n2p, Hp)
+    wlp[: 2 * db, :H] = wl3.reshape(2 * db, H)                    # row n = 2 t + c
+    blp = torch.zeros(n2p // 2, 2)
+    blp[:, 0] = c * log2e                                         # padded targets: alpha = 1, beta = 0
+    blp[:db, 0] = (0.5 * bl2[:, 0] + c) * log2e
+    blp[:db, 1] = 0.5 * bl2[:, 1]
+    return w1p, wlp, blp
+
+
+def neutra_tc_supported(d: int, M: int, H: int, Lc: int) -> bool:
+    """Shapes the tensor-core NeuTra kernel (csrc/tc_neutra.cu) runs: tensor-core eligible, hidden width (padded to 16) a
+    multiple of 32, d % 4 == 0 and a shared-memory plan that fits (the library decides)."""
+    if not tc_supported(d, M, H) or Lc < 1:
+        return False
+    return N.lib().nfmc_neutra_tc_transposed_bytes(d, Lc, _tc_hidden(H)) > 0
+
+
+@torch.no_grad()
+def pack_realnvp_tc_transposed(bij: "RealNVP") -> torch.Tensor:
+    """The dgrad operands of the tensor-core NeuTra kernel (csrc/tc_neutra.cu), per coupling: ``Wl'^T image
+    [N2p/8][Hp][8]`` (B operand of dH = dU' . Wl': row = hidden unit, K = U' column) and ``W1^T image [Hp/8][K1][8]``
+    (B operand of dS = dHpre . W1: row = source index, K = hidden unit), bf16, the same rounded values as the forward
+    images of ``pack_realnvp_tc``."""
+    d = bij.n_dim
+    da, db = d // 2, d - d // 2
+    M, H = bij.conditioner_shape()
+    Hp = _tc_hidden(H)
+    n2p = ((2 * db + 15) // 16) * 16
+    k1 = ((da + 2 + 15) // 16) * 16
+    chunks = []
+    for l in range(bij.n_coupling):
+        w1p, wlp, _ = _tc_coupling_matrices(bij, l)
+        img_wlT = wlp.reshape(n2p // 8, 8, Hp).permute(0, 2, 1).contiguous()   # [kg over U' columns][h][8]
+        img_w1T = w1p.reshape(Hp // 8, 8, k1).permute(0, 2, 1).contiguous()    # [kg over hidden units][source j][8]
+        chunks += [img_wlT.to(torch.bfloat16).view(torch.uint8).reshape(-1), img_w1T.to(torch.bfloat16).view(torch.uint8).reshape(-1)]
+    return torch.cat(chunks).contiguous()
 
 
 def create_flow_object(flow_string: str, event_shape, **kwargs) -> Flow:

@@ -840,6 +840,19 @@ class NeuTraHMC(Sampler):
         return out
 
     def _launch_latent(self, ses, pot, fd, k, imd, rng, st, sink):
+        bij = self.kernel.flow.bijection
+        if bij.uses_tensor_cores_for_neutra():
+            # wide flow: conditioner forward and input-VJP on tcgen05 (csrc/tc_neutra.cu)
+            dev = ses.device
+            td, keep = bij.tc_descriptor(dev)
+            bt = bij.tc_transposed(dev)
+            nb = N.lib().nfmc_neutra_tc_workspace_bytes(ses.d, ses.n)
+            ws = ses.workspace(nb)
+            N.check(N.lib().nfmc_neutra_hmc_steps_tc(C.byref(pot), C.byref(td), N.ptr(bt), bt.numel(), N.ptr(ses.x), ses.n, k,
+                                                     float(self.inner_kernel.step_size), int(self.inner_kernel.n_leapfrog_steps),
+                                                     N.ptr(imd), 1, C.byref(rng), ses.chain0, C.byref(st),
+                                                     None if sink is None else C.byref(sink), N.ptr(ws), nb, ses.stream))
+            return
         N.check(N.lib().nfmc_neutra_hmc_steps(C.byref(pot), C.byref(fd), N.ptr(ses.x), ses.n, k,
                                               float(self.inner_kernel.step_size), int(self.inner_kernel.n_leapfrog_steps),
                                               N.ptr(imd), C.byref(rng), ses.chain0, C.byref(st),

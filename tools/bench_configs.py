@@ -75,6 +75,10 @@ if __name__ == "__main__":
     run("tess funnel d=100 n=2^18 (frozen flow)", "tess", "fn", 100, 1 << 18, 10)
     run("neutra_mh funnel d=100 n=2^20", "neutra_mh", "fn", 100, 1 << 20, 20)
     run("dlmc mixture d=100 n=2^17 (refit every iteration)", "dlmc", "gm", 100, 1 << 17, 4)
+    run("C3-wide neutra_hmc funnel d=100 n=262144 H=256 Lc=4 (tcgen05 forward + dgrad)", "neutra_hmc", "fn", 100, 262144, 3,
+        flow_spec=wide, inner_kernel_kwargs={"step_size": 0.01})
+    run("C3-wide neutra_hmc funnel d=100 n=262144 H=64 Lc=2 (tcgen05 forward + dgrad)", "neutra_hmc", "fn", 100, 262144, 3,
+        flow_spec='realnvp%{"n_layers": 2, "conditioner_kwargs": {"n_layers": 2, "n_hidden": 64}}', inner_kernel_kwargs={"step_size": 0.01})
     run("wide-flow jump_mala d=100 n=2^20 H=256 Lc=4 (tcgen05)", "jump_mala", "g0", 100, 1 << 20, 5, K=100, flow_spec=wide)
     run("wide-flow imh d=100 n=2^20 H=256 Lc=4 (tcgen05)", "imh", "g0", 100, 1 << 20, 10, flow_spec=wide)
     run("wide-flow jump_mala K=1 (jump-dominated) d=100 n=2^20 H=256 Lc=4 (tcgen05)", "jump_mala", "g0", 100, 1 << 20, 10, K=1, flow_spec=wide)
