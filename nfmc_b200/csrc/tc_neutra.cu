@@ -12,7 +12,10 @@
 //        G4  dS  [128 x K1]   = (dH * (1 - tanh^2))[128 x Hp] . W1          (dgrad of the first layer)
 //      bf16 operands, fp32 accumulators in tensor memory; tanh(Hpre), dU' and dH*(1-tanh^2) are written back to tensor
 //      memory as packed bf16 and consumed from there as the A operands of G2 / G3 / G4 (never through shared memory).
-//   3. small elementwise kernels for the momentum draw, the leapfrog updates and the accept step (hmc.py:51-58,103-113).
+//      The leapfrog update (hmc.py:51-58: half-kicks p <- p - tau/2 grad, drift z <- z + tau p m) is fused into the kernel's
+//      output stage: the momentum and latent tiles are staged by TMA into the weight buffers the last coupling has released,
+//      updated in place and stored back by TMA -- no gradient tensor is ever written.
+//   3. small kernels for the momentum draw and the accept step (hmc.py:100,103-113).
 // The reference evaluates the gradient 2L times per step; consecutive half-kicks share an evaluation here (L + 1).
 //
 // Tensor-memory plan of the unwind kernel (one tile at a time, 512 columns):
@@ -38,7 +41,7 @@ namespace nfmc {
 
 constexpr int kNuColU = 256, kNuColDhHi = 384;
 enum { kNuBarA1 = 0, kNuBarG1, kNuBarHid, kNuBarG2, kNuBarDu, kNuBarG3, kNuBarDpre, kNuBarG4, kNuBarW1, kNuBarWl, kNuBarWlT,
-       kNuBarW1T, kNuBarXFull, kNuBarXRead, kNuBarGOut, kNuNumBars };
+       kNuBarW1T, kNuBarXFull, kNuBarXRead, kNuBarGOut, kNuBarPZFull, kNuBarPZOut, kNuBarBufFree, kNuNumBars };
 
 struct NuArgs {
   const unsigned char* blob;    // tc blob: affines | per coupling {W1 image, Wl' image, bl'}
@@ -48,9 +51,15 @@ struct NuArgs {
   PotParams pot;
   const float* x;        // [n, d]  x = T^-1(z) from the inverse pass
   const float* ld_inv;   // [n]     log|det dx/dz|
-  float* grad;           // [n, d]  dU~/dz (logical order)
+  float* grad;           // [n, d]  dU~/dz (logical order), or nullptr when the leapfrog update is fused (p != nullptr)
   float* value;          // [n]     U~(z)
   long long n;
+  // fused leapfrog update (hmc.py:51-58): p <- p - kicks * tau/2 * grad;  if drift: z <- z + tau * (p * m)
+  float* p;              // [n, d] momentum, updated in place (nullptr: gradient output mode)
+  float* zw;             // [n, d] latent state, updated in place when drift
+  const float* imd;      // [d] inverse mass diagonal or nullptr (= ones)
+  float half_tau, tau;
+  int kicks, drift;
 };
 
 struct NuSmem {
@@ -66,15 +75,20 @@ __host__ __device__ inline size_t nu_wlT_bytes(const TcShape& S) {
   return ((w > t ? w : t) + 127) & ~size_t(127);
 }
 __host__ __device__ inline size_t nu_w1T_bytes(const TcShape& S) { return (size_t)S.Hp * S.K1 * 2; }
+// the Wl' buffer doubles as the z tile buffer of the fused leapfrog update
+__host__ __device__ inline size_t nu_wl_bytes(const TcShape& S) {
+  const size_t w = tc_wl_bytes(S), t = tc_tile_bytes(S);
+  return ((w > t ? w : t) + 127) & ~size_t(127);
+}
 __host__ __device__ inline size_t nu_smem_total(const TcShape& S) {
-  return tc_a1_bytes(S) + tc_w1_bytes(S) + tc_wl_bytes(S) + nu_wlT_bytes(S) + nu_w1T_bytes(S) + (size_t)S.Lc * S.N2p * 4 + tc_aff4_bytes(S) +
+  return tc_a1_bytes(S) + tc_w1_bytes(S) + nu_wl_bytes(S) + nu_wlT_bytes(S) + nu_w1T_bytes(S) + (size_t)S.Lc * S.N2p * 4 + tc_aff4_bytes(S) +
          (size_t)kNuNumBars * 8 + 16;
 }
 __device__ __forceinline__ NuSmem nu_carve(unsigned char* p, const TcShape& S) {
   NuSmem m;
   m.a1 = p; m.red = reinterpret_cast<float*>(p); p += tc_a1_bytes(S);
   m.w1 = p; p += tc_w1_bytes(S);
-  m.wl = p; p += tc_wl_bytes(S);
+  m.wl = p; p += nu_wl_bytes(S);
   m.wlT = p; p += nu_wlT_bytes(S);
   m.w1T = p; p += nu_w1T_bytes(S);
   m.bl = reinterpret_cast<float*>(p); p += (size_t)S.Lc * S.N2p * 4;
@@ -283,10 +297,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) neutra_unwind_tc_kernel(const _
 
   // ---- prologue -----------------------------------------------------------------------------------------------------------
   if (tid == 0) {
-    const int full[] = {kNuBarA1, kNuBarHid, kNuBarDu, kNuBarDpre, kNuBarXRead, kNuBarGOut};
+    const int full[] = {kNuBarA1, kNuBarHid, kNuBarDu, kNuBarDpre, kNuBarXRead, kNuBarGOut, kNuBarPZOut};
     for (int i = 0; i < kNuNumBars; ++i) {
       bool wide = false;
-      for (int j = 0; j < 6; ++j) wide = wide || (full[j] == i);
+      for (int j = 0; j < 7; ++j) wide = wide || (full[j] == i);
       mbar_init(bar(i), wide ? kTcEpiThreads : 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -333,6 +347,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) neutra_unwind_tc_kernel(const _
   if ((long long)blockIdx.x < tiles) my_tiles = (tiles - 1 - blockIdx.x) / gridDim.x + 1;
   const uint32_t total_uses = (uint32_t)(my_tiles * Lc);
   const size_t cbT = (size_t)S.N2p * Hp * 2 + nu_w1T_bytes(S);
+  const bool fused = A.p != nullptr;
 
   if (warp >= kTcEpiWarps) {
     reg_dealloc<kTcRegsService>();
@@ -427,7 +442,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) neutra_unwind_tc_kernel(const _
           if (u > 0) mbar_wait(bar(kNuBarG1), prev);
           mbar_expect_tx(bar(kNuBarW1), b1);
           tma_bulk_load(smem_u32(sm.w1), w, b1, bar(kNuBarW1));
-          if (u > 0) mbar_wait(bar(kNuBarG2), prev);
+          if (u > 0) {
+            if (l == 0 && fused) mbar_wait(bar(kNuBarBufFree), (uint32_t)((u / (uint32_t)Lc - 1) & 1));   // the buffer held the z tile
+            else mbar_wait(bar(kNuBarG2), prev);
+          }
           mbar_expect_tx(bar(kNuBarWl), b2);
           tma_bulk_load(smem_u32(sm.wl), w + b1, b2, bar(kNuBarWl));
           if (l == 0) mbar_wait(bar(kNuBarXRead), (uint32_t)((u / (uint32_t)Lc) & 1));   // the buffer still holds the x tile
@@ -447,11 +465,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) neutra_unwind_tc_kernel(const _
           long long rows = A.n - tile * kTcRows;
           if (rows > kTcRows) rows = kTcRows;
           const uint32_t bytes = (uint32_t)(rows * d * 4);
+          const long long off = tile * kTcRows * (long long)d;
           mbar_expect_tx(bar(kNuBarXFull), bytes);
-          tma_bulk_load(smem_u32(sm.wlT), A.x + tile * kTcRows * (long long)d, bytes, bar(kNuBarXFull));
-          mbar_wait(bar(kNuBarGOut), (uint32_t)(p & 1));
-          tma_bulk_store(A.grad + tile * kTcRows * (long long)d, smem_u32(sm.wlT), bytes);
-          tma_store_wait_read<0>();
+          tma_bulk_load(smem_u32(sm.wlT), A.x + off, bytes, bar(kNuBarXFull));
+          if (fused) {
+            // the momentum tile (and the latent tile, if it drifts) arrive under the last coupling: z into the Wl' buffer once
+            // its last GEMM 2 has completed, p into the Wl'^T buffer once its last GEMM 3 has
+            // (this lane follows the GEMM barriers phase by phase: a parity wait cannot tell phases two apart)
+            mbar_expect_tx(bar(kNuBarPZFull), A.drift ? 2 * bytes : bytes);
+            for (int l = 0; l < Lc; ++l) {
+              const uint32_t par = (uint32_t)((p * Lc + l) & 1);
+              mbar_wait(bar(kNuBarG2), par);
+              if (l == Lc - 1 && A.drift) tma_bulk_load(smem_u32(sm.wl), A.zw + off, bytes, bar(kNuBarPZFull));
+              mbar_wait(bar(kNuBarG3), par);
+            }
+            tma_bulk_load(smem_u32(sm.wlT), A.p + off, bytes, bar(kNuBarPZFull));
+            mbar_wait(bar(kNuBarPZOut), (uint32_t)(p & 1));
+            tma_bulk_store(A.p + off, smem_u32(sm.wlT), bytes);
+            if (A.drift) tma_bulk_store(A.zw + off, smem_u32(sm.wl), bytes);
+            tma_store_wait_read<0>();
+            mbar_arrive(bar(kNuBarBufFree));
+          } else {
+            mbar_wait(bar(kNuBarGOut), (uint32_t)(p & 1));
+            tma_bulk_store(A.grad + off, smem_u32(sm.wlT), bytes);
+            tma_store_wait_read<0>();
+          }
         }
         tma_store_wait_all();
       }
@@ -531,11 +569,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) neutra_unwind_tc_kernel(const _
         nu_affine_unwind(sm.aff4, l + 1, e0, st[0], st[1], gr[0], gr[1]);
         use += 1;
       }
-      // ---- dU~/dz leaves through the tile buffer (logical order: flipped when Lc is odd) ------------------------------------------
-      tc_row_write_half<0>(tile_row, d, da, e0, flip, gr[0]);
-      tc_row_write_half<1>(tile_row, d, da, e0, flip, gr[1]);
-      fence_async_smem();
-      mbar_arrive(bar(kNuBarGOut));
+      if (fused) {
+        // ---- leapfrog update in place on the staged momentum / latent tiles (logical order: flipped when Lc is odd) -----------
+        float* zrow = reinterpret_cast<float*>(sm.wl) + (size_t)r * d;
+        mbar_wait(bar(kNuBarPZFull), (uint32_t)(p & 1));
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float pv[kTcOwn], zv[kTcOwn];
+          if (half == 0) tc_row_read_half<0>(tile_row, d, da, e0, flip, pv); else tc_row_read_half<1>(tile_row, d, da, e0, flip, pv);
+          if (A.drift) { if (half == 0) tc_row_read_half<0>(zrow, d, da, e0, flip, zv); else tc_row_read_half<1>(zrow, d, da, e0, flip, zv); }
+#pragma unroll
+          for (int i = 0; i < kTcOwn; ++i) {
+            const float gv = gr[half][i];
+            float v = fmaf(-A.half_tau, gv, pv[i]);                                   // hmc.py:51-53
+            if (A.kicks == 2) v = fmaf(-A.half_tau, gv, v);
+            pv[i] = v;
+            if (A.drift) {                                                            // hmc.py:56-58
+              const int pos = half * da + e0 + i;
+              const float m = (A.imd && e0 + i < da) ? __ldg(A.imd + (flip ? d - 1 - pos : pos)) : 1.f;
+              zv[i] = fmaf(A.tau, A.imd ? v * m : v, zv[i]);
+            }
+          }
+          if (half == 0) tc_row_write_half<0>(tile_row, d, da, e0, flip, pv); else tc_row_write_half<1>(tile_row, d, da, e0, flip, pv);
+          if (A.drift) { if (half == 0) tc_row_write_half<0>(zrow, d, da, e0, flip, zv); else tc_row_write_half<1>(zrow, d, da, e0, flip, zv); }
+        }
+        fence_async_smem();
+        mbar_arrive(bar(kNuBarPZOut));
+      } else {
+        // ---- dU~/dz leaves through the tile buffer (logical order: flipped when Lc is odd) ----------------------------------------
+        tc_row_write_half<0>(tile_row, d, da, e0, flip, gr[0]);
+        tc_row_write_half<1>(tile_row, d, da, e0, flip, gr[1]);
+        fence_async_smem();
+        mbar_arrive(bar(kNuBarGOut));
+      }
     }
   }
   tc_fence_before();
@@ -560,21 +626,6 @@ __global__ void neutra_tc_init_kernel(const float* __restrict__ xi, const float*
     }
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) kin0[row] = 0.5f * s;
-  }
-}
-// kicks x (p <- p - tau/2 g), then optionally the drift z <- z + tau (p m)   (hmc.py:51-58)
-__global__ void neutra_tc_leap_kernel(float* __restrict__ p, float* __restrict__ z, const float* __restrict__ g, const float* __restrict__ imd,
-                                      float half_tau, float tau, int kicks, int drift, long long count, int d) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
-    float pv = p[i];
-    const float gv = __ldg(g + i);
-    pv = fmaf(-half_tau, gv, pv);
-    if (kicks == 2) pv = fmaf(-half_tau, gv, pv);
-    p[i] = pv;
-    if (drift) {
-      const float m = imd ? __ldg(imd + (int)(i % d)) : 1.f;
-      z[i] = fmaf(tau, imd ? pv * m : pv, z[i]);
-    }
   }
 }
 // accept test (hmc.py:107-113), masked overwrite (mcmc/base.py:77), moments and counters of the post-accept state, sink
@@ -662,30 +713,43 @@ extern "C" int64_t nfmc_neutra_tc_transposed_bytes(int32_t d, int32_t n_coupling
 }
 
 extern "C" int64_t nfmc_neutra_tc_workspace_bytes(int32_t d, int64_t n) {
-  return (int64_t)(4 * al256((size_t)n * d * 4) + 6 * al256((size_t)n * 4));
+  return (int64_t)(3 * al256((size_t)n * d * 4) + 6 * al256((size_t)n * 4));
+}
+
+// inverse pass (z -> x, log|det|) followed by the unwind kernel; A carries the output mode (gradient tile or fused leapfrog)
+static int nu_value_grad(const nfmc_potential* pot, const nfmc_realnvp_tc* flow, const void* blob_t, NuArgs& A, const float* z, float* x,
+                         float* ld, float* u, int64_t n, void* stream) {
+  if (int e = nfmc_flow_tc_pass(flow, 1, z, x, ld, n, stream)) return e;
+  A.blob = static_cast<const unsigned char*>(flow->blob);
+  A.blobT = static_cast<const unsigned char*>(blob_t);
+  A.pot_kind = pot->kind; A.pot = pot_params(pot);
+  A.x = x; A.ld_inv = ld; A.value = u; A.n = n;
+  const size_t smem = nu_smem_total(A.S);
+  const long long tiles = (n + kTcRows - 1) / kTcRows;
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    if (int e = check_cuda(cudaFuncSetAttribute(neutra_unwind_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "neutra_unwind_tc_kernel attribute")) return e;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  neutra_unwind_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(A);
+  return check_cuda(cudaGetLastError(), "neutra_unwind_tc_kernel launch");
 }
 
 // U~(z) and dU~/dz on the tensor cores (x [n, d] and ld [n] are scratch outputs: x = T^-1(z), log|det dx/dz|)
 extern "C" int nfmc_neutra_potential_tc(const nfmc_potential* pot, const nfmc_realnvp_tc* flow, const void* blob_t, int64_t blob_t_bytes,
                                         const float* z, float* x, float* ld, float* u, float* grad, int64_t n, void* stream) {
   if (int e = validate_pot(pot)) return e;
-  NuArgs A;
+  NuArgs A{};
   if (int e = nu_shape(flow, blob_t, blob_t_bytes, A.S, "neutra_potential_tc")) return e;
   if (pot->d != flow->d) return set_error("neutra_potential_tc: potential and flow event sizes differ");
   if (!z || !x || !ld || !u || !grad || n < 1) return set_error("neutra_potential_tc: bad arguments");
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(grad) & 15))
     return set_error("neutra_potential_tc: x / grad must be 16-byte aligned");
-  if (int e = nfmc_flow_tc_pass(flow, 1, z, x, ld, n, stream)) return e;
-  A.blob = static_cast<const unsigned char*>(flow->blob);
-  A.blobT = static_cast<const unsigned char*>(blob_t);
-  A.pot_kind = pot->kind; A.pot = pot_params(pot);
-  A.x = x; A.ld_inv = ld; A.grad = grad; A.value = u; A.n = n;
-  const size_t smem = nu_smem_total(A.S);
-  const long long tiles = (n + kTcRows - 1) / kTcRows;
-  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  cudaFuncSetAttribute(neutra_unwind_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  neutra_unwind_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(A);
-  return check_cuda(cudaGetLastError(), "neutra_unwind_tc_kernel launch");
+  A.grad = grad;
+  return nu_value_grad(pot, flow, blob_t, A, z, x, ld, u, n, stream);
 }
 
 // T NeuTra-HMC iterations on the tensor-core path (same contract as nfmc_neutra_hmc_steps; z in logical order).
@@ -698,7 +762,9 @@ extern "C" int nfmc_neutra_hmc_steps_tc(const nfmc_potential* pot, const nfmc_re
   if ((rng->normals == nullptr) != (rng->uniforms == nullptr) && adjusted)
     return set_error("neutra_hmc_steps_tc: inject both normals and uniforms, or neither");
   TcShape S;
+  if (int e = validate_pot(pot)) return e;
   if (int e = nu_shape(flow, blob_t, blob_t_bytes, S, "neutra_hmc_steps_tc")) return e;
+  if (pot->d != flow->d) return set_error("neutra_hmc_steps_tc: potential and flow event sizes differ");
   const int d = flow->d;
   if (!workspace || workspace_bytes < nfmc_neutra_tc_workspace_bytes(d, n)) return set_error("neutra_hmc_steps_tc: workspace too small");
   cudaStream_t s = (cudaStream_t)stream;
@@ -707,13 +773,11 @@ extern "C" int nfmc_neutra_hmc_steps_tc(const nfmc_potential* pot, const nfmc_re
   float* p = reinterpret_cast<float*>(w);
   float* zw = reinterpret_cast<float*>(w + nd);
   float* x = reinterpret_cast<float*>(w + 2 * nd);
-  float* g = reinterpret_cast<float*>(w + 3 * nd);
-  float* ld = reinterpret_cast<float*>(w + 4 * nd);
-  float* u0 = reinterpret_cast<float*>(w + 4 * nd + nn);
-  float* u1 = reinterpret_cast<float*>(w + 4 * nd + 2 * nn);
-  float* kin0 = reinterpret_cast<float*>(w + 4 * nd + 3 * nn);
-  float* unif = reinterpret_cast<float*>(w + 4 * nd + 4 * nn);
-  const int ew_grid = (int)std::min<long long>(((long long)n * d + 255) / 256, 16ll * sm_count());
+  float* ld = reinterpret_cast<float*>(w + 3 * nd);
+  float* u0 = reinterpret_cast<float*>(w + 3 * nd + nn);
+  float* u1 = reinterpret_cast<float*>(w + 3 * nd + 2 * nn);
+  float* kin0 = reinterpret_cast<float*>(w + 3 * nd + 3 * nn);
+  float* unif = reinterpret_cast<float*>(w + 3 * nd + 4 * nn);
   const int row_grid = (int)std::min<long long>((n + 7) / 8, 8ll * sm_count());
   const float half_tau = step_size / 2;
   const StatsArgs st{stats ? stats->sum_x : nullptr, stats ? stats->sum_x2 : nullptr, stats ? stats->counts : nullptr};
@@ -726,15 +790,19 @@ extern "C" int nfmc_neutra_hmc_steps_tc(const nfmc_potential* pot, const nfmc_re
     } else {
       nfmc_rng r2 = *rng;
       r2.step0 = rng->step0 + (uint64_t)k;
-      if (int e = nfmc_rng_fill(&r2, 0, chain0, d, n, 1, g, unif, stream)) return e;     // g is free until the first gradient
-      xi = g; uu = unif;
+      if (int e = nfmc_rng_fill(&r2, 0, chain0, d, n, 1, x, unif, stream)) return e;     // x is free until the first inverse pass
+      xi = x; uu = unif;
     }
     neutra_tc_init_kernel<<<row_grid, 256, 0, s>>>(xi, inv_mass_diag, z, p, zw, kin0, n, d);
     for (int l = 0; l <= n_leapfrog; ++l) {
-      if (int e = nfmc_neutra_potential_tc(pot, flow, blob_t, blob_t_bytes, zw, x, ld, l == 0 ? u0 : u1, g, n, stream)) return e;
-      const int kicks = (l == 0 || l == n_leapfrog) ? 1 : 2;
-      neutra_tc_leap_kernel<<<ew_grid, 256, 0, s>>>(p, zw, g, inv_mass_diag, half_tau, step_size, kicks, l < n_leapfrog ? 1 : 0,
-                                                    (long long)n * d, d);
+      // gradient at the current point with the leapfrog update fused into the kernel's output stage: one half-kick at the two
+      // ends of the trajectory, two in between (consecutive half-kicks of hmc.py:68-71 share the gradient), then the drift
+      NuArgs A{};
+      A.S = S;
+      A.p = p; A.zw = zw; A.imd = inv_mass_diag; A.half_tau = half_tau; A.tau = step_size;
+      A.kicks = (l == 0 || l == n_leapfrog) ? 1 : 2;
+      A.drift = l < n_leapfrog ? 1 : 0;
+      if (int e = nu_value_grad(pot, flow, blob_t, A, zw, x, ld, l == 0 ? u0 : u1, n, stream)) return e;
     }
     float* sink_row = nullptr;
     if (sink && sink->samples) {
