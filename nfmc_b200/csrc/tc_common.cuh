@@ -157,15 +157,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// The suspend-time hint lets the hardware park a waiting warp (it wakes as soon as the phase completes) instead of having it
+// spin through try_wait / branch / yield: in the r02c profile of the flow kernel those three were 27 % of all issued
+// instructions, most of them from the service warps that share a scheduler with four epilogue warps each.
+constexpr uint32_t kMbarSuspendNs = 200000u;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   while (!done) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(kMbarSuspendNs)
         : "memory");
   }
 }
@@ -279,13 +283,16 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return __byte_perm(__float_as_uint(a) + 0x8000u, __float_as_uint(b) + 0x8000u, 0x7632);
 }
-// tanh of two values at once, straight in the bf16 the next GEMM consumes: one MUFU op per pair
-__device__ __forceinline__ uint32_t tanh_bf16x2(float a, float b) {
-  uint32_t y;
-  const uint32_t p = pack_bf16(a, b);
-  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(p));
+// tanh of two values, packed as the bf16 pair the next GEMM consumes.  tanh.approx.bf16x2 looks like one operation per
+// pair but compiles to pack (2 VIADD + PRMT), MUFU.TANH.BF16 on each half and a PRMT to re-pack (SASS of the r02c build):
+// six instructions.  Taking tanh.approx.f32 of the unrounded values and packing the results costs five, and the
+// activation sees the fp32 pre-activation instead of its bf16 rounding.
+__device__ __forceinline__ float tanh_f32(float v) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(v));
   return y;
 }
+__device__ __forceinline__ uint32_t tanh_bf16x2(float a, float b) { return pack_bf16(tanh_f32(a), tanh_f32(b)); }
 __device__ __forceinline__ float fast_ex2(float v) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));

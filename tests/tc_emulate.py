@@ -67,7 +67,7 @@ def run_pass(blob_u8, d, Lc, Hp, x, inverse: bool):
         a1[:, da + 1] = 1.0
         w1m = w1.permute(1, 0, 2).reshape(Hp, k1)              # [h][k]
         hpre = a1 @ w1m.t()
-        hid = _bf16(torch.tanh(_bf16(hpre)))
+        hid = _bf16(torch.tanh(hpre))                           # tanh.approx.f32 of the fp32 accumulator, then bf16
         # GEMM 2 in the kernel's K-step order: step s multiplies hidden units [8s,8s+8) with k-group s of the image and
         # [Hp/2+8s, ...) with k-group s + Hp/16
         u = torch.zeros(n, n2p)
