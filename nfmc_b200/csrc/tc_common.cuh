@@ -20,6 +20,10 @@ constexpr int kTcRegion = 256;               // TMEM columns per tile
 constexpr int kTcUCol = 128;                 // column of the U accumulator inside a tile's region
 constexpr int kTcMaxSlots = 16;              // weight buffers per image kind (resident mode: one per coupling)
 constexpr float kLog2e = 1.4426950408889634f;
+#ifndef NFMC_TC_TANH_MUFU_HI
+#define NFMC_TC_TANH_MUFU_HI 2
+#endif
+constexpr int kTcTanhMufuPairsHi = NFMC_TC_TANH_MUFU_HI;   // of a K-step's 8 pairs, 4 + this many go through MUFU.TANH, the rest through the FMA pipe
 
 // Packed flow shape + shared-memory plan.
 //   nb1 / nbl: number of shared-memory buffers for the W1 / Wl images; == Lc means every coupling's image stays resident
@@ -293,6 +297,28 @@ __device__ __forceinline__ float tanh_f32(float v) {
   return y;
 }
 __device__ __forceinline__ uint32_t tanh_bf16x2(float a, float b) { return pack_bf16(tanh_f32(a), tanh_f32(b)); }
+// The same pair on the FMA pipe: tanh(x) ~ xc * P(xc^2), xc = clamp(x, +-3.75), P of degree 8 (minimax in RELATIVE error:
+// 9.5e-4 everywhere, half of bf16's rounding step), evaluated for both values at once with packed FFMA2.  Epilogue 1 is
+// bound by the MUFU unit (16 results per clock and SM: 2 048 cycles for the 128 x 256 tanh of a tile at H = 256), so
+// some pairs take this route and the two pipes work side by side.  Measured (d = 100, Lc = 4, H = 256, forward pass, ms): all
+// MUFU 0.639, 2 of 8 pairs here 0.631 (log_prob 0.612 -> 0.592), 3 of 8 0.670, 4 of 8 0.719 -- the route costs 17 issue slots
+// per pair against 5, and issue slots are the scarcer resource; 2 of 8 is the default.
+__device__ __forceinline__ uint32_t tanh_poly_bf16x2(float a, float b) {
+  const float c = 3.75f;
+  const float2 x = make_float2(fminf(fmaxf(a, -c), c), fminf(fmaxf(b, -c), c));
+  const float2 t = mul2(x, x);
+  float2 p = splat2(1.816051865e-08f);
+  p = fma2(p, t, splat2(-1.175949670e-06f));
+  p = fma2(p, t, splat2(3.218734409e-05f));
+  p = fma2(p, t, splat2(-4.870880060e-04f));
+  p = fma2(p, t, splat2(4.496934319e-03f));
+  p = fma2(p, t, splat2(-2.666925219e-02f));
+  p = fma2(p, t, splat2(1.070194904e-01f));
+  p = fma2(p, t, splat2(-3.221402460e-01f));
+  p = fma2(p, t, splat2(9.991282172e-01f));
+  const float2 y = mul2(x, p);
+  return pack_bf16(y.x, y.y);
+}
 __device__ __forceinline__ float fast_ex2(float v) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
@@ -867,7 +893,8 @@ __device__ __forceinline__ void tc_epi1_step(uint32_t dst, uint32_t (&a)[8], uin
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     p[i] = tanh_bf16x2(__uint_as_float(a[2 * i]), __uint_as_float(a[2 * i + 1]));
-    p[4 + i] = tanh_bf16x2(__uint_as_float(b[2 * i]), __uint_as_float(b[2 * i + 1]));
+    if (i < kTcTanhMufuPairsHi) p[4 + i] = tanh_bf16x2(__uint_as_float(b[2 * i]), __uint_as_float(b[2 * i + 1]));
+    else p[4 + i] = tanh_poly_bf16x2(__uint_as_float(b[2 * i]), __uint_as_float(b[2 * i + 1]));
   }
   tmem_st8(dst, p);
 }
