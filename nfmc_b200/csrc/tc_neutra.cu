@@ -39,6 +39,13 @@
 
 namespace nfmc {
 
+#ifdef NFMC_NU_TRACE
+__device__ long long* g_nu_trace = nullptr;   // [4096] {event id, clock} of epilogue thread 0 of CTA 0 (tools/nu_trace.py)
+#define NU_EV(id) do { if (tr_p && tr_n < 2000) { tr_p[2 * tr_n] = (id); tr_p[2 * tr_n + 1] = clock64(); ++tr_n; } } while (0)
+#else
+#define NU_EV(id)
+#endif
+
 constexpr int kNuColU = 256, kNuColDhHi = 384;
 enum { kNuBarA1 = 0, kNuBarG1, kNuBarHid, kNuBarG2, kNuBarDu, kNuBarG3, kNuBarDpre, kNuBarG4, kNuBarW1, kNuBarWl, kNuBarWlT,
        kNuBarW1T, kNuBarXFull, kNuBarXRead, kNuBarGOut, kNuBarPZFull, kNuBarPZOut, kNuBarBufFree, kNuNumBars };
@@ -66,7 +73,7 @@ struct NuSmem {
   unsigned char *a1, *w1, *wl, *wlT, *w1T;
   float* bl;
   float4* aff4;
-  float* red;          // aliases the A1 image (used between tiles only)
+  float* red;          // [2][6][128] row scratch of the potential (two sets, alternating by tile)
   uint64_t* bars;
   uint32_t* tmem_slot;
 };
@@ -82,17 +89,18 @@ __host__ __device__ inline size_t nu_wl_bytes(const TcShape& S) {
 }
 __host__ __device__ inline size_t nu_smem_total(const TcShape& S) {
   return tc_a1_bytes(S) + tc_w1_bytes(S) + nu_wl_bytes(S) + nu_wlT_bytes(S) + nu_w1T_bytes(S) + (size_t)S.Lc * S.N2p * 4 + tc_aff4_bytes(S) +
-         (size_t)kNuNumBars * 8 + 16;
+         (size_t)2 * 6 * kTcRows * 4 + (size_t)kNuNumBars * 8 + 16;
 }
 __device__ __forceinline__ NuSmem nu_carve(unsigned char* p, const TcShape& S) {
   NuSmem m;
-  m.a1 = p; m.red = reinterpret_cast<float*>(p); p += tc_a1_bytes(S);
+  m.a1 = p; p += tc_a1_bytes(S);
   m.w1 = p; p += tc_w1_bytes(S);
   m.wl = p; p += nu_wl_bytes(S);
   m.wlT = p; p += nu_wlT_bytes(S);
   m.w1T = p; p += nu_w1T_bytes(S);
   m.bl = reinterpret_cast<float*>(p); p += (size_t)S.Lc * S.N2p * 4;
   m.aff4 = reinterpret_cast<float4*>(p); p += tc_aff4_bytes(S);
+  m.red = reinterpret_cast<float*>(p); p += (size_t)2 * 6 * kTcRows * 4;
   m.bars = reinterpret_cast<uint64_t*>(p);
   m.tmem_slot = reinterpret_cast<uint32_t*>(p + (size_t)kNuNumBars * 8);
   return m;
@@ -439,20 +447,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) neutra_unwind_tc_kernel(const _
           const uint32_t prev = (u - 1) & 1;
           const unsigned char* w = wblob + (size_t)l * cb;
           const unsigned char* wT = A.blobT + (size_t)l * cbT;
-          if (u > 0) mbar_wait(bar(kNuBarG1), prev);
+          if (u > 0) mbar_wait_relaxed(bar(kNuBarG1), prev);
           mbar_expect_tx(bar(kNuBarW1), b1);
           tma_bulk_load(smem_u32(sm.w1), w, b1, bar(kNuBarW1));
           if (u > 0) {
-            if (l == 0 && fused) mbar_wait(bar(kNuBarBufFree), (uint32_t)((u / (uint32_t)Lc - 1) & 1));   // the buffer held the z tile
-            else mbar_wait(bar(kNuBarG2), prev);
+            if (l == 0 && fused) mbar_wait_relaxed(bar(kNuBarBufFree), (uint32_t)((u / (uint32_t)Lc - 1) & 1));   // the buffer held the z tile
+            else mbar_wait_relaxed(bar(kNuBarG2), prev);
           }
           mbar_expect_tx(bar(kNuBarWl), b2);
           tma_bulk_load(smem_u32(sm.wl), w + b1, b2, bar(kNuBarWl));
-          if (l == 0) mbar_wait(bar(kNuBarXRead), (uint32_t)((u / (uint32_t)Lc) & 1));   // the buffer still holds the x tile
-          else mbar_wait(bar(kNuBarG3), prev);
+          if (l == 0) mbar_wait_relaxed(bar(kNuBarXRead), (uint32_t)((u / (uint32_t)Lc) & 1));   // the buffer still holds the x tile
+          else mbar_wait_relaxed(bar(kNuBarG3), prev);
           mbar_expect_tx(bar(kNuBarWlT), b3);
           tma_bulk_load(smem_u32(sm.wlT), wT, b3, bar(kNuBarWlT));
-          if (u > 0) mbar_wait(bar(kNuBarG4), prev);
+          if (u > 0) mbar_wait_relaxed(bar(kNuBarG4), prev);
           mbar_expect_tx(bar(kNuBarW1T), b4);
           tma_bulk_load(smem_u32(sm.w1T), wT + b3, b4, bar(kNuBarW1T));
         }
@@ -466,8 +474,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) neutra_unwind_tc_kernel(const _
           if (rows > kTcRows) rows = kTcRows;
           const uint32_t bytes = (uint32_t)(rows * d * 4);
           const long long off = tile * kTcRows * (long long)d;
-          mbar_expect_tx(bar(kNuBarXFull), bytes);
-          tma_bulk_load(smem_u32(sm.wlT), A.x + off, bytes, bar(kNuBarXFull));
+          if (!fused || p == 0) {             // fused mode: later tiles are requested at the end of the previous iteration
+            mbar_expect_tx(bar(kNuBarXFull), bytes);
+            tma_bulk_load(smem_u32(sm.wlT), A.x + off, bytes, bar(kNuBarXFull));
+          }
           if (fused) {
             // the momentum tile (and the latent tile, if it drifts) arrive under the last coupling: z into the Wl' buffer once
             // its last GEMM 2 has completed, p into the Wl'^T buffer once its last GEMM 3 has
@@ -475,18 +485,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) neutra_unwind_tc_kernel(const _
             mbar_expect_tx(bar(kNuBarPZFull), A.drift ? 2 * bytes : bytes);
             for (int l = 0; l < Lc; ++l) {
               const uint32_t par = (uint32_t)((p * Lc + l) & 1);
-              mbar_wait(bar(kNuBarG2), par);
+              mbar_wait_relaxed(bar(kNuBarG2), par);
               if (l == Lc - 1 && A.drift) tma_bulk_load(smem_u32(sm.wl), A.zw + off, bytes, bar(kNuBarPZFull));
-              mbar_wait(bar(kNuBarG3), par);
+              mbar_wait_relaxed(bar(kNuBarG3), par);
             }
             tma_bulk_load(smem_u32(sm.wlT), A.p + off, bytes, bar(kNuBarPZFull));
-            mbar_wait(bar(kNuBarPZOut), (uint32_t)(p & 1));
+            mbar_wait_relaxed(bar(kNuBarPZOut), (uint32_t)(p & 1));
             tma_bulk_store(A.p + off, smem_u32(sm.wlT), bytes);
             if (A.drift) tma_bulk_store(A.zw + off, smem_u32(sm.wl), bytes);
+            // the next x tile goes into the Wl'^T buffer as soon as the momentum store (the OLDER bulk group) has read it
+            if (A.drift) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+            if (p + 1 < my_tiles) {
+              const long long tile2 = tile + gridDim.x;
+              long long rows2 = A.n - tile2 * kTcRows;
+              if (rows2 > kTcRows) rows2 = kTcRows;
+              const uint32_t bytes2 = (uint32_t)(rows2 * d * 4);
+              mbar_expect_tx(bar(kNuBarXFull), bytes2);
+              tma_bulk_load(smem_u32(sm.wlT), A.x + tile2 * kTcRows * (long long)d, bytes2, bar(kNuBarXFull));
+            }
             tma_store_wait_read<0>();
             mbar_arrive(bar(kNuBarBufFree));
           } else {
-            mbar_wait(bar(kNuBarGOut), (uint32_t)(p & 1));
+            mbar_wait_relaxed(bar(kNuBarGOut), (uint32_t)(p & 1));
             tma_bulk_store(A.grad + off, smem_u32(sm.wlT), bytes);
             tma_store_wait_read<0>();
           }
@@ -505,32 +525,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) neutra_unwind_tc_kernel(const _
     float* tile_row = reinterpret_cast<float*>(sm.wlT) + (size_t)r * d;
     uint32_t use = 0;
     float st[2][kTcOwn], gr[2][kTcOwn];
+#ifdef NFMC_NU_TRACE
+    long long* tr_p = (blockIdx.x == 0 && tid == 0) ? g_nu_trace : nullptr;
+    int tr_n = 0;
+#endif
 
     for (long long p = 0; p < my_tiles; ++p) {
       const long long tile = (long long)blockIdx.x + p * gridDim.x;
       const long long row_g = tile * kTcRows + r;
       // ---- x out of the tile buffer; U(x), grad U(x) -----------------------------------------------------------------------
-      mbar_wait(bar(kNuBarXFull), (uint32_t)(p & 1));
+      const float ld_inv_r = (g == 0 && row_g < A.n) ? __ldg(A.ld_inv + row_g) : 0.f;   // in flight while the tile lands
+      NU_EV(0);
+      mbar_wait_relaxed(bar(kNuBarXFull), (uint32_t)(p & 1));
+      NU_EV(1);
       tc_row_read_half<0>(tile_row, d, da, e0, false, st[0]);
       tc_row_read_half<1>(tile_row, d, da, e0, false, st[1]);
       mbar_arrive(bar(kNuBarXRead));
-      sm.red[g * kTcRows + r] = nu_pot_partial(A.pot_kind, A.pot, da, e0, st[0], st[1]);
+      float* red = sm.red + (size_t)(p & 1) * 6 * kTcRows;      // the other set may still be read by slower warps of the last tile
+      red[g * kTcRows + r] = nu_pot_partial(A.pot_kind, A.pot, da, e0, st[0], st[1]);
       if (g == 0) {
-        sm.red[4 * kTcRows + r] = st[0][0];
-        sm.red[5 * kTcRows + r] = da >= 2 ? st[0][1] : st[1][0];
+        red[4 * kTcRows + r] = st[0][0];
+        red[5 * kTcRows + r] = da >= 2 ? st[0][1] : st[1][0];
       }
       tc_epi_barrier();
-      float u_val;
       {
-        const float Ssum = sm.red[r] + sm.red[kTcRows + r] + sm.red[2 * kTcRows + r] + sm.red[3 * kTcRows + r];
-        u_val = nu_pot_value_grad(A.pot_kind, A.pot, d, da, e0, Ssum, sm.red[4 * kTcRows + r], sm.red[5 * kTcRows + r], st[0], st[1],
-                                  gr[0], gr[1]);
+        const float Ssum = red[r] + red[kTcRows + r] + red[2 * kTcRows + r] + red[3 * kTcRows + r];
+        const float u_val = nu_pot_value_grad(A.pot_kind, A.pot, d, da, e0, Ssum, red[4 * kTcRows + r], red[5 * kTcRows + r], st[0], st[1],
+                                              gr[0], gr[1]);
+        if (g == 0 && row_g < A.n) A.value[row_g] = u_val - ld_inv_r;                    // neutra.py:62-64
       }
-      if (g == 0 && row_g < A.n) A.value[row_g] = u_val - __ldg(A.ld_inv + row_g);     // neutra.py:62-64
-      tc_epi_barrier();                     // the scratch aliases the A1 image
-      // (the scratch only covers k-groups 0 and 1 of the image, which every coupling rewrites)
       // ---- backward sweep x -> z -----------------------------------------------------------------------------------------------
       nu_affine_unwind(sm.aff4, 0, e0, st[0], st[1], gr[0], gr[1]);
+      NU_EV(2);
 #pragma unroll 1
       for (int l = 0; l < Lc; ++l) {
         const uint32_t par = use & 1;
@@ -539,23 +565,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) neutra_unwind_tc_kernel(const _
         fence_async_smem();
         tc_fence_before();
         mbar_arrive(bar(kNuBarA1));
+        NU_EV(10);
         mbar_wait(bar(kNuBarG1), par);
+        NU_EV(11);
         tc_fence_after();
         tc_epi1(trow, Hp, g);
         tc_fence_before();
         mbar_arrive(bar(kNuBarHid));
+        NU_EV(12);
         mbar_wait(bar(kNuBarG2), par);
+        NU_EV(13);
         tc_fence_after();
         if (src) nu_epi2(trow + kNuColU, sm.bl + (size_t)l * S.N2p, S.N2p, g, da, st[0], gr[0]);
         else nu_epi2(trow + kNuColU, sm.bl + (size_t)l * S.N2p, S.N2p, g, da, st[1], gr[1]);
         tc_fence_before();
         mbar_arrive(bar(kNuBarDu));
+        NU_EV(14);
         mbar_wait(bar(kNuBarG3), par);
+        NU_EV(15);
         tc_fence_after();
         nu_epi3(trow, Hp, g);
         tc_fence_before();
         mbar_arrive(bar(kNuBarDpre));
+        NU_EV(16);
         mbar_wait(bar(kNuBarG4), par);
+        NU_EV(17);
         tc_fence_after();
         {
           uint32_t v[16];
@@ -567,34 +601,83 @@ __global__ void __launch_bounds__(kTcThreads, 1) neutra_unwind_tc_kernel(const _
         }
         tc_fence_before();
         nu_affine_unwind(sm.aff4, l + 1, e0, st[0], st[1], gr[0], gr[1]);
+        NU_EV(18);
         use += 1;
       }
       if (fused) {
         // ---- leapfrog update in place on the staged momentum / latent tiles (logical order: flipped when Lc is odd) -----------
         float* zrow = reinterpret_cast<float*>(sm.wl) + (size_t)r * d;
-        mbar_wait(bar(kNuBarPZFull), (uint32_t)(p & 1));
+        NU_EV(3);
+        mbar_wait_relaxed(bar(kNuBarPZFull), (uint32_t)(p & 1));
+        NU_EV(4);
+        // In place on the staged tiles, in 16-byte units where the row layout allows (d/2 is even, so elements come in valid pairs;
+        // the high half starts 8 bytes off a 16-byte boundary when d/2 % 4 == 2: pair, three quads, pair).  Shared-memory
+        // wavefronts are what this stage costs -- rows are 4 d bytes apart, so a warp-wide access is spread over 32 rows --
+        // and whole-row register arrays spilled to local memory (an L2 round trip at this carve-out): 16.7 k cycles per tile
+        // in the first r02 timeline, 10.4 k with 8-byte units.
+        auto unit2 = [&](int half, int c, float g0, float g1) {
+          const int k = e0 + 2 * c;
+          if (k >= da) return;
+          const int pos = half * da + k;
+          const int at = flip ? d - 2 - pos : pos;
+          float2 pv = *reinterpret_cast<const float2*>(tile_row + at);
+          float2 zv = A.drift ? *reinterpret_cast<const float2*>(zrow + at) : make_float2(0.f, 0.f);
+          if (flip) { pv = make_float2(pv.y, pv.x); zv = make_float2(zv.y, zv.x); }
+          pv.x = fmaf(-A.half_tau, g0, pv.x);                                       // hmc.py:51-53
+          pv.y = fmaf(-A.half_tau, g1, pv.y);
+          if (A.kicks == 2) { pv.x = fmaf(-A.half_tau, g0, pv.x); pv.y = fmaf(-A.half_tau, g1, pv.y); }
+          if (A.drift) {                                                            // hmc.py:56-58
+            float m0 = 1.f, m1 = 1.f;
+            if (A.imd) { m0 = __ldg(A.imd + (flip ? d - 1 - pos : pos)); m1 = __ldg(A.imd + (flip ? d - 2 - pos : pos + 1)); }
+            zv.x = fmaf(A.tau, A.imd ? pv.x * m0 : pv.x, zv.x);
+            zv.y = fmaf(A.tau, A.imd ? pv.y * m1 : pv.y, zv.y);
+          }
+          *reinterpret_cast<float2*>(tile_row + at) = flip ? make_float2(pv.y, pv.x) : pv;
+          if (A.drift) *reinterpret_cast<float2*>(zrow + at) = flip ? make_float2(zv.y, zv.x) : zv;
+        };
+        auto unit4 = [&](int half, int c, float g0, float g1, float g2, float g3) {       // unflipped, 16-byte aligned, c even / odd as planned
+          const int k = e0 + 2 * c;
+          if (k + 4 > da) { unit2(half, c, g0, g1); unit2(half, c + 1, g2, g3); return; }
+          const int at = half * da + k;
+          float4 pv = *reinterpret_cast<const float4*>(tile_row + at);
+          float4 zv = A.drift ? *reinterpret_cast<const float4*>(zrow + at) : make_float4(0.f, 0.f, 0.f, 0.f);
+          pv.x = fmaf(-A.half_tau, g0, pv.x); pv.y = fmaf(-A.half_tau, g1, pv.y);
+          pv.z = fmaf(-A.half_tau, g2, pv.z); pv.w = fmaf(-A.half_tau, g3, pv.w);
+          if (A.kicks == 2) {
+            pv.x = fmaf(-A.half_tau, g0, pv.x); pv.y = fmaf(-A.half_tau, g1, pv.y);
+            pv.z = fmaf(-A.half_tau, g2, pv.z); pv.w = fmaf(-A.half_tau, g3, pv.w);
+          }
+          if (A.drift) {
+            float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (A.imd) m = make_float4(__ldg(A.imd + at), __ldg(A.imd + at + 1), __ldg(A.imd + at + 2), __ldg(A.imd + at + 3));
+            zv.x = fmaf(A.tau, A.imd ? pv.x * m.x : pv.x, zv.x); zv.y = fmaf(A.tau, A.imd ? pv.y * m.y : pv.y, zv.y);
+            zv.z = fmaf(A.tau, A.imd ? pv.z * m.z : pv.z, zv.z); zv.w = fmaf(A.tau, A.imd ? pv.w * m.w : pv.w, zv.w);
+          }
+          *reinterpret_cast<float4*>(tile_row + at) = pv;
+          if (A.drift) *reinterpret_cast<float4*>(zrow + at) = zv;
+        };
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          float pv[kTcOwn], zv[kTcOwn];
-          if (half == 0) tc_row_read_half<0>(tile_row, d, da, e0, flip, pv); else tc_row_read_half<1>(tile_row, d, da, e0, flip, pv);
-          if (A.drift) { if (half == 0) tc_row_read_half<0>(zrow, d, da, e0, flip, zv); else tc_row_read_half<1>(zrow, d, da, e0, flip, zv); }
+          const float* gh = gr[half];
+          const bool shifted = half == 1 && (da & 2) != 0;     // this half starts 8 bytes off a 16-byte boundary
+          if (flip) {
 #pragma unroll
-          for (int i = 0; i < kTcOwn; ++i) {
-            const float gv = gr[half][i];
-            float v = fmaf(-A.half_tau, gv, pv[i]);                                   // hmc.py:51-53
-            if (A.kicks == 2) v = fmaf(-A.half_tau, gv, v);
-            pv[i] = v;
-            if (A.drift) {                                                            // hmc.py:56-58
-              const int pos = half * da + e0 + i;
-              const float m = (A.imd && e0 + i < da) ? __ldg(A.imd + (flip ? d - 1 - pos : pos)) : 1.f;
-              zv[i] = fmaf(A.tau, A.imd ? v * m : v, zv[i]);
-            }
+            for (int c = 0; c < kTcOwn / 2; ++c) unit2(half, c, gh[2 * c], gh[2 * c + 1]);
+          } else if (!shifted) {
+#pragma unroll
+            for (int c = 0; c < kTcOwn / 2; c += 2) { unit4(half, c, gh[2 * c], gh[2 * c + 1], gh[2 * c + 2], gh[2 * c + 3]); NU_EV(50 + c); }
+          } else {
+            unit2(half, 0, gh[0], gh[1]);
+#pragma unroll
+            for (int c = 1; c < kTcOwn / 2 - 1; c += 2) unit4(half, c, gh[2 * c], gh[2 * c + 1], gh[2 * c + 2], gh[2 * c + 3]);
+            unit2(half, kTcOwn / 2 - 1, gh[kTcOwn - 2], gh[kTcOwn - 1]);
           }
-          if (half == 0) tc_row_write_half<0>(tile_row, d, da, e0, flip, pv); else tc_row_write_half<1>(tile_row, d, da, e0, flip, pv);
-          if (A.drift) { if (half == 0) tc_row_write_half<0>(zrow, d, da, e0, flip, zv); else tc_row_write_half<1>(zrow, d, da, e0, flip, zv); }
+          NU_EV(42 + half);
         }
         fence_async_smem();
+        NU_EV(44);
         mbar_arrive(bar(kNuBarPZOut));
+        NU_EV(5);
       } else {
         // ---- dU~/dz leaves through the tile buffer (logical order: flipped when Lc is odd) ----------------------------------------
         tc_row_write_half<0>(tile_row, d, da, e0, flip, gr[0]);
@@ -705,6 +788,12 @@ int nu_shape(const nfmc_realnvp_tc* flow, const void* blobT, int64_t blobT_bytes
   return 0;
 }
 }  // namespace
+
+#ifdef NFMC_NU_TRACE
+extern "C" __attribute__((visibility("default"))) int nfmc_nu_trace_set(long long* buf) {
+  return (int)cudaMemcpyToSymbol(g_nu_trace, &buf, sizeof(buf));
+}
+#endif
 
 extern "C" int64_t nfmc_neutra_tc_transposed_bytes(int32_t d, int32_t n_coupling, int32_t hidden) {
   TcShape S;
