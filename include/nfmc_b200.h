@@ -228,6 +228,41 @@ NFMC_API int nfmc_tune_inv_mass(const double* sums, int32_t d, float imd_adjustm
 NFMC_API int nfmc_rng_fill(const nfmc_rng* rng, int32_t stream_id, int64_t chain0, int32_t d, int64_t n, int32_t n_steps,
                   float* normals, float* uniforms, void* stream);
 
+/* ---- external targets: the reference accepts ANY callable `target([n,*event]) -> [n]` and differentiates it with autograd
+ * (sample.py:34-36,65-66; mcmc/langevin.py:66-68; mcmc/hmc.py:40-48).  A callable cannot be fused into the step kernels, so for
+ * such targets the host evaluates U and grad U on the device (torch autograd) and these entry points do everything else:
+ * proposal, proposal potentials, leapfrog updates, Hamiltonians, log-ratio, accept, masked overwrite, moments, counters,
+ * sample sink.  All pointers are device memory, row-major fp32; noise / uniforms are explicit (nfmc_rng_fill draws the
+ * Philox numbers the fused kernels would use). ---------------------------------------------------------------------- */
+/* x' = x - tau/m^2 grad + sqrt(2 tau)/m noise (langevin.py:74-76); random_walk=1: x' = x + m noise (mh.py:52-56, grad unused) */
+NFMC_API int nfmc_ext_langevin_propose(const float* x, const float* grad, const float* noise, const float* inv_mass_diag,
+                              float step_size, int32_t random_walk, int64_t n, int32_t d, float* x_prime, void* stream);
+/* log_ratio [n] = (-U') - (-U) + (-q(x|x')) - (-q(x'|x)) with both proposal potentials as langevin.py:31-42 (util.py:392);
+ * random_walk=1: (-U') - (-U) (mh.py:59) */
+NFMC_API int nfmc_ext_langevin_log_ratio(const float* x, const float* x_prime, const float* grad, const float* grad_prime,
+                                const float* u, const float* u_prime, const float* inv_mass_diag, float step_size,
+                                int32_t random_walk, int64_t n, int32_t d, float* log_ratio, void* stream);
+/* p = noise / sqrt(m), kinetic [n] = sum p^2 m (hmc.py:100,104) */
+NFMC_API int nfmc_ext_hmc_momentum(const float* noise, const float* inv_mass_diag, int64_t n, int32_t d, float* p, float* kinetic,
+                          void* stream);
+/* `kicks` (0..2) half-kicks p -= tau/2 grad (hmc.py:51-53), then, if drift, x += tau m p (hmc.py:56-58) */
+NFMC_API int nfmc_ext_hmc_leapfrog(float* x, float* p, const float* grad, const float* inv_mass_diag, float step_size,
+                          int32_t kicks, int32_t drift, int64_t n, int32_t d, void* stream);
+/* log_ratio [n] = -(U1 + 1/2 sum p^2 m) + (U0 + 1/2 kinetic0) (hmc.py:103-111) */
+NFMC_API int nfmc_ext_hmc_log_ratio(const float* p, const float* inv_mass_diag, const float* u0, const float* kinetic0,
+                           const float* u1, int64_t n, int32_t d, float* log_ratio, void* stream);
+/* log_ratio [n] = (-U') - (-U) + log q(x) - log q(x') (jump.py:224-229, imh.py:226-231) */
+NFMC_API int nfmc_ext_jump_log_ratio(const float* u, const float* u_prime, const float* log_q, const float* log_q_prime, int64_t n,
+                            float* log_ratio, void* stream);
+/* accept iff log(uniforms) < log_ratio (adjusted=0: always); x[mask] = x'[mask] (mcmc/base.py:77) together with up to three
+ * caches that travel with the state (aux_a, aux_b: [n]; aux_grad: [n,d]; NULL pairs are skipped); moments of the post-accept
+ * state and counters into `stats` (counts[1] += n); the post-accept state goes to the sink row of step `sink_step` if the
+ * thinning rule keeps it */
+NFMC_API int nfmc_ext_accept(float* x, const float* x_prime, const float* log_ratio, const float* uniforms, int32_t adjusted,
+                    int64_t n, int32_t d, float* aux_a, const float* aux_a_prime, float* aux_b, const float* aux_b_prime,
+                    float* aux_grad, const float* aux_grad_prime, const nfmc_stats* stats, const nfmc_sink* sink,
+                    int32_t sink_step, void* stream);
+
 /* ---- flow training on the device (register-resident conditioner path: n_linear = 2, hidden <= 8) -----------------
  * Replaces the autograd + AdamW loop behind flow.fit (nfmc/jump.py:139-151,201; nfmc/imh.py:171-175) and
  * flow.variational_fit (nfmc/imh.py:67-72; nfmc/neutra.py:84-91); torchflows itself is absent, its optimiser settings

@@ -110,6 +110,14 @@ SIGNATURES = {
     "nfmc_flow_wide_fit_epoch": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64,
                                            _f32, _f32, _f32, _f32, _f32, _i32, _vp]),
     "nfmc_rng_fill": (C.c_int, [P(RngDesc), _i32, _i64, _i32, _i64, _i32, _vp, _vp, _vp]),
+    "nfmc_ext_langevin_propose": (C.c_int, [_vp, _vp, _vp, _vp, _f32, _i32, _i64, _i32, _vp, _vp]),
+    "nfmc_ext_langevin_log_ratio": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i32, _i64, _i32, _vp, _vp]),
+    "nfmc_ext_hmc_momentum": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "nfmc_ext_hmc_leapfrog": (C.c_int, [_vp, _vp, _vp, _vp, _f32, _i32, _i32, _i64, _i32, _vp]),
+    "nfmc_ext_hmc_log_ratio": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "nfmc_ext_jump_log_ratio": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "nfmc_ext_accept": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, P(StatsDesc), P(SinkDesc),
+                                  _i32, _vp]),
     "nfmc_potential_step": (C.c_int, [P(PotentialDesc), _vp, _i64, _f32, _vp]),
     "nfmc_dlmc_update": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _vp, _i64, _f32, _vp]),
     "nfmc_dlmc_latent_update": (C.c_int, [_vp, _vp, _f32, _i64, _vp]),

@@ -1,10 +1,12 @@
 """Built-in analytic target potentials (negative log densities) with closed-form gradients on the device.
 
 The reference accepts any Python callable and differentiates it with autograd
-(/root/reference/nfmc/algorithms/sampling/mcmc/langevin.py:66-68, mcmc/hmc.py:40-48).  The B200 path fuses
-U and grad U into the sampler kernels, so a target must be one of the potentials below (they mirror
+(/root/reference/nfmc/algorithms/sampling/mcmc/langevin.py:66-68, mcmc/hmc.py:40-48).  The fast B200 path fuses
+U and grad U into the sampler kernels, which needs one of the potentials below (they mirror
 ``potentials.base.Potential``: an object with ``event_shape`` that maps ``[n, *event] -> [n]``).  Calling a
-potential evaluates it with the CUDA kernel ``nfmc_potential_eval``; there is no CPU path.
+potential evaluates it with the CUDA kernel ``nfmc_potential_eval``; there is no CPU path.  Any other callable becomes a
+``CallablePotential`` (bottom of this file): autograd supplies U / grad U on the device and the ``nfmc_ext_*`` kernels do
+the sampler arithmetic around it.
 
 ========================  =====================================================================================
 ``StandardGaussian``      ``sum(x**2)`` -- the README / test target (README.md:45-46, test/util.py:4-5)
@@ -179,13 +181,65 @@ def make_potential(name: str, event_shape) -> Potential:
     return table[name](event_shape)
 
 
+class CallablePotential(Potential):
+    """Any Python callable ``[n, *event] -> [n]`` -- the reference's target contract (sample.py:34-36; the README's
+    ``lambda x: torch.sum(x ** 2, dim=1)``).  It cannot be fused into the step kernels, so the samplers take their
+    *external-target* path for it: U and grad U are evaluated on the device by calling the function under torch autograd
+    (exactly what the reference does: mcmc/langevin.py:66-68, mcmc/hmc.py:40-48), and the ``nfmc_ext_*`` kernels
+    (csrc/ext_kernels.cu) do the rest of every step.  The function must be written in torch operations that run on CUDA
+    tensors."""
+    kind = -1
+    external = True
+
+    def __init__(self, fn, event_shape):
+        super().__init__(event_shape)
+        if not callable(fn):
+            raise TypeError("target must be callable")
+        self.fn = fn
+
+    def descriptor(self, device):
+        raise N.NativeError("a callable target has no fused-kernel descriptor; samplers use the external-target path for it")
+
+    def _rows(self, x: torch.Tensor) -> torch.Tensor:
+        return x.reshape(-1, *self.event_shape)
+
+    def _check(self, u: torch.Tensor, n: int) -> torch.Tensor:
+        if not torch.is_tensor(u) or u.numel() != n:
+            raise ValueError(f"target must map [n, *event_shape] to [n]; got {tuple(getattr(u, 'shape', ()))} for n = {n}")
+        return u.reshape(n)
+
+    def value(self, x: torch.Tensor) -> torch.Tensor:
+        """U(x) as a contiguous fp32 [n] tensor on x's device (no graph)."""
+        xr = self._rows(x.detach())
+        with torch.no_grad():
+            u = self._check(self.fn(xr), xr.shape[0])
+        return u.to(torch.float32).contiguous()
+
+    def value_and_grad(self, x: torch.Tensor, need_grad: bool = True):
+        if not need_grad:
+            return self.value(x), None
+        with torch.enable_grad():
+            xr = self._rows(x.detach()).clone().requires_grad_(True)
+            u = self._check(self.fn(xr), xr.shape[0])
+            (g,) = torch.autograd.grad(u.sum(), xr)                      # langevin.py:68, hmc.py:43
+        return u.detach().to(torch.float32).contiguous(), g.detach().to(torch.float32).reshape(x.shape).contiguous()
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        return self.fn(x)
+
+    def log_prob_fn(self):
+        return lambda v: -self.fn(v)
+
+
+Potential.external = False
+
+
 def resolve_target(target, event_shape) -> Potential:
-    """The native path needs an analytic potential; arbitrary Python callables cannot be fused into the kernels."""
+    """A built-in analytic potential (fused into the kernels), its name, or any callable (external-target path)."""
     if isinstance(target, Potential):
         return target
     if isinstance(target, str):
         return make_potential(target, event_shape)
-    raise NotImplementedError(
-        "nfmc_b200 fuses the target potential and its gradient into the sm_100a kernels, so `target` must be one of "
-        "nfmc_b200.potentials.* (or its name as a string); arbitrary Python callables are not supported and there "
-        "is no eager fallback.  For the README example use nfmc_b200.potentials.StandardGaussian(event_shape).")
+    if callable(target):
+        return CallablePotential(target, event_shape)
+    raise TypeError(f"target must be a Potential, the name of one, or a callable [n, *event] -> [n]; got {type(target)!r}")

@@ -22,6 +22,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _native as N
+from . import external
 from .flow import Flow
 from .potentials import resolve_target
 from .records import (DLMCKernel, DLMCParameters, TESSKernel, TESSParameters, ESSKernel, ESSParameters, MHKernel, MHParameters, HMCKernel, HMCParameters, IMHKernel, IMHParameters, JumpNFMCOutput, JumpNFMCParameters,
@@ -138,6 +139,15 @@ class _DeviceTuner:
     def finish(self, kernel: MetropolisKernel):
         if kernel.inv_mass_diag is self.imd:
             kernel.inv_mass_diag = self.imd.cpu()             # the records keep the reference's host tensor
+
+
+def _require_analytic(target, who: str):
+    """Samplers whose kernels differentiate through the flow need the target's gradient inside the kernel."""
+    if getattr(target, "external", False):
+        raise NotImplementedError(
+            f"{who} needs a built-in analytic potential (nfmc_b200.potentials.*): its kernels evaluate the target inside the "
+            f"flow sweep.  Callable targets are supported by mala / ula / hmc / uhmc / mh / random walk, their jump_* "
+            f"variants, imh and adaptive_imh.")
 
 
 def _imd_device(kernel: MetropolisKernel, device) -> Optional[torch.Tensor]:
@@ -315,6 +325,10 @@ class Langevin(MetropolisSampler):
         return (2 * n, 2 * n) if self.params.adjustment else (n, n)
 
     def _launch(self, ses, n_steps, sink, normals=None, uniforms=None):
+        if self.target.external:                                  # callable target: autograd + the nfmc_ext_* kernels
+            return external.langevin_steps(self.target, ses, n_steps, float(self.kernel.step_size),
+                                           _imd_device(self.kernel, ses.device), bool(self.params.adjustment), False, sink,
+                                           normals, uniforms)
         pot, keep = self.target.descriptor(ses.device)
         imd = _imd_device(self.kernel, ses.device)
         rng = N.rng_desc(ses.seed, ses.local_step, normals, uniforms)
@@ -350,6 +364,10 @@ class HMC(MetropolisSampler):
         return (2 * L * n + (2 * n if self.params.adjustment else 0), 2 * L * n)
 
     def _launch(self, ses, n_steps, sink, normals=None, uniforms=None):
+        if self.target.external:
+            return external.hmc_steps(self.target, ses, n_steps, float(self.kernel.step_size),
+                                      int(self.kernel.n_leapfrog_steps), _imd_device(self.kernel, ses.device),
+                                      bool(self.params.adjustment), sink, normals, uniforms)
         pot, keep = self.target.descriptor(ses.device)
         imd = _imd_device(self.kernel, ses.device)
         rng = N.rng_desc(ses.seed, ses.local_step, normals, uniforms)
@@ -375,6 +393,9 @@ class MH(MetropolisSampler):
         return ((2 * n) if self.params.adjustment else 0, 0)                        # mh.py:68-71
 
     def _launch(self, ses, n_steps, sink, normals=None, uniforms=None):
+        if self.target.external:
+            return external.langevin_steps(self.target, ses, n_steps, 1.0, _imd_device(self.kernel, ses.device),
+                                           bool(self.params.adjustment), True, sink, normals, uniforms)
         pot, keep = self.target.descriptor(ses.device)
         imd = _imd_device(self.kernel, ses.device)
         rng = N.rng_desc(ses.seed, ses.local_step, normals, uniforms)
@@ -394,6 +415,7 @@ class ESS(MetropolisSampler):
                  params: Optional[ESSParameters] = None):
         super().__init__(event_shape, target, kernel or ESSKernel(tuple(event_shape)), params or ESSParameters())
         self.negative_log_likelihood = resolve_target(negative_log_likelihood, self.event_shape)
+        _require_analytic(self.negative_log_likelihood, "ESS (negative_log_likelihood)")
 
     @property
     def name(self):
@@ -461,6 +483,10 @@ class JumpNFMC(Sampler):
 
     def jump(self, ses: DeviceSession, sink=None, z=None, uniforms=None):
         flow: Flow = self.kernel.flow
+        if self.target.external:                                  # callable target: U(x), U(x') by calling it
+            external.jump_step(self.target, flow, ses, bool(self.params.adjusted_jumps), sink, z, uniforms)
+            ses.flow_step += 1
+            return
         pot, keep = self.target.descriptor(ses.device)
         rng = N.rng_desc(ses.seed, ses.flow_step, z, uniforms)
         st = ses.stats(jump=True)
@@ -500,6 +526,7 @@ class JumpNFMC(Sampler):
         dev = ses.device
         kind = self._fused_inner_kind()
         if (kind is not None and T > 0 and not store and not p.fit_nf and time_limit_seconds is None and not show_progress
+                and not self.target.external and not inner.target.external
                 and all(v is None for v in (normals, uniforms, jump_z, jump_uniforms, stage_normals))
                 and not self.kernel.flow.bijection.uses_tensor_cores()):
             # whole run in one call (nfmc_jump_sample_device): slabs of chains pipelined over several streams so that the
@@ -654,6 +681,8 @@ class AbstractIMH(Sampler):
         ses = DeviceSession(x0, event_shape, self.device, self.session_seed(), self.chain0)
         dev = ses.device
         T = int(self.params.n_iterations)
+        if self.target.external:
+            return self._run_external(ses, out, flow, T, show_progress, time_limit_seconds, store, z, uniforms, after_iteration)
         pot, keep = self.target.descriptor(dev)
         tc = flow.bijection.uses_tensor_cores()
         fd, keep2 = flow.bijection.tc_descriptor(dev) if tc else flow.bijection.descriptor(dev)
@@ -703,6 +732,49 @@ class AbstractIMH(Sampler):
                 after_iteration(start, out)
                 tc2 = flow.bijection.uses_tensor_cores()                              # parameters changed: re-pack
                 fd, keep2 = flow.bijection.tc_descriptor(dev) if tc2 else flow.bijection.descriptor(dev)
+        sx, sx2, cnt = ses.read_back()
+        out.statistics.expectations.add_sums(sx, sx2, ses.n * done)
+        out.statistics.update_counters(n_accepted_trajectories=cnt[0], n_attempted_trajectories=cnt[1])
+        if self.recompute_logq:
+            out.statistics.update_counters(n_target_gradient_calls=2 * ses.n * done)  # imh.py:146 (quirk Q3)
+        else:
+            out.statistics.update_counters(n_target_calls=2 * ses.n * done)           # imh.py:243-247
+        rs.set_last_device(ses.x.reshape(ses.n, *event_shape))
+        out.kernel = self.kernel
+        return out
+
+
+    def _run_external(self, ses, out, flow, T, show_progress, time_limit_seconds, store, z, uniforms, after_iteration):
+        """The same loop for a callable target: one ``external.jump_step`` per iteration; log q and U travel with the state."""
+        dev = ses.device
+        event_shape = out.event_shape
+        rs = out.running_samples
+        ses.tic()
+        logq = flow.log_prob(ses.x.reshape(ses.n, *event_shape)).reshape(ses.n).contiguous()          # imh.py:214
+        u_cache = self.target.value(ses.x)
+        out.statistics.update_elapsed_time(ses.toc())
+        done = 0
+        for i in _progress(range(T), self.name, show_progress):
+            if time_limit_seconds is not None and out.statistics.elapsed_time_seconds >= time_limit_seconds:
+                break
+            buf, sink = None, None
+            if store and _rows_kept(rs.seen_samples, 1, rs.thinning):
+                buf = torch.empty(1, ses.n, ses.d, device=dev, dtype=torch.float32)
+                sink = ses.sink(buf, rs.seen_samples, rs.thinning)
+            zz = None if z is None else N.dev_f32(z[i], dev)
+            uu = None if uniforms is None else N.dev_f32(uniforms[i], dev)
+            ses.tic()
+            external.jump_step(self.target, flow, ses, True, sink, zz, uu, logq=logq, recompute_logq=self.recompute_logq,
+                               jump_stats=False, u_cache=u_cache)
+            out.statistics.update_elapsed_time(ses.toc())
+            ses.flow_step += 1
+            done += 1
+            if buf is not None:
+                rs.add(buf.reshape(-1, ses.n, *event_shape), already_thinned=True, n_seen=1)
+            elif store:
+                rs.seen_samples += 1
+            if after_iteration is not None:
+                after_iteration(i, out)
         sx, sx2, cnt = ses.read_back()
         out.statistics.expectations.add_sums(sx, sx2, ses.n * done)
         out.statistics.update_counters(n_accepted_trajectories=cnt[0], n_attempted_trajectories=cnt[1])
@@ -775,6 +847,7 @@ class NeuTraHMC(Sampler):
                  kernel: NeuTraKernel = None, params: NeuTraParameters = None):
         es = int(math.prod(tuple(event_shape)))
         super().__init__(event_shape, target, kernel or NeuTraKernel(tuple(event_shape)), params or NeuTraParameters())
+        _require_analytic(self.target, "NeuTra")
         self.inner_kernel = inner_kernel or HMCKernel(event_size=es)
         self.inner_params = inner_params or HMCParameters()
         self.inner_params.n_iterations = self.params.n_iterations
@@ -910,6 +983,7 @@ class TESS(Sampler):
                  params: Optional[TESSParameters] = None):
         super().__init__(event_shape, target, kernel or TESSKernel(tuple(event_shape)), params or TESSParameters())
         self.negative_log_likelihood = resolve_target(negative_log_likelihood, self.event_shape)
+        _require_analytic(self.negative_log_likelihood, "TESS (negative_log_likelihood)")
 
     @property
     def name(self):
@@ -1019,6 +1093,8 @@ class DLMC(Sampler):
                  params: Optional[DLMCParameters] = None):
         super().__init__(event_shape, target, kernel or DLMCKernel(tuple(event_shape)), params or DLMCParameters())
         self.negative_log_likelihood = resolve_target(negative_log_likelihood, self.event_shape)
+        _require_analytic(self.target, "DLMC")
+        _require_analytic(self.negative_log_likelihood, "DLMC (negative_log_likelihood)")
 
     @property
     def name(self):

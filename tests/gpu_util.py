@@ -19,7 +19,14 @@ def product_flow_from_oracle(oflow, conditioner_dtype="fp32") -> Flow:
     return f.to("cuda").eval()
 
 
-def product_target(name, d):
+def product_target(name, d, callable_target: bool = False):
+    """The built-in analytic potential, or (``callable_target``) the same function as a plain Python callable in torch
+    operations -- what a user of the reference passes as ``target`` -- which sends the samplers down their external-target
+    path (autograd for U / grad U, nfmc_ext_* kernels for the rest)."""
+    if callable_target:
+        from oracle.potentials_ref import make_potential_ref
+        ref = make_potential_ref(str(name), (d,)).cuda()
+        return lambda x: ref(x)
     return P.make_potential(str(name), (d,))
 
 

@@ -110,7 +110,7 @@ def test_flow_sample_with_injected_base_draw(d, n_layers, ck):
 # ------------------------------------------------------------------------------------------------------------
 # golden cases (outputs of the unmodified reference) with the reference's own random draws injected
 # ------------------------------------------------------------------------------------------------------------
-def _golden_local(name, kind):
+def _golden_local(name, kind, ext=False):
     from gpu_util import product_target, run_local_injected
     from nfmc_b200.records import LangevinKernel, LangevinParameters, HMCKernel, HMCParameters
     from nfmc_b200.samplers import MALA, HMC
@@ -118,7 +118,7 @@ def _golden_local(name, kind):
     d = g["x0"].shape[1]
     K = int(g["K"])
     imd = torch.from_numpy(g["imd"])
-    tgt = product_target(g["pot"], d)
+    tgt = product_target(g["pot"], d, callable_target=ext)
     if kind == "mala":
         s = MALA((d,), tgt, LangevinKernel(event_size=d, inv_mass_diag=imd, step_size=float(g["step"])), LangevinParameters())
     elif kind == "ula":
@@ -147,30 +147,40 @@ def _golden_local(name, kind):
     close(sx2 / n_seen, g["second_moment"], atol=1e-5 * max(1.0, float(np.abs(g["second_moment"]).max())))
 
 
+# ext = True: the target is a plain Python callable (the reference's own contract) -> external-target path
+EXT = pytest.mark.parametrize("ext", [False, True], ids=["fused", "callable"])
+
+
+@EXT
 @pytest.mark.parametrize("name", ["mala_g0", "mala_fn"])
-def test_golden_mala(name):
-    _golden_local(name, "mala")
+def test_golden_mala(name, ext):
+    _golden_local(name, "mala", ext)
 
 
+@EXT
 @pytest.mark.parametrize("name", ["hmc_g1", "hmc_rb"])
-def test_golden_hmc(name):
-    _golden_local(name, "hmc")
+def test_golden_hmc(name, ext):
+    _golden_local(name, "hmc", ext)
 
 
-def test_golden_mh():
-    _golden_local("mh_gm", "mh")
+@EXT
+def test_golden_mh(ext):
+    _golden_local("mh_gm", "mh", ext)
 
 
-def test_golden_ula():
-    _golden_local("ula_g0", "ula")          # langevin.py:131-134
+@EXT
+def test_golden_ula(ext):
+    _golden_local("ula_g0", "ula", ext)          # langevin.py:131-134
 
 
-def test_golden_uhmc():
-    _golden_local("uhmc_gm", "uhmc")        # hmc.py:129-132
+@EXT
+def test_golden_uhmc(ext):
+    _golden_local("uhmc_gm", "uhmc", ext)        # hmc.py:129-132
 
 
+@EXT
 @pytest.mark.parametrize("name,kind", [("mala_tune_g1", "mala"), ("hmc_tune_fn", "hmc")])
-def test_golden_warmup_trajectory(name, kind):
+def test_golden_warmup_trajectory(name, kind, ext):
     """Warm-up (mcmc/base.py:39-54,142-161; tuning.py:15-41) with the reference's draws injected: the step size and the
     inverse-mass diagonal after EVERY iteration follow the reference's trajectory (the across-chain variance comes from
     fp64 sums on the device, the reference's from torch.var in fp32)."""
@@ -179,7 +189,7 @@ def test_golden_warmup_trajectory(name, kind):
     from nfmc_b200.samplers import MALA, HMC, _DeviceTuner
     g = load_case(name)
     d, K = g["x0"].shape[1], int(g["K"])
-    tgt = product_target(g["pot"], d)
+    tgt = product_target(g["pot"], d, callable_target=ext)
     if kind == "mala":
         s = MALA((d,), tgt, LangevinKernel(event_size=d, step_size=float(g["step"])), LangevinParameters(n_iterations=K))
     else:
@@ -218,9 +228,10 @@ def _check_output(out, g, jump=False):
         assert (st.n_accepted_jumps, st.n_attempted_jumps) == (jacc, jatt)
 
 
+@EXT
 @pytest.mark.parametrize("name,inner", [("jump_mala_g0", "mala"), ("jump_hmc_gm", "hmc"), ("jump_mala_g1_d100", "mala"),
                                         ("jump_hmc_g1_d100", "hmc"), ("jump_mala_gm_d1000", "mala")])
-def test_golden_jump(name, inner):
+def test_golden_jump(name, inner, ext):
     from gpu_util import product_target, product_flow_from_oracle
     from nfmc_b200.records import (LangevinKernel, LangevinParameters, HMCKernel, HMCParameters, NFMCKernel,
                                    JumpNFMCParameters)
@@ -228,7 +239,7 @@ def test_golden_jump(name, inner):
     g = load_case(name)
     n, d = g["x0"].shape
     T, K = int(g["T"]), int(g["K"])
-    tgt = product_target(g["pot"], d)
+    tgt = product_target(g["pot"], d, callable_target=ext)
     flow = product_flow_from_oracle(oracle_flow(g))
     if inner == "mala":
         s = JumpMALA((d,), tgt, kernel=NFMCKernel((d,), flow=flow), params=JumpNFMCParameters(n_iterations=T),
@@ -249,7 +260,8 @@ def test_golden_jump(name, inner):
     _check_output(out, g, jump=True)
 
 
-def test_golden_adaptive_imh():
+@EXT
+def test_golden_adaptive_imh(ext):
     """AdaptiveIMH.sample (imh.py:102-181) with the refit switched off as in the fixture: log q recomputed every iteration,
     2 n GRADIENT calls booked per iteration (imh.py:146), every iteration stored."""
     from gpu_util import product_target, product_flow_from_oracle
@@ -258,7 +270,7 @@ def test_golden_adaptive_imh():
     g = load_case("adaptive_imh_rb")
     n, d = g["x0"].shape
     T = int(g["T"])
-    s = AdaptiveIMH((d,), product_target(g["pot"], d), IMHKernel((d,), flow=product_flow_from_oracle(oracle_flow(g))),
+    s = AdaptiveIMH((d,), product_target(g["pot"], d, callable_target=ext), IMHKernel((d,), flow=product_flow_from_oracle(oracle_flow(g))),
                     IMHParameters(n_iterations=T))
     s.adapt = False
     # tape per iteration: uniform(n) for the accept test, then one scalar uniform for the refit decision (imh.py:152)
@@ -266,15 +278,16 @@ def test_golden_adaptive_imh():
     _check_output(out, g)
 
 
+@EXT
 @pytest.mark.parametrize("name", ["imh_rb", "imh_rb_d100"])
-def test_golden_fixed_imh(name):
+def test_golden_fixed_imh(name, ext):
     from gpu_util import product_target, product_flow_from_oracle
     from nfmc_b200.records import IMHKernel, IMHParameters
     from nfmc_b200.samplers import FixedIMH
     g = load_case(name)
     n, d = g["x0"].shape
     T = int(g["T"])
-    s = FixedIMH((d,), product_target(g["pot"], d), IMHKernel((d,), flow=product_flow_from_oracle(oracle_flow(g))),
+    s = FixedIMH((d,), product_target(g["pot"], d, callable_target=ext), IMHKernel((d,), flow=product_flow_from_oracle(oracle_flow(g))),
                  IMHParameters(n_iterations=T))
     out = s.sample(torch.from_numpy(g["x0"]), show_progress=False, z=torch.stack(g["normals"]), uniforms=torch.stack(g["uniforms"]))
     _check_output(out, g)

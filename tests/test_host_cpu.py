@@ -52,8 +52,13 @@ def test_no_cpu_fallback():
     from nfmc_b200 import _native as N
     with pytest.raises(N.NativeError):
         nfmc_b200.sample("g0", (5,), strategy="jump_mala", n_chains=4, n_iterations=2, show_progress=False)
-    with pytest.raises(NotImplementedError):
-        nfmc_b200.potentials.resolve_target(lambda x: (x ** 2).sum(-1), (5,))
+    # a callable target resolves to the external-target wrapper (no compute here); anything else is a TypeError
+    t = nfmc_b200.potentials.resolve_target(lambda x: (x ** 2).sum(-1), (5,))
+    assert t.external and t.event_shape == (5,)
+    with pytest.raises(N.NativeError):
+        t.descriptor(torch.device("cpu"))
+    with pytest.raises(TypeError):
+        nfmc_b200.potentials.resolve_target(3.0, (5,))
 
 
 def test_flow_state_dict_is_interchangeable_with_oracle():
