@@ -263,6 +263,12 @@ NFMC_API int nfmc_ext_accept(float* x, const float* x_prime, const float* log_ra
                     float* aux_grad, const float* aux_grad_prime, const nfmc_stats* stats, const nfmc_sink* sink,
                     int32_t sink_step, void* stream);
 
+/* NeuTra with an external target: grad_z [ U(T^-1 z) - log|det dT^-1/dz| ] (neutra.py:58-68) from z and grad_x = grad U(x) at
+ * x = T^-1 z (which nfmc_realnvp_inverse gives): inverse pass + reversible backward sweep seeded with grad_x.  log_det
+ * (optional, [n]) receives log|det dT^-1/dz|. */
+NFMC_API int nfmc_neutra_pullback(const nfmc_realnvp* flow, const float* z, const float* grad_x, float* grad_z, float* log_det,
+                         int64_t n, void* stream);
+
 /* ---- flow training on the device (register-resident conditioner path: n_linear = 2, hidden <= 8) -----------------
  * Replaces the autograd + AdamW loop behind flow.fit (nfmc/jump.py:139-151,201; nfmc/imh.py:171-175) and
  * flow.variational_fit (nfmc/imh.py:67-72; nfmc/neutra.py:84-91); torchflows itself is absent, its optimiser settings

@@ -267,6 +267,20 @@ extern "C" int nfmc_neutra_potential(const nfmc_potential* pot, const nfmc_realn
   return 0;
 }
 
+extern "C" int nfmc_neutra_pullback(const nfmc_realnvp* flow, const float* z, const float* grad_x, float* grad_z, float* log_det,
+                                    int64_t n, void* stream) {
+  if (int e = validate_flow(flow)) return e;
+  if (!z || !grad_x || !grad_z || n < 1) return set_error("neutra_pullback: bad arguments");
+  Layout L;
+  if (!layout_for_dim(flow->d, L)) return set_error("neutra_pullback: unsupported event size");
+  FlowArgs FA;
+  const size_t smem = plan_flow_smem(FA, flow, L, false);
+  const int grid = grid_for(n, L.gs, 2);
+  cudaStream_t s = (cudaStream_t)stream;
+  NFMC_DISPATCH_E(L.E, { return launch_neutra_pullback<E>(FA, z, grad_x, grad_z, log_det, n, grid, smem, s); });
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // NF jump / one IMH iteration with the flow passes on the tensor cores (wide conditioners).
 // workspace (device): z [n,d] | x' [n,d] | ld_inv [n] | log q(x) [n] | uniforms [n]

@@ -100,6 +100,9 @@ template <int E> int launch_neutra_mh(const NeutraArgs& A, int grid, size_t smem
 template <int E> int launch_neutra_potential(const FlowArgs& FA, int pot_kind, const PotParams& P, const float* z, float* u,
                                              float* grad, long long n, int grid, size_t smem, cudaStream_t s);
 
+template <int E> int launch_neutra_pullback(const FlowArgs& FA, const float* z, const float* gx, float* gz, float* ld, long long n,
+                                            int grid, size_t smem, cudaStream_t s);
+
 #define NFMC_SET_SMEM_RET(kern, bytes)                                                                     \
   do {                                                                                                     \
     if ((bytes) > 227 * 1024) return set_error("shared-memory plan exceeds 227 KB (conditioner too large for the generic kernel)"); \

@@ -235,6 +235,44 @@ __global__ void __launch_bounds__(kThreads) neutra_potential_kernel(FlowArgs FA,
 }
 
 
+// Pull a data-space cotangent back to the latent space for an EXTERNAL target (a Python callable differentiated by autograd,
+// nfmc_b200/external.py): given z and gx = grad U(x) at x = T^-1(z), writes grad_z [ U(T^-1 z) - log|det dT^-1/dz| ] -- the
+// gradient of NeuTra.adjusted_target (neutra.py:58-68) -- and, optionally, log|det dT^-1/dz| itself.  Same inverse pass and
+// reversible backward sweep as neutra_value_grad, with the seed read from memory instead of pot_grad.
+template <int E, bool SB, bool X, bool SM>
+__global__ void __launch_bounds__(kThreads) neutra_pullback_kernel(FlowArgs FA, const float* __restrict__ z, const float* __restrict__ gx,
+                                                                  float* __restrict__ gz, float* __restrict__ ld_out, long long n) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Geom g = make_geom(FA.d, FA.gs);
+  FlowSmem S = flow_smem_init<SB>(smem, FA, false);
+  const bool flip = (FA.Lc & 1) != 0;
+  const int cpc = kThreads / FA.gs;
+  const long long tiles = (n + cpc - 1) / cpc;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long chain_raw = tile * cpc + threadIdx.x / FA.gs;
+    const bool active = chain_raw < n;
+    const long long chain = active ? chain_raw : n - 1;
+    float xlo[E], xhi[E], glo[E], ghi[E];
+    const float* src = z + chain * (long long)FA.d;
+    if (flip) load_chain_flipped(src, g, xlo, xhi); else load_chain(src, g, xlo, xhi);
+    const float ld_inv = flow_inverse<E, SB, X, SM>(S.F, g, xlo, xhi, S.scr, nullptr);
+    load_chain(gx + chain * (long long)FA.d, g, glo, ghi);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int kk = g.j + g.gs * e;
+      if (kk >= g.da) glo[e] = 0.f;
+      if (kk >= g.db) ghi[e] = 0.f;
+    }
+    flow_unwind<E, SB, X, SM>(S.F, g, xlo, xhi, glo, ghi, S.scr, nullptr);
+    if (active) {
+      if (ld_out && g.j == 0) ld_out[chain] = ld_inv;
+      float* dst = gz + chain * (long long)FA.d;
+      if (flip) store_chain_flipped(dst, g, glo, ghi); else store_chain(dst, g, glo, ghi);
+    }
+  }
+}
+
+
 // ---------------------------------------------------------------------------------------------------------
 // NeuTra MH (nfmc/neutra.py:147-159): random-walk Metropolis (mcmc/mh.py:44-73) in the latent space on U~.  One inverse
 // pass + one potential per step, no gradient; U~ of the current state is carried (the reference re-evaluates it, to the
@@ -412,5 +450,26 @@ int launch_neutra_mh(const NeutraArgs& A, int grid, size_t smem, cudaStream_t s)
 }
 template int launch_neutra_mh<NFMC_ONLY_E>(const NeutraArgs&, int, size_t, cudaStream_t);
 template int launch_neutra_potential<NFMC_ONLY_E>(const FlowArgs&, int, const PotParams&, const float*, float*, float*, long long, int, size_t, cudaStream_t);
+
+template <int E>
+int launch_neutra_pullback(const FlowArgs& FA, const float* z, const float* gx, float* gz, float* ld, long long n, int grid,
+                           size_t smem, cudaStream_t s) {
+  constexpr bool XE = (E == 13 || E == 16);
+  const bool small = flow_is_small(FA.M, FA.H);
+  const bool xl = FA.exact && XE;
+#define NFMC_LAUNCH(SBv, Xv, Sv)                                                              \
+  do {                                                                                        \
+    NFMC_SET_SMEM_RET((neutra_pullback_kernel<E, SBv, Xv, Sv>), smem);                                        \
+    neutra_pullback_kernel<E, SBv, Xv, Sv><<<occupancy_grid(neutra_pullback_kernel<E, SBv, Xv, Sv>, smem, n, FA.gs), kThreads, smem, s>>>(FA, z, gx, gz, ld, n);                              \
+  } while (0)
+  if (!small) { if (FA.stage_blob) NFMC_LAUNCH(true, false, false); else NFMC_LAUNCH(false, false, false); }
+  else if (FA.stage_blob && xl) NFMC_LAUNCH(true, XE, true);
+  else if (FA.stage_blob) NFMC_LAUNCH(true, false, true);
+  else if (xl) NFMC_LAUNCH(false, XE, true);
+  else NFMC_LAUNCH(false, false, true);
+#undef NFMC_LAUNCH
+  return check_cuda(cudaGetLastError(), "neutra_pullback_kernel launch");
+}
+template int launch_neutra_pullback<NFMC_ONLY_E>(const FlowArgs&, const float*, const float*, float*, float*, long long, int, size_t, cudaStream_t);
 
 }  // namespace nfmc

@@ -142,3 +142,42 @@ def jump_step(target, flow, ses, adjusted: bool, sink, z=None, uniforms=None, lo
                                 N.ptr(up) if (u_cache is not None and up is not None) else None,
                                 N.ptr(logq) if adjusted else None, N.ptr(lqp) if adjusted else None,
                                 None, None, C.byref(st), _sink_ref(sink), 0, s))
+
+
+class LatentTarget:
+    """``NeuTra.adjusted_target`` (neutra.py:58-68) for a callable target: U~(z) = U(T^-1 z) - log|det dT^-1/dz| with its
+    gradient assembled from the flow's inverse pass (``nfmc_realnvp_inverse``), the callable's autograd gradient at
+    x = T^-1 z, and the flow's reversible backward sweep seeded with it (``nfmc_neutra_pullback``).  All flow passes use the
+    fp32 kernels so that value and gradient belong to the same function.  As in the reference (quirk Q1) the rows a NeuTra
+    run records are the latent states."""
+    external = True
+
+    def __init__(self, target, flow):
+        self.target = target
+        self.flow = flow
+
+    def to_data(self, z: torch.Tensor):
+        """(x, log|det dT^-1/dz|) for latent rows z [n, d]."""
+        bij = self.flow.bijection
+        dev = z.device
+        n = z.shape[0]
+        x = torch.empty_like(z)
+        ld = torch.empty(n, device=dev, dtype=torch.float32)
+        fd, keep = bij.descriptor(dev)
+        N.check(N.lib().nfmc_realnvp_inverse(C.byref(fd), N.ptr(z), N.ptr(x), N.ptr(ld), n, N.stream_ptr(dev)))
+        return x, ld
+
+    def value(self, z: torch.Tensor) -> torch.Tensor:
+        x, ld = self.to_data(z)
+        return -((-self.target.value(x)) + ld)                                  # neutra.py:62-64
+
+    def value_and_grad(self, z: torch.Tensor, need_grad: bool = True):
+        if not need_grad:
+            return self.value(z), None
+        x, ld = self.to_data(z)
+        u, gx = self.target.value_and_grad(x)
+        gz = torch.empty_like(z)
+        fd, keep = self.flow.bijection.descriptor(z.device)
+        N.check(N.lib().nfmc_neutra_pullback(C.byref(fd), N.ptr(z), N.ptr(gx.reshape(z.shape).contiguous()), N.ptr(gz), None,
+                                             z.shape[0], N.stream_ptr(z.device)))
+        return -((-u) + ld), gz

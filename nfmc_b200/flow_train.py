@@ -363,8 +363,10 @@ class WideTrainer(NativeTrainer):
         return -lq.double().mean()
 
 
-def make_trainer(flow, dev, lr: float) -> NativeTrainer:
-    if native_supported(flow):
+def make_trainer(flow, dev, lr: float, external_target: bool = False) -> NativeTrainer:
+    """``external_target``: the reverse-KL target is a Python callable -- only the wide trainer takes U / grad U from outside
+    (its sweep kernel is seeded with grad U(x)); the register-resident kernel evaluates the potential itself."""
+    if native_supported(flow) and not external_target:
         return NativeTrainer(flow, dev, lr)
     if wide_supported(flow):
         return WideTrainer(flow, dev, lr)
@@ -427,7 +429,7 @@ def _fit_native(flow, dev, x_train, x_val, n_epochs, lr, batch_size, shuffle, ke
 
 def _variational_fit_native(flow, dev, potential, n_epochs, lr, n_samples, early_stopping, early_stopping_threshold,
                             keep_best_weights, check_for_divergences, time_limit_seconds):
-    tr = make_trainer(flow, dev, lr)
+    tr = make_trainer(flow, dev, lr, external_target=bool(getattr(potential, "external", False)))
     seed = int(torch.randint(0, 2 ** 62, (), dtype=torch.int64))
     best, since_best = math.inf, 0
     best_theta = tr.theta.clone() if keep_best_weights else None
@@ -499,8 +501,8 @@ def variational_fit(flow, target_log_prob: Callable, n_epochs: int = 500, lr: fl
     d = flow.bijection.n_dim
     potential = getattr(target_log_prob, "potential", None)
     if potential is None:
-        raise NotImplementedError("variational_fit needs a target built from nfmc_b200.potentials (target_log_prob_fn): "
-                                  "arbitrary Python callables cannot be fused and there is no eager fallback")
+        raise NotImplementedError("variational_fit needs `potential.log_prob_fn()` of a nfmc_b200.potentials object (a built-in "
+                                  "potential or CallablePotential(fn, event_shape)), which carries U / grad U for the native sweep")
     return _variational_fit_native(flow, dev, potential, n_epochs, lr, int(n_samples), early_stopping,
                                    early_stopping_threshold, keep_best_weights, check_for_divergences,
                                    time_limit_seconds)

@@ -228,7 +228,9 @@ class CallablePotential(Potential):
         return self.fn(x)
 
     def log_prob_fn(self):
-        return lambda v: -self.fn(v)
+        fn = lambda v: -self.fn(v)     # noqa: E731
+        fn.potential = self            # variational_fit: U / grad U by autograd, flow sweep by the native wide trainer
+        return fn
 
 
 Potential.external = False

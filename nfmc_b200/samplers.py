@@ -147,7 +147,7 @@ def _require_analytic(target, who: str):
         raise NotImplementedError(
             f"{who} needs a built-in analytic potential (nfmc_b200.potentials.*): its kernels evaluate the target inside the "
             f"flow sweep.  Callable targets are supported by mala / ula / hmc / uhmc / mh / random walk, their jump_* "
-            f"variants, imh and adaptive_imh.")
+            f"variants, imh, adaptive_imh, neutra_hmc and neutra_mh.")
 
 
 def _imd_device(kernel: MetropolisKernel, device) -> Optional[torch.Tensor]:
@@ -847,7 +847,6 @@ class NeuTraHMC(Sampler):
                  kernel: NeuTraKernel = None, params: NeuTraParameters = None):
         es = int(math.prod(tuple(event_shape)))
         super().__init__(event_shape, target, kernel or NeuTraKernel(tuple(event_shape)), params or NeuTraParameters())
-        _require_analytic(self.target, "NeuTra")
         self.inner_kernel = inner_kernel or HMCKernel(event_size=es)
         self.inner_params = inner_params or HMCParameters()
         self.inner_params.n_iterations = self.params.n_iterations
@@ -865,7 +864,9 @@ class NeuTraHMC(Sampler):
         out = MCMCOutput(event_shape, store_samples=store)
         ses = DeviceSession(x0, event_shape, self.device, self.session_seed(), self.chain0)
         dev = ses.device
-        pot, keep = self.target.descriptor(dev)
+        ext = self.target.external
+        latent = external.LatentTarget(self.target, self.kernel.flow) if ext else None      # callable target
+        pot, keep = (None, None) if ext else self.target.descriptor(dev)
         fd, keep2 = self.kernel.flow.bijection.descriptor(dev)
         imd = _imd_device(self.inner_kernel, dev)
         chunk = 1 if (tuning or time_limit_seconds is not None or show_progress) else T
@@ -888,7 +889,10 @@ class NeuTraHMC(Sampler):
             rng = N.rng_desc(ses.seed, ses.local_step, nz, un)
             st = ses.stats()
             ses.tic()
-            self._launch_latent(ses, pot, fd, k, imd, rng, st, sink)
+            if ext:
+                self._launch_latent_external(latent, ses, k, imd, sink, nz, un)
+            else:
+                self._launch_latent(ses, pot, fd, k, imd, rng, st, sink)
             out.statistics.update_elapsed_time(ses.toc())
             ses.local_step += k
             done += k
@@ -931,6 +935,10 @@ class NeuTraHMC(Sampler):
                                               N.ptr(imd), C.byref(rng), ses.chain0, C.byref(st),
                                               None if sink is None else C.byref(sink), ses.stream))
 
+    def _launch_latent_external(self, latent, ses, k, imd, sink, normals, uniforms):
+        external.hmc_steps(latent, ses, k, float(self.inner_kernel.step_size), int(self.inner_kernel.n_leapfrog_steps), imd,
+                           True, sink, normals, uniforms)           # recorded rows stay in z-space (reference quirk Q1)
+
     def _calls_grads(self, n):
         L = int(self.inner_kernel.n_leapfrog_steps)
         return (2 * L + 2) * n, 2 * L * n                                             # hmc.py:122-125
@@ -965,6 +973,9 @@ class NeuTraMH(NeuTraHMC):
         N.check(N.lib().nfmc_neutra_mh_steps(C.byref(pot), C.byref(fd), N.ptr(ses.x), ses.n, k, N.ptr(imd),
                                              int(bool(self.inner_params.adjustment)), C.byref(rng), ses.chain0, C.byref(st),
                                              None if sink is None else C.byref(sink), ses.stream))
+
+    def _launch_latent_external(self, latent, ses, k, imd, sink, normals, uniforms):
+        external.langevin_steps(latent, ses, k, 1.0, imd, bool(self.inner_params.adjustment), True, sink, normals, uniforms)
 
     def _calls_grads(self, n):
         return ((2 * n) if self.inner_params.adjustment else 0), 0                     # mh.py:68-71

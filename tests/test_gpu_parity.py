@@ -293,29 +293,31 @@ def test_golden_fixed_imh(name, ext):
     _check_output(out, g)
 
 
+@EXT
 @pytest.mark.parametrize("name", ["neutra_hmc_fn", "neutra_hmc_fn_d100"])
-def test_golden_neutra_hmc(name):
+def test_golden_neutra_hmc(name, ext):
     from gpu_util import product_target, product_flow_from_oracle
     from nfmc_b200.records import HMCKernel, HMCParameters, NeuTraKernel, NeuTraParameters
     from nfmc_b200.samplers import NeuTraHMC
     g = load_case(name)
     n, d = g["x0"].shape
     T = int(g["T"])
-    s = NeuTraHMC((d,), product_target(g["pot"], d), HMCKernel(event_size=d, step_size=float(g["step"]), n_leapfrog_steps=int(g["L"])),
+    s = NeuTraHMC((d,), product_target(g["pot"], d, callable_target=ext), HMCKernel(event_size=d, step_size=float(g["step"]), n_leapfrog_steps=int(g["L"])),
                   HMCParameters(), NeuTraKernel((d,), flow=product_flow_from_oracle(oracle_flow(g))), NeuTraParameters(n_iterations=T))
     out = s.sample(torch.from_numpy(g["x0"]), show_progress=False, normals=torch.stack(g["normals"]),
                    uniforms=torch.stack(g["uniforms"]))
     _check_output(out, g)
 
 
-def test_golden_neutra_mh():
+@EXT
+def test_golden_neutra_mh(ext):
     from gpu_util import product_target, product_flow_from_oracle
     from nfmc_b200.records import MHKernel, MHParameters, NeuTraKernel, NeuTraParameters
     from nfmc_b200.samplers import NeuTraMH
     g = load_case("neutra_mh_gm")
     n, d = g["x0"].shape
     T = int(g["T"])
-    s = NeuTraMH((d,), product_target(g["pot"], d), MHKernel(event_size=d, inv_mass_diag=torch.from_numpy(g["imd"])), MHParameters(),
+    s = NeuTraMH((d,), product_target(g["pot"], d, callable_target=ext), MHKernel(event_size=d, inv_mass_diag=torch.from_numpy(g["imd"])), MHParameters(),
                  NeuTraKernel((d,), flow=product_flow_from_oracle(oracle_flow(g))), NeuTraParameters(n_iterations=T))
     out = s.sample(torch.from_numpy(g["x0"]), show_progress=False, normals=torch.stack(g["normals"]),
                    uniforms=torch.stack(g["uniforms"]))
