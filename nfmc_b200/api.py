@@ -138,7 +138,8 @@ def sample(target, event_shape: Optional[Tuple[int, ...]] = None, flow: Optional
            strategy: str = "imh", n_iterations: int = 100, n_warmup_iterations: int = 100, n_chains: int = 100,
            x0: torch.Tensor = None, warmup: bool = False, show_progress: bool = True,
            sampling_time_limit_seconds=None, warmup_time_limit_seconds=None, **kwargs) -> MCMCOutput:
-    """Sample from ``target`` (a ``nfmc_b200.potentials.Potential`` or its name).  Same arguments and return
+    """Sample from ``target``: a ``nfmc_b200.potentials.Potential`` or its name (fused kernels), or any callable
+    ``[n, *event] -> [n]`` in torch operations (external-target path, as the reference's own contract).  Same arguments and return
     type as the reference's ``nfmc.sample`` (sample.py:243-314); ``x0`` may be a host tensor -- it is copied to
     the GPU once and results come back as host tensors."""
     if flow == 'None':
