@@ -532,12 +532,16 @@ def native_arm(args):
     inst = prof.get(f"{args.workload}_d{d}_inst_per_warp_step")          # ncu: smsp__inst_executed / warp-steps, profiles/
     gs = 4 if d > 64 else (2 if d > 32 else 1)
     frac_issue = None
+    frac_fma_pipe = None
     if inst and clk and clk.get("sm_mhz"):
         warp_steps = chain_steps_per_launch * gs / 32.0
         frac_issue = inst * warp_steps / t_launch / (148 * 4 * clk["sm_mhz"] * 1e6)
+        pipe = prof.get(f"{args.workload}_d{d}_fma_pipe_cycles_per_warp_step")   # SASS mix x measured pipe rates (profiles/pipes_r02.txt)
+        if pipe:
+            frac_fma_pipe = pipe * warp_steps / t_launch / (148 * 4 * clk["sm_mhz"] * 1e6)
     roofline = {"bound": "fp32-issue", "kernel": "mala_kernel" if w["kind"] == 0 else "hmc_kernel",
                 "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": (achieved_tf / fp32_peak) if fp32_peak else None,
-                "frac_fp32": (achieved_tf / fp32_peak) if fp32_peak else None, "frac_issue": frac_issue,
+                "frac_fp32": (achieved_tf / fp32_peak) if fp32_peak else None, "frac_issue": frac_issue, "frac_fma_pipe": frac_fma_pipe,
                 "frac_hbm_notional": 8.0 * d * chain_steps_per_launch / t_launch / 1e9 / hbm_peak,
                 "traffic": prof.get(f"{args.workload}_d{d}"),
                 "peak_source": "FFMA peak measured in this run by tools/microbench_fp32 (fp32 FMA = 2 flop)",
@@ -548,7 +552,8 @@ def native_arm(args):
                           "region on the same buffers (inside the timed region launches of different slabs overlap)",
                 "note": "achieved = algorithmic fp32 operations per chain-step (SURVEY 8d: (c_U + 30) d) x K n chain-steps per launch / "
                         "launch time; frac_issue = warp-instructions per warp-step (ncu smsp__inst_executed, profiles/) x warp-steps / "
-                        "(148 SMs x 4 schedulers x SM clock); frac_hbm_notional = the 8 d bytes per chain-step of SURVEY 8d -- the kernel "
+                        "(148 SMs x 4 schedulers x SM clock); frac_fma_pipe = fma-pipe cycles per warp-step (SASS mix x the pipe rates of "
+                        "tools/probes/pipes.cu: IMAD.WIDE 4, FFMA2 2, FFMA 1 cycles) over the same denominator -- the busiest pipe; frac_hbm_notional = the 8 d bytes per chain-step of SURVEY 8d -- the kernel "
                         "keeps the state on chip for all K steps (traffic = ncu dram bytes per launch ~ 8 d n), so HBM is not its bound"}
     line = {
         "metric": f"{args.workload} chain-steps/sec", "value": value, "unit": "chain-steps/s", "n_gpus": world,

@@ -1030,11 +1030,15 @@ __device__ __forceinline__ void tc_pass_begin(const TcSmem& sm, const TcShape& S
                                               float (&hi)[kTcOwn]) {
   const int l0 = INV ? S.Lc - 1 : 0;
   tc_affine(sm.aff4, INV ? S.Lc : 0, INV, g * kTcOwn, lo, hi);
+  TC_TRACE_EPI(53 + t);
   if (t == 1 && S.na1 == 1) mbar_wait(sy.bar(kTcBarG1 + 0), sy.use & 1);   // shared A1 image: wait for tile 0's GEMM 1
+  TC_TRACE_EPI(55 + t);
   if ((l0 & 1) == 0) tc_write_a1(sm.a1(t), r, g, hi);
   else tc_write_a1(sm.a1(t), r, g, lo);
+  TC_TRACE_EPI(57 + t);
   fence_async_smem();
   tc_fence_before();
+  TC_TRACE_EPI(59 + t);
   mbar_arrive(sy.bar(kTcBarA1 + t));
 }
 // the Lc couplings of a pass over both tiles.  st holds the input (after tc_pass_begin) on entry and the output on

@@ -103,10 +103,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const __grid_con
         for (int t = 0; t < 2; ++t) {
           float* row = reinterpret_cast<float*>(sm.x(t)) + (size_t)r * d;
           mbar_wait(sync.bar(kTcBarXFull + t), (uint32_t)(p & 1));
+          { TcEpiSync& sy = sync; TC_TRACE_EPI(43 + t); }
           tc_row_exchange(row, d, da, e0, fl_in, fl_out, have_out, st[t][0], st[t][1]);
+          { TcEpiSync& sy = sync; TC_TRACE_EPI(49 + t); }
           if (have_out) fence_async_smem();
+          { TcEpiSync& sy = sync; TC_TRACE_EPI(51 + t); }
           mbar_arrive(sync.bar(kTcBarXReady + t));
+          { TcEpiSync& sy = sync; TC_TRACE_EPI(45 + t); }
           tc_pass_begin<INV>(sm, S, sync, t, r, g, st[t][0], st[t][1]);
+          { TcEpiSync& sy = sync; TC_TRACE_EPI(47 + t); }
         }
       } else {
         // ---- input: global -> tensor memory (fragment layout) -> registers (row layout) ---------------------------

@@ -36,6 +36,21 @@ __device__ __forceinline__ float mufu_sin(float a) {
   asm volatile("sin.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(a));
   return d;
 }
+__device__ __forceinline__ float mufu_tanh(float a) {
+  float d;
+  asm volatile("tanh.approx.f32 %0, %1;" : "=f"(d) : "f"(a));
+  return d;
+}
+__device__ __forceinline__ uint32_t mufu_tanh_h2(uint32_t a) {
+  uint32_t d;
+  asm volatile("tanh.approx.f16x2 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+__device__ __forceinline__ uint32_t mufu_tanh_b2(uint32_t a) {
+  uint32_t d;
+  asm volatile("tanh.approx.bf16x2 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
 __device__ __forceinline__ float fsel(float a, float b, int p) {
   float d;
   asm volatile("{.reg .pred q; setp.ne.s32 q, %3, 0; selp.f32 %0, %1, %2, q;}" : "=f"(d) : "f"(a), "f"(b), "r"(p));
@@ -76,6 +91,9 @@ __global__ void __launch_bounds__(1024) bench(float* out, int iters, uint32_t ka
       if (MODE == 9) { if (i < 2) f[i] = mufu_sin(f[i]); p[i] = fma2(p[i], pa, pa); }
       if (MODE == 10) f[i] = fsel(f[i], fa, (int)(u[i] & 1));
       if (MODE == 11) { f[i] = ffma(f[i], fa, fa); p[i] = fma2(p[i], pa, pa); }
+      if (MODE == 13) f[i] = mufu_tanh(f[i]);
+      if (MODE == 14) u[i] = mufu_tanh_h2(u[i]);
+      if (MODE == 15) u[i] = mufu_tanh_b2(u[i]);
       if (MODE == 12) {
         if (i < 4) {
           float4 m = vsm[threadIdx.x];
@@ -127,5 +145,8 @@ int main() {
   run<10>("SELP (+LOP)", 3 * ILP, out, cyc);
   run<11>("FFMA + FFMA2", 2 * ILP, out, cyc);
   run<12>("4x(LDS128+2FFMA2+STS128)", 16, out, cyc);
+  run<13>("MUFU.TANH f32", ILP, out, cyc);
+  run<14>("tanh.approx.f16x2 (per pair)", ILP, out, cyc);
+  run<15>("tanh.approx.bf16x2 (per pair)", ILP, out, cyc);
   return 0;
 }

@@ -35,7 +35,10 @@ t0 = ev[0][0]
 names = {0: "c.begin", 1: "c.w1_full", 2: "c.a1[0]", 3: "c.G1(0)issued", 4: "c.a1[1]", 5: "c.G1(1)issued", 6: "c.wl_full", 7: "c.hid[0]",
          8: "c.G2(0)issued", 9: "c.w1refill", 10: "c.hid[1]", 11: "c.G2(1)issued", 12: "c.end", 20: "e.wait g1[0]", 21: "e.wait g1[1]",
          22: "e.g1[0] ok", 23: "e.g1[1] ok", 24: "e.E1(0) done", 25: "e.E1(1) done", 26: "e.g2[0] ok", 27: "e.g2[1] ok", 28: "e.E2(0) done",
-         29: "e.E2(1) done", 40: "e.loaded", 41: "e.pass done", 42: "e.pair done"}
+         29: "e.E2(1) done", 43: "e.xfull(0)", 44: "e.xfull(1)", 45: "e.xready(0)", 46: "e.xready(1)", 47: "e.begun(0)", 48: "e.begun(1)",
+         49: "e.exchanged(0)", 50: "e.exchanged(1)", 51: "e.fenced(0)", 52: "e.fenced(1)", 53: "e.affine0(0)", 54: "e.affine0(1)",
+         55: "e.a1 free0(0)", 56: "e.a1 free0(1)", 57: "e.a1 written(0)", 58: "e.a1 written(1)", 59: "e.a1 fenced(0)", 60: "e.a1 fenced(1)",
+         39: "e.pair begin", 40: "e.loaded", 41: "e.pass done", 42: "e.pair done"}
 last = t0
 for t, who, i in ev[:int(os.environ.get("TRACE_ROWS", "160"))]:
     print(f"{t - t0:9d} (+{t - last:6d}) {'ctl' if who == 0 else 'epi'} {names.get(i, i)}")
