@@ -421,7 +421,10 @@ def tc_eligible(d: int, M: int, H: int) -> bool:
 
 
 def _tc_hidden(H: int) -> int:
-    return ((H + 15) // 16) * 16
+    """Hidden width of the packed tensor-core images: zero-padded to a multiple of 32 (the flow / jump kernels take any
+    multiple of 16, the NeuTra kernel's K-step pairing needs 32 -- padding to 32 makes every tensor-core flow a NeuTra
+    tensor-core flow too, e.g. a default H = 5 conditioner opted in with ``conditioner_dtype='bf16'``)."""
+    return ((H + 31) // 32) * 32
 
 
 @torch.no_grad()

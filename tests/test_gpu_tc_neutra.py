@@ -14,7 +14,8 @@ from oracle.realnvp_ref import make_flow
 pytestmark = pytest.mark.gpu
 
 CASES = [(100, 2, 64, "fn", 300), (100, 4, 256, "g1", 1000), (64, 3, 32, "rb", 129), (16, 1, 32, "g0", 5), (32, 2, 128, "gm", 777),
-         (100, 3, 96, "g0", 260), (120, 2, 256, "fn", 131)]
+         (100, 3, 96, "g0", 260), (120, 2, 256, "fn", 131),
+         (100, 2, 5, "fn", 300), (100, 2, 40, "g0", 200)]      # default conditioner (H = 5) and H = 40: padded to 32 / 64
 
 
 def _setup(d, Lc, H, pot, perturb=0.05):
@@ -168,5 +169,8 @@ def test_tc_neutra_rejects_ineligible_shapes():
     assert N.lib().nfmc_neutra_tc_transposed_bytes(102, 2, 64) == -1          # d % 4 != 0
     assert N.lib().nfmc_neutra_tc_transposed_bytes(128, 2, 256) == -1         # shared-memory plan too large
     assert N.lib().nfmc_neutra_tc_transposed_bytes(100, 4, 256) > 0
-    assert not RealNVP((100,), conditioner_kwargs=dict(n_layers=2, n_hidden=40)).uses_tensor_cores_for_neutra()
-    assert not RealNVP((100,)).uses_tensor_cores_for_neutra()
+    # the packed images pad the hidden width to a multiple of 32, so every tensor-core flow with d % 4 == 0 is eligible
+    assert RealNVP((100,), conditioner_kwargs=dict(n_layers=2, n_hidden=40)).uses_tensor_cores_for_neutra()
+    assert not RealNVP((102,), conditioner_kwargs=dict(n_layers=2, n_hidden=64)).uses_tensor_cores_for_neutra()
+    assert not RealNVP((100,)).uses_tensor_cores_for_neutra()                 # default conditioner: fp32 unless opted in
+    assert RealNVP((100,), conditioner_dtype="bf16").uses_tensor_cores_for_neutra()
