@@ -81,6 +81,8 @@ if __name__ == "__main__":
         flow_spec='realnvp%{"n_layers": 2, "conditioner_kwargs": {"n_layers": 2, "n_hidden": 64}}', inner_kernel_kwargs={"step_size": 0.01})
     run("C3 neutra_hmc funnel d=100 n=262144 DEFAULT conditioner opted into bf16 (tcgen05 forward + dgrad, H = 5 padded to 32)", "neutra_hmc",
         "fn", 100, 262144, 3, flow_spec='realnvp%{"conditioner_dtype": "bf16"}', inner_kernel_kwargs={"step_size": 0.01})
+    run("C4 imh rosenbrock d=100 n=2^20 DEFAULT conditioner opted into bf16 (tcgen05 fused IMH iteration)", "imh", "rb", 100, 1 << 20, 20,
+        flow_spec='realnvp%{"conditioner_dtype": "bf16"}')
     run("wide-flow jump_mala d=100 n=2^20 H=256 Lc=4 (tcgen05)", "jump_mala", "g0", 100, 1 << 20, 5, K=100, flow_spec=wide)
     run("wide-flow imh d=100 n=2^20 H=256 Lc=4 (tcgen05)", "imh", "g0", 100, 1 << 20, 10, flow_spec=wide)
     run("wide-flow jump_mala K=1 (jump-dominated) d=100 n=2^20 H=256 Lc=4 (tcgen05)", "jump_mala", "g0", 100, 1 << 20, 10, K=1, flow_spec=wide)
