@@ -102,6 +102,25 @@ def test_readme_example_runs_with_a_lambda_target():
     assert out.running_samples.last_sample.shape == (100, 25)
 
 
+def test_callable_target_with_a_matrix_event_shape_and_non_unit_mass():
+    """event_shape = (4, 5): the callable sees [n, 4, 5]; HMC with a non-identity inverse mass; jump_hmc through the API."""
+    from copy import deepcopy
+    es = (4, 5)
+    fn = lambda x: (x ** 2).sum(dim=(1, 2))                                               # noqa: E731
+    imd = torch.linspace(0.5, 2.0, 20)
+    k = HMCKernel(event_size=20, inv_mass_diag=imd, step_size=0.05, n_leapfrog_steps=4)
+    a = HMC(es, nfmc_b200.potentials.StandardGaussian(es), deepcopy(k), HMCParameters(n_iterations=5))
+    b = HMC(es, fn, deepcopy(k), HMCParameters(n_iterations=5))
+    a.seed = b.seed = 11
+    x0 = 0.7 * torch.randn(257, *es)
+    oa, ob = a.sample(x0, show_progress=False), b.sample(x0, show_progress=False)
+    assert oa.samples.shape == ob.samples.shape == (5, 257, 4, 5)
+    assert abs(oa.statistics.n_accepted_trajectories - ob.statistics.n_accepted_trajectories) <= 2
+    assert float(torch.quantile((oa.samples - ob.samples).abs().flatten(), 0.99)) < 1e-4
+    out = nfmc_b200.sample(fn, event_shape=es, strategy="jump_hmc", n_chains=64, n_iterations=3, show_progress=False)
+    assert out.samples.shape == (3 * 6, 64, 4, 5) and bool(torch.isfinite(out.samples).all())
+
+
 def test_callable_target_thinning_and_moments():
     """Sample sink with thinning on the external path, and the stationary moments of N(0, I/2) under MALA."""
     d, n, K = 10, 2048, 60
