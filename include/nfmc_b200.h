@@ -263,6 +263,16 @@ NFMC_API int nfmc_ext_accept(float* x, const float* x_prime, const float* log_ra
                     float* aux_grad, const float* aux_grad_prime, const nfmc_stats* stats, const nfmc_sink* sink,
                     int32_t sink_step, void* stream);
 
+/* elliptical slice sampling around an external negative log-likelihood (mcmc/ess.py:12-64): the 2 + M scalar uniforms of a
+ * step as the fused kernel draws them (Philox stream 2); threshold / initial angle / bracket -> state [n][4] = {log y, theta,
+ * theta_min, theta_max}, found [n] = 0; f' = f cos(theta) + nu sin(theta); one bracket round given nll(f') */
+NFMC_API int nfmc_ext_ess_uniforms(uint64_t seed, uint64_t step, int64_t chain0, int64_t n, int32_t n_uniforms, float* out, void* stream);
+NFMC_API int nfmc_ext_ess_begin(const float* nll_cur, const float* uniforms, int32_t n_uniforms, int64_t n, float* state, int32_t* found,
+                       void* stream);
+NFMC_API int nfmc_ext_ess_rotate(const float* f, const float* nu, const float* state, int64_t n, int32_t d, float* f_prime, void* stream);
+NFMC_API int nfmc_ext_ess_update(float* f, const float* f_prime, float* nll_cur, const float* nll_prime, float* state, int32_t* found,
+                        const float* uniforms, int32_t n_uniforms, int32_t round, int64_t n, int32_t d, void* stream);
+
 /* NeuTra with an external target: grad_z [ U(T^-1 z) - log|det dT^-1/dz| ] (neutra.py:58-68) from z and grad_x = grad U(x) at
  * x = T^-1 z (which nfmc_realnvp_inverse gives): inverse pass + reversible backward sweep seeded with grad_x.  log_det
  * (optional, [n]) receives log|det dT^-1/dz|. */

@@ -118,6 +118,10 @@ SIGNATURES = {
     "nfmc_ext_jump_log_ratio": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "nfmc_ext_accept": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, P(StatsDesc), P(SinkDesc),
                                   _i32, _vp]),
+    "nfmc_ext_ess_uniforms": (C.c_int, [_u64, _u64, _i64, _i64, _i32, _vp, _vp]),
+    "nfmc_ext_ess_begin": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _vp]),
+    "nfmc_ext_ess_rotate": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "nfmc_ext_ess_update": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _vp]),
     "nfmc_neutra_pullback": (C.c_int, [P(RealNVPDesc), _vp, _vp, _vp, _vp, _i64, _vp]),
     "nfmc_potential_step": (C.c_int, [P(PotentialDesc), _vp, _i64, _f32, _vp]),
     "nfmc_dlmc_update": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _vp, _i64, _f32, _vp]),

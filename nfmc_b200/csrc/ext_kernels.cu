@@ -212,6 +212,78 @@ __global__ void __launch_bounds__(kExtThreads) ext_accept_kernel(const ExtAccept
   }
 }
 
+// ---- elliptical slice sampling around an external negative log-likelihood (mcmc/ess.py:12-64, identity prior) -----------
+constexpr float kExtPiF = 3.14159274101257324f;       // (float) torch.pi
+constexpr float kExtTwoPiF = 6.28318548202514648f;    // (float) (2 * torch.pi)
+
+// the 2 + M scalar uniforms of one step as the fused kernel draws them (ess_kernel.cu): Philox stream 2, counter quad
+// i / 4, word i % 4, lane 0 of the chain's group
+__global__ void ext_ess_uniforms_kernel(uint64_t seed, uint64_t step, long long chain0, long long n, int n_uni, float* __restrict__ out) {
+  const PhiloxKeys PK = philox_keys(seed);
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+    const RngKey ukey = make_rng_key(seed, 2u, step, (uint64_t)(chain0 + c));
+    uint4 uq = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = 0; i < n_uni; ++i) {
+      if ((i & 3) == 0) uq = rng_quad(PK, ukey, i >> 2, 0);
+      const uint32_t w = (i & 3) == 0 ? uq.x : (i & 3) == 1 ? uq.y : (i & 3) == 2 ? uq.z : uq.w;
+      out[c * n_uni + i] = uniform_from_bits(w);
+    }
+  }
+}
+
+// threshold log y = -nll(f) + log u (ess.py:35-36), initial angle theta = 2 pi u' and bracket [theta - 2 pi, theta] (:39-41)
+// state[n][4] = {log_y, theta, theta_min, theta_max}; found[n] = 0
+__global__ void ext_ess_begin_kernel(const float* __restrict__ nll_cur, const float* __restrict__ uniforms, int n_uni, long long n,
+                                     float4* __restrict__ state, int* __restrict__ found) {
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+    const float log_y = __fadd_rn(-__ldg(nll_cur + c), logf(__ldg(uniforms + c * n_uni)));
+    const float theta = __fmul_rn(__fmul_rn(__ldg(uniforms + c * n_uni + 1), 2.f), kExtPiF);
+    state[c] = make_float4(log_y, theta, __fsub_rn(theta, kExtTwoPiF), theta);
+    found[c] = 0;
+  }
+}
+
+// f' = f cos(theta) + nu sin(theta)   (ess.py:46)
+__global__ void __launch_bounds__(kExtThreads) ext_ess_rotate_kernel(const float* __restrict__ f, const float* __restrict__ nu,
+                                                                     const float4* __restrict__ state, long long n, int d,
+                                                                     float* __restrict__ fp) {
+  const int lane = threadIdx.x & 31;
+  for (long long row = (long long)blockIdx.x * kExtWarps + (threadIdx.x >> 5); row < n; row += (long long)gridDim.x * kExtWarps) {
+    float sn, cs;
+    sincosf(state[row].y, &sn, &cs);
+    const long long b = row * d;
+    for (int c = lane; c < d; c += 32)
+      fp[b + c] = __fadd_rn(__fmul_rn(__ldg(f + b + c), cs), __fmul_rn(__ldg(nu + b + c), sn));
+  }
+}
+
+// one bracket round (ess.py:47-62): a chain that has not found its point yet and whose proposal lies above the threshold
+// takes it; every chain shrinks its bracket towards 0 and draws the next angle from it
+__global__ void __launch_bounds__(kExtThreads) ext_ess_update_kernel(float* __restrict__ f, const float* __restrict__ fp,
+                                                                     float* __restrict__ nll_cur, const float* __restrict__ nll_p,
+                                                                     float4* __restrict__ state, int* __restrict__ found,
+                                                                     const float* __restrict__ uniforms, int n_uni, int round,
+                                                                     long long n, int d) {
+  const int lane = threadIdx.x & 31;
+  for (long long row = (long long)blockIdx.x * kExtWarps + (threadIdx.x >> 5); row < n; row += (long long)gridDim.x * kExtWarps) {
+    float4 st = state[row];
+    const int was_found = found[row];
+    const float up = __ldg(nll_p + row);
+    const bool upd = (-up > st.x) && !was_found;                                   // :47,50
+    if (upd) {
+      const long long b = row * d;
+      for (int c = lane; c < d; c += 32) f[b + c] = __ldg(fp + b + c);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      if (upd) { nll_cur[row] = up; found[row] = 1; }
+      if (st.y < 0.f) st.z = st.y; else st.w = st.y;                               // :53-55
+      st.y = __fadd_rn(__fmul_rn(__ldg(uniforms + row * n_uni + 2 + round), __fsub_rn(st.w, st.z)), st.z);   // :58-59
+      state[row] = st;
+    }
+  }
+}
+
 static int ext_grid(long long work_items, int per_cta) {
   long long grid = (work_items + per_cta - 1) / per_cta;
   const long long cap = 8ll * sm_count();          // 8 resident CTAs of 256 threads per SM
@@ -299,4 +371,33 @@ extern "C" int nfmc_ext_accept(float* x, const float* x_prime, const float* log_
   }
   ext_accept_kernel<<<ext_grid(n, kExtWarps * 4), kExtThreads, (size_t)2 * d * sizeof(float), (cudaStream_t)stream>>>(A);
   return check_cuda(cudaGetLastError(), "ext_accept_kernel launch");
+}
+
+extern "C" int nfmc_ext_ess_uniforms(uint64_t seed, uint64_t step, int64_t chain0, int64_t n, int32_t n_uniforms, float* out, void* stream) {
+  if (int e = ext_check(out && n >= 1 && n_uniforms >= 2, "ext_ess_uniforms")) return e;
+  ext_ess_uniforms_kernel<<<ext_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(seed, step, chain0, n, n_uniforms, out);
+  return check_cuda(cudaGetLastError(), "ext_ess_uniforms_kernel launch");
+}
+
+extern "C" int nfmc_ext_ess_begin(const float* nll_cur, const float* uniforms, int32_t n_uniforms, int64_t n, float* state, int32_t* found,
+                                  void* stream) {
+  if (int e = ext_check(nll_cur && uniforms && state && found && n >= 1 && n_uniforms >= 2 &&
+                        (reinterpret_cast<uintptr_t>(state) & 15) == 0, "ext_ess_begin")) return e;
+  ext_ess_begin_kernel<<<ext_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(nll_cur, uniforms, n_uniforms, n, reinterpret_cast<float4*>(state), found);
+  return check_cuda(cudaGetLastError(), "ext_ess_begin_kernel launch");
+}
+
+extern "C" int nfmc_ext_ess_rotate(const float* f, const float* nu, const float* state, int64_t n, int32_t d, float* f_prime, void* stream) {
+  if (int e = ext_check(f && nu && state && f_prime && n >= 1 && d >= 1 && d <= NFMC_MAX_DIM, "ext_ess_rotate")) return e;
+  ext_ess_rotate_kernel<<<ext_grid(n, kExtWarps), kExtThreads, 0, (cudaStream_t)stream>>>(f, nu, reinterpret_cast<const float4*>(state), n, d, f_prime);
+  return check_cuda(cudaGetLastError(), "ext_ess_rotate_kernel launch");
+}
+
+extern "C" int nfmc_ext_ess_update(float* f, const float* f_prime, float* nll_cur, const float* nll_prime, float* state, int32_t* found,
+                                   const float* uniforms, int32_t n_uniforms, int32_t round, int64_t n, int32_t d, void* stream) {
+  if (int e = ext_check(f && f_prime && nll_cur && nll_prime && state && found && uniforms && n >= 1 && d >= 1 && d <= NFMC_MAX_DIM &&
+                        round >= 0 && round + 2 < n_uniforms, "ext_ess_update")) return e;
+  ext_ess_update_kernel<<<ext_grid(n, kExtWarps), kExtThreads, 0, (cudaStream_t)stream>>>(f, f_prime, nll_cur, nll_prime,
+      reinterpret_cast<float4*>(state), found, uniforms, n_uniforms, round, n, d);
+  return check_cuda(cudaGetLastError(), "ext_ess_update_kernel launch");
 }

@@ -99,6 +99,43 @@ def hmc_steps(target, ses, n_steps: int, step_size: float, n_leapfrog: int, imd,
                                         None, None, C.byref(st), _sink_ref(sink), k, s))
 
 
+def ess_steps(nll, ses, n_steps: int, max_iterations: int, sink, normals=None, uniforms=None):
+    """K elliptical-slice steps with prior N(0, I) around a callable negative log-likelihood (mcmc/ess.py:12-64,97-116):
+    per step the ellipse direction nu (Philox stream 0 or injected), the 2 + M scalar uniforms (Philox stream 2 or injected
+    ``[steps, n, 2 + M]``), then at most M bracket rounds of [rotate, evaluate the callable, shrink].  Every chain counts as
+    accepted (ess.py:107); counts[3] collects the chain-steps whose bracket produced a point."""
+    lib = N.lib()
+    n, d, s, dev = ses.n, ses.d, ses.stream, ses.device
+    M = int(max_iterations)
+    n_uni = 2 + M
+    f = ses.x
+    u_cur = nll.value(f)
+    fp = torch.empty_like(f)
+    state = torch.empty(n, 4, device=dev, dtype=torch.float32)
+    found = torch.empty(n, device=dev, dtype=torch.int32)
+    st = ses.stats()
+    for k in range(n_steps):
+        step = ses.local_step + k
+        nu, _ = _step_noise(ses, 0, step, normals, None, k, need_uniform=False)
+        if uniforms is not None:
+            un = uniforms[k].reshape(n, n_uni).contiguous()
+        else:
+            un = torch.empty(n, n_uni, device=dev, dtype=torch.float32)
+            N.check(lib.nfmc_ext_ess_uniforms(ses.seed & 0xFFFFFFFFFFFFFFFF, step, ses.chain0, n, n_uni, N.ptr(un), s))
+        N.check(lib.nfmc_ext_ess_begin(N.ptr(u_cur), N.ptr(un), n_uni, n, N.ptr(state), N.ptr(found), s))
+        for it in range(M):
+            if it > 0 and bool(found.all()):                             # later rounds cannot change a found chain (ess.py:50)
+                break
+            N.check(lib.nfmc_ext_ess_rotate(N.ptr(f), N.ptr(nu), N.ptr(state), n, d, N.ptr(fp), s))
+            u_p = nll.value(fp)
+            N.check(lib.nfmc_ext_ess_update(N.ptr(f), N.ptr(fp), N.ptr(u_cur), N.ptr(u_p), N.ptr(state), N.ptr(found), N.ptr(un),
+                                            n_uni, it, n, d, s))
+        ses.counts[3] += found.sum()
+        # the mask is all ones (ess.py:107): moments, counters and the sample row of the post-step state
+        N.check(lib.nfmc_ext_accept(N.ptr(f), N.ptr(f), None, None, 0, n, d, None, None, None, None, None, None, C.byref(st),
+                                    _sink_ref(sink), k, s))
+
+
 def flow_proposal(flow, ses, z: Optional[torch.Tensor], uniforms: Optional[torch.Tensor]):
     """x' = T^-1(z) with log q(x') for every chain (jump.py:205, imh.py:221): base draw from Philox stream 1 at the
     session's flow step, or injected.  Returns (x' [n,d], log q(x') [n], uniforms [n])."""

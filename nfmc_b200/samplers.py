@@ -147,7 +147,7 @@ def _require_analytic(target, who: str):
         raise NotImplementedError(
             f"{who} needs a built-in analytic potential (nfmc_b200.potentials.*): its kernels evaluate the target inside the "
             f"flow sweep.  Callable targets are supported by mala / ula / hmc / uhmc / mh / random walk, their jump_* "
-            f"variants, imh, adaptive_imh, neutra_hmc and neutra_mh.")
+            f"variants, ess / jump_ess, imh, adaptive_imh, neutra_hmc and neutra_mh.")
 
 
 def _imd_device(kernel: MetropolisKernel, device) -> Optional[torch.Tensor]:
@@ -415,7 +415,6 @@ class ESS(MetropolisSampler):
                  params: Optional[ESSParameters] = None):
         super().__init__(event_shape, target, kernel or ESSKernel(tuple(event_shape)), params or ESSParameters())
         self.negative_log_likelihood = resolve_target(negative_log_likelihood, self.event_shape)
-        _require_analytic(self.negative_log_likelihood, "ESS (negative_log_likelihood)")
 
     @property
     def name(self):
@@ -435,6 +434,9 @@ class ESS(MetropolisSampler):
         N.check(N.lib().nfmc_rng_fill(C.byref(rng), 3, ses.chain0, ses.d, ses.n, 1, N.ptr(ses.x), None, ses.stream))
 
     def _launch(self, ses, n_steps, sink, normals=None, uniforms=None):
+        if self.negative_log_likelihood.external:                 # callable likelihood: bracket rounds around its evaluation
+            return external.ess_steps(self.negative_log_likelihood, ses, n_steps, int(self.params.max_ess_step_iterations), sink,
+                                      normals, uniforms)
         pot, keep = self.negative_log_likelihood.descriptor(ses.device)
         rng = N.rng_desc(ses.seed, ses.local_step, normals, uniforms)
         st = ses.stats()

@@ -175,7 +175,7 @@ def test_unsupported_strategy_and_target_raise():
     assert sorted(nfmc_b200.get_supported_samplers()) == sorted([
         "hmc", "uhmc", "ula", "mala", "mh", "ess", "imh", "fixed_imh", "adaptive_imh", "jump_mala", "jump_ula", "jump_hmc",
         "jump_uhmc", "jump_ess", "jump_mh", "neutra_mh", "neutra_hmc", "tess", "dlmc"])        # reference: util.py:421-444
-    with pytest.raises(NotImplementedError):       # the slice samplers evaluate the likelihood inside their kernels: analytic only
+    with pytest.raises(NotImplementedError):       # transport ESS evaluates the likelihood inside the flow sweep: analytic only
         sample(_g((6,)), event_shape=(6,), strategy="tess", n_chains=4, n_iterations=2, show_progress=False,
                negative_log_likelihood=lambda x: (x ** 2).sum(-1))
     with pytest.raises(TypeError):

@@ -35,14 +35,19 @@ def _split_ess_tape(normals, uniforms, K, M):
     return x0, nu, un
 
 
-def test_golden_ess():
+# ext = True: target / likelihood are plain Python callables -> external-target path (autograd-free here: ESS only evaluates)
+EXT = pytest.mark.parametrize("ext", [False, True], ids=["fused", "callable"])
+
+
+@EXT
+def test_golden_ess(ext):
     from gpu_util import product_target
     from nfmc_b200.records import ESSKernel, ESSParameters, MCMCOutput
     from nfmc_b200.samplers import ESS, DeviceSession
     g = load_case("ess_fn")
     n, d = g["x0"].shape
     K, M = int(g["K"]), int(g["M"])
-    nll = product_target(g["pot"], d)
+    nll = product_target(g["pot"], d, callable_target=ext)
     s = ESS((d,), nll, nll, ESSKernel(event_shape=(d,)), ESSParameters(n_iterations=K, max_ess_step_iterations=M))
     x0, nu, un = _split_ess_tape(g["normals"], g["uniforms"], K, M)
     out = MCMCOutput((d,), store_samples=True)
@@ -60,14 +65,15 @@ def test_golden_ess():
     close(sx2 / (n * K), g["second_moment"], atol=2e-5 * max(1.0, float(np.abs(g["second_moment"]).max())))
 
 
-def test_golden_jump_ess():
+@EXT
+def test_golden_jump_ess(ext):
     from gpu_util import product_target, product_flow_from_oracle
     from nfmc_b200.records import ESSKernel, ESSParameters, NFMCKernel, JumpNFMCParameters
     from nfmc_b200.samplers import JumpESS
     g = load_case("jump_ess_gm")
     n, d = g["x0"].shape
     T, K, M = int(g["T"]), int(g["K"]), int(g["M"])
-    s = JumpESS((d,), product_target(g["pot"], d), product_target(g["nll"], d),
+    s = JumpESS((d,), product_target(g["pot"], d, callable_target=ext), product_target(g["nll"], d, callable_target=ext),
                 kernel=NFMCKernel((d,), flow=product_flow_from_oracle(oracle_flow(g))),
                 params=JumpNFMCParameters(n_iterations=T), inner_kernel=ESSKernel(event_shape=(d,)),
                 inner_params=ESSParameters(n_iterations=K, max_ess_step_iterations=M))

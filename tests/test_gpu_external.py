@@ -91,6 +91,24 @@ def test_jump_and_imh_callable_equal_fused_in_philox_mode():
     assert a.statistics.n_target_calls == b.statistics.n_target_calls
 
 
+def test_ess_callable_equals_fused_in_philox_mode():
+    """ESS with a lambda likelihood draws nu (stream 0) and its 2 + M scalar uniforms (stream 2) from the same Philox counters
+    as the fused kernel: same prior restart, same brackets, same states up to fp32 reduction order."""
+    from nfmc_b200.records import ESSKernel, ESSParameters
+    from nfmc_b200.samplers import ESS
+    d, n, K, M = 25, 333, 6, 5
+    outs = []
+    for nll in (nfmc_b200.potentials.StandardGaussian((d,)), readme_target):
+        s = ESS((d,), nll, nll, ESSKernel(event_shape=(d,)), ESSParameters(n_iterations=K, max_ess_step_iterations=M))
+        s.seed = 21
+        outs.append(s.sample(torch.randn(n, d), show_progress=False))
+    a, b = outs
+    assert a.samples.shape == b.samples.shape == (K, n, d)
+    assert float(torch.quantile((a.samples - b.samples).abs().flatten(), 0.99)) < 1e-4
+    assert a.statistics.n_accepted_trajectories == b.statistics.n_accepted_trajectories == n * K
+    assert a.statistics.n_target_calls == b.statistics.n_target_calls
+
+
 def test_readme_example_runs_with_a_lambda_target():
     """The reference README's own call (README.md:40-52), here with fewer iterations."""
     torch.manual_seed(0)
