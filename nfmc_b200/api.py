@@ -41,8 +41,8 @@ def create_sampler(target, event_shape: Optional[Tuple[int, ...]] = None, flow: 
 
     if flow is not None and not isinstance(flow, str):
         event_shape = flow.event_shape
-    elif isinstance(target, Potential):
-        event_shape = target.event_shape
+    elif isinstance(target, Potential) or (callable(target) and hasattr(target, 'event_shape')):
+        event_shape = tuple(target.event_shape)   # our potentials, or any `potentials.base.Potential`-like callable (sample.py:65-66)
     if event_shape is None:
         raise ValueError("event_shape is required")
     event_shape = tuple(event_shape)
@@ -146,8 +146,8 @@ def sample(target, event_shape: Optional[Tuple[int, ...]] = None, flow: Optional
         flow = None
     if flow is not None and not isinstance(flow, str):
         event_shape = flow.event_shape
-    elif isinstance(target, Potential):
-        event_shape = target.event_shape
+    elif isinstance(target, Potential) or (callable(target) and hasattr(target, 'event_shape')):
+        event_shape = tuple(target.event_shape)   # our potentials, or any `potentials.base.Potential`-like callable (sample.py:65-66)
     kwargs['param_kwargs'] = {**kwargs.get('param_kwargs', {}),
                               'n_iterations': n_iterations, 'n_warmup_iterations': n_warmup_iterations}
     sampler = create_sampler(target=target, event_shape=event_shape, flow=flow, strategy=strategy, **kwargs)

@@ -60,6 +60,15 @@ def test_no_cpu_fallback():
     with pytest.raises(TypeError):
         nfmc_b200.potentials.resolve_target(3.0, (5,))
 
+    class ForeignPotential:                      # duck-typed like potentials.base.Potential: callable with .event_shape
+        event_shape = (3, 2)
+
+        def __call__(self, x):
+            return (x ** 2).flatten(1).sum(1)
+
+    t = nfmc_b200.potentials.resolve_target(ForeignPotential(), (3, 2))
+    assert t.external and t.n_dim == 6
+
 
 def test_flow_state_dict_is_interchangeable_with_oracle():
     from nfmc_b200.flow import Flow, RealNVP
