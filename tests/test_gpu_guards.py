@@ -195,3 +195,72 @@ def test_guards_local_kernels_and_cuda_core_flow(d, n, K):
     N.check(N.lib().nfmc_potential_eval(C.byref(pd), N.ptr(x), N.ptr(u), N.ptr(g), n, s))
     G.check()
     assert bool(torch.isfinite(x).all())
+
+
+@pytest.mark.parametrize("n,d,M", [(33, 7, 3), (1, 100, 0), (517, 25, 5), (4099, 1024, 2)])
+def test_guards_external_target_kernels(n, d, M):
+    """Every nfmc_ext_* entry point and nfmc_neutra_pullback on guarded buffers, sizes off the warp / CTA granularity."""
+    from nfmc_b200 import _native as N
+    lib = N.lib()
+    G = Guarded()
+    torch.manual_seed(n + d)
+    s = N.stream_ptr(torch.device("cuda"))
+    x = G.make((n, d), fill=torch.randn(n, d))
+    xp = G.make((n, d))
+    g = G.make((n, d), fill=torch.randn(n, d))
+    gp = G.make((n, d), fill=torch.randn(n, d))
+    nz = G.make((n, d), fill=torch.randn(n, d))
+    u = G.make((n,), fill=torch.rand(n))
+    up = G.make((n,), fill=torch.rand(n))
+    lr = G.make((n,))
+    un = G.make((n,), fill=torch.rand(n))
+    imd = G.make((d,), fill=0.5 + torch.rand(d))
+    p = G.make((n, d))
+    kin = G.make((n,))
+    mom = G.make((2 * d,), dtype=torch.float64)
+    cnt = G.make((4,), dtype=torch.int64)
+    rows = G.make((2, n, d))
+    st = N.StatsDesc(mom.data_ptr(), mom.data_ptr() + 8 * d, cnt.data_ptr())
+    sink = N.SinkDesc(rows.data_ptr(), 0, 2)                          # thinning 2: steps 0 and 2 are kept
+    for m in (None, imd):
+        N.check(lib.nfmc_ext_langevin_propose(N.ptr(x), N.ptr(g), N.ptr(nz), N.ptr(m), 0.1, 0, n, d, N.ptr(xp), s))
+        N.check(lib.nfmc_ext_langevin_propose(N.ptr(x), None, N.ptr(nz), N.ptr(m), 1.0, 1, n, d, N.ptr(xp), s))
+        N.check(lib.nfmc_ext_langevin_log_ratio(N.ptr(x), N.ptr(xp), N.ptr(g), N.ptr(gp), N.ptr(u), N.ptr(up), N.ptr(m), 0.1, 0, n, d,
+                                                N.ptr(lr), s))
+        N.check(lib.nfmc_ext_hmc_momentum(N.ptr(nz), N.ptr(m), n, d, N.ptr(p), N.ptr(kin), s))
+        N.check(lib.nfmc_ext_hmc_leapfrog(N.ptr(xp), N.ptr(p), N.ptr(g), N.ptr(m), 0.05, 2, 1, n, d, s))
+        N.check(lib.nfmc_ext_hmc_log_ratio(N.ptr(p), N.ptr(m), N.ptr(u), N.ptr(kin), N.ptr(up), n, d, N.ptr(lr), s))
+    N.check(lib.nfmc_ext_jump_log_ratio(N.ptr(u), N.ptr(up), N.ptr(kin), N.ptr(un), n, N.ptr(lr), s))
+    for k in range(3):
+        N.check(lib.nfmc_ext_accept(N.ptr(x), N.ptr(xp), N.ptr(lr), N.ptr(un), 1, n, d, N.ptr(u), N.ptr(up), N.ptr(kin), N.ptr(un),
+                                    N.ptr(g), N.ptr(gp), C.byref(st), C.byref(sink), k, s))
+    assert int(cnt[1]) == 3 * n and 0 <= int(cnt[0]) <= 3 * n
+    # elliptical slice pieces
+    n_uni = 2 + M
+    uni = G.make((n, n_uni))
+    state = G.make((n, 4))
+    found = G.make((n,), dtype=torch.int32)
+    N.check(lib.nfmc_ext_ess_uniforms(5, 7, 11, n, n_uni, N.ptr(uni), s))
+    assert float(uni.min()) >= 0.0 and float(uni.max()) < 1.0
+    N.check(lib.nfmc_ext_ess_begin(N.ptr(u), N.ptr(uni), n_uni, n, N.ptr(state), N.ptr(found), s))
+    for it in range(M):
+        N.check(lib.nfmc_ext_ess_rotate(N.ptr(x), N.ptr(nz), N.ptr(state), n, d, N.ptr(xp), s))
+        N.check(lib.nfmc_ext_ess_update(N.ptr(x), N.ptr(xp), N.ptr(u), N.ptr(up), N.ptr(state), N.ptr(found), N.ptr(uni), n_uni, it, n, d, s))
+    G.check()
+    assert bool(torch.isfinite(x).all()) and bool(torch.isfinite(mom).all())
+
+
+@pytest.mark.parametrize("d,Lc,ck,n", [(7, 3, dict(n_layers=3, n_hidden=6), 33), (100, 2, None, 1031), (26, 3, None, 1)])
+def test_guards_neutra_pullback(d, Lc, ck, n):
+    from gpu_util import product_flow_from_oracle
+    from nfmc_b200 import _native as N
+    flow = product_flow_from_oracle(make_flow((d,), n_layers=Lc, conditioner_kwargs=ck, perturb=0.05, seed=d))
+    G = Guarded()
+    z = G.make((n, d), fill=0.5 * torch.randn(n, d))
+    gx = G.make((n, d), fill=torch.randn(n, d))
+    gz = G.make((n, d))
+    ld = G.make((n,))
+    fd, keep = flow.bijection.descriptor(torch.device("cuda"))
+    N.check(N.lib().nfmc_neutra_pullback(C.byref(fd), N.ptr(z), N.ptr(gx), N.ptr(gz), N.ptr(ld), n, N.stream_ptr(torch.device("cuda"))))
+    G.check()
+    assert bool(torch.isfinite(gz).all()) and bool(torch.isfinite(ld).all())
