@@ -180,8 +180,23 @@ class RealNVP(_Layer):
             self._packed_tc[key] = (ver, pack_realnvp_tc_transposed(self).to(device))
         return self._packed_tc[key][1]
 
-    def uses_tensor_cores_for_neutra(self) -> bool:
-        return self.uses_tensor_cores() and neutra_tc_supported(self.n_dim, *self.conditioner_shape(), self.n_coupling)
+    #: 'auto' sends a DEFAULT (narrow, H <= 8) conditioner to the tensor-core NeuTra kernels from this many chains on: there the
+    #: tcgen05 path is 1.5x the fp32 CUDA-core kernel (C3, 262 144 chains: 3.76e7 vs 2.51e7 chain-steps/s), below it the run is
+    #: launch-bound and the single fused fp32 launch wins
+    NEUTRA_AUTO_MIN_CHAINS = 32768
+
+    def uses_tensor_cores_for_neutra(self, n_chains: Optional[int] = None) -> bool:
+        """Whether NeuTra-HMC takes the tensor-core kernels (csrc/tc_neutra.cu) for this flow.  ``conditioner_dtype='bf16'``:
+        whenever the shape is eligible; ``'fp32'``: never; ``'auto'``: wide conditioners (H > 8) always, default ones only for
+        ``n_chains >= NEUTRA_AUTO_MIN_CHAINS`` (the north star's bf16-conditioner tolerance, rtol 1e-2, applies on that path)."""
+        shape = (self.n_dim, *self.conditioner_shape())
+        if not neutra_tc_supported(*shape, self.n_coupling):
+            return False
+        if self.conditioner_dtype == "bf16":
+            return True
+        if self.conditioner_dtype != "auto":
+            return False
+        return tc_eligible(*shape) or (n_chains is not None and n_chains >= self.NEUTRA_AUTO_MIN_CHAINS)
 
     def descriptor(self, device: torch.device):
         blob = self.blob(device)

@@ -920,7 +920,7 @@ class NeuTraHMC(Sampler):
 
     def _launch_latent(self, ses, pot, fd, k, imd, rng, st, sink):
         bij = self.kernel.flow.bijection
-        if bij.uses_tensor_cores_for_neutra():
+        if bij.uses_tensor_cores_for_neutra(ses.n):
             # wide flow: conditioner forward and input-VJP on tcgen05 (csrc/tc_neutra.cu)
             dev = ses.device
             td, keep = bij.tc_descriptor(dev)

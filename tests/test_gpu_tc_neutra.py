@@ -174,3 +174,6 @@ def test_tc_neutra_rejects_ineligible_shapes():
     assert not RealNVP((102,), conditioner_kwargs=dict(n_layers=2, n_hidden=64)).uses_tensor_cores_for_neutra()
     assert not RealNVP((100,)).uses_tensor_cores_for_neutra()                 # default conditioner: fp32 unless opted in
     assert RealNVP((100,), conditioner_dtype="bf16").uses_tensor_cores_for_neutra()
+    # 'auto': a default conditioner goes to the tensor cores only for large batches (where it is 1.5x faster); 'fp32' never
+    assert RealNVP((100,)).uses_tensor_cores_for_neutra(1 << 18) and not RealNVP((100,)).uses_tensor_cores_for_neutra(1000)
+    assert not RealNVP((100,), conditioner_dtype="fp32").uses_tensor_cores_for_neutra(1 << 18)

@@ -63,7 +63,10 @@ if __name__ == "__main__":
     wide = 'realnvp%{"n_layers": 4, "conditioner_kwargs": {"n_layers": 2, "n_hidden": 256}}'
     run("C1 README jump_mala d=25 n=100", "jump_mala", "g0", 25, 100, 200, K=100)
     run("C2 jump_hmc d=100 n=65536", "jump_hmc", "g1", 100, 65536, 20, K=5)
-    run("C3 neutra_hmc funnel d=100 n=262144", "neutra_hmc", "fn", 100, 262144, 3, inner_kernel_kwargs={"step_size": 0.01})
+    run("C3 neutra_hmc funnel d=100 n=262144 (default flow, conditioner_dtype='auto' -> tcgen05 at this batch size)", "neutra_hmc", "fn", 100,
+        262144, 3, inner_kernel_kwargs={"step_size": 0.01})
+    run("C3 neutra_hmc funnel d=100 n=262144, conditioner_dtype='fp32' (CUDA-core kernel)", "neutra_hmc", "fn", 100, 262144, 3,
+        flow_spec='realnvp%{"conditioner_dtype": "fp32"}', inner_kernel_kwargs={"step_size": 0.01})
     run("C4 imh rosenbrock d=100 n=2^20", "imh", "rb", 100, 1 << 20, 20)
     run("C4 adaptive_imh(no refit) d=100 n=2^17", "adaptive_imh", "rb", 100, 1 << 17, 100)
     run("C4 adaptive_imh WITH per-iteration refit d=100 n=2^17", "adaptive_imh", "rb", 100, 1 << 17, 24, adapt=True)
