@@ -168,6 +168,9 @@ def _device_scoped(fn):
     @functools.wraps(fn)
     def wrapper(self, x0, *args, **kwargs):
         dev = N.require_cuda(self.device if self.device is not None else (x0.device if torch.is_tensor(x0) and x0.is_cuda else None))
+        if torch.is_tensor(x0) and x0.ndim >= 1 and x0.shape[0] == 0:
+            # the reference divides by zero in its acceptance-rate bookkeeping on an empty batch (sampling/base.py:90-97)
+            raise ValueError("x0 holds no chains (shape %s): nothing to sample" % (tuple(x0.shape),))
         with torch.cuda.device(dev):
             return fn(self, x0, *args, **kwargs)
 
