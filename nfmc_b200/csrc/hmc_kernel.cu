@@ -224,13 +224,42 @@ __global__ void __launch_bounds__(kThreads, NFMC_HMC_MINB) hmc_fast_kernel(const
   const int cpc = kThreads / C.gs;
   const long long tiles = (C.n + cpc - 1) / cpc;
   const float half_tau = A.tau / 2;
-  const float2 TAU = splat2(A.tau), NHT = splat2(-half_tau);
   const PhiloxKeys PK = philox_keys(C.rng.seed);
   unsigned int n_acc = 0, n_bad = 0;
   constexpr int NQ = (E + 2) / 2;
   constexpr bool CTX = pot_grad_needs_ctx<POT>();
+  constexpr bool DIAG = POT == NFMC_POT_DIAG_GAUSSIAN;
   const int k_last = g.j + g.gs * (E - 1);
   const bool vl_last = k_last < g.da, vh_last = k_last < g.db;   // only the last slot can be invalid in an exact layout
+  // Invalid slots are kept at exactly zero WITHOUT select instructions inside the trajectory: the state and the masked
+  // momentum draw start at 0 there, and the last slot's step constants are 0 in its invalid components, so drift and
+  // kicks leave them at 0 (the selects and the predicates re-derived for them were 20 % of the loop's issue slots).
+  const float2 TAU = splat2(A.tau), NHT = splat2(-half_tau);
+  const float2 TAU_L = make_float2(vl_last ? A.tau : 0.f, vh_last ? A.tau : 0.f);
+  const float2 NHT_L = make_float2(vl_last ? -half_tau : 0.f, vh_last ? -half_tau : 0.f);
+  // Diagonal Gaussian: this lane's precisions {w[k], w[da + k]} and negated means per slot, staged once in shared memory
+  // (zero in invalid slots) -- the gradient is then one packed multiply per slot instead of two parameter loads from
+  // global memory per slot and leapfrog.  `centered` (every mean is 0, e.g. the ill-conditioned Gaussian of config C2)
+  // drops the subtraction: x - 0 == x bit for bit.
+  // (one entry per slot and LANE, so that every access is this thread's base pointer + a compile-time offset)
+  float2* wt = reinterpret_cast<float2*>(smem + off + (size_t)E * kThreads * sizeof(float4));
+  float2* nm = wt + E * 32;
+  bool centered = true;
+  if constexpr (DIAG) {
+    const float2* wm = reinterpret_cast<const float2*>(C.pot.params);
+    int any_mean = 0;
+    for (int i = threadIdx.x; i < E * 32; i += kThreads) {
+      const int e = i >> 5, kk = ((i & 31) & (g.gs - 1)) + g.gs * e;
+      const float2 pl = kk < g.da ? __ldg(wm + kk) : make_float2(0.f, 0.f);
+      const float2 ph = kk < g.db ? __ldg(wm + g.da + kk) : make_float2(0.f, 0.f);
+      wt[i] = make_float2(pl.x, ph.x);
+      nm[i] = make_float2(-pl.y, -ph.y);
+      any_mean |= (pl.y != 0.f) | (ph.y != 0.f);
+    }
+    centered = !__syncthreads_or(any_mean);
+    wt += g.j;      // lanes with the same j read the same address: one shared-memory wavefront per access
+    nm += g.j;
+  }
 
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const long long chain_raw = tile * cpc + threadIdx.x / C.gs;
@@ -253,9 +282,14 @@ __global__ void __launch_bounds__(kThreads, NFMC_HMC_MINB) hmc_fast_kernel(const
       for (int e = 0; e < E; ++e) { lo[e] = v[e].x; hi[e] = v[e].y; }
       return pot_prepare<POT, E>(C.pot, g, lo, hi);
     };
-    auto grad = [&](const PotCtx& c, int e, float2 v) {
+    // `cen` (a std::bool_constant): the diagonal Gaussian's means are all zero -- decided once per kernel, so the
+    // trajectory exists in two straight-line versions instead of carrying both operands and a select per slot
+    auto grad = [&](auto cen, const PotCtx& c, int e, float2 v) {
       if constexpr (POT == NFMC_POT_ISO_GAUSSIAN) {
         return mul2(splat2(C.pot.s0), v);
+      } else if constexpr (DIAG) {
+        if constexpr (decltype(cen)::value) return mul2(wt[e * 32], v);
+        else return mul2(wt[e * 32], add2(v, nm[e * 32]));
       } else {
         float glo, ghi;
         if (e < E - 1) pot_grad<POT, true>(C.pot, c, g, g.j + g.gs * e, v.x, v.y, glo, ghi);
@@ -274,6 +308,8 @@ __global__ void __launch_bounds__(kThreads, NFMC_HMC_MINB) hmc_fast_kernel(const
       float2 p[E], xt[E];
       float kin0 = 0.f;
       uint32_t ubits = 0;
+      PotCtx cur = ctx;
+      auto propose = [&](auto cen) {
       // ---- momentum p = xi (hmc.py:100), first half-kick with grad U(x0) (hmc.py:51-53) ---------------------------------
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
@@ -287,28 +323,35 @@ __global__ void __launch_bounds__(kThreads, NFMC_HMC_MINB) hmc_fast_kernel(const
           box_muller(hh ? w.z : w.x, hh ? w.w : w.y, nlo, nhi);
           const float2 nz = mask_last(e, make_float2(nlo, nhi));
           kin0 = fmaf(nz.x * nz.x, 1.f, fmaf(nz.y * nz.y, 1.f, kin0));
-          const float2 gv = grad(ctx, e, x[e]);
-          p[e] = (A.n_leapfrog > 0) ? fma2(NHT, gv, nz) : nz;
+          const float2 gv = grad(cen, ctx, e, x[e]);
+          p[e] = (A.n_leapfrog > 0) ? fma2(e == E - 1 ? NHT_L : NHT, gv, nz) : nz;
           xt[e] = x[e];
         }
       }
       // ---- trajectory (hmc.py:61-77) -----------------------------------------------------------------------------
-      PotCtx cur = ctx;
       for (int l = 0; l < A.n_leapfrog; ++l) {
         const bool more = l + 1 < A.n_leapfrog;
         if (CTX) {
 #pragma unroll
-          for (int e = 0; e < E; ++e) xt[e] = mask_last(e, fma2(TAU, p[e], xt[e]));          // hmc.py:56-58
+          for (int e = 0; e < E; ++e) xt[e] = fma2(e == E - 1 ? TAU_L : TAU, p[e], xt[e]);    // hmc.py:56-58
           cur = prepare(xt);
         }
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-          if (!CTX) xt[e] = mask_last(e, fma2(TAU, p[e], xt[e]));
-          const float2 gv = grad(cur, e, xt[e]);
-          float2 pv = fma2(NHT, gv, p[e]);                                                  // second half-kick
-          if (more) pv = fma2(NHT, gv, pv);                                                 // next step's first
-          p[e] = mask_last(e, pv);
+          if (!CTX) xt[e] = fma2(e == E - 1 ? TAU_L : TAU, p[e], xt[e]);
+          const float2 gv = grad(cen, cur, e, xt[e]);
+          const float2 nht = e == E - 1 ? NHT_L : NHT;
+          float2 pv = fma2(nht, gv, p[e]);                                                  // second half-kick
+          if (more) pv = fma2(nht, gv, pv);                                                 // next step's first
+          p[e] = pv;
         }
+      }
+      };
+      if constexpr (DIAG) {
+        if (centered) propose(std::true_type{});
+        else propose(std::false_type{});
+      } else {
+        propose(std::true_type{});
       }
       bool accept = true;
       if (!CTX && A.n_leapfrog > 0) cur = prepare(xt);
@@ -380,10 +423,12 @@ template <int E>
 int launch_hmc(int pot_kind, bool exact, const LocalArgs& A, int grid, size_t smem, cudaStream_t s) {
   NFMC_DISPATCH_POT(pot_kind, {
     if (exact && !A.c.rng.normals && !A.imd) {
-      // measured (2^20 chains, d = 100, L = 20, ms per step, packed vs scalar): iso 0.62 / 0.67, funnel 1.02 / 1.19,
-      // mixture 1.71 / 1.81, diagonal 1.11 / 0.88, Rosenbrock 0.84 / 0.77 -- potentials whose gradient reads
-      // per-dimension parameters or pairs elements keep the scalar kernel
-      constexpr bool PACKED = POT == NFMC_POT_ISO_GAUSSIAN || POT == NFMC_POT_FUNNEL || POT == NFMC_POT_MIXTURE4;
+      // measured (2^20 chains, d = 100, L = 20, ms per step, packed vs scalar): iso 0.55 / 0.67, funnel 1.00 / 1.19,
+      // mixture 1.64 / 1.81, diagonal 0.64 / 0.83 (precisions staged per lane in shared memory; with two parameter loads
+      // from global memory per slot and leapfrog the packed form took 1.11), Rosenbrock 0.84 / 0.73 -- its gradient pairs
+      // the two halves of a slot, so it keeps the scalar kernel
+      constexpr bool PACKED = POT == NFMC_POT_ISO_GAUSSIAN || POT == NFMC_POT_FUNNEL || POT == NFMC_POT_MIXTURE4 ||
+                              POT == NFMC_POT_DIAG_GAUSSIAN;
       if constexpr (PACKED) {
         NFMC_SET_SMEM_RET((hmc_fast_kernel<POT, E>), smem);
         hmc_fast_kernel<POT, E><<<occupancy_grid(hmc_fast_kernel<POT, E>, smem, A.c.n, A.c.gs), kThreads, smem, s>>>(A);

@@ -159,7 +159,9 @@ extern "C" int nfmc_hmc_steps(const nfmc_potential* pot, float* x, int64_t n, in
   LocalArgs A;
   fill_chain_args(A.c, pot, x, n, n_steps, rng, chain0, stats, sink, L);
   A.tau = step_size; A.sqrt_2tau = 0.f; A.imd = inv_mass_diag; A.adjusted = adjusted; A.n_leapfrog = n_leapfrog; A.random_walk = 0;
-  const size_t smem = local_smem_bytes(pot->d, inv_mass_diag != nullptr, sizeof(float4), L.E);
+  size_t smem = local_smem_bytes(pot->d, inv_mass_diag != nullptr, sizeof(float4), L.E);
+  // the packed kernel stages a diagonal Gaussian's per-lane precisions and negated means: 2 x [E][32] float2
+  if (pot->kind == NFMC_POT_DIAG_GAUSSIAN) smem += (size_t)2 * L.E * 32 * sizeof(float2);
   const int grid = grid_for(n, L.gs, 4);
   cudaStream_t s = (cudaStream_t)stream;
   NFMC_DISPATCH_E(L.E, { return launch_hmc<E>(pot->kind, L.exact, A, grid, smem, s); });

@@ -428,11 +428,16 @@ def test_hmc_philox_mode_equals_injected_mode():
     from nfmc_b200.records import HMCKernel, HMCParameters, MCMCOutput
     from nfmc_b200.samplers import HMC, DeviceSession
     dev = torch.device("cuda")
-    for pot, d, tau in (("g1", 100, 0.02), ("fn", 26, 0.05), ("g0", 1000, 0.05)):
+    from nfmc_b200.potentials import DiagonalGaussian
+    # "dg": a diagonal Gaussian WITH means (the packed kernel's staged-table path keeps the subtraction), d = 99 and 1000:
+    # odd split, invalid lanes in the last slot
+    for pot, d, tau in (("g1", 100, 0.02), ("fn", 26, 0.05), ("g0", 1000, 0.05), ("dg", 99, 0.05), ("dg", 1000, 0.05), ("gm", 25, 0.1),
+                        ("g1", 2, 0.02)):
         n, K, L, seed = 300, 4, 7, 99
         torch.manual_seed(0)
         x0 = 0.3 * torch.randn(n, d)
-        s = HMC((d,), product_target(pot, d), HMCKernel(event_size=d, step_size=tau, n_leapfrog_steps=L), HMCParameters())
+        target = DiagonalGaussian((d,), torch.linspace(0.5, 4.0, d), torch.linspace(-1.0, 1.0, d)) if pot == "dg" else product_target(pot, d)
+        s = HMC((d,), target, HMCKernel(event_size=d, step_size=tau, n_leapfrog_steps=L), HMCParameters())
         out = MCMCOutput((d,), store_samples=True)
         ses = DeviceSession(x0, (d,), None, seed=seed)
         buf = s.run_steps(ses, out, K, True)
