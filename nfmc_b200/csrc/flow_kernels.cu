@@ -16,11 +16,14 @@
 #ifndef NFMC_JUMP_MINB
 #define NFMC_JUMP_MINB 3
 #endif
+#ifndef NFMC_FLOW_MINB
+#define NFMC_FLOW_MINB 3      // resident CTAs per SM the flow-pass / propose-accept kernels are compiled for
+#endif
 
 namespace nfmc {
 
 template <int E, bool SB, bool X, bool SM>
-__global__ void __launch_bounds__(kThreads) flow_pass_kernel(FlowArgs A, int mode, const float* __restrict__ in,
+__global__ void __launch_bounds__(kThreads, NFMC_FLOW_MINB) flow_pass_kernel(FlowArgs A, int mode, const float* __restrict__ in,
                                                             float* __restrict__ out, float* __restrict__ aux, long long n) {
   extern __shared__ __align__(16) unsigned char smem[];
   const Geom g = make_geom(A.d, A.gs);
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(kThreads, NFMC_JUMP_MINB) jump_kernel(const Ju
 // split in two the jump takes 2.0 ms instead of 3.1 ms (2^20 chains, d = 100).  Rejected chains are not written back.
 // ---------------------------------------------------------------------------------------------------------
 template <int E, bool SB, bool X, bool SM>
-__global__ void __launch_bounds__(kThreads, 3) jump_propose_accept_kernel(const JumpArgs A) {
+__global__ void __launch_bounds__(kThreads, NFMC_FLOW_MINB) jump_propose_accept_kernel(const JumpArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ChainArgs& C = A.c;
   const Geom g = make_geom(C.d, C.gs);
