@@ -131,6 +131,14 @@ NFMC_API int nfmc_jump_step_tc(const nfmc_potential* pot, const nfmc_realnvp_tc*
                                const nfmc_stats* stats, const nfmc_sink* sink, void* workspace, int64_t workspace_bytes,
                                void* stream);
 
+/* the same step (jump.py:203-243, imh.py:214-249) for conditioner shapes outside the register-resident and tensor-core
+ * paths: flow->blob = the module-order parameter vector theta of nfmc_flow_wide_param_count() floats (see the wide
+ * training block below), both passes by the row-tile fp32 kernel; workspace as for nfmc_jump_step_tc */
+NFMC_API int nfmc_jump_step_wide(const nfmc_potential* pot, const nfmc_realnvp* flow, float* x, float* logq_cache,
+                                 int32_t recompute_logq, int64_t n, int32_t adjusted, const nfmc_rng* rng, int64_t chain0,
+                                 const nfmc_stats* stats, const nfmc_sink* sink, void* workspace, int64_t workspace_bytes,
+                                 void* stream);
+
 /* ---- NeuTra on the tensor cores (csrc/tc_neutra.cu): U~(z) = U(T^-1 z) - log|det dT^-1/dz| (nfmc/neutra.py:58-68) and
  * its gradient with the conditioner forward AND its input-VJP (dgrad) on tcgen05.  blob_t = the transposed weight images
  * of nfmc_b200.flow.pack_realnvp_tc_transposed() (nfmc_neutra_tc_transposed_bytes bytes; -1 = shape not eligible: needs
@@ -326,6 +334,10 @@ NFMC_API int nfmc_flow_wide_nll_grad(int32_t d, int32_t n_coupling, int32_t n_li
 /* one fp32 pass straight from theta: inverse = 0: x -> z, log|det dz/dx|; 1: z -> x, log|det dx/dz| (log_det may be NULL) */
 NFMC_API int nfmc_flow_wide_pass(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden, const float* theta,
                         int32_t inverse, const float* in, float* out, float* log_det, int64_t n, void* stream);
+/* log q(x) = log N(T(x); 0, I) + log|det dT/dx| by the same fp32 pass (Flow.log_prob: nfmc/jump.py:218, nfmc/imh.py:214) for
+ * the conditioner shapes outside the register-resident and tensor-core paths (n_linear != 2, odd d, d > 128 with H > 8) */
+NFMC_API int nfmc_flow_wide_log_prob(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden, const float* theta,
+                            const float* x, float* log_q, int64_t n, void* stream);
 /* backward sweep of a pass whose OUTPUT y [n, d] and output cotangent grad_y [n, d] are given (reverse KL: inverse = 1,
  * y = x = T^-1(z), grad_y = grad U(x)): grad_theta (+)= d/dtheta [ sum_i (grad_y . y)(theta) -/+ log|det| ], i.e. the
  * gradient of sum_i [U(x_i) - log|det dx/dz|] (inverse = 1) or of sum_i [f(z_i) - log|det dz/dx|] (inverse = 0);

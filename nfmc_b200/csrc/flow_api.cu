@@ -295,6 +295,57 @@ int nfmc_jump_step_tc_fused(const nfmc_potential* pot, const nfmc_realnvp_tc* fl
                             int64_t n, int adjusted, const nfmc_rng* rng, int64_t chain0, const nfmc_stats* stats,
                             const nfmc_sink* sink, void* stream);
 
+// The jump composed from separate launches: log q(x) by `logprob`, the Philox base draw (stream 1, the numbers the fused
+// kernels draw), x' = T^-1(z) by `inverse`, then the accept kernel.  Shared by the tensor-core fallback and the row-tile fp32
+// path for deep / odd-sized conditioners.
+template <class LogProb, class Inverse>
+static int composed_jump(const char* who, const nfmc_potential* pot, float* x, float* logq_cache, int32_t recompute_logq, int64_t n,
+                         int32_t adjusted, const nfmc_rng* rng, int64_t chain0, const nfmc_stats* stats, const nfmc_sink* sink,
+                         void* workspace, int64_t workspace_bytes, void* stream, LogProb logprob, Inverse inverse) {
+  if (workspace_bytes < nfmc_jump_tc_workspace_bytes(pot->d, n)) return set_error(std::string(who) + ": workspace too small");
+  const int d = pot->d;
+  const size_t row = ((size_t)n * d * sizeof(float) + 255) & ~size_t(255), vec = ((size_t)n * sizeof(float) + 255) & ~size_t(255);
+  unsigned char* w = static_cast<unsigned char*>(workspace);
+  float* z = reinterpret_cast<float*>(w);
+  float* xp = reinterpret_cast<float*>(w + row);
+  float* ld_inv = reinterpret_cast<float*>(w + 2 * row);
+  float* logq_x = reinterpret_cast<float*>(w + 2 * row + vec);
+  float* unif = reinterpret_cast<float*>(w + 2 * row + 2 * vec);
+  cudaStream_t s = (cudaStream_t)stream;
+  // log q(x): forward pass (jump.py:218) unless a valid cache is supplied (imh.py:214)
+  const float* fx = logq_x;
+  if (adjusted) {
+    if (logq_cache && !recompute_logq) fx = logq_cache;
+    else if (int e = logprob(x, logq_x)) return e;
+  }
+  // base draw z and accept uniforms (Philox stream 1, or injected)
+  const float* zsrc = z;
+  const float* usrc = unif;
+  if (rng->normals && rng->uniforms) { zsrc = rng->normals; usrc = rng->uniforms; }
+  else {
+    nfmc_rng r2{rng->seed, rng->step0, nullptr, nullptr};
+    if (int e = nfmc_rng_fill(&r2, 1, chain0, d, n, 1, z, unif, stream)) return e;
+    if (rng->normals) zsrc = rng->normals;
+    if (rng->uniforms) usrc = rng->uniforms;
+  }
+  // x' = T^-1(z), log|det| (jump.py:205)
+  if (int e = inverse(zsrc, xp, ld_inv)) return e;
+  Layout L;
+  if (!layout_for_dim(d, L)) return set_error(std::string(who) + ": unsupported event size");
+  AcceptArgs A;
+  A.c.pot = pot_params(pot);
+  A.c.x = x; A.c.n = n; A.c.chain0 = chain0; A.c.d = d; A.c.gs = L.gs; A.c.n_steps = 1;
+  A.c.rng = RngArgs{rng->seed, rng->step0, nullptr, nullptr};
+  A.c.stats = StatsArgs{stats ? stats->sum_x : nullptr, stats ? stats->sum_x2 : nullptr, stats ? stats->counts : nullptr};
+  A.c.sink = SinkArgs{sink ? sink->samples : nullptr, sink ? sink->seen0 : 0, (sink && sink->thinning > 0) ? sink->thinning : 1};
+  A.pot_kind = pot->kind; A.adjusted = adjusted;
+  A.x_prime = xp; A.z = zsrc; A.ld_inv = ld_inv; A.logq_x = fx; A.uniforms = usrc; A.logq_cache = logq_cache;
+  const size_t smem = (cta_stats_bytes_host(d) + 15) & ~size_t(15);
+  const int grid = grid_for(n, L.gs, 4);
+  NFMC_DISPATCH_E(L.E, { return launch_jump_accept<E>(A, grid, smem, s); });
+  return 0;
+}
+
 extern "C" int nfmc_jump_step_tc(const nfmc_potential* pot, const nfmc_realnvp_tc* flow, float* x, float* logq_cache,
                                  int32_t recompute_logq, int64_t n, int32_t adjusted, const nfmc_rng* rng, int64_t chain0,
                                  const nfmc_stats* stats, const nfmc_sink* sink, void* workspace, int64_t workspace_bytes,
@@ -308,46 +359,29 @@ extern "C" int nfmc_jump_step_tc(const nfmc_potential* pot, const nfmc_realnvp_t
     const int rc = nfmc_jump_step_tc_fused(pot, flow, x, logq_cache, recompute_logq, n, adjusted, rng, chain0, stats, sink, stream);
     if (rc >= 0) return rc;
   }
-  if (workspace_bytes < nfmc_jump_tc_workspace_bytes(pot->d, n)) return set_error("jump_step_tc: workspace too small");
-  const int d = pot->d;
-  const size_t row = ((size_t)n * d * sizeof(float) + 255) & ~size_t(255), vec = ((size_t)n * sizeof(float) + 255) & ~size_t(255);
-  unsigned char* w = static_cast<unsigned char*>(workspace);
-  float* z = reinterpret_cast<float*>(w);
-  float* xp = reinterpret_cast<float*>(w + row);
-  float* ld_inv = reinterpret_cast<float*>(w + 2 * row);
-  float* logq_x = reinterpret_cast<float*>(w + 2 * row + vec);
-  float* unif = reinterpret_cast<float*>(w + 2 * row + 2 * vec);
-  cudaStream_t s = (cudaStream_t)stream;
-  // log q(x): forward pass on the tensor cores (jump.py:218) unless a valid cache is supplied (imh.py:214)
-  const float* fx = logq_x;
-  if (adjusted) {
-    if (logq_cache && !recompute_logq) fx = logq_cache;
-    else if (int e = nfmc_flow_tc_pass(flow, 2, x, nullptr, logq_x, n, stream)) return e;
-  }
-  // base draw z and accept uniforms (Philox stream 1, or injected)
-  const float* zsrc = z;
-  const float* usrc = unif;
-  if (rng->normals && rng->uniforms) { zsrc = rng->normals; usrc = rng->uniforms; }
-  else {
-    nfmc_rng r2{rng->seed, rng->step0, nullptr, nullptr};
-    if (int e = nfmc_rng_fill(&r2, 1, chain0, d, n, 1, z, unif, stream)) return e;
-    if (rng->normals) zsrc = rng->normals;
-    if (rng->uniforms) usrc = rng->uniforms;
-  }
-  // x' = T^-1(z), log|det| (jump.py:205)
-  if (int e = nfmc_flow_tc_pass(flow, 1, zsrc, xp, ld_inv, n, stream)) return e;
-  Layout L;
-  if (!layout_for_dim(d, L)) return set_error("jump_step_tc: unsupported event size");
-  AcceptArgs A;
-  A.c.pot = pot_params(pot);
-  A.c.x = x; A.c.n = n; A.c.chain0 = chain0; A.c.d = d; A.c.gs = L.gs; A.c.n_steps = 1;
-  A.c.rng = RngArgs{rng->seed, rng->step0, nullptr, nullptr};
-  A.c.stats = StatsArgs{stats ? stats->sum_x : nullptr, stats ? stats->sum_x2 : nullptr, stats ? stats->counts : nullptr};
-  A.c.sink = SinkArgs{sink ? sink->samples : nullptr, sink ? sink->seen0 : 0, (sink && sink->thinning > 0) ? sink->thinning : 1};
-  A.pot_kind = pot->kind; A.adjusted = adjusted;
-  A.x_prime = xp; A.z = zsrc; A.ld_inv = ld_inv; A.logq_x = fx; A.uniforms = usrc; A.logq_cache = logq_cache;
-  const size_t smem = (cta_stats_bytes_host(d) + 15) & ~size_t(15);
-  const int grid = grid_for(n, L.gs, 4);
-  NFMC_DISPATCH_E(L.E, { return launch_jump_accept<E>(A, grid, smem, s); });
-  return 0;
+  return composed_jump("jump_step_tc", pot, x, logq_cache, recompute_logq, n, adjusted, rng, chain0, stats, sink, workspace,
+                       workspace_bytes, stream,
+                       [&](const float* in, float* lq) { return nfmc_flow_tc_pass(flow, 2, in, nullptr, lq, n, stream); },
+                       [&](const float* zz, float* out, float* ld) { return nfmc_flow_tc_pass(flow, 1, zz, out, ld, n, stream); });
+}
+
+// The same step for conditioner shapes outside the register-resident and the tensor-core paths (n_linear != 2, odd d, d > 128
+// with hidden > 8): both flow passes by the row-tile fp32 kernel of train_wide.cu, straight from the module-order parameter
+// vector (`flow->blob` = theta, `flow->blob_floats` = its length) -- 3-6x the generic per-chain conditioner of flow.cuh.
+extern "C" int nfmc_jump_step_wide(const nfmc_potential* pot, const nfmc_realnvp* flow, float* x, float* logq_cache,
+                                   int32_t recompute_logq, int64_t n, int32_t adjusted, const nfmc_rng* rng, int64_t chain0,
+                                   const nfmc_stats* stats, const nfmc_sink* sink, void* workspace, int64_t workspace_bytes,
+                                   void* stream) {
+  if (int e = validate_pot(pot)) return e;
+  if (!flow || !flow->blob || !x || !rng || !workspace || n < 1) return set_error("jump_step_wide: bad arguments");
+  if (pot->d != flow->d) return set_error("jump_step_wide: potential and flow event sizes differ");
+  if (flow->blob_floats != nfmc_flow_wide_param_count(flow->d, flow->n_coupling, flow->n_linear, flow->hidden))
+    return set_error("jump_step_wide: theta length does not match the flow shape");
+  if (int e = validate_injected(rng, adjusted, "jump_step_wide")) return e;
+  const int d = flow->d, Lc = flow->n_coupling, M = flow->n_linear, H = flow->hidden;
+  const float* theta = flow->blob;
+  return composed_jump("jump_step_wide", pot, x, logq_cache, recompute_logq, n, adjusted, rng, chain0, stats, sink, workspace,
+                       workspace_bytes, stream,
+                       [&](const float* in, float* lq) { return nfmc_flow_wide_log_prob(d, Lc, M, H, theta, in, lq, n, stream); },
+                       [&](const float* zz, float* out, float* ld) { return nfmc_flow_wide_pass(d, Lc, M, H, theta, 1, zz, out, ld, n, stream); });
 }

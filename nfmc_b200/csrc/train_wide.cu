@@ -57,6 +57,7 @@ struct WideArgs {
   const float* gy;        // SWEEP: cotangent of the pass output [n, d]
   float* y;               // PASS: output rows [n, d]
   float* ld;              // PASS: log|det| of the pass direction [n]
+  float* logp;            // PASS, x -> z only (optional): log q(x) = log N(z; 0, I) + log|det dz/dx| [n]
   double* loss;           // NLL: += sum_i -log q(x_i)
   float* gx;              // optional (NLL / SWEEP): cotangent that reaches the pass input [n, d]
   long long n;
@@ -448,13 +449,22 @@ __global__ void __launch_bounds__(kWT, 1) flow_train_wide_kernel(const WideArgs 
       // NOTE on columns: the latent z of a flow with an odd number of reversals sits reversed in the tile; stores and
       // loads always use LOGICAL indices, so nothing is flipped in global memory.
       const bool rev_out = pass_inv ? false : ((D.Lc & 1) != 0);
-      for (int it = threadIdx.x; it < R * d; it += kWT) {
-        const int r = it / d, i = it % d;
-        if (row0 + r < A.n) A.y[(row0 + r) * d + i] = T.V()[r * P.ldv + (rev_out ? d - 1 - i : i)];
-      }
+      if (A.y)
+        for (int it = threadIdx.x; it < R * d; it += kWT) {
+          const int r = it / d, i = it % d;
+          if (row0 + r < A.n) A.y[(row0 + r) * d + i] = T.V()[r * P.ldv + (rev_out ? d - 1 - i : i)];
+        }
       if (A.ld)
         for (int r = threadIdx.x; r < R; r += kWT)
           if (row0 + r < A.n) A.ld[row0 + r] = T.Ld()[r];
+      if (A.logp)
+        for (int it = threadIdx.x; it < R * 32; it += kWT) {
+          const int r = it >> 5, lane = it & 31;
+          float s = 0.f;
+          for (int c = lane; c < d; c += 32) { const float z = T.V()[r * P.ldv + c]; s = fmaf(z, z, s); }
+          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          if (lane == 0 && row0 + r < A.n) A.logp[row0 + r] = T.Ld()[r] - 0.5f * s - 0.5f * (float)d * 1.8378770664093453f;
+        }
       __syncthreads();
       continue;
     }
@@ -597,6 +607,16 @@ extern "C" int nfmc_flow_wide_pass(int32_t d, int32_t n_coupling, int32_t n_line
   WideArgs A{};
   A.D = wide_dims(d, n_coupling, n_linear, hidden);
   A.theta = theta; A.x = in; A.y = out; A.ld = log_det; A.n = n; A.mode = kWidePass; A.inv = inverse ? 1 : 0;
+  return wide_launch(A, (cudaStream_t)stream);
+}
+
+extern "C" int nfmc_flow_wide_log_prob(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden, const float* theta,
+                                       const float* x, float* log_q, int64_t n, void* stream) {
+  if (int e = wide_check(d, n_coupling, n_linear, hidden)) return e;
+  if (!theta || !x || !log_q || n < 1) return set_error("flow_wide_log_prob: bad arguments");
+  WideArgs A{};
+  A.D = wide_dims(d, n_coupling, n_linear, hidden);
+  A.theta = theta; A.x = x; A.logp = log_q; A.n = n; A.mode = kWidePass; A.inv = 0;
   return wide_launch(A, (cudaStream_t)stream);
 }
 

@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -161,6 +162,33 @@ class RealNVP(_Layer):
             return tc_supported(*shape)
         return self.conditioner_dtype == "auto" and tc_eligible(*shape)
 
+    def uses_row_tile_pass(self) -> bool:
+        """Conditioner shapes outside the register-resident path (M = 2, H <= 8) and outside the tensor-core path -- deep
+        conditioners (n_layers != 2, e.g. the reference's ``n_layers=5, n_hidden=100``), odd d or d > 128 with H > 8, or any
+        wide conditioner with ``conditioner_dtype='fp32'`` -- take the row-tile fp32 pass of csrc/train_wide.cu
+        (``nfmc_flow_wide_pass`` / ``nfmc_flow_wide_log_prob`` / ``nfmc_jump_step_wide``) for forward / inverse / log_prob and
+        the NF jump / IMH step: register-blocked weight reuse over a tile of rows instead of one weight load per chain and
+        multiply (3-6x the per-chain generic path, ``tools/bench_deep.py``)."""
+        M, H = self.conditioner_shape()
+        if (M == 2 and H <= SMALL_H) or self.uses_tensor_cores() or not self.couplings():
+            return False
+        if os.environ.get("NFMC_B200_NO_ROW_TILE") == "1":      # tests / A-B runs: keep the per-chain generic conditioner
+            return False
+        same = all((c.n_linear, c.n_hidden) == (M, H) for c in self.couplings())
+        return same and N.lib().nfmc_flow_wide_param_count(self.n_dim, self.n_coupling, M, H) > 0
+
+    def theta_descriptor(self, device: torch.device):
+        """Descriptor of the row-tile path: the module-order parameter vector (cached per device and parameter version)."""
+        key = "theta:" + str(device)
+        ver = self._version_key()
+        hit = self._packed.get(key)
+        if hit is None or hit[0] != ver:
+            theta = torch.cat([p.detach().reshape(-1) for p in self.parameters()]).to(device, torch.float32).contiguous()
+            self._packed[key] = (ver, theta)
+        theta = self._packed[key][1]
+        M, H = self.conditioner_shape()
+        return N.RealNVPDesc(self.n_dim, self.n_coupling, M, H, theta.data_ptr(), theta.numel()), theta
+
     def tc_descriptor(self, device: torch.device):
         key = str(device)
         ver = self._version_key()
@@ -216,6 +244,11 @@ class RealNVP(_Layer):
                 desc, keep = self.tc_descriptor(dev)
                 mode = 0 if fn_name == "nfmc_realnvp_forward" else 1
                 N.check(N.lib().nfmc_flow_tc_pass(C.byref(desc), mode, N.ptr(xd), N.ptr(y), N.ptr(ld), n, N.stream_ptr(dev)))
+            elif self.uses_row_tile_pass():
+                desc, keep = self.theta_descriptor(dev)
+                N.check(N.lib().nfmc_flow_wide_pass(desc.d, desc.n_coupling, desc.n_linear, desc.hidden, N.ptr(keep),
+                                                    0 if fn_name == "nfmc_realnvp_forward" else 1, N.ptr(xd), N.ptr(y), N.ptr(ld), n,
+                                                    N.stream_ptr(dev)))
             else:
                 desc, keep = self.descriptor(dev)
                 N.check(getattr(N.lib(), fn_name)(C.byref(desc), N.ptr(xd), N.ptr(y), N.ptr(ld), n, N.stream_ptr(dev)))
@@ -265,6 +298,10 @@ class Flow(nn.Module):
             if bij.uses_tensor_cores():
                 desc, keep = bij.tc_descriptor(dev)
                 N.check(N.lib().nfmc_flow_tc_pass(C.byref(desc), 2, N.ptr(xd), None, N.ptr(out), n, N.stream_ptr(dev)))
+            elif bij.uses_row_tile_pass():
+                desc, keep = bij.theta_descriptor(dev)
+                N.check(N.lib().nfmc_flow_wide_log_prob(desc.d, desc.n_coupling, desc.n_linear, desc.hidden, N.ptr(keep),
+                                                        N.ptr(xd), N.ptr(out), n, N.stream_ptr(dev)))
             else:
                 desc, keep = bij.descriptor(dev)
                 N.check(N.lib().nfmc_flow_log_prob(C.byref(desc), N.ptr(xd), N.ptr(out), n, N.stream_ptr(dev)))

@@ -503,6 +503,13 @@ class JumpNFMC(Sampler):
             N.check(N.lib().nfmc_jump_step_tc(C.byref(pot), C.byref(fd), N.ptr(ses.x), None, 1, ses.n,
                                               int(bool(self.params.adjusted_jumps)), C.byref(rng), ses.chain0,
                                               C.byref(st), sk, N.ptr(ws), nb, ses.stream))
+        elif flow.bijection.uses_row_tile_pass():                 # deep / odd-sized conditioner: row-tile fp32 passes
+            fd, keep2 = flow.bijection.theta_descriptor(ses.device)
+            nb = N.lib().nfmc_jump_tc_workspace_bytes(ses.d, ses.n)
+            ws = ses.workspace(nb)
+            N.check(N.lib().nfmc_jump_step_wide(C.byref(pot), C.byref(fd), N.ptr(ses.x), None, 1, ses.n,
+                                                int(bool(self.params.adjusted_jumps)), C.byref(rng), ses.chain0,
+                                                C.byref(st), sk, N.ptr(ws), nb, ses.stream))
         else:
             fd, keep2 = flow.bijection.descriptor(ses.device)
             # two kernels (forward pass for log q(x), then proposal + accept): faster than the fused jump kernel
@@ -533,7 +540,7 @@ class JumpNFMC(Sampler):
         if (kind is not None and T > 0 and not store and not p.fit_nf and time_limit_seconds is None and not show_progress
                 and not self.target.external and not inner.target.external
                 and all(v is None for v in (normals, uniforms, jump_z, jump_uniforms, stage_normals))
-                and not self.kernel.flow.bijection.uses_tensor_cores()):
+                and not self.kernel.flow.bijection.uses_tensor_cores() and not self.kernel.flow.bijection.uses_row_tile_pass()):
             # whole run in one call (nfmc_jump_sample_device): slabs of chains pipelined over several streams so that the
             # jump kernel of one slab overlaps the local kernel of another; same Philox steps as the loop below
             pot, keep = self.target.descriptor(dev)
@@ -689,17 +696,27 @@ class AbstractIMH(Sampler):
         if self.target.external:
             return self._run_external(ses, out, flow, T, show_progress, time_limit_seconds, store, z, uniforms, after_iteration)
         pot, keep = self.target.descriptor(dev)
-        tc = flow.bijection.uses_tensor_cores()
-        fd, keep2 = flow.bijection.tc_descriptor(dev) if tc else flow.bijection.descriptor(dev)
+        def describe():
+            """(tensor cores?, row-tile fp32 pass?, descriptor, tensor it points into) under the flow's current parameters"""
+            bij = flow.bijection
+            if bij.uses_tensor_cores():
+                return (True, False) + bij.tc_descriptor(dev)
+            if bij.uses_row_tile_pass():
+                return (False, True) + bij.theta_descriptor(dev)
+            return (False, False) + bij.descriptor(dev)
+        tc, wide, fd, keep2 = describe()
         logq = torch.empty(ses.n, device=dev, dtype=torch.float32)
         ses.tic()
         if not self.recompute_logq:                                                  # imh.py:214
             if tc:
                 N.check(N.lib().nfmc_flow_tc_pass(C.byref(fd), 2, N.ptr(ses.x), None, N.ptr(logq), ses.n, ses.stream))
+            elif wide:
+                N.check(N.lib().nfmc_flow_wide_log_prob(fd.d, fd.n_coupling, fd.n_linear, fd.hidden, N.ptr(keep2), N.ptr(ses.x),
+                                                        N.ptr(logq), ses.n, ses.stream))
             else:
                 N.check(N.lib().nfmc_flow_log_prob(C.byref(fd), N.ptr(ses.x), N.ptr(logq), ses.n, ses.stream))
         out.statistics.update_elapsed_time(ses.toc())
-        chunk = 1 if (tc or after_iteration is not None or time_limit_seconds is not None or show_progress) else T
+        chunk = 1 if (tc or wide or after_iteration is not None or time_limit_seconds is not None or show_progress) else T
         rs = out.running_samples
         done = 0
         for start in _progress(range(0, T, max(chunk, 1)), self.name, show_progress):
@@ -718,12 +735,13 @@ class AbstractIMH(Sampler):
             rng = N.rng_desc(ses.seed, ses.flow_step, zz, uu)
             st = ses.stats()
             ses.tic()
-            if tc:
+            if tc or wide:
                 nb = N.lib().nfmc_jump_tc_workspace_bytes(ses.d, ses.n)
                 ws = ses.workspace(nb)
-                N.check(N.lib().nfmc_jump_step_tc(C.byref(pot), C.byref(fd), N.ptr(ses.x), N.ptr(logq),
-                                                  int(self.recompute_logq), ses.n, 1, C.byref(rng), ses.chain0, C.byref(st),
-                                                  None if sink is None else C.byref(sink), N.ptr(ws), nb, ses.stream))
+                step = N.lib().nfmc_jump_step_tc if tc else N.lib().nfmc_jump_step_wide
+                N.check(step(C.byref(pot), C.byref(fd), N.ptr(ses.x), N.ptr(logq),
+                             int(self.recompute_logq), ses.n, 1, C.byref(rng), ses.chain0, C.byref(st),
+                             None if sink is None else C.byref(sink), N.ptr(ws), nb, ses.stream))
             else:
                 N.check(N.lib().nfmc_imh_steps(C.byref(pot), C.byref(fd), N.ptr(ses.x), N.ptr(logq), ses.n, k,
                                                int(self.recompute_logq), C.byref(rng), ses.chain0, C.byref(st),
@@ -735,8 +753,7 @@ class AbstractIMH(Sampler):
                 rs.add(buf.reshape(-1, ses.n, *event_shape), already_thinned=True, n_seen=k)
             if after_iteration is not None:
                 after_iteration(start, out)
-                tc2 = flow.bijection.uses_tensor_cores()                              # parameters changed: re-pack
-                fd, keep2 = flow.bijection.tc_descriptor(dev) if tc2 else flow.bijection.descriptor(dev)
+                tc, wide, fd, keep2 = describe()                                      # parameters changed: re-pack
         sx, sx2, cnt = ses.read_back()
         out.statistics.expectations.add_sums(sx, sx2, ses.n * done)
         out.statistics.update_counters(n_accepted_trajectories=cnt[0], n_attempted_trajectories=cnt[1])

@@ -1,0 +1,121 @@
+"""Row-tile fp32 flow passes (csrc/train_wide.cu: nfmc_flow_wide_pass / nfmc_flow_wide_log_prob) and the NF jump / IMH step
+composed from them (nfmc_jump_step_wide) -- the sampling path of every conditioner shape outside the register-resident
+(M = 2, H <= 8) and tensor-core (M = 2, even d <= 128) kernels: deep conditioners such as the reference's
+``n_layers=5, n_hidden=100`` (/root/reference/test/test_flow_kwargs.py:49), odd d, d > 128 with a wide conditioner.
+Oracle: oracle/realnvp_ref.py and oracle/samplers_ref.py with the draws injected; tolerance rtol 1e-4 (fp32)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import samplers_ref as R                              # noqa: E402  (checker only)
+from oracle.potentials_ref import make_potential_ref             # noqa: E402
+from oracle.realnvp_ref import make_flow                          # noqa: E402
+
+DEEP = [(37, 3, dict(n_layers=3, n_hidden=20)), (100, 2, dict(n_layers=5, n_hidden=100)), (101, 2, dict(n_layers=2, n_hidden=64)),
+        (8, 1, dict(n_layers=1)), (200, 2, dict(n_layers=2, n_hidden=24))]
+
+
+def _pair(d, n_layers, ck, seed=4, perturb=0.05):
+    from gpu_util import product_flow_from_oracle
+    oflow = make_flow((d,), n_layers=n_layers, conditioner_kwargs=ck, perturb=perturb, seed=seed)
+    return oflow, product_flow_from_oracle(oflow)
+
+
+def test_routing():
+    from nfmc_b200.flow import RealNVP
+    assert not RealNVP((100,)).uses_row_tile_pass()                                                        # default: registers
+    assert not RealNVP((100,), conditioner_kwargs=dict(n_layers=2, n_hidden=64)).uses_row_tile_pass()      # tcgen05
+    assert RealNVP((100,), conditioner_kwargs=dict(n_layers=2, n_hidden=64), conditioner_dtype="fp32").uses_row_tile_pass()
+    assert RealNVP((100,), n_layers=10, conditioner_kwargs=dict(n_layers=5, n_hidden=100)).uses_row_tile_pass()   # the reference's deep shape
+    assert RealNVP((101,), conditioner_kwargs=dict(n_layers=2, n_hidden=64)).uses_row_tile_pass()          # odd d
+    assert RealNVP((1000,), conditioner_kwargs=dict(n_layers=2, n_hidden=64)).uses_row_tile_pass()         # d > 128
+
+
+@pytest.mark.parametrize("d,n_layers,ck", DEEP)
+def test_passes_and_log_prob_against_oracle(d, n_layers, ck):
+    oflow, flow = _pair(d, n_layers, ck)
+    assert flow.bijection.uses_row_tile_pass()
+    n = 333                                              # not a multiple of any row tile
+    torch.manual_seed(d)
+    x = torch.randn(n, d)
+    with torch.no_grad():
+        z_ref, ld_ref = oflow.bijection.forward(x)
+        xi_ref, ldi_ref = oflow.bijection.inverse(x)
+        lp_ref = oflow.log_prob(x)
+    z, ld = flow.bijection.forward(x.cuda())
+    xi, ldi = flow.bijection.inverse(x.cuda())
+    lp = flow.log_prob(x.cuda())
+    for got, want in ((z, z_ref), (ld, ld_ref), (xi, xi_ref), (ldi, ldi_ref), (lp, lp_ref)):
+        np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-4 * max(1.0, float(want.abs().max())))
+
+
+@pytest.mark.parametrize("d,n_layers,ck", DEEP[:3])
+def test_generic_per_chain_path_still_agrees(monkeypatch, d, n_layers, ck):
+    """NFMC_B200_NO_ROW_TILE=1 keeps the per-chain generic conditioner of flow.cuh (still what Flow.sample, the fused NeuTra
+    kernel and tess use for these shapes): both paths give the same numbers."""
+    oflow, flow = _pair(d, n_layers, ck)
+    x = torch.randn(129, d, generator=torch.Generator().manual_seed(1)).cuda()
+    z, ld = flow.bijection.forward(x)
+    lp = flow.log_prob(x)
+    monkeypatch.setenv("NFMC_B200_NO_ROW_TILE", "1")
+    assert not flow.bijection.uses_row_tile_pass()
+    z2, ld2 = flow.bijection.forward(x)
+    lp2 = flow.log_prob(x)
+    for a, b in ((z, z2), (ld, ld2), (lp, lp2)):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-4, atol=2e-5 * max(1.0, float(b.abs().max())))
+
+
+@pytest.mark.parametrize("d,n_layers,ck", DEEP[:3])
+def test_fixed_imh_against_oracle(d, n_layers, ck):
+    from gpu_util import product_target
+    from nfmc_b200.records import IMHKernel, IMHParameters
+    from nfmc_b200.samplers import FixedIMH
+    oflow, flow = _pair(d, n_layers, ck, perturb=0.03)
+    n, T = 777, 4
+    torch.manual_seed(5)
+    x0 = torch.randn(n, d)
+    z, u = torch.randn(T, n, d), torch.rand(T, n)
+    run = R.run_fixed_imh(x0, make_potential_ref("g0", (d,)), oflow, T, R.TapeDraws(list(z), list(u)), trace=True)
+    s = FixedIMH((d,), product_target("g0", d), IMHKernel((d,), flow=flow), IMHParameters(n_iterations=T))
+    out = s.sample(x0, show_progress=False, z=z, uniforms=u)
+    la = torch.stack(run.trace["log_alpha"])
+    clear = ((la - torch.log(u)).abs().min(dim=0).values > 1e-3 * (1 + la.abs().max(dim=0).values))
+    assert clear.float().mean() > 0.97
+    np.testing.assert_allclose(out.samples[:, clear].numpy(), run.samples[:, clear].numpy(), rtol=1e-4,
+                               atol=2e-5 * max(1.0, float(run.samples.abs().max())))
+    assert abs(out.statistics.n_accepted_trajectories - run.n_accepted) <= int((~clear).sum()) * T
+    assert out.statistics.n_attempted_trajectories == n * T
+
+
+def test_jump_mala_deep_flow_philox_equals_injected_and_counters():
+    """jump_mala with the reference's deep conditioner shape: the run drawing its own Philox numbers equals the run fed those
+    numbers (nfmc_rng_fill, stream 1 for the base draw), and the counters follow the reference's formulas (jump.py:214-239)."""
+    import nfmc_b200
+    from nfmc_b200 import _native as N
+    from nfmc_b200.potentials import StandardGaussian
+    d, n, T, K = 100, 600, 3, 4
+    oflow, flow = _pair(d, 3, dict(n_layers=5, n_hidden=100), perturb=0.01)
+    torch.manual_seed(2)
+    x0 = 0.7 * torch.randn(n, d)
+
+    def make():
+        s = nfmc_b200.create_sampler(StandardGaussian((d,)), flow=flow, strategy="jump_mala", param_kwargs=dict(n_iterations=T),
+                                     inner_param_kwargs=dict(n_iterations=K))
+        s.seed = 77
+        return s
+    out = make().sample(x0, show_progress=False)
+    st = out.statistics
+    assert st.n_attempted_jumps == n * T and st.n_attempted_trajectories == n * T * K
+    assert out.samples.shape == (T * (K + 1), n, d) and bool(torch.isfinite(out.samples).all())
+    dev = torch.device("cuda")
+    jz, ju = torch.empty(T, n, d, device=dev), torch.empty(T, n, device=dev)
+    for t in range(T):
+        rng = N.rng_desc(77, t, None, None)
+        N.check(N.lib().nfmc_rng_fill(C.byref(rng), 1, 0, d, n, 1, N.ptr(jz[t]), N.ptr(ju[t]), N.stream_ptr(dev)))
+    out2 = make().sample(x0, show_progress=False, jump_z=jz, jump_uniforms=ju)
+    assert torch.equal(out.samples, out2.samples)
+    assert out2.statistics.n_accepted_jumps == st.n_accepted_jumps

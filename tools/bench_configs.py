@@ -86,6 +86,13 @@ if __name__ == "__main__":
         "fn", 100, 262144, 3, flow_spec='realnvp%{"conditioner_dtype": "bf16"}', inner_kernel_kwargs={"step_size": 0.01})
     run("C4 imh rosenbrock d=100 n=2^20 DEFAULT conditioner opted into bf16 (tcgen05 fused IMH iteration)", "imh", "rb", 100, 1 << 20, 20,
         flow_spec='realnvp%{"conditioner_dtype": "bf16"}')
+    deep = 'realnvp%{"n_layers": 10, "conditioner_kwargs": {"n_layers": 5, "n_hidden": 100}}'
+    run("deep-flow imh d=100 n=2^16 Lc=10 M=5 H=100 (the reference's test_flow_kwargs shape; row-tile fp32 passes)", "imh", "g0", 100,
+        1 << 16, 5, flow_spec=deep)
+    run("deep-flow jump_mala K=10 d=100 n=2^16 Lc=10 M=5 H=100 (row-tile fp32 passes)", "jump_mala", "g0", 100, 1 << 16, 3, K=10,
+        flow_spec=deep)
+    run("odd-d wide-flow imh d=101 n=2^18 Lc=2 H=64 (row-tile fp32 passes)", "imh", "g0", 101, 1 << 18, 5,
+        flow_spec='realnvp%{"n_layers": 2, "conditioner_kwargs": {"n_layers": 2, "n_hidden": 64}}')
     run("wide-flow jump_mala d=100 n=2^20 H=256 Lc=4 (tcgen05)", "jump_mala", "g0", 100, 1 << 20, 5, K=100, flow_spec=wide)
     run("wide-flow imh d=100 n=2^20 H=256 Lc=4 (tcgen05)", "imh", "g0", 100, 1 << 20, 10, flow_spec=wide)
     run("wide-flow jump_mala K=1 (jump-dominated) d=100 n=2^20 H=256 Lc=4 (tcgen05)", "jump_mala", "g0", 100, 1 << 20, 10, K=1, flow_spec=wide)
