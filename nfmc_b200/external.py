@@ -200,13 +200,21 @@ class LatentTarget:
         n = z.shape[0]
         x = torch.empty_like(z)
         ld = torch.empty(n, device=dev, dtype=torch.float32)
+        if bij.uses_row_tile_pass():            # deep / odd-sized conditioner: row-tile fp32 pass (csrc/train_wide.cu)
+            fd, theta = bij.theta_descriptor(dev)
+            N.check(N.lib().nfmc_flow_wide_pass(fd.d, fd.n_coupling, fd.n_linear, fd.hidden, N.ptr(theta), 1, N.ptr(z), N.ptr(x),
+                                                N.ptr(ld), n, N.stream_ptr(dev)))
+            return x, ld
         fd, keep = bij.descriptor(dev)
         N.check(N.lib().nfmc_realnvp_inverse(C.byref(fd), N.ptr(z), N.ptr(x), N.ptr(ld), n, N.stream_ptr(dev)))
         return x, ld
 
+    def _u(self, x: torch.Tensor) -> torch.Tensor:
+        return self.target.value(x) if hasattr(self.target, "value") else self.target.value_and_grad(x, need_grad=False)[0]
+
     def value(self, z: torch.Tensor) -> torch.Tensor:
         x, ld = self.to_data(z)
-        return -((-self.target.value(x)) + ld)                                  # neutra.py:62-64
+        return -((-self._u(x)) + ld)                                            # neutra.py:62-64
 
     def value_and_grad(self, z: torch.Tensor, need_grad: bool = True):
         if not need_grad:
@@ -214,7 +222,16 @@ class LatentTarget:
         x, ld = self.to_data(z)
         u, gx = self.target.value_and_grad(x)
         gz = torch.empty_like(z)
-        fd, keep = self.flow.bijection.descriptor(z.device)
-        N.check(N.lib().nfmc_neutra_pullback(C.byref(fd), N.ptr(z), N.ptr(gx.reshape(z.shape).contiguous()), N.ptr(gz), None,
+        bij = self.flow.bijection
+        gx = gx.reshape(z.shape).contiguous()
+        if bij.uses_row_tile_pass():
+            # backward sweep of the z -> x pass seeded with grad U(x): grad_in = d/dz [U(x(z)) - log|det dx/dz|] (train_wide.cu,
+            # mode SWEEP with the parameter-gradient emitters off)
+            fd, theta = bij.theta_descriptor(z.device)
+            N.check(N.lib().nfmc_flow_wide_sweep(fd.d, fd.n_coupling, fd.n_linear, fd.hidden, N.ptr(theta), 1, N.ptr(x), N.ptr(gx),
+                                                 z.shape[0], None, N.ptr(gz), 0, N.stream_ptr(z.device)))
+            return -((-u) + ld), gz
+        fd, keep = bij.descriptor(z.device)
+        N.check(N.lib().nfmc_neutra_pullback(C.byref(fd), N.ptr(z), N.ptr(gx), N.ptr(gz), None,
                                              z.shape[0], N.stream_ptr(z.device)))
         return -((-u) + ld), gz

@@ -119,3 +119,52 @@ def test_jump_mala_deep_flow_philox_equals_injected_and_counters():
     out2 = make().sample(x0, show_progress=False, jump_z=jz, jump_uniforms=ju)
     assert torch.equal(out.samples, out2.samples)
     assert out2.statistics.n_accepted_jumps == st.n_accepted_jumps
+
+
+@pytest.mark.parametrize("d,n_layers,ck,pot", [(37, 3, dict(n_layers=3, n_hidden=20), "gm"), (100, 2, dict(n_layers=5, n_hidden=100), "fn"),
+                                               (101, 2, dict(n_layers=2, n_hidden=64), "g1")])
+def test_neutra_latent_potential_and_gradient(d, n_layers, ck, pot):
+    """U~(z) = U(T^-1 z) - log|det dT^-1/dz| and its gradient (neutra.py:58-68) composed from the row-tile inverse pass, the
+    potential kernel and the row-tile backward sweep, against autograd through the oracle flow."""
+    from gpu_util import product_target
+    from nfmc_b200.external import LatentTarget
+    oflow, flow = _pair(d, n_layers, ck, perturb=0.05)
+    torch.manual_seed(d)
+    z = 0.5 * torch.randn(131, d)
+    u_ref, g_ref = R.value_and_grad(R.neutra_potential(oflow, make_potential_ref(pot, (d,))), z)
+    lt = LatentTarget(product_target(pot, d), flow)
+    u, g = lt.value_and_grad(z.cuda())
+    np.testing.assert_allclose(u.cpu().numpy(), u_ref.numpy(), rtol=1e-4, atol=1e-5 * max(1.0, float(u_ref.abs().max())))
+    np.testing.assert_allclose(g.cpu().numpy(), g_ref.numpy(), rtol=1e-4, atol=2e-5 * max(1.0, float(g_ref.abs().max())))
+    np.testing.assert_allclose(lt.value(z.cuda()).cpu().numpy(), u_ref.numpy(), rtol=1e-4, atol=1e-5 * max(1.0, float(u_ref.abs().max())))
+
+
+@pytest.mark.parametrize("kind", ["hmc", "mh"])
+def test_neutra_deep_flow_against_oracle(kind):
+    from gpu_util import product_target
+    from nfmc_b200.records import HMCKernel, HMCParameters, MHKernel, MHParameters, NeuTraKernel, NeuTraParameters
+    from nfmc_b200.samplers import NeuTraHMC, NeuTraMH
+    d, n, T, L, tau = 37, 257, 3, 5, 0.05
+    oflow, flow = _pair(d, 3, dict(n_layers=3, n_hidden=20), perturb=0.05)
+    torch.manual_seed(3)
+    z0 = 0.5 * torch.randn(n, d)
+    normals, uniforms = torch.randn(T, n, d), torch.rand(T, n)
+    tgt_ref = make_potential_ref("g0", (d,))
+    if kind == "hmc":
+        imd = torch.ones(d)
+        run = R.run_neutra_hmc(z0, tgt_ref, oflow, T, R.TapeDraws(list(normals), list(uniforms)), tau, imd, n_leapfrog=L, trace=True)
+        s = NeuTraHMC((d,), product_target("g0", d), HMCKernel(event_size=d, step_size=tau, n_leapfrog_steps=L), HMCParameters(),
+                      NeuTraKernel((d,), flow=flow), NeuTraParameters(n_iterations=T))
+    else:
+        imd = torch.full((d,), 0.05)
+        run = R.run_neutra_mh(z0, tgt_ref, oflow, T, R.TapeDraws(list(normals), list(uniforms)), imd, trace=True)
+        s = NeuTraMH((d,), product_target("g0", d), MHKernel(event_size=d, inv_mass_diag=imd), MHParameters(),
+                     NeuTraKernel((d,), flow=flow), NeuTraParameters(n_iterations=T))
+    out = s.sample(z0, show_progress=False, normals=normals, uniforms=uniforms)
+    lr = torch.stack(run.trace["log_ratio"])
+    clear = (lr - torch.log(uniforms)).abs().min(dim=0).values > 1e-3 * (1.0 + lr.abs().max(dim=0).values)
+    assert clear.float().mean() > 0.9
+    np.testing.assert_allclose(out.samples[:, clear].numpy(), run.samples[:, clear].numpy(), rtol=1e-4,
+                               atol=5e-5 * max(1.0, float(run.samples.abs().max())))
+    assert abs(out.statistics.n_accepted_trajectories - run.n_accepted) <= int((~clear).sum()) * T
+    assert out.statistics.n_target_calls == run.n_target_calls

@@ -91,6 +91,8 @@ if __name__ == "__main__":
         1 << 16, 5, flow_spec=deep)
     run("deep-flow jump_mala K=10 d=100 n=2^16 Lc=10 M=5 H=100 (row-tile fp32 passes)", "jump_mala", "g0", 100, 1 << 16, 3, K=10,
         flow_spec=deep)
+    run("deep-flow neutra_hmc d=100 n=2^14 Lc=10 M=5 H=100 L=20 (row-tile fp32 pass + sweep)", "neutra_hmc", "fn", 100, 1 << 14, 2,
+        flow_spec=deep, inner_kernel_kwargs={"step_size": 0.01})
     run("odd-d wide-flow imh d=101 n=2^18 Lc=2 H=64 (row-tile fp32 passes)", "imh", "g0", 101, 1 << 18, 5,
         flow_spec='realnvp%{"n_layers": 2, "conditioner_kwargs": {"n_layers": 2, "n_hidden": 64}}')
     run("wide-flow jump_mala d=100 n=2^20 H=256 Lc=4 (tcgen05)", "jump_mala", "g0", 100, 1 << 20, 5, K=100, flow_spec=wide)
