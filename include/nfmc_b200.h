@@ -338,6 +338,10 @@ NFMC_API int nfmc_flow_wide_pass(int32_t d, int32_t n_coupling, int32_t n_linear
  * the conditioner shapes outside the register-resident and tensor-core paths (n_linear != 2, odd d, d > 128 with H > 8) */
 NFMC_API int nfmc_flow_wide_log_prob(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden, const float* theta,
                             const float* x, float* log_q, int64_t n, void* stream);
+/* Flow.sample(n, return_log_prob=True) (jump.py:205, imh.py:221) for those shapes: base draw z from rng (Philox stream 1, or
+ * rng->normals), x = T^-1(z) [n, d], log_q (optional) = log N(z) - log|det dx/dz| [n] */
+NFMC_API int nfmc_flow_wide_sample(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden, const float* theta,
+                          const nfmc_rng* rng, int64_t chain0, float* x, float* log_q, int64_t n, void* stream);
 /* backward sweep of a pass whose OUTPUT y [n, d] and output cotangent grad_y [n, d] are given (reverse KL: inverse = 1,
  * y = x = T^-1(z), grad_y = grad U(x)): grad_theta (+)= d/dtheta [ sum_i (grad_y . y)(theta) -/+ log|det| ], i.e. the
  * gradient of sum_i [U(x_i) - log|det dx/dz|] (inverse = 1) or of sum_i [f(z_i) - log|det dz/dx|] (inverse = 0);

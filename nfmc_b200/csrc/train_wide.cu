@@ -57,7 +57,7 @@ struct WideArgs {
   const float* gy;        // SWEEP: cotangent of the pass output [n, d]
   float* y;               // PASS: output rows [n, d]
   float* ld;              // PASS: log|det| of the pass direction [n]
-  float* logp;            // PASS, x -> z only (optional): log q(x) = log N(z; 0, I) + log|det dz/dx| [n]
+  float* logp;            // PASS (optional): log q at the data end of the pass [n] -- x -> z: log N(z) + log|det dz/dx|; z -> x: log N(z) - log|det dx/dz|
   double* loss;           // NLL: += sum_i -log q(x_i)
   float* gx;              // optional (NLL / SWEEP): cotangent that reaches the pass input [n, d]
   long long n;
@@ -421,6 +421,18 @@ __global__ void __launch_bounds__(kWT, 1) flow_train_wide_kernel(const WideArgs 
       T.Active()[r] = (row0 + r < A.n) ? 1.f : 0.f;
     }
     __syncthreads();
+    if (A.mode == kWidePass && pass_inv && A.logp) {
+      // z -> x with log q(x) wanted (Flow.sample(return_log_prob=True)): log N(z; 0, I) now, while the tile still holds z;
+      // log|det dx/dz| is subtracted when the pass has finished
+      for (int it = threadIdx.x; it < R * 32; it += kWT) {
+        const int r = it >> 5, lane = it & 31;
+        float s = 0.f;
+        for (int c = lane; c < d; c += 32) { const float z = T.V()[r * P.ldv + c]; s = fmaf(z, z, s); }
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && row0 + r < A.n) A.logp[row0 + r] = -0.5f * s - 0.5f * (float)d * 1.8378770664093453f;
+      }
+      __syncthreads();
+    }
     // ---- the pass (NLL: x -> z;  PASS: either direction) ---------------------------------------------------------------
     if (A.mode != kWideSweep) {
       if (!pass_inv) {
@@ -457,7 +469,10 @@ __global__ void __launch_bounds__(kWT, 1) flow_train_wide_kernel(const WideArgs 
       if (A.ld)
         for (int r = threadIdx.x; r < R; r += kWT)
           if (row0 + r < A.n) A.ld[row0 + r] = T.Ld()[r];
-      if (A.logp)
+      if (A.logp && pass_inv)
+        for (int r = threadIdx.x; r < R; r += kWT)
+          if (row0 + r < A.n) A.logp[row0 + r] -= T.Ld()[r];
+      if (A.logp && !pass_inv)
         for (int it = threadIdx.x; it < R * 32; it += kWT) {
           const int r = it >> 5, lane = it & 31;
           float s = 0.f;
@@ -617,6 +632,22 @@ extern "C" int nfmc_flow_wide_log_prob(int32_t d, int32_t n_coupling, int32_t n_
   WideArgs A{};
   A.D = wide_dims(d, n_coupling, n_linear, hidden);
   A.theta = theta; A.x = x; A.logp = log_q; A.n = n; A.mode = kWidePass; A.inv = 0;
+  return wide_launch(A, (cudaStream_t)stream);
+}
+
+extern "C" int nfmc_flow_wide_sample(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden, const float* theta,
+                                     const nfmc_rng* rng, int64_t chain0, float* x, float* log_q, int64_t n, void* stream) {
+  if (int e = wide_check(d, n_coupling, n_linear, hidden)) return e;
+  if (!theta || !rng || !x || n < 1) return set_error("flow_wide_sample: bad arguments");
+  const float* z = rng->normals;
+  if (!z) {                    // base draw: Philox stream 1, the numbers nfmc_flow_sample and the jump kernels draw
+    nfmc_rng r2{rng->seed, rng->step0, nullptr, nullptr};
+    if (int e = nfmc_rng_fill(&r2, 1, chain0, d, n, 1, x, nullptr, stream)) return e;
+    z = x;                     // in place: a CTA reads its rows into shared memory before it writes them
+  }
+  WideArgs A{};
+  A.D = wide_dims(d, n_coupling, n_linear, hidden);
+  A.theta = theta; A.x = z; A.y = x; A.logp = log_q; A.n = n; A.mode = kWidePass; A.inv = 1;
   return wide_launch(A, (cudaStream_t)stream);
 }
 

@@ -323,9 +323,14 @@ class Flow(nn.Module):
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (), dtype=torch.int64))
         rng = N.rng_desc(seed, 0, zd, None)
-        desc, keep = bij.descriptor(dev)
         with torch.cuda.device(dev):
-            N.check(N.lib().nfmc_flow_sample(C.byref(desc), C.byref(rng), 0, N.ptr(x), N.ptr(lq), n, N.stream_ptr(dev)))
+            if bij.uses_row_tile_pass():
+                desc, keep = bij.theta_descriptor(dev)
+                N.check(N.lib().nfmc_flow_wide_sample(desc.d, desc.n_coupling, desc.n_linear, desc.hidden, N.ptr(keep), C.byref(rng), 0,
+                                                      N.ptr(x), N.ptr(lq), n, N.stream_ptr(dev)))
+            else:
+                desc, keep = bij.descriptor(dev)
+                N.check(N.lib().nfmc_flow_sample(C.byref(desc), C.byref(rng), 0, N.ptr(x), N.ptr(lq), n, N.stream_ptr(dev)))
         x = x.reshape(*sample_shape, *bij.event_shape)
         if return_log_prob:
             return x, lq.reshape(tuple(sample_shape))

@@ -168,3 +168,35 @@ def test_neutra_deep_flow_against_oracle(kind):
                                atol=5e-5 * max(1.0, float(run.samples.abs().max())))
     assert abs(out.statistics.n_accepted_trajectories - run.n_accepted) <= int((~clear).sum()) * T
     assert out.statistics.n_target_calls == run.n_target_calls
+
+
+@pytest.mark.parametrize("d,n_layers,ck", DEEP[:3])
+def test_flow_sample_row_tile(monkeypatch, d, n_layers, ck):
+    """Flow.sample(return_log_prob=True) (jump.py:205, imh.py:221): injected base draw against the oracle; the Philox draw is the
+    one the per-chain kernel makes (same seed -> same x), and log q is consistent with Flow.log_prob."""
+    oflow, flow = _pair(d, n_layers, ck)
+    n = 515
+    z = torch.randn(n, d, generator=torch.Generator().manual_seed(d))
+    with torch.no_grad():
+        x_ref, ld_ref = oflow.bijection.inverse(z)
+        lq_ref = oflow.log_prob(x_ref)
+    x, lq = flow.sample((n,), return_log_prob=True, z=z.cuda())
+    np.testing.assert_allclose(x.cpu().numpy(), x_ref.numpy(), rtol=1e-4, atol=2e-5 * max(1.0, float(x_ref.abs().max())))
+    np.testing.assert_allclose(lq.cpu().numpy(), lq_ref.numpy(), rtol=1e-4, atol=1e-4 * max(1.0, float(lq_ref.abs().max())))
+    xs, lqs = flow.sample((n,), return_log_prob=True, seed=123)
+    np.testing.assert_allclose(flow.log_prob(xs).cpu().numpy(), lqs.cpu().numpy(), rtol=1e-4, atol=1e-4 * max(1.0, float(lqs.abs().max())))
+    # the Philox base draw is nfmc_rng_fill's stream 1 in LOGICAL order: feeding those numbers back reproduces the sample bitwise
+    from nfmc_b200 import _native as N
+    dev = torch.device("cuda")
+    zf = torch.empty(n, d, device=dev)
+    rng = N.rng_desc(123, 0, None, None)
+    N.check(N.lib().nfmc_rng_fill(C.byref(rng), 1, 0, d, n, 1, N.ptr(zf), None, N.stream_ptr(dev)))
+    xi, lqi = flow.sample((n,), return_log_prob=True, z=zf)
+    assert torch.equal(xi, xs) and torch.equal(lqi, lqs)
+    if n_layers % 2 == 0:
+        # ... and, for an even number of reversals, the draw of the per-chain kernel (which draws in PHYSICAL order: with an
+        # odd number of reversals its logical z is the mirror image of the same numbers -- an equally valid N(0, I) draw)
+        monkeypatch.setenv("NFMC_B200_NO_ROW_TILE", "1")
+        xg, lqg = flow.sample((n,), return_log_prob=True, seed=123)
+        np.testing.assert_allclose(xs.cpu().numpy(), xg.cpu().numpy(), rtol=1e-4, atol=2e-5 * max(1.0, float(xg.abs().max())))
+        np.testing.assert_allclose(lqs.cpu().numpy(), lqg.cpu().numpy(), rtol=1e-4, atol=1e-4 * max(1.0, float(lqg.abs().max())))
