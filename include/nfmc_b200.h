@@ -133,8 +133,9 @@ NFMC_API int nfmc_jump_step_tc(const nfmc_potential* pot, const nfmc_realnvp_tc*
 
 /* the same step (jump.py:203-243, imh.py:214-249) for conditioner shapes outside the register-resident and tensor-core
  * paths: flow->blob = the module-order parameter vector theta of nfmc_flow_wide_param_count() floats (see the wide
- * training block below), both passes by the row-tile fp32 kernel; workspace as for nfmc_jump_step_tc */
-NFMC_API int nfmc_jump_step_wide(const nfmc_potential* pot, const nfmc_realnvp* flow, float* x, float* logq_cache,
+ * training block below; theta_transposed: its linear weights are stored [in][out]), both passes by the row-tile fp32 kernel;
+ * workspace as for nfmc_jump_step_tc */
+NFMC_API int nfmc_jump_step_wide(const nfmc_potential* pot, const nfmc_realnvp* flow, int32_t theta_transposed, float* x, float* logq_cache,
                                  int32_t recompute_logq, int64_t n, int32_t adjusted, const nfmc_rng* rng, int64_t chain0,
                                  const nfmc_stats* stats, const nfmc_sink* sink, void* workspace, int64_t workspace_bytes,
                                  void* stream);
@@ -331,17 +332,19 @@ NFMC_API int64_t nfmc_flow_wide_param_count(int32_t d, int32_t n_coupling, int32
 NFMC_API int nfmc_flow_wide_nll_grad(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden, const float* theta,
                             const float* x, const int64_t* rows, int64_t n, float* grad_theta, double* loss,
                             float* grad_x, int32_t accumulate, void* stream);
-/* one fp32 pass straight from theta: inverse = 0: x -> z, log|det dz/dx|; 1: z -> x, log|det dx/dz| (log_det may be NULL) */
+/* one fp32 pass straight from theta: inverse bit 0 = 0: x -> z, log|det dz/dx|; 1: z -> x, log|det dx/dz| (log_det may be NULL);
+ * inverse bit 1 (value 2): every linear's weight is stored TRANSPOSED in theta ([in][out], same offsets) -- the layout the
+ * sampling path packs (nfmc_b200.flow.RealNVP.theta_descriptor), read coalesced by the forward GEMMs */
 NFMC_API int nfmc_flow_wide_pass(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden, const float* theta,
                         int32_t inverse, const float* in, float* out, float* log_det, int64_t n, void* stream);
 /* log q(x) = log N(T(x); 0, I) + log|det dT/dx| by the same fp32 pass (Flow.log_prob: nfmc/jump.py:218, nfmc/imh.py:214) for
  * the conditioner shapes outside the register-resident and tensor-core paths (n_linear != 2, odd d, d > 128 with H > 8) */
 NFMC_API int nfmc_flow_wide_log_prob(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden, const float* theta,
-                            const float* x, float* log_q, int64_t n, void* stream);
+                            int32_t transposed, const float* x, float* log_q, int64_t n, void* stream);
 /* Flow.sample(n, return_log_prob=True) (jump.py:205, imh.py:221) for those shapes: base draw z from rng (Philox stream 1, or
  * rng->normals), x = T^-1(z) [n, d], log_q (optional) = log N(z) - log|det dx/dz| [n] */
 NFMC_API int nfmc_flow_wide_sample(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden, const float* theta,
-                          const nfmc_rng* rng, int64_t chain0, float* x, float* log_q, int64_t n, void* stream);
+                          int32_t transposed, const nfmc_rng* rng, int64_t chain0, float* x, float* log_q, int64_t n, void* stream);
 /* backward sweep of a pass whose OUTPUT y [n, d] and output cotangent grad_y [n, d] are given (reverse KL: inverse = 1,
  * y = x = T^-1(z), grad_y = grad U(x)): grad_theta (+)= d/dtheta [ sum_i (grad_y . y)(theta) -/+ log|det| ], i.e. the
  * gradient of sum_i [U(x_i) - log|det dx/dz|] (inverse = 1) or of sum_i [f(z_i) - log|det dz/dx|] (inverse = 0);

@@ -67,7 +67,7 @@ SIGNATURES = {
     "nfmc_jump_tc_workspace_bytes": (_i64, [_i32, _i64]),
     "nfmc_jump_step_tc": (C.c_int, [P(PotentialDesc), P(RealNVPTcDesc), _vp, _vp, _i32, _i64, _i32, P(RngDesc), _i64,
                                     P(StatsDesc), P(SinkDesc), _vp, _i64, _vp]),
-    "nfmc_jump_step_wide": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _vp, _vp, _i32, _i64, _i32, P(RngDesc), _i64,
+    "nfmc_jump_step_wide": (C.c_int, [P(PotentialDesc), P(RealNVPDesc), _i32, _vp, _vp, _i32, _i64, _i32, P(RngDesc), _i64,
                                       P(StatsDesc), P(SinkDesc), _vp, _i64, _vp]),
     "nfmc_flow_sample": (C.c_int, [P(RealNVPDesc), P(RngDesc), _i64, _vp, _vp, _i64, _vp]),
     "nfmc_mala_steps": (C.c_int, [P(PotentialDesc), _vp, _i64, _i32, _f32, _vp, _i32, P(RngDesc), _i64,
@@ -107,8 +107,8 @@ SIGNATURES = {
     "nfmc_flow_wide_param_count": (_i64, [_i32, _i32, _i32, _i32]),
     "nfmc_flow_wide_nll_grad": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
     "nfmc_flow_wide_pass": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
-    "nfmc_flow_wide_log_prob": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
-    "nfmc_flow_wide_sample": (C.c_int, [_i32, _i32, _i32, _i32, _vp, P(RngDesc), _i64, _vp, _vp, _i64, _vp]),
+    "nfmc_flow_wide_log_prob": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64, _vp]),
+    "nfmc_flow_wide_sample": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _i32, P(RngDesc), _i64, _vp, _vp, _i64, _vp]),
     "nfmc_flow_wide_sweep": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _i32, _vp]),
     "nfmc_adamw_step_scaled": (C.c_int, [_vp, _vp, _f32, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp]),
     "nfmc_flow_wide_fit_epoch": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64,

@@ -368,7 +368,7 @@ extern "C" int nfmc_jump_step_tc(const nfmc_potential* pot, const nfmc_realnvp_t
 // The same step for conditioner shapes outside the register-resident and the tensor-core paths (n_linear != 2, odd d, d > 128
 // with hidden > 8): both flow passes by the row-tile fp32 kernel of train_wide.cu, straight from the module-order parameter
 // vector (`flow->blob` = theta, `flow->blob_floats` = its length) -- 3-6x the generic per-chain conditioner of flow.cuh.
-extern "C" int nfmc_jump_step_wide(const nfmc_potential* pot, const nfmc_realnvp* flow, float* x, float* logq_cache,
+extern "C" int nfmc_jump_step_wide(const nfmc_potential* pot, const nfmc_realnvp* flow, int32_t theta_transposed, float* x, float* logq_cache,
                                    int32_t recompute_logq, int64_t n, int32_t adjusted, const nfmc_rng* rng, int64_t chain0,
                                    const nfmc_stats* stats, const nfmc_sink* sink, void* workspace, int64_t workspace_bytes,
                                    void* stream) {
@@ -382,6 +382,8 @@ extern "C" int nfmc_jump_step_wide(const nfmc_potential* pot, const nfmc_realnvp
   const float* theta = flow->blob;
   return composed_jump("jump_step_wide", pot, x, logq_cache, recompute_logq, n, adjusted, rng, chain0, stats, sink, workspace,
                        workspace_bytes, stream,
-                       [&](const float* in, float* lq) { return nfmc_flow_wide_log_prob(d, Lc, M, H, theta, in, lq, n, stream); },
-                       [&](const float* zz, float* out, float* ld) { return nfmc_flow_wide_pass(d, Lc, M, H, theta, 1, zz, out, ld, n, stream); });
+                       [&](const float* in, float* lq) { return nfmc_flow_wide_log_prob(d, Lc, M, H, theta, theta_transposed, in, lq, n, stream); },
+                       [&](const float* zz, float* out, float* ld) {
+                         return nfmc_flow_wide_pass(d, Lc, M, H, theta, 1 | (theta_transposed ? 2 : 0), zz, out, ld, n, stream);
+                       });
 }

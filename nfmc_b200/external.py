@@ -202,7 +202,7 @@ class LatentTarget:
         ld = torch.empty(n, device=dev, dtype=torch.float32)
         if bij.uses_row_tile_pass():            # deep / odd-sized conditioner: row-tile fp32 pass (csrc/train_wide.cu)
             fd, theta = bij.theta_descriptor(dev)
-            N.check(N.lib().nfmc_flow_wide_pass(fd.d, fd.n_coupling, fd.n_linear, fd.hidden, N.ptr(theta), 1, N.ptr(z), N.ptr(x),
+            N.check(N.lib().nfmc_flow_wide_pass(fd.d, fd.n_coupling, fd.n_linear, fd.hidden, N.ptr(theta), 3, N.ptr(z), N.ptr(x),
                                                 N.ptr(ld), n, N.stream_ptr(dev)))
             return x, ld
         fd, keep = bij.descriptor(dev)
@@ -227,7 +227,7 @@ class LatentTarget:
         if bij.uses_row_tile_pass():
             # backward sweep of the z -> x pass seeded with grad U(x): grad_in = d/dz [U(x(z)) - log|det dx/dz|] (train_wide.cu,
             # mode SWEEP with the parameter-gradient emitters off)
-            fd, theta = bij.theta_descriptor(z.device)
+            fd, theta = bij.theta_descriptor(z.device, transposed=False)
             N.check(N.lib().nfmc_flow_wide_sweep(fd.d, fd.n_coupling, fd.n_linear, fd.hidden, N.ptr(theta), 1, N.ptr(x), N.ptr(gx),
                                                  z.shape[0], None, N.ptr(gz), 0, N.stream_ptr(z.device)))
             return -((-u) + ld), gz

@@ -177,14 +177,18 @@ class RealNVP(_Layer):
         same = all((c.n_linear, c.n_hidden) == (M, H) for c in self.couplings())
         return same and N.lib().nfmc_flow_wide_param_count(self.n_dim, self.n_coupling, M, H) > 0
 
-    def theta_descriptor(self, device: torch.device):
-        """Descriptor of the row-tile path: the module-order parameter vector (cached per device and parameter version)."""
-        key = "theta:" + str(device)
+    def theta_descriptor(self, device: torch.device, transposed: bool = True):
+        """Descriptor of the row-tile path: the module-order parameter vector (cached per device and parameter version).
+        ``transposed`` (what the pass / log_prob / sample / jump entry points take with their ``transposed`` flag set): every
+        linear's weight stored ``[in][out]`` at the same offset, so that the forward GEMMs, whose lanes run over output units,
+        read it coalesced; ``transposed=False`` is the modules' own ``[out][in]`` order (the backward sweep and the trainer)."""
+        key = ("thetaT:" if transposed else "theta:") + str(device)
         ver = self._version_key()
         hit = self._packed.get(key)
         if hit is None or hit[0] != ver:
-            theta = torch.cat([p.detach().reshape(-1) for p in self.parameters()]).to(device, torch.float32).contiguous()
-            self._packed[key] = (ver, theta)
+            lin = {id(m.weight) for c in self.couplings() for m in c.linears()} if transposed else set()
+            parts = [(p.detach().t() if id(p) in lin else p.detach()).reshape(-1) for p in self.parameters()]
+            self._packed[key] = (ver, torch.cat(parts).to(device, torch.float32).contiguous())
         theta = self._packed[key][1]
         M, H = self.conditioner_shape()
         return N.RealNVPDesc(self.n_dim, self.n_coupling, M, H, theta.data_ptr(), theta.numel()), theta
@@ -247,7 +251,7 @@ class RealNVP(_Layer):
             elif self.uses_row_tile_pass():
                 desc, keep = self.theta_descriptor(dev)
                 N.check(N.lib().nfmc_flow_wide_pass(desc.d, desc.n_coupling, desc.n_linear, desc.hidden, N.ptr(keep),
-                                                    0 if fn_name == "nfmc_realnvp_forward" else 1, N.ptr(xd), N.ptr(y), N.ptr(ld), n,
+                                                    2 if fn_name == "nfmc_realnvp_forward" else 3, N.ptr(xd), N.ptr(y), N.ptr(ld), n,
                                                     N.stream_ptr(dev)))
             else:
                 desc, keep = self.descriptor(dev)
@@ -300,7 +304,7 @@ class Flow(nn.Module):
                 N.check(N.lib().nfmc_flow_tc_pass(C.byref(desc), 2, N.ptr(xd), None, N.ptr(out), n, N.stream_ptr(dev)))
             elif bij.uses_row_tile_pass():
                 desc, keep = bij.theta_descriptor(dev)
-                N.check(N.lib().nfmc_flow_wide_log_prob(desc.d, desc.n_coupling, desc.n_linear, desc.hidden, N.ptr(keep),
+                N.check(N.lib().nfmc_flow_wide_log_prob(desc.d, desc.n_coupling, desc.n_linear, desc.hidden, N.ptr(keep), 1,
                                                         N.ptr(xd), N.ptr(out), n, N.stream_ptr(dev)))
             else:
                 desc, keep = bij.descriptor(dev)
@@ -326,7 +330,7 @@ class Flow(nn.Module):
         with torch.cuda.device(dev):
             if bij.uses_row_tile_pass():
                 desc, keep = bij.theta_descriptor(dev)
-                N.check(N.lib().nfmc_flow_wide_sample(desc.d, desc.n_coupling, desc.n_linear, desc.hidden, N.ptr(keep), C.byref(rng), 0,
+                N.check(N.lib().nfmc_flow_wide_sample(desc.d, desc.n_coupling, desc.n_linear, desc.hidden, N.ptr(keep), 1, C.byref(rng), 0,
                                                       N.ptr(x), N.ptr(lq), n, N.stream_ptr(dev)))
             else:
                 desc, keep = bij.descriptor(dev)

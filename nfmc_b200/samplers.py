@@ -507,7 +507,7 @@ class JumpNFMC(Sampler):
             fd, keep2 = flow.bijection.theta_descriptor(ses.device)
             nb = N.lib().nfmc_jump_tc_workspace_bytes(ses.d, ses.n)
             ws = ses.workspace(nb)
-            N.check(N.lib().nfmc_jump_step_wide(C.byref(pot), C.byref(fd), N.ptr(ses.x), None, 1, ses.n,
+            N.check(N.lib().nfmc_jump_step_wide(C.byref(pot), C.byref(fd), 1, N.ptr(ses.x), None, 1, ses.n,
                                                 int(bool(self.params.adjusted_jumps)), C.byref(rng), ses.chain0,
                                                 C.byref(st), sk, N.ptr(ws), nb, ses.stream))
         else:
@@ -711,7 +711,7 @@ class AbstractIMH(Sampler):
             if tc:
                 N.check(N.lib().nfmc_flow_tc_pass(C.byref(fd), 2, N.ptr(ses.x), None, N.ptr(logq), ses.n, ses.stream))
             elif wide:
-                N.check(N.lib().nfmc_flow_wide_log_prob(fd.d, fd.n_coupling, fd.n_linear, fd.hidden, N.ptr(keep2), N.ptr(ses.x),
+                N.check(N.lib().nfmc_flow_wide_log_prob(fd.d, fd.n_coupling, fd.n_linear, fd.hidden, N.ptr(keep2), 1, N.ptr(ses.x),
                                                         N.ptr(logq), ses.n, ses.stream))
             else:
                 N.check(N.lib().nfmc_flow_log_prob(C.byref(fd), N.ptr(ses.x), N.ptr(logq), ses.n, ses.stream))
@@ -738,10 +738,12 @@ class AbstractIMH(Sampler):
             if tc or wide:
                 nb = N.lib().nfmc_jump_tc_workspace_bytes(ses.d, ses.n)
                 ws = ses.workspace(nb)
-                step = N.lib().nfmc_jump_step_tc if tc else N.lib().nfmc_jump_step_wide
-                N.check(step(C.byref(pot), C.byref(fd), N.ptr(ses.x), N.ptr(logq),
-                             int(self.recompute_logq), ses.n, 1, C.byref(rng), ses.chain0, C.byref(st),
-                             None if sink is None else C.byref(sink), N.ptr(ws), nb, ses.stream))
+                tail = (N.ptr(ses.x), N.ptr(logq), int(self.recompute_logq), ses.n, 1, C.byref(rng), ses.chain0, C.byref(st),
+                        None if sink is None else C.byref(sink), N.ptr(ws), nb, ses.stream)
+                if tc:
+                    N.check(N.lib().nfmc_jump_step_tc(C.byref(pot), C.byref(fd), *tail))
+                else:
+                    N.check(N.lib().nfmc_jump_step_wide(C.byref(pot), C.byref(fd), 1, *tail))      # 1: theta packed transposed
             else:
                 N.check(N.lib().nfmc_imh_steps(C.byref(pot), C.byref(fd), N.ptr(ses.x), N.ptr(logq), ses.n, k,
                                                int(self.recompute_logq), C.byref(rng), ses.chain0, C.byref(st),
