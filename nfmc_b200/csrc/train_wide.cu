@@ -390,8 +390,8 @@ struct WideTile {
   }
 };
 
-template <int R>
-__global__ void __launch_bounds__(kWT, 1) flow_train_wide_kernel(const WideArgs A) {
+template <int R, int MINB>
+__global__ void __launch_bounds__(kWT, MINB) flow_train_wide_kernel(const WideArgs A) {
   extern __shared__ __align__(16) float wsm[];
   const WideDims& D = A.D;
   const bool need_grad = A.mode != kWidePass;
@@ -550,13 +550,24 @@ int wide_check(int d, int Lc, int M, int H) {
   return 0;
 }
 
+// MINB = resident CTAs per SM the kernel is compiled for: 2 (128 registers, no spills) for the passes of the sampling path --
+// full batches, where a second CTA hides the weight loads' latency (ncu with one CTA: 2 warps per scheduler, long_scoreboard
+// 1.7 per issue; deep-flow pass 7.2 -> 5.0 ms) --, 1 (182 registers) for the training modes, whose minibatches are fewer
+// tiles than SMs and run 7-12 % slower under the register cap.
+template <int R, int MINB>
+int wide_launch_rm(const WideArgs& A, size_t smem, cudaStream_t s) {
+  if (int e = check_cuda(cudaFuncSetAttribute(flow_train_wide_kernel<R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "wide smem attribute")) return e;
+  const long long tiles = (A.n + R - 1) / R;
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flow_train_wide_kernel<R, MINB>, kWT, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  if (per_sm > MINB) per_sm = MINB;
+  const int grid = (int)std::min<long long>(tiles, (long long)per_sm * sm_count());
+  flow_train_wide_kernel<R, MINB><<<grid, kWT, smem, s>>>(A);
+  return check_cuda(cudaGetLastError(), "flow_train_wide_kernel launch");
+}
 template <int R>
 int wide_launch_r(const WideArgs& A, size_t smem, cudaStream_t s) {
-  if (int e = check_cuda(cudaFuncSetAttribute(flow_train_wide_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "wide smem attribute")) return e;
-  const long long tiles = (A.n + R - 1) / R;
-  const int grid = (int)std::min<long long>(tiles, sm_count());
-  flow_train_wide_kernel<R><<<grid, kWT, smem, s>>>(A);
-  return check_cuda(cudaGetLastError(), "flow_train_wide_kernel launch");
+  return A.mode == kWidePass ? wide_launch_rm<R, 2>(A, smem, s) : wide_launch_rm<R, 1>(A, smem, s);
 }
 
 int wide_launch(WideArgs& A, cudaStream_t s) {
