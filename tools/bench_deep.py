@@ -27,9 +27,16 @@ for name, d, spec, n in [("deep M=5 H=100 Lc=10 d=100", 100, 'realnvp%{"n_layers
     x = torch.randn(n, d, device="cuda")
     assert not f.bijection.uses_tensor_cores()
     tr = WideTrainer(f, torch.device("cuda"), 1e-3)
+    assert f.bijection.uses_row_tile_pass()
+    zs, ls = f.bijection.forward(x)                      # sampling path: row-tile kernel, weights packed transposed, 2 CTAs/SM
+    zw, lw = tr.run_pass(x, False)                       # trainer's pass: same kernel on the module-order vector
+    rec = {"shape": name, "rows": n, "row_tile_transposed_forward_ms": t(lambda: f.bijection.forward(x)),
+           "row_tile_transposed_inverse_ms": t(lambda: f.bijection.inverse(x)),
+           "row_tile_module_order_forward_ms": t(lambda: tr.run_pass(x, False)), "row_tile_module_order_inverse_ms": t(lambda: tr.run_pass(x, True))}
+    os.environ["NFMC_B200_NO_ROW_TILE"] = "1"            # per-chain generic conditioner of flow.cuh
     zg, lg = f.bijection.forward(x)
-    zw, lw = tr.run_pass(x, False)
-    err = float((zg - zw).abs().max()), float((lg - lw).abs().max())
-    print(json.dumps({"shape": name, "rows": n, "generic_forward_ms": t(lambda: f.bijection.forward(x)), "wide_pass_forward_ms": t(lambda: tr.run_pass(x, False)),
-                      "generic_inverse_ms": t(lambda: f.bijection.inverse(x)), "wide_pass_inverse_ms": t(lambda: tr.run_pass(x, True)),
-                      "max_abs_diff_z": err[0], "max_abs_diff_logdet": err[1]}), flush=True)
+    rec.update(generic_forward_ms=t(lambda: f.bijection.forward(x)), generic_inverse_ms=t(lambda: f.bijection.inverse(x)),
+               max_abs_diff_z_vs_generic=float((zg - zs).abs().max()), max_abs_diff_logdet_vs_generic=float((lg - ls).abs().max()),
+               max_abs_diff_z_vs_module_order=float((zw - zs).abs().max()))
+    del os.environ["NFMC_B200_NO_ROW_TILE"]
+    print(json.dumps(rec), flush=True)
