@@ -189,9 +189,12 @@ class LatentTarget:
     run records are the latent states."""
     external = True
 
-    def __init__(self, target, flow):
+    def __init__(self, target, flow, row_tile: Optional[bool] = None):
         self.target = target
         self.flow = flow
+        # flow passes / backward sweep by the row-tile fp32 kernels of csrc/train_wide.cu (deep or odd-sized conditioners; also a
+        # tensor-core flow whose shape the tensor-core NeuTra kernels refuse) instead of the per-chain kernels of flow.cuh
+        self.row_tile = flow.bijection.uses_row_tile_pass() if row_tile is None else bool(row_tile)
 
     def to_data(self, z: torch.Tensor):
         """(x, log|det dT^-1/dz|) for latent rows z [n, d]."""
@@ -200,7 +203,7 @@ class LatentTarget:
         n = z.shape[0]
         x = torch.empty_like(z)
         ld = torch.empty(n, device=dev, dtype=torch.float32)
-        if bij.uses_row_tile_pass():            # deep / odd-sized conditioner: row-tile fp32 pass (csrc/train_wide.cu)
+        if self.row_tile:            # deep / odd-sized conditioner: row-tile fp32 pass (csrc/train_wide.cu)
             fd, theta = bij.theta_descriptor(dev)
             N.check(N.lib().nfmc_flow_wide_pass(fd.d, fd.n_coupling, fd.n_linear, fd.hidden, N.ptr(theta), 3, N.ptr(z), N.ptr(x),
                                                 N.ptr(ld), n, N.stream_ptr(dev)))
@@ -224,7 +227,7 @@ class LatentTarget:
         gz = torch.empty_like(z)
         bij = self.flow.bijection
         gx = gx.reshape(z.shape).contiguous()
-        if bij.uses_row_tile_pass():
+        if self.row_tile:
             # backward sweep of the z -> x pass seeded with grad U(x): grad_in = d/dz [U(x(z)) - log|det dx/dz|] (train_wide.cu,
             # mode SWEEP with the parameter-gradient emitters off)
             fd, theta = bij.theta_descriptor(z.device, transposed=False)

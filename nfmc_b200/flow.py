@@ -169,8 +169,14 @@ class RealNVP(_Layer):
         (``nfmc_flow_wide_pass`` / ``nfmc_flow_wide_log_prob`` / ``nfmc_jump_step_wide``) for forward / inverse / log_prob and
         the NF jump / IMH step: register-blocked weight reuse over a tile of rows instead of one weight load per chain and
         multiply (3-6x the per-chain generic path, ``tools/bench_deep.py``)."""
+        return self.row_tile_supported() and not self.uses_tensor_cores()
+
+    def row_tile_supported(self) -> bool:
+        """Shape test of the row-tile fp32 kernels: any conditioner outside the register-resident path whose couplings share
+        one shape.  (NeuTra also takes them for a tensor-core flow whose shape the tensor-core NeuTra kernels refuse, e.g.
+        d % 4 != 0: value and gradient of the latent potential then both come from the fp32 pass.)"""
         M, H = self.conditioner_shape()
-        if (M == 2 and H <= SMALL_H) or self.uses_tensor_cores() or not self.couplings():
+        if (M == 2 and H <= SMALL_H) or not self.couplings():
             return False
         if os.environ.get("NFMC_B200_NO_ROW_TILE") == "1":      # tests / A-B runs: keep the per-chain generic conditioner
             return False

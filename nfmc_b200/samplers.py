@@ -891,8 +891,9 @@ class NeuTraHMC(Sampler):
         bij = self.kernel.flow.bijection
         # callable target, or a conditioner shape only the row-tile fp32 kernels cover (deep, odd d, ...): the latent step is
         # composed from the inverse pass, U / grad U at x = T^-1 z, the backward sweep and the nfmc_ext_* kernels
-        ext = self.target.external or (bij.uses_row_tile_pass() and not bij.uses_tensor_cores_for_neutra(ses.n))
-        latent = external.LatentTarget(self.target, self.kernel.flow) if ext else None
+        row_tile = bij.row_tile_supported() and not bij.uses_tensor_cores_for_neutra(ses.n)
+        ext = self.target.external or row_tile
+        latent = external.LatentTarget(self.target, self.kernel.flow, row_tile=row_tile if row_tile else None) if ext else None
         pot, keep = (None, None) if ext else self.target.descriptor(dev)
         fd, keep2 = self.kernel.flow.bijection.descriptor(dev)
         imd = _imd_device(self.inner_kernel, dev)

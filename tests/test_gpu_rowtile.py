@@ -200,3 +200,29 @@ def test_flow_sample_row_tile(monkeypatch, d, n_layers, ck):
         xg, lqg = flow.sample((n,), return_log_prob=True, seed=123)
         np.testing.assert_allclose(xs.cpu().numpy(), xg.cpu().numpy(), rtol=1e-4, atol=2e-5 * max(1.0, float(xg.abs().max())))
         np.testing.assert_allclose(lqs.cpu().numpy(), lqg.cpu().numpy(), rtol=1e-4, atol=1e-4 * max(1.0, float(lqg.abs().max())))
+
+
+def test_neutra_hmc_tensor_core_flow_outside_the_tc_neutra_kernels():
+    """d = 102, H = 64: the flow passes are tensor-core eligible, the tensor-core NeuTra kernels are not (d % 4 != 0).  NeuTra
+    then runs the row-tile fp32 kernels (not the per-chain generic conditioner): fp32 agreement with the oracle."""
+    from gpu_util import product_flow_from_oracle, product_target
+    from nfmc_b200.records import HMCKernel, HMCParameters, NeuTraKernel, NeuTraParameters
+    from nfmc_b200.samplers import NeuTraHMC
+    d, n, T, L, tau = 102, 200, 2, 4, 0.03
+    oflow = make_flow((d,), n_layers=2, conditioner_kwargs=dict(n_layers=2, n_hidden=64), perturb=0.03, seed=8)
+    flow = product_flow_from_oracle(oflow, conditioner_dtype="auto")
+    bij = flow.bijection
+    assert bij.uses_tensor_cores() and not bij.uses_tensor_cores_for_neutra(n) and bij.row_tile_supported() and not bij.uses_row_tile_pass()
+    torch.manual_seed(4)
+    z0 = 0.5 * torch.randn(n, d)
+    normals, uniforms = torch.randn(T, n, d), torch.rand(T, n)
+    run = R.run_neutra_hmc(z0, make_potential_ref("g0", (d,)), oflow, T, R.TapeDraws(list(normals), list(uniforms)), tau, torch.ones(d),
+                           n_leapfrog=L, trace=True)
+    s = NeuTraHMC((d,), product_target("g0", d), HMCKernel(event_size=d, step_size=tau, n_leapfrog_steps=L), HMCParameters(),
+                  NeuTraKernel((d,), flow=flow), NeuTraParameters(n_iterations=T))
+    out = s.sample(z0, show_progress=False, normals=normals, uniforms=uniforms)
+    lr = torch.stack(run.trace["log_ratio"])
+    clear = (lr - torch.log(uniforms)).abs().min(dim=0).values > 1e-3 * (1.0 + lr.abs().max(dim=0).values)
+    assert clear.float().mean() > 0.9
+    np.testing.assert_allclose(out.samples[:, clear].numpy(), run.samples[:, clear].numpy(), rtol=1e-4,
+                               atol=5e-5 * max(1.0, float(run.samples.abs().max())))
