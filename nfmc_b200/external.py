@@ -146,8 +146,14 @@ def flow_proposal(flow, ses, z: Optional[torch.Tensor], uniforms: Optional[torch
         un = None if uniforms is None else uniforms.reshape(ses.n)
     xp = torch.empty(ses.n, ses.d, device=ses.device, dtype=torch.float32)
     lqp = torch.empty(ses.n, device=ses.device, dtype=torch.float32)
-    fd, keep = flow.bijection.descriptor(ses.device)
     rng = N.rng_desc(ses.seed, ses.flow_step, zz, None)
+    bij = flow.bijection
+    if bij.row_tile_supported():            # wide / deep conditioner: row-tile fp32 kernel (csrc/train_wide.cu)
+        fd, keep = bij.theta_descriptor(ses.device)
+        N.check(N.lib().nfmc_flow_wide_sample(fd.d, fd.n_coupling, fd.n_linear, fd.hidden, N.ptr(keep), 1, C.byref(rng), ses.chain0,
+                                              N.ptr(xp), N.ptr(lqp), ses.n, ses.stream))
+        return xp, lqp, un
+    fd, keep = bij.descriptor(ses.device)
     N.check(N.lib().nfmc_flow_sample(C.byref(fd), C.byref(rng), ses.chain0, N.ptr(xp), N.ptr(lqp), ses.n, ses.stream))
     return xp, lqp, un
 

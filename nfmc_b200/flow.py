@@ -334,8 +334,8 @@ class Flow(nn.Module):
             seed = int(torch.randint(0, 2 ** 62, (), dtype=torch.int64))
         rng = N.rng_desc(seed, 0, zd, None)
         with torch.cuda.device(dev):
-            if bij.uses_row_tile_pass():
-                desc, keep = bij.theta_descriptor(dev)
+            if bij.row_tile_supported():       # also tensor-core flows: there is no tcgen05 sampling entry, and the row-tile fp32
+                desc, keep = bij.theta_descriptor(dev)      # kernel is several times the per-chain generic conditioner
                 N.check(N.lib().nfmc_flow_wide_sample(desc.d, desc.n_coupling, desc.n_linear, desc.hidden, N.ptr(keep), 1, C.byref(rng), 0,
                                                       N.ptr(x), N.ptr(lq), n, N.stream_ptr(dev)))
             else:

@@ -226,3 +226,23 @@ def test_neutra_hmc_tensor_core_flow_outside_the_tc_neutra_kernels():
     assert clear.float().mean() > 0.9
     np.testing.assert_allclose(out.samples[:, clear].numpy(), run.samples[:, clear].numpy(), rtol=1e-4,
                                atol=5e-5 * max(1.0, float(run.samples.abs().max())))
+
+
+def test_callable_target_with_deep_flow_equals_builtin_target():
+    """A callable target (external path: autograd for U, flow proposal by nfmc_flow_wide_sample, log q by nfmc_flow_wide_log_prob)
+    and the same function as a built-in potential (nfmc_jump_step_wide) make the same IMH run from the same Philox seed."""
+    from gpu_util import product_target
+    from nfmc_b200.records import IMHKernel, IMHParameters
+    from nfmc_b200.samplers import FixedIMH
+    d, n, T = 37, 500, 4
+    oflow, flow = _pair(d, 3, dict(n_layers=3, n_hidden=20), perturb=0.03)
+    x0 = torch.randn(n, d, generator=torch.Generator().manual_seed(6))
+    outs = []
+    for callable_target in (False, True):
+        s = FixedIMH((d,), product_target("g0", d, callable_target=callable_target), IMHKernel((d,), flow=flow), IMHParameters(n_iterations=T))
+        s.seed = 31
+        outs.append(s.sample(x0, show_progress=False))
+    a, b = outs
+    same = (a.samples - b.samples).abs().amax(dim=(0, 2)) < 1e-4
+    assert same.float().mean() > 0.97              # a decision within rounding of its threshold may flip
+    assert abs(a.statistics.n_accepted_trajectories - b.statistics.n_accepted_trajectories) <= int((~same).sum()) * T
