@@ -264,3 +264,51 @@ def test_guards_neutra_pullback(d, Lc, ck, n):
     N.check(N.lib().nfmc_neutra_pullback(C.byref(fd), N.ptr(z), N.ptr(gx), N.ptr(gz), N.ptr(ld), n, N.stream_ptr(torch.device("cuda"))))
     G.check()
     assert bool(torch.isfinite(gz).all()) and bool(torch.isfinite(ld).all())
+
+
+@pytest.mark.parametrize("d,Lc,ck,n", [(100, 3, dict(n_layers=5, n_hidden=100), 129), (37, 3, dict(n_layers=3, n_hidden=20), 1),
+                                       (101, 2, dict(n_layers=2, n_hidden=64), 383), (200, 2, dict(n_layers=2, n_hidden=24), 4000 + 77)])
+def test_guards_row_tile_passes_and_jump(d, Lc, ck, n):
+    """The row-tile fp32 entry points of the sampling path (csrc/train_wide.cu PASS mode, csrc/flow_api.cu): forward / inverse /
+    log_prob / sample (in-place base draw), the composed jump / IMH step and the backward sweep NeuTra uses."""
+    from gpu_util import product_flow_from_oracle, product_target
+    from nfmc_b200 import _native as N
+    oflow = make_flow((d,), n_layers=Lc, conditioner_kwargs=ck, perturb=0.03, seed=2)
+    flow = product_flow_from_oracle(oflow)
+    bij = flow.bijection
+    assert bij.uses_row_tile_pass()
+    dev = torch.device("cuda")
+    fd, theta = bij.theta_descriptor(dev)
+    fdm, theta_m = bij.theta_descriptor(dev, transposed=False)
+    shp = (fd.d, fd.n_coupling, fd.n_linear, fd.hidden)
+    s = N.stream_ptr(dev)
+    G = Guarded()
+    x = G.make((n, d), fill=0.5 * torch.randn(n, d))
+    for flags in (2, 3, 0, 1):                 # transposed forward / inverse, module-order forward / inverse
+        out, ld = G.make((n, d)), G.make((n,))
+        N.check(N.lib().nfmc_flow_wide_pass(*shp, N.ptr(theta if flags & 2 else theta_m), flags, N.ptr(x), N.ptr(out), N.ptr(ld), n, s))
+    lq = G.make((n,))
+    N.check(N.lib().nfmc_flow_wide_log_prob(*shp, N.ptr(theta), 1, N.ptr(x), N.ptr(lq), n, s))
+    xs, lqs = G.make((n, d)), G.make((n,))
+    rng = N.rng_desc(5, 0, None, None)
+    N.check(N.lib().nfmc_flow_wide_sample(*shp, N.ptr(theta), 1, C.byref(rng), 11, N.ptr(xs), N.ptr(lqs), n, s))
+    gz = G.make((n, d))
+    gy = G.make((n, d), fill=torch.randn(n, d))
+    N.check(N.lib().nfmc_flow_wide_sweep(*shp, N.ptr(theta_m), 1, N.ptr(x), N.ptr(gy), n, None, N.ptr(gz), 0, s))
+    G.check()
+    assert bool(torch.isfinite(lq).all()) and bool(torch.isfinite(xs).all()) and bool(torch.isfinite(gz).all())
+    pd, k2 = product_target("g0", d).descriptor(dev)
+    mom = G.make((2 * d,), torch.float64)
+    cnt = G.make((8,), torch.int64)
+    st = N.StatsDesc(mom.data_ptr(), mom.data_ptr() + 8 * d, cnt.data_ptr())
+    sink_buf = G.make((n, d))
+    sink = N.SinkDesc(sink_buf.data_ptr(), 0, 1)
+    cache = G.make((n,), fill=lq)
+    nb = N.lib().nfmc_jump_tc_workspace_bytes(d, n)
+    ws = G.make((nb,), torch.uint8)
+    for step, use_cache in enumerate((False, True)):
+        rng = N.rng_desc(7, step, None, None)
+        N.check(N.lib().nfmc_jump_step_wide(C.byref(pd), C.byref(fd), 1, N.ptr(x), N.ptr(cache) if use_cache else None, 0, n, 1, C.byref(rng),
+                                            3, C.byref(st), C.byref(sink), N.ptr(ws), nb, s))
+    G.check()
+    assert int(cnt[1]) == 2 * n and bool(torch.isfinite(x).all())
