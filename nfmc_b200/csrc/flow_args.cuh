@@ -33,7 +33,20 @@ __device__ __forceinline__ FlowSmem flow_smem_init(unsigned char* smem, const Fl
   float* fbase = reinterpret_cast<float*>(smem + off);
   const float* blob = A.blob;
   if (SB) {
-    for (int i = threadIdx.x; i < (int)A.blob_floats; i += blockDim.x) fbase[i] = __ldg(A.blob + i);
+    // 128-bit copies, four in flight per thread: the scalar load -> store loop it replaces waited one global-memory latency per
+    // element (30 in a row for a d = 100 default flow) and was the largest single stall site of the jump kernels (ncu source
+    // page, profiles/jpa_r02_*: 8-11 % of all stall samples on its STS)
+    const int nf = (int)A.blob_floats;
+    int done = 0;
+    if ((reinterpret_cast<uintptr_t>(A.blob) & 15) == 0) {
+      const float4* src = reinterpret_cast<const float4*>(A.blob);
+      float4* dst = reinterpret_cast<float4*>(fbase);
+      const int n4 = nf >> 2;
+#pragma unroll 4
+      for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = __ldg(src + i);
+      done = n4 << 2;
+    }
+    for (int i = done + threadIdx.x; i < nf; i += blockDim.x) fbase[i] = __ldg(A.blob + i);
     blob = fbase;
     fbase += ((int)A.blob_floats + 3) & ~3;
     __syncthreads();
