@@ -624,7 +624,9 @@ int wide_launch_rm(const WideArgs& A, size_t smem, cudaStream_t s) {
 }
 template <int R>
 int wide_launch_r(const WideArgs& A, size_t smem, cudaStream_t s) {
-  return A.mode == kWidePass ? wide_launch_rm<R, 2>(A, smem, s) : wide_launch_rm<R, 1>(A, smem, s);
+  // the sampling-side sweep (NeuTra's latent gradient: cotangent to the pass input only, full batches) shares the two-CTA build
+  const bool sampling = A.mode == kWidePass || (A.mode == kWideSweep && !A.gtheta);
+  return sampling ? wide_launch_rm<R, 2>(A, smem, s) : wide_launch_rm<R, 1>(A, smem, s);
 }
 
 int wide_launch(WideArgs& A, cudaStream_t s) {
@@ -633,6 +635,8 @@ int wide_launch(WideArgs& A, cudaStream_t s) {
   const bool need_grad = A.mode != kWidePass;
   const size_t cap = 227 * 1024;
   int R = (A.n >= 32ll * sm_count()) ? 32 : (A.n >= 16ll * sm_count() / 2 ? 16 : 8);
+  // NeuTra's sweep (cotangent to the input only): 16-row tiles, so that two CTAs fit an SM next to the gradient buffers (+6 %)
+  if (A.mode == kWideSweep && !A.gtheta && R == 32) R = 16;
   if (const char* e = getenv("NFMC_WIDE_ROWS")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) R = v; }
   while (R > 8 && (size_t)wide_plan(A.D, R, need_grad).total * sizeof(float) > cap) R >>= 1;
   const size_t smem = (size_t)wide_plan(A.D, R, need_grad).total * sizeof(float);
