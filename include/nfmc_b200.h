@@ -352,6 +352,12 @@ NFMC_API int nfmc_flow_wide_sample(int32_t d, int32_t n_coupling, int32_t n_line
 NFMC_API int nfmc_flow_wide_sweep(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden, const float* theta,
                          int32_t inverse, const float* y, const float* grad_y, int64_t n, float* grad_theta,
                          float* grad_in, int32_t accumulate, void* stream);
+/* the sweep's cotangent path alone (NeuTra's latent gradient, nfmc/neutra.py:58-68 under autograd: grad_in = d/dz [U(x(z)) -
+ * log|det dx/dz|] for inverse = 1, y = x, grad_y = grad U(x)); theta_t (optional): theta with every linear's weight transposed,
+ * read by the conditioner's forward GEMMs */
+NFMC_API int nfmc_flow_wide_pullback(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden, const float* theta,
+                            const float* theta_t, int32_t inverse, const float* y, const float* grad_y, int64_t n,
+                            float* grad_in, void* stream);
 /* AdamW with the gradient multiplied by grad_scale first (1 / batch) */
 NFMC_API int nfmc_adamw_step_scaled(float* theta, const float* grad, float grad_scale, float* exp_avg, float* exp_avg_sq,
                            int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,

@@ -109,6 +109,7 @@ SIGNATURES = {
     "nfmc_flow_wide_pass": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
     "nfmc_flow_wide_log_prob": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64, _vp]),
     "nfmc_flow_wide_sample": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _i32, P(RngDesc), _i64, _vp, _vp, _i64, _vp]),
+    "nfmc_flow_wide_pullback": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp]),
     "nfmc_flow_wide_sweep": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _i32, _vp]),
     "nfmc_adamw_step_scaled": (C.c_int, [_vp, _vp, _f32, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp]),
     "nfmc_flow_wide_fit_epoch": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64,

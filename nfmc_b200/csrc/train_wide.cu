@@ -63,6 +63,8 @@ struct WideArgs {
   long long n;
   int mode;               // 0 NLL, 1 PASS, 2 SWEEP
   int inv;                // direction of the pass: 0 = x -> z, 1 = z -> x
+  const float* theta_t;   // SWEEP (optional): a copy of theta with every linear's weight transposed -- the conditioner's forward
+                          // GEMMs read it (coalesced), the dgrad GEMMs keep `theta` (whose order is the coalesced one for them)
   int wt;                 // PASS only: every linear's weight is stored TRANSPOSED in theta ([in][out] instead of the modules'
                           // [out][in]; same offsets): the forward GEMMs' lanes run over output units, so only this layout is
                           // read coalesced (module order costs 32 cache lines per weight load: 9 % of the fp32 peak)
@@ -229,8 +231,9 @@ struct WideTile {
   const WidePlan& P;
   float* sm;
   bool rev;          // logical index i lives in column d-1-i
-  bool wt;           // linear weights stored [in][out] (WideArgs::wt)
-  __device__ WideTile(const WideDims& D_, const WidePlan& P_, float* sm_) : D(D_), P(P_), sm(sm_), rev(false), wt(false) {}
+  bool wt;           // the forward GEMMs read linear weights stored [in][out] (WideArgs::wt / WideArgs::theta_t)
+  const float* fwd;  // SWEEP with WideArgs::theta_t: parameter vector the conditioner's forward GEMMs read instead of `theta`
+  __device__ WideTile(const WideDims& D_, const WidePlan& P_, float* sm_) : D(D_), P(P_), sm(sm_), rev(false), wt(false), fwd(nullptr) {}
   __device__ __forceinline__ int col(int i) const { return rev ? D.d - 1 - i : i; }
   __device__ __forceinline__ float* V() const { return sm + P.oV; }
   __device__ __forceinline__ float* G() const { return sm + P.oG; }
@@ -315,7 +318,7 @@ struct WideTile {
     long long o = off;
     for (int m = 0; m < D.M; ++m) {
       const int K = D.lin_in(m), N = D.lin_out(m);
-      const float* W = theta + o;
+      const float* W = (fwd ? fwd : theta) + o;      // fwd: the transposed copy, forward GEMMs only (biases are the same in both)
       const float* b = W + (size_t)N * K;
       if (m < D.M - 1) {
         float* out = Act(m);
@@ -458,7 +461,8 @@ __global__ void __launch_bounds__(kWT, MINB) flow_train_wide_kernel(const WideAr
   double loss = 0.0;
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     WideTile<R> T(D, P, wsm);
-    T.wt = A.mode == kWidePass && A.wt != 0;
+    T.wt = (A.mode == kWidePass && A.wt != 0) || (A.mode == kWideSweep && A.theta_t != nullptr);
+    T.fwd = A.mode == kWideSweep ? A.theta_t : nullptr;
     const long long row0 = tile * R;
     // ---- load (global rows are always in LOGICAL order; a tile that starts at the latent end of a flow with an odd number
     //      of reversals is seated reversed) ---------------------------------------------------------------------------------
@@ -742,6 +746,17 @@ extern "C" int nfmc_flow_wide_sweep(int32_t d, int32_t n_coupling, int32_t n_lin
     if (int e = check_cuda(cudaMemsetAsync(grad_theta, 0, (size_t)A.D.n_theta() * sizeof(float), s), "zero grad")) return e;
   A.theta = theta; A.gtheta = grad_theta; A.x = y; A.gy = grad_y; A.gx = grad_in; A.n = n; A.mode = kWideSweep; A.inv = inverse ? 1 : 0;
   return wide_launch(A, s);
+}
+
+extern "C" int nfmc_flow_wide_pullback(int32_t d, int32_t n_coupling, int32_t n_linear, int32_t hidden, const float* theta,
+                                       const float* theta_t, int32_t inverse, const float* y, const float* grad_y, int64_t n,
+                                       float* grad_in, void* stream) {
+  if (int e = wide_check(d, n_coupling, n_linear, hidden)) return e;
+  if (!theta || !y || !grad_y || !grad_in || n < 1) return set_error("flow_wide_pullback: bad arguments");
+  WideArgs A{};
+  A.D = wide_dims(d, n_coupling, n_linear, hidden);
+  A.theta = theta; A.theta_t = theta_t; A.x = y; A.gy = grad_y; A.gx = grad_in; A.n = n; A.mode = kWideSweep; A.inv = inverse ? 1 : 0;
+  return wide_launch(A, (cudaStream_t)stream);
 }
 
 extern "C" int nfmc_adamw_step_scaled(float* theta, const float* grad, float grad_scale, float* exp_avg, float* exp_avg_sq,

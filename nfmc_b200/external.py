@@ -237,8 +237,9 @@ class LatentTarget:
             # backward sweep of the z -> x pass seeded with grad U(x): grad_in = d/dz [U(x(z)) - log|det dx/dz|] (train_wide.cu,
             # mode SWEEP with the parameter-gradient emitters off)
             fd, theta = bij.theta_descriptor(z.device, transposed=False)
-            N.check(N.lib().nfmc_flow_wide_sweep(fd.d, fd.n_coupling, fd.n_linear, fd.hidden, N.ptr(theta), 1, N.ptr(x), N.ptr(gx),
-                                                 z.shape[0], None, N.ptr(gz), 0, N.stream_ptr(z.device)))
+            fdt, theta_t = bij.theta_descriptor(z.device, transposed=True)
+            N.check(N.lib().nfmc_flow_wide_pullback(fd.d, fd.n_coupling, fd.n_linear, fd.hidden, N.ptr(theta), N.ptr(theta_t), 1, N.ptr(x),
+                                                    N.ptr(gx), z.shape[0], N.ptr(gz), N.stream_ptr(z.device)))
             return -((-u) + ld), gz
         fd, keep = bij.descriptor(z.device)
         N.check(N.lib().nfmc_neutra_pullback(C.byref(fd), N.ptr(z), N.ptr(gx), N.ptr(gz), None,

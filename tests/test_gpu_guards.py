@@ -295,7 +295,10 @@ def test_guards_row_tile_passes_and_jump(d, Lc, ck, n):
     gz = G.make((n, d))
     gy = G.make((n, d), fill=torch.randn(n, d))
     N.check(N.lib().nfmc_flow_wide_sweep(*shp, N.ptr(theta_m), 1, N.ptr(x), N.ptr(gy), n, None, N.ptr(gz), 0, s))
+    gz2 = G.make((n, d))
+    N.check(N.lib().nfmc_flow_wide_pullback(*shp, N.ptr(theta_m), N.ptr(theta), 1, N.ptr(x), N.ptr(gy), n, N.ptr(gz2), s))
     G.check()
+    assert torch.equal(gz, gz2)                 # forward GEMMs on the transposed copy: same numbers
     assert bool(torch.isfinite(lq).all()) and bool(torch.isfinite(xs).all()) and bool(torch.isfinite(gz).all())
     pd, k2 = product_target("g0", d).descriptor(dev)
     mom = G.make((2 * d,), torch.float64)
